@@ -1,0 +1,1078 @@
+/*
+ * oracle.c -- CPU restatement of the reference hot path.  TEST INFRASTRUCTURE ONLY
+ * (see oracle.h).  "parity unpinned" at the rand-0.8 boundary (no Rust toolchain here).
+ *
+ * All `file:line` citations are into the reference tree (Renmusxd/IsingMonteCarlo,
+ * crate qmc 2.20.0).  The data-structure shape follows the reference on purpose (one
+ * node per slot holding its operator and doubly linked p / per-variable links, LIFO
+ * DFS for clusters) so that this file can also be timed as the CPU baseline.
+ */
+#include "oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ===================================================================================
+ * RNG contract: Philox4x32-10, one 64-bit word per draw
+ * =================================================================================== */
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        if (r > 0) {
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+    }
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+
+/* W[c]: 128-bit counter = c >> 1, word = (x[2(c&1)+1] << 32) | x[2(c&1)] */
+uint64_t orc_stream_word(uint64_t key, uint64_t cursor) {
+    uint64_t blk = cursor >> 1;
+    uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u};
+    uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+    uint32_t x[4];
+    orc_philox4x32_10(ctr, k, x);
+    unsigned h = (unsigned)(cursor & 1u) * 2u;
+    return ((uint64_t)x[h + 1] << 32) | x[h];
+}
+
+typedef struct {
+    uint64_t key, cursor;
+    const uint64_t *script; /* scripted words for known-answer tests (or NULL) */
+    uint64_t script_len;
+    int error;
+} Stream;
+
+static uint64_t next_u64(Stream *s) {
+    if (s->script) {
+        if (s->cursor >= s->script_len) {
+            s->error = 1;
+            s->cursor++;
+            return 0;
+        }
+        return s->script[s->cursor++];
+    }
+    return orc_stream_word(s->key, s->cursor++);
+}
+/* one stream word per call; a u32 is the word's high half (Appendix A.3) */
+static uint32_t next_u32(Stream *s) { return (uint32_t)(next_u64(s) >> 32); }
+
+uint64_t orc_bool_threshold(double p) { return (uint64_t)(p * 18446744073709551616.0); }
+
+/* rand 0.8 Bernoulli (Rng::gen_bool): p==1 -> true without a draw; else v < (p*2^64) as u64 */
+static int gen_bool(Stream *s, double p) {
+    if (!(p >= 0.0 && p < 1.0)) {
+        if (p == 1.0) return 1;
+        s->error = 2; /* the reference panics here */
+        return 0;
+    }
+    uint64_t p_int = orc_bool_threshold(p);
+    uint64_t v = next_u64(s);
+    return v < p_int;
+}
+
+/* rand 0.8 UniformInt<usize>::sample_single_inclusive (64-bit, widening multiply + zone) */
+static uint64_t gen_range_usize(Stream *s, uint64_t range) {
+    uint64_t zone = (range << __builtin_clzll(range)) - 1u;
+    for (;;) {
+        uint64_t v = next_u64(s);
+        unsigned __int128 m = (unsigned __int128)v * range;
+        uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
+        if (lo <= zone) return hi;
+    }
+}
+
+/* rand 0.8 UniformInt<u8>: widened to u32, exact rejection zone */
+static uint32_t gen_range_u8(Stream *s, uint32_t range) {
+    uint32_t ints_to_reject = (0xFFFFFFFFu - range + 1u) % range;
+    uint32_t zone = 0xFFFFFFFFu - ints_to_reject;
+    for (;;) {
+        uint32_t v = next_u32(s);
+        uint64_t m = (uint64_t)v * range;
+        uint32_t hi = (uint32_t)(m >> 32), lo = (uint32_t)m;
+        if (lo <= zone) return hi;
+    }
+}
+
+/* rand 0.8 UniformFloat<f64>::sample_single for 0.0..1.0 (52-bit mantissa fill) */
+static double gen_range_f64_01(Stream *s) {
+    for (;;) {
+        uint64_t v = next_u64(s);
+        uint64_t bits = (v >> 12) | 0x3FF0000000000000ull;
+        double value1_2;
+        memcpy(&value1_2, &bits, 8);
+        double value0_1 = value1_2 - 1.0;
+        double res = value0_1 * 1.0 + 0.0;
+        if (res < 1.0) return res;
+    }
+}
+
+/* rand 0.8 Standard f64: 53 random bits * 2^-53 */
+static double gen_f64(Stream *s) {
+    uint64_t v = next_u64(s) >> 11;
+    return (double)v * (1.0 / 9007199254740992.0);
+}
+
+/* rand 0.8 Standard bool: sign bit of a u32 */
+static int gen_std_bool(Stream *s) { return (int32_t)next_u32(s) < 0; }
+
+int orc_gen_bool(uint64_t key, uint64_t *cursor, double p) {
+    Stream s = {key, *cursor, NULL, 0, 0};
+    int r = gen_bool(&s, p);
+    *cursor = s.cursor;
+    return r;
+}
+uint64_t orc_gen_range_usize(uint64_t key, uint64_t *cursor, uint64_t n) {
+    Stream s = {key, *cursor, NULL, 0, 0};
+    uint64_t r = gen_range_usize(&s, n);
+    *cursor = s.cursor;
+    return r;
+}
+uint32_t orc_gen_range_u8(uint64_t key, uint64_t *cursor, uint32_t n) {
+    Stream s = {key, *cursor, NULL, 0, 0};
+    uint32_t r = gen_range_u8(&s, n);
+    *cursor = s.cursor;
+    return r;
+}
+double orc_gen_range_f64_01(uint64_t key, uint64_t *cursor) {
+    Stream s = {key, *cursor, NULL, 0, 0};
+    double r = gen_range_f64_01(&s);
+    *cursor = s.cursor;
+    return r;
+}
+double orc_gen_f64(uint64_t key, uint64_t *cursor) {
+    Stream s = {key, *cursor, NULL, 0, 0};
+    double r = gen_f64(&s);
+    *cursor = s.cursor;
+    return r;
+}
+int orc_gen_std_bool(uint64_t key, uint64_t *cursor) {
+    Stream s = {key, *cursor, NULL, 0, 0};
+    int r = gen_std_bool(&s);
+    *cursor = s.cursor;
+    return r;
+}
+
+/* f64::powi lowers to compiler-rt __powidf2: square-and-multiply, reciprocal at the end */
+double orc_powi(double a, int b) {
+    const int recip = b < 0;
+    double r = 1.0;
+    for (;;) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return recip ? 1.0 / r : r;
+}
+
+/* ===================================================================================
+ * SSE replica: storage (op_container.rs:224-237, fast_ops.rs:35-49,181-190)
+ * =================================================================================== */
+
+#define SIDE_IN 0
+#define SIDE_OUT 1
+#define NONE (-1)
+
+typedef struct {
+    uint8_t present; /* Option<Node> */
+    uint8_t nv;      /* vars.len(): 1 or 2 */
+    uint8_t constant;
+    uint8_t in[2], out[2];
+    uint32_t bond;
+    uint32_t vars[2];
+    int64_t prev_p, next_p;         /* previous_p / next_p */
+    int64_t prev_vp[2], next_vp[2]; /* previous_for_vars / next_for_vars: PRel.p */
+    int8_t prev_vr[2], next_vr[2];  /*                                     PRel.relv */
+} Node;
+
+typedef struct {
+    int64_t *a;
+    int8_t *b;
+    int8_t *c;
+    uint64_t len, cap;
+} Stack; /* StackTuplizer (util/allocator.rs:73-139): LIFO of tuples */
+
+static void stack_push(Stack *s, int64_t a, int b, int c) {
+    if (s->len == s->cap) {
+        s->cap = s->cap ? 2 * s->cap : 1024;
+        s->a = (int64_t *)realloc(s->a, s->cap * sizeof(int64_t));
+        s->b = (int8_t *)realloc(s->b, s->cap);
+        s->c = (int8_t *)realloc(s->c, s->cap);
+    }
+    s->a[s->len] = a, s->b[s->len] = (int8_t)b, s->c[s->len] = (int8_t)c;
+    s->len++;
+}
+static void stack_free(Stack *s) {
+    free(s->a), free(s->b), free(s->c);
+    memset(s, 0, sizeof(*s));
+}
+
+struct OrcSse {
+    uint32_t nvars, nedges;
+    uint32_t *ea, *eb;
+    double *J;
+    double transverse, longitudinal;
+    double offset; /* total_energy_offset, qmc_ising.rs:97-99 */
+    uint64_t cutoff; /* QmcIsingGraph::cutoff */
+    Node *ops;       /* FastOps::ops */
+    uint64_t ops_len;
+    uint64_t n;
+    int64_t first_p, last_p;   /* p_ends */
+    int64_t *vfirst_p, *vlast_p; /* var_ends */
+    int8_t *vfirst_r, *vlast_r;
+    uint8_t *state;
+    Stream rng;
+    /* cluster scratch (boundaries StackTuplizer, cluster.rs:50-52) */
+    int64_t *b_in, *b_out;
+    uint64_t b_len, b_cap;
+    Stack frontier, interior;
+    /* fast mode scratch */
+    uint32_t *uf;
+    uint64_t uf_cap;
+    int error;
+};
+
+static uint32_t num_bonds(const OrcSse *g) {
+    /* qmc_ising.rs:664-670 */
+    return g->nedges + g->nvars + (fabs(g->longitudinal) > DBL_EPSILON ? g->nvars : 0u);
+}
+
+/* bonds_fn, qmc_ising.rs:671-681 */
+static void edge_fn(const OrcSse *g, uint32_t b, uint32_t vars[2], int *nv, int *constant) {
+    if (b < g->nedges) {
+        vars[0] = g->ea[b], vars[1] = g->eb[b], *nv = 2, *constant = 0;
+    } else if (b < g->nedges + g->nvars) {
+        vars[0] = b - g->nedges, *nv = 1, *constant = 1;
+    } else {
+        vars[0] = b - g->nvars - g->nedges, *nv = 1, *constant = 0;
+    }
+}
+
+/* qmc_ising.rs:863-875 */
+static double two_site_hamiltonian(int i0, int i1, int o0, int o1, double bond) {
+    if (i0 == o0 && i1 == o1) {
+        double t;
+        if (!i0 && !i1) t = -bond;
+        else if (!i0 && i1) t = bond;
+        else if (i0 && !i1) t = bond;
+        else t = -bond;
+        return fabs(bond) + t;
+    }
+    return 0.0;
+}
+/* qmc_ising.rs:877-879 */
+static double transverse_hamiltonian(int in, int out, double transverse) {
+    (void)in, (void)out;
+    return transverse;
+}
+/* qmc_ising.rs:881-888 */
+static double longitudinal_hamiltonian(int in, int out, double longitudinal) {
+    double t;
+    if (in != out) t = 0.0;
+    else if (in) t = longitudinal;
+    else t = -longitudinal;
+    return fabs(longitudinal) + t;
+}
+/* QmcIsingGraph::hamiltonian, qmc_ising.rs:179-205 */
+static double hamiltonian(const OrcSse *g, uint32_t bond, const uint8_t *in, const uint8_t *out) {
+    if (bond < g->nedges) return two_site_hamiltonian(in[0], in[1], out[0], out[1], g->J[bond]);
+    if (bond < g->nedges + g->nvars) return transverse_hamiltonian(in[0], out[0], g->transverse);
+    return longitudinal_hamiltonian(in[0], out[0], g->longitudinal);
+}
+
+static int node_is_diagonal(const Node *nd) {
+    for (int r = 0; r < nd->nv; r++)
+        if (nd->in[r] != nd->out[r]) return 0;
+    return 1;
+}
+/* cluster.rs:284-286 */
+static int is_edge(const Node *nd) { return nd->constant && nd->nv == 1; }
+
+static void ops_resize(OrcSse *g, uint64_t len) {
+    /* FastOps::set_cutoff, fast_ops.rs:1259-1263 / mutate_subsection fast_ops.rs:622-624 */
+    if (len > g->ops_len) {
+        g->ops = (Node *)realloc(g->ops, len * sizeof(Node));
+        memset(g->ops + g->ops_len, 0, (len - g->ops_len) * sizeof(Node));
+        g->ops_len = len;
+    }
+}
+
+OrcSse *orc_sse_create(uint32_t nvars, uint32_t nedges, const uint32_t *ea, const uint32_t *eb,
+                       const double *J, double transverse, double longitudinal, uint64_t cutoff,
+                       uint64_t rng_key, const uint8_t *state_or_null) {
+    /* new_with_rng_with_manager_hook, qmc_ising.rs:80-128 */
+    OrcSse *g = (OrcSse *)calloc(1, sizeof(OrcSse));
+    g->nvars = nvars, g->nedges = nedges;
+    g->ea = (uint32_t *)malloc(sizeof(uint32_t) * (nedges ? nedges : 1));
+    g->eb = (uint32_t *)malloc(sizeof(uint32_t) * (nedges ? nedges : 1));
+    g->J = (double *)malloc(sizeof(double) * (nedges ? nedges : 1));
+    memcpy(g->ea, ea, sizeof(uint32_t) * nedges);
+    memcpy(g->eb, eb, sizeof(uint32_t) * nedges);
+    memcpy(g->J, J, sizeof(double) * nedges);
+    g->transverse = transverse, g->longitudinal = longitudinal;
+    double edge_offset = 0.0;
+    for (uint32_t e = 0; e < nedges; e++) edge_offset += fabs(J[e]);
+    double field_offset = (double)nvars * (transverse + fabs(longitudinal));
+    g->offset = edge_offset + field_offset;
+    g->cutoff = cutoff;
+    ops_resize(g, cutoff);
+    g->first_p = g->last_p = NONE;
+    g->vfirst_p = (int64_t *)malloc(sizeof(int64_t) * nvars);
+    g->vlast_p = (int64_t *)malloc(sizeof(int64_t) * nvars);
+    g->vfirst_r = (int8_t *)malloc(nvars);
+    g->vlast_r = (int8_t *)malloc(nvars);
+    for (uint32_t v = 0; v < nvars; v++) g->vfirst_p[v] = g->vlast_p[v] = NONE;
+    g->rng.key = rng_key;
+    g->state = (uint8_t *)malloc(nvars);
+    if (state_or_null) {
+        memcpy(g->state, state_or_null, nvars);
+    } else {
+        /* make_random_spin_state, classical/graph.rs:451-453 */
+        for (uint32_t v = 0; v < nvars; v++) g->state[v] = (uint8_t)gen_std_bool(&g->rng);
+    }
+    return g;
+}
+
+void orc_sse_destroy(OrcSse *g) {
+    if (!g) return;
+    free(g->ea), free(g->eb), free(g->J), free(g->ops);
+    free(g->vfirst_p), free(g->vlast_p), free(g->vfirst_r), free(g->vlast_r);
+    free(g->state), free(g->b_in), free(g->b_out), free(g->uf);
+    stack_free(&g->frontier), stack_free(&g->interior);
+    free(g);
+}
+
+void orc_sse_set_script(OrcSse *g, const uint64_t *words, uint64_t nwords) {
+    g->rng.script = words, g->rng.script_len = nwords, g->rng.cursor = 0;
+}
+int orc_sse_error(const OrcSse *g) { return g->error | (g->rng.error << 8); }
+
+/* Rebuild every link from the op array.  Semantically what the incremental splices in
+ * FastOps::mutate_p maintain (fast_ops.rs:337-607; same construction as
+ * clear_and_install_ops fast_ops.rs:89-173). */
+static void rebuild_links(OrcSse *g) {
+    for (uint32_t v = 0; v < g->nvars; v++) g->vfirst_p[v] = g->vlast_p[v] = NONE;
+    g->first_p = g->last_p = NONE;
+    uint64_t n = 0;
+    for (uint64_t p = 0; p < g->ops_len; p++) {
+        Node *nd = &g->ops[p];
+        if (!nd->present) continue;
+        n++;
+        nd->prev_p = g->last_p, nd->next_p = NONE;
+        if (g->last_p != NONE) g->ops[g->last_p].next_p = (int64_t)p;
+        else g->first_p = (int64_t)p;
+        g->last_p = (int64_t)p;
+        for (int r = 0; r < nd->nv; r++) {
+            uint32_t v = nd->vars[r];
+            nd->next_vp[r] = NONE, nd->next_vr[r] = 0;
+            if (g->vlast_p[v] != NONE) {
+                Node *pn = &g->ops[g->vlast_p[v]];
+                pn->next_vp[g->vlast_r[v]] = (int64_t)p, pn->next_vr[g->vlast_r[v]] = (int8_t)r;
+                nd->prev_vp[r] = g->vlast_p[v], nd->prev_vr[r] = g->vlast_r[v];
+            } else {
+                nd->prev_vp[r] = NONE, nd->prev_vr[r] = 0;
+                g->vfirst_p[v] = (int64_t)p, g->vfirst_r[v] = (int8_t)r;
+            }
+            g->vlast_p[v] = (int64_t)p, g->vlast_r[v] = (int8_t)r;
+        }
+    }
+    g->n = n;
+}
+
+/* ===================================================================================
+ * Diagonal update: diagonal.rs:114-135 (driver), :142-191 (rule); loop fast_ops.rs:611-637
+ * =================================================================================== */
+static void diagonal_update(OrcSse *g, double beta) {
+    const uint64_t cutoff = g->cutoff;
+    const uint32_t nb = num_bonds(g);
+    ops_resize(g, cutoff); /* fast_ops.rs:622-624 */
+    uint8_t *state = g->state;
+    uint64_t n = g->n; /* s.get_n(): live */
+    for (uint64_t p = 0; p < cutoff; p++) {
+        Node *nd = &g->ops[p];
+        uint32_t b;
+        if (!nd->present) {
+            b = (uint32_t)gen_range_usize(&g->rng, nb); /* diagonal.rs:152 */
+        } else if (node_is_diagonal(nd)) {
+            b = nd->bond; /* :153 */
+        } else {
+            for (int r = 0; r < nd->nv; r++) state[nd->vars[r]] = nd->out[r]; /* :154-160 */
+            continue;
+        }
+        uint32_t vars[2];
+        int nv, constant;
+        edge_fn(g, b, vars, &nv, &constant);
+        uint8_t sub[2] = {0, 0};
+        for (int r = 0; r < nv; r++) sub[r] = state[vars[r]];
+        double mat_element = hamiltonian(g, b, sub, sub);
+        double numerator = beta * (double)nb * mat_element; /* :168 */
+        double denominator = (double)(cutoff - n);         /* :169 */
+        if (!nd->present) {
+            if (numerator > denominator || gen_bool(&g->rng, numerator / denominator)) { /* :173 */
+                nd->present = 1, nd->nv = (uint8_t)nv, nd->constant = (uint8_t)constant, nd->bond = b;
+                for (int r = 0; r < nv; r++)
+                    nd->vars[r] = vars[r], nd->in[r] = sub[r], nd->out[r] = sub[r];
+                n++;
+            }
+        } else {
+            denominator = denominator + 1.0; /* :182 */
+            if (denominator > numerator || gen_bool(&g->rng, denominator / numerator)) { /* :183 */
+                nd->present = 0;
+                n--;
+            }
+        }
+    }
+    g->n = n;
+    rebuild_links(g);
+}
+
+/* ===================================================================================
+ * Cluster update, reference order: cluster.rs:36-172, :193-271, :289-306
+ * =================================================================================== */
+static void boundaries_resize(OrcSse *g, uint64_t len) {
+    if (len > g->b_cap) {
+        g->b_cap = len + len / 2 + 16;
+        g->b_in = (int64_t *)realloc(g->b_in, g->b_cap * sizeof(int64_t));
+        g->b_out = (int64_t *)realloc(g->b_out, g->b_cap * sizeof(int64_t));
+    }
+    g->b_len = len;
+    for (uint64_t p = 0; p < len; p++) g->b_in[p] = g->b_out[p] = NONE;
+}
+
+/* set_boundary, cluster.rs:289-306.  Returns true if both sides now hold a cluster. */
+static int set_boundary(OrcSse *g, int64_t p, int side, int64_t c) {
+    int64_t *slot = side == SIDE_IN ? &g->b_in[p] : &g->b_out[p];
+    if (*slot == NONE || *slot == c) *slot = c;
+    else g->error = 3; /* unreachable!() in the reference */
+    return g->b_in[p] != NONE && g->b_out[p] != NONE;
+}
+
+/* expand_whole_cluster, cluster.rs:193-271 */
+static void expand_whole_cluster(OrcSse *g, int64_t p0, int relv0, int side0, int64_t c) {
+    Stack *in = &g->interior;
+    in->len = 0;
+    const Node *op = &g->ops[p0];
+    if (!is_edge(op)) {
+        for (int r = 0; r < op->nv; r++) stack_push(in, p0, r, SIDE_IN); /* :205-211 */
+        for (int r = 0; r < op->nv; r++) stack_push(in, p0, r, SIDE_OUT);
+    } else {
+        stack_push(in, p0, relv0, side0); /* :212-215 */
+    }
+    while (in->len) {
+        in->len--;
+        int64_t p = in->a[in->len];
+        int relvar = in->b[in->len], side = in->c[in->len];
+        set_boundary(g, p, side, c); /* :218 */
+        const Node *nd = &g->ops[p];
+        uint32_t var = nd->vars[relvar];
+        int64_t q;
+        int rq, sq;
+        if (side == SIDE_IN) { /* :224-232 */
+            q = nd->prev_vp[relvar], rq = nd->prev_vr[relvar];
+            if (q == NONE) q = g->vlast_p[var], rq = g->vlast_r[var];
+            sq = SIDE_OUT;
+        } else { /* :233-241 */
+            q = nd->next_vp[relvar], rq = nd->next_vr[relvar];
+            if (q == NONE) q = g->vfirst_p[var], rq = g->vfirst_r[var];
+            sq = SIDE_IN;
+        }
+        const Node *qn = &g->ops[q];
+        if (is_edge(qn)) { /* :245-248 */
+            if (!set_boundary(g, q, sq, c)) stack_push(&g->frontier, q, 0, sq == SIDE_IN ? SIDE_OUT : SIDE_IN);
+        } else { /* :249-268 */
+            int64_t a = g->b_in[q], b = g->b_out[q];
+            int ok = (a == NONE && b == NONE) || (a == c && b == NONE) || (a == NONE && b == c);
+            if (ok) {
+                g->b_in[q] = c, g->b_out[q] = c; /* set_boundaries :308-315 */
+                for (int r = 0; r < qn->nv; r++)
+                    if (!(r == rq && sq == SIDE_IN)) stack_push(in, q, r, SIDE_IN);
+                for (int r = 0; r < qn->nv; r++)
+                    if (!(r == rq && sq == SIDE_OUT)) stack_push(in, q, r, SIDE_OUT);
+            }
+        }
+    }
+}
+
+/* flip_each_cluster_rng, cluster.rs:36-172; `has_weights` selects the h != 0 closure of
+ * qmc_ising.rs:754-776 (longitudinal ops give weight 0.0, everything else 1.0). */
+static uint64_t cluster_update_strict(OrcSse *g, int has_weights) {
+    if (g->n == 0) return 0; /* :46-48 */
+    const int64_t last_p = g->last_p;
+    boundaries_resize(g, (uint64_t)last_p + 1);
+    /* find_constant_op :175-186 */
+    int64_t cp = g->first_p;
+    while (cp != NONE && !is_edge(&g->ops[cp])) cp = g->ops[cp].next_p;
+    uint64_t n_clusters;
+    if (cp != NONE) {
+        Stack *fr = &g->frontier;
+        fr->len = 0;
+        stack_push(fr, cp, 0, SIDE_OUT); /* :57-59 */
+        stack_push(fr, cp, 0, SIDE_IN);
+        int64_t cluster_num = 0;
+        uint64_t scan = 0; /* smallest unmapped p is monotone, so the :82-88 scan can resume */
+        for (;;) {
+            while (fr->len) { /* :62-80 */
+                fr->len--;
+                int64_t p = fr->a[fr->len];
+                int side = fr->c[fr->len];
+                if (g->b_in[p] != NONE && g->b_out[p] != NONE) continue;
+                expand_whole_cluster(g, p, 0, side, cluster_num);
+                cluster_num++;
+            }
+            int64_t unmapped = NONE; /* :82-88 */
+            for (; scan <= (uint64_t)last_p; scan++) {
+                if (g->ops[scan].present && g->b_in[scan] == NONE && g->b_out[scan] == NONE) {
+                    unmapped = (int64_t)scan;
+                    break;
+                }
+            }
+            if (unmapped == NONE) break;
+            stack_push(fr, unmapped, 0, SIDE_OUT); /* :89-91 */
+            stack_push(fr, unmapped, 0, SIDE_IN);
+        }
+        n_clusters = (uint64_t)cluster_num;
+    } else { /* :98-107 */
+        for (int64_t p = 0; p <= last_p; p++)
+            if (g->ops[p].present) g->b_in[p] = g->b_out[p] = 0;
+        n_clusters = 1;
+    }
+
+    uint8_t *flips = (uint8_t *)malloc(n_clusters ? n_clusters : 1);
+    if (has_weights) { /* :111-136 */
+        double *w = (double *)malloc(sizeof(double) * n_clusters);
+        for (uint64_t k = 0; k < n_clusters; k++) w[k] = 1.0;
+        for (int64_t p = 0; p <= last_p; p++) {
+            if (g->b_in[p] == NONE) continue;
+            if (g->b_in[p] == g->b_out[p]) {
+                double f = g->ops[p].bond >= g->nedges + g->nvars ? 0.0 : 1.0; /* qmc_ising.rs:759-775 */
+                w[g->b_in[p]] *= f;
+            }
+        }
+        for (uint64_t k = 0; k < n_clusters; k++) flips[k] = (uint8_t)gen_bool(&g->rng, w[k] * 0.5);
+        free(w);
+    } else { /* :137 */
+        for (uint64_t k = 0; k < n_clusters; k++) flips[k] = (uint8_t)gen_bool(&g->rng, 0.5);
+    }
+    for (int64_t p = 0; p <= last_p; p++) { /* :139-167 */
+        if (g->b_in[p] == NONE) continue;
+        Node *nd = &g->ops[p];
+        if (flips[g->b_in[p]]) {
+            for (int r = 0; r < nd->nv; r++) nd->in[r] = !nd->in[r];
+            for (int r = 0; r < nd->nv; r++)
+                if (nd->prev_vp[r] == NONE) g->state[nd->vars[r]] = nd->in[r];
+        }
+        if (flips[g->b_out[p]])
+            for (int r = 0; r < nd->nv; r++) nd->out[r] = !nd->out[r];
+    }
+    free(flips);
+    return n_clusters;
+}
+
+/* ===================================================================================
+ * Cluster update, canonical ("fast") order -- builder-defined contract, same Markov
+ * kernel as cluster.rs:36-172 but order-independent so that it can be labelled with a
+ * parallel union-find (DESIGN.md "fast mode"):
+ *   * site ops (constant, one variable; cluster.rs:284-286) cut world lines into segments.
+ *     ids: v in [0,N) = the segment of variable v crossing p = 0;  N + k = the segment that
+ *     starts at the output of the k-th site op (p order).
+ *   * every two-variable op joins the two segments it touches; the segment after the last
+ *     site op of v is joined with segment v (periodic closure).
+ *   * cluster root = smallest segment id.  No site op at all => one cluster (cluster.rs:98-107).
+ *   * a cluster holding a longitudinal op never flips (weight 0, qmc_ising.rs:759-775);
+ *     otherwise flip = bit (root & 127) of Philox(key, ctr = (root >> 7, c_lo, c_hi, 'CLUS')),
+ *     c = stream cursor at the start of the step; the step then advances the cursor by 1.
+ * =================================================================================== */
+#define TAG_CLUS 0x434C5553u
+
+static uint32_t uf_find(uint32_t *uf, uint32_t x) {
+    while (uf[x] != x) {
+        uf[x] = uf[uf[x]];
+        x = uf[x];
+    }
+    return x;
+}
+static void uf_union(uint32_t *uf, uint32_t a, uint32_t b) {
+    a = uf_find(uf, a), b = uf_find(uf, b);
+    if (a < b) uf[b] = a;
+    else if (b < a) uf[a] = b;
+}
+
+static int fast_flip_bit(uint64_t key, uint64_t cursor, uint32_t root) {
+    uint32_t ctr[4] = {root >> 7, (uint32_t)cursor, (uint32_t)(cursor >> 32), TAG_CLUS};
+    uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+    uint32_t x[4];
+    orc_philox4x32_10(ctr, k, x);
+    return (x[(root >> 5) & 3] >> (root & 31)) & 1u;
+}
+
+static uint64_t cluster_update_fast(OrcSse *g, int has_weights) {
+    if (g->n == 0) return 0;
+    const uint32_t N = g->nvars;
+    const int64_t last_p = g->last_p;
+    boundaries_resize(g, (uint64_t)last_p + 1);
+    uint64_t need = (uint64_t)N + g->n + 1;
+    if (need > g->uf_cap) {
+        g->uf_cap = need + need / 2;
+        g->uf = (uint32_t *)realloc(g->uf, g->uf_cap * sizeof(uint32_t));
+    }
+    uint32_t *uf = g->uf;
+    uint32_t *cur = (uint32_t *)malloc(sizeof(uint32_t) * N);
+    for (uint32_t v = 0; v < N; v++) uf[v] = v, cur[v] = v;
+    uint32_t nsite = 0;
+    /* pass 1: segment ids per leg (stored in b_in/b_out) and unions */
+    for (int64_t p = 0; p <= last_p; p++) {
+        const Node *nd = &g->ops[p];
+        if (!nd->present) continue;
+        if (is_edge(nd)) {
+            uint32_t v = nd->vars[0];
+            g->b_in[p] = cur[v];
+            uint32_t id = N + nsite++;
+            uf[id] = id;
+            cur[v] = id;
+            g->b_out[p] = id;
+        } else {
+            g->b_in[p] = g->b_out[p] = cur[nd->vars[0]];
+            if (nd->nv == 2) uf_union(uf, cur[nd->vars[0]], cur[nd->vars[1]]);
+        }
+    }
+    for (uint32_t v = 0; v < N; v++) uf_union(uf, v, cur[v]); /* periodic closure */
+    const uint32_t nseg = N + nsite;
+    if (nsite == 0) /* cluster.rs:98-107: no cluster edge => everything is one cluster */
+        for (uint32_t x = 0; x < nseg; x++) uf[x] = 0;
+    /* frozen clusters + cluster count (roots that own at least one leg) */
+    uint8_t *frozen = (uint8_t *)calloc(nseg, 1), *used = (uint8_t *)calloc(nseg, 1);
+    for (int64_t p = 0; p <= last_p; p++) {
+        const Node *nd = &g->ops[p];
+        if (!nd->present) continue;
+        uint32_t ri = uf_find(uf, (uint32_t)g->b_in[p]), ro = uf_find(uf, (uint32_t)g->b_out[p]);
+        used[ri] = used[ro] = 1;
+        if (has_weights && nd->bond >= g->nedges + N) frozen[ri] = 1;
+    }
+    uint64_t n_clusters = 0;
+    for (uint32_t x = 0; x < nseg; x++) n_clusters += used[x];
+    const uint64_t c0 = g->rng.cursor;
+    /* apply: same edits as cluster.rs:139-167 */
+    for (int64_t p = 0; p <= last_p; p++) {
+        Node *nd = &g->ops[p];
+        if (!nd->present) continue;
+        uint32_t ri = uf_find(uf, (uint32_t)g->b_in[p]), ro = uf_find(uf, (uint32_t)g->b_out[p]);
+        g->b_in[p] = ri, g->b_out[p] = ro;
+        int fi = !frozen[ri] && fast_flip_bit(g->rng.key, c0, ri);
+        int fo = !frozen[ro] && fast_flip_bit(g->rng.key, c0, ro);
+        if (fi) {
+            for (int r = 0; r < nd->nv; r++) nd->in[r] = !nd->in[r];
+            for (int r = 0; r < nd->nv; r++)
+                if (nd->prev_vp[r] == NONE) g->state[nd->vars[r]] = nd->in[r];
+        }
+        if (fo)
+            for (int r = 0; r < nd->nv; r++) nd->out[r] = !nd->out[r];
+    }
+    g->rng.cursor = c0 + 1;
+    free(frozen), free(used), free(cur);
+    return n_clusters;
+}
+
+/* single_cluster_step qmc_ising.rs:273-320 / timestep :754-784 */
+static uint64_t cluster_and_free_spins(OrcSse *g, int mode) {
+    int has_weights = fabs(g->longitudinal) > DBL_EPSILON;
+    uint64_t ncl = mode == ORC_MODE_FAST ? cluster_update_fast(g, has_weights)
+                                         : cluster_update_strict(g, has_weights);
+    for (uint32_t v = 0; v < g->nvars; v++) /* qmc_ising.rs:780-784 */
+        if (g->vfirst_p[v] == NONE) g->state[v] = (uint8_t)gen_bool(&g->rng, 0.5);
+    return ncl;
+}
+
+/* QmcIsingGraph::timestep, qmc_ising.rs:644-795 (rvb and heat-bath off: defaults :122,:126) */
+void orc_sse_timestep(OrcSse *g, double beta, int mode) {
+    diagonal_update(g, beta);
+    cluster_and_free_spins(g, mode);
+    uint64_t grown = g->n + g->n / 2; /* :786 */
+    if (grown > g->cutoff) g->cutoff = grown;
+}
+
+/* qmc_ising.rs:208-270 */
+void orc_sse_single_diagonal_step(OrcSse *g, double beta) {
+    diagonal_update(g, beta);
+    uint64_t grown = g->n + g->n / 2;
+    if (grown > g->cutoff) g->cutoff = grown;
+}
+uint64_t orc_sse_single_cluster_step(OrcSse *g, int mode) { return cluster_and_free_spins(g, mode); }
+
+/* QmcStepper::timesteps_measure_with_self, qmc_stepper.rs:133-162; energy qmc_ising.rs:805-809 */
+double orc_sse_timesteps(OrcSse *g, uint64_t t, double beta, uint64_t sampling_freq, int mode,
+                         uint8_t *samples_or_null) {
+    uint64_t steps_measured = 0, total_n = 0;
+    if (sampling_freq == 0) sampling_freq = 1;
+    for (uint64_t i = 0; i < t; i++) {
+        orc_sse_timestep(g, beta, mode);
+        if ((i + 1) % sampling_freq == 0) {
+            if (samples_or_null) memcpy(samples_or_null + steps_measured * g->nvars, g->state, g->nvars);
+            steps_measured++;
+            total_n += g->n;
+        }
+    }
+    double average_n = (double)total_n / (double)steps_measured;
+    return -(average_n / beta) + g->offset;
+}
+
+uint32_t orc_sse_nvars(const OrcSse *g) { return g->nvars; }
+uint64_t orc_sse_get_n(const OrcSse *g) { return g->n; }
+uint64_t orc_sse_get_cutoff(const OrcSse *g) { return g->cutoff; }
+void orc_sse_set_cutoff(OrcSse *g, uint64_t cutoff) { /* qmc_ising.rs:537-540 */
+    g->cutoff = cutoff;
+    ops_resize(g, cutoff);
+}
+uint64_t orc_sse_get_cursor(const OrcSse *g) { return g->rng.cursor; }
+void orc_sse_set_cursor(OrcSse *g, uint64_t cursor) { g->rng.cursor = cursor; }
+double orc_sse_get_offset(const OrcSse *g) { return g->offset; }
+void orc_sse_get_state(const OrcSse *g, uint8_t *out) { memcpy(out, g->state, g->nvars); }
+void orc_sse_set_state(OrcSse *g, const uint8_t *in) { memcpy(g->state, in, g->nvars); }
+
+uint64_t orc_sse_get_bond_count(const OrcSse *g, uint32_t bond) { /* fast_ops.rs:1281-1294 */
+    uint64_t c = 0;
+    for (uint64_t p = 0; p < g->ops_len; p++) c += g->ops[p].present && g->ops[p].bond == bond;
+    return c;
+}
+
+void orc_sse_dump_ops(const OrcSse *g, uint32_t *words) {
+    for (uint64_t p = 0; p < g->cutoff; p++) {
+        const Node *nd = p < g->ops_len ? &g->ops[p] : NULL;
+        if (!nd || !nd->present) {
+            words[p] = ORC_OP_EMPTY;
+            continue;
+        }
+        uint32_t w = nd->bond;
+        for (int r = 0; r < nd->nv; r++) w |= (uint32_t)nd->in[r] << (24 + r), w |= (uint32_t)nd->out[r] << (26 + r);
+        words[p] = w;
+    }
+}
+
+int orc_sse_load_ops(OrcSse *g, const uint32_t *words, uint64_t nwords, const uint8_t *state) {
+    /* FastOps::new_from_ops, fast_ops.rs:80-87 */
+    if (nwords > g->cutoff) orc_sse_set_cutoff(g, nwords);
+    memset(g->ops, 0, g->ops_len * sizeof(Node));
+    for (uint64_t p = 0; p < nwords; p++) {
+        uint32_t w = words[p];
+        if (w == ORC_OP_EMPTY) continue;
+        uint32_t b = w & 0xFFFFFFu;
+        if (b >= g->nedges + 2 * g->nvars) return -1;
+        Node *nd = &g->ops[p];
+        int nv, constant;
+        edge_fn(g, b, nd->vars, &nv, &constant);
+        nd->present = 1, nd->nv = (uint8_t)nv, nd->constant = (uint8_t)constant, nd->bond = b;
+        for (int r = 0; r < nv; r++) nd->in[r] = (w >> (24 + r)) & 1u, nd->out[r] = (w >> (26 + r)) & 1u;
+    }
+    if (state) memcpy(g->state, state, g->nvars);
+    rebuild_links(g);
+    return 0;
+}
+
+/* OpContainer::verify op_container.rs:137-159 + QmcIsingGraph::verify qmc_ising.rs:829-860 */
+int orc_sse_verify(const OrcSse *g) {
+    uint8_t *rolling = (uint8_t *)malloc(g->nvars);
+    memcpy(rolling, g->state, g->nvars);
+    int ok = 1;
+    uint64_t n = 0;
+    for (uint64_t p = 0; p < g->ops_len && ok; p++) {
+        const Node *nd = &g->ops[p];
+        if (!nd->present) continue;
+        n++;
+        if (p >= g->cutoff) ok = 0;
+        if (!(fabs(hamiltonian(g, nd->bond, nd->in, nd->out)) > DBL_EPSILON)) ok = 0;
+        for (int r = 0; r < nd->nv; r++)
+            if (rolling[nd->vars[r]] != nd->in[r]) ok = 0;
+        for (int r = 0; r < nd->nv; r++) rolling[nd->vars[r]] = nd->out[r];
+    }
+    if (memcmp(rolling, g->state, g->nvars) != 0) ok = 0;
+    if (n != g->n) ok = 0;
+    free(rolling);
+    return ok;
+}
+
+void orc_sse_get_boundaries(const OrcSse *g, int64_t *b_in, int64_t *b_out, uint64_t nslots) {
+    for (uint64_t p = 0; p < nslots; p++) {
+        b_in[p] = p < g->b_len ? g->b_in[p] : NONE;
+        b_out[p] = p < g->b_len ? g->b_out[p] : NONE;
+    }
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* graphs.par_iter_mut().for_each(|(g, beta)| g.timesteps(t, beta)), tempering_container.rs:367-371 */
+uint64_t orc_sse_batch_timesteps(OrcSse **reps, uint32_t nreps, uint64_t t, const double *betas,
+                                 int mode, double *energies_or_null, int nthreads) {
+    uint64_t total = 0;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(+ : total)
+#endif
+    for (uint32_t r = 0; r < nreps; r++) {
+        uint64_t tn = 0;
+        for (uint64_t i = 0; i < t; i++) {
+            orc_sse_timestep(reps[r], betas[r], mode);
+            tn += reps[r]->n;
+        }
+        if (energies_or_null) energies_or_null[r] = -(((double)tn / (double)t) / betas[r]) + reps[r]->offset;
+        total += tn;
+    }
+    (void)nthreads;
+    return total;
+}
+
+/* ===================================================================================
+ * Parallel tempering: tempering_container.rs:83-149, :241-302; swap qmc_ising.rs:593-602
+ * =================================================================================== */
+static void swap_manager_and_state(OrcSse *a, OrcSse *b) {
+#define SWAPF(T, f) do { T t_ = a->f; a->f = b->f; b->f = t_; } while (0)
+    SWAPF(Node *, ops);
+    SWAPF(uint64_t, ops_len);
+    SWAPF(uint64_t, n);
+    SWAPF(int64_t, first_p);
+    SWAPF(int64_t, last_p);
+    SWAPF(int64_t *, vfirst_p);
+    SWAPF(int64_t *, vlast_p);
+    SWAPF(int8_t *, vfirst_r);
+    SWAPF(int8_t *, vlast_r);
+    SWAPF(uint8_t *, state);
+#undef SWAPF
+}
+
+static uint64_t perform_swaps(Stream *rng, OrcSse **graphs, const double *betas, uint32_t len) {
+    /* tempering_container.rs:241-260; all Hamiltonians equal => rel_h_weight = 1.0 (:286-292) */
+    uint64_t swaps = 0;
+    for (uint32_t i = 0; i + 1 < len; i += 2) {
+        double p = gen_range_f64_01(rng); /* :255 */
+        OrcSse *ga = graphs[i], *gb = graphs[i + 1];
+        double temp_swap = orc_powi(betas[i] / betas[i + 1], (int32_t)gb->n - (int32_t)ga->n); /* :294 */
+        double p_swap = temp_swap * 1.0;
+        if (p_swap > p) { /* :296-301 */
+            swap_manager_and_state(ga, gb);
+            swaps++;
+        }
+    }
+    return swaps;
+}
+
+uint64_t orc_pt_step(OrcSse **slots, uint32_t nslots, const double *betas, uint64_t pt_key,
+                     uint64_t *pt_cursor) {
+    if (nslots <= 1) return 0; /* :122-124 */
+    uint64_t max_cutoff = 0; /* :129-137 */
+    for (uint32_t i = 0; i < nslots; i++)
+        if (slots[i]->cutoff > max_cutoff) max_cutoff = slots[i]->cutoff;
+    for (uint32_t i = 0; i < nslots; i++) orc_sse_set_cutoff(slots[i], max_cutoff);
+    Stream rng = {pt_key, *pt_cursor, NULL, 0, 0};
+    /* make_first_subgraphs / make_second_subgraphs :83-99 */
+    uint32_t a_len = (nslots % 2 == 0) ? nslots : nslots - 1;
+    uint32_t b_len = (nslots % 2 == 1) ? nslots - 1 : nslots - 2;
+    uint64_t swaps = 0;
+    if (gen_bool(&rng, 0.5)) { /* :140-146 */
+        swaps += perform_swaps(&rng, slots, betas, a_len);
+        swaps += perform_swaps(&rng, slots + 1, betas + 1, b_len);
+    } else {
+        swaps += perform_swaps(&rng, slots + 1, betas + 1, b_len);
+        swaps += perform_swaps(&rng, slots, betas, a_len);
+    }
+    *pt_cursor = rng.cursor;
+    return swaps;
+}
+
+/* ===================================================================================
+ * Classical graph: classical/graph.rs:56-119, :339-347, :430-453
+ * =================================================================================== */
+#define TAG_CB 0x43420000u
+
+struct OrcCls {
+    uint32_t nvars;
+    uint32_t *adj_start; /* binding_mat as CSR, neighbours sorted by index (graph.rs:69-78) */
+    uint32_t *adj_idx;
+    double *adj_j;
+    double *biases;
+    uint8_t *state;
+    Stream rng;
+    uint64_t sweep; /* checkerboard sweep counter */
+};
+
+OrcCls *orc_cls_create(uint32_t nvars, uint32_t nedges, const uint32_t *ea, const uint32_t *eb,
+                       const double *J, const double *biases, uint64_t rng_key,
+                       const uint8_t *state_or_null) {
+    OrcCls *g = (OrcCls *)calloc(1, sizeof(OrcCls));
+    g->nvars = nvars;
+    g->rng.key = rng_key;
+    g->state = (uint8_t *)malloc(nvars);
+    if (state_or_null) memcpy(g->state, state_or_null, nvars);
+    else
+        for (uint32_t v = 0; v < nvars; v++) g->state[v] = (uint8_t)gen_std_bool(&g->rng); /* :57, :451-453 */
+    g->biases = (double *)malloc(sizeof(double) * nvars);
+    memcpy(g->biases, biases, sizeof(double) * nvars);
+    g->adj_start = (uint32_t *)calloc((size_t)nvars + 1, sizeof(uint32_t));
+    for (uint32_t e = 0; e < nedges; e++) g->adj_start[ea[e] + 1]++, g->adj_start[eb[e] + 1]++;
+    for (uint32_t v = 0; v < nvars; v++) g->adj_start[v + 1] += g->adj_start[v];
+    uint32_t tot = g->adj_start[nvars];
+    g->adj_idx = (uint32_t *)malloc(sizeof(uint32_t) * (tot ? tot : 1));
+    g->adj_j = (double *)malloc(sizeof(double) * (tot ? tot : 1));
+    uint32_t *fill = (uint32_t *)calloc(nvars, sizeof(uint32_t));
+    for (uint32_t e = 0; e < nedges; e++) { /* push order :71-74 */
+        uint32_t a = ea[e], b = eb[e];
+        g->adj_idx[g->adj_start[a] + fill[a]] = b, g->adj_j[g->adj_start[a] + fill[a]++] = J[e];
+        g->adj_idx[g->adj_start[b] + fill[b]] = a, g->adj_j[g->adj_start[b] + fill[b]++] = J[e];
+    }
+    free(fill);
+    for (uint32_t v = 0; v < nvars; v++) { /* stable sort_by_key :76-78 */
+        uint32_t s = g->adj_start[v], e = g->adj_start[v + 1];
+        for (uint32_t i = s + 1; i < e; i++) {
+            uint32_t ki = g->adj_idx[i];
+            double kj = g->adj_j[i];
+            uint32_t j = i;
+            while (j > s && g->adj_idx[j - 1] > ki) {
+                g->adj_idx[j] = g->adj_idx[j - 1], g->adj_j[j] = g->adj_j[j - 1];
+                j--;
+            }
+            g->adj_idx[j] = ki, g->adj_j[j] = kj;
+        }
+    }
+    return g;
+}
+
+void orc_cls_destroy(OrcCls *g) {
+    if (!g) return;
+    free(g->adj_start), free(g->adj_idx), free(g->adj_j), free(g->biases), free(g->state);
+    free(g);
+}
+
+/* delta_e of do_spin_flip, graph.rs:98-115 */
+static double cls_delta_e(const OrcCls *g, uint32_t i) {
+    int curr = g->state[i];
+    double delta_e = 0.0;
+    for (uint32_t k = g->adj_start[i]; k < g->adj_start[i + 1]; k++) {
+        double old_coupling = !(curr ^ g->state[g->adj_idx[k]]) ? 1.0 : -1.0;
+        delta_e += -2.0 * g->adj_j[k] * old_coupling;
+    }
+    return delta_e + (2.0 * g->biases[i] * (curr ? 1.0 : -1.0));
+}
+
+void orc_cls_spin_flips(OrcCls *g, double beta, uint64_t count) {
+    for (uint64_t t = 0; t < count; t++) {
+        uint32_t i = (uint32_t)gen_range_usize(&g->rng, g->nvars); /* :98 */
+        double delta_e = cls_delta_e(g, i);
+        int flip; /* should_flip :339-347 */
+        if (delta_e > 0.0) {
+            double chance = exp(-beta * delta_e);
+            flip = gen_f64(&g->rng) < chance;
+        } else {
+            flip = 1;
+        }
+        if (flip) g->state[i] = !g->state[i];
+    }
+}
+
+uint64_t orc_cls_threshold(double beta, double delta_e) {
+    if (!(delta_e > 0.0)) return 4294967296ull;
+    double chance = exp(-beta * delta_e);
+    double scaled = ceil(chance * 4294967296.0); /* #{d : d * 2^-32 < chance} */
+    if (scaled >= 4294967296.0) return 4294967296ull;
+    return (uint64_t)scaled;
+}
+
+/* Checkerboard schedule (builder-defined; the reference has none).  Per site the rule is
+ * graph.rs:98-118 + :339-347 with a fixed-width 32-bit draw: site of rank r inside colour c
+ * uses word (r & 3) of Philox(key, ctr = (r >> 2, sweep_lo, sweep_hi, 'CB' << 16 | c)) and
+ * flips iff delta_e <= 0 or d * 2^-32 < exp(-beta * delta_e). */
+void orc_cls_checkerboard_sweeps(OrcCls *g, double beta, const uint32_t *colours,
+                                 uint32_t ncolours, uint64_t nsweeps) {
+    uint32_t k[2] = {(uint32_t)g->rng.key, (uint32_t)(g->rng.key >> 32)};
+    for (uint64_t s = 0; s < nsweeps; s++, g->sweep++) {
+        for (uint32_t c = 0; c < ncolours; c++) {
+            uint32_t rank = 0;
+            uint32_t x[4] = {0, 0, 0, 0};
+            for (uint32_t i = 0; i < g->nvars; i++) {
+                if (colours[i] != c) continue;
+                if ((rank & 3u) == 0) {
+                    uint32_t ctr[4] = {rank >> 2, (uint32_t)g->sweep, (uint32_t)(g->sweep >> 32), TAG_CB | c};
+                    orc_philox4x32_10(ctr, k, x);
+                }
+                uint32_t d = x[rank & 3u];
+                rank++;
+                double delta_e = cls_delta_e(g, i);
+                int flip;
+                if (delta_e > 0.0) {
+                    double chance = exp(-beta * delta_e);
+                    flip = (double)d * (1.0 / 4294967296.0) < chance;
+                } else {
+                    flip = 1;
+                }
+                if (flip) g->state[i] = !g->state[i];
+            }
+        }
+    }
+}
+
+/* get_energy, graph.rs:430-447 */
+double orc_cls_energy(const OrcCls *g) {
+    double acc = 0.0;
+    for (uint32_t i = 0; i < g->nvars; i++) {
+        int si = g->state[i];
+        double total_e = 0.0;
+        for (uint32_t k = g->adj_start[i]; k < g->adj_start[i + 1]; k++) {
+            double old_coupling = !(si ^ g->state[g->adj_idx[k]]) ? 1.0 : -1.0;
+            total_e += g->adj_j[k] * old_coupling / 2.0;
+        }
+        double bias_e = si ? -g->biases[i] : g->biases[i];
+        acc = acc + total_e + bias_e;
+    }
+    return acc;
+}
+
+double orc_cls_magnetization(const OrcCls *g) {
+    int64_t m = 0;
+    for (uint32_t i = 0; i < g->nvars; i++) m += g->state[i] ? 1 : -1;
+    return (double)m / (double)g->nvars;
+}
+void orc_cls_get_state(const OrcCls *g, uint8_t *out) { memcpy(out, g->state, g->nvars); }
+void orc_cls_set_state(OrcCls *g, const uint8_t *in) { memcpy(g->state, in, g->nvars); }
+uint64_t orc_cls_get_cursor(const OrcCls *g) { return g->rng.cursor; }
+uint64_t orc_cls_get_sweep(const OrcCls *g) { return g->sweep; }
+void orc_cls_set_sweep(OrcCls *g, uint64_t sweep) { g->sweep = sweep; }
+
+void orc_cls_batch_checkerboard(OrcCls **reps, uint32_t nreps, const double *betas,
+                                const uint32_t *colours, uint32_t ncolours, uint64_t nsweeps,
+                                int nthreads) {
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+#endif
+    for (uint32_t r = 0; r < nreps; r++)
+        orc_cls_checkerboard_sweeps(reps[r], betas[r], colours, ncolours, nsweeps);
+    (void)nthreads;
+}
+
+void orc_cls_batch_spin_flips(OrcCls **reps, uint32_t nreps, const double *betas, uint64_t count,
+                              int nthreads) {
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+#endif
+    for (uint32_t r = 0; r < nreps; r++) orc_cls_spin_flips(reps[r], betas[r], count);
+    (void)nthreads;
+}

@@ -1,0 +1,125 @@
+"""Pins the RNG contract of the oracle: Philox4x32-10 Random123 known
+answers and the rand-0.8 draw->value mappings restated in oracle/oracle.c."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+KATS = [
+    ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+    ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+    ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+     [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+]
+
+
+@pytest.mark.parametrize("ctr,key,expect", KATS)
+def test_philox_known_answers(ctr, key, expect):
+    assert [int(x) for x in po.philox(ctr, key)] == expect
+
+
+def test_philox_matches_torch_engine_constants():
+    # independent restatement in numpy (same multipliers / Weyl constants as curand_philox4x32_x.h:88-91)
+    def ref(ctr, key):
+        c = [int(x) for x in ctr]
+        k = [int(x) for x in key]
+        for r in range(10):
+            if r:
+                k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+            p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+        return c
+
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        ctr = rng.integers(0, 2**32, 4, dtype=np.uint64)
+        key = rng.integers(0, 2**32, 2, dtype=np.uint64)
+        assert [int(x) for x in po.philox(ctr, key)] == ref(ctr, key)
+
+
+def test_stream_word_layout():
+    # W[c]: counter = c >> 1, low/high pair selected by c & 1 (Appendix A.3)
+    key = 0x0123456789ABCDEF
+    for c in (0, 1, 2, 3, 2**33 + 5):
+        x = po.philox([(c >> 1) & 0xFFFFFFFF, (c >> 1) >> 32, 0, 0], [key & 0xFFFFFFFF, key >> 32])
+        h = (c & 1) * 2
+        assert po.stream_word(key, c) == (int(x[h + 1]) << 32) | int(x[h])
+
+
+def test_gen_bool_semantics():
+    L = po.lib()
+    assert L.orc_bool_threshold(0.5) == 1 << 63
+    assert L.orc_bool_threshold(2.0 / 6.0) == 0x5555555555555400
+    assert L.orc_bool_threshold(0.0) == 0
+    cur = C.c_uint64(0)
+    assert L.orc_gen_bool(7, C.byref(cur), 1.0) == 1 and cur.value == 0  # p == 1: no draw
+    assert L.orc_gen_bool(7, C.byref(cur), 0.0) == 0 and cur.value == 1  # p == 0: one draw
+    for c in range(64):
+        cur = C.c_uint64(c)
+        w = po.stream_word(7, c)
+        assert L.orc_gen_bool(7, C.byref(cur), 0.5) == int(w < (1 << 63))
+        assert cur.value == c + 1
+
+
+def test_gen_range_usize_semantics():
+    L = po.lib()
+    for n in (1, 2, 3, 8, 3072, 12288, 2**40 + 3):
+        zone = ((n << (64 - n.bit_length())) - 1) & (2**64 - 1)
+        if n == 3:
+            assert zone == 0xBFFFFFFFFFFFFFFF  # Appendix B, D1
+        cur_py = 0
+        cur = C.c_uint64(0)
+        for _ in range(200):
+            got = L.orc_gen_range_usize(11, C.byref(cur), n)
+            while True:
+                v = po.stream_word(11, cur_py)
+                cur_py += 1
+                m = v * n
+                if (m & (2**64 - 1)) <= zone:
+                    break
+            assert got == m >> 64 and cur.value == cur_py
+
+
+def test_gen_range_u8_and_floats():
+    L = po.lib()
+    cur = C.c_uint64(0)
+    for c in range(100):
+        w = po.stream_word(3, c)
+        cur = C.c_uint64(c)
+        assert L.orc_gen_f64(3, C.byref(cur)) == (w >> 11) * 2.0**-53
+        cur = C.c_uint64(c)
+        assert L.orc_gen_range_f64_01(3, C.byref(cur)) == (w >> 12) * 2.0**-52
+        cur = C.c_uint64(c)
+        assert L.orc_gen_std_bool(3, C.byref(cur)) == (w >> 63)
+        cur = C.c_uint64(c)
+        hi32 = w >> 32
+        for t in (2, 3):
+            cur = C.c_uint64(c)
+            got = L.orc_gen_range_u8(3, C.byref(cur), t)
+            zone = 0xFFFFFFFF - ((2**32 - t) % t)
+            if ((hi32 * t) & 0xFFFFFFFF) <= zone:
+                assert got == (hi32 * t) >> 32 and cur.value == c + 1
+
+
+def test_powi_is_compiler_rt_square_and_multiply():
+    L = po.lib()
+
+    def powidf2(a, b):
+        recip, r = b < 0, 1.0
+        b = abs(b)
+        while True:
+            if b & 1:
+                r *= a
+            b //= 2
+            if b == 0:
+                break
+            a *= a
+        if recip:
+            return 1.0 / r if r != 0.0 else float('inf')
+        return r
+
+    for a in (0.5, 0.9375, 1.0625, 16.0 / 15.5, 0.999):
+        for b in (0, 1, -1, 2, 3, -7, 100, -1234, 5000):
+            assert L.orc_powi(a, b) == powidf2(a, b)
