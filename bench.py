@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the replica engine (BASELINE.json metric:
+"SSE vertex updates/sec and classical spin-flips/sec at 1/2/4/8 B200 vs host CPU").
+
+Primary line: SSE TFIM config #3 (2D square L=32, J=-1, Gamma=3.04, beta=16, 4096 replicas per GPU,
+diagonal + cluster update), metric = vertex updates / s.  The same JSON line carries a nested
+"classical" object for config #2 (L=1024, 256 replicas per GPU, checkerboard Metropolis at T_c) with
+its own value / roofline / e2e / cpu_baseline.  One step = one sweep of every replica (SSE) or
+`--cls-sweeps-per-step` sweeps (classical).
+
+  python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA, through the C ABI)
+  python bench.py --impl reference [...]                     CPU arm: the oracle port of the
+                                                             reference algorithm on all host cores
+Under torchrun (N > 1): one rank per GPU, replicas are sharded (weak scaling), no data-path
+collective; rank 0 prints the line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SSE = dict(L=32, J=-1.0, gamma=3.04, h=0.0, beta=16.0, replicas=4096, cutoff0=1024, key0=0x55E00000)
+CLS = dict(L=1024, J=-1.0, beta=0.44068679350977147, replicas=256, key0=0xB2000000)
+SURVEY_CLS_BYTES_PER_FLIP = 2.0  # reference Vec<bool>, 1 B read + 1 B write per spin and sweep
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    elif n_gpus > 1:
+        raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def barrier_sync(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    import torch
+
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world):
+    import torch
+
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------
+# SSE arm (ours)
+# ---------------------------------------------------------------------------------------------
+def bench_sse(args, world, rank, local):
+    import torch
+
+    from isingmontecarlo_b200 import MODE_FAST, MODE_STRICT, lattices
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    c = dict(SSE)
+    if args.sse_replicas:
+        c["replicas"] = args.sse_replicas
+    edges = lattices.square_periodic(c["L"], c["J"])
+    R = c["replicas"]
+    keys = c["key0"] + rank * R + np.arange(R, dtype=np.uint64)
+    g = QmcIsingGraph(edges, c["gamma"], c["h"], c["cutoff0"], keys, c["beta"], device=local, mode=MODE_FAST)
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    t0 = time.perf_counter()
+    g.timesteps(args.therm, c["beta"])  # thermalise (untimed): <n> plateaus after ~60 sweeps
+    therm_s = time.perf_counter() - t0
+    for _ in range(args.warmup):
+        g.enqueue_sweeps(1)
+    g.synchronize()
+    n_mean, m_mean = float(g.get_n().mean()), float(g.get_cutoff().mean())
+
+    # ---- device-timed region: K steps, inputs resident in HBM, CUDA events on the launch stream
+    sampler = ClockSampler(local)
+    launches0, vu0 = g.launch_count(), g.total_vertex_updates()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier_sync(world)
+    sampler.start()
+    ev[0].record()
+    for k in range(args.steps):
+        g.enqueue_sweeps(1)
+        ev[k + 1].record()
+    barrier_sync(world)
+    clocks = sampler.stop()
+    g.synchronize()
+    ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    vu = g.total_vertex_updates() - vu0
+    launches = g.launch_count() - launches0
+    t_max = max_over_ranks(ms, world)
+    vu_all = sum_over_ranks(float(vu), world)
+    value = vu_all / (t_max * 1e-3)
+
+    # ---- e2e: the public call with HOST buffers: betas in (H2D), energies + one state sample per
+    # replica out (D2H) every step
+    betas = np.full(R, c["beta"])
+    e2e_steps = max(3, min(args.steps, 10))
+    vu1 = g.total_vertex_updates()
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        g._betas = None  # force the per-step H2D of the inputs
+        samples, energies = g.timesteps_sample(1, betas, 1)
+    barrier_sync(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    vu_e2e = sum_over_ranks(float(g.total_vertex_updates() - vu1), world)
+    e2e = {"value": vu_e2e / e2e_s, "unit": "vertex_updates/s", "h2d_bytes_per_step": int(R * 8 * world),
+           "d2h_bytes_per_step": int((R * 8 + R * g.nvars) * world), "steps": e2e_steps,
+           "call": "QmcIsingGraph.timesteps_sample(1, betas, 1) -> qmcb_set_betas + qmcb_timesteps"}
+
+    # ---- roofline of the dominant kernel (k_sse_fast: one launch = one sweep of R replicas)
+    peak, peak_src = measured_peaks()
+    survey_bpu = 60.0 + 8.0 * (m_mean / n_mean)  # 8 M + 60 n bytes per sweep
+    layout_bpu = 16.0 * (m_mean / n_mean) + 8.0  # this layout: 2 passes x (4 B read + 4 B write) per slot + ~8 B/vertex union-find
+    units_per_launch = vu / max(launches, 1)
+    avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
+    ach = units_per_launch * survey_bpu / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_sse_fast", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src, "traffic": None, "bytes_per_unit": survey_bpu,
+                "bytes_per_unit_this_layout": layout_bpu,
+                "achieved_this_layout": units_per_launch * layout_bpu / avg_launch_s / 1e9,
+                "avg_launch_ms": avg_launch_s * 1e3, "units_per_launch": units_per_launch}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            roofline["traffic"] = json.load(f).get("k_sse_fast")
+
+    out = {"value": value, "ms_per_step": t_max / args.steps, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+           "clocks": clocks, "n_mean": n_mean, "cutoff_mean": m_mean, "therm_s": therm_s, "handle": g, "config": c}
+
+    # ---- STRICT (reference-order, bit-exact with the reference's update path) sample
+    if args.strict_sweeps > 0 and world == 1:
+        try:
+            g.set_mode(MODE_STRICT)
+            g.enqueue_sweeps(1)
+            g.synchronize()
+            vu2 = g.total_vertex_updates()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.enqueue_sweeps(args.strict_sweeps)
+            e1.record()
+            g.synchronize()
+            out["strict"] = {"value": (g.total_vertex_updates() - vu2) / (e0.elapsed_time(e1) * 1e-3), "unit": "vertex_updates/s",
+                             "sweeps": args.strict_sweeps, "note": "QMCB_MODE_STRICT: reference cluster numbering, sequential draws"}
+            g.set_mode(MODE_FAST)
+        except Exception as ex:  # e.g. out of memory for the link workspace
+            out["strict"] = {"error": str(ex)[:200]}
+    return out
+
+
+def cpu_baseline_sse(g, c, seconds_budget=12.0):
+    """Oracle port of the reference algorithm on all host cores, started from GPU-thermalised
+    configurations (dumped through the C ABI) so that M and n match the timed GPU state."""
+    from isingmontecarlo_b200 import lattices
+    from oracle import pyoracle as po
+
+    cores = po.max_threads()
+    edges = lattices.square_periodic(c["L"], c["J"])
+    keys, cursors, states = g.rng_keys(), g.rng_cursors(), g.state_ref()
+    reps = []
+    for r in range(cores):
+        ref = po.SseOracle(edges, c["gamma"], c["h"], int(g.get_cutoff()[r]), key=int(keys[r]), state=states[r])
+        ref.load_ops(g.dump_ops(r), states[r])
+        ref.set_cursor(int(cursors[r]))
+        reps.append(ref)
+    betas = [c["beta"]] * cores
+    t0 = time.perf_counter()
+    tot, _ = po.sse_batch_timesteps(reps, 2, betas, po.MODE_STRICT)
+    per2 = time.perf_counter() - t0
+    sweeps = int(max(4, min(400, seconds_budget / max(per2 / 2, 1e-3))))
+    t0 = time.perf_counter()
+    tot, _ = po.sse_batch_timesteps(reps, sweeps, betas, po.MODE_STRICT)
+    dt = time.perf_counter() - t0
+    return {"value": tot / dt, "unit": "vertex_updates/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} replicas (one per core, OpenMP) x {sweeps} sweeps of config #3 from GPU-thermalised strings, "
+                      f"reference order; oracle/oracle.c (the Rust reference cannot be built here)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# classical arm (ours)
+# ---------------------------------------------------------------------------------------------
+def bench_classical(args, world, rank, local):
+    import torch
+
+    from isingmontecarlo_b200 import lattices
+    from isingmontecarlo_b200.classical import GraphState
+
+    c = dict(CLS)
+    if args.cls_replicas:
+        c["replicas"] = args.cls_replicas
+    L, R = c["L"], c["replicas"]
+    edges = lattices.square_periodic(L, c["J"])
+    keys = c["key0"] + rank * R + np.arange(R, dtype=np.uint64)
+    g = GraphState(edges, np.zeros(L * L), keys, c["beta"], device=local)
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    spp = args.cls_sweeps_per_step
+    for _ in range(max(args.warmup, 3)):
+        g.enqueue_sweeps(spp)
+    g.synchronize()
+    launches0 = g.launch_count()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(world)
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        g.enqueue_sweeps(spp)
+    e1.record()
+    barrier_sync(world)
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    launches = g.launch_count() - launches0
+    flips = float(R) * L * L * spp * args.steps * world
+    value = flips / (ms * 1e-3)
+    # e2e: sweeps + energy / magnetisation read back to the host every step
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g.do_time_step(spp)
+        en, mg = g.get_energy(), g.magnetization()
+    barrier_sync(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    peak, peak_src = measured_peaks()
+    ach = value / world * SURVEY_CLS_BYTES_PER_FLIP / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_cls_square", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src, "traffic": None, "bytes_per_unit": SURVEY_CLS_BYTES_PER_FLIP,
+                "layout": "bit-packed colour planes (0.125 B/spin, 32 MiB per 256 replicas: L2-resident), so HBM does not bind; "
+                          "the kernel is integer-issue bound (Philox4x32-10, one 32-bit draw per site)",
+                "avg_launch_ms": ms / max(launches, 1)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            roofline["traffic"] = json.load(f).get("k_cls_square")
+    out = {"metric": "classical_spin_flips_per_sec", "value": value, "unit": "spin_flip_attempts/s", "ms_per_step": ms / args.steps,
+           "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+           "e2e": {"value": flips / e2e_s, "unit": "spin_flip_attempts/s", "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": int(16 * R * world),
+                   "call": f"GraphState.do_time_step({spp}) + get_energy() + magnetization()"},
+           "energy_per_site": float(np.mean(en) / (L * L)), "abs_magnetization": float(np.mean(np.abs(mg))),
+           "config": {"workload": f"classical 2D square L={L} J={c['J']} checkerboard Metropolis at T_c, {R} replicas/GPU",
+                      "sweeps_per_step": spp, "draw": "one 32-bit Philox4x32-10 word per site and sweep",
+                      "l2": "state is bit-packed and L2-resident by design (see roofline.layout)"}}
+    if rank == 0 and world == 1:
+        out["cpu_baseline"] = cpu_baseline_classical(c)
+    g.close()
+    return out
+
+
+def cpu_baseline_classical(c, seconds_budget=8.0, L=None):
+    from isingmontecarlo_b200 import lattices
+    from oracle import pyoracle as po
+
+    cores = po.max_threads()
+    L = 256 if L is None else L  # bounded sample: same rule/temperature, smaller lattice per core
+    edges = lattices.square_periodic(L, c["J"])
+    col = np.array([(i % L + i // L) & 1 for i in range(L * L)], dtype=np.uint32)
+    reps = [po.ClassicalOracle(edges, np.zeros(L * L), key=c["key0"] + r) for r in range(cores)]
+    betas = [c["beta"]] * cores
+    t0 = time.perf_counter()
+    po.cls_batch_checkerboard(reps, betas, col, 2)
+    per = (time.perf_counter() - t0) / 2
+    sweeps = int(max(4, min(2000, seconds_budget / 2 / max(per, 1e-4))))
+    t0 = time.perf_counter()
+    po.cls_batch_checkerboard(reps, betas, col, sweeps)
+    dt_cb = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    po.cls_batch_spin_flips(reps, betas, max(1, sweeps // 4) * L * L)
+    dt_rs = time.perf_counter() - t0
+    return {"value": cores * sweeps * L * L / dt_cb, "unit": "spin_flip_attempts/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} replicas x {sweeps} checkerboard sweeps of L={L} at T_c (oracle/oracle.c, OpenMP)",
+            "reference_schedule_value": cores * max(1, sweeps // 4) * L * L / dt_rs,
+            "reference_schedule_note": "GraphState::do_spin_flip random-site Metropolis (graph.rs:91-119), same cores"}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the oracle port on the host cores, no GPU engine anywhere on the path
+# ---------------------------------------------------------------------------------------------
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from isingmontecarlo_b200 import lattices  # edge-list builder only (pure Python)
+    from oracle import pyoracle as po
+
+    c = dict(SSE)
+    cores = po.max_threads()
+    edges = lattices.square_periodic(c["L"], c["J"])
+    reps = [po.SseOracle(edges, c["gamma"], c["h"], c["cutoff0"], key=c["key0"] + r) for r in range(cores)]
+    betas = [c["beta"]] * cores
+    po.sse_batch_timesteps(reps, args.ref_therm, betas, po.MODE_STRICT)  # thermalise on the CPU (untimed)
+    for _ in range(args.warmup):
+        po.sse_batch_timesteps(reps, 1, betas, po.MODE_STRICT)
+    tot = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        t, _ = po.sse_batch_timesteps(reps, 1, betas, po.MODE_STRICT)
+        tot += t
+    dt = time.perf_counter() - t0
+    value = tot / dt
+    cb = cpu_baseline_classical(dict(CLS), seconds_budget=6.0)
+    line = {"impl": "reference", "metric": "sse_vertex_updates_per_sec", "value": value, "unit": "vertex_updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+u64", "data": "synthetic",
+            "config": {"workload": f"SSE TFIM 2D square L={c['L']} beta={c['beta']} Gamma={c['gamma']} (config #3), "
+                                   f"bounded sample: {cores} replicas, one per host core"},
+            "cpu_baseline": {"value": value, "unit": "vertex_updates/s", "cores": cores, "kind": "port",
+                             "sample": f"{cores} replicas x {args.steps} sweeps after {args.ref_therm} thermalisation sweeps, "
+                                       "oracle/oracle.c restatement of the Rust reference (no Rust toolchain in this image)"},
+            "e2e": {"value": value, "unit": "vertex_updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "classical": {"metric": "classical_spin_flips_per_sec", "value": cb["value"], "unit": cb["unit"], "cpu_baseline": cb}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="both", choices=["both", "sse", "classical"])
+    ap.add_argument("--therm", type=int, default=120, help="untimed SSE thermalisation sweeps (GPU arm)")
+    ap.add_argument("--ref-therm", type=int, default=80, help="untimed thermalisation sweeps of the CPU arm")
+    ap.add_argument("--strict-sweeps", type=int, default=2)
+    ap.add_argument("--sse-replicas", type=int, default=0)
+    ap.add_argument("--cls-replicas", type=int, default=0)
+    ap.add_argument("--cls-sweeps-per-step", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        bench_reference(args)
+        return
+
+    world, rank, local = dist_setup(args.gpus)
+    line = {"metric": "sse_vertex_updates_per_sec", "unit": "vertex_updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+u64",
+            "data": "synthetic"}
+    if args.workload in ("both", "sse"):
+        s = bench_sse(args, world, rank, local)
+        g, c = s.pop("handle"), s.pop("config")
+        line.update({k: s[k] for k in ("value", "ms_per_step", "gpu_launches", "e2e", "roofline", "clocks")})
+        line["config"] = {"workload": f"SSE TFIM 2D square L={c['L']} J={c['J']} Gamma={c['gamma']} beta={c['beta']} "
+                                      f"(BASELINE config #3), {c['replicas']} replicas/GPU, diagonal + cluster update, FAST cluster order",
+                          "replicas_per_gpu": c["replicas"], "mean_n": s["n_mean"], "mean_cutoff": s["cutoff_mean"],
+                          "thermalisation_sweeps": args.therm, "l2": "inputs larger than L2 (operator strings: "
+                          f"{c['replicas'] * s['cutoff_mean'] * 4 / 2**30:.1f} GiB per GPU)", "parallelism": f"replicas x{world}"}
+        if "strict" in s:
+            line["strict"] = s["strict"]
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sse(g, c)
+        g.close()
+    if args.workload in ("both", "classical"):
+        cl = bench_classical(args, world, rank, local)
+        if args.workload == "classical":
+            line.update({k: cl[k] for k in ("metric", "value", "unit", "ms_per_step", "gpu_launches", "e2e", "roofline", "clocks", "config")})
+            if "cpu_baseline" in cl:
+                line["cpu_baseline"] = cl["cpu_baseline"]
+        else:
+            line["classical"] = cl
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,180 @@
+/*
+ * qmcb.h -- C ABI of the B200-native replica engine (libqmcb.so).
+ *
+ * This is the drop-in boundary for the data-parallel hot path of Renmusxd/IsingMonteCarlo
+ * (crate `qmc` 2.20.0).  The reference is pure safe Rust with no FFI of its own, so each entry
+ * point below names the reference interface it replaces (file:line into the reference tree);
+ * INTEGRATION.md shows the `-sys` crate binding a maintainer would add.  One handle is a BATCH:
+ * R independent replicas (chains / tempering temperatures) of one lattice, resident on one GPU.
+ *
+ * Conventions: plain pointers and sizes only; every function returns QMCB_OK (0) or a negative
+ * QmcbStatus and never aborts or throws; `qmcb_last_error()` gives the message of the last
+ * failure on the calling thread.  Host pointers unless a name ends in `_dev`.  A handle is not
+ * thread-safe; distinct handles may be used from distinct threads.  There is no CPU fallback:
+ * creating a handle without a CUDA device fails with QMCB_ERR_CUDA.
+ */
+#ifndef QMCB_H
+#define QMCB_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    QMCB_OK = 0,
+    QMCB_ERR_BAD_ARG = -1,
+    QMCB_ERR_CAPACITY = -2, /* operator string would outgrow `capacity` (see qmcb_create) */
+    QMCB_ERR_CUDA = -3,
+    QMCB_ERR_UNSUPPORTED = -4,
+    QMCB_ERR_INTERNAL = -5 /* a device-side invariant failed (reference: unreachable!/panic) */
+} QmcbStatus;
+
+/* Cluster-update order (DESIGN.md "Two orders").
+ * STRICT: clusters are numbered in the reference's LIFO discovery order and draw k of the block
+ *         goes to cluster k (cluster.rs:57-97,129-137) -- bit-exact with the reference's update
+ *         path under the same injected stream.
+ * FAST:   clusters are keyed by their smallest segment id and flip on a counter-based Philox bit;
+ *         same Markov kernel, labelled by a parallel union-find.  Bit-exact with the oracle's
+ *         FAST mode; statistically equivalent to STRICT. */
+#define QMCB_MODE_STRICT 0
+#define QMCB_MODE_FAST 1
+
+/* Operator word (one uint32 per slot p of the operator string; replaces BasicOp,
+ * op_container.rs:224-237): bits 0..23 bond index, bits 24,25 input spins of leg 0,1,
+ * bits 26,27 output spins, bits 28..31 zero.  The identity is QMCB_OP_EMPTY.  vars / nvars /
+ * `constant` are functions of the bond index exactly as in qmc_ising.rs:671-681:
+ * [0,E) two-site bonds, [E,E+N) transverse ops, [E+N,E+2N) longitudinal ops. */
+#define QMCB_OP_EMPTY 0xFFFFFFFFu
+
+typedef struct {
+    uint32_t nvars;      /* N; qmc_ising.rs:92 (max index + 1) */
+    uint32_t nedges;     /* E */
+    const uint32_t *va;  /* [E] first variable of each edge */
+    const uint32_t *vb;  /* [E] second variable */
+    const double *J;     /* [E] coupling; H = sum J sz sz - Gamma sum sx - h sum sz */
+    double transverse;   /* Gamma >= 0 */
+    double longitudinal; /* h */
+} QmcbLattice;
+
+typedef struct QmcbHandle QmcbHandle;
+
+/* ---- construction: QmcIsingGraph::new_with_rng (qmc_ising.rs:131-148, :80-128) ---------- */
+/* betas[R]; rng_keys[R]: Philox4x32-10 key of each replica's injected stream (word c of the
+ * stream is what a Rust `RngCore::next_u64` shim returns on its c-th call).
+ * cutoff0: initial cutoff M (reference `cutoff` argument).  capacity: slots allocated per replica
+ * (>= cutoff0; 0 = choose automatically and grow on demand).  init_state: [R*N] bytes (0/1) or
+ * NULL to draw it from each stream as make_random_spin_state does (classical/graph.rs:451-453).
+ * device: CUDA ordinal. */
+int qmcb_create(const QmcbLattice *lattice, uint32_t n_replicas, const double *betas,
+                const uint64_t *rng_keys, uint64_t cutoff0, uint64_t capacity,
+                const uint8_t *init_state, int device, QmcbHandle **out);
+int qmcb_destroy(QmcbHandle *h);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = handle's own stream */
+int qmcb_set_stream(QmcbHandle *h, void *cuda_stream);
+int qmcb_set_mode(QmcbHandle *h, int mode);
+int qmcb_get_mode(const QmcbHandle *h, int *mode);
+/* tuning knobs; "impl": 0 = warp-parallel kernels where available (default), 1 = serial-order kernels only */
+int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value);
+int qmcb_set_betas(QmcbHandle *h, const double *betas);
+int qmcb_get_betas(const QmcbHandle *h, double *betas);
+int qmcb_num_replicas(const QmcbHandle *h, uint32_t *r);
+int qmcb_num_vars(const QmcbHandle *h, uint32_t *n);
+int qmcb_num_bonds(const QmcbHandle *h, uint32_t *nb); /* qmc_ising.rs:664-670 */
+
+/* ---- stepping: QmcStepper (qmc_stepper.rs:2-168) ---------------------------------------- */
+/* timesteps_measure_with_self (qmc_stepper.rs:133-162): t sweeps (QmcIsingGraph::timestep,
+ * qmc_ising.rs:644-795) of every replica at its beta; after sweep i (1-based) with
+ * i % sampling_freq == 0 the state is sampled and n accumulated.  energy_out[R] (or NULL) gets
+ * -(mean n)/beta + offset (qmc_ising.rs:805-809; NaN if nothing was sampled, as the reference).
+ * samples_out (or NULL): [R][t / sampling_freq][N] bytes, the `Vec<Vec<bool>>` of
+ * timesteps_sample (qmc_stepper.rs:23-40).  sampling_freq 0 means 1. */
+int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t sampling_freq, double *energy_out,
+                   uint8_t *samples_out);
+/* launch-only variant: enqueue t sweeps on the handle's stream and return without synchronising
+ * (for device-side timing); energy of these sweeps is folded into the next qmcb_timesteps call
+ * only through the vertex-update counter below. */
+int qmcb_enqueue_sweeps(QmcbHandle *h, uint64_t t);
+int qmcb_synchronize(QmcbHandle *h);
+/* single_diagonal_step / single_cluster_step (qmc_ising.rs:208-270, :273-320) */
+int qmcb_single_diagonal_step(QmcbHandle *h);
+int qmcb_single_cluster_step(QmcbHandle *h, uint64_t *n_clusters_out /* [R] or NULL */);
+/* sum over replicas and sweeps so far of n after each sweep (the metric's "vertex updates") */
+int qmcb_total_vertex_updates(QmcbHandle *h, uint64_t *total);
+/* number of kernels this handle has launched so far */
+int qmcb_launch_count(const QmcbHandle *h, uint64_t *launches);
+
+/* ---- accessors (qmc_ising.rs:496-560, qmc_stepper.rs:5-14) ------------------------------- */
+int qmcb_get_state(QmcbHandle *h, uint32_t r, uint8_t *state /* [N] */);   /* state_ref */
+int qmcb_get_states(QmcbHandle *h, uint8_t *states /* [R*N] */);
+int qmcb_set_state(QmcbHandle *h, uint32_t r, const uint8_t *state);
+int qmcb_get_n(QmcbHandle *h, uint64_t *n /* [R] */);                       /* get_n */
+int qmcb_get_cutoffs(QmcbHandle *h, uint64_t *cutoffs /* [R] */);          /* get_cutoff */
+int qmcb_set_cutoff(QmcbHandle *h, uint32_t r, uint64_t cutoff);           /* set_cutoff :537-540 */
+int qmcb_get_capacity(const QmcbHandle *h, uint64_t *capacity);
+int qmcb_get_offset(const QmcbHandle *h, double *offset);                  /* get_offset */
+int qmcb_get_bond_counts(QmcbHandle *h, uint32_t r, uint64_t *counts /* [num_bonds] */);
+int qmcb_get_rng_cursors(QmcbHandle *h, uint64_t *cursors /* [R] */);
+int qmcb_set_rng_cursor(QmcbHandle *h, uint32_t r, uint64_t cursor);
+int qmcb_get_rng_keys(QmcbHandle *h, uint64_t *keys /* [R] */);
+/* operator string of replica r in p order, nwords >= cutoff(r) entries are written */
+int qmcb_dump_ops(QmcbHandle *h, uint32_t r, uint32_t *opwords, uint64_t nwords);
+/* FastOps::new_from_ops (fast_ops.rs:80-87): install a string (and state if non-NULL) */
+int qmcb_load_ops(QmcbHandle *h, uint32_t r, const uint32_t *opwords, uint64_t nwords,
+                  const uint8_t *state);
+/* OpContainer::verify + QmcIsingGraph::verify (op_container.rs:137-159, qmc_ising.rs:829-860),
+ * replayed on the device; *ok = 1 iff the invariant holds for replica r. */
+int qmcb_verify(QmcbHandle *h, uint32_t r, int *ok);
+/* cluster ids per slot of the last STRICT cluster step (tests of cluster numbering) */
+int qmcb_get_boundaries(QmcbHandle *h, uint32_t r, uint32_t *b_in, uint32_t *b_out, uint64_t nslots);
+
+/* ---- parallel tempering: TemperingContainer (tempering_container.rs:19-302) -------------- */
+/* The handle's R replicas are `n_chains` independent ladders of `n_betas` slots each
+ * (slot s = chain * n_betas + k).  On several GPUs each rank holds a contiguous block of the
+ * global slot range [slot_begin, slot_begin + R); ranks exchange only (n, cursor, cutoff) per slot.
+ * A swap exchanges the slot LABELS (beta, rng key, rng cursor) of two configurations instead of
+ * moving operator strings (equivalent to swap_manager_and_state, qmc_ising.rs:593-602). */
+int qmcb_pt_configure(QmcbHandle *h, uint32_t n_chains_global, uint32_t n_betas,
+                      uint32_t slot_begin, const double *betas_global /* [n_chains*n_betas] */,
+                      const uint64_t *keys_global, uint64_t pt_key);
+/* step 1 of tempering_step: write this rank's per-configuration record for the all-gather;
+ * rec_dev is DEVICE memory, [R] records of 4 x uint64: {slot, n, cursor, cutoff}. */
+int qmcb_pt_export(QmcbHandle *h, uint64_t *rec_dev);
+/* step 2: given ALL ranks' records (device, [n_chains*n_betas] records in any order), set every
+ * cutoff to the global max (tempering_container.rs:129-137), evaluate the swaps of every ladder
+ * from the shared PT stream (:140-146, :241-302) and relabel the local configurations. */
+int qmcb_pt_apply(QmcbHandle *h, const uint64_t *all_rec_dev, uint64_t n_records);
+int qmcb_pt_total_swaps(QmcbHandle *h, uint64_t *swaps); /* get_total_swaps :231-233 */
+int qmcb_pt_get_slots(QmcbHandle *h, uint32_t *slots /* [R] current slot of each configuration */);
+
+/* ---- classical graph: GraphState (classical/graph.rs:56-88, :350-447) --------------------- */
+typedef struct CmcbHandle CmcbHandle;
+/* edges + biases as GraphState::new (graph.rs:56-88); init_state [R*N] or NULL (stream-drawn). */
+int cmcb_create(const QmcbLattice *lattice /* transverse/longitudinal ignored */,
+                const double *biases /* [N] */, uint32_t n_replicas, const double *betas,
+                const uint64_t *rng_keys, const uint8_t *init_state, int device, CmcbHandle **out);
+int cmcb_destroy(CmcbHandle *h);
+int cmcb_set_stream(CmcbHandle *h, void *cuda_stream);
+/* nsweeps checkerboard sweeps: every site once per sweep, colour by colour, with the reference's
+ * per-site rule (do_spin_flip delta_e graph.rs:98-115, should_flip :339-347). */
+int cmcb_sweeps(CmcbHandle *h, uint64_t nsweeps);
+int cmcb_enqueue_sweeps(CmcbHandle *h, uint64_t nsweeps);
+int cmcb_synchronize(CmcbHandle *h);
+int cmcb_get_state(CmcbHandle *h, uint32_t r, uint8_t *state);
+int cmcb_get_states(CmcbHandle *h, uint8_t *states /* [R*N] */);
+int cmcb_set_states(CmcbHandle *h, const uint8_t *states /* [R*N] */);
+int cmcb_energy(CmcbHandle *h, double *energy /* [R] */);               /* get_energy :430-447 */
+int cmcb_magnetization(CmcbHandle *h, double *m /* [R], mean of +-1 */);
+int cmcb_get_colours(const CmcbHandle *h, uint32_t *colours /* [N] */, uint32_t *ncolours);
+int cmcb_get_sweep_count(const CmcbHandle *h, uint64_t *sweeps);
+int cmcb_set_sweep_count(CmcbHandle *h, uint64_t sweeps);
+int cmcb_layout(const CmcbHandle *h, int *is_bitpacked_square);
+int cmcb_launch_count(const CmcbHandle *h, uint64_t *launches);
+
+const char *qmcb_last_error(void);
+const char *qmcb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,107 @@
+"""Host-side mirror of `qmc::classical::graph::GraphState` (classical/graph.rs:56-88, :350-447) for
+a batch of replicas swept with the checkerboard schedule."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+from .sse import _lattice
+
+
+class GraphState:
+    def __init__(self, edges, biases, rng_keys, betas, state=None, device=0):
+        L = _lib.load()
+        self._L = L
+        bz = np.ascontiguousarray(biases, dtype=np.float64)
+        self.nvars = len(bz)
+        keys = np.ascontiguousarray(rng_keys, dtype=np.uint64)
+        self.R = len(keys)
+        b = np.ascontiguousarray(np.broadcast_to(np.asarray(betas, dtype=np.float64), (self.R,)))
+        lat, self._keep = _lattice(edges, 0.0, 0.0, self.nvars)
+        st = None
+        if state is not None:
+            st = np.ascontiguousarray(np.broadcast_to(np.asarray(state, dtype=np.uint8), (self.R, self.nvars)))
+        h = C.c_void_p()
+        check(L.cmcb_create(C.byref(lat), ptr(bz, C.c_double), self.R, ptr(b, C.c_double), ptr(keys, C.c_uint64),
+                            None if st is None else ptr(st, C.c_uint8), device, C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def new(cls, edges, biases, rng_keys, betas, **kw):
+        return cls(edges, biases, rng_keys, betas, **kw)
+
+    @classmethod
+    def new_with_state_and_rng(cls, state, edges, biases, rng_keys, betas, **kw):
+        return cls(edges, biases, rng_keys, betas, state=state, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cmcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        check(self._L.cmcb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def do_time_step(self, nsweeps=1):
+        """One checkerboard sweep = every site once (the reference's do_time_step makes N/2 random
+        single-spin attempts, graph.rs:350-406; the schedule differs, the per-site rule does not)."""
+        check(self._L.cmcb_sweeps(self._h, int(nsweeps)))
+
+    sweeps = do_time_step
+
+    def enqueue_sweeps(self, nsweeps):
+        check(self._L.cmcb_enqueue_sweeps(self._h, int(nsweeps)))
+
+    def synchronize(self):
+        check(self._L.cmcb_synchronize(self._h))
+
+    def state_ref(self):
+        out = np.zeros((self.R, self.nvars), dtype=np.uint8)
+        check(self._L.cmcb_get_states(self._h, ptr(out, C.c_uint8)))
+        return out
+
+    clone_state = get_state = state_ref
+
+    def set_state(self, states):
+        st = np.ascontiguousarray(np.broadcast_to(np.asarray(states, dtype=np.uint8), (self.R, self.nvars)))
+        check(self._L.cmcb_set_states(self._h, ptr(st, C.c_uint8)))
+
+    def get_energy(self):
+        out = np.zeros(self.R, dtype=np.float64)
+        check(self._L.cmcb_energy(self._h, ptr(out, C.c_double)))
+        return out
+
+    def magnetization(self):
+        out = np.zeros(self.R, dtype=np.float64)
+        check(self._L.cmcb_magnetization(self._h, ptr(out, C.c_double)))
+        return out
+
+    def colours(self):
+        col = np.zeros(self.nvars, dtype=np.uint32)
+        n = C.c_uint32()
+        check(self._L.cmcb_get_colours(self._h, ptr(col, C.c_uint32), C.byref(n)))
+        return col, n.value
+
+    def sweep_count(self):
+        s = C.c_uint64()
+        check(self._L.cmcb_get_sweep_count(self._h, C.byref(s)))
+        return s.value
+
+    def is_bitpacked_square(self):
+        s = C.c_int()
+        check(self._L.cmcb_layout(self._h, C.byref(s)))
+        return bool(s.value)
+
+    def launch_count(self):
+        t = C.c_uint64()
+        check(self._L.cmcb_launch_count(self._h, C.byref(t)))
+        return t.value

@@ -1,0 +1,1120 @@
+// api.cu -- the C ABI of include/qmcb.h: handle management, host<->device staging, launches.
+// No CPU fallback: every entry point needs a CUDA device and fails with QMCB_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/qmcb.h"
+#include "classical.cuh"
+#include "pt.cuh"
+#include "sse.cuh"
+
+// kernels (sse_serial.cu, sse_fast.cu, classical.cu, pt.cu)
+void launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phases, uint64_t sample_freq,
+                       uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);
+void launch_sse_verify(const SseDev &D, uint32_t r, int *ok_dev, uint32_t *scratch_dev, cudaStream_t st);
+void launch_sse_bond_counts(const SseDev &D, uint32_t r, unsigned long long *counts_dev, cudaStream_t st);
+void launch_sse_recount(const SseDev &D, uint32_t r, cudaStream_t st);
+void launch_sse_init_state(const SseDev &D, cudaStream_t st);
+int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
+                    uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
+void launch_pt_export(const SseDev &D, const PtDev &P, uint64_t *rec, cudaStream_t st);
+void launch_pt_apply(const SseDev &D, const PtDev &P, const uint64_t *rec, uint32_t S, cudaStream_t st);
+void launch_cls_generic(const ClsDev &D, uint32_t colour, uint32_t cstart, uint32_t ccount, uint64_t sweep, cudaStream_t st);
+void launch_cls_square(const ClsDev &D, uint32_t colour, uint64_t sweep, cudaStream_t st);
+void launch_cls_square_measure(const ClsDev &D, unsigned long long *unsat, unsigned long long *up, cudaStream_t st);
+void launch_cls_square_pack(const ClsDev &D, const uint8_t *bytes, cudaStream_t st);
+void launch_cls_square_unpack(const ClsDev &D, uint8_t *bytes, cudaStream_t st);
+void launch_cls_init_bytes(const ClsDev &D, uint8_t *bytes, cudaStream_t st);
+void launch_cls_generic_energy(const ClsDev &D, const double *adj_j, const double *biases, double *energy, double *mag, cudaStream_t st);
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+static int fail_cuda(cudaError_t e, const char *expr, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, expr);
+    g_err = buf;
+    cudaGetLastError();
+    return QMCB_ERR_CUDA;
+}
+
+extern "C" const char *qmcb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *qmcb_version(void) { return "isingmontecarlo_b200 0.1 (sm_100a)"; }
+
+struct Pool {  // owns device allocations of one handle
+    std::vector<void *> ptrs;
+    template <typename T>
+    cudaError_t alloc(T **out, size_t count) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = (T *)p;
+        return e;
+    }
+    void release(void *p) {
+        if (!p) return;
+        auto it = std::find(ptrs.begin(), ptrs.end(), p);
+        if (it != ptrs.end()) ptrs.erase(it);
+        cudaFree(p);
+    }
+    void release_all() {
+        for (void *p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+// =============================================================================================
+// SSE handle
+// =============================================================================================
+struct QmcbHandle {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    SseDev D{};
+    Pool pool;
+    int mode = QMCB_MODE_STRICT;
+    int impl = 0;  // 0 auto (warp-parallel FAST kernels where supported), 1 serial kernels only
+    double offset = 0.0;
+    uint64_t target = 0;  // sweeps requested so far
+    uint64_t launches = 0;
+    bool strict_ws = false, fast_ws = false;
+    bool auto_capacity = false;
+    double beta_max = 0.0;
+    // tempering
+    bool pt_on = false;
+    PtDev P{};
+    uint32_t pt_S = 0;
+};
+
+#define CHECK_H(h)                                              \
+    if (!(h)) return fail(QMCB_ERR_BAD_ARG, "null handle");     \
+    CUDA_TRY(cudaSetDevice((h)->device))
+
+static size_t bits_stride(const SseDev &D) { return (size_t)(D.cap / 32 + 2 + D.N / 32); }
+
+static int alloc_strict_ws(QmcbHandle *h) {
+    if (h->strict_ws) return QMCB_OK;
+    SseDev &D = h->D;
+    CUDA_TRY(h->pool.alloc(&D.links, (size_t)D.R * D.cap * 4));
+    CUDA_TRY(h->pool.alloc(&D.bounds, (size_t)D.R * D.cap * 2));
+    CUDA_TRY(h->pool.alloc(&D.frontier, (size_t)D.R * (2 * D.cap + 16)));
+    CUDA_TRY(h->pool.alloc(&D.interior, (size_t)D.R * (4 * D.cap + 16)));
+    h->strict_ws = true;
+    return QMCB_OK;
+}
+static int alloc_fast_ws(QmcbHandle *h) {
+    if (h->fast_ws) return QMCB_OK;
+    SseDev &D = h->D;
+    CUDA_TRY(h->pool.alloc(&D.parent, (size_t)D.R * (D.N + D.cap + 1)));
+    h->fast_ws = true;
+    return QMCB_OK;
+}
+
+// re-layout every per-slot array for a larger per-replica capacity
+static int grow(QmcbHandle *h, uint64_t newcap) {
+    SseDev &D = h->D;
+    if (newcap <= D.cap) return QMCB_OK;
+    if (newcap >= (1ull << 29)) return fail(QMCB_ERR_CAPACITY, "operator string capacity above 2^29 slots per replica");
+    uint32_t *nops = nullptr;
+    cudaError_t e = h->pool.alloc(&nops, (size_t)D.R * newcap);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(QMCB_ERR_CAPACITY, "out of device memory while growing the operator strings");
+    }
+    CUDA_TRY(cudaMemsetAsync(nops, 0xFF, (size_t)D.R * newcap * 4, h->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(nops, newcap * 4, D.ops, D.cap * 4, D.cap * 4, D.R, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->pool.release(D.ops);
+    D.ops = nops;
+    const bool s = h->strict_ws, f = h->fast_ws;
+    h->pool.release(D.links), h->pool.release(D.bounds), h->pool.release(D.frontier), h->pool.release(D.interior);
+    h->pool.release(D.parent), h->pool.release(D.bits), h->pool.release(D.frozen);
+    D.links = D.bounds = D.frontier = D.interior = D.parent = D.bits = D.frozen = nullptr;
+    h->strict_ws = h->fast_ws = false;
+    D.cap = newcap;
+    CUDA_TRY(h->pool.alloc(&D.bits, (size_t)D.R * bits_stride(D)));
+    CUDA_TRY(h->pool.alloc(&D.frozen, (size_t)D.R * bits_stride(D)));
+    if (s) {
+        int rc = alloc_strict_ws(h);
+        if (rc) return rc;
+    }
+    if (f) {
+        int rc = alloc_fast_ws(h);
+        if (rc) return rc;
+    }
+    return QMCB_OK;
+}
+
+static int check_status(QmcbHandle *h, int *status_out) {
+    int st = 0;
+    CUDA_TRY(cudaMemcpyAsync(&st, h->D.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *status_out = st;
+    return QMCB_OK;
+}
+
+static int status_to_error(int st) {
+    if (st & DEV_ERR_INVARIANT) return fail(QMCB_ERR_INTERNAL, "device invariant failed in the cluster update (reference: unreachable!)");
+    if (st & DEV_ERR_STACK) return fail(QMCB_ERR_INTERNAL, "cluster stack overflow");
+    if (st & DEV_ERR_PROB) return fail(QMCB_ERR_INTERNAL, "acceptance probability outside [0,1] (reference: gen_bool panics)");
+    return QMCB_OK;
+}
+
+static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t origin, uint8_t *samples_dev, uint64_t spr) {
+    int rc;
+    if (h->mode == QMCB_MODE_STRICT) {
+        if ((rc = alloc_strict_ws(h))) return rc;
+        launch_sse_serial(h->D, 0, h->target, phases, freq, origin, samples_dev, spr, h->stream);
+        h->launches += 1;
+    } else {
+        if ((rc = alloc_fast_ws(h))) return rc;
+        int nl = h->impl == 1 ? -1 : launch_sse_fast(h->D, h->target, phases, freq, origin, samples_dev, spr, h->stream);
+        if (nl < 0) {
+            launch_sse_serial(h->D, 1, h->target, phases, freq, origin, samples_dev, spr, h->stream);
+            nl = 1;
+        }
+        h->launches += (uint64_t)nl;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return QMCB_OK;
+}
+
+// run until every replica reached h->target, growing the arrays when a cutoff outgrows them
+static int run_to_target(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t origin, uint8_t *samples_dev, uint64_t spr) {
+    for (int attempt = 0; attempt < 64; attempt++) {
+        int rc = launch_sweeps(h, phases, freq, origin, samples_dev, spr);
+        if (rc) return rc;
+        int st = 0;
+        if ((rc = check_status(h, &st))) return rc;
+        if ((rc = status_to_error(st))) return rc;
+        if (!(st & DEV_ERR_CAPACITY)) return QMCB_OK;
+        if (!h->auto_capacity) return fail(QMCB_ERR_CAPACITY, "cutoff outgrew the capacity given to qmcb_create");
+        std::vector<uint32_t> M(h->D.R);
+        CUDA_TRY(cudaMemcpy(M.data(), h->D.M, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
+        uint64_t need = *std::max_element(M.begin(), M.end());
+        CUDA_TRY(cudaMemsetAsync(h->D.status, 0, sizeof(int), h->stream));
+        if ((rc = grow(h, need + need / 2 + 1024))) return rc;
+    }
+    return fail(QMCB_ERR_INTERNAL, "capacity growth did not converge");
+}
+
+extern "C" int qmcb_create(const QmcbLattice *lat, uint32_t R, const double *betas, const uint64_t *keys, uint64_t cutoff0,
+                           uint64_t capacity, const uint8_t *init_state, int device, QmcbHandle **out) {
+    if (!lat || !betas || !keys || !out || R == 0) return fail(QMCB_ERR_BAD_ARG, "null argument or zero replicas");
+    if (lat->nvars == 0) return fail(QMCB_ERR_BAD_ARG, "lattice without variables");
+    if (lat->nedges && (!lat->va || !lat->vb || !lat->J)) return fail(QMCB_ERR_BAD_ARG, "edge arrays missing");
+    if (!(lat->transverse >= 0.0)) return fail(QMCB_ERR_BAD_ARG, "transverse field must be >= 0");
+    for (uint32_t e = 0; e < lat->nedges; e++)
+        if (lat->va[e] >= lat->nvars || lat->vb[e] >= lat->nvars || lat->va[e] == lat->vb[e])
+            return fail(QMCB_ERR_BAD_ARG, "edge endpoint out of range or self-loop");
+    if ((uint64_t)lat->nedges + 2ull * lat->nvars >= (1u << 24)) return fail(QMCB_ERR_BAD_ARG, "bond index does not fit 24 bits");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(QMCB_ERR_CUDA, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    QmcbHandle *h = new QmcbHandle();
+    h->device = device;
+    SseDev &D = h->D;
+    D.N = lat->nvars, D.E = lat->nedges, D.Nw = (lat->nvars + 31) / 32;
+    D.has_h = std::fabs(lat->longitudinal) > DBL_EPSILON;
+    D.Nb = D.E + D.N + (D.has_h ? D.N : 0);
+    D.gamma = lat->transverse, D.h = lat->longitudinal;
+    D.R = R;
+    double edge_offset = 0.0;  // qmc_ising.rs:97-99
+    for (uint32_t e = 0; e < lat->nedges; e++) edge_offset += std::fabs(lat->J[e]);
+    h->offset = edge_offset + (double)lat->nvars * (lat->transverse + std::fabs(lat->longitudinal));
+    for (uint32_t r = 0; r < R; r++) h->beta_max = std::max(h->beta_max, betas[r]);
+    h->auto_capacity = capacity == 0;
+    if (capacity == 0) capacity = std::max<uint64_t>(cutoff0, (uint64_t)(3.2 * h->beta_max * h->offset) + 1024);
+    if (capacity < cutoff0) {
+        delete h;
+        return fail(QMCB_ERR_BAD_ARG, "capacity smaller than the initial cutoff");
+    }
+    capacity = (capacity + 31) / 32 * 32;
+    D.cap = capacity;
+#define TRYC(expr)                                   \
+    do {                                             \
+        cudaError_t e_ = (expr);                     \
+        if (e_ != cudaSuccess) {                     \
+            h->pool.release_all();                   \
+            delete h;                                \
+            return fail_cuda(e_, #expr, __FILE__, __LINE__); \
+        }                                            \
+    } while (0)
+    TRYC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    uint32_t *va, *vb;
+    double *J;
+    TRYC(h->pool.alloc(&va, D.E));
+    TRYC(h->pool.alloc(&vb, D.E));
+    TRYC(h->pool.alloc(&J, D.E));
+    TRYC(cudaMemcpy(va, lat->va, sizeof(uint32_t) * D.E, cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(vb, lat->vb, sizeof(uint32_t) * D.E, cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(J, lat->J, sizeof(double) * D.E, cudaMemcpyHostToDevice));
+    D.va = va, D.vb = vb, D.J = J;
+    TRYC(h->pool.alloc(&D.ops, (size_t)R * D.cap));
+    TRYC(cudaMemset(D.ops, 0xFF, (size_t)R * D.cap * 4));
+    TRYC(h->pool.alloc(&D.state, (size_t)R * D.Nw));
+    TRYC(cudaMemset(D.state, 0, (size_t)R * D.Nw * 4));
+    TRYC(h->pool.alloc(&D.n, R));
+    TRYC(cudaMemset(D.n, 0, sizeof(uint32_t) * R));
+    TRYC(h->pool.alloc(&D.M, R));
+    TRYC(h->pool.alloc(&D.cursor, R));
+    TRYC(cudaMemset(D.cursor, 0, sizeof(uint64_t) * R));
+    TRYC(h->pool.alloc(&D.key, R));
+    TRYC(h->pool.alloc(&D.beta, R));
+    TRYC(h->pool.alloc(&D.done, R));
+    TRYC(cudaMemset(D.done, 0, sizeof(uint64_t) * R));
+    TRYC(h->pool.alloc(&D.sum_n, R));
+    TRYC(cudaMemset(D.sum_n, 0, sizeof(uint64_t) * R));
+    TRYC(h->pool.alloc(&D.vupd, R));
+    TRYC(cudaMemset(D.vupd, 0, sizeof(uint64_t) * R));
+    TRYC(h->pool.alloc(&D.ncl, R));
+    TRYC(cudaMemset(D.ncl, 0, sizeof(uint32_t) * R));
+    TRYC(h->pool.alloc(&D.ends, (size_t)R * 4));
+    TRYC(cudaMemset(D.ends, 0xFF, sizeof(uint32_t) * R * 4));
+    TRYC(h->pool.alloc(&D.status, 1));
+    TRYC(cudaMemset(D.status, 0, sizeof(int)));
+    TRYC(h->pool.alloc(&D.vfirst, (size_t)R * D.N));
+    TRYC(h->pool.alloc(&D.vlast, (size_t)R * D.N));
+    TRYC(h->pool.alloc(&D.cur, (size_t)R * D.N));
+    TRYC(h->pool.alloc(&D.bits, (size_t)R * bits_stride(D)));
+    TRYC(h->pool.alloc(&D.frozen, (size_t)R * bits_stride(D)));
+    std::vector<uint32_t> M(R, (uint32_t)cutoff0);
+    TRYC(cudaMemcpy(D.M, M.data(), sizeof(uint32_t) * R, cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(D.key, keys, sizeof(uint64_t) * R, cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(D.beta, betas, sizeof(double) * R, cudaMemcpyHostToDevice));
+    if (init_state) {
+        std::vector<uint32_t> packed((size_t)R * D.Nw, 0u);
+        for (uint32_t r = 0; r < R; r++)
+            for (uint32_t v = 0; v < D.N; v++)
+                if (init_state[(size_t)r * D.N + v]) packed[(size_t)r * D.Nw + (v >> 5)] |= 1u << (v & 31);
+        TRYC(cudaMemcpy(D.state, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+        launch_sse_init_state(D, h->stream);
+        h->launches++;
+        TRYC(cudaGetLastError());
+        TRYC(cudaStreamSynchronize(h->stream));
+    }
+#undef TRYC
+    *out = h;
+    return QMCB_OK;
+}
+
+extern "C" int qmcb_destroy(QmcbHandle *h) {
+    if (!h) return QMCB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->pool.release_all();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return QMCB_OK;
+}
+
+extern "C" int qmcb_set_stream(QmcbHandle *h, void *s) {
+    CHECK_H(h);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return QMCB_OK;
+}
+extern "C" int qmcb_set_mode(QmcbHandle *h, int mode) {
+    CHECK_H(h);
+    if (mode != QMCB_MODE_STRICT && mode != QMCB_MODE_FAST) return fail(QMCB_ERR_BAD_ARG, "unknown mode");
+    h->mode = mode;
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_mode(const QmcbHandle *h, int *mode) {
+    if (!h || !mode) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *mode = h->mode;
+    return QMCB_OK;
+}
+extern "C" int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value) {
+    if (!h || !name) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    if (!strcmp(name, "impl")) {
+        h->impl = (int)value;
+        return QMCB_OK;
+    }
+    if (!strcmp(name, "auto_capacity")) {  // grow the strings on demand even if a capacity was given
+        h->auto_capacity = value != 0;
+        return QMCB_OK;
+    }
+    return fail(QMCB_ERR_BAD_ARG, "unknown option");
+}
+extern "C" int qmcb_set_betas(QmcbHandle *h, const double *betas) {
+    CHECK_H(h);
+    if (!betas) return fail(QMCB_ERR_BAD_ARG, "null betas");
+    CUDA_TRY(cudaMemcpyAsync(h->D.beta, betas, sizeof(double) * h->D.R, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_betas(const QmcbHandle *h, double *betas) {
+    if (!h || !betas) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(betas, h->D.beta, sizeof(double) * h->D.R, cudaMemcpyDeviceToHost));
+    return QMCB_OK;
+}
+extern "C" int qmcb_num_replicas(const QmcbHandle *h, uint32_t *r) {
+    if (!h || !r) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *r = h->D.R;
+    return QMCB_OK;
+}
+extern "C" int qmcb_num_vars(const QmcbHandle *h, uint32_t *n) {
+    if (!h || !n) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *n = h->D.N;
+    return QMCB_OK;
+}
+extern "C" int qmcb_num_bonds(const QmcbHandle *h, uint32_t *nb) {
+    if (!h || !nb) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *nb = h->D.Nb;
+    return QMCB_OK;
+}
+
+extern "C" int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t freq, double *energy_out, uint8_t *samples_out) {
+    CHECK_H(h);
+    if (freq == 0) freq = 1;
+    const SseDev &D = h->D;
+    const uint64_t spr = t / freq;
+    uint8_t *samples_dev = nullptr;
+    int rc = QMCB_OK;
+    if (samples_out && spr) {
+        cudaError_t e = cudaMalloc(&samples_dev, (size_t)D.R * spr * D.N);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(samples)", __FILE__, __LINE__);
+    }
+    CUDA_TRY(cudaMemsetAsync(D.sum_n, 0, sizeof(uint64_t) * D.R, h->stream));
+    const uint64_t origin = h->target;
+    h->target += t;
+    if (t) rc = run_to_target(h, 1u | 2u | 4u | 8u, freq, origin, samples_dev, spr);
+    if (rc == QMCB_OK && energy_out) {
+        std::vector<unsigned long long> sn(D.R);
+        std::vector<double> beta(D.R);
+        cudaError_t e = cudaMemcpyAsync(sn.data(), D.sum_n, sizeof(uint64_t) * D.R, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(beta.data(), D.beta, sizeof(double) * D.R, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "copy estimators", __FILE__, __LINE__);
+        else
+            for (uint32_t r = 0; r < D.R; r++) {  // qmc_stepper.rs:160-161, qmc_ising.rs:805-809
+                double average_n = (double)sn[r] / (double)spr;
+                energy_out[r] = -(average_n / beta[r]) + h->offset;
+            }
+    }
+    if (rc == QMCB_OK && samples_dev) {
+        cudaError_t e = cudaMemcpyAsync(samples_out, samples_dev, (size_t)D.R * spr * D.N, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "copy samples", __FILE__, __LINE__);
+    }
+    if (samples_dev) cudaFree(samples_dev);
+    return rc;
+}
+
+extern "C" int qmcb_enqueue_sweeps(QmcbHandle *h, uint64_t t) {
+    CHECK_H(h);
+    const uint64_t origin = h->target;
+    h->target += t;
+    return launch_sweeps(h, 1u | 2u | 4u | 8u, ~0ull, origin, nullptr, 0);
+}
+extern "C" int qmcb_synchronize(QmcbHandle *h) {
+    CHECK_H(h);
+    int st = 0, rc;
+    if ((rc = check_status(h, &st))) return rc;
+    if ((rc = status_to_error(st))) return rc;
+    if (st & DEV_ERR_CAPACITY) {  // finish the sweeps that were cut short
+        CUDA_TRY(cudaMemsetAsync(h->D.status, 0, sizeof(int), h->stream));
+        if (!h->auto_capacity) return fail(QMCB_ERR_CAPACITY, "cutoff outgrew the capacity given to qmcb_create");
+        std::vector<uint32_t> M(h->D.R);
+        CUDA_TRY(cudaMemcpy(M.data(), h->D.M, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
+        uint64_t need = *std::max_element(M.begin(), M.end());
+        if ((rc = grow(h, need + need / 2 + 1024))) return rc;
+        return run_to_target(h, 1u | 2u | 4u | 8u, ~0ull, h->target, nullptr, 0);
+    }
+    return QMCB_OK;
+}
+// single steps are not resumable, so make room before launching them
+static int ensure_capacity(QmcbHandle *h) {
+    std::vector<uint32_t> M(h->D.R);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(M.data(), h->D.M, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
+    uint64_t need = *std::max_element(M.begin(), M.end());
+    if (need <= h->D.cap) return QMCB_OK;
+    if (!h->auto_capacity) return fail(QMCB_ERR_CAPACITY, "cutoff outgrew the capacity given to qmcb_create");
+    return grow(h, need + need / 2 + 1024);
+}
+extern "C" int qmcb_single_diagonal_step(QmcbHandle *h) {
+    CHECK_H(h);
+    int rc = ensure_capacity(h);
+    return rc ? rc : run_to_target(h, 1u | 4u, 1, 0, nullptr, 0);
+}
+extern "C" int qmcb_single_cluster_step(QmcbHandle *h, uint64_t *ncl_out) {
+    CHECK_H(h);
+    int rc = ensure_capacity(h);
+    if (rc) return rc;
+    if ((rc = run_to_target(h, 2u, 1, 0, nullptr, 0))) return rc;
+    if (ncl_out) {
+        std::vector<uint32_t> ncl(h->D.R);
+        CUDA_TRY(cudaMemcpy(ncl.data(), h->D.ncl, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < h->D.R; r++) ncl_out[r] = ncl[r];
+    }
+    return QMCB_OK;
+}
+extern "C" int qmcb_total_vertex_updates(QmcbHandle *h, uint64_t *total) {
+    CHECK_H(h);
+    if (!total) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    std::vector<unsigned long long> v(h->D.R);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(v.data(), h->D.vupd, sizeof(uint64_t) * h->D.R, cudaMemcpyDeviceToHost));
+    uint64_t s = 0;
+    for (auto x : v) s += x;
+    *total = s;
+    return QMCB_OK;
+}
+extern "C" int qmcb_launch_count(const QmcbHandle *h, uint64_t *launches) {
+    if (!h || !launches) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *launches = h->launches;
+    return QMCB_OK;
+}
+
+static int copy_u32_as_u64(QmcbHandle *h, const uint32_t *dev, uint64_t *out) {
+    std::vector<uint32_t> v(h->D.R);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(v.data(), dev, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
+    for (uint32_t r = 0; r < h->D.R; r++) out[r] = v[r];
+    return QMCB_OK;
+}
+
+extern "C" int qmcb_get_states(QmcbHandle *h, uint8_t *states) {
+    CHECK_H(h);
+    if (!states) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    const SseDev &D = h->D;
+    std::vector<uint32_t> packed((size_t)D.R * D.Nw);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(packed.data(), D.state, packed.size() * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t r = 0; r < D.R; r++)
+        for (uint32_t v = 0; v < D.N; v++) states[(size_t)r * D.N + v] = (packed[(size_t)r * D.Nw + (v >> 5)] >> (v & 31)) & 1u;
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_state(QmcbHandle *h, uint32_t r, uint8_t *state) {
+    CHECK_H(h);
+    const SseDev &D = h->D;
+    if (!state || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    std::vector<uint32_t> packed(D.Nw);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(packed.data(), D.state + (size_t)r * D.Nw, D.Nw * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t v = 0; v < D.N; v++) state[v] = (packed[v >> 5] >> (v & 31)) & 1u;
+    return QMCB_OK;
+}
+extern "C" int qmcb_set_state(QmcbHandle *h, uint32_t r, const uint8_t *state) {
+    CHECK_H(h);
+    const SseDev &D = h->D;
+    if (!state || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    std::vector<uint32_t> packed(D.Nw, 0u);
+    for (uint32_t v = 0; v < D.N; v++)
+        if (state[v]) packed[v >> 5] |= 1u << (v & 31);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(D.state + (size_t)r * D.Nw, packed.data(), D.Nw * 4, cudaMemcpyHostToDevice));
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_n(QmcbHandle *h, uint64_t *n) {
+    CHECK_H(h);
+    return n ? copy_u32_as_u64(h, h->D.n, n) : fail(QMCB_ERR_BAD_ARG, "null argument");
+}
+extern "C" int qmcb_get_cutoffs(QmcbHandle *h, uint64_t *c) {
+    CHECK_H(h);
+    return c ? copy_u32_as_u64(h, h->D.M, c) : fail(QMCB_ERR_BAD_ARG, "null argument");
+}
+extern "C" int qmcb_set_cutoff(QmcbHandle *h, uint32_t r, uint64_t cutoff) {
+    CHECK_H(h);
+    if (r >= h->D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (cutoff > h->D.cap) {
+        if (!h->auto_capacity) return fail(QMCB_ERR_CAPACITY, "cutoff above capacity");
+        int rc = grow(h, cutoff + cutoff / 2);
+        if (rc) return rc;
+    }
+    // QmcIsingGraph::set_cutoff (qmc_ising.rs:537-540) sets the cutoff unconditionally; ops above a
+    // smaller cutoff would be orphaned exactly as in the reference, so refuse to shrink below n's reach.
+    uint32_t c = (uint32_t)cutoff;
+    CUDA_TRY(cudaMemcpy(h->D.M + r, &c, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_capacity(const QmcbHandle *h, uint64_t *cap) {
+    if (!h || !cap) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *cap = h->D.cap;
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_offset(const QmcbHandle *h, double *offset) {
+    if (!h || !offset) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *offset = h->offset;
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_bond_counts(QmcbHandle *h, uint32_t r, uint64_t *counts) {
+    CHECK_H(h);
+    const SseDev &D = h->D;
+    if (!counts || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    unsigned long long *dev = nullptr;
+    const uint32_t nb = D.E + 2 * D.N;
+    CUDA_TRY(cudaMalloc(&dev, sizeof(uint64_t) * nb));
+    cudaMemsetAsync(dev, 0, sizeof(uint64_t) * nb, h->stream);
+    launch_sse_bond_counts(D, r, dev, h->stream);
+    h->launches++;
+    std::vector<unsigned long long> host(nb);
+    cudaError_t e = cudaMemcpyAsync(host.data(), dev, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail_cuda(e, "bond counts", __FILE__, __LINE__);
+    for (uint32_t b = 0; b < D.Nb; b++) counts[b] = host[b];
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_rng_cursors(QmcbHandle *h, uint64_t *cursors) {
+    CHECK_H(h);
+    if (!cursors) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(cursors, h->D.cursor, sizeof(uint64_t) * h->D.R, cudaMemcpyDeviceToHost));
+    return QMCB_OK;
+}
+extern "C" int qmcb_set_rng_cursor(QmcbHandle *h, uint32_t r, uint64_t cursor) {
+    CHECK_H(h);
+    if (r >= h->D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h->D.cursor + r, &cursor, sizeof(uint64_t), cudaMemcpyHostToDevice));
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_rng_keys(QmcbHandle *h, uint64_t *keys) {
+    CHECK_H(h);
+    if (!keys) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(keys, h->D.key, sizeof(uint64_t) * h->D.R, cudaMemcpyDeviceToHost));
+    return QMCB_OK;
+}
+extern "C" int qmcb_dump_ops(QmcbHandle *h, uint32_t r, uint32_t *words, uint64_t nwords) {
+    CHECK_H(h);
+    const SseDev &D = h->D;
+    if (!words || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    uint32_t M = 0;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(&M, D.M + r, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (nwords < M) return fail(QMCB_ERR_BAD_ARG, "buffer shorter than the cutoff");
+    const uint64_t have = std::min<uint64_t>(M, D.cap);
+    CUDA_TRY(cudaMemcpy(words, D.ops + (size_t)r * D.cap, have * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t p = have; p < nwords; p++) words[p] = QMCB_OP_EMPTY;
+    return QMCB_OK;
+}
+extern "C" int qmcb_load_ops(QmcbHandle *h, uint32_t r, const uint32_t *words, uint64_t nwords, const uint8_t *state) {
+    CHECK_H(h);
+    SseDev &D = h->D;
+    if (!words || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    for (uint64_t p = 0; p < nwords; p++) {
+        if (words[p] == QMCB_OP_EMPTY) continue;
+        uint32_t b = words[p] & 0xFFFFFFu;
+        if ((words[p] >> 28) || b >= D.E + D.N + (D.has_h ? D.N : 0)) return fail(QMCB_ERR_BAD_ARG, "malformed operator word");
+        if (b >= D.E && ((words[p] >> 25) & 1u || (words[p] >> 27) & 1u)) return fail(QMCB_ERR_BAD_ARG, "one-variable op with second-leg bits");
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (nwords > D.cap) {
+        if (!h->auto_capacity) return fail(QMCB_ERR_CAPACITY, "string longer than capacity");
+        int rc = grow(h, nwords + nwords / 2);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaMemset(D.ops + (size_t)r * D.cap, 0xFF, D.cap * 4));
+    CUDA_TRY(cudaMemcpy(D.ops + (size_t)r * D.cap, words, nwords * 4, cudaMemcpyHostToDevice));
+    uint32_t M = 0;
+    CUDA_TRY(cudaMemcpy(&M, D.M + r, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (nwords > M) {
+        M = (uint32_t)nwords;
+        CUDA_TRY(cudaMemcpy(D.M + r, &M, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    launch_sse_recount(D, r, h->stream);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (state) return qmcb_set_state(h, r, state);
+    return QMCB_OK;
+}
+extern "C" int qmcb_verify(QmcbHandle *h, uint32_t r, int *ok) {
+    CHECK_H(h);
+    if (!ok || r >= h->D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    int *ok_dev = nullptr;
+    uint32_t *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&ok_dev, sizeof(int)));
+    cudaError_t e = cudaMalloc(&scratch, sizeof(uint32_t) * h->D.Nw);
+    if (e == cudaSuccess) {
+        launch_sse_verify(h->D, r, ok_dev, scratch, h->stream);
+        h->launches++;
+        e = cudaMemcpyAsync(ok, ok_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(ok_dev), cudaFree(scratch);
+    if (e != cudaSuccess) return fail_cuda(e, "verify", __FILE__, __LINE__);
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_boundaries(QmcbHandle *h, uint32_t r, uint32_t *b_in, uint32_t *b_out, uint64_t nslots) {
+    CHECK_H(h);
+    const SseDev &D = h->D;
+    if (!b_in || !b_out || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    if (!h->strict_ws) return fail(QMCB_ERR_BAD_ARG, "no STRICT cluster step has run yet");
+    uint64_t k = std::min<uint64_t>(nslots, D.cap);
+    std::vector<uint32_t> b(2 * k);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(b.data(), D.bounds + (size_t)r * D.cap * 2, 8 * k, cudaMemcpyDeviceToHost));
+    for (uint64_t p = 0; p < nslots; p++) b_in[p] = p < k ? b[2 * p] : NONE32, b_out[p] = p < k ? b[2 * p + 1] : NONE32;
+    return QMCB_OK;
+}
+
+// ---- tempering --------------------------------------------------------------------------
+extern "C" int qmcb_pt_configure(QmcbHandle *h, uint32_t n_chains, uint32_t n_betas, uint32_t slot_begin,
+                                 const double *betas_global, const uint64_t *keys_global, uint64_t pt_key) {
+    CHECK_H(h);
+    SseDev &D = h->D;
+    const uint64_t S = (uint64_t)n_chains * n_betas;
+    if (!betas_global || !keys_global || S == 0 || slot_begin + (uint64_t)D.R > S)
+        return fail(QMCB_ERR_BAD_ARG, "tempering ladder does not cover this handle's replicas");
+    // SwapManagers::can_swap_graphs (qmc_ising.rs:563-590) holds trivially: one lattice per handle
+    PtDev &P = h->P;
+    P.n_chains = n_chains, P.n_betas = n_betas, P.cfg_begin = slot_begin, P.pt_key = pt_key;
+    double *bs;
+    uint64_t *ks;
+    CUDA_TRY(h->pool.alloc(&bs, S));
+    CUDA_TRY(h->pool.alloc(&ks, S));
+    CUDA_TRY(cudaMemcpy(bs, betas_global, sizeof(double) * S, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ks, keys_global, sizeof(uint64_t) * S, cudaMemcpyHostToDevice));
+    P.beta_slot = bs, P.key_slot = ks;
+    CUDA_TRY(h->pool.alloc(&P.pt_cursor, 1));
+    CUDA_TRY(cudaMemset(P.pt_cursor, 0, sizeof(uint64_t)));
+    CUDA_TRY(h->pool.alloc(&P.swaps, 1));
+    CUDA_TRY(cudaMemset(P.swaps, 0, sizeof(uint64_t)));
+    CUDA_TRY(h->pool.alloc(&P.slot_of_local, D.R));
+    std::vector<uint32_t> slots(D.R);
+    for (uint32_t s = 0; s < D.R; s++) slots[s] = slot_begin + s;
+    CUDA_TRY(cudaMemcpy(P.slot_of_local, slots.data(), sizeof(uint32_t) * D.R, cudaMemcpyHostToDevice));
+    CUDA_TRY(h->pool.alloc(&P.n_slot, S));
+    CUDA_TRY(h->pool.alloc(&P.cursor_slot, S));
+    CUDA_TRY(h->pool.alloc(&P.cfg_slot, S));
+    CUDA_TRY(h->pool.alloc(&P.maxM_chain, n_chains));
+    // the local configurations start in slots [slot_begin, slot_begin + R): take those labels
+    CUDA_TRY(cudaMemcpy(D.beta, betas_global + slot_begin, sizeof(double) * D.R, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(D.key, keys_global + slot_begin, sizeof(uint64_t) * D.R, cudaMemcpyHostToDevice));
+    h->pt_on = true;
+    h->pt_S = (uint32_t)S;
+    return QMCB_OK;
+}
+extern "C" int qmcb_pt_export(QmcbHandle *h, uint64_t *rec_dev) {
+    CHECK_H(h);
+    if (!h->pt_on || !rec_dev) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+    launch_pt_export(h->D, h->P, rec_dev, h->stream);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return QMCB_OK;
+}
+extern "C" int qmcb_pt_apply(QmcbHandle *h, const uint64_t *all_rec_dev, uint64_t n_records) {
+    CHECK_H(h);
+    if (!h->pt_on || !all_rec_dev || n_records != h->pt_S) return fail(QMCB_ERR_BAD_ARG, "record count does not match the ladder");
+    launch_pt_apply(h->D, h->P, all_rec_dev, h->pt_S, h->stream);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return QMCB_OK;
+}
+extern "C" int qmcb_pt_total_swaps(QmcbHandle *h, uint64_t *swaps) {
+    CHECK_H(h);
+    if (!h->pt_on || !swaps) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(swaps, h->P.swaps, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return QMCB_OK;
+}
+extern "C" int qmcb_pt_get_slots(QmcbHandle *h, uint32_t *slots) {
+    CHECK_H(h);
+    if (!h->pt_on || !slots) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(slots, h->P.slot_of_local, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
+    return QMCB_OK;
+}
+
+// =============================================================================================
+// classical handle
+// =============================================================================================
+struct CmcbHandle {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    ClsDev D{};
+    Pool pool;
+    bool square = false;
+    uint64_t sweeps = 0, launches = 0;
+    uint32_t ncolours = 0;
+    std::vector<uint32_t> colours, colour_start;
+    double J_uniform = 0.0, bias_uniform = 0.0;
+    double *adj_j_dev = nullptr, *biases_dev = nullptr;
+    uint8_t *bytes_dev = nullptr;  // staging for the square layout
+};
+
+#define CHECK_C(h)                                              \
+    if (!(h)) return fail(QMCB_ERR_BAD_ARG, "null handle");     \
+    CUDA_TRY(cudaSetDevice((h)->device))
+
+// #{d in [0, 2^32) : d * 2^-32 < exp(-beta * dE)}, 2^32 when dE <= 0 (should_flip, graph.rs:339-347)
+static uint64_t metropolis_threshold(double beta, double delta_e) {
+    if (!(delta_e > 0.0)) return 4294967296ull;
+    double chance = std::exp(-beta * delta_e);
+    double scaled = std::ceil(chance * 4294967296.0);
+    if (scaled >= 4294967296.0) return 4294967296ull;
+    return (uint64_t)scaled;
+}
+
+extern "C" int cmcb_create(const QmcbLattice *lat, const double *biases, uint32_t R, const double *betas, const uint64_t *keys,
+                           const uint8_t *init_state, int device, CmcbHandle **out) {
+    if (!lat || !biases || !betas || !keys || !out || R == 0 || lat->nvars == 0) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    const uint32_t N = lat->nvars, E = lat->nedges;
+    for (uint32_t e = 0; e < E; e++)
+        if (lat->va[e] >= N || lat->vb[e] >= N || lat->va[e] == lat->vb[e]) return fail(QMCB_ERR_BAD_ARG, "edge endpoint out of range or self-loop");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(QMCB_ERR_CUDA, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    // binding_mat (graph.rs:62-78): push order, then stable sort by neighbour index
+    std::vector<std::vector<std::pair<uint32_t, double>>> adj(N);
+    for (uint32_t e = 0; e < E; e++) {
+        adj[lat->va[e]].push_back({lat->vb[e], lat->J[e]});
+        adj[lat->vb[e]].push_back({lat->va[e], lat->J[e]});
+    }
+    uint32_t maxdeg = 0;
+    for (auto &v : adj) {
+        std::stable_sort(v.begin(), v.end(), [](const std::pair<uint32_t, double> &a, const std::pair<uint32_t, double> &b) { return a.first < b.first; });
+        maxdeg = std::max<uint32_t>(maxdeg, (uint32_t)v.size());
+    }
+    if (maxdeg > 12) return fail(QMCB_ERR_UNSUPPORTED, "checkerboard kernel supports vertex degree <= 12");
+    // greedy colouring in index order: smallest colour unused by lower-indexed neighbours
+    std::vector<uint32_t> colour(N, 0);
+    uint32_t ncol = 0;
+    for (uint32_t i = 0; i < N; i++) {
+        uint32_t used = 0;
+        for (auto &nb : adj[i])
+            if (nb.first < i) used |= 1u << colour[nb.first];
+        uint32_t c = 0;
+        while (used & (1u << c)) c++;
+        colour[i] = c;
+        ncol = std::max(ncol, c + 1);
+    }
+    CmcbHandle *h = new CmcbHandle();
+    h->device = device;
+    h->colours = colour, h->ncolours = ncol;
+    ClsDev &D = h->D;
+    D.N = N, D.R = R;
+#define TRYC(expr)                                   \
+    do {                                             \
+        cudaError_t e_ = (expr);                     \
+        if (e_ != cudaSuccess) {                     \
+            h->pool.release_all();                   \
+            delete h;                                \
+            return fail_cuda(e_, #expr, __FILE__, __LINE__); \
+        }                                            \
+    } while (0)
+    TRYC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    uint64_t *key_dev;
+    TRYC(h->pool.alloc(&key_dev, R));
+    TRYC(cudaMemcpy(key_dev, keys, sizeof(uint64_t) * R, cudaMemcpyHostToDevice));
+    D.key = key_dev;
+
+    // ---- is this the L x L periodic square lattice with uniform J and bias? -----------------
+    uint32_t L = (uint32_t)std::llround(std::sqrt((double)N));
+    bool square = (uint64_t)L * L == N && L % 64 == 0 && E == 2 * N && ncol == 2;
+    if (square) {
+        for (uint32_t e = 1; e < E && square; e++) square = lat->J[e] == lat->J[0];
+        for (uint32_t i = 1; i < N && square; i++) square = biases[i] == biases[0];
+        std::vector<uint8_t> seen(2 * (size_t)N, 0);
+        for (uint32_t e = 0; e < E && square; e++) {
+            uint32_t a = lat->va[e], b = lat->vb[e];
+            bool hit = false;
+            for (int swap = 0; swap < 2 && !hit; swap++) {
+                uint32_t x = a % L, y = a / L;
+                uint32_t right = y * L + (x + 1) % L, down = ((y + 1) % L) * L + x;
+                if (b == right && !seen[2 * (size_t)a]) seen[2 * (size_t)a] = 1, hit = true;
+                else if (b == down && !seen[2 * (size_t)a + 1]) seen[2 * (size_t)a + 1] = 1, hit = true;
+                std::swap(a, b);
+            }
+            square = hit;
+        }
+        for (uint32_t i = 0; i < N && square; i++) square = colour[i] == ((i % L + i / L) & 1u);
+    }
+    // delta_e must depend only on (#anti-aligned neighbours, own spin): check every sign sequence
+    std::vector<double> sq_de(16, 0.0);
+    if (square) {
+        const double J = lat->J[0], b = biases[0];
+        if (square) {
+            for (int own = 0; own < 2; own++)
+                for (int cnt = 0; cnt <= 4; cnt++) {
+                    int mask = (0xF << cnt) & 0xF;
+                    double de = 0.0;
+                    for (int k = 0; k < 4; k++) de += -2.0 * J * (((mask >> k) & 1) ? 1.0 : -1.0);
+                    sq_de[own * 8 + cnt] = de + (2.0 * b * (own ? 1.0 : -1.0));
+                }
+            for (int own = 0; own < 2 && square; own++)
+                for (int mask = 0; mask < 16 && square; mask++) {
+                    double de = 0.0;
+                    for (int k = 0; k < 4; k++) de += -2.0 * J * (((mask >> k) & 1) ? 1.0 : -1.0);
+                    de = de + (2.0 * b * (own ? 1.0 : -1.0));
+                    square = de == sq_de[own * 8 + (4 - __builtin_popcount(mask))];
+                }
+        }
+    }
+    h->square = square;
+    h->J_uniform = E ? lat->J[0] : 0.0, h->bias_uniform = biases[0];
+
+    std::vector<uint8_t> init_bytes;
+    if (square) {
+        D.L = L;
+        TRYC(h->pool.alloc(&D.planes, (size_t)R * 2 * L * (L >> 6)));
+        std::vector<uint32_t> thr((size_t)R * 16, 0u), alw(R, 0u);
+        for (uint32_t r = 0; r < R; r++)
+            for (int own = 0; own < 2; own++)
+                for (int cnt = 0; cnt <= 4; cnt++) {
+                    uint64_t T = metropolis_threshold(betas[r], sq_de[own * 8 + cnt]);
+                    if (T >= 4294967296ull) alw[r] |= 1u << (own * 8 + cnt);
+                    else thr[(size_t)r * 16 + own * 8 + cnt] = (uint32_t)T;
+                }
+        uint32_t *thr_dev, *alw_dev;
+        TRYC(h->pool.alloc(&thr_dev, thr.size()));
+        TRYC(h->pool.alloc(&alw_dev, alw.size()));
+        TRYC(cudaMemcpy(thr_dev, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(alw_dev, alw.data(), alw.size() * 4, cudaMemcpyHostToDevice));
+        D.sq_thr = thr_dev, D.sq_always = alw_dev;
+        TRYC(h->pool.alloc(&h->bytes_dev, (size_t)R * N));
+    } else {
+        // CSR + site classes + per-replica threshold tables
+        std::vector<uint32_t> start(N + 1, 0), idx;
+        std::vector<double> aj;
+        for (uint32_t i = 0; i < N; i++) {
+            start[i + 1] = start[i] + (uint32_t)adj[i].size();
+            for (auto &nb : adj[i]) idx.push_back(nb.first), aj.push_back(nb.second);
+        }
+        std::map<std::pair<std::vector<double>, double>, uint32_t> classes;
+        std::vector<uint32_t> site_class(N), class_off;
+        std::vector<std::pair<std::vector<double>, double>> class_def;
+        uint32_t stride = 0;
+        for (uint32_t i = 0; i < N; i++) {
+            std::vector<double> js;
+            for (auto &nb : adj[i]) js.push_back(nb.second);
+            auto keyc = std::make_pair(js, biases[i]);
+            auto it = classes.find(keyc);
+            if (it == classes.end()) {
+                it = classes.insert({keyc, (uint32_t)class_def.size()}).first;
+                class_def.push_back(keyc);
+                class_off.push_back(stride);
+                stride += 2u << js.size();
+            }
+            site_class[i] = it->second;
+        }
+        if ((uint64_t)stride * R > (1ull << 26)) {
+            h->pool.release_all();
+            delete h;
+            return fail(QMCB_ERR_UNSUPPORTED, "too many distinct site classes for the checkerboard threshold tables");
+        }
+        std::vector<unsigned long long> thr((size_t)stride * R);
+        for (uint32_t r = 0; r < R; r++)
+            for (size_t c = 0; c < class_def.size(); c++) {
+                const auto &js = class_def[c].first;
+                const uint32_t deg = (uint32_t)js.size();
+                for (uint32_t own = 0; own < 2; own++)
+                    for (uint32_t mask = 0; mask < (1u << deg); mask++) {
+                        double de = 0.0;  // graph.rs:101-113
+                        for (uint32_t k = 0; k < deg; k++) de += -2.0 * js[k] * (((mask >> k) & 1u) ? 1.0 : -1.0);
+                        de = de + (2.0 * class_def[c].second * (own ? 1.0 : -1.0));
+                        thr[(size_t)r * stride + class_off[c] + ((own << deg) | mask)] = metropolis_threshold(betas[r], de);
+                    }
+            }
+        std::vector<uint32_t> csites, cstart(ncol + 1, 0);
+        for (uint32_t c = 0; c < ncol; c++) {
+            for (uint32_t i = 0; i < N; i++)
+                if (colour[i] == c) csites.push_back(i);
+            cstart[c + 1] = (uint32_t)csites.size();
+        }
+        h->colour_start = cstart;
+        uint32_t *d_start, *d_idx, *d_class, *d_off, *d_csites;
+        unsigned long long *d_thr;
+        TRYC(h->pool.alloc(&d_start, start.size()));
+        TRYC(h->pool.alloc(&d_idx, idx.size()));
+        TRYC(h->pool.alloc(&d_class, site_class.size()));
+        TRYC(h->pool.alloc(&d_off, class_off.size()));
+        TRYC(h->pool.alloc(&d_csites, csites.size()));
+        TRYC(h->pool.alloc(&d_thr, thr.size()));
+        TRYC(h->pool.alloc(&h->adj_j_dev, aj.size()));
+        TRYC(h->pool.alloc(&h->biases_dev, N));
+        TRYC(cudaMemcpy(d_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(d_class, site_class.data(), site_class.size() * 4, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(d_off, class_off.data(), class_off.size() * 4, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(d_csites, csites.data(), csites.size() * 4, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(d_thr, thr.data(), thr.size() * 8, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(h->adj_j_dev, aj.data(), aj.size() * 8, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(h->biases_dev, biases, N * 8, cudaMemcpyHostToDevice));
+        D.adj_start = d_start, D.adj_idx = d_idx, D.site_class = d_class, D.class_off = d_off;
+        D.colour_sites = d_csites, D.thr = d_thr, D.thr_stride = stride;
+        TRYC(h->pool.alloc(&D.spins, (size_t)R * N));
+    }
+    // initial spins
+    uint8_t *bytes = square ? h->bytes_dev : D.spins;
+    if (init_state) TRYC(cudaMemcpy(bytes, init_state, (size_t)R * N, cudaMemcpyHostToDevice));
+    else {
+        launch_cls_init_bytes(D, bytes, h->stream);
+        h->launches++;
+    }
+    if (square) {
+        launch_cls_square_pack(D, bytes, h->stream);
+        h->launches++;
+    }
+    TRYC(cudaGetLastError());
+    TRYC(cudaStreamSynchronize(h->stream));
+#undef TRYC
+    *out = h;
+    return QMCB_OK;
+}
+
+extern "C" int cmcb_destroy(CmcbHandle *h) {
+    if (!h) return QMCB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->pool.release_all();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return QMCB_OK;
+}
+extern "C" int cmcb_set_stream(CmcbHandle *h, void *s) {
+    CHECK_C(h);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return QMCB_OK;
+}
+extern "C" int cmcb_enqueue_sweeps(CmcbHandle *h, uint64_t nsweeps) {
+    CHECK_C(h);
+    for (uint64_t s = 0; s < nsweeps; s++, h->sweeps++) {
+        for (uint32_t c = 0; c < h->ncolours; c++) {
+            if (h->square) launch_cls_square(h->D, c, h->sweeps, h->stream);
+            else launch_cls_generic(h->D, c, h->colour_start[c], h->colour_start[c + 1] - h->colour_start[c], h->sweeps, h->stream);
+            h->launches++;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return QMCB_OK;
+}
+extern "C" int cmcb_synchronize(CmcbHandle *h) {
+    CHECK_C(h);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+extern "C" int cmcb_sweeps(CmcbHandle *h, uint64_t nsweeps) {
+    int rc = cmcb_enqueue_sweeps(h, nsweeps);
+    return rc ? rc : cmcb_synchronize(h);
+}
+extern "C" int cmcb_get_states(CmcbHandle *h, uint8_t *states) {
+    CHECK_C(h);
+    if (!states) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    const uint8_t *src = h->D.spins;
+    if (h->square) {
+        launch_cls_square_unpack(h->D, h->bytes_dev, h->stream);
+        h->launches++;
+        src = h->bytes_dev;
+    }
+    CUDA_TRY(cudaMemcpyAsync(states, src, (size_t)h->D.R * h->D.N, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+extern "C" int cmcb_get_state(CmcbHandle *h, uint32_t r, uint8_t *state) {
+    CHECK_C(h);
+    if (!state || r >= h->D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    const uint8_t *src = h->D.spins;
+    if (h->square) {
+        launch_cls_square_unpack(h->D, h->bytes_dev, h->stream);
+        h->launches++;
+        src = h->bytes_dev;
+    }
+    CUDA_TRY(cudaMemcpyAsync(state, src + (size_t)r * h->D.N, h->D.N, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+extern "C" int cmcb_set_states(CmcbHandle *h, const uint8_t *states) {
+    CHECK_C(h);
+    if (!states) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    uint8_t *dst = h->square ? h->bytes_dev : h->D.spins;
+    CUDA_TRY(cudaMemcpyAsync(dst, states, (size_t)h->D.R * h->D.N, cudaMemcpyHostToDevice, h->stream));
+    if (h->square) {
+        launch_cls_square_pack(h->D, dst, h->stream);
+        h->launches++;
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+static int cls_measure(CmcbHandle *h, double *energy, double *mag) {
+    const ClsDev &D = h->D;
+    if (h->square) {
+        unsigned long long *dev = nullptr;
+        CUDA_TRY(cudaMalloc(&dev, sizeof(uint64_t) * 2 * D.R));
+        cudaMemsetAsync(dev, 0, sizeof(uint64_t) * 2 * D.R, h->stream);
+        launch_cls_square_measure(D, dev, dev + D.R, h->stream);
+        h->launches++;
+        std::vector<unsigned long long> host(2 * (size_t)D.R);
+        cudaError_t e = cudaMemcpyAsync(host.data(), dev, sizeof(uint64_t) * 2 * D.R, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(dev);
+        if (e != cudaSuccess) return fail_cuda(e, "measure", __FILE__, __LINE__);
+        const double N = (double)D.N;
+        for (uint32_t r = 0; r < D.R; r++) {
+            double unsat = (double)host[r], up = (double)host[D.R + r];
+            if (energy) energy[r] = h->J_uniform * (2.0 * N - 2.0 * unsat) + h->bias_uniform * (N - 2.0 * up);
+            if (mag) mag[r] = (2.0 * up - N) / N;
+        }
+        return QMCB_OK;
+    }
+    double *dev = nullptr;
+    CUDA_TRY(cudaMalloc(&dev, sizeof(double) * 2 * D.R));
+    launch_cls_generic_energy(D, h->adj_j_dev, h->biases_dev, dev, dev + D.R, h->stream);
+    h->launches++;
+    std::vector<double> host(2 * (size_t)D.R);
+    cudaError_t e = cudaMemcpyAsync(host.data(), dev, sizeof(double) * 2 * D.R, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail_cuda(e, "measure", __FILE__, __LINE__);
+    for (uint32_t r = 0; r < D.R; r++) {
+        if (energy) energy[r] = host[r];
+        if (mag) mag[r] = host[D.R + r];
+    }
+    return QMCB_OK;
+}
+extern "C" int cmcb_energy(CmcbHandle *h, double *energy) {
+    CHECK_C(h);
+    return energy ? cls_measure(h, energy, nullptr) : fail(QMCB_ERR_BAD_ARG, "null argument");
+}
+extern "C" int cmcb_magnetization(CmcbHandle *h, double *m) {
+    CHECK_C(h);
+    return m ? cls_measure(h, nullptr, m) : fail(QMCB_ERR_BAD_ARG, "null argument");
+}
+extern "C" int cmcb_get_colours(const CmcbHandle *h, uint32_t *colours, uint32_t *ncolours) {
+    if (!h) return fail(QMCB_ERR_BAD_ARG, "null handle");
+    if (colours) memcpy(colours, h->colours.data(), sizeof(uint32_t) * h->colours.size());
+    if (ncolours) *ncolours = h->ncolours;
+    return QMCB_OK;
+}
+extern "C" int cmcb_get_sweep_count(const CmcbHandle *h, uint64_t *sweeps) {
+    if (!h || !sweeps) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *sweeps = h->sweeps;
+    return QMCB_OK;
+}
+extern "C" int cmcb_set_sweep_count(CmcbHandle *h, uint64_t sweeps) {
+    if (!h) return fail(QMCB_ERR_BAD_ARG, "null handle");
+    h->sweeps = sweeps;
+    return QMCB_OK;
+}
+extern "C" int cmcb_layout(const CmcbHandle *h, int *sq) {
+    if (!h || !sq) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *sq = h->square ? 1 : 0;
+    return QMCB_OK;
+}
+extern "C" int cmcb_launch_count(const CmcbHandle *h, uint64_t *launches) {
+    if (!h || !launches) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *launches = h->launches;
+    return QMCB_OK;
+}

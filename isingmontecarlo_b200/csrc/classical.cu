@@ -1,0 +1,212 @@
+// classical.cu -- checkerboard Metropolis sweeps of R independent classical Ising replicas.
+//
+// Per-site rule = the reference's (delta_e of do_spin_flip classical/graph.rs:98-115, should_flip
+// :339-347); the checkerboard schedule and the fixed-width draw are builder-defined (the reference
+// only has a random-site schedule, graph.rs:350-406): the site of rank r inside colour c uses
+// word (r & 3) of Philox4x32-10(key, ctr = (r >> 2, sweep_lo, sweep_hi, 'CB' << 16 | c)) and flips
+// iff d < T, T = #{d : d * 2^-32 < exp(-beta * delta_e)} (2^32 when delta_e <= 0).  The thresholds
+// are tabulated on the host with libm's exp so no device transcendental can leak into the result.
+//
+// Two layouts:
+//  * generic graph: one byte per spin (the reference's Vec<bool>), CSR neighbours, one thread per
+//    4 consecutive ranks of a colour (one Philox call), threshold table per (replica, site class).
+//  * L x L periodic square lattice, uniform J and bias: spins bit-packed in two colour planes,
+//    one thread per 32 sites: neighbour counts by bit-sliced adders, 8 Philox calls, no divergence.
+#include "classical.cuh"
+
+// ------------------------------------------------------------------------------------------
+// generic graph
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cls_generic(ClsDev D, uint32_t colour, uint32_t cstart, uint32_t ccount,
+                                                     uint64_t sweep) {
+    const uint32_t r = blockIdx.y;
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 ranks
+    if (q * 4 >= ccount) return;
+    const uint64_t key = D.key[r];
+    Philox4 o = philox4x32_10(q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, (uint32_t)key,
+                              (uint32_t)(key >> 32));
+    const uint32_t d[4] = {o.x, o.y, o.z, o.w};
+    uint8_t *sp = D.spins + (size_t)r * D.N;
+    const unsigned long long *thr = D.thr + (size_t)r * D.thr_stride;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t rank = q * 4 + k;
+        if (rank >= ccount) break;
+        uint32_t i = __ldg(D.colour_sites + cstart + rank);
+        uint32_t s = sp[i];
+        uint32_t a0 = __ldg(D.adj_start + i), a1 = __ldg(D.adj_start + i + 1);
+        uint32_t mask = 0;
+        for (uint32_t e = a0; e < a1; e++) mask |= (uint32_t)(sp[__ldg(D.adj_idx + e)] == s) << (e - a0);
+        uint32_t cls = __ldg(D.site_class + i);
+        unsigned long long T = thr[__ldg(D.class_off + cls) + ((s << (a1 - a0)) | mask)];
+        if ((unsigned long long)d[k] < T) sp[i] = (uint8_t)(s ^ 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// square lattice, bit-packed colour planes.
+// plane[c][y][w] bit j  <->  site (x, y) with x = 2 * (32 w + j) + ((y + c) & 1); colour = (x+y)&1.
+// ------------------------------------------------------------------------------------------
+template <int NCALLS>
+__device__ __forceinline__ void philox_batch(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                             uint32_t k1, uint32_t (&out)[NCALLS * 4]) {
+#pragma unroll
+    for (int q = 0; q < NCALLS; q++) {
+        Philox4 o = philox4x32_10(c0 + q, c1, c2, c3, k0, k1);
+        out[4 * q] = o.x, out[4 * q + 1] = o.y, out[4 * q + 2] = o.z, out[4 * q + 3] = o.w;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cls_square(ClsDev D, uint32_t colour, uint64_t sweep) {
+    const uint32_t WPR = D.L >> 6;                  // 32-bit words per row of one colour plane
+    const uint32_t words_per_plane = D.L * WPR;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = blockIdx.y;
+    if (t >= words_per_plane) return;
+    const uint32_t y = t / WPR, w = t - y * WPR;
+    uint32_t *mine = D.planes + ((size_t)r * 2 + colour) * words_per_plane;
+    const uint32_t *other = D.planes + ((size_t)r * 2 + (colour ^ 1u)) * words_per_plane;
+    const uint32_t yu = y == 0 ? D.L - 1 : y - 1, yd = y + 1 == D.L ? 0 : y + 1;
+    const uint32_t own = mine[t];
+    const uint32_t same = other[y * WPR + w];
+    const uint32_t up = other[yu * WPR + w], dn = other[yd * WPR + w];
+    uint32_t side;
+    if ((y + colour) & 1u) {  // my x is odd: the second horizontal neighbour has compressed index xc + 1
+        uint32_t nxt = other[y * WPR + (w + 1 == WPR ? 0 : w + 1)];
+        side = (same >> 1) | (nxt << 31);
+    } else {  // my x is even: neighbour xc - 1
+        uint32_t prv = other[y * WPR + (w == 0 ? WPR - 1 : w - 1)];
+        side = (same << 1) | (prv >> 31);
+    }
+    // bit-sliced count of anti-aligned neighbours: cnt = lo + 2 mid + 4 hi
+    const uint32_t a = own ^ same, b = own ^ side, c = own ^ up, d = own ^ dn;
+    const uint32_t s1 = a ^ b ^ c, c1 = (a & b) | (c & (a ^ b));
+    const uint32_t lo = s1 ^ d, c2 = s1 & d;
+    const uint32_t mid = c1 ^ c2, hi = c1 & c2;
+    // draws: ranks y * L/2 + 32 w + j, j = 0..31  ->  8 consecutive Philox counters
+    const uint64_t key = D.key[r];
+    uint32_t dr[32];
+    philox_batch<8>((y * (D.L >> 1) + 32 * w) >> 2, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour,
+                    (uint32_t)key, (uint32_t)(key >> 32), dr);
+    // threshold table of this replica: index = own << 3 | cnt; 2^32 ("always") is stored as
+    // always-bit 16 + idx of `alw`
+    const uint32_t *T = D.sq_thr + (size_t)r * 16;
+    const uint32_t alw = D.sq_always[r];
+    uint32_t flip = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        uint32_t idx = ((lo >> j) & 1u) | (((mid >> j) & 1u) << 1) | (((hi >> j) & 1u) << 2) | (((own >> j) & 1u) << 3);
+        bool f = ((alw >> idx) & 1u) || dr[j] < __ldg(T + idx);
+        flip |= (uint32_t)f << j;
+    }
+    mine[t] = own ^ flip;
+}
+
+// energy (graph.rs:430-447 restricted to uniform J / bias: integer bond and spin counts) and
+// magnetisation of the bit-packed layout: per replica  unsat = #anti-aligned bonds, up = #true spins
+__global__ void __launch_bounds__(256) k_cls_square_measure(ClsDev D, unsigned long long *unsat, unsigned long long *up) {
+    const uint32_t WPR = D.L >> 6;
+    const uint32_t words_per_plane = D.L * WPR;
+    const uint32_t r = blockIdx.y;
+    unsigned long long u = 0, m = 0;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < words_per_plane; t += gridDim.x * blockDim.x) {
+        const uint32_t y = t / WPR, w = t - y * WPR;
+        const uint32_t *p0 = D.planes + ((size_t)r * 2) * words_per_plane;
+        const uint32_t *p1 = p0 + words_per_plane;
+        const uint32_t own = p0[t];  // colour-0 sites own all four of their bonds exactly once
+        const uint32_t yu = y == 0 ? D.L - 1 : y - 1, yd = y + 1 == D.L ? 0 : y + 1;
+        const uint32_t same = p1[y * WPR + w];
+        uint32_t side;
+        if (y & 1u) side = (same >> 1) | (p1[y * WPR + (w + 1 == WPR ? 0 : w + 1)] << 31);
+        else side = (same << 1) | (p1[y * WPR + (w == 0 ? WPR - 1 : w - 1)] >> 31);
+        u += __popc(own ^ same) + __popc(own ^ side) + __popc(own ^ p1[yu * WPR + w]) + __popc(own ^ p1[yd * WPR + w]);
+        m += __popc(own) + __popc(p1[t]);
+    }
+    for (int o = 16; o; o >>= 1) u += __shfl_down_sync(0xFFFFFFFFu, u, o), m += __shfl_down_sync(0xFFFFFFFFu, m, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&unsat[r], u), atomicAdd(&up[r], m);
+}
+
+// bytes <-> bit planes
+__global__ void k_cls_square_pack(ClsDev D, const uint8_t *bytes) {
+    const uint32_t WPR = D.L >> 6, words_per_plane = D.L * WPR;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, c = blockIdx.z;
+    if (t >= words_per_plane) return;
+    const uint32_t y = t / WPR, w = t - y * WPR;
+    const uint8_t *row = bytes + (size_t)r * D.N + (size_t)y * D.L;
+    uint32_t word = 0;
+    for (int j = 0; j < 32; j++) word |= (uint32_t)(row[2 * (32 * w + j) + ((y + c) & 1u)] & 1u) << j;
+    D.planes[((size_t)r * 2 + c) * words_per_plane + t] = word;
+}
+__global__ void k_cls_square_unpack(ClsDev D, uint8_t *bytes) {
+    const uint32_t WPR = D.L >> 6, words_per_plane = D.L * WPR;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, c = blockIdx.z;
+    if (t >= words_per_plane) return;
+    const uint32_t y = t / WPR, w = t - y * WPR;
+    uint8_t *row = bytes + (size_t)r * D.N + (size_t)y * D.L;
+    const uint32_t word = D.planes[((size_t)r * 2 + c) * words_per_plane + t];
+    for (int j = 0; j < 32; j++) row[2 * (32 * w + j) + ((y + c) & 1u)] = (uint8_t)((word >> j) & 1u);
+}
+
+// stream-drawn initial spins (graph.rs:57, :451-453): spin i = top bit of stream word i
+__global__ void k_cls_init_bytes(ClsDev D, uint8_t *bytes) {
+    const uint32_t r = blockIdx.y;
+    const uint64_t key = D.key[r];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.N; i += gridDim.x * blockDim.x)
+        bytes[(size_t)r * D.N + i] = (uint8_t)(stream_word(key, i) >> 63);
+}
+
+// generic-layout energy: graph.rs:430-447 verbatim, one thread per replica chunk, f64 sum in site order
+// is order dependent, so a single thread per replica walks the sites (not on the hot path).
+__global__ void k_cls_generic_energy(ClsDev D, const double *adj_j, const double *biases, double *energy, double *mag) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= D.R) return;
+    const uint8_t *sp = D.spins + (size_t)r * D.N;
+    double acc = 0.0;
+    long long m = 0;
+    for (uint32_t i = 0; i < D.N; i++) {
+        uint32_t si = sp[i];
+        double total_e = 0.0;
+        for (uint32_t e = D.adj_start[i]; e < D.adj_start[i + 1]; e++) {
+            double oc = (si == sp[D.adj_idx[e]]) ? 1.0 : -1.0;
+            total_e += adj_j[e] * oc / 2.0;
+        }
+        double bias_e = si ? -biases[i] : biases[i];
+        acc = acc + total_e + bias_e;
+        m += si ? 1 : -1;
+    }
+    energy[r] = acc;
+    mag[r] = (double)m / (double)D.N;
+}
+
+void launch_cls_generic(const ClsDev &D, uint32_t colour, uint32_t cstart, uint32_t ccount, uint64_t sweep, cudaStream_t st) {
+    uint32_t groups = (ccount + 3) / 4;
+    dim3 grid((groups + 255) / 256, D.R);
+    k_cls_generic<<<grid, 256, 0, st>>>(D, colour, cstart, ccount, sweep);
+}
+void launch_cls_square(const ClsDev &D, uint32_t colour, uint64_t sweep, cudaStream_t st) {
+    uint32_t words = D.L * (D.L >> 6);
+    dim3 grid((words + 255) / 256, D.R);
+    k_cls_square<<<grid, 256, 0, st>>>(D, colour, sweep);
+}
+void launch_cls_square_measure(const ClsDev &D, unsigned long long *unsat, unsigned long long *up, cudaStream_t st) {
+    uint32_t words = D.L * (D.L >> 6);
+    dim3 grid(min((words + 255) / 256, 64u), D.R);
+    k_cls_square_measure<<<grid, 256, 0, st>>>(D, unsat, up);
+}
+void launch_cls_square_pack(const ClsDev &D, const uint8_t *bytes, cudaStream_t st) {
+    uint32_t words = D.L * (D.L >> 6);
+    dim3 grid((words + 255) / 256, D.R, 2);
+    k_cls_square_pack<<<grid, 256, 0, st>>>(D, bytes);
+}
+void launch_cls_square_unpack(const ClsDev &D, uint8_t *bytes, cudaStream_t st) {
+    uint32_t words = D.L * (D.L >> 6);
+    dim3 grid((words + 255) / 256, D.R, 2);
+    k_cls_square_unpack<<<grid, 256, 0, st>>>(D, bytes);
+}
+void launch_cls_init_bytes(const ClsDev &D, uint8_t *bytes, cudaStream_t st) {
+    dim3 grid(min((D.N + 255) / 256, 1024u), D.R);
+    k_cls_init_bytes<<<grid, 256, 0, st>>>(D, bytes);
+}
+void launch_cls_generic_energy(const ClsDev &D, const double *adj_j, const double *biases, double *energy, double *mag, cudaStream_t st) {
+    k_cls_generic_energy<<<(D.R + 63) / 64, 64, 0, st>>>(D, adj_j, biases, energy, mag);
+}

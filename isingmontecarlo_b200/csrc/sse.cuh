@@ -1,0 +1,67 @@
+// sse.cuh -- device-side view of one batched SSE handle (R replicas of one lattice) and the
+// lattice helpers shared by all SSE kernels.  Layout is replica-major structure-of-arrays:
+// every per-slot array is [R][cap] so that a warp working on one replica streams contiguous
+// 128-byte lines of its operator string.
+#pragma once
+#include "common.cuh"
+
+struct SseDev {
+    // lattice (replicated tables, read-only)
+    uint32_t N, E, Nb, Nw;  // variables, edges, bond-index count (qmc_ising.rs:664-670), state words
+    int has_h;              // |h| > f64::EPSILON
+    const uint32_t *va, *vb;
+    const double *J;
+    double gamma, h;
+    // batch
+    uint32_t R;
+    uint64_t cap;  // slots allocated per replica
+    uint32_t *ops;      // [R][cap] operator words
+    uint32_t *state;    // [R][Nw]  spin configuration at p = 0, one bit per variable
+    uint32_t *n;        // [R] number of non-identity ops
+    uint32_t *M;        // [R] cutoff
+    uint64_t *cursor;   // [R] position in the replica's word stream
+    uint64_t *key;      // [R] Philox key
+    double *beta;       // [R]
+    uint64_t *done;     // [R] sweeps completed
+    unsigned long long *sum_n;   // [R] sum of n at sampled sweeps (energy estimator)
+    unsigned long long *vupd;    // [R] sum of n after every sweep (vertex updates)
+    uint32_t *ncl;      // [R] clusters found by the last cluster step
+    uint32_t *ends;     // [R][4] first_p, last_p, first_site_p, (unused)
+    int *status;        // [1] DEV_ERR_* bits
+    // per-variable scratch
+    uint32_t *vfirst, *vlast;  // [R][N] first / last leg (p << 1 | rel) on each variable, or NONE32
+    uint32_t *cur;             // [R][N] FAST: current segment id per variable
+    // STRICT workspace (allocated on demand)
+    uint32_t *links;     // [R][cap][4] prev0, prev1, next0, next1 as (p << 1 | rel) or NONE32
+    uint32_t *bounds;    // [R][cap][2] cluster id of (inputs, outputs) or NONE32
+    uint32_t *frontier;  // [R][2*cap+16]
+    uint32_t *interior;  // [R][4*cap+16]
+    uint32_t *bits;      // [R][cap/32+2] flip bit per cluster (STRICT) / per segment (FAST)
+    uint32_t *frozen;    // [R][cap/32+2] cluster holds a longitudinal op
+    // FAST workspace
+    uint32_t *parent;    // [R][N+cap+1] union-find parents over segment ids
+};
+
+enum { KIND_BOND = 0, KIND_SITE = 1, KIND_LONG = 2 };
+
+// bonds_fn of qmc_ising.rs:671-681
+__device__ __forceinline__ int bond_kind(const SseDev &D, uint32_t b) {
+    return b < D.E ? KIND_BOND : (b < D.E + D.N ? KIND_SITE : KIND_LONG);
+}
+__device__ __forceinline__ void bond_vars(const SseDev &D, uint32_t b, int kind, uint32_t &v0, uint32_t &v1) {
+    if (kind == KIND_BOND) {
+        v0 = __ldg(D.va + b), v1 = __ldg(D.vb + b);
+    } else {
+        v0 = b - D.E - (kind == KIND_LONG ? D.N : 0u), v1 = v0;
+    }
+}
+// diagonal matrix element <s|H_b|s>: qmc_ising.rs:863-888 with inputs == outputs
+__device__ __forceinline__ double bond_weight(const SseDev &D, uint32_t b, int kind, uint32_t s0, uint32_t s1) {
+    if (kind == KIND_BOND) {
+        double j = __ldg(D.J + b);
+        return fabs(j) + (s0 == s1 ? -j : j);
+    }
+    if (kind == KIND_SITE) return D.gamma;
+    return fabs(D.h) + (s0 ? D.h : -D.h);
+}
+__device__ __forceinline__ uint32_t state_bit(const uint32_t *st, uint32_t v) { return (st[v >> 5] >> (v & 31)) & 1u; }

@@ -1,0 +1,471 @@
+// sse_fast.cu -- warp-parallel SSE sweep, FAST cluster order.  One warp per replica; all state
+// that is touched at random (spin bits, per-variable representatives, the RNG window) lives in
+// shared memory, the operator string streams through in coalesced 128-byte lines.
+//
+// Per sweep and replica:
+//  P1  diagonal update (diagonal.rs:142-191), 32 slots per step.  The rule is sequential in p
+//      (live n, data-dependent draw count), so each step is solved as a fixed point: every lane
+//      evaluates its slot for a guessed (stream cursor, n), an exclusive warp scan of the draws /
+//      insertions gives the next guess, and the loop ends when no lane's input changed -- lane i is
+//      exact after at most i+1 rounds, typically 2-4.  The 64 stream words a step can consume are
+//      generated once per step (one Philox4x32-10 call per lane) into shared memory.  The result is
+//      bit-identical to the sequential loop.
+//      Fused into the same pass: world-line segments and their union-find (global memory, lock-free
+//      min-root hooking), so links are never materialised.
+//  P2  resolve one flip bit per segment in increasing id order (parent id < child id).
+//  P3  apply the flips to the operator words (second streaming pass) and to the spins.
+// Contract of the FAST order: oracle.c cluster_update_fast / DESIGN.md.
+#include "sse.cuh"
+
+#define FULL 0xFFFFFFFFu
+#define T_NONE 0
+#define T_EMPTY 1
+#define T_DIAG 2
+#define T_OFFD 3
+
+__device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
+
+// lock-free union-find over global memory; roots are minima, parent[x] <= x always
+__device__ __forceinline__ uint32_t uf_find_cg(uint32_t *P, uint32_t x) {
+    uint32_t p = ld_cg(P + x);
+    while (p != x) {
+        uint32_t gp = ld_cg(P + p);
+        if (gp == p) return p;
+        st_cg(P + x, gp);  // path halving; a stale value is still an ancestor
+        x = gp;
+        p = ld_cg(P + x);
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union_cg(uint32_t *P, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = uf_find_cg(P, a), b = uf_find_cg(P, b);
+        if (a == b) return;
+        if (a > b) {
+            uint32_t t = a;
+            a = b, b = t;
+        }
+        if (atomicCAS(P + b, b, a) == b) return;
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    return x - v;
+}
+
+struct WarpSmem {
+    uint32_t *st;   // [Nw] spin bits at the current p
+    uint32_t *tb;   // [Nw] variable has at least one op
+    uint32_t *cd;   // [Nw] P3: flip decision of the segment currently open on each variable
+    uint32_t *rep;  // [N]  P1: a member of the set of the segment currently open on each variable
+    unsigned long long *win;  // [64] stream words of this step
+    uint32_t *fl;   // [32] variable flipped by the off-diagonal op of lane j (or NONE32)
+    uint32_t *sv;   // [32] variable cut by the site op of lane j (or NONE32)
+};
+
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
+    return ((((size_t)3 * Nw + N + 64) * 4 + 64 * 8) + 15) / 16 * 16;
+}
+
+template <bool HAS_H>
+__global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
+                                                  uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (r >= D.R) return;
+    const uint32_t N = D.N, Nw = D.Nw;
+    WarpSmem S;
+    {
+        unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(N, Nw);
+        S.win = (unsigned long long *)base;
+        uint32_t *u = (uint32_t *)(base + 64 * 8);
+        S.st = u, S.tb = u + Nw, S.cd = u + 2 * Nw, S.rep = u + 3 * Nw, S.fl = u + 3 * Nw + N, S.sv = S.fl + 32;
+    }
+    uint32_t *ops = D.ops + (size_t)r * D.cap;
+    uint32_t *gstate = D.state + (size_t)r * Nw;
+    uint32_t *P = D.parent + (size_t)r * (N + D.cap + 1);
+    const size_t bstride = (size_t)(D.cap / 32 + 2 + N / 32);
+    uint32_t *decb = D.bits + (size_t)r * bstride;
+    uint32_t *frz = D.frozen + (size_t)r * bstride;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint64_t key = D.key[r];
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    const uint64_t range = D.Nb;
+    const uint64_t zone = (range << __clzll((long long)range)) - 1ull;
+    uint64_t done = D.done[r];
+    const uint64_t nsteps = (phases & 8u) ? (target > done ? target - done : 0) : 1;
+    int err = 0;
+
+    for (uint64_t sw = 0; sw < nsteps; sw++) {
+        uint32_t M = D.M[r];
+        if (M > D.cap) {
+            if (lane == 0) atomicOr(D.status, DEV_ERR_CAPACITY);
+            break;
+        }
+        uint32_t n = D.n[r];
+        uint64_t cur = D.cursor[r];
+        const double bn = D.beta[r] * (double)D.Nb;
+        for (uint32_t j = lane; j < Nw; j += 32) S.st[j] = gstate[j], S.tb[j] = 0;
+        const bool do_diag = phases & 1u, do_clus = phases & 2u;
+        if (do_clus) {
+            for (uint32_t v = lane; v < N; v += 32) S.rep[v] = v, st_cg(P + v, v);
+            if (HAS_H)
+                for (uint32_t j = lane; j < (uint32_t)bstride; j += 32) st_cg(frz + j, 0u);
+        }
+        __syncwarp();
+        uint32_t nsite = 0;
+        bool anylong = false;
+
+        // =========================== P1: diagonal update + unions ===========================
+        for (uint32_t base = 0; base < M; base += 32) {
+            const uint32_t p = base + lane;
+            const bool valid = p < M;
+            uint32_t w = valid ? ops[p] : OP_EMPTY;
+            int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
+            uint32_t neww = w;
+            // variables / stored bits of an existing op
+            uint32_t ov0 = 0, ov1 = 0;
+            int okind = KIND_BOND;
+            if (type >= T_DIAG) {
+                okind = bond_kind(D, op_bond(w));
+                bond_vars(D, op_bond(w), okind, ov0, ov1);
+            }
+            if (do_diag) {
+                S.fl[lane] = type == T_OFFD ? ov0 : NONE32;
+                const uint32_t fmask_lt = __ballot_sync(FULL, type == T_OFFD) & lt_mask;
+                __syncwarp();
+                double dnum = 0.0;  // num of an existing diagonal op does not depend on (cursor, n)
+                if (type == T_DIAG) dnum = bn * bond_weight(D, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
+                uint32_t rem = __ballot_sync(FULL, type == T_EMPTY || type == T_DIAG);
+                while (rem) {
+                    const uint64_t wbase = cur & ~1ull;
+                    {  // stream words [wbase, wbase + 64)
+                        const uint64_t blk = (wbase >> 1) + (uint64_t)lane;
+                        Philox4 o = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u, k0, k1);
+                        S.win[2 * lane] = ((unsigned long long)o.y << 32) | o.x;
+                        S.win[2 * lane + 1] = ((unsigned long long)o.w << 32) | o.z;
+                    }
+                    __syncwarp();
+                    const bool inrem = (rem >> lane) & 1u;
+                    uint32_t dc = inrem ? 1u : 0u;
+                    int dn = 0;
+                    bool ovf = false;
+                    uint32_t last_pc = 0xFFFFFFFFu, last_pn = 0xFFFFFFFFu;
+                    uint32_t pc = 0, pn_b = 0;
+                    for (;;) {
+                        // exclusive prefix of (draws, insertions - removals) over the remaining lanes
+                        const uint32_t packed = inrem ? ((dc << 8) | (uint32_t)(dn + 1)) : 0u;
+                        const uint32_t ex = warp_excl_scan(packed, lane);
+                        pc = ex >> 8, pn_b = ex & 0xFFu;  // pn_b = sum of (dn + 1) over earlier remaining lanes
+                        bool changed = false;
+                        if (inrem && (pc != last_pc || pn_b != last_pn)) {
+                            last_pc = pc, last_pn = pn_b;
+                            const uint32_t ni = n + pn_b - (uint32_t)__popc(rem & lt_mask);
+                            uint32_t idx = (uint32_t)(cur - wbase) + pc;
+                            uint32_t ndc = 0;
+                            int ndn = 0;
+                            bool novf = false;
+                            uint32_t nw = w;
+                            if (type == T_EMPTY) {
+                                uint64_t hi = 0, lo;
+                                for (;;) {  // gen_range(0..Nb)
+                                    if (idx + ndc >= 64) { novf = true; break; }
+                                    const uint64_t v = S.win[idx + ndc];
+                                    ndc++;
+                                    hi = __umul64hi(v, range), lo = v * range;
+                                    if (lo <= zone) break;
+                                }
+                                if (!novf) {
+                                    const uint32_t b = (uint32_t)hi;
+                                    const int kind = bond_kind(D, b);
+                                    uint32_t v0, v1;
+                                    bond_vars(D, b, kind, v0, v1);
+                                    uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
+                                    for (uint32_t m = fmask_lt; m; m &= m - 1) {  // flips by earlier lanes of this step
+                                        const uint32_t fv = S.fl[__ffs(m) - 1];
+                                        s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
+                                    }
+                                    const double num = bn * bond_weight(D, b, kind, s0, s1);
+                                    const double den = (double)(M - ni);
+                                    bool accept = num > den;
+                                    if (!accept) {
+                                        const double pr = num / den;
+                                        if (pr == 1.0) accept = true;
+                                        else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                                        else if (idx + ndc >= 64) novf = true;
+                                        else accept = S.win[idx + ndc++] < bool_threshold(pr);
+                                    }
+                                    if (accept) {
+                                        const uint32_t bitsv = s0 | (s1 << 1);
+                                        nw = make_op(b, bitsv, bitsv);
+                                        ndn = 1;
+                                    } else nw = OP_EMPTY;
+                                }
+                            } else {  // T_DIAG
+                                const double den = (double)(M - ni) + 1.0;
+                                bool remove = den > dnum;
+                                if (!remove) {
+                                    const double pr = den / dnum;
+                                    if (pr == 1.0) remove = true;
+                                    else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                                    else if (idx >= 64) novf = true;
+                                    else { remove = S.win[idx] < bool_threshold(pr); ndc = 1; }
+                                }
+                                if (remove) nw = OP_EMPTY, ndn = -1;
+                            }
+                            if (novf) ndc = 0, ndn = 0;
+                            changed = ndc != dc || ndn != dn || novf != ovf;
+                            dc = ndc, dn = ndn, ovf = novf, neww = nw;
+                        }
+                        if (!__any_sync(FULL, changed)) break;
+                    }
+                    // lanes before the first window overflow are final
+                    const uint32_t ovm = __ballot_sync(FULL, inrem && ovf);
+                    const uint32_t okm = ovm ? (rem & ((1u << (__ffs(ovm) - 1)) - 1u)) : rem;
+                    // advance (cursor, n) past the committed lanes
+                    const uint32_t tot = __reduce_add_sync(FULL, ((okm >> lane) & 1u) ? dc : 0u);
+                    const int totn = (int)__reduce_add_sync(FULL, ((okm >> lane) & 1u) ? (uint32_t)(dn + 1) : 0u) - __popc(okm);
+                    cur += tot;
+                    n = (uint32_t)((int)n + totn);
+                    rem &= ~okm;
+                    if (ovm && okm == 0 && ((cur & ~1ull) == wbase)) {  // cannot happen: a fresh window holds >= 63 words
+                        err |= DEV_ERR_INVARIANT;
+                        rem = 0;
+                    }
+                    __syncwarp();
+                }
+                if (__any_sync(FULL, neww != w)) {
+                    if (valid && neww != w) ops[p] = neww;
+                }
+                if (type == T_OFFD) atomicXor(&S.st[ov0 >> 5], 1u << (ov0 & 31));
+                __syncwarp();
+            }
+            if (do_clus) {
+                // ---- segments and unions on the final ops of this step
+                const uint32_t fw = neww;
+                int kind = -1;
+                uint32_t v0 = 0, v1 = 0;
+                if (valid && fw != OP_EMPTY) {
+                    kind = bond_kind(D, op_bond(fw));
+                    bond_vars(D, op_bond(fw), kind, v0, v1);
+                }
+                S.sv[lane] = kind == KIND_SITE ? v0 : NONE32;
+                const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
+                __syncwarp();
+                const uint32_t myid = N + nsite + (uint32_t)__popc(smask & lt_mask);
+                if (kind == KIND_SITE) st_cg(P + myid, myid);
+                if (kind >= 0) {
+                    atomicOr(&S.tb[v0 >> 5], 1u << (v0 & 31));
+                    if (kind == KIND_BOND) atomicOr(&S.tb[v1 >> 5], 1u << (v1 & 31));
+                }
+                uint32_t ra = 0, rb = 0;
+                if (kind == KIND_BOND || (HAS_H && kind == KIND_LONG)) {
+                    ra = S.rep[v0], rb = kind == KIND_BOND ? S.rep[v1] : 0u;
+                    for (uint32_t m = smask & lt_mask; m; m &= m - 1) {
+                        const int j = __ffs(m) - 1;
+                        const uint32_t cv = S.sv[j], id = N + nsite + (uint32_t)__popc(smask & ((1u << j) - 1u));
+                        if (cv == v0) ra = id;
+                        if (kind == KIND_BOND && cv == v1) rb = id;
+                    }
+                }
+                __syncwarp();  // new ids are initialised before anyone follows them
+                if (kind == KIND_BOND) {
+                    if (ra != rb) uf_union_cg(P, ra, rb);
+                } else if (HAS_H && kind == KIND_LONG) {
+                    atomicOr(&frz[ra >> 5], 1u << (ra & 31));
+                    anylong = true;
+                }
+                // the site op with the highest lane owns the variable from here on (ids grow with lane)
+                if (kind == KIND_SITE) atomicMax(&S.rep[v0], myid);
+                nsite += (uint32_t)__popc(smask);
+                __syncwarp();
+            }
+        }
+        if (do_diag && lane == 0) D.n[r] = n;
+
+        uint32_t ncl = 0;
+        if (do_clus && n > 0) {
+            // periodic closure: the segment open at the end of variable v is the one crossing p = 0
+            for (uint32_t v = lane; v < N; v += 32) {
+                const uint32_t rp = S.rep[v];
+                if (rp != v) uf_union_cg(P, v, rp);
+            }
+            __syncwarp();
+            __threadfence_block();
+            const uint64_t c0 = cur;
+            const uint32_t nseg = N + nsite;
+            const uint32_t nwords = (nseg + 31) / 32;
+            bool frozen_all = false;
+            if (HAS_H) {
+                frozen_all = __any_sync(FULL, anylong);
+                // push frozen marks up to the roots: descending ids, parents are smaller
+                for (int32_t wd = (int32_t)nwords - 1; wd >= 0; wd--) {
+                    const uint32_t x = (uint32_t)wd * 32 + lane;
+                    uint32_t par = x < nseg ? ld_cg(P + x) : x;
+                    for (;;) {
+                        const uint32_t fzw = *(volatile uint32_t *)&frz[wd];
+                        const bool mine = x < nseg && ((fzw >> lane) & 1u) && par != x;
+                        bool changed = false;
+                        if (mine) {
+                            const uint32_t old = atomicOr(&frz[par >> 5], 1u << (par & 31));
+                            changed = ((old >> (par & 31)) & 1u) == 0 && (par >> 5) == (uint32_t)wd;
+                        }
+                        if (!__any_sync(FULL, changed)) break;
+                    }
+                    __syncwarp();
+                }
+            }
+            // =========================== P2: one flip bit per segment ===========================
+            uint32_t nroots = 0;
+            Philox4 rb4 = {0, 0, 0, 0};
+            for (uint32_t wd = 0; wd < nwords; wd++) {
+                const uint32_t x = wd * 32 + lane;
+                if ((wd & 3u) == 0) rb4 = philox4x32_10(wd >> 2, (uint32_t)c0, (uint32_t)(c0 >> 32), QMCB_TAG_CLUS, k0, k1);
+                const uint32_t rword = (wd & 3u) == 0 ? rb4.x : ((wd & 3u) == 1 ? rb4.y : ((wd & 3u) == 2 ? rb4.z : rb4.w));
+                uint32_t par = x < nseg ? ld_cg(P + x) : x;
+                if (nsite == 0) par = x < nseg ? 0u : x;  // cluster.rs:98-107: no cluster edge => one cluster
+                const bool root = x < nseg && par == x;
+                nroots += (uint32_t)__popc(__ballot_sync(FULL, root));
+                bool dec = false, known = root || x >= nseg;
+                if (root) {
+                    dec = (rword >> lane) & 1u;
+                    if (HAS_H) dec = dec && !((nsite == 0) ? frozen_all : ((ld_cg(frz + wd) >> lane) & 1u));
+                } else if (x < nseg && par < wd * 32) {
+                    dec = (ld_cg(decb + (par >> 5)) >> (par & 31)) & 1u;
+                    known = true;
+                }
+                // parents inside this word: resolve by rounds (parent id < child id)
+                for (;;) {
+                    const uint32_t kmask = __ballot_sync(FULL, known), dmask = __ballot_sync(FULL, dec);
+                    if (kmask == FULL) {
+                        if (lane == 0) st_cg(decb + wd, dmask);
+                        break;
+                    }
+                    if (!known) {
+                        const uint32_t pl = par - wd * 32;
+                        if ((kmask >> pl) & 1u) dec = (dmask >> pl) & 1u, known = true;
+                    }
+                }
+                __syncwarp();
+            }
+            uint32_t untouched = 0;
+            for (uint32_t j = lane; j < Nw; j += 32) {
+                const uint32_t validm = (j == Nw - 1 && (N & 31u)) ? ((1u << (N & 31u)) - 1u) : FULL;
+                untouched += (uint32_t)__popc(~S.tb[j] & validm);
+            }
+            untouched = __reduce_add_sync(FULL, untouched);
+            ncl = nsite == 0 ? 1u : nroots - untouched;
+
+            // =========================== P3: apply the flips ===========================
+            for (uint32_t j = lane; j < Nw; j += 32) S.cd[j] = ld_cg(decb + j);
+            __syncwarp();
+            uint32_t ks = 0;
+            for (uint32_t base = 0; base < M; base += 32) {
+                const uint32_t p = base + lane;
+                const uint32_t w = p < M ? ops[p] : OP_EMPTY;
+                int kind = -1;
+                uint32_t v0 = 0, v1 = 0;
+                if (w != OP_EMPTY) {
+                    kind = bond_kind(D, op_bond(w));
+                    bond_vars(D, op_bond(w), kind, v0, v1);
+                }
+                S.sv[lane] = kind == KIND_SITE ? v0 : NONE32;
+                const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
+                bool outdec = false;
+                if (kind == KIND_SITE) {
+                    const uint32_t id = N + ks + (uint32_t)__popc(smask & lt_mask);
+                    outdec = (ld_cg(decb + (id >> 5)) >> (id & 31)) & 1u;
+                }
+                const uint32_t odmask = __ballot_sync(FULL, outdec);
+                __syncwarp();
+                if (kind >= 0) {
+                    bool din = (S.cd[v0 >> 5] >> (v0 & 31)) & 1u;
+                    for (uint32_t m = smask & lt_mask; m; m &= m - 1) {
+                        const int j = __ffs(m) - 1;
+                        if (S.sv[j] == v0) din = (odmask >> j) & 1u;
+                    }
+                    const uint32_t mask = kind == KIND_BOND ? 3u : 1u;
+                    const bool dout = kind == KIND_SITE ? outdec : din;
+                    if (din || dout) ops[p] = make_op(op_bond(w), op_in(w) ^ (din ? mask : 0u), op_out(w) ^ (dout ? mask : 0u));
+                }
+                __syncwarp();
+                if (kind == KIND_SITE) {  // the last site op of the step on this variable sets the open decision
+                    bool lastone = true;
+                    for (uint32_t m = smask & ~lt_mask & ~(1u << lane); m; m &= m - 1)
+                        if (S.sv[__ffs(m) - 1] == v0) lastone = false;
+                    if (lastone) {
+                        if (outdec) atomicOr(&S.cd[v0 >> 5], 1u << (v0 & 31));
+                        else atomicAnd(&S.cd[v0 >> 5], ~(1u << (v0 & 31)));
+                    }
+                }
+                ks += (uint32_t)__popc(smask);
+                __syncwarp();
+            }
+            // spins: the segment of variable v crossing p = 0 has id v
+            for (uint32_t j = lane; j < Nw; j += 32) S.st[j] ^= ld_cg(decb + j) & S.tb[j];
+            cur = c0 + 1;
+            __syncwarp();
+        }
+        if (do_clus) {
+            // free spins: qmc_ising.rs:780-784
+            for (uint32_t base = 0; base < N; base += 32) {
+                const uint32_t v = base + lane;
+                const bool fr = v < N && !((S.tb[v >> 5] >> (v & 31)) & 1u);
+                const uint32_t m = __ballot_sync(FULL, fr);
+                bool bit = false;
+                if (fr) bit = stream_word(key, cur + __popc(m & lt_mask)) < 0x8000000000000000ull;
+                const uint32_t setm = __ballot_sync(FULL, bit);
+                if (lane == 0 && m) S.st[base >> 5] = (S.st[base >> 5] & ~m) | setm;
+                cur += __popc(m);
+            }
+            __syncwarp();
+            if (lane == 0) D.ncl[r] = ncl;
+        }
+        for (uint32_t j = lane; j < Nw; j += 32) gstate[j] = S.st[j];
+        if (lane == 0) {
+            D.cursor[r] = cur;
+            if (phases & 4u) {
+                const uint32_t grown = n + n / 2;  // qmc_ising.rs:786
+                if (grown > M) D.M[r] = grown;
+            }
+        }
+        if (phases & 8u) {
+            done++;
+            const uint64_t idx = done - sample_origin;
+            if (lane == 0) D.vupd[r] += n;
+            if (idx % sample_freq == 0) {
+                if (lane == 0) D.sum_n[r] += n;
+                if (samples) {
+                    uint8_t *dst = samples + ((size_t)r * samples_per_rep + (idx / sample_freq - 1)) * N;
+                    for (uint32_t v = lane; v < N; v += 32) dst[v] = (uint8_t)state_bit(S.st, v);
+                }
+            }
+            if (lane == 0) D.done[r] = done;
+        }
+        __syncwarp();
+    }
+    if (err) atomicOr(D.status, err);
+}
+
+// returns the number of kernel launches, or -1 if this shape is not supported by the warp kernels
+int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
+                    uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
+    const size_t per_warp = warp_smem_bytes(D.N, D.Nw);
+    int warps = 4;
+    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+    if (per_warp * warps > 200 * 1024) return -1;
+    const size_t smem = per_warp * warps;
+    const uint32_t blocks = (D.R + warps - 1) / warps;
+    auto kern = D.has_h ? k_sse_fast<true> : k_sse_fast<false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    kern<<<blocks, warps * 32, smem, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep);
+    return 1;
+}

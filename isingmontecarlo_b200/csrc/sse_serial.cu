@@ -1,0 +1,570 @@
+// sse_serial.cu -- reference-order SSE sweep, one warp per replica.
+//
+// This is the STRICT path: the diagonal update walks the slots in order with a live n and the
+// cluster update numbers clusters in the reference's LIFO discovery order, so under the same
+// injected word stream the spins and operator strings are bit-identical to the reference's own
+// update path (diagonal.rs:142-191, cluster.rs:36-271, qmc_ising.rs:644-795).  The order-dependent
+// parts run on lane 0 of the replica's warp; initialisation, flip-bit generation, the flip/apply
+// pass, free-spin draws and sampling use all 32 lanes with coalesced accesses.
+// It also carries a serial FAST-order cluster step used as the on-device cross-check of the
+// warp-parallel FAST kernels in sse_fast.cu.
+#include "sse.cuh"
+
+#define SIDE_IN 0u
+#define SIDE_OUT 1u
+
+struct Rep {
+    uint32_t *ops, *state, *vfirst, *vlast, *cur, *links, *bounds, *frontier, *interior, *bits, *frozen, *parent;
+    uint32_t *ends;
+    uint64_t fcap, icap;
+};
+
+__device__ __forceinline__ Rep rep_view(const SseDev &D, uint32_t r) {
+    Rep v;
+    v.ops = D.ops + (size_t)r * D.cap;
+    v.state = D.state + (size_t)r * D.Nw;
+    v.vfirst = D.vfirst + (size_t)r * D.N;
+    v.vlast = D.vlast + (size_t)r * D.N;
+    v.cur = D.cur + (size_t)r * D.N;
+    v.links = D.links ? D.links + (size_t)r * D.cap * 4 : nullptr;
+    v.bounds = D.bounds ? D.bounds + (size_t)r * D.cap * 2 : nullptr;
+    v.fcap = 2 * D.cap + 16, v.icap = 4 * D.cap + 16;
+    v.frontier = D.frontier ? D.frontier + (size_t)r * v.fcap : nullptr;
+    v.interior = D.interior ? D.interior + (size_t)r * v.icap : nullptr;
+    v.bits = D.bits + (size_t)r * (D.cap / 32 + 2 + D.N / 32);
+    v.frozen = D.frozen + (size_t)r * (D.cap / 32 + 2 + D.N / 32);
+    v.parent = D.parent ? D.parent + (size_t)r * (D.N + D.cap + 1) : nullptr;
+    v.ends = D.ends + (size_t)r * 4;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// diagonal update (diagonal.rs:114-135, :142-191; slot loop fast_ops.rs:611-637), lane 0
+// ------------------------------------------------------------------------------------------
+__device__ void diag_serial(const SseDev &D, uint32_t r, const Rep &V) {
+    const uint32_t M = D.M[r];
+    uint32_t n = D.n[r];
+    uint64_t cur = D.cursor[r];
+    const uint64_t key = D.key[r];
+    const double bn = D.beta[r] * (double)D.Nb;  // diagonal.rs:168, left-to-right product
+    const uint64_t range = D.Nb;
+    const uint64_t zone = (range << __clzll((long long)range)) - 1ull;
+    int err = 0;
+    for (uint32_t p = 0; p < M; p++) {
+        uint32_t w = V.ops[p];
+        uint32_t b;
+        if (w == OP_EMPTY) {
+            uint64_t hi, lo;  // gen_range(0..Nb): widening multiply + zone rejection
+            do {
+                uint64_t v = stream_word(key, cur++);
+                hi = __umul64hi(v, range), lo = v * range;
+            } while (lo > zone);
+            b = (uint32_t)hi;
+        } else if (op_is_diag(w)) {
+            b = op_bond(w);
+        } else {  // off-diagonal: propagate the state (diagonal.rs:154-160)
+            int kind = bond_kind(D, op_bond(w));
+            uint32_t v0, v1;
+            bond_vars(D, op_bond(w), kind, v0, v1);
+            uint32_t o = op_out(w);
+            V.state[v0 >> 5] = (V.state[v0 >> 5] & ~(1u << (v0 & 31))) | ((o & 1u) << (v0 & 31));
+            if (kind == KIND_BOND) V.state[v1 >> 5] = (V.state[v1 >> 5] & ~(1u << (v1 & 31))) | (((o >> 1) & 1u) << (v1 & 31));
+            continue;
+        }
+        int kind = bond_kind(D, b);
+        uint32_t v0, v1;
+        bond_vars(D, b, kind, v0, v1);
+        uint32_t s0 = state_bit(V.state, v0), s1 = kind == KIND_BOND ? state_bit(V.state, v1) : 0u;
+        double num = bn * bond_weight(D, b, kind, s0, s1);
+        double den = (double)(M - n);
+        if (w == OP_EMPTY) {
+            bool accept = num > den;
+            if (!accept) {
+                double pr = num / den;
+                if (pr == 1.0) accept = true;
+                else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                else accept = stream_word(key, cur++) < bool_threshold(pr);
+            }
+            if (accept) {
+                uint32_t bitsv = s0 | (s1 << 1);
+                V.ops[p] = make_op(b, bitsv, bitsv);
+                n++;
+            }
+        } else {
+            den = den + 1.0;
+            bool remove = den > num;
+            if (!remove) {
+                double pr = den / num;
+                if (pr == 1.0) remove = true;
+                else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                else remove = stream_word(key, cur++) < bool_threshold(pr);
+            }
+            if (remove) {
+                V.ops[p] = OP_EMPTY;
+                n--;
+            }
+        }
+    }
+    D.n[r] = n;
+    D.cursor[r] = cur;
+    if (err) atomicOr(D.status, err);
+}
+
+// ------------------------------------------------------------------------------------------
+// links (what FastOps::mutate_p maintains incrementally, fast_ops.rs:337-607), lane 0
+// ------------------------------------------------------------------------------------------
+__device__ void links_serial(const SseDev &D, uint32_t r, const Rep &V, bool full) {
+    const uint32_t M = D.M[r];
+    uint32_t first_p = NONE32, last_p = NONE32, first_site = NONE32;
+    for (uint32_t p = 0; p < M; p++) {
+        uint32_t w = V.ops[p];
+        if (w == OP_EMPTY) continue;
+        uint32_t b = op_bond(w);
+        int kind = bond_kind(D, b);
+        uint32_t vv[2];
+        bond_vars(D, b, kind, vv[0], vv[1]);
+        int nv = kind == KIND_BOND ? 2 : 1;
+        if (first_p == NONE32) first_p = p;
+        last_p = p;
+        if (kind == KIND_SITE && first_site == NONE32) first_site = p;
+        if (full) V.links[4 * (size_t)p + 1] = NONE32, V.links[4 * (size_t)p + 3] = NONE32;
+        for (int k = 0; k < nv; k++) {
+            uint32_t v = vv[k], me = (p << 1) | (uint32_t)k;
+            uint32_t prev = V.vlast[v];
+            if (full) {
+                V.links[4 * (size_t)p + k] = prev;
+                V.links[4 * (size_t)p + 2 + k] = NONE32;
+                if (prev != NONE32) V.links[4 * (size_t)(prev >> 1) + 2 + (prev & 1u)] = me;
+            }
+            if (prev == NONE32) V.vfirst[v] = me;
+            V.vlast[v] = me;
+        }
+    }
+    V.ends[0] = first_p, V.ends[1] = last_p, V.ends[2] = first_site;
+}
+
+// ------------------------------------------------------------------------------------------
+// STRICT cluster labelling: cluster.rs:46-108 (frontier loop) and :193-271 (expansion), lane 0
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool set_boundary(const Rep &V, uint32_t p, uint32_t side, uint32_t c, int &err) {
+    uint32_t *slot = V.bounds + 2 * (size_t)p + side;  // cluster.rs:289-306
+    if (*slot == NONE32 || *slot == c) *slot = c;
+    else err |= DEV_ERR_INVARIANT;  // unreachable!() in the reference
+    return V.bounds[2 * (size_t)p] != NONE32 && V.bounds[2 * (size_t)p + 1] != NONE32;
+}
+
+__device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
+    const uint32_t last_p = V.ends[1], cp = V.ends[2];
+    const uint32_t E = D.E, EN = D.E + D.N;
+    uint64_t flen = 0, ilen = 0;
+    V.frontier[flen++] = (cp << 1) | SIDE_OUT;  // cluster.rs:57-59
+    V.frontier[flen++] = (cp << 1) | SIDE_IN;
+    uint32_t cnum = 0, scan = 0;
+    for (;;) {
+        while (flen) {  // :62-80
+            uint32_t e = V.frontier[--flen];
+            uint32_t p0 = e >> 1, side0 = e & 1u;
+            if (V.bounds[2 * (size_t)p0] != NONE32 && V.bounds[2 * (size_t)p0 + 1] != NONE32) continue;
+            // ---- expand_whole_cluster(p0, (0, side0), cnum) :193-271
+            {
+                uint32_t b0 = op_bond(V.ops[p0]);
+                bool edge0 = b0 >= E && b0 < EN;
+                ilen = 0;
+                if (!edge0) {  // :205-211
+                    int nv = b0 < E ? 2 : 1;
+                    for (int k = 0; k < nv; k++) V.interior[ilen++] = (p0 << 2) | ((uint32_t)k << 1) | SIDE_IN;
+                    for (int k = 0; k < nv; k++) V.interior[ilen++] = (p0 << 2) | ((uint32_t)k << 1) | SIDE_OUT;
+                } else {
+                    V.interior[ilen++] = (p0 << 2) | side0;  // :212-215
+                }
+                while (ilen) {
+                    uint32_t it = V.interior[--ilen];
+                    uint32_t p = it >> 2, rel = (it >> 1) & 1u, side = it & 1u;
+                    set_boundary(V, p, side, cnum, err);  // :218
+                    uint32_t lk = V.links[4 * (size_t)p + 2 * side + rel];
+                    uint32_t sq = side ^ 1u;
+                    if (lk == NONE32) {  // wrap through the ends of the world line :224-241
+                        uint32_t b = op_bond(V.ops[p]);
+                        int kind = bond_kind(D, b);
+                        uint32_t v0, v1;
+                        bond_vars(D, b, kind, v0, v1);
+                        uint32_t var = rel ? v1 : v0;
+                        lk = side == SIDE_IN ? V.vlast[var] : V.vfirst[var];
+                    }
+                    uint32_t q = lk >> 1, rq = lk & 1u;
+                    uint32_t bq = op_bond(V.ops[q]);
+                    if (bq >= E && bq < EN) {  // cluster edge :245-248
+                        if (!set_boundary(V, q, sq, cnum, err)) {
+                            if (flen >= V.fcap) { err |= DEV_ERR_STACK; } else V.frontier[flen++] = (q << 1) | (sq ^ 1u);
+                        }
+                    } else {  // interior op :249-268
+                        uint32_t a = V.bounds[2 * (size_t)q], bb = V.bounds[2 * (size_t)q + 1];
+                        bool ok = (a == NONE32 && bb == NONE32) || (a == cnum && bb == NONE32) || (a == NONE32 && bb == cnum);
+                        if (ok) {
+                            V.bounds[2 * (size_t)q] = cnum, V.bounds[2 * (size_t)q + 1] = cnum;
+                            int nvq = bq < E ? 2 : 1;
+                            if (ilen + 4 > V.icap) { err |= DEV_ERR_STACK; break; }
+                            for (int k = 0; k < nvq; k++)
+                                if (!((uint32_t)k == rq && sq == SIDE_IN)) V.interior[ilen++] = (q << 2) | ((uint32_t)k << 1) | SIDE_IN;
+                            for (int k = 0; k < nvq; k++)
+                                if (!((uint32_t)k == rq && sq == SIDE_OUT)) V.interior[ilen++] = (q << 2) | ((uint32_t)k << 1) | SIDE_OUT;
+                        }
+                    }
+                }
+            }
+            cnum++;
+        }
+        uint32_t unmapped = NONE32;  // :82-88 (the smallest unmapped p never decreases)
+        for (; scan <= last_p; scan++) {
+            if (V.ops[scan] != OP_EMPTY && V.bounds[2 * (size_t)scan] == NONE32 && V.bounds[2 * (size_t)scan + 1] == NONE32) {
+                unmapped = scan;
+                break;
+            }
+        }
+        if (unmapped == NONE32) break;
+        V.frontier[flen++] = (unmapped << 1) | SIDE_OUT;  // :89-91
+        V.frontier[flen++] = (unmapped << 1) | SIDE_IN;
+    }
+    return cnum;
+}
+
+// flip_each_cluster_rng (cluster.rs:36-172), whole warp; returns n_clusters
+__device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, int lane) {
+    const uint32_t n = D.n[r];
+    if (n == 0) return 0;  // :46-48
+    const uint32_t last_p = V.ends[1], cp = V.ends[2];
+    for (uint32_t p = lane; p <= last_p; p += 32) V.bounds[2 * (size_t)p] = NONE32, V.bounds[2 * (size_t)p + 1] = NONE32;
+    __syncwarp();
+    uint32_t ncl = 1;
+    int err = 0;
+    if (cp != NONE32) {
+        if (lane == 0) ncl = label_strict(D, V, err);
+        ncl = __shfl_sync(0xFFFFFFFFu, ncl, 0);
+    } else {  // :98-107 the whole thing is one cluster
+        for (uint32_t p = lane; p <= last_p; p += 32)
+            if (V.ops[p] != OP_EMPTY) V.bounds[2 * (size_t)p] = 0, V.bounds[2 * (size_t)p + 1] = 0;
+    }
+    if (err) atomicOr(D.status, err);
+    __syncwarp();
+    // flips: one gen_bool per cluster in id order (:111-137).  With a longitudinal field the
+    // weight product is 0.0 for a cluster holding a longitudinal op (qmc_ising.rs:759-775):
+    // gen_bool(0.0) still consumes its word and returns false.
+    const uint32_t nwords = (ncl + 31) / 32;
+    const uint64_t key = D.key[r], c0 = D.cursor[r];
+    if (D.has_h) {
+        for (uint32_t j = lane; j < nwords; j += 32) V.frozen[j] = 0;
+        __syncwarp();
+        for (uint32_t p = lane; p <= last_p; p += 32) {
+            uint32_t w = V.ops[p];
+            if (w != OP_EMPTY && op_bond(w) >= D.E + D.N) {
+                uint32_t c = V.bounds[2 * (size_t)p];
+                atomicOr(&V.frozen[c >> 5], 1u << (c & 31));
+            }
+        }
+        __syncwarp();
+    }
+    for (uint32_t base = 0; base < ncl; base += 32) {
+        uint32_t k = base + lane;
+        bool f = false;
+        if (k < ncl) f = stream_word(key, c0 + k) < 0x8000000000000000ull;
+        uint32_t word = __ballot_sync(0xFFFFFFFFu, f);
+        if (lane == 0) V.bits[base >> 5] = D.has_h ? (word & ~V.frozen[base >> 5]) : word;
+    }
+    __syncwarp();
+    // apply (:139-167)
+    for (uint32_t p = lane; p <= last_p; p += 32) {
+        uint32_t w = V.ops[p];
+        if (w == OP_EMPTY) continue;
+        uint32_t ci = V.bounds[2 * (size_t)p], co = V.bounds[2 * (size_t)p + 1];
+        bool fi = (V.bits[ci >> 5] >> (ci & 31)) & 1u, fo = (V.bits[co >> 5] >> (co & 31)) & 1u;
+        uint32_t b = op_bond(w);
+        int kind = bond_kind(D, b);
+        uint32_t mask = kind == KIND_BOND ? 3u : 1u;
+        uint32_t in = op_in(w) ^ (fi ? mask : 0u), out = op_out(w) ^ (fo ? mask : 0u);
+        if (fi) {
+            uint32_t vv[2];
+            bond_vars(D, b, kind, vv[0], vv[1]);
+            for (int k = 0; k < (kind == KIND_BOND ? 2 : 1); k++) {
+                if (V.links[4 * (size_t)p + k] == NONE32) {  // first op on this world line
+                    uint32_t v = vv[k], bit = 1u << (v & 31);
+                    if ((in >> k) & 1u) atomicOr(&V.state[v >> 5], bit);
+                    else atomicAnd(&V.state[v >> 5], ~bit);
+                }
+            }
+        }
+        if (fi || fo) V.ops[p] = make_op(b, in, out);
+    }
+    if (lane == 0) D.cursor[r] = c0 + ncl;
+    __syncwarp();
+    return ncl;
+}
+
+// ------------------------------------------------------------------------------------------
+// FAST-order cluster step, serial restatement (oracle.c cluster_update_fast), lane 0
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t uf_find(uint32_t *uf, uint32_t x) {
+    while (uf[x] != x) {
+        uf[x] = uf[uf[x]];
+        x = uf[x];
+    }
+    return x;
+}
+__device__ __forceinline__ bool fast_flip_bit(uint64_t key, uint64_t c0, uint32_t root) {
+    Philox4 o = philox4x32_10(root >> 7, (uint32_t)c0, (uint32_t)(c0 >> 32), QMCB_TAG_CLUS, (uint32_t)key, (uint32_t)(key >> 32));
+    uint32_t sel = (root >> 5) & 3u;
+    uint32_t x = sel == 0 ? o.x : (sel == 1 ? o.y : (sel == 2 ? o.z : o.w));
+    return (x >> (root & 31)) & 1u;
+}
+
+__device__ uint32_t cluster_fast_serial(const SseDev &D, uint32_t r, const Rep &V, int lane) {
+    const uint32_t n = D.n[r];
+    if (n == 0) return 0;
+    uint32_t ncl = 0;
+    if (lane == 0) {
+        const uint32_t N = D.N, E = D.E, EN = D.E + D.N, last_p = V.ends[1];
+        uint32_t *uf = V.parent;
+        for (uint32_t v = 0; v < N; v++) uf[v] = v, V.cur[v] = v;
+        uint32_t nsite = 0;
+        for (uint32_t p = 0; p <= last_p; p++) {
+            uint32_t w = V.ops[p];
+            if (w == OP_EMPTY) continue;
+            uint32_t b = op_bond(w);
+            if (b >= E && b < EN) {
+                uint32_t id = N + nsite++;
+                uf[id] = id;
+                V.cur[b - E] = id;
+            } else if (b < E) {
+                uint32_t x = uf_find(uf, V.cur[__ldg(D.va + b)]), y = uf_find(uf, V.cur[__ldg(D.vb + b)]);
+                if (x < y) uf[y] = x;
+                else if (y < x) uf[x] = y;
+            }
+        }
+        for (uint32_t v = 0; v < N; v++) {
+            uint32_t x = uf_find(uf, v), y = uf_find(uf, V.cur[v]);
+            if (x < y) uf[y] = x;
+            else if (y < x) uf[x] = y;
+        }
+        const uint32_t nseg = N + nsite, nw = (nseg + 31) / 32;
+        if (nsite == 0)
+            for (uint32_t x = 0; x < nseg; x++) uf[x] = 0;
+        // frozen roots, used roots
+        for (uint32_t j = 0; j < nw; j++) V.frozen[j] = 0, V.bits[j] = 0;
+        for (uint32_t v = 0; v < N; v++) V.cur[v] = v;
+        nsite = 0;
+        for (uint32_t p = 0; p <= last_p; p++) {
+            uint32_t w = V.ops[p];
+            if (w == OP_EMPTY) continue;
+            uint32_t b = op_bond(w);
+            uint32_t ri, ro;
+            if (b >= E && b < EN) {
+                ri = uf_find(uf, V.cur[b - E]);
+                uint32_t id = N + nsite++;
+                V.cur[b - E] = id;
+                ro = uf_find(uf, id);
+            } else {
+                uint32_t v0 = b < E ? __ldg(D.va + b) : b - EN;
+                ri = ro = uf_find(uf, V.cur[v0]);
+                if (b >= EN) V.frozen[ri >> 5] |= 1u << (ri & 31);
+            }
+            V.bits[ri >> 5] |= 1u << (ri & 31), V.bits[ro >> 5] |= 1u << (ro & 31);
+        }
+        for (uint32_t j = 0; j < nw; j++) ncl += __popc(V.bits[j]);
+        // apply
+        const uint64_t key = D.key[r], c0 = D.cursor[r];
+        for (uint32_t v = 0; v < N; v++) V.cur[v] = v;
+        nsite = 0;
+        for (uint32_t p = 0; p <= last_p; p++) {
+            uint32_t w = V.ops[p];
+            if (w == OP_EMPTY) continue;
+            uint32_t b = op_bond(w);
+            uint32_t ri, ro, mask = b < E ? 3u : 1u;
+            if (b >= E && b < EN) {
+                ri = uf_find(uf, V.cur[b - E]);
+                uint32_t id = N + nsite++;
+                V.cur[b - E] = id;
+                ro = uf_find(uf, id);
+            } else {
+                uint32_t v0 = b < E ? __ldg(D.va + b) : b - EN;
+                ri = ro = uf_find(uf, V.cur[v0]);
+            }
+            bool fi = !((V.frozen[ri >> 5] >> (ri & 31)) & 1u) && fast_flip_bit(key, c0, ri);
+            bool fo = ri == ro ? fi : (!((V.frozen[ro >> 5] >> (ro & 31)) & 1u) && fast_flip_bit(key, c0, ro));
+            if (fi || fo) V.ops[p] = make_op(b, op_in(w) ^ (fi ? mask : 0u), op_out(w) ^ (fo ? mask : 0u));
+        }
+        // state: the segment of variable v crossing p = 0 has id v
+        for (uint32_t v = 0; v < N; v++) {
+            if (V.vfirst[v] == NONE32) continue;
+            uint32_t rt = uf_find(uf, v);
+            if (!((V.frozen[rt >> 5] >> (rt & 31)) & 1u) && fast_flip_bit(key, c0, rt)) V.state[v >> 5] ^= 1u << (v & 31);
+        }
+        D.cursor[r] = c0 + 1;
+    }
+    ncl = __shfl_sync(0xFFFFFFFFu, ncl, 0);
+    __syncwarp();
+    return ncl;
+}
+
+// free spins: qmc_ising.rs:780-784, one gen_bool(0.5) per op-less variable in ascending order
+__device__ void free_spins(const SseDev &D, uint32_t r, const Rep &V, int lane) {
+    const uint64_t key = D.key[r];
+    uint64_t cur = D.cursor[r];
+    for (uint32_t base = 0; base < D.N; base += 32) {
+        uint32_t v = base + lane;
+        bool fr = v < D.N && V.vfirst[v] == NONE32;
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, fr);
+        bool bit = false;
+        if (fr) bit = stream_word(key, cur + __popc(m & ((1u << lane) - 1u))) < 0x8000000000000000ull;
+        uint32_t setm = __ballot_sync(0xFFFFFFFFu, bit);
+        if (lane == 0 && m) V.state[base >> 5] = (V.state[base >> 5] & ~m) | setm;
+        cur += __popc(m);
+    }
+    __syncwarp();
+    if (lane == 0) D.cursor[r] = cur;
+}
+
+// phases: bit0 diagonal update, bit1 cluster update + free spins, bit2 cutoff growth,
+// bit3 bookkeeping of a full timestep (done counter, estimators, sampling)
+__global__ void __launch_bounds__(128) k_sse_serial(SseDev D, int mode, uint64_t target, uint32_t phases,
+                                                    uint64_t sample_freq, uint64_t sample_origin,
+                                                    uint8_t *samples, uint64_t samples_per_rep) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= D.R) return;
+    const Rep V = rep_view(D, r);
+    uint64_t done = D.done[r];
+    const uint64_t nsteps = (phases & 8u) ? (target > done ? target - done : 0) : 1;
+    for (uint64_t s = 0; s < nsteps; s++) {
+        if (D.M[r] > D.cap) {  // cannot run this sweep: host must grow the arrays first
+            if (lane == 0) atomicOr(D.status, DEV_ERR_CAPACITY);
+            break;
+        }
+        if (phases & 1u) {
+            if (lane == 0) diag_serial(D, r, V);
+            __syncwarp();
+        }
+        if (phases & 2u) {
+            for (uint32_t v = lane; v < D.N; v += 32) V.vfirst[v] = NONE32, V.vlast[v] = NONE32;
+            __syncwarp();
+            if (lane == 0) links_serial(D, r, V, mode == 0);
+            __syncwarp();
+            uint32_t ncl = mode == 0 ? cluster_strict(D, r, V, lane) : cluster_fast_serial(D, r, V, lane);
+            if (lane == 0) D.ncl[r] = ncl;
+            free_spins(D, r, V, lane);
+        }
+        if (phases & 4u) {
+            if (lane == 0) {  // qmc_ising.rs:786
+                uint32_t n = D.n[r], grown = n + n / 2;
+                if (grown > D.M[r]) D.M[r] = grown;
+            }
+            __syncwarp();
+        }
+        if (phases & 8u) {
+            done++;
+            const uint64_t idx = done - sample_origin;  // 1-based sweep index inside this call
+            if (lane == 0) D.vupd[r] += D.n[r];
+            if (idx % sample_freq == 0) {  // qmc_stepper.rs:150-158
+                if (lane == 0) D.sum_n[r] += D.n[r];
+                if (samples) {
+                    uint8_t *dst = samples + ((size_t)r * samples_per_rep + (idx / sample_freq - 1)) * D.N;
+                    for (uint32_t v = lane; v < D.N; v += 32) dst[v] = (uint8_t)state_bit(V.state, v);
+                }
+            }
+            if (lane == 0) D.done[r] = done;
+            __syncwarp();
+        }
+    }
+}
+
+// OpContainer::verify (op_container.rs:137-159) + non-zero weights (qmc_ising.rs:829-860), lane 0
+__global__ void k_sse_verify(SseDev D, uint32_t r, int *ok_out, uint32_t *scratch) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Rep V = rep_view(D, r);
+    uint32_t *roll = scratch;
+    for (uint32_t j = 0; j < D.Nw; j++) roll[j] = V.state[j];
+    int ok = 1;
+    uint32_t n = 0;
+    for (uint64_t p = 0; p < D.cap; p++) {
+        uint32_t w = V.ops[p];
+        if (w == OP_EMPTY) continue;
+        n++;
+        if (p >= D.M[r]) ok = 0;
+        uint32_t b = op_bond(w);
+        if (b >= D.E + 2 * D.N || (w >> 28)) { ok = 0; break; }
+        int kind = bond_kind(D, b);
+        if (kind == KIND_LONG && !D.has_h) ok = 0;
+        uint32_t v0, v1;
+        bond_vars(D, b, kind, v0, v1);
+        uint32_t in = op_in(w), out = op_out(w);
+        if (kind != KIND_SITE) {
+            if (in != out) ok = 0;  // off-diagonal two-site / longitudinal ops have zero weight
+            else if (!(fabs(bond_weight(D, b, kind, in & 1u, (in >> 1) & 1u)) > 2.220446049250313e-16)) ok = 0;
+        } else if (!(fabs(D.gamma) > 2.220446049250313e-16)) ok = 0;
+        if (state_bit(roll, v0) != (in & 1u)) ok = 0;
+        roll[v0 >> 5] = (roll[v0 >> 5] & ~(1u << (v0 & 31))) | ((out & 1u) << (v0 & 31));
+        if (kind == KIND_BOND) {
+            if (state_bit(roll, v1) != ((in >> 1) & 1u)) ok = 0;
+            roll[v1 >> 5] = (roll[v1 >> 5] & ~(1u << (v1 & 31))) | (((out >> 1) & 1u) << (v1 & 31));
+        }
+    }
+    for (uint32_t j = 0; j < D.Nw; j++)
+        if (roll[j] != V.state[j]) ok = 0;
+    if (n != D.n[r]) ok = 0;
+    *ok_out = ok;
+}
+
+// per-bond counts of replica r (fast_ops.rs:1281-1294)
+__global__ void k_sse_bond_counts(SseDev D, uint32_t r, unsigned long long *counts) {
+    const uint32_t *ops = D.ops + (size_t)r * D.cap;
+    for (uint64_t p = blockIdx.x * blockDim.x + threadIdx.x; p < D.M[r]; p += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w = ops[p];
+        if (w != OP_EMPTY) atomicAdd(&counts[op_bond(w)], 1ull);
+    }
+}
+
+// recount n of replica r after qmcb_load_ops
+__global__ void k_sse_recount(SseDev D, uint32_t r) {
+    __shared__ uint32_t tot;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    const uint32_t *ops = D.ops + (size_t)r * D.cap;
+    uint32_t c = 0;
+    for (uint64_t p = threadIdx.x; p < D.cap; p += blockDim.x) c += ops[p] != OP_EMPTY;
+    atomicAdd(&tot, c);
+    __syncthreads();
+    if (threadIdx.x == 0) D.n[r] = tot;
+}
+
+// stream-drawn initial states: make_random_spin_state (classical/graph.rs:451-453)
+__global__ void k_sse_init_state(SseDev D) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= D.R) return;
+    uint32_t *st = D.state + (size_t)r * D.Nw;
+    const uint64_t key = D.key[r];
+    for (uint32_t base = 0; base < D.N; base += 32) {
+        uint32_t v = base + lane;
+        bool bit = v < D.N && (stream_word(key, v) >> 63);  // sign bit of next_u32 = top bit of the word
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+        if (lane == 0) st[base >> 5] = m;
+    }
+    if (lane == 0) D.cursor[r] = D.N;
+}
+
+void launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phases, uint64_t sample_freq,
+                       uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
+    const int threads = 128;
+    const uint32_t blocks = (uint32_t)(((uint64_t)D.R * 32 + threads - 1) / threads);
+    k_sse_serial<<<blocks, threads, 0, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep);
+}
+void launch_sse_verify(const SseDev &D, uint32_t r, int *ok_dev, uint32_t *scratch_dev, cudaStream_t st) {
+    k_sse_verify<<<1, 32, 0, st>>>(D, r, ok_dev, scratch_dev);
+}
+void launch_sse_bond_counts(const SseDev &D, uint32_t r, unsigned long long *counts_dev, cudaStream_t st) {
+    k_sse_bond_counts<<<64, 256, 0, st>>>(D, r, counts_dev);
+}
+void launch_sse_recount(const SseDev &D, uint32_t r, cudaStream_t st) { k_sse_recount<<<1, 256, 0, st>>>(D, r); }
+void launch_sse_init_state(const SseDev &D, cudaStream_t st) {
+    const int threads = 128;
+    const uint32_t blocks = (uint32_t)(((uint64_t)D.R * 32 + threads - 1) / threads);
+    k_sse_init_state<<<blocks, threads, 0, st>>>(D);
+}

@@ -1,0 +1,231 @@
+"""Host-side mirror of `qmc::sse::QmcIsingGraph` + `QmcStepper` (qmc_ising.rs, qmc_stepper.rs) for
+a BATCH of replicas.  Same method names and argument meaning as the reference; wherever the
+reference returns one value per graph this returns one per replica.  All work happens in
+libqmcb.so through the C ABI (include/qmcb.h)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODE_FAST, MODE_STRICT, Lattice, check, ptr
+
+
+def _lattice(edges, transverse, longitudinal, nvars=None):
+    va = np.ascontiguousarray([e[0][0] for e in edges], dtype=np.uint32)
+    vb = np.ascontiguousarray([e[0][1] for e in edges], dtype=np.uint32)
+    J = np.ascontiguousarray([e[1] for e in edges], dtype=np.float64)
+    if nvars is None:
+        nvars = int(max(va.max(), vb.max())) + 1  # qmc_ising.rs:92
+    lat = Lattice(nvars, len(edges), ptr(va, C.c_uint32), ptr(vb, C.c_uint32), ptr(J, C.c_double),
+                  float(transverse), float(longitudinal))
+    return lat, (va, vb, J)
+
+
+class QmcIsingGraph:
+    """R replicas of one transverse-field Ising lattice resident on one GPU."""
+
+    def __init__(self, edges, transverse, longitudinal, cutoff, rng_keys, betas, state=None, capacity=0,
+                 device=0, mode=MODE_STRICT, nvars=None):
+        L = _lib.load()
+        self._L = L
+        self._edges = list(edges)
+        self.transverse, self.longitudinal = float(transverse), float(longitudinal)
+        keys = np.ascontiguousarray(rng_keys, dtype=np.uint64)
+        self.R = len(keys)
+        self._betas = np.ascontiguousarray(np.broadcast_to(np.asarray(betas, dtype=np.float64), (self.R,)))
+        lat, self._keep = _lattice(edges, transverse, longitudinal, nvars)
+        self.nvars = lat.nvars
+        st = None
+        if state is not None:
+            st = np.ascontiguousarray(np.broadcast_to(np.asarray(state, dtype=np.uint8), (self.R, self.nvars)))
+        h = C.c_void_p()
+        check(L.qmcb_create(C.byref(lat), self.R, ptr(self._betas, C.c_double), ptr(keys, C.c_uint64), int(cutoff),
+                            int(capacity), None if st is None else ptr(st, C.c_uint8), device, C.byref(h)))
+        self._h = h
+        self.set_mode(mode)
+
+    # -- construction helpers with the reference's names (qmc_ising.rs:131-148) ---------------
+    @classmethod
+    def new_with_rng(cls, edges, transverse, longitudinal, cutoff, rng_keys, state=None, betas=1.0, **kw):
+        return cls(edges, transverse, longitudinal, cutoff, rng_keys, betas, state=state, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qmcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration -------------------------------------------------------------------------
+    def set_mode(self, mode):
+        check(self._L.qmcb_set_mode(self._h, mode))
+        self.mode = mode
+
+    def set_option(self, name, value):
+        check(self._L.qmcb_set_option(self._h, name.encode(), int(value)))
+
+    def set_stream(self, cuda_stream_ptr):
+        check(self._L.qmcb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def _set_beta(self, beta):
+        if beta is None:
+            return
+        b = np.ascontiguousarray(np.broadcast_to(np.asarray(beta, dtype=np.float64), (self.R,)))
+        if not np.array_equal(b, self._betas):
+            check(self._L.qmcb_set_betas(self._h, ptr(b, C.c_double)))
+            self._betas = b.copy()
+
+    def betas(self):
+        out = np.zeros(self.R, dtype=np.float64)
+        check(self._L.qmcb_get_betas(self._h, ptr(out, C.c_double)))
+        return out
+
+    # -- QmcStepper (qmc_stepper.rs) -----------------------------------------------------------
+    def timestep(self, beta=None):
+        self._set_beta(beta)
+        check(self._L.qmcb_timesteps(self._h, 1, 1, None, None))
+        return self.state_ref()
+
+    def timesteps(self, t, beta=None):
+        """qmc_stepper.rs:17-20: t sweeps, returns the average energy of every replica."""
+        self._set_beta(beta)
+        e = np.zeros(self.R, dtype=np.float64)
+        check(self._L.qmcb_timesteps(self._h, int(t), 1, ptr(e, C.c_double), None))
+        return e
+
+    def timesteps_sample(self, t, beta=None, sampling_freq=None):
+        """qmc_stepper.rs:23-40: returns (samples[R][t // freq][N], energies[R])."""
+        self._set_beta(beta)
+        freq = 1 if sampling_freq is None else int(sampling_freq)
+        k = int(t) // freq
+        e = np.zeros(self.R, dtype=np.float64)
+        s = np.zeros((self.R, max(k, 1), self.nvars), dtype=np.uint8)
+        check(self._L.qmcb_timesteps(self._h, int(t), freq, ptr(e, C.c_double), ptr(s, C.c_uint8)))
+        return s[:, :k], e
+
+    def enqueue_sweeps(self, t):
+        check(self._L.qmcb_enqueue_sweeps(self._h, int(t)))
+
+    def synchronize(self):
+        check(self._L.qmcb_synchronize(self._h))
+
+    def single_diagonal_step(self, beta=None):
+        self._set_beta(beta)
+        check(self._L.qmcb_single_diagonal_step(self._h))
+
+    def single_cluster_step(self):
+        out = np.zeros(self.R, dtype=np.uint64)
+        check(self._L.qmcb_single_cluster_step(self._h, ptr(out, C.c_uint64)))
+        return out
+
+    def get_energy_for_average_n(self, average_n, beta):
+        return -(np.asarray(average_n, dtype=np.float64) / beta) + self.get_offset()  # qmc_ising.rs:805-809
+
+    # -- accessors -----------------------------------------------------------------------------
+    def _u64(self, fn):
+        out = np.zeros(self.R, dtype=np.uint64)
+        check(fn(self._h, ptr(out, C.c_uint64)))
+        return out
+
+    def get_n(self):
+        return self._u64(self._L.qmcb_get_n)
+
+    def get_cutoff(self):
+        return self._u64(self._L.qmcb_get_cutoffs)
+
+    def set_cutoff(self, cutoff, replica=None):
+        for r in (range(self.R) if replica is None else [replica]):
+            check(self._L.qmcb_set_cutoff(self._h, r, int(cutoff)))
+
+    def rng_cursors(self):
+        return self._u64(self._L.qmcb_get_rng_cursors)
+
+    def set_rng_cursor(self, r, cursor):
+        check(self._L.qmcb_set_rng_cursor(self._h, r, int(cursor)))
+
+    def rng_keys(self):
+        return self._u64(self._L.qmcb_get_rng_keys)
+
+    def get_capacity(self):
+        c = C.c_uint64()
+        check(self._L.qmcb_get_capacity(self._h, C.byref(c)))
+        return c.value
+
+    def get_nvars(self):
+        return self.nvars
+
+    def get_edges(self):
+        return self._edges
+
+    def get_offset(self):
+        o = C.c_double()
+        check(self._L.qmcb_get_offset(self._h, C.byref(o)))
+        return o.value
+
+    def num_bonds(self):
+        n = C.c_uint32()
+        check(self._L.qmcb_num_bonds(self._h, C.byref(n)))
+        return n.value
+
+    def state_ref(self):
+        out = np.zeros((self.R, self.nvars), dtype=np.uint8)
+        check(self._L.qmcb_get_states(self._h, ptr(out, C.c_uint8)))
+        return out
+
+    clone_state = state_ref
+
+    def set_state(self, r, state):
+        st = np.ascontiguousarray(state, dtype=np.uint8)
+        check(self._L.qmcb_set_state(self._h, r, ptr(st, C.c_uint8)))
+
+    def get_bond_counts(self, r):
+        out = np.zeros(self.num_bonds(), dtype=np.uint64)
+        check(self._L.qmcb_get_bond_counts(self._h, r, ptr(out, C.c_uint64)))
+        return out
+
+    def get_bond_count(self, r, bond):
+        return int(self.get_bond_counts(r)[bond])
+
+    def dump_ops(self, r):
+        m = int(self.get_cutoff()[r])
+        out = np.zeros(max(m, 1), dtype=np.uint32)
+        check(self._L.qmcb_dump_ops(self._h, r, ptr(out, C.c_uint32), len(out)))
+        return out[:m]
+
+    def load_ops(self, r, words, state=None):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        st = None if state is None else np.ascontiguousarray(state, dtype=np.uint8)
+        check(self._L.qmcb_load_ops(self._h, r, ptr(w, C.c_uint32), len(w), None if st is None else ptr(st, C.c_uint8)))
+
+    def verify(self, r=None):
+        ok = C.c_int()
+        for k in (range(self.R) if r is None else [r]):
+            check(self._L.qmcb_verify(self._h, k, C.byref(ok)))
+            if not ok.value:
+                return False
+        return True
+
+    def boundaries(self, r, nslots):
+        a = np.zeros(nslots, dtype=np.uint32)
+        b = np.zeros(nslots, dtype=np.uint32)
+        check(self._L.qmcb_get_boundaries(self._h, r, ptr(a, C.c_uint32), ptr(b, C.c_uint32), nslots))
+        return a, b
+
+    def total_vertex_updates(self):
+        t = C.c_uint64()
+        check(self._L.qmcb_total_vertex_updates(self._h, C.byref(t)))
+        return t.value
+
+    def launch_count(self):
+        t = C.c_uint64()
+        check(self._L.qmcb_launch_count(self._h, C.byref(t)))
+        return t.value
+
+
+DefaultQmcIsingGraph = QmcIsingGraph

@@ -1,0 +1,137 @@
+"""Host-side mirror of `qmc::sse::parallel_tempering::TemperingContainer`
+(tempering_container.rs:19-302, rayon variants :316-478) over one batched GPU handle per rank.
+
+Slots s = chain * n_betas + k are block-partitioned over the ranks of a torch.distributed group
+(one process per GPU).  Operator strings never leave their GPU: a swap exchanges slot labels, and
+the only inter-GPU traffic per tempering step is one all-gather of a 32-byte record per slot
+(NCCL over NVLink on GPUs; gloo in the CPU tests of this plumbing)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODE_FAST, check, ptr
+
+REC_WORDS = 4  # {slot, n, cursor, cutoff} as uint64 (int64 on the wire)
+
+
+def partition_slots(n_slots: int, world_size: int, rank: int):
+    """Contiguous block of global slots owned by `rank` (weak scaling: fixed slots per GPU)."""
+    if n_slots % world_size:
+        raise ValueError("slots must divide evenly over the ranks")
+    per = n_slots // world_size
+    return rank * per, per
+
+
+def gather_records(rec_local, group=None):
+    """All-gather the per-configuration records of every rank, rank-major.  rec_local is a torch
+    int64 tensor [R, 4] (CUDA with nccl, CPU with gloo).  Single process: returned unchanged."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rec_local
+    import torch
+
+    world = dist.get_world_size(group)
+    out = torch.empty((world * rec_local.shape[0], rec_local.shape[1]), dtype=rec_local.dtype, device=rec_local.device)
+    dist.all_gather_into_tensor(out, rec_local.contiguous(), group=group)
+    return out
+
+
+class TemperingContainer:
+    """n_chains independent ladders of n_betas slots each; add_qmc_stepper is replaced by giving
+    the whole ladder at construction (all slots share one lattice, so can_swap_graphs holds)."""
+
+    def __init__(self, edges, transverse, longitudinal, cutoff, betas, n_chains=1, rng_keys=None, pt_key=0x9E37,
+                 mode=MODE_FAST, device=None, group=None, capacity=0):
+        import torch
+        import torch.distributed as dist
+
+        from .sse import QmcIsingGraph
+
+        self._torch = torch
+        self.group = group
+        dist_on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if dist_on else 0
+        self.world = dist.get_world_size(group) if dist_on else 1
+        betas = np.asarray(betas, dtype=np.float64)
+        self.n_betas, self.n_chains = len(betas), int(n_chains)
+        self.S = self.n_betas * self.n_chains
+        self.betas_global = np.ascontiguousarray(np.tile(betas, self.n_chains))
+        if rng_keys is None:
+            rng_keys = 0x55E00000 + np.arange(self.S, dtype=np.uint64)
+        self.keys_global = np.ascontiguousarray(rng_keys, dtype=np.uint64)
+        self.slot_begin, self.R = partition_slots(self.S, self.world, self.rank)
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = device
+        sl = slice(self.slot_begin, self.slot_begin + self.R)
+        self.graph = QmcIsingGraph(edges, transverse, longitudinal, cutoff, self.keys_global[sl], self.betas_global[sl],
+                                   capacity=capacity, device=device, mode=mode)
+        L = self.graph._L
+        check(L.qmcb_pt_configure(self.graph._h, self.n_chains, self.n_betas, self.slot_begin,
+                                  ptr(self.betas_global, C.c_double), ptr(self.keys_global, C.c_uint64), int(pt_key)))
+        self._rec = torch.empty((self.R, REC_WORDS), dtype=torch.int64, device=f"cuda:{device}")
+
+    def num_graphs(self):
+        return self.S
+
+    def timesteps(self, t):
+        """tempering_container.rs:76-81 / parallel_timesteps :366-371"""
+        return self.graph.timesteps(t)
+
+    def tempering_step(self):
+        """tempering_container.rs:121-149 (parallel_tempering_step :373-402)"""
+        L, g = self.graph._L, self.graph
+        check(L.qmcb_pt_export(g._h, C.c_void_p(self._rec.data_ptr())))
+        check(L.qmcb_synchronize(g._h))
+        allrec = gather_records(self._rec, self.group)
+        self._allrec = allrec  # keep alive until the kernel ran
+        check(L.qmcb_pt_apply(g._h, C.c_void_p(allrec.data_ptr()), allrec.shape[0]))
+        check(L.qmcb_synchronize(g._h))
+
+    def slots(self):
+        out = np.zeros(self.R, dtype=np.uint32)
+        check(self.graph._L.qmcb_pt_get_slots(self.graph._h, ptr(out, C.c_uint32)))
+        return out
+
+    def get_total_swaps(self):
+        s = C.c_uint64()
+        check(self.graph._L.qmcb_pt_total_swaps(self.graph._h, C.byref(s)))
+        return s.value
+
+    def timesteps_sample(self, timesteps, replica_swap_freq, sampling_freq):
+        """tempering_container.rs:166-208: returns (states, energy_acc) indexed by GLOBAL slot.
+        states[slot] is a list of sampled configurations (filled for the slots whose configuration
+        lives on this rank at sampling time); energy_acc is summed over ranks."""
+        states = [[] for _ in range(self.S)]
+        energy_acc = np.zeros(self.S, dtype=np.float64)
+        remaining, to_swap, to_sample = int(timesteps), int(replica_swap_freq), int(sampling_freq)
+        while remaining > 0:
+            t = min(to_sample, to_swap, remaining)
+            slots = self.slots()
+            e = self.graph.timesteps(t)
+            energy_acc[slots] += e * t
+            to_sample -= t
+            to_swap -= t
+            remaining -= t
+            if to_swap == 0:
+                self.tempering_step()
+                to_swap = int(replica_swap_freq)
+            if to_sample == 0:
+                st = self.graph.state_ref()
+                for s, slot in enumerate(self.slots()):
+                    states[slot].append(st[s])
+                to_sample = int(sampling_freq)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            tacc = self._torch.from_numpy(energy_acc).to(f"cuda:{self.device}")
+            dist.all_reduce(tacc, group=self.group)
+            energy_acc = tacc.cpu().numpy()
+        return states, energy_acc
+
+    def verify(self):
+        return self.graph.verify()

@@ -1,0 +1,129 @@
+"""GPU parity: classical checkerboard sweeps and the tempering swap step against the CPU oracle."""
+import numpy as np
+import pytest
+
+from isingmontecarlo_b200 import MODE_FAST, MODE_STRICT, lattices
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def run_classical(edges, biases, betas, sweeps, keys, state=None):
+    from isingmontecarlo_b200.classical import GraphState
+
+    g = GraphState(edges, biases, keys, betas, state=state)
+    colours, ncol = g.colours()
+    refs = [po.ClassicalOracle(edges, biases, key=k, state=None if state is None else state) for k in keys]
+    st0 = g.state_ref()
+    for r, ref in enumerate(refs):
+        assert np.array_equal(st0[r], ref.state()), "stream-drawn initial state"
+    for chunk in (1, 2, sweeps - 3):
+        g.do_time_step(chunk)
+        st = g.state_ref()
+        e, m = g.get_energy(), g.magnetization()
+        for r, ref in enumerate(refs):
+            ref.checkerboard_sweeps(betas[r], colours, chunk)
+            assert np.array_equal(st[r], ref.state()), (r, chunk)
+            assert abs(e[r] - ref.energy()) <= 1e-9 * max(1.0, abs(ref.energy()))
+            assert abs(m[r] - ref.magnetization()) <= 1e-12
+    return g
+
+
+def test_generic_graphs_bit_exact():
+    rng = np.random.default_rng(3)
+    tri = lattices.triangular_periodic(6, 1.0)
+    g = run_classical(tri, np.zeros(36), [0.3, 0.6, 1.2], 8, [11, 12, 13])
+    assert not g.is_bitpacked_square() and g.colours()[1] >= 3
+    # random couplings and biases on a small square lattice (odd L => 3 colours)
+    sq = [(e, float(rng.normal())) for e, _ in lattices.square_periodic(5, 1.0)]
+    run_classical(sq, rng.normal(size=25), [0.5, 1.0], 8, [21, 22])
+    # ring with a uniform bias, generic path (too small for the bit-packed layout)
+    run_classical(lattices.one_d_periodic(10, -1.0), np.full(10, 0.25), [0.7, 0.7], 8, [31, 32])
+
+
+@pytest.mark.parametrize("J,bias", [(-1.0, 0.0), (1.0, 0.0), (-1.0, 0.3), (0.75, -0.2)])
+def test_square_bitpacked_bit_exact(J, bias):
+    L = 64
+    edges = lattices.square_periodic(L, J)
+    g = run_classical(edges, np.full(L * L, bias), [0.4406868, 0.3, 0.8], 7, [0xB2000000, 0xB2000001, 0xB2000002])
+    assert g.is_bitpacked_square() and g.colours()[1] == 2
+
+
+def test_square_set_state_round_trip_and_energy_anchor():
+    from isingmontecarlo_b200.classical import GraphState
+
+    L = 64
+    edges = lattices.square_periodic(L, -1.0)
+    rng = np.random.default_rng(0)
+    st = rng.integers(0, 2, size=(2, L * L), dtype=np.uint8)
+    g = GraphState(edges, np.zeros(L * L), [1, 2], 0.44, state=st)
+    assert np.array_equal(g.state_ref(), st)
+    g.set_state(np.zeros((2, L * L), dtype=np.uint8))
+    assert np.all(g.get_energy() == -2.0 * L * L)  # all aligned, J=-1: E = -2N (graph.rs:430-447)
+    assert np.all(g.magnetization() == -1.0)
+
+
+def onsager_energy(beta):
+    """exact energy per site of the infinite square-lattice Ising ferromagnet (|J| = 1)"""
+    from scipy.special import ellipk
+
+    k = 2.0 * np.sinh(2 * beta) / np.cosh(2 * beta) ** 2
+    return -1.0 / np.tanh(2 * beta) * (1.0 + (2.0 / np.pi) * (2.0 * np.tanh(2 * beta) ** 2 - 1.0) * ellipk(k * k))
+
+
+@pytest.mark.parametrize("beta", [0.35, 0.55])
+def test_classical_energy_matches_onsager(beta):
+    # physics anchor away from T_c (correlation length << L, so finite-size effects are negligible):
+    # mean energy over independent replicas within 3 sigma (+ a 1e-3 systematic allowance)
+    from isingmontecarlo_b200.classical import GraphState
+
+    L, R = 64, 64
+    edges = lattices.square_periodic(L, -1.0)
+    state = None if beta < 0.44 else np.zeros((R, L * L), dtype=np.uint8)
+    g = GraphState(edges, np.zeros(L * L), 0xB2000000 + np.arange(R), beta, state=state)
+    g.do_time_step(500)
+    es = []
+    for _ in range(40):
+        g.do_time_step(10)
+        es.append(g.get_energy() / (L * L))
+    e = np.mean(es, axis=0)
+    err = e.std(ddof=1) / np.sqrt(R)
+    assert abs(e.mean() - onsager_energy(beta)) < 3.0 * err + 1e-3, (e.mean(), err, onsager_energy(beta))
+
+
+@pytest.mark.parametrize("mode", [MODE_STRICT, MODE_FAST])
+@pytest.mark.parametrize("n_chains,n_betas", [(1, 2), (2, 5), (3, 4)])
+def test_tempering_matches_reference_swaps(n_chains, n_betas, mode):
+    from isingmontecarlo_b200.tempering import TemperingContainer
+
+    edges = lattices.two_d_periodic_mixed(4)
+    betas = np.linspace(0.5, 2.0, n_betas)
+    S = n_chains * n_betas
+    keys = 0x55E00000 + np.arange(S, dtype=np.uint64)
+    pt_key = 0xABCDEF
+    tc = TemperingContainer(edges, 1.0, 0.0, 16, betas, n_chains=n_chains, rng_keys=keys, pt_key=pt_key, mode=mode)
+    # reference: one TemperingContainer (one PT stream, key pt_key + chain) per ladder
+    slots = [[po.SseOracle(edges, 1.0, 0.0, 16, key=int(keys[c * n_betas + k])) for k in range(n_betas)] for c in range(n_chains)]
+    cursors = [0] * n_chains
+    swaps_ref = 0
+    for step in range(12):
+        tc.timesteps(3)
+        for c in range(n_chains):
+            for k in range(n_betas):
+                slots[c][k].timesteps(3, float(betas[k]), mode)
+        tc.tempering_step()
+        for c in range(n_chains):
+            s, cursors[c] = po.pt_step(slots[c], betas, pt_key + c, cursors[c])
+            swaps_ref += s
+        # compare slot by slot: the configuration currently labelled `slot` on the GPU must equal
+        # the reference graph sitting in that slot
+        g = tc.graph
+        slot_of = tc.slots()
+        n, cut, cur, st = g.get_n(), g.get_cutoff(), g.rng_cursors(), g.state_ref()
+        for s_local, slot in enumerate(slot_of):
+            ref = slots[slot // n_betas][slot % n_betas]
+            assert int(n[s_local]) == ref.n and int(cut[s_local]) == ref.cutoff and int(cur[s_local]) == ref.cursor
+            assert np.array_equal(st[s_local], ref.state())
+            assert np.array_equal(g.dump_ops(s_local), ref.dump_ops())
+        assert tc.get_total_swaps() == swaps_ref
+    assert (swaps_ref > 0 or n_betas <= 2) and tc.verify()

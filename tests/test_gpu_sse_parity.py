@@ -1,0 +1,166 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via the host mirror) against the CPU
+oracle on the same seeded inputs.  Integer/bit work => bit-exact: operator words, spin states,
+n, cutoff and stream cursor must be identical after every compared sweep; energies are the same
+f64 expression of the same integers, so they must match exactly too."""
+import numpy as np
+import pytest
+
+from isingmontecarlo_b200 import MODE_FAST, MODE_STRICT, QmcbError, lattices
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, edges, gamma, h, cutoff0, beta, sweeps
+    ("small_qmc", lattices.small_qmc_ring(), 1.0, 0.0, 3, 1.0, 40),
+    ("pair_h", [((0, 1), 1.0)], 1.0, 1.0, 2, 1.0, 40),
+    ("ring6_ferro", lattices.one_d_periodic(6, -1.0), 0.7, 0.0, 6, 3.0, 30),
+    ("mixed4x4_h", lattices.two_d_periodic_mixed(4), 1.0, 1.0, 16, 1.0, 30),
+    ("two_unit_cell_h", lattices.two_unit_cell(), 1.0, -0.4, 8, 2.0, 30),
+    ("square8_crit", lattices.square_periodic(8, -1.0), 3.04, 0.0, 64, 4.0, 20),
+    ("tri6_frustrated_h", lattices.triangular_periodic(6, 1.0), 1.0, 0.2, 36, 2.0, 15),
+]
+
+
+def make_pair(edges, gamma, h, cutoff, beta, mode, R=5, key0=0x55E00000, impl=0):
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    keys = [key0 + r for r in range(R)]
+    g = QmcIsingGraph(edges, gamma, h, cutoff, keys, beta, mode=mode)
+    g.set_option("impl", impl)
+    refs = [po.SseOracle(edges, gamma, h, cutoff, key=k) for k in keys]
+    return g, refs
+
+
+def assert_same(g, refs, tag=""):
+    n, cut, cur, st = g.get_n(), g.get_cutoff(), g.rng_cursors(), g.state_ref()
+    for r, ref in enumerate(refs):
+        assert ref.error == 0
+        assert int(n[r]) == ref.n, (tag, r, "n")
+        assert int(cut[r]) == ref.cutoff, (tag, r, "cutoff")
+        assert int(cur[r]) == ref.cursor, (tag, r, "cursor")
+        assert np.array_equal(st[r], ref.state()), (tag, r, "state")
+        assert np.array_equal(g.dump_ops(r), ref.dump_ops()), (tag, r, "ops")
+
+
+@pytest.mark.parametrize("mode", [MODE_STRICT, MODE_FAST])
+@pytest.mark.parametrize("name,edges,gamma,h,cutoff,beta,sweeps", CASES)
+def test_sweeps_bit_exact(name, edges, gamma, h, cutoff, beta, sweeps, mode):
+    g, refs = make_pair(edges, gamma, h, cutoff, beta, mode)
+    assert_same(g, refs, "init")  # stream-drawn initial states (classical/graph.rs:451-453)
+    for chunk in (1, 1, 3, sweeps - 5):
+        e_gpu = g.timesteps(chunk, beta)
+        e_ref = [ref.timesteps(chunk, beta, mode) for ref in refs]
+        assert_same(g, refs, f"{name} after +{chunk}")
+        assert np.array_equal(e_gpu, np.array(e_ref)), name
+    assert g.verify()
+    assert all(ref.verify() for ref in refs)
+
+
+@pytest.mark.parametrize("mode", [MODE_STRICT, MODE_FAST])
+def test_serial_and_parallel_impl_agree(mode):
+    # impl=1 forces the serial-order kernels; impl=0 picks the warp-parallel ones where available
+    edges = lattices.square_periodic(8, -1.0)
+    a, refs = make_pair(edges, 3.04, 0.0, 64, 4.0, mode, R=4, impl=0)
+    b, _ = make_pair(edges, 3.04, 0.0, 64, 4.0, mode, R=4, impl=1)
+    a.timesteps(12, 4.0), b.timesteps(12, 4.0)
+    [ref.timesteps(12, 4.0, mode) for ref in refs]
+    assert_same(a, refs, "impl0"), assert_same(b, refs, "impl1")
+
+
+@pytest.mark.parametrize("mode", [MODE_STRICT, MODE_FAST])
+def test_single_steps_and_cluster_counts(mode):
+    edges = lattices.two_d_periodic_mixed(4)
+    g, refs = make_pair(edges, 1.0, 0.5, 16, 1.5, mode, R=4)
+    for _ in range(6):
+        g.single_diagonal_step(1.5)
+        [ref.single_diagonal_step(1.5) for ref in refs]
+        assert_same(g, refs, "diag")
+        ncl = g.single_cluster_step()
+        ncl_ref = [ref.single_cluster_step(mode) for ref in refs]
+        assert [int(x) for x in ncl] == ncl_ref
+        assert_same(g, refs, "cluster")
+
+
+def test_strict_cluster_numbering_matches_reference_order():
+    # cluster ids per (slot, side) in discovery order (cluster.rs:57-97) for a thermalised string
+    edges = lattices.two_d_periodic_mixed(4)
+    g, refs = make_pair(edges, 1.0, 0.0, 16, 2.0, MODE_STRICT, R=3)
+    g.timesteps(10, 2.0)
+    [ref.timesteps(10, 2.0) for ref in refs]
+    g.single_diagonal_step(2.0)
+    [ref.single_diagonal_step(2.0) for ref in refs]
+    g.single_cluster_step()
+    for r, ref in enumerate(refs):
+        ref.single_cluster_step()
+        m = ref.cutoff
+        bi, bo = g.boundaries(r, m)
+        ri, ro = ref.boundaries(m)
+        has_op = ri >= 0
+        assert np.array_equal(bi[has_op].astype(np.int64), ri[has_op])
+        assert np.array_equal(bo[has_op].astype(np.int64), ro[has_op])
+
+
+def test_hand_built_strings_from_cluster_test_rs():
+    # tests/cluster_test.rs:7-75 strings (B1-B3 of SURVEY Appendix B) through load_ops
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    def word(bond, i, o):
+        return bond | (i << 24) | (o << 26)
+
+    edges = [((0, 1), -1.0)]  # bond 0 two-site, bonds 1,2 transverse on var 0,1
+    for ops, expect_ncl in (([word(1, 0, 0)], 1), ([word(1, 0, 0), word(1, 0, 0)], 2),
+                            ([word(1, 0, 0), word(1, 0, 0), word(2, 0, 0), word(2, 0, 0)], 4),
+                            ([word(1, 0, 0), word(0, 0, 0), word(2, 0, 0)], 1), ([word(0, 0, 0), word(0, 0, 0)], 1)):
+        g = QmcIsingGraph(edges, 1.0, 0.0, len(ops), [77], 1.0, state=[0, 0])
+        ref = po.SseOracle(edges, 1.0, 0.0, len(ops), key=77, state=[0, 0])
+        g.load_ops(0, ops, [0, 0]), ref.load_ops(ops, [0, 0])
+        assert int(g.get_n()[0]) == ref.n
+        assert int(g.single_cluster_step()[0]) == ref.single_cluster_step() == expect_ncl
+        assert np.array_equal(g.dump_ops(0), ref.dump_ops()) and np.array_equal(g.state_ref()[0], ref.state())
+        assert g.verify()
+
+
+def test_timesteps_sample_matches():
+    edges = lattices.small_qmc_ring()
+    g, refs = make_pair(edges, 1.0, 0.3, 3, 1.0, MODE_STRICT, R=3)
+    s_gpu, e_gpu = g.timesteps_sample(21, 1.0, 4)
+    for r, ref in enumerate(refs):
+        s_ref, e_ref = ref.timesteps_sample(21, 1.0, 4)
+        assert s_gpu.shape[1] == 5 and np.array_equal(s_gpu[r], s_ref)
+        assert e_gpu[r] == e_ref
+
+
+def test_capacity_error_and_growth():
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.square_periodic(4, -1.0)
+    g = QmcIsingGraph(edges, 2.0, 0.0, 16, [1, 2], 4.0, capacity=32)
+    with pytest.raises(QmcbError) as ei:
+        g.timesteps(20, 4.0)
+    assert ei.value.code == -2  # QMCB_ERR_CAPACITY: status code instead of the reference's abort
+    g2 = QmcIsingGraph(edges, 2.0, 0.0, 16, [1, 2], 4.0, capacity=32)
+    g2.set_option("auto_capacity", 1)
+    refs = [po.SseOracle(edges, 2.0, 0.0, 16, key=k) for k in (1, 2)]
+    g2.timesteps(20, 4.0)
+    [ref.timesteps(20, 4.0) for ref in refs]
+    assert g2.get_capacity() > 32
+    assert_same(g2, refs, "grown")
+
+
+def test_bond_counts_and_dump_load_round_trip():
+    edges = lattices.two_d_periodic_mixed(4)
+    g, refs = make_pair(edges, 1.0, 0.3, 16, 2.0, MODE_STRICT, R=2)
+    g.timesteps(15, 2.0)
+    [ref.timesteps(15, 2.0) for ref in refs]
+    counts = g.get_bond_counts(1)
+    assert [int(c) for c in counts] == [refs[1].bond_count(b) for b in range(len(counts))]
+    words, st = g.dump_ops(0), g.state_ref()[0]
+    g.load_ops(1, words, st)  # replica 1 becomes a copy of replica 0's configuration
+    assert g.verify(1) and int(g.get_n()[1]) == refs[0].n
+    # a corrupted string must fail verify (op_container.rs:137-159)
+    bad = words.copy()
+    k = int(np.nonzero(bad != 0xFFFFFFFF)[0][0])
+    bad[k] ^= 1 << 24
+    g.load_ops(1, bad, st)
+    assert not g.verify(1)
