@@ -148,7 +148,9 @@ def bench_sse(args, world, rank, local):
     R = c["replicas"]
     keys = c["key0"] + rank * R + np.arange(R, dtype=np.uint64)
     g = QmcIsingGraph(edges, c["gamma"], c["h"], c["cutoff0"], keys, c["beta"], device=local, mode=MODE_FAST)
-    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()  # a real (non-default) stream so that torch.cuda.Event sees the kernels
+    torch.cuda.set_stream(stream)
+    g.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()
     g.timesteps(args.therm, c["beta"])  # thermalise (untimed): <n> plateaus after ~60 sweeps
     therm_s = time.perf_counter() - t0
@@ -212,8 +214,8 @@ def bench_sse(args, world, rank, local):
         with open(prof) as f:
             roofline["traffic"] = json.load(f).get("k_sse_fast")
 
-    out = {"value": value, "ms_per_step": t_max / args.steps, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
-           "clocks": clocks, "n_mean": n_mean, "cutoff_mean": m_mean, "therm_s": therm_s, "handle": g, "config": c}
+    out = {"value": value, "ms_per_step": t_max / args.steps, "therm_s": therm_s, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+           "clocks": clocks, "n_mean": n_mean, "cutoff_mean": m_mean, "handle": g, "config": c}
 
     # ---- STRICT (reference-order, bit-exact with the reference's update path) sample
     if args.strict_sweeps > 0 and world == 1:
@@ -279,7 +281,9 @@ def bench_classical(args, world, rank, local):
     edges = lattices.square_periodic(L, c["J"])
     keys = c["key0"] + rank * R + np.arange(R, dtype=np.uint64)
     g = GraphState(edges, np.zeros(L * L), keys, c["beta"], device=local)
-    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    g.set_stream(stream.cuda_stream)
     spp = args.cls_sweeps_per_step
     for _ in range(max(args.warmup, 3)):
         g.enqueue_sweeps(spp)

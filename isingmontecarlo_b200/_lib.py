@@ -36,6 +36,7 @@ SIGNATURES = {
     "qmcb_set_mode": [vp, C.c_int],
     "qmcb_get_mode": [vp, C.POINTER(C.c_int)],
     "qmcb_set_option": [vp, C.c_char_p, C.c_int64],
+    "qmcb_get_debug_counters": [vp, u64p],
     "qmcb_set_betas": [vp, f64p],
     "qmcb_get_betas": [vp, f64p],
     "qmcb_num_replicas": [vp, u32p],

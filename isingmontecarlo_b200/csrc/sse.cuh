@@ -28,6 +28,7 @@ struct SseDev {
     uint32_t *ncl;      // [R] clusters found by the last cluster step
     uint32_t *ends;     // [R][4] first_p, last_p, first_site_p, (unused)
     int *status;        // [1] DEV_ERR_* bits
+    unsigned long long *dbg;  // [16] optional event counters (NULL = off)
     // per-variable scratch
     uint32_t *vfirst, *vlast;  // [R][N] first / last leg (p << 1 | rel) on each variable, or NONE32
     uint32_t *cur;             // [R][N] FAST: current segment id per variable

@@ -22,6 +22,7 @@
 #define T_EMPTY 1
 #define T_DIAG 2
 #define T_OFFD 3
+#define DBG(i, v) do { if (D.dbg && lane == 0) atomicAdd(D.dbg + (i), (unsigned long long)(v)); } while (0)
 
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ void st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
@@ -68,10 +69,12 @@ struct WarpSmem {
     unsigned long long *win;  // [64] stream words of this step
     uint32_t *fl;   // [32] variable flipped by the off-diagonal op of lane j (or NONE32)
     uint32_t *sv;   // [32] variable cut by the site op of lane j (or NONE32)
+    uint32_t *opw;  // [64] op word an empty slot would insert from window word y
+    unsigned char *G;  // [64] cursor after an empty slot that starts reading at window position x
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
-    return ((((size_t)3 * Nw + N + 64) * 4 + 64 * 8) + 15) / 16 * 16;
+    return ((((size_t)3 * Nw + N + 64 + 64 + 16) * 4 + 64 * 8) + 15) / 16 * 16;
 }
 
 template <bool HAS_H>
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
         unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(N, Nw);
         S.win = (unsigned long long *)base;
         uint32_t *u = (uint32_t *)(base + 64 * 8);
-        S.st = u, S.tb = u + Nw, S.cd = u + 2 * Nw, S.rep = u + 3 * Nw, S.fl = u + 3 * Nw + N, S.sv = S.fl + 32;
+        S.st = u, S.tb = u + Nw, S.cd = u + 2 * Nw, S.rep = u + 3 * Nw, S.fl = u + 3 * Nw + N, S.sv = S.fl + 32, S.opw = S.sv + 32, S.G = (unsigned char *)(S.opw + 64);
     }
     uint32_t *ops = D.ops + (size_t)r * D.cap;
     uint32_t *gstate = D.state + (size_t)r * Nw;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
         uint32_t n = D.n[r];
         uint64_t cur = D.cursor[r];
         const double bn = D.beta[r] * (double)D.Nb;
-        for (uint32_t j = lane; j < Nw; j += 32) S.st[j] = gstate[j], S.tb[j] = 0;
+        for (uint32_t j = lane; j < Nw; j += 32) S.st[j] = gstate[j], S.tb[j] = 0, S.cd[j] = 0;
         const bool do_diag = phases & 1u, do_clus = phases & 2u;
         if (do_clus) {
             for (uint32_t v = lane; v < N; v += 32) S.rep[v] = v, st_cg(P + v, v);
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
             const uint32_t p = base + lane;
             const bool valid = p < M;
             uint32_t w = valid ? ops[p] : OP_EMPTY;
+            DBG(0, 1);
             int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
             uint32_t neww = w;
             // variables / stored bits of an existing op
@@ -140,11 +144,14 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
             }
             if (do_diag) {
                 S.fl[lane] = type == T_OFFD ? ov0 : NONE32;
+                if (type == T_OFFD) atomicOr(&S.cd[ov0 >> 5], 1u << (ov0 & 31));  // hazard bitmap of this step
                 const uint32_t fmask_lt = __ballot_sync(FULL, type == T_OFFD) & lt_mask;
+                const uint32_t emask = __ballot_sync(FULL, type == T_EMPTY), dmask = __ballot_sync(FULL, type == T_DIAG);
                 __syncwarp();
                 double dnum = 0.0;  // num of an existing diagonal op does not depend on (cursor, n)
                 if (type == T_DIAG) dnum = bn * bond_weight(D, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
-                uint32_t rem = __ballot_sync(FULL, type == T_EMPTY || type == T_DIAG);
+                uint32_t rem = emask | dmask;
+                bool try_fast = true;
                 while (rem) {
                     const uint64_t wbase = cur & ~1ull;
                     {  // stream words [wbase, wbase + 64)
@@ -155,97 +162,265 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                     }
                     __syncwarp();
                     const bool inrem = (rem >> lane) & 1u;
-                    uint32_t dc = inrem ? 1u : 0u;
+                    uint32_t dc = 0, okm;
                     int dn = 0;
-                    bool ovf = false;
-                    uint32_t last_pc = 0xFFFFFFFFu, last_pn = 0xFFFFFFFFu;
-                    uint32_t pc = 0, pn_b = 0;
-                    for (;;) {
-                        // exclusive prefix of (draws, insertions - removals) over the remaining lanes
-                        const uint32_t packed = inrem ? ((dc << 8) | (uint32_t)(dn + 1)) : 0u;
-                        const uint32_t ex = warp_excl_scan(packed, lane);
-                        pc = ex >> 8, pn_b = ex & 0xFFu;  // pn_b = sum of (dn + 1) over earlier remaining lanes
-                        bool changed = false;
-                        if (inrem && (pc != last_pc || pn_b != last_pn)) {
-                            last_pc = pc, last_pn = pn_b;
-                            const uint32_t ni = n + pn_b - (uint32_t)__popc(rem & lt_mask);
-                            uint32_t idx = (uint32_t)(cur - wbase) + pc;
-                            uint32_t ndc = 0;
-                            int ndn = 0;
-                            bool novf = false;
-                            uint32_t nw = w;
-                            if (type == T_EMPTY) {
-                                uint64_t hi = 0, lo;
-                                for (;;) {  // gen_range(0..Nb)
-                                    if (idx + ndc >= 64) { novf = true; break; }
-                                    const uint64_t v = S.win[idx + ndc];
-                                    ndc++;
-                                    hi = __umul64hi(v, range), lo = v * range;
-                                    if (lo <= zone) break;
-                                }
-                                if (!novf) {
-                                    const uint32_t b = (uint32_t)hi;
+                    if (try_fast) {
+                        DBG(1, 1);
+                        // ---- table walk.  Which bond a word encodes, whether rand's zone test rejects it and
+                        // the weight it gets are properties of the WORD (the spins it looks at only change at
+                        // the few off-diagonal ops of this step: "hazards"), so every window position is decoded
+                        // once, in parallel, into: ACC (word passes gen_range's zone), EX (a second word is read),
+                        // OKI (the op is inserted), HZ (needs the exact per-lane evaluation).  "Same for every
+                        // admissible n" is decided on the den interval spanned by the whole step (the rules are
+                        // monotone in den).  G[x] = cursor after an empty slot that starts reading at x.  The
+                        // cursors of all lanes then follow from a short uniform walk x <- G[x] / x + 1.
+                        const uint32_t remE = emask & rem, remD = dmask & rem;
+                        const uint32_t cntE = (uint32_t)__popc(remE & lt_mask), cntD = (uint32_t)__popc(remD & lt_mask);
+                        const double dlo = (double)(M - (n + cntE)), dhi = (double)(M - (n - cntD));          // this lane
+                        const double dloA = (double)(M - (n + (uint32_t)__popc(remE))), dhiA = (double)(M - (n - (uint32_t)__popc(remD)));
+                        // DIAG lanes: draw or not, and the thresholds at both ends of their den interval
+                        bool ambdc = false, draws = false;
+                        uint64_t t_lo = 0, t_hi = 0;
+                        if (inrem && type == T_DIAG) {
+                            const bool nd_lo = dlo + 1.0 >= dnum, nd_hi = dhi + 1.0 >= dnum;  // den >= num: removed, no draw
+                            if (!nd_lo) {
+                                draws = true, ambdc = nd_hi;
+                                t_lo = bool_threshold((dlo + 1.0) / dnum), t_hi = bool_threshold((dhi + 1.0) / dnum);
+                            }
+                        }
+                        const uint32_t drawD = __ballot_sync(FULL, draws), ambD = __ballot_sync(FULL, ambdc);
+                        // decode window positions y = lane and lane + 32
+                        uint32_t accb[2], exb[2], okb[2], hzb[2];
+#pragma unroll
+                        for (int hh = 0; hh < 2; hh++) {
+                            const uint32_t y = (uint32_t)lane + 32u * hh;
+                            const uint64_t v = S.win[y];
+                            const uint64_t hi = __umul64hi(v, range), lo = v * range;
+                            const bool acc = lo <= zone;
+                            bool ex = false, ok = false, hz = false;
+                            uint32_t opw = OP_EMPTY;
+                            if (acc) {
+                                const uint32_t b = (uint32_t)hi;
+                                const int kind = bond_kind(D, b);
+                                uint32_t v0, v1;
+                                bond_vars(D, b, kind, v0, v1);
+                                const uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
+                                hz = state_bit(S.cd, v0) || (kind == KIND_BOND && state_bit(S.cd, v1));
+                                const double num = bn * bond_weight(D, b, kind, s0, s1);
+                                const uint32_t bitsv = s0 | (s1 << 1);
+                                opw = make_op(b, bitsv, bitsv);
+                                if (num >= dhiA) ok = true;                      // inserted without a second word
+                                else if (num == 0.0) ex = true;                  // gen_bool(0.0): one word, false
+                                else if (num > 0.0 && num < dloA && y + 1 < 64) {
+                                    ex = true;
+                                    const uint64_t v2 = S.win[y + 1];
+                                    if (v2 < bool_threshold(num / dhiA)) ok = true;
+                                    else if (!(v2 >= bool_threshold(num / dloA))) hz = true;
+                                } else hz = true;
+                            }
+                            S.opw[y] = opw;
+                            accb[hh] = __ballot_sync(FULL, acc), exb[hh] = __ballot_sync(FULL, ex);
+                            okb[hh] = __ballot_sync(FULL, ok), hzb[hh] = __ballot_sync(FULL, hz);
+                        }
+                        const uint64_t ACC = ((uint64_t)accb[1] << 32) | accb[0], EX = ((uint64_t)exb[1] << 32) | exb[0];
+                        const uint64_t OKI = ((uint64_t)okb[1] << 32) | okb[0], HZ = ((uint64_t)hzb[1] << 32) | hzb[0];
+#pragma unroll
+                        for (int hh = 0; hh < 2; hh++) {  // successor table
+                            const uint32_t x = (uint32_t)lane + 32u * hh;
+                            const uint64_t m = ACC >> x;
+                            uint32_t g = 255u;  // window exhausted
+                            if (m) {
+                                const uint32_t y = x + (uint32_t)__ffsll((long long)m) - 1u;
+                                g = ((HZ >> y) & 1ull) ? 254u : y + 1u + (uint32_t)((EX >> y) & 1ull);
+                            }
+                            S.G[x] = (unsigned char)g;
+                        }
+                        __syncwarp();
+                        // uniform walk over the remaining lanes
+                        uint32_t x = (uint32_t)(cur - wbase), myx = 0, stop = 32u;
+                        bool need_exact = false, overridden = false;
+                        for (uint32_t mm = rem; mm; mm &= mm - 1) {
+                            const uint32_t i = (uint32_t)__ffs(mm) - 1u;
+                            if ((uint32_t)lane == i) myx = x;
+                            if ((remE >> i) & 1u) {
+                                uint32_t g = x < 64u ? (uint32_t)S.G[x] : 255u;
+                                if (g >= 254u) {
+                                    if (g == 255u) { stop = i; break; }
+                                    // hazard: the word's spins are flipped inside this step -> evaluate for lane i
+                                    DBG(12, 1);
+                                    const uint32_t y = x + (uint32_t)__ffsll((long long)(ACC >> x)) - 1u;
+                                    const uint32_t wv = S.opw[y];
+                                    const uint32_t b = op_bond(wv);
                                     const int kind = bond_kind(D, b);
                                     uint32_t v0, v1;
                                     bond_vars(D, b, kind, v0, v1);
                                     uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
-                                    for (uint32_t m = fmask_lt; m; m &= m - 1) {  // flips by earlier lanes of this step
-                                        const uint32_t fv = S.fl[__ffs(m) - 1];
+                                    for (uint32_t m2 = __ballot_sync(FULL, type == T_OFFD) & ((1u << i) - 1u); m2; m2 &= m2 - 1) {
+                                        const uint32_t fv = S.fl[__ffs(m2) - 1];
                                         s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
                                     }
                                     const double num = bn * bond_weight(D, b, kind, s0, s1);
-                                    const double den = (double)(M - ni);
-                                    bool accept = num > den;
-                                    if (!accept) {
-                                        const double pr = num / den;
-                                        if (pr == 1.0) accept = true;
-                                        else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
-                                        else if (idx + ndc >= 64) novf = true;
-                                        else accept = S.win[idx + ndc++] < bool_threshold(pr);
-                                    }
-                                    if (accept) {
-                                        const uint32_t bitsv = s0 | (s1 << 1);
-                                        nw = make_op(b, bitsv, bitsv);
-                                        ndn = 1;
-                                    } else nw = OP_EMPTY;
+                                    const uint32_t bitsv = s0 | (s1 << 1);
+                                    bool ok, ex;
+                                    if (num >= dhiA) ok = true, ex = false;
+                                    else if (num == 0.0) ok = false, ex = true;
+                                    else if (num > 0.0 && num < dloA && y + 1 < 64) {
+                                        ex = true;
+                                        const uint64_t v2 = S.win[y + 1];
+                                        if (v2 < bool_threshold(num / dhiA)) ok = true;
+                                        else if (v2 >= bool_threshold(num / dloA)) ok = false;
+                                        else { stop = i, need_exact = true; break; }
+                                    } else { stop = i, need_exact = true; break; }
+                                    if ((uint32_t)lane == i) overridden = true, neww = ok ? make_op(b, bitsv, bitsv) : OP_EMPTY, dn = ok, dc = y + 1u + (ex ? 1u : 0u) - x;
+                                    g = y + 1u + (ex ? 1u : 0u);
                                 }
-                            } else {  // T_DIAG
-                                const double den = (double)(M - ni) + 1.0;
-                                bool remove = den > dnum;
-                                if (!remove) {
-                                    const double pr = den / dnum;
-                                    if (pr == 1.0) remove = true;
-                                    else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
-                                    else if (idx >= 64) novf = true;
-                                    else { remove = S.win[idx] < bool_threshold(pr); ndc = 1; }
+                                x = g;
+                            } else {  // diagonal op
+                                if ((ambD >> i) & 1u) { stop = i, need_exact = true; break; }
+                                if ((drawD >> i) & 1u) {
+                                    if (x >= 64u) { stop = i; break; }
+                                    x += 1u;
                                 }
-                                if (remove) nw = OP_EMPTY, ndn = -1;
                             }
-                            if (novf) ndc = 0, ndn = 0;
-                            changed = ndc != dc || ndn != dn || novf != ovf;
-                            dc = ndc, dn = ndn, ovf = novf, neww = nw;
                         }
-                        if (!__any_sync(FULL, changed)) break;
+                        const uint32_t resolved = stop >= 32u ? rem : (rem & ((1u << stop) - 1u));
+                        // decisions of the resolved lanes
+                        bool unres = false;
+                        if ((resolved >> lane) & 1u) {
+                            if (type == T_EMPTY) {
+                                if (!overridden) {
+                                    const uint32_t y = myx + (uint32_t)__ffsll((long long)(ACC >> myx)) - 1u;
+                                    const bool ok = (OKI >> y) & 1ull;
+                                    neww = ok ? S.opw[y] : OP_EMPTY;
+                                    dn = ok, dc = y + 1u + (uint32_t)((EX >> y) & 1ull) - myx;
+                                }
+                            } else if (!draws) neww = OP_EMPTY, dn = -1, dc = 0;
+                            else {
+                                const uint64_t v = S.win[myx];
+                                dc = 1;
+                                if (v < t_lo) neww = OP_EMPTY, dn = -1;
+                                else if (v >= t_hi) neww = w, dn = 0;
+                                else unres = true;  // needs the exact n: resolved below, in order
+                            }
+                        }
+                        for (uint32_t um = __ballot_sync(FULL, unres); um; um = __ballot_sync(FULL, unres)) {
+                            DBG(13, 1);
+                            const uint32_t u = (uint32_t)__ffs(um) - 1u;
+                            const uint32_t pre = __reduce_add_sync(FULL, (((resolved >> lane) & 1u) && (uint32_t)lane < u) ? (uint32_t)(dn + 1) : 0u);
+                            if ((uint32_t)lane == u) {
+                                const uint32_t ni = n + pre - (uint32_t)__popc(resolved & lt_mask);
+                                const double pr = ((double)(M - ni) + 1.0) / dnum;
+                                const bool remove = S.win[myx] < bool_threshold(pr);
+                                neww = remove ? OP_EMPTY : w, dn = remove ? -1 : 0, unres = false;
+                            }
+                        }
+                        okm = resolved;
+                        if (okm == 0 || need_exact) {
+                            if (okm == 0) {
+                                if (!need_exact) err |= DEV_ERR_INVARIANT;  // a fresh window cannot be exhausted by one lane
+                                DBG(2, 1);
+                                try_fast = false;
+                                if (inrem) neww = w;
+                                __syncwarp();
+                                continue;
+                            }
+                            try_fast = false;  // commit the prefix, then the exact path takes the next lane
+                        }
+                    } else {
+                        // ---- exact fixed point (rare): every lane re-evaluates until no input changes
+                        try_fast = true;
+                        DBG(3, 1);
+                        dc = inrem ? 1u : 0u;
+                        bool ovf = false;
+                        uint32_t last_pc = 0xFFFFFFFFu, last_pn = 0xFFFFFFFFu;
+                        for (;;) {
+                            const uint32_t packed = inrem ? ((dc << 8) | (uint32_t)(dn + 1)) : 0u;
+                            const uint32_t ex = warp_excl_scan(packed, lane);
+                            const uint32_t pc = ex >> 8, pn_b = ex & 0xFFu;
+                            bool changed = false;
+                            if (inrem && (pc != last_pc || pn_b != last_pn)) {
+                                last_pc = pc, last_pn = pn_b;
+                                const uint32_t ni = n + pn_b - (uint32_t)__popc(rem & lt_mask);
+                                const uint32_t idx = (uint32_t)(cur - wbase) + pc;
+                                uint32_t ndc = 0;
+                                int ndn = 0;
+                                bool novf = false;
+                                uint32_t nw = w;
+                                if (type == T_EMPTY) {
+                                    uint64_t hi = 0, lo;
+                                    for (;;) {  // gen_range(0..Nb)
+                                        if (idx + ndc >= 64) { novf = true; break; }
+                                        const uint64_t v = S.win[idx + ndc];
+                                        ndc++;
+                                        hi = __umul64hi(v, range), lo = v * range;
+                                        if (lo <= zone) break;
+                                    }
+                                    if (!novf) {
+                                        const uint32_t b = (uint32_t)hi;
+                                        const int kind = bond_kind(D, b);
+                                        uint32_t v0, v1;
+                                        bond_vars(D, b, kind, v0, v1);
+                                        uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
+                                        for (uint32_t m = fmask_lt; m; m &= m - 1) {  // flips by earlier lanes of this step
+                                            const uint32_t fv = S.fl[__ffs(m) - 1];
+                                            s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
+                                        }
+                                        const double num = bn * bond_weight(D, b, kind, s0, s1);
+                                        const double den = (double)(M - ni);
+                                        bool accept = num > den;
+                                        if (!accept) {
+                                            const double pr = num / den;
+                                            if (pr == 1.0) accept = true;
+                                            else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                                            else if (idx + ndc >= 64) novf = true;
+                                            else accept = S.win[idx + ndc++] < bool_threshold(pr);
+                                        }
+                                        if (accept) {
+                                            const uint32_t bitsv = s0 | (s1 << 1);
+                                            nw = make_op(b, bitsv, bitsv);
+                                            ndn = 1;
+                                        } else nw = OP_EMPTY;
+                                    }
+                                } else {  // T_DIAG
+                                    const double den = (double)(M - ni) + 1.0;
+                                    bool remove = den > dnum;
+                                    if (!remove) {
+                                        const double pr = den / dnum;
+                                        if (pr == 1.0) remove = true;
+                                        else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                                        else if (idx >= 64) novf = true;
+                                        else { remove = S.win[idx] < bool_threshold(pr); ndc = 1; }
+                                    }
+                                    if (remove) nw = OP_EMPTY, ndn = -1;
+                                }
+                                if (novf) ndc = 0, ndn = 0;
+                                changed = ndc != dc || ndn != dn || novf != ovf;
+                                dc = ndc, dn = ndn, ovf = novf, neww = nw;
+                            }
+                            if (!__any_sync(FULL, changed)) break;
+                        }
+                        // lanes before the first window overflow are final
+                        const uint32_t ovm = __ballot_sync(FULL, inrem && ovf);
+                        okm = ovm ? (rem & ((1u << (__ffs(ovm) - 1)) - 1u)) : rem;
+                        if (okm == 0) {  // cannot happen: a fresh window holds >= 63 words
+                            err |= DEV_ERR_INVARIANT;
+                            okm = rem;
+                        }
                     }
-                    // lanes before the first window overflow are final
-                    const uint32_t ovm = __ballot_sync(FULL, inrem && ovf);
-                    const uint32_t okm = ovm ? (rem & ((1u << (__ffs(ovm) - 1)) - 1u)) : rem;
                     // advance (cursor, n) past the committed lanes
-                    const uint32_t tot = __reduce_add_sync(FULL, ((okm >> lane) & 1u) ? dc : 0u);
-                    const int totn = (int)__reduce_add_sync(FULL, ((okm >> lane) & 1u) ? (uint32_t)(dn + 1) : 0u) - __popc(okm);
+                    const bool mine = (okm >> lane) & 1u;
+                    const uint32_t tot = __reduce_add_sync(FULL, mine ? dc : 0u);
+                    const int totn = (int)__reduce_add_sync(FULL, mine ? (uint32_t)(dn + 1) : 0u) - __popc(okm);
+                    if (inrem && !mine) neww = w;
                     cur += tot;
                     n = (uint32_t)((int)n + totn);
                     rem &= ~okm;
-                    if (ovm && okm == 0 && ((cur & ~1ull) == wbase)) {  // cannot happen: a fresh window holds >= 63 words
-                        err |= DEV_ERR_INVARIANT;
-                        rem = 0;
-                    }
                     __syncwarp();
                 }
                 if (__any_sync(FULL, neww != w)) {
                     if (valid && neww != w) ops[p] = neww;
                 }
-                if (type == T_OFFD) atomicXor(&S.st[ov0 >> 5], 1u << (ov0 & 31));
+                if (type == T_OFFD) atomicXor(&S.st[ov0 >> 5], 1u << (ov0 & 31)), atomicAnd(&S.cd[ov0 >> 5], ~(1u << (ov0 & 31)));
                 __syncwarp();
             }
             if (do_clus) {

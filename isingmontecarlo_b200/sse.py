@@ -70,6 +70,11 @@ class QmcIsingGraph:
     def set_option(self, name, value):
         check(self._L.qmcb_set_option(self._h, name.encode(), int(value)))
 
+    def debug_counters(self):
+        out = np.zeros(16, dtype=np.uint64)
+        check(self._L.qmcb_get_debug_counters(self._h, ptr(out, C.c_uint64)))
+        return out
+
     def set_stream(self, cuda_stream_ptr):
         check(self._L.qmcb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

@@ -740,6 +740,7 @@ void orc_sse_set_cutoff(OrcSse *g, uint64_t cutoff) { /* qmc_ising.rs:537-540 */
 }
 uint64_t orc_sse_get_cursor(const OrcSse *g) { return g->rng.cursor; }
 void orc_sse_set_cursor(OrcSse *g, uint64_t cursor) { g->rng.cursor = cursor; }
+void orc_sse_set_key(OrcSse *g, uint64_t key) { g->rng.key = key; }
 double orc_sse_get_offset(const OrcSse *g) { return g->offset; }
 void orc_sse_get_state(const OrcSse *g, uint8_t *out) { memcpy(out, g->state, g->nvars); }
 void orc_sse_set_state(OrcSse *g, const uint8_t *in) { memcpy(g->state, in, g->nvars); }

@@ -65,6 +65,7 @@ uint64_t orc_sse_get_cutoff(const OrcSse *g);
 void orc_sse_set_cutoff(OrcSse *g, uint64_t cutoff);
 uint64_t orc_sse_get_cursor(const OrcSse *g);
 void orc_sse_set_cursor(OrcSse *g, uint64_t cursor);
+void orc_sse_set_key(OrcSse *g, uint64_t key);
 double orc_sse_get_offset(const OrcSse *g);
 void orc_sse_get_state(const OrcSse *g, uint8_t *out);
 void orc_sse_set_state(OrcSse *g, const uint8_t *in);

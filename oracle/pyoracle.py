@@ -66,6 +66,7 @@ def lib():
     sig("orc_sse_set_cutoff", None, vp, C.c_uint64)
     sig("orc_sse_get_cursor", C.c_uint64, vp)
     sig("orc_sse_set_cursor", None, vp, C.c_uint64)
+    sig("orc_sse_set_key", None, vp, C.c_uint64)
     sig("orc_sse_get_offset", C.c_double, vp)
     sig("orc_sse_get_state", None, vp, u8p)
     sig("orc_sse_set_state", None, vp, u8p)
@@ -131,8 +132,8 @@ class SseOracle:
         self._script = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_sse_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.orc_sse_destroy(self._h)
             self._h = None
 
     def set_script(self, words):
@@ -171,6 +172,9 @@ class SseOracle:
 
     def set_cursor(self, c):
         lib().orc_sse_set_cursor(self._h, c)
+
+    def set_key(self, k):
+        lib().orc_sse_set_key(self._h, k)
 
     def state(self):
         out = np.zeros(self.nvars, dtype=np.uint8)
@@ -237,8 +241,8 @@ class ClassicalOracle:
                                        None if st is None else _p(st, C.c_uint8))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_cls_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.orc_cls_destroy(self._h)
             self._h = None
 
     def spin_flips(self, beta, count):

@@ -1,0 +1,37 @@
+"""Small driver for profiling the SSE kernels: thermalise R replicas of config #3, then run a few
+timed sweeps.  Usage: python tools/prof_sse.py [R] [therm] [sweeps] [mode]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from isingmontecarlo_b200 import MODE_FAST, MODE_STRICT, lattices  # noqa: E402
+from isingmontecarlo_b200.sse import QmcIsingGraph  # noqa: E402
+
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+therm = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+sweeps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+mode = MODE_STRICT if len(sys.argv) > 4 and sys.argv[4] == "strict" else MODE_FAST
+L = int(os.environ.get("PROF_L", "32"))
+beta = float(os.environ.get("PROF_BETA", "16"))
+edges = lattices.square_periodic(L, -1.0)
+g = QmcIsingGraph(edges, 3.04, 0.0, L * L, 0x55E00000 + np.arange(R, dtype=np.uint64), beta, mode=MODE_FAST)
+t0 = time.perf_counter()
+g.timesteps(therm, beta)
+print(f"therm {therm} sweeps: {time.perf_counter() - t0:.3f} s, <n>={g.get_n().mean():.0f} <M>={g.get_cutoff().mean():.0f}")
+g.set_mode(mode)
+if os.environ.get('PROF_DBG'):
+    g.set_option('debug_counters', 1)
+for k in range(sweeps):
+    v0 = g.total_vertex_updates()
+    t0 = time.perf_counter()
+    g.enqueue_sweeps(1)
+    g.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"sweep {k}: {dt * 1e3:.2f} ms, {(g.total_vertex_updates() - v0) / dt:.3e} vertex updates/s")
+
+if os.environ.get('PROF_DBG'):
+    c = g.debug_counters()
+    print('dbg: chunks', c[0], 'fast', c[1], 'fast_fail_first', c[2], 'slow', c[3], 'why[delta|empty<<1|amb<<2]', list(c[4:12]))
