@@ -39,15 +39,15 @@ __device__ __forceinline__ uint32_t uf_find_cg(uint32_t *P, uint32_t x) {
     }
     return x;
 }
-__device__ __forceinline__ void uf_union_cg(uint32_t *P, uint32_t a, uint32_t b) {
+__device__ __forceinline__ uint32_t uf_union_cg(uint32_t *P, uint32_t a, uint32_t b) {
     for (;;) {
         a = uf_find_cg(P, a), b = uf_find_cg(P, b);
-        if (a == b) return;
+        if (a == b) return a;
         if (a > b) {
             uint32_t t = a;
             a = b, b = t;
         }
-        if (atomicCAS(P + b, b, a) == b) return;
+        if (atomicCAS(P + b, b, a) == b) return a;
     }
 }
 
@@ -236,53 +236,61 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                             S.G[x] = (unsigned char)g;
                         }
                         __syncwarp();
-                        // uniform walk over the remaining lanes
+                        // uniform walk over the EMPTY lanes only: between two of them the cursor advances by the
+                        // number of drawing diagonal ops, which every lane counts for itself with mask arithmetic
+                        const uint32_t stopA = ambD ? (uint32_t)__ffs(ambD) - 1u : 32u;  // needs the exact path
+                        const uint32_t predE = remE & lt_mask;
+                        const int le = predE ? 31 - __clz(predE) : -1;  // last EMPTY lane before me
+                        const uint32_t after_le = le < 0 ? FULL : ~((2u << le) - 1u);
+                        const uint32_t dcount = (uint32_t)__popc(drawD & lt_mask & after_le);  // draws between it and me
                         uint32_t x = (uint32_t)(cur - wbase), myx = 0, stop = 32u;
-                        bool need_exact = false, overridden = false;
-                        for (uint32_t mm = rem; mm; mm &= mm - 1) {
-                            const uint32_t i = (uint32_t)__ffs(mm) - 1u;
-                            if ((uint32_t)lane == i) myx = x;
-                            if ((remE >> i) & 1u) {
-                                uint32_t g = x < 64u ? (uint32_t)S.G[x] : 255u;
-                                if (g >= 254u) {
-                                    if (g == 255u) { stop = i; break; }
-                                    // hazard: the word's spins are flipped inside this step -> evaluate for lane i
-                                    DBG(12, 1);
-                                    const uint32_t y = x + (uint32_t)__ffsll((long long)(ACC >> x)) - 1u;
-                                    const uint32_t wv = S.opw[y];
-                                    const uint32_t b = op_bond(wv);
-                                    const int kind = bond_kind(D, b);
-                                    uint32_t v0, v1;
-                                    bond_vars(D, b, kind, v0, v1);
-                                    uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
-                                    for (uint32_t m2 = __ballot_sync(FULL, type == T_OFFD) & ((1u << i) - 1u); m2; m2 &= m2 - 1) {
-                                        const uint32_t fv = S.fl[__ffs(m2) - 1];
-                                        s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
-                                    }
-                                    const double num = bn * bond_weight(D, b, kind, s0, s1);
-                                    const uint32_t bitsv = s0 | (s1 << 1);
-                                    bool ok, ex;
-                                    if (num >= dhiA) ok = true, ex = false;
-                                    else if (num == 0.0) ok = false, ex = true;
-                                    else if (num > 0.0 && num < dloA && y + 1 < 64) {
-                                        ex = true;
-                                        const uint64_t v2 = S.win[y + 1];
-                                        if (v2 < bool_threshold(num / dhiA)) ok = true;
-                                        else if (v2 >= bool_threshold(num / dloA)) ok = false;
-                                        else { stop = i, need_exact = true; break; }
-                                    } else { stop = i, need_exact = true; break; }
-                                    if ((uint32_t)lane == i) overridden = true, neww = ok ? make_op(b, bitsv, bitsv) : OP_EMPTY, dn = ok, dc = y + 1u + (ex ? 1u : 0u) - x;
-                                    g = y + 1u + (ex ? 1u : 0u);
+                        uint32_t basex = x;  // cursor right after my last EMPTY predecessor
+                        bool hz_fail = false, overridden = false;
+                        uint32_t mmE = stopA < 32u ? (remE & ((1u << stopA) - 1u)) : remE;
+                        while (mmE) {
+                            const uint32_t i = (uint32_t)__ffs(mmE) - 1u;
+                            mmE &= mmE - 1;
+                            const uint32_t xs = x + __shfl_sync(FULL, dcount, i);
+                            uint32_t g = xs < 64u ? (uint32_t)S.G[xs] : 255u;
+                            if (g >= 254u) {
+                                if (g == 255u) { stop = i; break; }
+                                // hazard: the word's spins are flipped inside this step -> evaluate for lane i
+                                DBG(12, 1);
+                                const uint32_t y = xs + (uint32_t)__ffsll((long long)(ACC >> xs)) - 1u;
+                                const uint32_t b = op_bond(S.opw[y]);
+                                const int kind = bond_kind(D, b);
+                                uint32_t v0, v1;
+                                bond_vars(D, b, kind, v0, v1);
+                                uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
+                                for (uint32_t m2 = __ballot_sync(FULL, type == T_OFFD) & ((1u << i) - 1u); m2; m2 &= m2 - 1) {
+                                    const uint32_t fv = S.fl[__ffs(m2) - 1];
+                                    s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
                                 }
-                                x = g;
-                            } else {  // diagonal op
-                                if ((ambD >> i) & 1u) { stop = i, need_exact = true; break; }
-                                if ((drawD >> i) & 1u) {
-                                    if (x >= 64u) { stop = i; break; }
-                                    x += 1u;
-                                }
+                                const double num = bn * bond_weight(D, b, kind, s0, s1);
+                                const uint32_t bitsv = s0 | (s1 << 1);
+                                bool ok = false, ex = false, fail = false;
+                                if (num >= dhiA) ok = true;
+                                else if (num == 0.0) ex = true;
+                                else if (num > 0.0 && num < dloA && y + 1 < 64) {
+                                    ex = true;
+                                    const uint64_t v2 = S.win[y + 1];
+                                    if (v2 < bool_threshold(num / dhiA)) ok = true;
+                                    else if (!(v2 >= bool_threshold(num / dloA))) fail = true;
+                                } else fail = true;
+                                if (fail) { stop = i, hz_fail = true; break; }
+                                g = y + 1u + (ex ? 1u : 0u);
+                                if ((uint32_t)lane == i) overridden = true, neww = ok ? make_op(b, bitsv, bitsv) : OP_EMPTY, dn = ok, dc = g - xs;
                             }
+                            if ((uint32_t)lane == i) myx = xs;
+                            if (le == (int)i) basex = g;
+                            x = g;
                         }
+                        if (stop >= 32u && stopA < 32u) stop = stopA;
+                        bool need_exact = hz_fail || (stopA < 32u && stop == stopA);
+                        if (type != T_EMPTY) myx = basex + dcount;
+                        // a drawing diagonal op beyond the window ends the resolved prefix as well
+                        const uint32_t ovD = __ballot_sync(FULL, inrem && type == T_DIAG && draws && myx >= 64u && (uint32_t)lane < stop);
+                        if (ovD) stop = (uint32_t)__ffs(ovD) - 1u, need_exact = false;
                         const uint32_t resolved = stop >= 32u ? rem : (rem & ((1u << stop) - 1u));
                         // decisions of the resolved lanes
                         bool unres = false;
@@ -432,28 +440,40 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                     kind = bond_kind(D, op_bond(fw));
                     bond_vars(D, op_bond(fw), kind, v0, v1);
                 }
-                S.sv[lane] = kind == KIND_SITE ? v0 : NONE32;
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
-                __syncwarp();
                 const uint32_t myid = N + nsite + (uint32_t)__popc(smask & lt_mask);
                 if (kind == KIND_SITE) st_cg(P + myid, myid);
                 if (kind >= 0) {
                     atomicOr(&S.tb[v0 >> 5], 1u << (v0 & 31));
                     if (kind == KIND_BOND) atomicOr(&S.tb[v1 >> 5], 1u << (v1 & 31));
                 }
-                uint32_t ra = 0, rb = 0;
-                if (kind == KIND_BOND || (HAS_H && kind == KIND_LONG)) {
-                    ra = S.rep[v0], rb = kind == KIND_BOND ? S.rep[v1] : 0u;
-                    for (uint32_t m = smask & lt_mask; m; m &= m - 1) {
+                // representative of the segment open on my variables at my slot: the table entry, unless a
+                // site op of this step cuts the variable at an earlier lane (uniform loop over those site ops)
+                const bool joins = kind == KIND_BOND || (HAS_H && kind == KIND_LONG);
+                uint32_t ra = 0, rb = 0, oa = 0, ob = 0;
+                bool fa = false, fb = false;  // value came from the table (may be refreshed with the root)
+                if (joins) {
+                    oa = ra = S.rep[v0], fa = true;
+                    if (kind == KIND_BOND) ob = rb = S.rep[v1], fb = true;
+                }
+                {
+                    uint32_t id = N + nsite;
+                    for (uint32_t m = smask; m; m &= m - 1, id++) {
                         const int j = __ffs(m) - 1;
-                        const uint32_t cv = S.sv[j], id = N + nsite + (uint32_t)__popc(smask & ((1u << j) - 1u));
-                        if (cv == v0) ra = id;
-                        if (kind == KIND_BOND && cv == v1) rb = id;
+                        const uint32_t cv = __shfl_sync(FULL, v0, j);
+                        if (j < lane) {
+                            if (cv == v0) ra = id, fa = false;
+                            if (cv == v1 && kind == KIND_BOND) rb = id, fb = false;
+                        }
                     }
                 }
                 __syncwarp();  // new ids are initialised before anyone follows them
                 if (kind == KIND_BOND) {
-                    if (ra != rb) uf_union_cg(P, ra, rb);
+                    if (ra != rb) {
+                        const uint32_t root = uf_union_cg(P, ra, rb);
+                        if (fa) atomicCAS(&S.rep[v0], oa, root);  // cache the root: equal roots skip the union
+                        if (fb) atomicCAS(&S.rep[v1], ob, root);
+                    }
                 } else if (HAS_H && kind == KIND_LONG) {
                     atomicOr(&frz[ra >> 5], 1u << (ra & 31));
                     anylong = true;
@@ -552,7 +572,6 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                     kind = bond_kind(D, op_bond(w));
                     bond_vars(D, op_bond(w), kind, v0, v1);
                 }
-                S.sv[lane] = kind == KIND_SITE ? v0 : NONE32;
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
                 bool outdec = false;
                 if (kind == KIND_SITE) {
@@ -560,26 +579,25 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                     outdec = (ld_cg(decb + (id >> 5)) >> (id & 31)) & 1u;
                 }
                 const uint32_t odmask = __ballot_sync(FULL, outdec);
-                __syncwarp();
-                if (kind >= 0) {
-                    bool din = (S.cd[v0 >> 5] >> (v0 & 31)) & 1u;
-                    for (uint32_t m = smask & lt_mask; m; m &= m - 1) {
-                        const int j = __ffs(m) - 1;
-                        if (S.sv[j] == v0) din = (odmask >> j) & 1u;
+                bool din = kind >= 0 ? ((S.cd[v0 >> 5] >> (v0 & 31)) & 1u) : false;
+                bool lastone = true;
+                for (uint32_t m = smask; m; m &= m - 1) {  // uniform loop over the site ops of this step
+                    const int j = __ffs(m) - 1;
+                    const uint32_t cv = __shfl_sync(FULL, v0, j);
+                    if (cv == v0) {
+                        if (j < lane) din = (odmask >> j) & 1u;  // decision of the segment opened by that site op
+                        else if (j > lane) lastone = false;
                     }
+                }
+                if (kind >= 0) {
                     const uint32_t mask = kind == KIND_BOND ? 3u : 1u;
                     const bool dout = kind == KIND_SITE ? outdec : din;
                     if (din || dout) ops[p] = make_op(op_bond(w), op_in(w) ^ (din ? mask : 0u), op_out(w) ^ (dout ? mask : 0u));
                 }
                 __syncwarp();
-                if (kind == KIND_SITE) {  // the last site op of the step on this variable sets the open decision
-                    bool lastone = true;
-                    for (uint32_t m = smask & ~lt_mask & ~(1u << lane); m; m &= m - 1)
-                        if (S.sv[__ffs(m) - 1] == v0) lastone = false;
-                    if (lastone) {
-                        if (outdec) atomicOr(&S.cd[v0 >> 5], 1u << (v0 & 31));
-                        else atomicAnd(&S.cd[v0 >> 5], ~(1u << (v0 & 31)));
-                    }
+                if (kind == KIND_SITE && lastone) {  // the last site op of the step on a variable sets its open decision
+                    if (outdec) atomicOr(&S.cd[v0 >> 5], 1u << (v0 & 31));
+                    else atomicAnd(&S.cd[v0 >> 5], ~(1u << (v0 & 31)));
                 }
                 ks += (uint32_t)__popc(smask);
                 __syncwarp();
