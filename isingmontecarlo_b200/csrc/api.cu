@@ -342,6 +342,11 @@ extern "C" int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value) {
         h->impl = (int)value;
         return QMCB_OK;
     }
+    if (!strcmp(name, "minblocks")) {
+        extern int g_sse_fast_minblocks;
+        g_sse_fast_minblocks = (int)value;
+        return QMCB_OK;
+    }
     if (!strcmp(name, "debug_counters")) {
         if (value && !h->D.dbg) {
             if (h->pool.alloc(&h->D.dbg, 16) != cudaSuccess) return fail(QMCB_ERR_CUDA, "alloc debug counters");

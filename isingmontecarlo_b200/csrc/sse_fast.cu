@@ -77,8 +77,8 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
     return ((((size_t)3 * Nw + N + 64 + 64 + 16) * 4 + 64 * 8) + 15) / 16 * 16;
 }
 
-template <bool HAS_H>
-__global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
+template <bool HAS_H, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
                                                   uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -184,8 +184,14 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                         if (inrem && type == T_DIAG) {
                             const bool nd_lo = dlo + 1.0 >= dnum, nd_hi = dhi + 1.0 >= dnum;  // den >= num: removed, no draw
                             if (!nd_lo) {
+                                // conservative bounds on the threshold over the den interval: one reciprocal, a
+                                // guard band far above its rounding error; a word inside the band (p ~ 2^-43) is
+                                // settled below with the exact division at the exact n
                                 draws = true, ambdc = nd_hi;
-                                t_lo = bool_threshold((dlo + 1.0) / dnum), t_hi = bool_threshold((dhi + 1.0) / dnum);
+                                const double rc = 1.0 / dnum;
+                                const uint64_t a_lo = bool_threshold((dlo + 1.0) * rc), a_hi = bool_threshold((dhi + 1.0) * rc);
+                                t_lo = a_lo > (1ull << 20) ? a_lo - (1ull << 20) : 0ull;
+                                t_hi = a_hi < ~0ull - (1ull << 20) ? a_hi + (1ull << 20) : ~0ull;
                             }
                         }
                         const uint32_t drawD = __ballot_sync(FULL, draws), ambD = __ballot_sync(FULL, ambdc);
@@ -247,43 +253,53 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                         uint32_t basex = x;  // cursor right after my last EMPTY predecessor
                         bool hz_fail = false, overridden = false;
                         uint32_t mmE = stopA < 32u ? (remE & ((1u << stopA) - 1u)) : remE;
-                        while (mmE) {
-                            const uint32_t i = (uint32_t)__ffs(mmE) - 1u;
-                            mmE &= mmE - 1;
-                            const uint32_t xs = x + __shfl_sync(FULL, dcount, i);
-                            uint32_t g = xs < 64u ? (uint32_t)S.G[xs] : 255u;
-                            if (g >= 254u) {
-                                if (g == 255u) { stop = i; break; }
-                                // hazard: the word's spins are flipped inside this step -> evaluate for lane i
-                                DBG(12, 1);
-                                const uint32_t y = xs + (uint32_t)__ffsll((long long)(ACC >> xs)) - 1u;
-                                const uint32_t b = op_bond(S.opw[y]);
-                                const int kind = bond_kind(D, b);
-                                uint32_t v0, v1;
-                                bond_vars(D, b, kind, v0, v1);
-                                uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
-                                for (uint32_t m2 = __ballot_sync(FULL, type == T_OFFD) & ((1u << i) - 1u); m2; m2 &= m2 - 1) {
-                                    const uint32_t fv = S.fl[__ffs(m2) - 1];
-                                    s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
+                        for (;;) {
+                            uint32_t hz_i = 32u, hz_x = 0;
+                            while (mmE) {  // tight loop; the rare hazard is handled outside
+                                const uint32_t i = (uint32_t)__ffs(mmE) - 1u;
+                                const uint32_t xs = x + __shfl_sync(FULL, dcount, i);
+                                const uint32_t g = xs < 64u ? (uint32_t)S.G[xs] : 255u;
+                                if (g >= 254u) {
+                                    if (g == 255u) stop = i, mmE = 0;
+                                    else hz_i = i, hz_x = xs;
+                                    break;
                                 }
-                                const double num = bn * bond_weight(D, b, kind, s0, s1);
-                                const uint32_t bitsv = s0 | (s1 << 1);
-                                bool ok = false, ex = false, fail = false;
-                                if (num >= dhiA) ok = true;
-                                else if (num == 0.0) ex = true;
-                                else if (num > 0.0 && num < dloA && y + 1 < 64) {
-                                    ex = true;
-                                    const uint64_t v2 = S.win[y + 1];
-                                    if (v2 < bool_threshold(num / dhiA)) ok = true;
-                                    else if (!(v2 >= bool_threshold(num / dloA))) fail = true;
-                                } else fail = true;
-                                if (fail) { stop = i, hz_fail = true; break; }
-                                g = y + 1u + (ex ? 1u : 0u);
-                                if ((uint32_t)lane == i) overridden = true, neww = ok ? make_op(b, bitsv, bitsv) : OP_EMPTY, dn = ok, dc = g - xs;
+                                mmE &= mmE - 1;
+                                if ((uint32_t)lane == i) myx = xs;
+                                if (le == (int)i) basex = g;
+                                x = g;
                             }
-                            if ((uint32_t)lane == i) myx = xs;
+                            if (hz_i >= 32u) break;
+                            // hazard: the word's spins are flipped inside this step -> evaluate for lane hz_i
+                            DBG(12, 1);
+                            const uint32_t i = hz_i, xs = hz_x;
+                            const uint32_t y = xs + (uint32_t)__ffsll((long long)(ACC >> xs)) - 1u;
+                            const uint32_t b = op_bond(S.opw[y]);
+                            const int kind = bond_kind(D, b);
+                            uint32_t v0, v1;
+                            bond_vars(D, b, kind, v0, v1);
+                            uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
+                            for (uint32_t m2 = __ballot_sync(FULL, type == T_OFFD) & ((1u << i) - 1u); m2; m2 &= m2 - 1) {
+                                const uint32_t fv = S.fl[__ffs(m2) - 1];
+                                s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
+                            }
+                            const double num = bn * bond_weight(D, b, kind, s0, s1);
+                            const uint32_t bitsv = s0 | (s1 << 1);
+                            bool ok = false, ex = false, fail = false;
+                            if (num >= dhiA) ok = true;
+                            else if (num == 0.0) ex = true;
+                            else if (num > 0.0 && num < dloA && y + 1 < 64) {
+                                ex = true;
+                                const uint64_t v2 = S.win[y + 1];
+                                if (v2 < bool_threshold(num / dhiA)) ok = true;
+                                else if (!(v2 >= bool_threshold(num / dloA))) fail = true;
+                            } else fail = true;
+                            if (fail) { stop = i, hz_fail = true; break; }
+                            const uint32_t g = y + 1u + (ex ? 1u : 0u);
+                            if ((uint32_t)lane == i) overridden = true, neww = ok ? make_op(b, bitsv, bitsv) : OP_EMPTY, dn = ok, dc = g - xs, myx = xs;
                             if (le == (int)i) basex = g;
                             x = g;
+                            mmE &= mmE - 1;
                         }
                         if (stop >= 32u && stopA < 32u) stop = stopA;
                         bool need_exact = hz_fail || (stopA < 32u && stop == stopA);
@@ -444,8 +460,8 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                 const uint32_t myid = N + nsite + (uint32_t)__popc(smask & lt_mask);
                 if (kind == KIND_SITE) st_cg(P + myid, myid);
                 if (kind >= 0) {
-                    atomicOr(&S.tb[v0 >> 5], 1u << (v0 & 31));
-                    if (kind == KIND_BOND) atomicOr(&S.tb[v1 >> 5], 1u << (v1 & 31));
+                    if (!state_bit(S.tb, v0)) atomicOr(&S.tb[v0 >> 5], 1u << (v0 & 31));
+                    if (kind == KIND_BOND && !state_bit(S.tb, v1)) atomicOr(&S.tb[v1 >> 5], 1u << (v1 & 31));
                 }
                 // representative of the segment open on my variables at my slot: the table entry, unless a
                 // site op of this step cuts the variable at an earlier lane (uniform loop over those site ops)
@@ -457,15 +473,13 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                     if (kind == KIND_BOND) ob = rb = S.rep[v1], fb = true;
                 }
                 {
-                    uint32_t id = N + nsite;
-                    for (uint32_t m = smask; m; m &= m - 1, id++) {
-                        const int j = __ffs(m) - 1;
-                        const uint32_t cv = __shfl_sync(FULL, v0, j);
-                        if (j < lane) {
-                            if (cv == v0) ra = id, fa = false;
-                            if (cv == v1 && kind == KIND_BOND) rb = id, fb = false;
-                        }
-                    }
+                    // lanes with the same key see each other: site ops publish their variable in both rounds,
+                    // joining ops ask for v0 then v1; the nearest earlier site op on the variable wins
+                    const uint32_t nokey = 0x80000000u | (uint32_t)lane;
+                    const uint32_t ma = __match_any_sync(FULL, kind >= 0 ? v0 : nokey) & smask & lt_mask;
+                    const uint32_t mb = __match_any_sync(FULL, kind == KIND_BOND ? v1 : (kind == KIND_SITE ? v0 : nokey)) & smask & lt_mask;
+                    if (joins && ma) ra = N + nsite + (uint32_t)__popc(smask & ((1u << (31 - __clz(ma))) - 1u)), fa = false;
+                    if (kind == KIND_BOND && mb) rb = N + nsite + (uint32_t)__popc(smask & ((1u << (31 - __clz(mb))) - 1u)), fb = false;
                 }
                 __syncwarp();  // new ids are initialised before anyone follows them
                 if (kind == KIND_BOND) {
@@ -580,15 +594,9 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
                 }
                 const uint32_t odmask = __ballot_sync(FULL, outdec);
                 bool din = kind >= 0 ? ((S.cd[v0 >> 5] >> (v0 & 31)) & 1u) : false;
-                bool lastone = true;
-                for (uint32_t m = smask; m; m &= m - 1) {  // uniform loop over the site ops of this step
-                    const int j = __ffs(m) - 1;
-                    const uint32_t cv = __shfl_sync(FULL, v0, j);
-                    if (cv == v0) {
-                        if (j < lane) din = (odmask >> j) & 1u;  // decision of the segment opened by that site op
-                        else if (j > lane) lastone = false;
-                    }
-                }
+                const uint32_t mt = __match_any_sync(FULL, kind >= 0 ? v0 : (0x80000000u | (uint32_t)lane)) & smask;
+                if (mt & lt_mask) din = (odmask >> (31 - __clz(mt & lt_mask))) & 1u;  // segment opened by the nearest earlier site op
+                const bool lastone = (mt & ~lt_mask & ~(1u << lane)) == 0;
                 if (kind >= 0) {
                     const uint32_t mask = kind == KIND_BOND ? 3u : 1u;
                     const bool dout = kind == KIND_SITE ? outdec : din;
@@ -648,6 +656,8 @@ __global__ void __launch_bounds__(128) k_sse_fast(SseDev D, uint64_t target, uin
     if (err) atomicOr(D.status, err);
 }
 
+int g_sse_fast_minblocks = 7;  // resident blocks per SM the kernel is compiled for (register cap)
+
 // returns the number of kernel launches, or -1 if this shape is not supported by the warp kernels
 int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
@@ -657,7 +667,14 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
     if (per_warp * warps > 200 * 1024) return -1;
     const size_t smem = per_warp * warps;
     const uint32_t blocks = (D.R + warps - 1) / warps;
-    auto kern = D.has_h ? k_sse_fast<true> : k_sse_fast<false>;
+    typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t);
+    Kern kern;
+    switch (g_sse_fast_minblocks) {
+        case 4: kern = D.has_h ? k_sse_fast<true, 4> : k_sse_fast<false, 4>; break;
+        case 6: kern = D.has_h ? k_sse_fast<true, 6> : k_sse_fast<false, 6>; break;
+        case 8: kern = D.has_h ? k_sse_fast<true, 8> : k_sse_fast<false, 8>; break;
+        default: kern = D.has_h ? k_sse_fast<true, 7> : k_sse_fast<false, 7>; break;
+    }
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     kern<<<blocks, warps * 32, smem, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep);
     return 1;

@@ -22,6 +22,8 @@ t0 = time.perf_counter()
 g.timesteps(therm, beta)
 print(f"therm {therm} sweeps: {time.perf_counter() - t0:.3f} s, <n>={g.get_n().mean():.0f} <M>={g.get_cutoff().mean():.0f}")
 g.set_mode(mode)
+if os.environ.get('PROF_MINB'):
+    g.set_option('minblocks', int(os.environ['PROF_MINB']))
 if os.environ.get('PROF_DBG'):
     g.set_option('debug_counters', 1)
 for k in range(sweeps):
