@@ -888,20 +888,22 @@ extern "C" int cmcb_create(const QmcbLattice *lat, const double *biases, uint32_
     if (square) {
         D.L = L;
         TRYC(h->pool.alloc(&D.planes, (size_t)R * 2 * L * (L >> 6)));
-        std::vector<uint32_t> thr((size_t)R * 16, 0u), alw(R, 0u);
+        std::vector<uint32_t> thr((size_t)R * 16, 0u), alw(R, 0u), prob(R, 0u);
         for (uint32_t r = 0; r < R; r++)
             for (int own = 0; own < 2; own++)
                 for (int cnt = 0; cnt <= 4; cnt++) {
                     uint64_t T = metropolis_threshold(betas[r], sq_de[own * 8 + cnt]);
                     if (T >= 4294967296ull) alw[r] |= 1u << (own * 8 + cnt);
-                    else thr[(size_t)r * 16 + own * 8 + cnt] = (uint32_t)T;
+                    else if (T > 0) prob[r] |= 1u << (own * 8 + cnt), thr[(size_t)r * 16 + own * 8 + cnt] = (uint32_t)T;
                 }
-        uint32_t *thr_dev, *alw_dev;
+        uint32_t *thr_dev, *alw_dev, *prob_dev;
         TRYC(h->pool.alloc(&thr_dev, thr.size()));
         TRYC(h->pool.alloc(&alw_dev, alw.size()));
+        TRYC(h->pool.alloc(&prob_dev, prob.size()));
         TRYC(cudaMemcpy(thr_dev, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
         TRYC(cudaMemcpy(alw_dev, alw.data(), alw.size() * 4, cudaMemcpyHostToDevice));
-        D.sq_thr = thr_dev, D.sq_always = alw_dev;
+        TRYC(cudaMemcpy(prob_dev, prob.data(), prob.size() * 4, cudaMemcpyHostToDevice));
+        D.sq_thr = thr_dev, D.sq_always = alw_dev, D.sq_prob = prob_dev;
         TRYC(h->pool.alloc(&h->bytes_dev, (size_t)R * N));
     } else {
         // CSR + site classes + per-replica threshold tables

@@ -2,59 +2,79 @@
 //
 // Per-site rule = the reference's (delta_e of do_spin_flip classical/graph.rs:98-115, should_flip
 // :339-347); the checkerboard schedule and the fixed-width draw are builder-defined (the reference
-// only has a random-site schedule, graph.rs:350-406): the site of rank r inside colour c uses
-// word (r & 3) of Philox4x32-10(key, ctr = (r >> 2, sweep_lo, sweep_hi, 'CB' << 16 | c)) and flips
-// iff d < T, T = #{d : d * 2^-32 < exp(-beta * delta_e)} (2^32 when delta_e <= 0).  The thresholds
-// are tabulated on the host with libm's exp so no device transcendental can leak into the result.
+// only has a random-site schedule, graph.rs:350-406).  Draws are BIT-SLICED: the sites of a colour
+// are grouped 32 consecutive ranks per group; bit-plane k (MSB first) of group g is output word (k & 3)
+// of Philox4x32-10(key, ctr = (4 g + ((k & 15) >> 2), sweep_lo, sweep_hi, tag | c)), tag 'CB'/'CC' << 16
+// for planes 0..15 / 16..31, and site j of the group draws d = sum_k bit_j(plane_k) << (31 - k).  It
+// flips iff d < T, T = #{d : d * 2^-32 < exp(-beta * delta_e)} (2^32 when delta_e <= 0).  The
+// thresholds are tabulated on the host with libm's exp so no device transcendental can leak in.
+// A 32-site word is compared against a threshold with a bit-serial ripple over the planes (3 logic
+// ops per plane for all 32 sites, ties included), and the low 16 planes are only generated when a
+// site of a probabilistic class still ties after the high 16 (p = 2^-16 per site).
 //
 // Two layouts:
 //  * generic graph: one byte per spin (the reference's Vec<bool>), CSR neighbours, one thread per
-//    4 consecutive ranks of a colour (one Philox call), threshold table per (replica, site class).
+//    group of 32 ranks of a colour, threshold table per (replica, site class).
 //  * L x L periodic square lattice, uniform J and bias: spins bit-packed in two colour planes,
-//    one thread per 32 sites: neighbour counts by bit-sliced adders, 8 Philox calls, no divergence.
+//    one thread per 32 sites: neighbour counts by bit-sliced adders, 4 Philox calls, no divergence.
 #include "classical.cuh"
 
 // ------------------------------------------------------------------------------------------
-// generic graph
+// generic graph: one thread per group of 32 ranks of the colour
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cls_generic(ClsDev D, uint32_t colour, uint32_t cstart, uint32_t ccount,
+__device__ __forceinline__ void planes16(uint32_t group, uint64_t sweep, uint32_t tag_c, uint32_t k0, uint32_t k1, uint32_t *pl) {
+#pragma unroll
+    for (uint32_t q = 0; q < 4; q++) {
+        Philox4 o = philox4x32_10(4 * group + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), tag_c, k0, k1);
+        pl[4 * q] = o.x, pl[4 * q + 1] = o.y, pl[4 * q + 2] = o.z, pl[4 * q + 3] = o.w;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_cls_generic(ClsDev D, uint32_t colour, uint32_t cstart, uint32_t ccount,
                                                      uint64_t sweep) {
     const uint32_t r = blockIdx.y;
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 ranks
-    if (q * 4 >= ccount) return;
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;  // group of 32 ranks
+    if (g * 32 >= ccount) return;
     const uint64_t key = D.key[r];
-    Philox4 o = philox4x32_10(q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, (uint32_t)key,
-                              (uint32_t)(key >> 32));
-    const uint32_t d[4] = {o.x, o.y, o.z, o.w};
+    uint32_t pl[32];
+    planes16(g, sweep, QMCB_TAG_CB | colour, (uint32_t)key, (uint32_t)(key >> 32), pl);
+    planes16(g, sweep, QMCB_TAG_CB2 | colour, (uint32_t)key, (uint32_t)(key >> 32), pl + 16);
     uint8_t *sp = D.spins + (size_t)r * D.N;
     const unsigned long long *thr = D.thr + (size_t)r * D.thr_stride;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint32_t rank = q * 4 + k;
+    for (uint32_t j = 0; j < 32; j++) {
+        const uint32_t rank = g * 32 + j;
         if (rank >= ccount) break;
-        uint32_t i = __ldg(D.colour_sites + cstart + rank);
-        uint32_t s = sp[i];
-        uint32_t a0 = __ldg(D.adj_start + i), a1 = __ldg(D.adj_start + i + 1);
+        uint32_t d = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k++) d |= ((pl[k] >> j) & 1u) << (31 - k);
+        const uint32_t i = __ldg(D.colour_sites + cstart + rank);
+        const uint32_t s = sp[i];
+        const uint32_t a0 = __ldg(D.adj_start + i), a1 = __ldg(D.adj_start + i + 1);
         uint32_t mask = 0;
         for (uint32_t e = a0; e < a1; e++) mask |= (uint32_t)(sp[__ldg(D.adj_idx + e)] == s) << (e - a0);
-        uint32_t cls = __ldg(D.site_class + i);
-        unsigned long long T = thr[__ldg(D.class_off + cls) + ((s << (a1 - a0)) | mask)];
-        if ((unsigned long long)d[k] < T) sp[i] = (uint8_t)(s ^ 1u);
+        const uint32_t cls = __ldg(D.site_class + i);
+        const unsigned long long T = thr[__ldg(D.class_off + cls) + ((s << (a1 - a0)) | mask)];
+        if ((unsigned long long)d < T) sp[i] = (uint8_t)(s ^ 1u);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // square lattice, bit-packed colour planes.
 // plane[c][y][w] bit j  <->  site (x, y) with x = 2 * (32 w + j) + ((y + c) & 1); colour = (x+y)&1.
+// The 32 sites of a word are exactly one group of 32 consecutive ranks (rank = y * L/2 + 32 w + j).
 // ------------------------------------------------------------------------------------------
-template <int NCALLS>
-__device__ __forceinline__ void philox_batch(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                             uint32_t k1, uint32_t (&out)[NCALLS * 4]) {
+// sites (bits of `sel`) whose draw is below T, looking at planes pl[0..15] = bits hi..hi-15 of the draw;
+// on return `eq` holds the selected sites still tied with T on those bits
+__device__ __forceinline__ uint32_t ripple16(const uint32_t *pl, uint32_t T16, uint32_t sel, uint32_t &eq) {
+    uint32_t lt = 0;
+    eq = sel;
 #pragma unroll
-    for (int q = 0; q < NCALLS; q++) {
-        Philox4 o = philox4x32_10(c0 + q, c1, c2, c3, k0, k1);
-        out[4 * q] = o.x, out[4 * q + 1] = o.y, out[4 * q + 2] = o.z, out[4 * q + 3] = o.w;
+    for (int k = 0; k < 16; k++) {
+        const uint32_t tk = (uint32_t)((int32_t)(T16 << (16 + k)) >> 31);  // bit (15 - k) of T16 as a mask
+        lt |= eq & ~pl[k] & tk;
+        eq &= ~(pl[k] ^ tk);
     }
+    return lt;
 }
 
 __global__ void __launch_bounds__(256) k_cls_square(ClsDev D, uint32_t colour, uint64_t sweep) {
@@ -78,26 +98,52 @@ __global__ void __launch_bounds__(256) k_cls_square(ClsDev D, uint32_t colour, u
         uint32_t prv = other[y * WPR + (w == 0 ? WPR - 1 : w - 1)];
         side = (same << 1) | (prv >> 31);
     }
-    // bit-sliced count of anti-aligned neighbours: cnt = lo + 2 mid + 4 hi
+    // bit-sliced count of anti-aligned neighbours: cnt = lo + 2 mid + 4 hi, then one-hot masks
     const uint32_t a = own ^ same, b = own ^ side, c = own ^ up, d = own ^ dn;
     const uint32_t s1 = a ^ b ^ c, c1 = (a & b) | (c & (a ^ b));
     const uint32_t lo = s1 ^ d, c2 = s1 & d;
     const uint32_t mid = c1 ^ c2, hi = c1 & c2;
-    // draws: ranks y * L/2 + 32 w + j, j = 0..31  ->  8 consecutive Philox counters
+    uint32_t cm[5];
+    cm[0] = ~(lo | mid | hi), cm[1] = lo & ~mid, cm[2] = mid & ~lo, cm[3] = lo & mid, cm[4] = hi;
+    // the 16 most significant bit-planes of the 32 draws of this word
     const uint64_t key = D.key[r];
-    uint32_t dr[32];
-    philox_batch<8>((y * (D.L >> 1) + 32 * w) >> 2, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour,
-                    (uint32_t)key, (uint32_t)(key >> 32), dr);
-    // threshold table of this replica: index = own << 3 | cnt; 2^32 ("always") is stored as
-    // always-bit 16 + idx of `alw`
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    uint32_t pl[16];
+    planes16(t, sweep, QMCB_TAG_CB | colour, k0, k1, pl);
+    // classes: index = own << 3 | cnt;  always-flip classes, and probabilistic ones with threshold T
+    const uint32_t alw = D.sq_always[r], prob = D.sq_prob[r];
     const uint32_t *T = D.sq_thr + (size_t)r * 16;
-    const uint32_t alw = D.sq_always[r];
-    uint32_t flip = 0;
+    uint32_t flip = 0, tied = 0;
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-        uint32_t idx = ((lo >> j) & 1u) | (((mid >> j) & 1u) << 1) | (((hi >> j) & 1u) << 2) | (((own >> j) & 1u) << 3);
-        bool f = ((alw >> idx) & 1u) || dr[j] < __ldg(T + idx);
-        flip |= (uint32_t)f << j;
+    for (int o = 0; o < 2; o++) {
+        const uint32_t om = o ? own : ~own;
+#pragma unroll
+        for (int cc = 0; cc < 5; cc++) {
+            const uint32_t idx = o * 8 + cc;
+            if ((alw >> idx) & 1u) flip |= om & cm[cc];
+            else if ((prob >> idx) & 1u) {  // block-uniform branch
+                uint32_t eq;
+                flip |= ripple16(pl, __ldg(T + idx) >> 16, om & cm[cc], eq);
+                tied |= eq;
+            }
+        }
+    }
+    if (tied) {  // some draw equals its threshold on the high 16 bits (p = 2^-16 per site): low 16 planes
+        uint32_t pl2[16];
+        planes16(t, sweep, QMCB_TAG_CB2 | colour, k0, k1, pl2);
+#pragma unroll
+        for (int o = 0; o < 2; o++) {
+            const uint32_t om = o ? own : ~own;
+#pragma unroll
+            for (int cc = 0; cc < 5; cc++) {
+                const uint32_t idx = o * 8 + cc;
+                if ((prob >> idx) & 1u) {
+                    uint32_t eqh, eql;
+                    ripple16(pl, __ldg(T + idx) >> 16, om & cm[cc], eqh);
+                    if (eqh) flip |= ripple16(pl2, __ldg(T + idx) & 0xFFFFu, eqh, eql);
+                }
+            }
+        }
     }
     mine[t] = own ^ flip;
 }
@@ -179,9 +225,9 @@ __global__ void k_cls_generic_energy(ClsDev D, const double *adj_j, const double
 }
 
 void launch_cls_generic(const ClsDev &D, uint32_t colour, uint32_t cstart, uint32_t ccount, uint64_t sweep, cudaStream_t st) {
-    uint32_t groups = (ccount + 3) / 4;
-    dim3 grid((groups + 255) / 256, D.R);
-    k_cls_generic<<<grid, 256, 0, st>>>(D, colour, cstart, ccount, sweep);
+    uint32_t groups = (ccount + 31) / 32;
+    dim3 grid((groups + 127) / 128, D.R);
+    k_cls_generic<<<grid, 128, 0, st>>>(D, colour, cstart, ccount, sweep);
 }
 void launch_cls_square(const ClsDev &D, uint32_t colour, uint64_t sweep, cudaStream_t st) {
     uint32_t words = D.L * (D.L >> 6);

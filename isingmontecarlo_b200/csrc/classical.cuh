@@ -19,4 +19,5 @@ struct ClsDev {
     uint32_t *planes;          // [R][2][L][L/64] bit-packed colour planes
     const uint32_t *sq_thr;    // [R][16] thresholds, index own << 3 | #anti-aligned neighbours
     const uint32_t *sq_always; // [R] bit idx set: always flip (threshold 2^32)
+    const uint32_t *sq_prob;   // [R] bit idx set: 0 < threshold < 2^32
 };

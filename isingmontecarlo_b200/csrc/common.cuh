@@ -5,7 +5,8 @@
 #include <stdint.h>
 
 #define QMCB_TAG_CLUS 0x434C5553u  // counter word 3 of the FAST-mode cluster bits
-#define QMCB_TAG_CB 0x43420000u    // counter word 3 (| colour) of the checkerboard draws
+#define QMCB_TAG_CB 0x43420000u    // counter word 3 (| colour) of the checkerboard draws, high 16 bits
+#define QMCB_TAG_CB2 0x43430000u   // ... low 16 bits
 #define OP_EMPTY 0xFFFFFFFFu
 #define NONE32 0xFFFFFFFFu
 

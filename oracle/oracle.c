@@ -903,6 +903,7 @@ uint64_t orc_pt_step(OrcSse **slots, uint32_t nslots, const double *betas, uint6
  * Classical graph: classical/graph.rs:56-119, :339-347, :430-453
  * =================================================================================== */
 #define TAG_CB 0x43420000u
+#define TAG_CB2 0x43430000u
 
 struct OrcCls {
     uint32_t nvars;
@@ -997,23 +998,36 @@ uint64_t orc_cls_threshold(double beta, double delta_e) {
 }
 
 /* Checkerboard schedule (builder-defined; the reference has none).  Per site the rule is
- * graph.rs:98-118 + :339-347 with a fixed-width 32-bit draw: site of rank r inside colour c
- * uses word (r & 3) of Philox(key, ctr = (r >> 2, sweep_lo, sweep_hi, 'CB' << 16 | c)) and
- * flips iff delta_e <= 0 or d * 2^-32 < exp(-beta * delta_e). */
+ * graph.rs:98-118 + :339-347 with a fixed-width 32-bit draw d.  Draws are defined bit-sliced so that
+ * a SIMD implementation can compare 32 sites at once: the sites of colour c are grouped by rank,
+ * 32 consecutive ranks per group; bit-plane k (k = 0 is the most significant bit of d) of group g is
+ * output word (k & 3) of Philox4x32-10(key, ctr = (4 g + ((k & 15) >> 2), sweep_lo, sweep_hi, tag | c)),
+ * tag = 'CB' << 16 for planes 0..15 and 'CC' << 16 for planes 16..31; the draw of rank r is
+ * d = sum_k bit (r & 31) of plane_k << (31 - k).  The site flips iff delta_e <= 0 or
+ * d * 2^-32 < exp(-beta * delta_e).  (The low 16 planes only matter when the high 16 tie.) */
+static void cb_planes(const uint32_t k[2], uint32_t group, uint64_t sweep, uint32_t c, uint32_t planes[32]) {
+    for (uint32_t q = 0; q < 8; q++) {
+        uint32_t ctr[4] = {4 * group + (q & 3u), (uint32_t)sweep, (uint32_t)(sweep >> 32), (q < 4 ? TAG_CB : TAG_CB2) | c};
+        orc_philox4x32_10(ctr, k, planes + 4 * q);
+    }
+}
+static uint32_t cb_draw_from_planes(const uint32_t planes[32], uint32_t j) {
+    uint32_t d = 0;
+    for (uint32_t kk = 0; kk < 32; kk++) d |= ((planes[kk] >> j) & 1u) << (31 - kk);
+    return d;
+}
+
 void orc_cls_checkerboard_sweeps(OrcCls *g, double beta, const uint32_t *colours,
                                  uint32_t ncolours, uint64_t nsweeps) {
     uint32_t k[2] = {(uint32_t)g->rng.key, (uint32_t)(g->rng.key >> 32)};
     for (uint64_t s = 0; s < nsweeps; s++, g->sweep++) {
         for (uint32_t c = 0; c < ncolours; c++) {
             uint32_t rank = 0;
-            uint32_t x[4] = {0, 0, 0, 0};
+            uint32_t planes[32];
             for (uint32_t i = 0; i < g->nvars; i++) {
                 if (colours[i] != c) continue;
-                if ((rank & 3u) == 0) {
-                    uint32_t ctr[4] = {rank >> 2, (uint32_t)g->sweep, (uint32_t)(g->sweep >> 32), TAG_CB | c};
-                    orc_philox4x32_10(ctr, k, x);
-                }
-                uint32_t d = x[rank & 3u];
+                if ((rank & 31u) == 0) cb_planes(k, rank >> 5, g->sweep, c, planes);
+                uint32_t d = cb_draw_from_planes(planes, rank & 31u);
                 rank++;
                 double delta_e = cls_delta_e(g, i);
                 int flip;
