@@ -888,22 +888,35 @@ extern "C" int cmcb_create(const QmcbLattice *lat, const double *biases, uint32_
     if (square) {
         D.L = L;
         TRYC(h->pool.alloc(&D.planes, (size_t)R * 2 * L * (L >> 6)));
-        std::vector<uint32_t> thr((size_t)R * 16, 0u), alw(R, 0u), prob(R, 0u);
-        for (uint32_t r = 0; r < R; r++)
+        std::vector<uint32_t> gT((size_t)R * 10, 0u), gmem((size_t)R * 10, 0u), alw(R, 0u);
+        uint32_t maxg = 0;
+        for (uint32_t r = 0; r < R; r++) {
+            uint32_t ng = 0;
             for (int own = 0; own < 2; own++)
                 for (int cnt = 0; cnt <= 4; cnt++) {
-                    uint64_t T = metropolis_threshold(betas[r], sq_de[own * 8 + cnt]);
-                    if (T >= 4294967296ull) alw[r] |= 1u << (own * 8 + cnt);
-                    else if (T > 0) prob[r] |= 1u << (own * 8 + cnt), thr[(size_t)r * 16 + own * 8 + cnt] = (uint32_t)T;
+                    const uint32_t idx = own * 8 + cnt;
+                    const uint64_t T = metropolis_threshold(betas[r], sq_de[idx]);
+                    if (T >= 4294967296ull) alw[r] |= 1u << idx;
+                    else if (T > 0) {  // classes with the same threshold share a group
+                        uint32_t g = 0;
+                        while (g < ng && gT[(size_t)r * 10 + g] != (uint32_t)T) g++;
+                        if (g == ng) gT[(size_t)r * 10 + ng++] = (uint32_t)T;
+                        gmem[(size_t)r * 10 + g] |= 1u << idx;
+                    }
                 }
-        uint32_t *thr_dev, *alw_dev, *prob_dev;
-        TRYC(h->pool.alloc(&thr_dev, thr.size()));
+            maxg = std::max(maxg, ng);
+        }
+        uint32_t *gT_dev, *gmem_dev, *alw_dev;
+        TRYC(h->pool.alloc(&gT_dev, gT.size()));
+        TRYC(h->pool.alloc(&gmem_dev, gmem.size()));
         TRYC(h->pool.alloc(&alw_dev, alw.size()));
-        TRYC(h->pool.alloc(&prob_dev, prob.size()));
-        TRYC(cudaMemcpy(thr_dev, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(gT_dev, gT.data(), gT.size() * 4, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(gmem_dev, gmem.data(), gmem.size() * 4, cudaMemcpyHostToDevice));
         TRYC(cudaMemcpy(alw_dev, alw.data(), alw.size() * 4, cudaMemcpyHostToDevice));
-        TRYC(cudaMemcpy(prob_dev, prob.data(), prob.size() * 4, cudaMemcpyHostToDevice));
-        D.sq_thr = thr_dev, D.sq_always = alw_dev, D.sq_prob = prob_dev;
+        D.sq_gT = gT_dev, D.sq_gmem = gmem_dev, D.sq_always = alw_dev, D.sq_ngroups = maxg;
+        D.sq_wpr_shift = -1;
+        for (int sh = 0; sh < 20; sh++)
+            if ((L >> 6) == (1u << sh)) D.sq_wpr_shift = sh;
         TRYC(h->pool.alloc(&h->bytes_dev, (size_t)R * N));
     } else {
         // CSR + site classes + per-replica threshold tables

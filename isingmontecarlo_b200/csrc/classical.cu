@@ -63,89 +63,122 @@ __global__ void __launch_bounds__(128) k_cls_generic(ClsDev D, uint32_t colour, 
 // plane[c][y][w] bit j  <->  site (x, y) with x = 2 * (32 w + j) + ((y + c) & 1); colour = (x+y)&1.
 // The 32 sites of a word are exactly one group of 32 consecutive ranks (rank = y * L/2 + 32 w + j).
 // ------------------------------------------------------------------------------------------
-// sites (bits of `sel`) whose draw is below T, looking at planes pl[0..15] = bits hi..hi-15 of the draw;
-// on return `eq` holds the selected sites still tied with T on those bits
-__device__ __forceinline__ uint32_t ripple16(const uint32_t *pl, uint32_t T16, uint32_t sel, uint32_t &eq) {
-    uint32_t lt = 0;
-    eq = sel;
+// Philox4x32-10 with the ten round keys precomputed (block-uniform, in shared memory)
+__device__ __forceinline__ void philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t *rk, uint32_t *out) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const uint32_t tk = (uint32_t)((int32_t)(T16 << (16 + k)) >> 31);  // bit (15 - k) of T16 as a mask
-        lt |= eq & ~pl[k] & tk;
-        eq &= ~(pl[k] ^ tk);
+    for (int i = 0; i < 10; i++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ rk[2 * i], n2 = h0 ^ c3 ^ rk[2 * i + 1];
+        c0 = n0, c1 = l1, c2 = n2, c3 = l0;
     }
-    return lt;
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
 }
 
-__global__ void __launch_bounds__(256) k_cls_square(ClsDev D, uint32_t colour, uint64_t sweep) {
+#define SQ_MAXG 10  // threshold groups (distinct thresholds strictly between 0 and 2^32)
+
+// One thread per 32 sites.  All prob. classes are compared in ONE bit-serial ripple: per plane the
+// threshold bit of every site is muxed from the block-uniform masks of its class group (G logic ops),
+// then lt |= eq & ~p & t;  eq &= ~(p ^ t)  (3 logic ops) decide all 32 sites, ties included.
+template <int G>
+__global__ void __launch_bounds__(256, 4) k_cls_square(ClsDev D, uint32_t colour, uint64_t sweep) {
+    __shared__ uint32_t s_rk[20];
+    __shared__ uint32_t s_tk[G > 0 ? G : 1][32];  // s_tk[g][k]: bit (31 - k) of the threshold of group g as a mask
+    __shared__ uint32_t s_mem[G > 0 ? G : 1];
+    const uint32_t r = blockIdx.y;
+    {
+        const uint64_t key = D.key[r];
+        if (threadIdx.x < 10) {
+            s_rk[2 * threadIdx.x] = (uint32_t)key + 0x9E3779B9u * threadIdx.x;
+            s_rk[2 * threadIdx.x + 1] = (uint32_t)(key >> 32) + 0xBB67AE85u * threadIdx.x;
+        }
+        for (uint32_t i = threadIdx.x; i < (uint32_t)G * 32; i += blockDim.x) {
+            const uint32_t T = D.sq_gT[(size_t)r * SQ_MAXG + (i >> 5)];
+            s_tk[i >> 5][i & 31] = ((T >> (31 - (i & 31))) & 1u) ? 0xFFFFFFFFu : 0u;
+        }
+        if (threadIdx.x < (uint32_t)G) s_mem[threadIdx.x] = D.sq_gmem[(size_t)r * SQ_MAXG + threadIdx.x];
+    }
+    __syncthreads();
     const uint32_t WPR = D.L >> 6;                  // 32-bit words per row of one colour plane
     const uint32_t words_per_plane = D.L * WPR;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t r = blockIdx.y;
-    if (t >= words_per_plane) return;
-    const uint32_t y = t / WPR, w = t - y * WPR;
     uint32_t *mine = D.planes + ((size_t)r * 2 + colour) * words_per_plane;
     const uint32_t *other = D.planes + ((size_t)r * 2 + (colour ^ 1u)) * words_per_plane;
-    const uint32_t yu = y == 0 ? D.L - 1 : y - 1, yd = y + 1 == D.L ? 0 : y + 1;
-    const uint32_t own = mine[t];
-    const uint32_t same = other[y * WPR + w];
-    const uint32_t up = other[yu * WPR + w], dn = other[yd * WPR + w];
-    uint32_t side;
-    if ((y + colour) & 1u) {  // my x is odd: the second horizontal neighbour has compressed index xc + 1
-        uint32_t nxt = other[y * WPR + (w + 1 == WPR ? 0 : w + 1)];
-        side = (same >> 1) | (nxt << 31);
-    } else {  // my x is even: neighbour xc - 1
-        uint32_t prv = other[y * WPR + (w == 0 ? WPR - 1 : w - 1)];
-        side = (same << 1) | (prv >> 31);
-    }
-    // bit-sliced count of anti-aligned neighbours: cnt = lo + 2 mid + 4 hi, then one-hot masks
-    const uint32_t a = own ^ same, b = own ^ side, c = own ^ up, d = own ^ dn;
-    const uint32_t s1 = a ^ b ^ c, c1 = (a & b) | (c & (a ^ b));
-    const uint32_t lo = s1 ^ d, c2 = s1 & d;
-    const uint32_t mid = c1 ^ c2, hi = c1 & c2;
-    uint32_t cm[5];
-    cm[0] = ~(lo | mid | hi), cm[1] = lo & ~mid, cm[2] = mid & ~lo, cm[3] = lo & mid, cm[4] = hi;
-    // the 16 most significant bit-planes of the 32 draws of this word
-    const uint64_t key = D.key[r];
-    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
-    uint32_t pl[16];
-    planes16(t, sweep, QMCB_TAG_CB | colour, k0, k1, pl);
-    // classes: index = own << 3 | cnt;  always-flip classes, and probabilistic ones with threshold T
-    const uint32_t alw = D.sq_always[r], prob = D.sq_prob[r];
-    const uint32_t *T = D.sq_thr + (size_t)r * 16;
-    uint32_t flip = 0, tied = 0;
-#pragma unroll
-    for (int o = 0; o < 2; o++) {
-        const uint32_t om = o ? own : ~own;
-#pragma unroll
-        for (int cc = 0; cc < 5; cc++) {
-            const uint32_t idx = o * 8 + cc;
-            if ((alw >> idx) & 1u) flip |= om & cm[cc];
-            else if ((prob >> idx) & 1u) {  // block-uniform branch
-                uint32_t eq;
-                flip |= ripple16(pl, __ldg(T + idx) >> 16, om & cm[cc], eq);
-                tied |= eq;
-            }
+    const uint32_t always = D.sq_always[r];
+    // a block walks over several chunks of 256 words so that the set-up above is paid once
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < words_per_plane; t += gridDim.x * blockDim.x) {
+        uint32_t y, w;
+        if (D.sq_wpr_shift >= 0) y = t >> D.sq_wpr_shift, w = t & (WPR - 1u);
+        else y = t / WPR, w = t - y * WPR;
+        const uint32_t yu = y == 0 ? D.L - 1 : y - 1, yd = y + 1 == D.L ? 0 : y + 1;
+        const uint32_t own = mine[t];
+        const uint32_t same = other[t];
+        const uint32_t up = other[yu * WPR + w], dn = other[yd * WPR + w];
+        uint32_t side;
+        if ((y + colour) & 1u) {  // my x is odd: the second horizontal neighbour has compressed index xc + 1
+            const uint32_t nxt = other[w + 1 == WPR ? t + 1 - WPR : t + 1];
+            side = (same >> 1) | (nxt << 31);
+        } else {  // my x is even: neighbour xc - 1
+            const uint32_t prv = other[w == 0 ? t + WPR - 1 : t - 1];
+            side = (same << 1) | (prv >> 31);
         }
-    }
-    if (tied) {  // some draw equals its threshold on the high 16 bits (p = 2^-16 per site): low 16 planes
-        uint32_t pl2[16];
-        planes16(t, sweep, QMCB_TAG_CB2 | colour, k0, k1, pl2);
-#pragma unroll
-        for (int o = 0; o < 2; o++) {
-            const uint32_t om = o ? own : ~own;
+        // bit-sliced count of anti-aligned neighbours: cnt = lo + 2 mid + 4 hi, then one-hot masks
+        const uint32_t a = own ^ same, b = own ^ side, c = own ^ up, d = own ^ dn;
+        const uint32_t s1 = a ^ b ^ c, c1 = (a & b) | (c & (a ^ b));
+        const uint32_t lo = s1 ^ d, c2 = s1 & d;
+        const uint32_t mid = c1 ^ c2, hi = c1 & c2;
+        uint32_t cm[5];
+        cm[0] = ~(lo | mid | hi), cm[1] = lo & ~mid, cm[2] = mid & ~lo, cm[3] = lo & mid, cm[4] = hi;
+        // sites of a set of classes (bit idx = own << 3 | cnt of `members`)
+        auto class_sites = [&](uint32_t members) -> uint32_t {
+            uint32_t m0 = 0, m1 = 0;
 #pragma unroll
             for (int cc = 0; cc < 5; cc++) {
-                const uint32_t idx = o * 8 + cc;
-                if ((prob >> idx) & 1u) {
-                    uint32_t eqh, eql;
-                    ripple16(pl, __ldg(T + idx) >> 16, om & cm[cc], eqh);
-                    if (eqh) flip |= ripple16(pl2, __ldg(T + idx) & 0xFFFFu, eqh, eql);
+                m0 |= ((members >> cc) & 1u) ? cm[cc] : 0u;
+                m1 |= ((members >> (8 + cc)) & 1u) ? cm[cc] : 0u;
+            }
+            return (~own & m0) | (own & m1);
+        };
+        uint32_t flip = class_sites(always);  // delta_e <= 0 (threshold 2^32): always
+        if (G > 0) {
+            uint32_t sel[G > 0 ? G : 1], eq = 0;
+#pragma unroll
+            for (int g = 0; g < G; g++) sel[g] = class_sites(s_mem[g]), eq |= sel[g];
+            uint32_t lt = 0;
+            uint32_t pl[4];
+            // planes 0..11 always; 12..15 and 16..31 only while some site still ties with its threshold
+            // (p = 2^-12 resp. 2^-16 per site), so most words need three Philox calls
+#define RIPPLE_PLANE(k)                                              \
+    {                                                                \
+        uint32_t tk = 0;                                             \
+        _Pragma("unroll") for (int g = 0; g < G; g++) tk |= sel[g] & s_tk[g][k]; \
+        const uint32_t p = pl[(k) & 3];                              \
+        lt |= eq & ~p & tk;                                          \
+        eq &= ~(p ^ tk);                                             \
+    }
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                philox_rk(4 * t + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, s_rk, pl);
+#pragma unroll
+                for (int i = 0; i < 4; i++) RIPPLE_PLANE(4 * q + i)
+            }
+            if (eq) {
+                philox_rk(4 * t + 3, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, s_rk, pl);
+#pragma unroll
+                for (int i = 0; i < 4; i++) RIPPLE_PLANE(12 + i)
+                if (eq) {
+#pragma unroll 1
+                    for (int q = 0; q < 4; q++) {
+                        philox_rk(4 * t + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB2 | colour, s_rk, pl);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) RIPPLE_PLANE(16 + 4 * q + i)
+                    }
                 }
             }
+#undef RIPPLE_PLANE
+            flip |= lt;
         }
+        mine[t] = own ^ flip;
     }
-    mine[t] = own ^ flip;
 }
 
 // energy (graph.rs:430-447 restricted to uniform J / bias: integer bond and spin counts) and
@@ -231,8 +264,17 @@ void launch_cls_generic(const ClsDev &D, uint32_t colour, uint32_t cstart, uint3
 }
 void launch_cls_square(const ClsDev &D, uint32_t colour, uint64_t sweep, cudaStream_t st) {
     uint32_t words = D.L * (D.L >> 6);
-    dim3 grid((words + 255) / 256, D.R);
-    k_cls_square<<<grid, 256, 0, st>>>(D, colour, sweep);
+    dim3 grid((words + 1023) / 1024, D.R);  // four chunks of 256 words per block
+    switch (D.sq_ngroups) {
+        case 0: k_cls_square<0><<<grid, 256, 0, st>>>(D, colour, sweep); break;
+        case 1: k_cls_square<1><<<grid, 256, 0, st>>>(D, colour, sweep); break;
+        case 2: k_cls_square<2><<<grid, 256, 0, st>>>(D, colour, sweep); break;
+        case 3: k_cls_square<3><<<grid, 256, 0, st>>>(D, colour, sweep); break;
+        case 4: k_cls_square<4><<<grid, 256, 0, st>>>(D, colour, sweep); break;
+        case 5: k_cls_square<5><<<grid, 256, 0, st>>>(D, colour, sweep); break;
+        case 6: k_cls_square<6><<<grid, 256, 0, st>>>(D, colour, sweep); break;
+        default: k_cls_square<SQ_MAXG><<<grid, 256, 0, st>>>(D, colour, sweep); break;
+    }
 }
 void launch_cls_square_measure(const ClsDev &D, unsigned long long *unsat, unsigned long long *up, cudaStream_t st) {
     uint32_t words = D.L * (D.L >> 6);

@@ -17,7 +17,10 @@ struct ClsDev {
     // square layout (L % 64 == 0, uniform J and bias)
     uint32_t L;
     uint32_t *planes;          // [R][2][L][L/64] bit-packed colour planes
-    const uint32_t *sq_thr;    // [R][16] thresholds, index own << 3 | #anti-aligned neighbours
-    const uint32_t *sq_always; // [R] bit idx set: always flip (threshold 2^32)
-    const uint32_t *sq_prob;   // [R] bit idx set: 0 < threshold < 2^32
+    // classes are indexed own << 3 | #anti-aligned neighbours; classes with equal thresholds form a group
+    const uint32_t *sq_always; // [R] class bits: always flip (threshold 2^32)
+    const uint32_t *sq_gT;     // [R][10] threshold of each probabilistic group (0 < T < 2^32)
+    const uint32_t *sq_gmem;   // [R][10] class bits of each group (0 = unused)
+    uint32_t sq_ngroups;       // max number of groups over the replicas
+    int sq_wpr_shift;          // log2(L / 64) if that is a power of two, else -1
 };
