@@ -212,7 +212,9 @@ def bench_sse(args, world, rank, local):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:
-            roofline["traffic"] = json.load(f).get("k_sse_fast")
+            tr = json.load(f).get("k_sse_fast")
+            roofline["traffic"] = tr["bytes_per_launch"] if tr else None
+            roofline["traffic_note"] = "ncu dram__bytes_read+write per launch (profiles/%s)" % tr["source"] if tr else None
 
     out = {"value": value, "ms_per_step": t_max / args.steps, "therm_s": therm_s, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
            "clocks": clocks, "n_mean": n_mean, "cutoff_mean": m_mean, "handle": g, "config": c}
@@ -321,7 +323,9 @@ def bench_classical(args, world, rank, local):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:
-            roofline["traffic"] = json.load(f).get("k_cls_square")
+            tr = json.load(f).get("k_cls_square")
+            roofline["traffic"] = tr["bytes_per_launch"] if tr else None
+            roofline["traffic_note"] = "ncu dram__bytes_read+write per launch (profiles/%s)" % tr["source"] if tr else None
     out = {"metric": "classical_spin_flips_per_sec", "value": value, "unit": "spin_flip_attempts/s", "ms_per_step": ms / args.steps,
            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
            "e2e": {"value": flips / e2e_s, "unit": "spin_flip_attempts/s", "h2d_bytes_per_step": 0,
