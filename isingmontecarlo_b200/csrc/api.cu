@@ -92,6 +92,8 @@ struct QmcbHandle {
     bool pt_on = false;
     PtDev P{};
     uint32_t pt_S = 0;
+    uint8_t *samples_dev = nullptr;  // reused between qmcb_timesteps calls
+    size_t samples_cap = 0;
 };
 
 #define CHECK_H(h)                                              \
@@ -405,8 +407,15 @@ extern "C" int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t freq, double *
     uint8_t *samples_dev = nullptr;
     int rc = QMCB_OK;
     if (samples_out && spr) {
-        cudaError_t e = cudaMalloc(&samples_dev, (size_t)D.R * spr * D.N);
-        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(samples)", __FILE__, __LINE__);
+        const size_t need = (size_t)D.R * spr * D.N;
+        if (need > h->samples_cap) {
+            if (h->samples_dev) h->pool.release(h->samples_dev);
+            h->samples_dev = nullptr, h->samples_cap = 0;
+            cudaError_t e = h->pool.alloc(&h->samples_dev, need);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(samples)", __FILE__, __LINE__);
+            h->samples_cap = need;
+        }
+        samples_dev = h->samples_dev;
     }
     CUDA_TRY(cudaMemsetAsync(D.sum_n, 0, sizeof(uint64_t) * D.R, h->stream));
     const uint64_t origin = h->target;
@@ -430,7 +439,6 @@ extern "C" int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t freq, double *
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail_cuda(e, "copy samples", __FILE__, __LINE__);
     }
-    if (samples_dev) cudaFree(samples_dev);
     return rc;
 }
 

@@ -71,10 +71,11 @@ struct WarpSmem {
     uint32_t *sv;   // [32] variable cut by the site op of lane j (or NONE32)
     uint32_t *opw;  // [64] op word an empty slot would insert from window word y
     unsigned char *G;  // [64] cursor after an empty slot that starts reading at window position x
+    unsigned char *wk, *wx, *wg, *wl;  // [32] walk: gap before, start cursor, cursor after, lane of the k-th EMPTY lane
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
-    return ((((size_t)3 * Nw + N + 64 + 64 + 16) * 4 + 64 * 8) + 15) / 16 * 16;
+    return ((((size_t)3 * Nw + N + 64 + 64 + 16 + 32) * 4 + 64 * 8) + 15) / 16 * 16;
 }
 
 template <bool HAS_H, int MINB>
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
         unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(N, Nw);
         S.win = (unsigned long long *)base;
         uint32_t *u = (uint32_t *)(base + 64 * 8);
-        S.st = u, S.tb = u + Nw, S.cd = u + 2 * Nw, S.rep = u + 3 * Nw, S.fl = u + 3 * Nw + N, S.sv = S.fl + 32, S.opw = S.sv + 32, S.G = (unsigned char *)(S.opw + 64);
+        S.st = u, S.tb = u + Nw, S.cd = u + 2 * Nw, S.rep = u + 3 * Nw, S.fl = u + 3 * Nw + N, S.sv = S.fl + 32, S.opw = S.sv + 32, S.G = (unsigned char *)(S.opw + 64), S.wk = S.G + 64, S.wx = S.wk + 32, S.wg = S.wx + 32, S.wl = S.wg + 32;
     }
     uint32_t *ops = D.ops + (size_t)r * D.cap;
     uint32_t *gstate = D.state + (size_t)r * Nw;
@@ -128,10 +129,12 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
         bool anylong = false;
 
         // =========================== P1: diagonal update + unions ===========================
+        uint32_t wnext = lane < M ? ld_cg(ops + lane) : OP_EMPTY;  // software prefetch of the next 128-byte line
         for (uint32_t base = 0; base < M; base += 32) {
             const uint32_t p = base + lane;
             const bool valid = p < M;
-            uint32_t w = valid ? ops[p] : OP_EMPTY;
+            uint32_t w = wnext;
+            wnext = p + 32 < M ? ld_cg(ops + p + 32) : OP_EMPTY;
             DBG(0, 1);
             int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
             uint32_t neww = w;
@@ -249,30 +252,31 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                         const int le = predE ? 31 - __clz(predE) : -1;  // last EMPTY lane before me
                         const uint32_t after_le = le < 0 ? FULL : ~((2u << le) - 1u);
                         const uint32_t dcount = (uint32_t)__popc(drawD & lt_mask & after_le);  // draws between it and me
-                        uint32_t x = (uint32_t)(cur - wbase), myx = 0, stop = 32u;
-                        uint32_t basex = x;  // cursor right after my last EMPTY predecessor
+                        const uint32_t kidx = (uint32_t)__popc(predE);  // my index among the EMPTY lanes
+                        if (inrem && type == T_EMPTY) S.wk[kidx] = (unsigned char)dcount, S.wl[kidx] = (unsigned char)lane;
+                        __syncwarp();
+                        const uint32_t x0 = (uint32_t)(cur - wbase);
+                        uint32_t x = x0, myx = 0, stop = 32u;
                         bool hz_fail = false, overridden = false;
-                        uint32_t mmE = stopA < 32u ? (remE & ((1u << stopA) - 1u)) : remE;
+                        const uint32_t nE = (uint32_t)__popc(stopA < 32u ? (remE & ((1u << stopA) - 1u)) : remE);
+                        uint32_t k = 0;
                         for (;;) {
-                            uint32_t hz_i = 32u, hz_x = 0;
-                            while (mmE) {  // tight loop; the rare hazard is handled outside
-                                const uint32_t i = (uint32_t)__ffs(mmE) - 1u;
-                                const uint32_t xs = x + __shfl_sync(FULL, dcount, i);
+                            uint32_t hz_x = 0xFFFFFFFFu;
+                            for (; k < nE; k++) {  // tight loop; the rare hazard is handled outside
+                                const uint32_t xs = x + S.wk[k];
                                 const uint32_t g = xs < 64u ? (uint32_t)S.G[xs] : 255u;
                                 if (g >= 254u) {
-                                    if (g == 255u) stop = i, mmE = 0;
-                                    else hz_i = i, hz_x = xs;
+                                    if (g == 255u) stop = S.wl[k];
+                                    else hz_x = xs;
                                     break;
                                 }
-                                mmE &= mmE - 1;
-                                if ((uint32_t)lane == i) myx = xs;
-                                if (le == (int)i) basex = g;
+                                S.wx[k] = (unsigned char)xs, S.wg[k] = (unsigned char)g;
                                 x = g;
                             }
-                            if (hz_i >= 32u) break;
-                            // hazard: the word's spins are flipped inside this step -> evaluate for lane hz_i
+                            if (hz_x == 0xFFFFFFFFu) break;
+                            // hazard: the word's spins are flipped inside this step -> evaluate for that lane
                             DBG(12, 1);
-                            const uint32_t i = hz_i, xs = hz_x;
+                            const uint32_t i = S.wl[k], xs = hz_x;
                             const uint32_t y = xs + (uint32_t)__ffsll((long long)(ACC >> xs)) - 1u;
                             const uint32_t b = op_bond(S.opw[y]);
                             const int kind = bond_kind(D, b);
@@ -296,14 +300,20 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                             } else fail = true;
                             if (fail) { stop = i, hz_fail = true; break; }
                             const uint32_t g = y + 1u + (ex ? 1u : 0u);
-                            if ((uint32_t)lane == i) overridden = true, neww = ok ? make_op(b, bitsv, bitsv) : OP_EMPTY, dn = ok, dc = g - xs, myx = xs;
-                            if (le == (int)i) basex = g;
+                            if ((uint32_t)lane == i) overridden = true, neww = ok ? make_op(b, bitsv, bitsv) : OP_EMPTY, dn = ok, dc = g - xs;
+                            S.wx[k] = (unsigned char)xs, S.wg[k] = (unsigned char)g;
                             x = g;
-                            mmE &= mmE - 1;
+                            k++;
                         }
+                        __syncwarp();
+                        // every lane picks up its own cursor: EMPTY lanes their start, the others the cursor
+                        // after their last EMPTY predecessor plus the diagonal draws in between
+                        const uint32_t kstop = k;  // EMPTY lanes with index >= kstop are unresolved
+                        if (type == T_EMPTY) myx = kidx < kstop ? (uint32_t)S.wx[kidx] : 0u;
+                        else myx = (kidx == 0 ? x0 : (kidx <= kstop ? (uint32_t)S.wg[kidx - 1] : 0u)) + dcount;
+                        if (stop >= 32u && kstop < nE) stop = S.wl[kstop];
                         if (stop >= 32u && stopA < 32u) stop = stopA;
                         bool need_exact = hz_fail || (stopA < 32u && stop == stopA);
-                        if (type != T_EMPTY) myx = basex + dcount;
                         // a drawing diagonal op beyond the window ends the resolved prefix as well
                         const uint32_t ovD = __ballot_sync(FULL, inrem && type == T_DIAG && draws && myx >= 64u && (uint32_t)lane < stop);
                         if (ovD) stop = (uint32_t)__ffs(ovD) - 1u, need_exact = false;
@@ -442,7 +452,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                     __syncwarp();
                 }
                 if (__any_sync(FULL, neww != w)) {
-                    if (valid && neww != w) ops[p] = neww;
+                    if (valid && neww != w) st_cg(ops + p, neww);
                 }
                 if (type == T_OFFD) atomicXor(&S.st[ov0 >> 5], 1u << (ov0 & 31)), atomicAnd(&S.cd[ov0 >> 5], ~(1u << (ov0 & 31)));
                 __syncwarp();
@@ -577,9 +587,11 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
             for (uint32_t j = lane; j < Nw; j += 32) S.cd[j] = ld_cg(decb + j);
             __syncwarp();
             uint32_t ks = 0;
+            uint32_t w3next = lane < M ? ld_cg(ops + lane) : OP_EMPTY;
             for (uint32_t base = 0; base < M; base += 32) {
                 const uint32_t p = base + lane;
-                const uint32_t w = p < M ? ops[p] : OP_EMPTY;
+                const uint32_t w = w3next;
+                w3next = p + 32 < M ? ld_cg(ops + p + 32) : OP_EMPTY;
                 int kind = -1;
                 uint32_t v0 = 0, v1 = 0;
                 if (w != OP_EMPTY) {
@@ -600,7 +612,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                 if (kind >= 0) {
                     const uint32_t mask = kind == KIND_BOND ? 3u : 1u;
                     const bool dout = kind == KIND_SITE ? outdec : din;
-                    if (din || dout) ops[p] = make_op(op_bond(w), op_in(w) ^ (din ? mask : 0u), op_out(w) ^ (dout ? mask : 0u));
+                    if (din || dout) st_cg(ops + p, make_op(op_bond(w), op_in(w) ^ (din ? mask : 0u), op_out(w) ^ (dout ? mask : 0u)));
                 }
                 __syncwarp();
                 if (kind == KIND_SITE && lastone) {  // the last site op of the step on a variable sets its open decision

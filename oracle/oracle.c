@@ -56,6 +56,9 @@ typedef struct {
     const uint64_t *script; /* scripted words for known-answer tests (or NULL) */
     uint64_t script_len;
     int error;
+    /* last Philox block (two stream words), so that a block is computed once, not twice */
+    uint64_t blk_key, blk_idx, blk_w[2];
+    int blk_valid;
 } Stream;
 
 static uint64_t next_u64(Stream *s) {
@@ -67,7 +70,18 @@ static uint64_t next_u64(Stream *s) {
         }
         return s->script[s->cursor++];
     }
-    return orc_stream_word(s->key, s->cursor++);
+    {
+        const uint64_t c = s->cursor++, blk = c >> 1;
+        if (!s->blk_valid || s->blk_idx != blk || s->blk_key != s->key) {
+            uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u};
+            uint32_t k[2] = {(uint32_t)s->key, (uint32_t)(s->key >> 32)};
+            uint32_t x[4];
+            orc_philox4x32_10(ctr, k, x);
+            s->blk_w[0] = ((uint64_t)x[1] << 32) | x[0], s->blk_w[1] = ((uint64_t)x[3] << 32) | x[2];
+            s->blk_idx = blk, s->blk_key = s->key, s->blk_valid = 1;
+        }
+        return s->blk_w[c & 1u];
+    }
 }
 /* one stream word per call; a u32 is the word's high half (Appendix A.3) */
 static uint32_t next_u32(Stream *s) { return (uint32_t)(next_u64(s) >> 32); }
@@ -132,37 +146,37 @@ static double gen_f64(Stream *s) {
 static int gen_std_bool(Stream *s) { return (int32_t)next_u32(s) < 0; }
 
 int orc_gen_bool(uint64_t key, uint64_t *cursor, double p) {
-    Stream s = {key, *cursor, NULL, 0, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
     int r = gen_bool(&s, p);
     *cursor = s.cursor;
     return r;
 }
 uint64_t orc_gen_range_usize(uint64_t key, uint64_t *cursor, uint64_t n) {
-    Stream s = {key, *cursor, NULL, 0, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
     uint64_t r = gen_range_usize(&s, n);
     *cursor = s.cursor;
     return r;
 }
 uint32_t orc_gen_range_u8(uint64_t key, uint64_t *cursor, uint32_t n) {
-    Stream s = {key, *cursor, NULL, 0, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
     uint32_t r = gen_range_u8(&s, n);
     *cursor = s.cursor;
     return r;
 }
 double orc_gen_range_f64_01(uint64_t key, uint64_t *cursor) {
-    Stream s = {key, *cursor, NULL, 0, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
     double r = gen_range_f64_01(&s);
     *cursor = s.cursor;
     return r;
 }
 double orc_gen_f64(uint64_t key, uint64_t *cursor) {
-    Stream s = {key, *cursor, NULL, 0, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
     double r = gen_f64(&s);
     *cursor = s.cursor;
     return r;
 }
 int orc_gen_std_bool(uint64_t key, uint64_t *cursor) {
-    Stream s = {key, *cursor, NULL, 0, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
     int r = gen_std_bool(&s);
     *cursor = s.cursor;
     return r;
@@ -883,7 +897,7 @@ uint64_t orc_pt_step(OrcSse **slots, uint32_t nslots, const double *betas, uint6
     for (uint32_t i = 0; i < nslots; i++)
         if (slots[i]->cutoff > max_cutoff) max_cutoff = slots[i]->cutoff;
     for (uint32_t i = 0; i < nslots; i++) orc_sse_set_cutoff(slots[i], max_cutoff);
-    Stream rng = {pt_key, *pt_cursor, NULL, 0, 0};
+    Stream rng = {pt_key, *pt_cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
     /* make_first_subgraphs / make_second_subgraphs :83-99 */
     uint32_t a_len = (nslots % 2 == 0) ? nslots : nslots - 1;
     uint32_t b_len = (nslots % 2 == 1) ? nslots - 1 : nslots - 2;

@@ -127,3 +127,21 @@ def test_tempering_matches_reference_swaps(n_chains, n_betas, mode):
             assert np.array_equal(g.dump_ops(s_local), ref.dump_ops())
         assert tc.get_total_swaps() == swaps_ref
     assert (swaps_ref > 0 or n_betas <= 2) and tc.verify()
+
+
+def test_tempering_over_nccl_two_ranks():
+    # multi-GPU path for real: one process per GPU, all-gather of the slot records over NCCL
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", os.path.join(root, "tests", "pt_worker.py"), root],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert res.stdout.count(" ok ") == 2
