@@ -174,6 +174,23 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
     int rc;
     if (h->mode == QMCB_MODE_STRICT) {
         if ((rc = alloc_strict_ws(h))) return rc;
+        const bool full = (phases & 0xFu) == 0xFu;
+        if (full && h->impl != 1 && h->target > origin) {
+            // the diagonal update is order-exact in the warp-parallel kernel, so STRICT sweeps use it too:
+            // per sweep one launch for the diagonal update, one for links + reference-order clusters
+            if ((rc = alloc_fast_ws(h))) return rc;
+            bool ok = true;
+            for (uint64_t tgt = origin + 1; tgt <= h->target && ok; tgt++) {
+                int nl = launch_sse_fast(h->D, tgt, 1u | 16u, freq, origin, nullptr, 0, h->stream);
+                if (nl < 0) { ok = false; break; }
+                launch_sse_serial(h->D, 0, tgt, 2u | 4u | 8u | 16u, freq, origin, samples_dev, spr, h->stream);
+                h->launches += (uint64_t)nl + 1;
+            }
+            if (ok) {
+                CUDA_TRY(cudaGetLastError());
+                return QMCB_OK;
+            }
+        }
         launch_sse_serial(h->D, 0, h->target, phases, freq, origin, samples_dev, spr, h->stream);
         h->launches += 1;
     } else {

@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
     const uint64_t range = D.Nb;
     const uint64_t zone = (range << __clzll((long long)range)) - 1ull;
     uint64_t done = D.done[r];
-    const uint64_t nsteps = (phases & 8u) ? (target > done ? target - done : 0) : 1;
+    // bit 4 (16): run exactly the step that takes this replica from target - 1 to target (split launches)
+    const uint64_t nsteps = (phases & 16u) ? (done + 1 == target ? 1 : 0) : ((phases & 8u) ? (target > done ? target - done : 0) : 1);
     int err = 0;
 
     for (uint64_t sw = 0; sw < nsteps; sw++) {

@@ -423,7 +423,8 @@ __device__ void free_spins(const SseDev &D, uint32_t r, const Rep &V, int lane) 
 }
 
 // phases: bit0 diagonal update, bit1 cluster update + free spins, bit2 cutoff growth,
-// bit3 bookkeeping of a full timestep (done counter, estimators, sampling)
+// bit3 bookkeeping of a full timestep (done counter, estimators, sampling),
+// bit4 run only the single step that takes the replica from target - 1 to target
 __global__ void __launch_bounds__(128) k_sse_serial(SseDev D, int mode, uint64_t target, uint32_t phases,
                                                     uint64_t sample_freq, uint64_t sample_origin,
                                                     uint8_t *samples, uint64_t samples_per_rep) {
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(128) k_sse_serial(SseDev D, int mode, uint64_t
     if (r >= D.R) return;
     const Rep V = rep_view(D, r);
     uint64_t done = D.done[r];
-    const uint64_t nsteps = (phases & 8u) ? (target > done ? target - done : 0) : 1;
+    const uint64_t nsteps = (phases & 16u) ? (done + 1 == target ? 1 : 0) : ((phases & 8u) ? (target > done ? target - done : 0) : 1);
     for (uint64_t s = 0; s < nsteps; s++) {
         if (D.M[r] > D.cap) {  // cannot run this sweep: host must grow the arrays first
             if (lane == 0) atomicOr(D.status, DEV_ERR_CAPACITY);

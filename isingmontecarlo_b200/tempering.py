@@ -89,6 +89,8 @@ class TemperingContainer:
         check(L.qmcb_synchronize(g._h))
         allrec = gather_records(self._rec, self.group)
         self._allrec = allrec  # keep alive until the kernel ran
+        # the collective is ordered on torch's current stream, the swap kernel runs on the handle's stream
+        self._torch.cuda.current_stream().synchronize()
         check(L.qmcb_pt_apply(g._h, C.c_void_p(allrec.data_ptr()), allrec.shape[0]))
         check(L.qmcb_synchronize(g._h))
 
