@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256, 4) k_cls_square(ClsDev D, uint32_t colour
         }
         for (uint32_t i = threadIdx.x; i < (uint32_t)G * 32; i += blockDim.x) {
             const uint32_t T = D.sq_gT[(size_t)r * SQ_MAXG + (i >> 5)];
-            s_tk[i >> 5][i & 31] = ((T >> (31 - (i & 31))) & 1u) ? 0xFFFFFFFFu : 0u;
+            s_tk[i >> 5][i & 31] = (T >> (31 - (i & 31))) & 1u;  // 0/1: used as a multiplier (FMA pipe), not a mask
         }
         if (threadIdx.x < (uint32_t)G) s_mem[threadIdx.x] = D.sq_gmem[(size_t)r * SQ_MAXG + threadIdx.x];
     }
@@ -128,13 +128,15 @@ __global__ void __launch_bounds__(256, 4) k_cls_square(ClsDev D, uint32_t colour
         const uint32_t mid = c1 ^ c2, hi = c1 & c2;
         uint32_t cm[5];
         cm[0] = ~(lo | mid | hi), cm[1] = lo & ~mid, cm[2] = mid & ~lo, cm[3] = lo & mid, cm[4] = hi;
-        // sites of a set of classes (bit idx = own << 3 | cnt of `members`)
+        // sites of a set of classes (bit idx = own << 3 | cnt of `members`).  The one-hot masks cm[] are
+        // disjoint, so OR == ADD and "mask if member" == mask * bit: integer multiply-adds run on the FMA
+        // pipe and leave the (binding) ALU pipe to the logic ops
         auto class_sites = [&](uint32_t members) -> uint32_t {
             uint32_t m0 = 0, m1 = 0;
 #pragma unroll
             for (int cc = 0; cc < 5; cc++) {
-                m0 |= ((members >> cc) & 1u) ? cm[cc] : 0u;
-                m1 |= ((members >> (8 + cc)) & 1u) ? cm[cc] : 0u;
+                m0 = cm[cc] * ((members >> cc) & 1u) + m0;
+                m1 = cm[cc] * ((members >> (8 + cc)) & 1u) + m1;
             }
             return (~own & m0) | (own & m1);
         };
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(256, 4) k_cls_square(ClsDev D, uint32_t colour
 #define RIPPLE_PLANE(k)                                              \
     {                                                                \
         uint32_t tk = 0;                                             \
-        _Pragma("unroll") for (int g = 0; g < G; g++) tk |= sel[g] & s_tk[g][k]; \
+        _Pragma("unroll") for (int g = 0; g < G; g++) tk = sel[g] * s_tk[g][k] + tk; /* disjoint sel: mux by multiply-add */ \
         const uint32_t p = pl[(k) & 3];                              \
         lt |= eq & ~p & tk;                                          \
         eq &= ~(p ^ tk);                                             \
