@@ -368,6 +368,50 @@ def cpu_baseline_classical(c, seconds_budget=8.0, L=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# tempering arm (BASELINE config #4): SSE L=64, n_betas x n_chains slots sharded over the ranks,
+# one all-gather of 32 B per slot per tempering step (NCCL)
+# ---------------------------------------------------------------------------------------------
+def bench_pt(args, world, rank, local):
+    import torch
+
+    from isingmontecarlo_b200 import MODE_FAST, lattices
+    from isingmontecarlo_b200.tempering import TemperingContainer
+
+    L, n_betas = args.pt_l, args.pt_betas
+    slots_per_gpu = args.pt_slots_per_gpu
+    n_chains = max(1, slots_per_gpu * world // n_betas)
+    betas = np.geomspace(0.25, 16.0, n_betas)
+    edges = lattices.square_periodic(L, -1.0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    tc = TemperingContainer(edges, 3.04, 0.0, L * L, betas, n_chains=n_chains, pt_key=0x9E37, mode=MODE_FAST, device=local)
+    tc.graph.set_stream(stream.cuda_stream)
+    for _ in range(args.pt_therm):
+        tc.timesteps(1)
+        tc.tempering_step()
+    g = tc.graph
+    vu0, l0 = g.total_vertex_updates(), g.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(world)
+    e0.record()
+    for _ in range(args.steps):
+        g.enqueue_sweeps(1)
+        tc.tempering_step()
+    e1.record()
+    barrier_sync(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    vu = sum_over_ranks(float(g.total_vertex_updates() - vu0), world)
+    out = {"metric": "sse_vertex_updates_per_sec", "value": vu / (ms * 1e-3), "unit": "vertex_updates/s", "ms_per_step": ms / args.steps,
+           "gpu_launches": int(g.launch_count() - l0), "total_swaps": int(tc.get_total_swaps()),
+           "collective": f"all_gather of {32 * tc.S} B per tempering step (torch.distributed, {'nccl' if world > 1 else 'single rank'})",
+           "config": {"workload": f"SSE TFIM L={L} parallel tempering, {n_betas} betas (geometric 0.25..16) x {n_chains} chains, "
+                                  f"{tc.R} slots/GPU, swap every sweep (BASELINE config #4 shape)", "mean_n": float(g.get_n().mean()),
+                      "max_cutoff": int(g.get_cutoff().max())}}
+    g.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # reference arm: the oracle port on the host cores, no GPU engine anywhere on the path
 # ---------------------------------------------------------------------------------------------
 def bench_reference(args):
@@ -412,7 +456,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="both", choices=["both", "sse", "classical"])
+    ap.add_argument("--workload", default="both", choices=["both", "sse", "classical", "pt"])
+    ap.add_argument("--pt-l", type=int, default=64)
+    ap.add_argument("--pt-betas", type=int, default=512)
+    ap.add_argument("--pt-slots-per-gpu", type=int, default=1024)
+    ap.add_argument("--pt-therm", type=int, default=30)
     ap.add_argument("--therm", type=int, default=120, help="untimed SSE thermalisation sweeps (GPU arm)")
     ap.add_argument("--ref-therm", type=int, default=80, help="untimed thermalisation sweeps of the CPU arm")
     ap.add_argument("--strict-sweeps", type=int, default=2)
@@ -445,6 +493,8 @@ def main():
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sse(g, c)
         g.close()
+    if args.workload == "pt":
+        line.update(bench_pt(args, world, rank, local))
     if args.workload in ("both", "classical"):
         cl = bench_classical(args, world, rank, local)
         if args.workload == "classical":

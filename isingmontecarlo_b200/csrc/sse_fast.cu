@@ -15,6 +15,8 @@
 //  P2  resolve one flip bit per segment in increasing id order (parent id < child id).
 //  P3  apply the flips to the operator words (second streaming pass) and to the spins.
 // Contract of the FAST order: oracle.c cluster_update_fast / DESIGN.md.
+#include <algorithm>
+
 #include "sse.cuh"
 
 #define FULL 0xFFFFFFFFu
@@ -675,9 +677,17 @@ int g_sse_fast_minblocks = 7;  // resident blocks per SM the kernel is compiled 
 int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
     const size_t per_warp = warp_smem_bytes(D.N, D.Nw);
-    int warps = 4;
-    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-    if (per_warp * warps > 200 * 1024) return -1;
+    // warps per block: the choice that keeps most warps resident per SM (227 KB of shared memory, 1 KB
+    // reserved per block); large lattices need one warp per block
+    int warps = 0;
+    size_t best = 0;
+    for (int wpb = 4; wpb >= 1; wpb >>= 1) {
+        const size_t blk = per_warp * wpb + 1024;
+        if (blk > 227 * 1024) continue;
+        size_t resident = std::min<size_t>((227 * 1024) / blk, 32) * wpb;
+        if (resident > best) best = resident, warps = wpb;
+    }
+    if (!warps) return -1;
     const size_t smem = per_warp * warps;
     const uint32_t blocks = (D.R + warps - 1) / warps;
     typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t);
