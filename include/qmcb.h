@@ -77,7 +77,7 @@ int qmcb_get_mode(const QmcbHandle *h, int *mode);
 /* tuning knobs; "impl": 0 = warp-parallel kernels where available (default), 1 = serial-order kernels only */
 int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value);
 /* event counters of the SSE kernels (after qmcb_set_option(h, "debug_counters", 1)); diagnostics only */
-int qmcb_get_debug_counters(QmcbHandle *h, uint64_t *out16);
+int qmcb_get_debug_counters(QmcbHandle *h, uint64_t *out64 /* [64] */);
 int qmcb_set_betas(QmcbHandle *h, const double *betas);
 int qmcb_get_betas(const QmcbHandle *h, double *betas);
 int qmcb_num_replicas(const QmcbHandle *h, uint32_t *r);

@@ -368,8 +368,8 @@ extern "C" int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value) {
     }
     if (!strcmp(name, "debug_counters")) {
         if (value && !h->D.dbg) {
-            if (h->pool.alloc(&h->D.dbg, 16) != cudaSuccess) return fail(QMCB_ERR_CUDA, "alloc debug counters");
-            cudaMemset(h->D.dbg, 0, 16 * sizeof(unsigned long long));
+            if (h->pool.alloc(&h->D.dbg, 64) != cudaSuccess) return fail(QMCB_ERR_CUDA, "alloc debug counters");
+            cudaMemset(h->D.dbg, 0, 64 * sizeof(unsigned long long));
         }
         return QMCB_OK;
     }
@@ -383,7 +383,7 @@ extern "C" int qmcb_get_debug_counters(QmcbHandle *h, uint64_t *out16) {
     CHECK_H(h);
     if (!out16 || !h->D.dbg) return fail(QMCB_ERR_BAD_ARG, "debug counters are off");
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    CUDA_TRY(cudaMemcpy(out16, h->D.dbg, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out16, h->D.dbg, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return QMCB_OK;
 }
 extern "C" int qmcb_set_betas(QmcbHandle *h, const double *betas) {

@@ -25,6 +25,13 @@
 #define T_DIAG 2
 #define T_OFFD 3
 #define DBG(i, v) do { if (D.dbg && lane == 0) atomicAdd(D.dbg + (i), (unsigned long long)(v)); } while (0)
+// phase timers, compiled in with -DQMCB_PHASE_TIMERS (tools/prof_sse.py prints them): TICK(k) adds the cycles
+// since the previous TICK to dbg[32 + k]
+#ifdef QMCB_PHASE_TIMERS
+#define TICK(k) do { if (D.dbg) { const long long t_ = clock64(); if (lane == 0) atomicAdd(D.dbg + 32 + (k), (unsigned long long)(t_ - tick_)); tick_ = t_; } } while (0)
+#else
+#define TICK(k) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ void st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
@@ -106,6 +113,9 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     const uint64_t range = D.Nb;
     const uint64_t zone = (range << __clzll((long long)range)) - 1ull;
+#ifdef QMCB_PHASE_TIMERS
+    long long tick_ = clock64();
+#endif
     uint64_t done = D.done[r];
     // bit 4 (16): run exactly the step that takes this replica from target - 1 to target (split launches)
     const uint64_t nsteps = (phases & 16u) ? (done + 1 == target ? 1 : 0) : ((phases & 8u) ? (target > done ? target - done : 0) : 1);
@@ -139,6 +149,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
             uint32_t w = wnext;
             wnext = p + 32 < M ? ld_cg(ops + p + 32) : OP_EMPTY;
             DBG(0, 1);
+            TICK(0);  // between steps
             int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
             uint32_t neww = w;
             // variables / stored bits of an existing op
@@ -158,6 +169,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                 if (type == T_DIAG) dnum = bn * bond_weight(D, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
                 uint32_t rem = emask | dmask;
                 bool try_fast = true;
+                TICK(1);  // load, classify, decode of existing ops, flip list
                 while (rem) {
                     const uint64_t wbase = cur & ~1ull;
                     {  // stream words [wbase, wbase + 64)
@@ -167,6 +179,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                         S.win[2 * lane + 1] = ((unsigned long long)o.w << 32) | o.z;
                     }
                     __syncwarp();
+                    TICK(2);  // Philox window
                     const bool inrem = (rem >> lane) & 1u;
                     uint32_t dc = 0, okm;
                     int dn = 0;
@@ -234,6 +247,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                             accb[hh] = __ballot_sync(FULL, acc), exb[hh] = __ballot_sync(FULL, ex);
                             okb[hh] = __ballot_sync(FULL, ok), hzb[hh] = __ballot_sync(FULL, hz);
                         }
+                        TICK(3);  // diagonal-lane thresholds + decode of the window
                         const uint64_t ACC = ((uint64_t)accb[1] << 32) | accb[0], EX = ((uint64_t)exb[1] << 32) | exb[0];
                         const uint64_t OKI = ((uint64_t)okb[1] << 32) | okb[0], HZ = ((uint64_t)hzb[1] << 32) | hzb[0];
 #pragma unroll
@@ -311,6 +325,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                         __syncwarp();
                         // every lane picks up its own cursor: EMPTY lanes their start, the others the cursor
                         // after their last EMPTY predecessor plus the diagonal draws in between
+                        TICK(4);  // successor table + walk
                         const uint32_t kstop = k;  // EMPTY lanes with index >= kstop are unresolved
                         if (type == T_EMPTY) myx = kidx < kstop ? (uint32_t)S.wx[kidx] : 0u;
                         else myx = (kidx == 0 ? x0 : (kidx <= kstop ? (uint32_t)S.wg[kidx - 1] : 0u)) + dcount;
@@ -454,12 +469,14 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                     rem &= ~okm;
                     __syncwarp();
                 }
+                TICK(5);  // decisions + commit
                 if (__any_sync(FULL, neww != w)) {
                     if (valid && neww != w) st_cg(ops + p, neww);
                 }
                 if (type == T_OFFD) atomicXor(&S.st[ov0 >> 5], 1u << (ov0 & 31)), atomicAnd(&S.cd[ov0 >> 5], ~(1u << (ov0 & 31)));
                 __syncwarp();
             }
+            TICK(6);  // store + state flips
             if (do_clus) {
                 // ---- segments and unions on the final ops of this step
                 const uint32_t fw = neww;
@@ -509,6 +526,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                 if (kind == KIND_SITE) atomicMax(&S.rep[v0], myid);
                 nsite += (uint32_t)__popc(smask);
                 __syncwarp();
+                TICK(7);  // segment ids + union-find
             }
         }
         if (do_diag && lane == 0) D.n[r] = n;
@@ -522,6 +540,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
             }
             __syncwarp();
             __threadfence_block();
+            TICK(8);  // closure
             const uint64_t c0 = cur;
             const uint32_t nseg = N + nsite;
             const uint32_t nwords = (nseg + 31) / 32;
@@ -586,6 +605,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
             untouched = __reduce_add_sync(FULL, untouched);
             ncl = nsite == 0 ? 1u : nroots - untouched;
 
+            TICK(9);  // P2
             // =========================== P3: apply the flips ===========================
             for (uint32_t j = lane; j < Nw; j += 32) S.cd[j] = ld_cg(decb + j);
             __syncwarp();
@@ -625,6 +645,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                 ks += (uint32_t)__popc(smask);
                 __syncwarp();
             }
+            TICK(10);  // P3
             // spins: the segment of variable v crossing p = 0 has id v
             for (uint32_t j = lane; j < Nw; j += 32) S.st[j] ^= ld_cg(decb + j) & S.tb[j];
             cur = c0 + 1;

@@ -71,7 +71,7 @@ class QmcIsingGraph:
         check(self._L.qmcb_set_option(self._h, name.encode(), int(value)))
 
     def debug_counters(self):
-        out = np.zeros(16, dtype=np.uint64)
+        out = np.zeros(64, dtype=np.uint64)
         check(self._L.qmcb_get_debug_counters(self._h, ptr(out, C.c_uint64)))
         return out
 

@@ -37,3 +37,12 @@ for k in range(sweeps):
 if os.environ.get('PROF_DBG'):
     c = g.debug_counters()
     print('dbg: chunks', c[0], 'fast', c[1], 'fast_fail_first', c[2], 'slow', c[3], 'why[delta|empty<<1|amb<<2]', list(c[4:12]))
+    names = ["between steps", "load+classify", "philox window", "thresholds+decode", "table+walk", "decisions+commit", "store+flips",
+             "segment ids+union-find", "closure", "P2", "P3"]
+    t = c[32:32 + len(names)].astype(float)
+    if t.sum() == 0:
+        print('(build with EXTRA=-DQMCB_PHASE_TIMERS to get phase timers)')
+        t[:] = 1
+    print("phase cycles per replica-sweep (lane 0 clock64, summed over replicas / R / sweeps):")
+    for nm, v in zip(names, t):
+        print(f"  {nm:22s} {v / R / sweeps / 1e6:8.2f} Mcycles  {100 * v / t.sum():5.1f}%")
