@@ -187,14 +187,18 @@ def bench_sse(args, world, rank, local):
     vu1 = g.total_vertex_updates()
     barrier_sync(world)
     t0 = time.perf_counter()
+    e2e_step_ms = []
     for _ in range(e2e_steps):
+        t1 = time.perf_counter()
         g._betas = None  # force the per-step H2D of the inputs
         samples, energies = g.timesteps_sample(1, betas, 1)
+        e2e_step_ms.append((time.perf_counter() - t1) * 1e3)
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
     vu_e2e = sum_over_ranks(float(g.total_vertex_updates() - vu1), world)
     e2e = {"value": vu_e2e / e2e_s, "unit": "vertex_updates/s", "h2d_bytes_per_step": int(R * 8 * world),
            "d2h_bytes_per_step": int((R * 8 + R * g.nvars) * world), "steps": e2e_steps,
+           "ms_per_step": e2e_s / e2e_steps * 1e3, "step_ms": [round(x, 2) for x in e2e_step_ms],
            "call": "QmcIsingGraph.timesteps_sample(1, betas, 1) -> qmcb_set_betas + qmcb_timesteps"}
 
     # ---- roofline of the dominant kernel (k_sse_fast: one launch = one sweep of R replicas)

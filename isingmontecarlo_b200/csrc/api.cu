@@ -105,8 +105,7 @@ static size_t bits_stride(const SseDev &D) { return (size_t)(D.cap / 32 + 2 + D.
 static int alloc_strict_ws(QmcbHandle *h) {
     if (h->strict_ws) return QMCB_OK;
     SseDev &D = h->D;
-    CUDA_TRY(h->pool.alloc(&D.links, (size_t)D.R * D.cap * 4));
-    CUDA_TRY(h->pool.alloc(&D.bounds, (size_t)D.R * D.cap * 2));
+    CUDA_TRY(h->pool.alloc(&D.rec, (size_t)D.R * D.cap * 8));
     CUDA_TRY(h->pool.alloc(&D.frontier, (size_t)D.R * (2 * D.cap + 16)));
     CUDA_TRY(h->pool.alloc(&D.interior, (size_t)D.R * (4 * D.cap + 16)));
     h->strict_ws = true;
@@ -137,9 +136,9 @@ static int grow(QmcbHandle *h, uint64_t newcap) {
     h->pool.release(D.ops);
     D.ops = nops;
     const bool s = h->strict_ws, f = h->fast_ws;
-    h->pool.release(D.links), h->pool.release(D.bounds), h->pool.release(D.frontier), h->pool.release(D.interior);
+    h->pool.release(D.rec), h->pool.release(D.frontier), h->pool.release(D.interior);
     h->pool.release(D.parent), h->pool.release(D.bits), h->pool.release(D.frozen);
-    D.links = D.bounds = D.frontier = D.interior = D.parent = D.bits = D.frozen = nullptr;
+    D.rec = D.frontier = D.interior = D.parent = D.bits = D.frozen = nullptr;
     h->strict_ws = h->fast_ws = false;
     D.cap = newcap;
     CUDA_TRY(h->pool.alloc(&D.bits, (size_t)D.R * bits_stride(D)));
@@ -704,10 +703,14 @@ extern "C" int qmcb_get_boundaries(QmcbHandle *h, uint32_t r, uint32_t *b_in, ui
     if (!b_in || !b_out || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
     if (!h->strict_ws) return fail(QMCB_ERR_BAD_ARG, "no STRICT cluster step has run yet");
     uint64_t k = std::min<uint64_t>(nslots, D.cap);
-    std::vector<uint32_t> b(2 * k);
+    std::vector<uint32_t> b(8 * k), ow(k);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    CUDA_TRY(cudaMemcpy(b.data(), D.bounds + (size_t)r * D.cap * 2, 8 * k, cudaMemcpyDeviceToHost));
-    for (uint64_t p = 0; p < nslots; p++) b_in[p] = p < k ? b[2 * p] : NONE32, b_out[p] = p < k ? b[2 * p + 1] : NONE32;
+    CUDA_TRY(cudaMemcpy(b.data(), D.rec + (size_t)r * D.cap * 8, 32 * k, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ow.data(), D.ops + (size_t)r * D.cap, 4 * k, cudaMemcpyDeviceToHost));
+    for (uint64_t p = 0; p < nslots; p++) {
+        const bool has = p < k && ow[p] != QMCB_OP_EMPTY;  // records of empty slots are stale
+        b_in[p] = has ? b[8 * p + 5] : NONE32, b_out[p] = has ? b[8 * p + 6] : NONE32;
+    }
     return QMCB_OK;
 }
 

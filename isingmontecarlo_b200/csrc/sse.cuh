@@ -33,8 +33,7 @@ struct SseDev {
     uint32_t *vfirst, *vlast;  // [R][N] first / last leg (p << 1 | rel) on each variable, or NONE32
     uint32_t *cur;             // [R][N] FAST: current segment id per variable
     // STRICT workspace (allocated on demand)
-    uint32_t *links;     // [R][cap][4] prev0, prev1, next0, next1 as (p << 1 | rel) or NONE32
-    uint32_t *bounds;    // [R][cap][2] cluster id of (inputs, outputs) or NONE32
+    uint32_t *rec;       // [R][cap][8] one 32-byte record per slot: op word, 4 links, 2 cluster ids (sse_serial.cu)
     uint32_t *frontier;  // [R][2*cap+16]
     uint32_t *interior;  // [R][4*cap+16]
     uint32_t *bits;      // [R][cap/32+2] flip bit per cluster (STRICT) / per segment (FAST)

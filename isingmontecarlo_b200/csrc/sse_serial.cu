@@ -13,8 +13,16 @@
 #define SIDE_IN 0u
 #define SIDE_OUT 1u
 
+// STRICT workspace: one 32-byte record (= one DRAM sector) per slot, so that a step of the cluster walk
+// touches one sector per node:  [0] op word, [1..2] previous leg on the world line of leg 0 / 1,
+// [3..4] next leg, [5] cluster of the inputs, [6] cluster of the outputs, [7] unused.
+// legs are (p << 1 | rel), NONE32 at the ends (fast_ops.rs:181-190; boundaries cluster.rs:50-52)
+#define REC_OP(V, p) ((V).rec[8 * (size_t)(p)])
+#define REC_LINK(V, p, i) ((V).rec[8 * (size_t)(p) + 1 + (i)])
+#define REC_BND(V, p, side) ((V).rec[8 * (size_t)(p) + 5 + (side)])
+
 struct Rep {
-    uint32_t *ops, *state, *vfirst, *vlast, *cur, *links, *bounds, *frontier, *interior, *bits, *frozen, *parent;
+    uint32_t *ops, *state, *vfirst, *vlast, *cur, *rec, *frontier, *interior, *bits, *frozen, *parent;
     uint32_t *ends;
     uint64_t fcap, icap;
 };
@@ -26,8 +34,7 @@ __device__ __forceinline__ Rep rep_view(const SseDev &D, uint32_t r) {
     v.vfirst = D.vfirst + (size_t)r * D.N;
     v.vlast = D.vlast + (size_t)r * D.N;
     v.cur = D.cur + (size_t)r * D.N;
-    v.links = D.links ? D.links + (size_t)r * D.cap * 4 : nullptr;
-    v.bounds = D.bounds ? D.bounds + (size_t)r * D.cap * 2 : nullptr;
+    v.rec = D.rec ? D.rec + (size_t)r * D.cap * 8 : nullptr;
     v.fcap = 2 * D.cap + 16, v.icap = 4 * D.cap + 16;
     v.frontier = D.frontier ? D.frontier + (size_t)r * v.fcap : nullptr;
     v.interior = D.interior ? D.interior + (size_t)r * v.icap : nullptr;
@@ -127,14 +134,17 @@ __device__ void links_serial(const SseDev &D, uint32_t r, const Rep &V, bool ful
         if (first_p == NONE32) first_p = p;
         last_p = p;
         if (kind == KIND_SITE && first_site == NONE32) first_site = p;
-        if (full) V.links[4 * (size_t)p + 1] = NONE32, V.links[4 * (size_t)p + 3] = NONE32;
+        if (full) {
+            REC_OP(V, p) = w;
+            for (int i = 0; i < 4; i++) REC_LINK(V, p, i) = NONE32;
+            REC_BND(V, p, 0) = NONE32, REC_BND(V, p, 1) = NONE32;
+        }
         for (int k = 0; k < nv; k++) {
             uint32_t v = vv[k], me = (p << 1) | (uint32_t)k;
             uint32_t prev = V.vlast[v];
             if (full) {
-                V.links[4 * (size_t)p + k] = prev;
-                V.links[4 * (size_t)p + 2 + k] = NONE32;
-                if (prev != NONE32) V.links[4 * (size_t)(prev >> 1) + 2 + (prev & 1u)] = me;
+                REC_LINK(V, p, k) = prev;
+                if (prev != NONE32) REC_LINK(V, prev >> 1, 2 + (prev & 1u)) = me;
             }
             if (prev == NONE32) V.vfirst[v] = me;
             V.vlast[v] = me;
@@ -143,15 +153,72 @@ __device__ void links_serial(const SseDev &D, uint32_t r, const Rep &V, bool ful
     V.ends[0] = first_p, V.ends[1] = last_p, V.ends[2] = first_site;
 }
 
+// The same links, built by the whole warp: 32 slots per step, two half-steps of 16 slots = 32 legs, one
+// lane per leg.  match.any finds the legs of the half-step that sit on the same variable (the two legs of
+// one op never do), the nearest earlier one is the predecessor, otherwise the table `last` (shared
+// memory, one entry per variable) holds it.
+__device__ void links_parallel(const SseDev &D, uint32_t r, const Rep &V, int lane, uint32_t *last) {
+    const uint32_t M = D.M[r];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint32_t v = lane; v < D.N; v += 32) last[v] = NONE32, V.vfirst[v] = NONE32;
+    __syncwarp();
+    uint32_t first_p = NONE32, last_p = NONE32, first_site = NONE32;
+    for (uint32_t base = 0; base < M; base += 32) {
+        const uint32_t p = base + lane;
+        const uint32_t w = p < M ? V.ops[p] : OP_EMPTY;
+        int kind = -1;
+        uint32_t v0 = 0, v1 = 0;
+        if (w != OP_EMPTY) {
+            kind = bond_kind(D, op_bond(w));
+            bond_vars(D, op_bond(w), kind, v0, v1);
+            uint4 a, b;
+            a.x = w, a.y = NONE32, a.z = NONE32, a.w = NONE32;
+            b.x = NONE32, b.y = NONE32, b.z = NONE32, b.w = 0u;
+            *reinterpret_cast<uint4 *>(&V.rec[8 * (size_t)p]) = a;
+            *reinterpret_cast<uint4 *>(&V.rec[8 * (size_t)p + 4]) = b;
+        }
+        const uint32_t hasm = __ballot_sync(0xFFFFFFFFu, kind >= 0), sitem = __ballot_sync(0xFFFFFFFFu, kind == KIND_SITE);
+        if (hasm) {
+            if (first_p == NONE32) first_p = base + (uint32_t)__ffs(hasm) - 1u;
+            last_p = base + 31u - (uint32_t)__clz(hasm);
+        }
+        if (sitem && first_site == NONE32) first_site = base + (uint32_t)__ffs(sitem) - 1u;
+        __syncwarp();  // records of this step exist before anyone links to them
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int s = 16 * half + (lane >> 1);
+            const uint32_t rel = (uint32_t)lane & 1u;
+            const int sk = __shfl_sync(0xFFFFFFFFu, kind, s);
+            const uint32_t sv0 = __shfl_sync(0xFFFFFFFFu, v0, s), sv1 = __shfl_sync(0xFFFFFFFFu, v1, s);
+            const bool legvalid = sk >= 0 && (rel == 0 || sk == KIND_BOND);
+            const uint32_t sv = rel ? sv1 : sv0;
+            const uint32_t legm = __ballot_sync(0xFFFFFFFFu, legvalid);
+            const uint32_t m = __match_any_sync(0xFFFFFFFFu, legvalid ? sv : (0x80000000u | (uint32_t)lane)) & legm;
+            if (legvalid) {
+                const uint32_t me = ((base + (uint32_t)s) << 1) | rel;
+                uint32_t prev;
+                if (m & lt_mask) {
+                    const uint32_t j = 31u - (uint32_t)__clz(m & lt_mask);
+                    prev = ((base + 16u * half + (j >> 1)) << 1) | (j & 1u);
+                } else prev = last[sv];
+                REC_LINK(V, base + s, rel) = prev;
+                if (prev != NONE32) REC_LINK(V, prev >> 1, 2 + (prev & 1u)) = me;
+                else V.vfirst[sv] = me;
+                if ((m & ~lt_mask & ~(1u << lane)) == 0) last[sv] = me;  // last leg of the half-step on this variable
+            }
+            __syncwarp();
+        }
+    }
+    for (uint32_t v = lane; v < D.N; v += 32) V.vlast[v] = last[v];
+    if (lane == 0) V.ends[0] = first_p, V.ends[1] = last_p, V.ends[2] = first_site;
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------
 // STRICT cluster labelling: cluster.rs:46-108 (frontier loop) and :193-271 (expansion), lane 0
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool set_boundary(const Rep &V, uint32_t p, uint32_t side, uint32_t c, int &err) {
-    uint32_t *slot = V.bounds + 2 * (size_t)p + side;  // cluster.rs:289-306
-    if (*slot == NONE32 || *slot == c) *slot = c;
-    else err |= DEV_ERR_INVARIANT;  // unreachable!() in the reference
-    return V.bounds[2 * (size_t)p] != NONE32 && V.bounds[2 * (size_t)p + 1] != NONE32;
-}
+__device__ __forceinline__ uint4 ld_rec_lo(const Rep &V, uint32_t p) { return *reinterpret_cast<const uint4 *>(&V.rec[8 * (size_t)p]); }
+__device__ __forceinline__ uint4 ld_rec_hi(const Rep &V, uint32_t p) { return *reinterpret_cast<const uint4 *>(&V.rec[8 * (size_t)p + 4]); }
 
 __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
     const uint32_t last_p = V.ends[1], cp = V.ends[2];
@@ -164,10 +231,13 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
         while (flen) {  // :62-80
             uint32_t e = V.frontier[--flen];
             uint32_t p0 = e >> 1, side0 = e & 1u;
-            if (V.bounds[2 * (size_t)p0] != NONE32 && V.bounds[2 * (size_t)p0 + 1] != NONE32) continue;
+            {
+                const uint4 h0 = ld_rec_hi(V, p0);
+                if (h0.y != NONE32 && h0.z != NONE32) continue;
+            }
             // ---- expand_whole_cluster(p0, (0, side0), cnum) :193-271
             {
-                uint32_t b0 = op_bond(V.ops[p0]);
+                uint32_t b0 = op_bond(REC_OP(V, p0));
                 bool edge0 = b0 >= E && b0 < EN;
                 ilen = 0;
                 if (!edge0) {  // :205-211
@@ -180,11 +250,17 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
                 while (ilen) {
                     uint32_t it = V.interior[--ilen];
                     uint32_t p = it >> 2, rel = (it >> 1) & 1u, side = it & 1u;
-                    set_boundary(V, p, side, cnum, err);  // :218
-                    uint32_t lk = V.links[4 * (size_t)p + 2 * side + rel];
+                    const uint4 pl = ld_rec_lo(V, p), ph = ld_rec_hi(V, p);  // one sector: op, links, boundaries
+                    {  // set_boundary(p, side, cnum) :218, :289-306
+                        const uint32_t curb = side ? ph.z : ph.y;
+                        if (curb == NONE32) REC_BND(V, p, side) = cnum;
+                        else if (curb != cnum) err |= DEV_ERR_INVARIANT;  // unreachable!() in the reference
+                    }
+                    const uint32_t li = 2 * side + rel;
+                    uint32_t lk = li == 0 ? pl.y : (li == 1 ? pl.z : (li == 2 ? pl.w : ph.x));
                     uint32_t sq = side ^ 1u;
                     if (lk == NONE32) {  // wrap through the ends of the world line :224-241
-                        uint32_t b = op_bond(V.ops[p]);
+                        uint32_t b = op_bond(pl.x);
                         int kind = bond_kind(D, b);
                         uint32_t v0, v1;
                         bond_vars(D, b, kind, v0, v1);
@@ -192,16 +268,20 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
                         lk = side == SIDE_IN ? V.vlast[var] : V.vfirst[var];
                     }
                     uint32_t q = lk >> 1, rq = lk & 1u;
-                    uint32_t bq = op_bond(V.ops[q]);
+                    const uint4 ql = ld_rec_lo(V, q), qh = ld_rec_hi(V, q);
+                    uint32_t bq = op_bond(ql.x);
                     if (bq >= E && bq < EN) {  // cluster edge :245-248
-                        if (!set_boundary(V, q, sq, cnum, err)) {
+                        const uint32_t mine = sq ? qh.z : qh.y, other = sq ? qh.y : qh.z;
+                        if (mine == NONE32) REC_BND(V, q, sq) = cnum;
+                        else if (mine != cnum) err |= DEV_ERR_INVARIANT;
+                        if (other == NONE32) {  // not both sides set: the other side starts a new cluster later
                             if (flen >= V.fcap) { err |= DEV_ERR_STACK; } else V.frontier[flen++] = (q << 1) | (sq ^ 1u);
                         }
                     } else {  // interior op :249-268
-                        uint32_t a = V.bounds[2 * (size_t)q], bb = V.bounds[2 * (size_t)q + 1];
+                        uint32_t a = qh.y, bb = qh.z;
                         bool ok = (a == NONE32 && bb == NONE32) || (a == cnum && bb == NONE32) || (a == NONE32 && bb == cnum);
                         if (ok) {
-                            V.bounds[2 * (size_t)q] = cnum, V.bounds[2 * (size_t)q + 1] = cnum;
+                            REC_BND(V, q, 0) = cnum, REC_BND(V, q, 1) = cnum;
                             int nvq = bq < E ? 2 : 1;
                             if (ilen + 4 > V.icap) { err |= DEV_ERR_STACK; break; }
                             for (int k = 0; k < nvq; k++)
@@ -216,7 +296,9 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
         }
         uint32_t unmapped = NONE32;  // :82-88 (the smallest unmapped p never decreases)
         for (; scan <= last_p; scan++) {
-            if (V.ops[scan] != OP_EMPTY && V.bounds[2 * (size_t)scan] == NONE32 && V.bounds[2 * (size_t)scan + 1] == NONE32) {
+            if (V.ops[scan] == OP_EMPTY) continue;
+            const uint4 h = ld_rec_hi(V, scan);
+            if (h.y == NONE32 && h.z == NONE32) {
                 unmapped = scan;
                 break;
             }
@@ -233,8 +315,7 @@ __device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, in
     const uint32_t n = D.n[r];
     if (n == 0) return 0;  // :46-48
     const uint32_t last_p = V.ends[1], cp = V.ends[2];
-    for (uint32_t p = lane; p <= last_p; p += 32) V.bounds[2 * (size_t)p] = NONE32, V.bounds[2 * (size_t)p + 1] = NONE32;
-    __syncwarp();
+    // (the link pass initialised the boundaries of every op to None, cluster.rs:50-52)
     uint32_t ncl = 1;
     int err = 0;
     if (cp != NONE32) {
@@ -242,7 +323,7 @@ __device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, in
         ncl = __shfl_sync(0xFFFFFFFFu, ncl, 0);
     } else {  // :98-107 the whole thing is one cluster
         for (uint32_t p = lane; p <= last_p; p += 32)
-            if (V.ops[p] != OP_EMPTY) V.bounds[2 * (size_t)p] = 0, V.bounds[2 * (size_t)p + 1] = 0;
+            if (V.ops[p] != OP_EMPTY) REC_BND(V, p, 0) = 0, REC_BND(V, p, 1) = 0;
     }
     if (err) atomicOr(D.status, err);
     __syncwarp();
@@ -257,7 +338,7 @@ __device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, in
         for (uint32_t p = lane; p <= last_p; p += 32) {
             uint32_t w = V.ops[p];
             if (w != OP_EMPTY && op_bond(w) >= D.E + D.N) {
-                uint32_t c = V.bounds[2 * (size_t)p];
+                uint32_t c = REC_BND(V, p, 0);
                 atomicOr(&V.frozen[c >> 5], 1u << (c & 31));
             }
         }
@@ -275,7 +356,7 @@ __device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, in
     for (uint32_t p = lane; p <= last_p; p += 32) {
         uint32_t w = V.ops[p];
         if (w == OP_EMPTY) continue;
-        uint32_t ci = V.bounds[2 * (size_t)p], co = V.bounds[2 * (size_t)p + 1];
+        uint32_t ci = REC_BND(V, p, 0), co = REC_BND(V, p, 1);
         bool fi = (V.bits[ci >> 5] >> (ci & 31)) & 1u, fo = (V.bits[co >> 5] >> (co & 31)) & 1u;
         uint32_t b = op_bond(w);
         int kind = bond_kind(D, b);
@@ -285,7 +366,7 @@ __device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, in
             uint32_t vv[2];
             bond_vars(D, b, kind, vv[0], vv[1]);
             for (int k = 0; k < (kind == KIND_BOND ? 2 : 1); k++) {
-                if (V.links[4 * (size_t)p + k] == NONE32) {  // first op on this world line
+                if (REC_LINK(V, p, k) == NONE32) {  // first op on this world line
                     uint32_t v = vv[k], bit = 1u << (v & 31);
                     if ((in >> k) & 1u) atomicOr(&V.state[v >> 5], bit);
                     else atomicAnd(&V.state[v >> 5], ~bit);
@@ -427,7 +508,8 @@ __device__ void free_spins(const SseDev &D, uint32_t r, const Rep &V, int lane) 
 // bit4 run only the single step that takes the replica from target - 1 to target
 __global__ void __launch_bounds__(128) k_sse_serial(SseDev D, int mode, uint64_t target, uint32_t phases,
                                                     uint64_t sample_freq, uint64_t sample_origin,
-                                                    uint8_t *samples, uint64_t samples_per_rep) {
+                                                    uint8_t *samples, uint64_t samples_per_rep, int par_links) {
+    extern __shared__ uint32_t smem_last[];  // [warps per block][N] when par_links
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= D.R) return;
@@ -444,10 +526,14 @@ __global__ void __launch_bounds__(128) k_sse_serial(SseDev D, int mode, uint64_t
             __syncwarp();
         }
         if (phases & 2u) {
-            for (uint32_t v = lane; v < D.N; v += 32) V.vfirst[v] = NONE32, V.vlast[v] = NONE32;
-            __syncwarp();
-            if (lane == 0) links_serial(D, r, V, mode == 0);
-            __syncwarp();
+            if (mode == 0 && par_links) {
+                links_parallel(D, r, V, lane, smem_last + (size_t)(threadIdx.x >> 5) * D.N);
+            } else {
+                for (uint32_t v = lane; v < D.N; v += 32) V.vfirst[v] = NONE32, V.vlast[v] = NONE32;
+                __syncwarp();
+                if (lane == 0) links_serial(D, r, V, mode == 0);
+                __syncwarp();
+            }
             uint32_t ncl = mode == 0 ? cluster_strict(D, r, V, lane) : cluster_fast_serial(D, r, V, lane);
             if (lane == 0) D.ncl[r] = ncl;
             free_spins(D, r, V, lane);
@@ -555,7 +641,10 @@ void launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phas
                        uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
     const int threads = 128;
     const uint32_t blocks = (uint32_t)(((uint64_t)D.R * 32 + threads - 1) / threads);
-    k_sse_serial<<<blocks, threads, 0, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep);
+    const size_t smem = (size_t)(threads / 32) * D.N * sizeof(uint32_t);
+    const int par = mode == 0 && smem <= 160 * 1024;
+    if (par && smem > 48 * 1024) cudaFuncSetAttribute(k_sse_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_sse_serial<<<blocks, threads, par ? smem : 0, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep, par);
 }
 void launch_sse_verify(const SseDev &D, uint32_t r, int *ok_dev, uint32_t *scratch_dev, cudaStream_t st) {
     k_sse_verify<<<1, 32, 0, st>>>(D, r, ok_dev, scratch_dev);
