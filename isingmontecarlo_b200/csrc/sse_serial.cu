@@ -220,6 +220,15 @@ __device__ void links_parallel(const SseDev &D, uint32_t r, const Rep &V, int la
 __device__ __forceinline__ uint4 ld_rec_lo(const Rep &V, uint32_t p) { return *reinterpret_cast<const uint4 *>(&V.rec[8 * (size_t)p]); }
 __device__ __forceinline__ uint4 ld_rec_hi(const Rep &V, uint32_t p) { return *reinterpret_cast<const uint4 *>(&V.rec[8 * (size_t)p + 4]); }
 
+// the walk is a chain of dependent sector loads; when a leg is pushed its link is already in registers,
+// so the record it will land on is requested right away (L2 prefetch) and is close by when the leg is popped
+__device__ __forceinline__ void prefetch_rec(const Rep &V, uint32_t leg) {
+    if (leg != NONE32) asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.rec[8 * (size_t)(leg >> 1)]));
+}
+__device__ __forceinline__ uint32_t rec_link(const uint4 &lo, const uint4 &hi, uint32_t li) {
+    return li == 0 ? lo.y : (li == 1 ? lo.z : (li == 2 ? lo.w : hi.x));
+}
+
 __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
     const uint32_t last_p = V.ends[1], cp = V.ends[2];
     const uint32_t E = D.E, EN = D.E + D.N;
@@ -257,7 +266,7 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
                         else if (curb != cnum) err |= DEV_ERR_INVARIANT;  // unreachable!() in the reference
                     }
                     const uint32_t li = 2 * side + rel;
-                    uint32_t lk = li == 0 ? pl.y : (li == 1 ? pl.z : (li == 2 ? pl.w : ph.x));
+                    uint32_t lk = rec_link(pl, ph, li);
                     uint32_t sq = side ^ 1u;
                     if (lk == NONE32) {  // wrap through the ends of the world line :224-241
                         uint32_t b = op_bond(pl.x);
@@ -276,6 +285,7 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
                         else if (mine != cnum) err |= DEV_ERR_INVARIANT;
                         if (other == NONE32) {  // not both sides set: the other side starts a new cluster later
                             if (flen >= V.fcap) { err |= DEV_ERR_STACK; } else V.frontier[flen++] = (q << 1) | (sq ^ 1u);
+                            prefetch_rec(V, rec_link(ql, qh, 2u * (sq ^ 1u)));
                         }
                     } else {  // interior op :249-268
                         uint32_t a = qh.y, bb = qh.z;
@@ -285,9 +295,15 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
                             int nvq = bq < E ? 2 : 1;
                             if (ilen + 4 > V.icap) { err |= DEV_ERR_STACK; break; }
                             for (int k = 0; k < nvq; k++)
-                                if (!((uint32_t)k == rq && sq == SIDE_IN)) V.interior[ilen++] = (q << 2) | ((uint32_t)k << 1) | SIDE_IN;
+                                if (!((uint32_t)k == rq && sq == SIDE_IN)) {
+                                    V.interior[ilen++] = (q << 2) | ((uint32_t)k << 1) | SIDE_IN;
+                                    prefetch_rec(V, rec_link(ql, qh, (uint32_t)k));
+                                }
                             for (int k = 0; k < nvq; k++)
-                                if (!((uint32_t)k == rq && sq == SIDE_OUT)) V.interior[ilen++] = (q << 2) | ((uint32_t)k << 1) | SIDE_OUT;
+                                if (!((uint32_t)k == rq && sq == SIDE_OUT)) {
+                                    V.interior[ilen++] = (q << 2) | ((uint32_t)k << 1) | SIDE_OUT;
+                                    prefetch_rec(V, rec_link(ql, qh, 2u + (uint32_t)k));
+                                }
                         }
                     }
                 }
