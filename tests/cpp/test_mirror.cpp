@@ -1,0 +1,97 @@
+// The reference's own integration tests, re-read against the C++ mirror (include/qmcb.hpp):
+//   tests/longitudinal_crash.rs:39-178  (16 seeds x small lattices with a longitudinal field, 1000 steps, verify())
+//   examples/small_qmc.rs               (4-site ring, 1000 steps)
+//   tests/convert_test.rs:5-7 lattice   (3-ring, 10 steps)
+// Batched: the 16 seeds of a reference test are the 16 replicas of one handle.  Both cluster orders run.
+#include <cstdio>
+#include <cstdlib>
+
+#include "qmcb.hpp"
+
+using qmcb::Edge;
+
+static std::vector<Edge> two_d_periodic(size_t l) {  // tests/longitudinal_crash.rs:5-23
+    std::vector<Edge> right, down;
+    auto f = [l](size_t i, size_t j) { return j * l + i; };
+    for (size_t i = 0; i < l; i++)
+        for (size_t j = 0; j < l; j++) {
+            right.push_back({{f(i, j), f((i + 1) % l, j)}, -1.0});
+            down.push_back({{f(i, j), f(i, (j + 1) % l)}, i % 2 == 0 ? 1.0 : -1.0});
+        }
+    right.insert(right.end(), down.begin(), down.end());
+    return right;
+}
+static std::vector<Edge> two_unit_cell() {  // :25-37
+    return {{{0, 1}, -1.0}, {{1, 2}, 1.0}, {{2, 3}, 1.0}, {{3, 0}, 1.0}, {{1, 7}, 1.0}, {{4, 5}, -1.0}, {{5, 6}, 1.0}, {{6, 7}, 1.0}, {{7, 4}, 1.0}};
+}
+
+#define ASSERT(x)                                                        \
+    do {                                                                 \
+        if (!(x)) {                                                      \
+            std::fprintf(stderr, "assert failed %s:%d: %s\n", __FILE__, __LINE__, #x); \
+            std::exit(1);                                                \
+        }                                                                \
+    } while (0)
+
+int main() {
+    std::vector<uint64_t> seeds;
+    for (uint64_t i = 0; i < 16; i++) seeds.push_back(i);
+    for (int mode : {QMCB_MODE_STRICT, QMCB_MODE_FAST}) {
+        {  // run_simple :39-55
+            std::vector<bool> st(2, false);
+            auto ising = qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 1}, 1.0}}, 1.0, 1.0, 2, seeds, &st, mode);
+            ising.timesteps(1000, 1.0);
+            ASSERT(ising.verify());
+        }
+        {  // run_three / four lattices with longitudinal field :77-133
+            for (size_t l : {3u, 4u}) {
+                auto ising = qmcb::DefaultQmcIsingGraph::new_with_rng(two_d_periodic(l), 1.0, 1.0, l * l, seeds, nullptr, mode);
+                ising.timesteps(1000, 1.0);
+                ASSERT(ising.verify());
+            }
+        }
+        {  // two unit cells :135-178
+            auto ising = qmcb::DefaultQmcIsingGraph::new_with_rng(two_unit_cell(), 1.0, 1.0, 8, seeds, nullptr, mode);
+            ising.timesteps(1000, 1.0);
+            ASSERT(ising.verify());
+        }
+        {  // examples/small_qmc.rs
+            auto g = qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 1}, -1.0}, {{1, 2}, 1.0}, {{2, 3}, 1.0}, {{3, 0}, 1.0}}, 1.0, 0.0, 3, seeds, nullptr, mode);
+            auto e = g.timesteps(1000, 1.0);
+            double mean = 0;
+            for (double x : e) mean += x / e.size();
+            ASSERT(mean > -4.6 && mean < -3.6);  // exact -4.055 (DESIGN / SURVEY Appendix E)
+            ASSERT(g.verify());
+        }
+        {  // convert_test.rs lattice: timestep returns the state, sampling shape
+            std::vector<bool> st(3, true);
+            auto ising = qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 1}, 1.0}, {{1, 2}, 1.0}, {{2, 0}, 1.0}}, 1.0, 0.0, 3, {1234}, &st, mode);
+            for (int i = 0; i < 10; i++) ASSERT(ising.timestep(1.0)[0].size() == 3);
+            auto se = ising.timesteps_sample(20, 1.0, 5);
+            ASSERT(se.first[0].size() == 4 && se.first[0][0].size() == 3);
+        }
+    }
+    {  // error behaviour: status codes become exceptions, never aborts
+        bool threw = false;
+        try {
+            qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 0}, 1.0}}, 1.0, 0.0, 2, {1});  // self-loop
+        } catch (const qmcb::Error &e) {
+            threw = e.code == QMCB_ERR_BAD_ARG;
+        }
+        ASSERT(threw);
+    }
+    {  // classical mirror
+        std::vector<Edge> edges;
+        const size_t L = 8;
+        for (size_t i = 0; i < L; i++)
+            for (size_t j = 0; j < L; j++) {
+                edges.push_back({{j * L + i, j * L + (i + 1) % L}, -1.0});
+                edges.push_back({{j * L + i, ((j + 1) % L) * L + i}, -1.0});
+            }
+        auto g = qmcb::GraphState::create(edges, std::vector<double>(L * L, 0.0), {1, 2, 3}, {2.0, 2.0, 2.0});
+        g.do_time_step(200);
+        for (double e : g.get_energy()) ASSERT(e < -80.0);  // quench into the ordered phase: -128 (uniform) or -96 (one stripe)
+    }
+    std::printf("cpp mirror ok\n");
+    return 0;
+}

@@ -164,3 +164,16 @@ def test_bond_counts_and_dump_load_round_trip():
     bad[k] ^= 1 << 24
     g.load_ops(1, bad, st)
     assert not g.verify(1)
+
+
+def test_cpp_host_mirror_runs_the_reference_integration_tests():
+    # include/qmcb.hpp mirrors QmcIsingGraph / QmcStepper / GraphState in C++; tests/cpp/test_mirror.cpp is
+    # tests/longitudinal_crash.rs + examples/small_qmc.rs + convert_test.rs re-read against it
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "isingmontecarlo_b200", "csrc"), "-s", "mirror"], check=True)
+    res = subprocess.run([os.path.join(root, "isingmontecarlo_b200", "_build", "test_mirror")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "cpp mirror ok" in res.stdout
