@@ -84,7 +84,7 @@ template <int G>
 __global__ void __launch_bounds__(256, 4) k_cls_square(ClsDev D, uint32_t colour, uint64_t sweep) {
     __shared__ uint32_t s_rk[20];
     __shared__ uint32_t s_tk[G > 0 ? G : 1][32];  // s_tk[g][k]: bit (31 - k) of the threshold of group g as a mask
-    __shared__ uint32_t s_mem[G > 0 ? G : 1];
+    __shared__ __align__(16) uint32_t s_cmsk[G + 1][12];  // [set][own * 5 + cnt] class membership as masks; set G = always-flip
     const uint32_t r = blockIdx.y;
     {
         const uint64_t key = D.key[r];
@@ -96,14 +96,17 @@ __global__ void __launch_bounds__(256, 4) k_cls_square(ClsDev D, uint32_t colour
             const uint32_t T = D.sq_gT[(size_t)r * SQ_MAXG + (i >> 5)];
             s_tk[i >> 5][i & 31] = (T >> (31 - (i & 31))) & 1u;  // 0/1: used as a multiplier (FMA pipe), not a mask
         }
-        if (threadIdx.x < (uint32_t)G) s_mem[threadIdx.x] = D.sq_gmem[(size_t)r * SQ_MAXG + threadIdx.x];
+        for (uint32_t i = threadIdx.x; i < (uint32_t)(G + 1) * 10; i += blockDim.x) {
+            const uint32_t set = i / 10, j = i % 10;  // j = own * 5 + cnt  ->  class bit own * 8 + cnt
+            const uint32_t members = set < (uint32_t)G ? D.sq_gmem[(size_t)r * SQ_MAXG + set] : D.sq_always[r];
+            s_cmsk[set][j] = ((members >> ((j / 5) * 8 + (j % 5))) & 1u) ? 0xFFFFFFFFu : 0u;
+        }
     }
     __syncthreads();
     const uint32_t WPR = D.L >> 6;                  // 32-bit words per row of one colour plane
     const uint32_t words_per_plane = D.L * WPR;
     uint32_t *mine = D.planes + ((size_t)r * 2 + colour) * words_per_plane;
     const uint32_t *other = D.planes + ((size_t)r * 2 + (colour ^ 1u)) * words_per_plane;
-    const uint32_t always = D.sq_always[r];
     // a block walks over several chunks of 256 words so that the set-up above is paid once
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < words_per_plane; t += gridDim.x * blockDim.x) {
         uint32_t y, w;
@@ -128,23 +131,18 @@ __global__ void __launch_bounds__(256, 4) k_cls_square(ClsDev D, uint32_t colour
         const uint32_t mid = c1 ^ c2, hi = c1 & c2;
         uint32_t cm[5];
         cm[0] = ~(lo | mid | hi), cm[1] = lo & ~mid, cm[2] = mid & ~lo, cm[3] = lo & mid, cm[4] = hi;
-        // sites of a set of classes (bit idx = own << 3 | cnt of `members`).  The one-hot masks cm[] are
-        // disjoint, so OR == ADD and "mask if member" == mask * bit: integer multiply-adds run on the FMA
-        // pipe and leave the (binding) ALU pipe to the logic ops
-        auto class_sites = [&](uint32_t members) -> uint32_t {
+        // sites of a set of classes: the membership of class (own, cnt) is a block-uniform mask in shared memory
+        auto class_sites = [&](const uint32_t *mk) -> uint32_t {
             uint32_t m0 = 0, m1 = 0;
 #pragma unroll
-            for (int cc = 0; cc < 5; cc++) {
-                m0 = cm[cc] * ((members >> cc) & 1u) + m0;
-                m1 = cm[cc] * ((members >> (8 + cc)) & 1u) + m1;
-            }
+            for (int cc = 0; cc < 5; cc++) m0 |= cm[cc] & mk[cc], m1 |= cm[cc] & mk[5 + cc];
             return (~own & m0) | (own & m1);
         };
-        uint32_t flip = class_sites(always);  // delta_e <= 0 (threshold 2^32): always
+        uint32_t flip = class_sites(s_cmsk[G]);  // delta_e <= 0 (threshold 2^32): always
         if (G > 0) {
             uint32_t sel[G > 0 ? G : 1], eq = 0;
 #pragma unroll
-            for (int g = 0; g < G; g++) sel[g] = class_sites(s_mem[g]), eq |= sel[g];
+            for (int g = 0; g < G; g++) sel[g] = class_sites(s_cmsk[g]), eq |= sel[g];
             uint32_t lt = 0;
             uint32_t pl[4];
             // planes 0..11 always; 12..15 and 16..31 only while some site still ties with its threshold
