@@ -74,6 +74,12 @@ int qmcb_destroy(QmcbHandle *h);
 int qmcb_set_stream(QmcbHandle *h, void *cuda_stream);
 int qmcb_set_mode(QmcbHandle *h, int mode);
 int qmcb_get_mode(const QmcbHandle *h, int *mode);
+/* QmcIsingGraph::set_enable_heatbath (qmc_ising.rs:444-486): use the heat-bath diagonal update
+ * (heatbath.rs:149-209; bond chosen by cumulative maximum weight, BondWeights :10-61) instead of
+ * the Metropolis rule (diagonal.rs:142-191).  Same injected stream, reference draw order:
+ * gen_bool, then gen_range(0. ..1.0) and gen_range(0. ..total) when an insertion is attempted. */
+int qmcb_set_enable_heatbath(QmcbHandle *h, int enable);
+int qmcb_get_enable_heatbath(const QmcbHandle *h, int *enabled);
 /* tuning knobs; "impl": 0 = warp-parallel kernels where available (default), 1 = serial-order kernels only */
 int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value);
 /* event counters of the SSE kernels (after qmcb_set_option(h, "debug_counters", 1)); diagnostics only */

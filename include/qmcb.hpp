@@ -165,6 +165,7 @@ public:
         return true;
     }
     void set_mode(int mode) { check(qmcb_set_mode(h_, mode)); }
+    void set_enable_heatbath(bool enable) { check(qmcb_set_enable_heatbath(h_, enable ? 1 : 0)); }  // qmc_ising.rs:444-486
     QmcbHandle *raw() { return h_; }
 };
 using DefaultQmcIsingGraph = QmcIsingGraph;

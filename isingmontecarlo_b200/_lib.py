@@ -35,6 +35,8 @@ SIGNATURES = {
     "qmcb_set_stream": [vp, vp],
     "qmcb_set_mode": [vp, C.c_int],
     "qmcb_get_mode": [vp, C.POINTER(C.c_int)],
+    "qmcb_set_enable_heatbath": [vp, C.c_int],
+    "qmcb_get_enable_heatbath": [vp, C.POINTER(C.c_int)],
     "qmcb_set_option": [vp, C.c_char_p, C.c_int64],
     "qmcb_get_debug_counters": [vp, u64p],
     "qmcb_set_betas": [vp, f64p],

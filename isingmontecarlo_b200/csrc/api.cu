@@ -94,6 +94,10 @@ struct QmcbHandle {
     uint32_t pt_S = 0;
     uint8_t *samples_dev = nullptr;  // reused between qmcb_timesteps calls
     size_t samples_cap = 0;
+    // host copy of the lattice (heat-bath tables, checkpoints)
+    std::vector<uint32_t> va_h, vb_h;
+    std::vector<double> J_h;
+    double *hb_cum_dev = nullptr, *hb_maxw_dev = nullptr;
 };
 
 #define CHECK_H(h)                                              \
@@ -278,6 +282,7 @@ extern "C" int qmcb_create(const QmcbLattice *lat, uint32_t R, const double *bet
     TRYC(cudaMemcpy(vb, lat->vb, sizeof(uint32_t) * D.E, cudaMemcpyHostToDevice));
     TRYC(cudaMemcpy(J, lat->J, sizeof(double) * D.E, cudaMemcpyHostToDevice));
     D.va = va, D.vb = vb, D.J = J;
+    h->va_h.assign(lat->va, lat->va + D.E), h->vb_h.assign(lat->vb, lat->vb + D.E), h->J_h.assign(lat->J, lat->J + D.E);
     TRYC(h->pool.alloc(&D.ops, (size_t)R * D.cap));
     TRYC(cudaMemset(D.ops, 0xFF, (size_t)R * D.cap * 4));
     TRYC(h->pool.alloc(&D.state, (size_t)R * D.Nw));
@@ -347,6 +352,49 @@ extern "C" int qmcb_set_mode(QmcbHandle *h, int mode) {
     CHECK_H(h);
     if (mode != QMCB_MODE_STRICT && mode != QMCB_MODE_FAST) return fail(QMCB_ERR_BAD_ARG, "unknown mode");
     h->mode = mode;
+    return QMCB_OK;
+}
+// QmcIsingGraph::set_enable_heatbath (qmc_ising.rs:444-486): BondWeights from make_bond_weights
+// (heatbath.rs:130-146: maximum diagonal weight per bond; BondWeights::new :17-35: running sum)
+extern "C" int qmcb_set_enable_heatbath(QmcbHandle *h, int enable) {
+    CHECK_H(h);
+    SseDev &D = h->D;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!enable) {
+        D.hb_cum = D.hb_maxw = nullptr;
+        return QMCB_OK;
+    }
+    if (!h->hb_cum_dev) {
+        std::vector<double> maxw(D.Nb), cum(D.Nb);
+        for (uint32_t b = 0; b < D.Nb; b++) {
+            double acc = 0.0;
+            if (b < D.E) {  // two_site_hamiltonian, qmc_ising.rs:863-875, over the four diagonal substates
+                const double j = h->J_h[b], cand[2] = {std::fabs(j) - j, std::fabs(j) + j};
+                for (double w : cand)
+                    if (w > acc) acc = w;
+            } else if (b < D.E + D.N) {
+                if (D.gamma > acc) acc = D.gamma;
+            } else {
+                const double cand[2] = {std::fabs(D.h) - D.h, std::fabs(D.h) + D.h};
+                for (double w : cand)
+                    if (w > acc) acc = w;
+            }
+            maxw[b] = acc;
+            cum[b] = b == 0 ? acc : acc + cum[b - 1];
+        }
+        if (!(cum[D.Nb - 1] > 0.0)) return fail(QMCB_ERR_BAD_ARG, "heat-bath update needs a non-zero total bond weight");
+        CUDA_TRY(h->pool.alloc(&h->hb_cum_dev, D.Nb));
+        CUDA_TRY(h->pool.alloc(&h->hb_maxw_dev, D.Nb));
+        CUDA_TRY(cudaMemcpy(h->hb_cum_dev, cum.data(), sizeof(double) * D.Nb, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->hb_maxw_dev, maxw.data(), sizeof(double) * D.Nb, cudaMemcpyHostToDevice));
+        D.hb_total = cum[D.Nb - 1];
+    }
+    D.hb_cum = h->hb_cum_dev, D.hb_maxw = h->hb_maxw_dev;
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_enable_heatbath(const QmcbHandle *h, int *enabled) {
+    if (!h || !enabled) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *enabled = h->D.hb_cum != nullptr;
     return QMCB_OK;
 }
 extern "C" int qmcb_get_mode(const QmcbHandle *h, int *mode) {

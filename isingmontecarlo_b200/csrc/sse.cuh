@@ -40,6 +40,9 @@ struct SseDev {
     uint32_t *frozen;    // [R][cap/32+2] cluster holds a longitudinal op
     // FAST workspace
     uint32_t *parent;    // [R][N+cap+1] union-find parents over segment ids
+    // heat-bath diagonal update (heatbath.rs:10-61 BondWeights); NULL = Metropolis rule
+    const double *hb_cum, *hb_maxw;  // [Nb] cumulative / per-bond maximum diagonal weight
+    double hb_total;
 };
 
 enum { KIND_BOND = 0, KIND_SITE = 1, KIND_LONG = 2 };
@@ -63,5 +66,23 @@ __device__ __forceinline__ double bond_weight(const SseDev &D, uint32_t b, int k
     }
     if (kind == KIND_SITE) return D.gamma;
     return fabs(D.h) + (s0 ? D.h : -D.h);
+}
+// BondWeights::index_for_cumulative (heatbath.rs:56-60): slice::binary_search_by, insertion point
+// when no element compares equal
+__device__ __forceinline__ uint32_t hb_index_for_cumulative(const double *cum, uint32_t len, double val) {
+    uint32_t size = len, left = 0, right = len;
+    while (left < right) {
+        const uint32_t mid = left + size / 2;
+        const double c = __ldg(cum + mid);
+        if (c < val) left = mid + 1;
+        else if (c > val) right = mid;
+        else return mid;
+        size = right - left;
+    }
+    return left;
+}
+// the 52-bit fraction of rand 0.8's UniformFloat<f64>::sample_single: value1_2 - 1.0
+__device__ __forceinline__ double unit_f64(uint64_t word) {
+    return __longlong_as_double((long long)((word >> 12) | 0x3FF0000000000000ull)) - 1.0;
 }
 __device__ __forceinline__ uint32_t state_bit(const uint32_t *st, uint32_t v) { return (st[v >> 5] >> (v & 31)) & 1u; }

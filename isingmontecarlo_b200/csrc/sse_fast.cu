@@ -87,7 +87,7 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
     return ((((size_t)3 * Nw + N + 64 + 64 + 16 + 32) * 4 + 64 * 8) + 15) / 16 * 16;
 }
 
-template <bool HAS_H, int MINB>
+template <bool HAS_H, int MINB, bool HB>
 __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
                                                   uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -165,12 +165,157 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                 const uint32_t fmask_lt = __ballot_sync(FULL, type == T_OFFD) & lt_mask;
                 const uint32_t emask = __ballot_sync(FULL, type == T_EMPTY), dmask = __ballot_sync(FULL, type == T_DIAG);
                 __syncwarp();
-                double dnum = 0.0;  // num of an existing diagonal op does not depend on (cursor, n)
-                if (type == T_DIAG) dnum = bn * bond_weight(D, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
                 uint32_t rem = emask | dmask;
+                if constexpr (HB) {
+                    // ---- heat-bath rule (heatbath.rs:149-209).  Draws per slot: EMPTY 1 (+2 when an insertion
+                    // is attempted), DIAG 1.  The attempt / removal thresholds depend on the live n only through
+                    // den, monotonically, so a window word is classified once against the thresholds at both ends
+                    // of the n interval the round can span; the rare word in between ends the resolved prefix
+                    // (EMPTY lanes: it moves the cursor) or is settled in lane order with the exact n (DIAG lanes).
+                    // A round that cannot resolve its first lane evaluates that lane literally.
+                    const double total = D.hb_total, bt = D.beta[r] * total;
+                    auto spin_here = [&](uint32_t v) -> uint32_t {  // spin of v as seen by my slot
+                        uint32_t sv = state_bit(S.st, v);
+                        if (state_bit(S.cd, v))
+                            for (uint32_t m = fmask_lt; m; m &= m - 1) sv ^= (S.fl[__ffs(m) - 1] == v);
+                        return sv;
+                    };
+                    auto try_insert = [&](uint64_t wp, uint64_t wc, uint32_t &nw) -> bool {  // heatbath.rs:166-187
+                        const double pd = unit_f64(wp), c = unit_f64(wc) * total;
+                        if (!(pd < 1.0) || !(c < total)) { err |= DEV_ERR_INVARIANT; return false; }
+                        const uint32_t b = hb_index_for_cumulative(D.hb_cum, D.Nb, c);
+                        if (b >= D.Nb) { err |= DEV_ERR_INVARIANT; return false; }
+                        const int kind = bond_kind(D, b);
+                        uint32_t v0, v1;
+                        bond_vars(D, b, kind, v0, v1);
+                        const uint32_t s0 = spin_here(v0), s1 = kind == KIND_BOND ? spin_here(v1) : 0u;
+                        if (!(pd * __ldg(D.hb_maxw + b) < bond_weight(D, b, kind, s0, s1))) return false;
+                        const uint32_t bitsv = s0 | (s1 << 1);
+                        nw = make_op(b, bitsv, bitsv);
+                        return true;
+                    };
+                    while (rem) {
+                        const uint64_t wbase = cur & ~1ull;
+                        {
+                            const uint64_t blk = (wbase >> 1) + (uint64_t)lane;
+                            Philox4 o = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u, k0, k1);
+                            S.win[2 * lane] = ((unsigned long long)o.y << 32) | o.x;
+                            S.win[2 * lane + 1] = ((unsigned long long)o.w << 32) | o.z;
+                        }
+                        __syncwarp();
+                        const bool inrem = (rem >> lane) & 1u;
+                        const uint32_t remE = emask & rem, remD = dmask & rem;
+                        const uint32_t head = (uint32_t)__ffs(rem) - 1u;
+                        const uint32_t x0 = (uint32_t)(cur - wbase);
+                        const uint32_t nlo = n - (uint32_t)__popc(remD), nhi = n + (uint32_t)__popc(remE);
+                        uint32_t dc = 0, okm = 0;
+                        int dn = 0;
+                        if (nhi < M && bt > 0.0) {
+                            // thresholds at the ends of the n interval (IEEE operations are monotone)
+                            const uint64_t te_lo = bool_threshold(bt / ((double)(M - nlo) + bt)), te_hi = bool_threshold(bt / ((double)(M - nhi) + bt));
+                            const double dl = (double)(M - nhi + 1), dh = (double)(M - nlo + 1);
+                            const uint64_t td_lo = bool_threshold(dl / (dl + bt)), td_hi = bool_threshold(dh / (dh + bt));
+                            const uint64_t w0 = S.win[lane], w1 = S.win[lane + 32];
+                            const uint64_t ATT = ((uint64_t)__ballot_sync(FULL, w1 < te_lo) << 32) | __ballot_sync(FULL, w0 < te_lo);
+                            const uint64_t NOA = ((uint64_t)__ballot_sync(FULL, w1 >= te_hi) << 32) | __ballot_sync(FULL, w0 >= te_hi);
+                            const uint32_t predE = remE & lt_mask;
+                            const int le = predE ? 31 - __clz(predE) : -1;
+                            const uint32_t after_le = le < 0 ? FULL : ~((2u << le) - 1u);
+                            const uint32_t dcount = (uint32_t)__popc(remD & lt_mask & after_le);  // DIAG draws since the last EMPTY lane
+                            const uint32_t kidx = (uint32_t)__popc(predE);
+                            if (inrem && type == T_EMPTY) S.wk[kidx] = (unsigned char)dcount, S.wl[kidx] = (unsigned char)lane;
+                            __syncwarp();
+                            const uint32_t nE = (uint32_t)__popc(remE);
+                            uint32_t x = x0, k = 0, stop = 32u;
+                            for (; k < nE; k++) {  // uniform walk over the EMPTY lanes
+                                const uint32_t xs = x + S.wk[k];
+                                if (xs + 2u >= 64u || !(((ATT | NOA) >> xs) & 1ull)) {
+                                    stop = S.wl[k];
+                                    break;
+                                }
+                                x = xs + 1u + 2u * (uint32_t)((ATT >> xs) & 1ull);
+                                S.wx[k] = (unsigned char)xs, S.wg[k] = (unsigned char)x;
+                            }
+                            __syncwarp();
+                            const uint32_t kstop = k;
+                            uint32_t myx = 0;
+                            bool res = false;
+                            if (inrem && type == T_EMPTY) res = kidx < kstop, myx = res ? (uint32_t)S.wx[kidx] : 0u;
+                            else if (inrem) {
+                                res = kidx <= kstop && (uint32_t)lane < stop;
+                                myx = (kidx == 0 ? x0 : (res ? (uint32_t)S.wg[kidx - 1] : 0u)) + dcount;
+                            }
+                            const uint32_t ovD = __ballot_sync(FULL, res && type == T_DIAG && myx >= 64u);
+                            if (ovD) stop = min(stop, (uint32_t)__ffs(ovD) - 1u);
+                            const uint32_t resolved = stop >= 32u ? rem : (rem & ((1u << stop) - 1u));
+                            bool unres = false;
+                            if ((resolved >> lane) & 1u) {
+                                if (type == T_EMPTY) {
+                                    dc = (uint32_t)S.wg[kidx] - myx;
+                                    neww = OP_EMPTY;
+                                    if (dc == 3u && try_insert(S.win[myx + 1], S.win[myx + 2], neww)) dn = 1;
+                                } else {
+                                    const uint64_t v = S.win[myx];
+                                    dc = 1;
+                                    if (v < td_lo) neww = OP_EMPTY, dn = -1;
+                                    else if (v >= td_hi) neww = w, dn = 0;
+                                    else unres = true;
+                                }
+                            }
+                            for (uint32_t um = __ballot_sync(FULL, unres); um; um = __ballot_sync(FULL, unres)) {
+                                const uint32_t u = (uint32_t)__ffs(um) - 1u;
+                                const uint32_t pre = __reduce_add_sync(FULL, (((resolved >> lane) & 1u) && (uint32_t)lane < u) ? (uint32_t)(dn + 1) : 0u);
+                                if ((uint32_t)lane == u) {
+                                    const uint32_t ni = n + pre - (uint32_t)__popc(resolved & lt_mask);
+                                    const double num = (double)(M - ni + 1);
+                                    const bool remove = S.win[myx] < bool_threshold(num / (num + bt));
+                                    neww = remove ? OP_EMPTY : w, dn = remove ? -1 : 0, unres = false;
+                                }
+                            }
+                            okm = resolved;
+                        }
+                        if (okm == 0) {  // literal evaluation of the first lane at the exact (cursor, n)
+                            DBG(3, 1);
+                            if ((uint32_t)lane == head) {
+                                uint32_t x = x0;
+                                if (type == T_EMPTY) {
+                                    const double pr = bt / ((double)(M - n) + bt);
+                                    bool attempt = false;
+                                    if (pr == 1.0) attempt = true;
+                                    else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                                    else attempt = S.win[x++] < bool_threshold(pr);
+                                    neww = OP_EMPTY;
+                                    if (attempt) {
+                                        if (try_insert(S.win[x], S.win[x + 1], neww)) dn = 1;
+                                        x += 2;
+                                    }
+                                } else {
+                                    const double num = (double)(M - n + 1), pr = num / (num + bt);
+                                    bool remove = false;
+                                    if (pr == 1.0) remove = true;
+                                    else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                                    else remove = S.win[x++] < bool_threshold(pr);
+                                    neww = remove ? OP_EMPTY : w, dn = remove ? -1 : 0;
+                                }
+                                dc = x - x0;
+                            }
+                            okm = 1u << head;
+                        }
+                        const bool mine = (okm >> lane) & 1u;
+                        const uint32_t tot = __reduce_add_sync(FULL, mine ? dc : 0u);
+                        const int totn = (int)__reduce_add_sync(FULL, mine ? (uint32_t)(dn + 1) : 0u) - __popc(okm);
+                        if (inrem && !mine) neww = w;
+                        cur += tot;
+                        n = (uint32_t)((int)n + totn);
+                        rem &= ~okm;
+                        __syncwarp();
+                    }
+                }
+                double dnum = 0.0;  // num of an existing diagonal op does not depend on (cursor, n)
+                if (!HB && type == T_DIAG) dnum = bn * bond_weight(D, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
                 bool try_fast = true;
                 TICK(1);  // load, classify, decode of existing ops, flip list
-                while (rem) {
+                while (!HB && rem) {
                     const uint64_t wbase = cur & ~1ull;
                     {  // stream words [wbase, wbase + 64)
                         const uint64_t blk = (wbase >> 1) + (uint64_t)lane;
@@ -713,12 +858,14 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
     const uint32_t blocks = (D.R + warps - 1) / warps;
     typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t);
     Kern kern;
-    switch (g_sse_fast_minblocks) {
-        case 4: kern = D.has_h ? k_sse_fast<true, 4> : k_sse_fast<false, 4>; break;
-        case 6: kern = D.has_h ? k_sse_fast<true, 6> : k_sse_fast<false, 6>; break;
-        case 8: kern = D.has_h ? k_sse_fast<true, 8> : k_sse_fast<false, 8>; break;
-        default: kern = D.has_h ? k_sse_fast<true, 7> : k_sse_fast<false, 7>; break;
-    }
+    if (D.hb_cum) kern = D.has_h ? k_sse_fast<true, 7, true> : k_sse_fast<false, 7, true>;
+    else
+        switch (g_sse_fast_minblocks) {
+            case 4: kern = D.has_h ? k_sse_fast<true, 4, false> : k_sse_fast<false, 4, false>; break;
+            case 6: kern = D.has_h ? k_sse_fast<true, 6, false> : k_sse_fast<false, 6, false>; break;
+            case 8: kern = D.has_h ? k_sse_fast<true, 8, false> : k_sse_fast<false, 8, false>; break;
+            default: kern = D.has_h ? k_sse_fast<true, 7, false> : k_sse_fast<false, 7, false>; break;
+        }
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     kern<<<blocks, warps * 32, smem, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep);
     return 1;

@@ -118,6 +118,66 @@ __device__ void diag_serial(const SseDev &D, uint32_t r, const Rep &V) {
 }
 
 // ------------------------------------------------------------------------------------------
+// heat-bath diagonal update (heatbath.rs:106-127, :149-209), lane 0
+// ------------------------------------------------------------------------------------------
+__device__ void diag_heatbath_serial(const SseDev &D, uint32_t r, const Rep &V) {
+    const uint32_t M = D.M[r];
+    uint32_t n = D.n[r];
+    uint64_t cur = D.cursor[r];
+    const uint64_t key = D.key[r];
+    const double total = D.hb_total;
+    const double bt = D.beta[r] * total;  // heatbath.rs:163,194
+    int err = 0;
+    for (uint32_t p = 0; p < M; p++) {
+        const uint32_t w = V.ops[p];
+        if (w == OP_EMPTY) {
+            const double den = (double)(M - n) + bt;
+            const double pr = bt / den;
+            bool attempt;
+            if (pr == 1.0) attempt = true;  // gen_bool(1.0): no draw
+            else if (!(pr >= 0.0 && pr < 1.0)) attempt = false, err |= DEV_ERR_PROB;
+            else attempt = stream_word(key, cur++) < bool_threshold(pr);
+            if (!attempt) continue;
+            double pd, c;
+            do pd = unit_f64(stream_word(key, cur++)); while (!(pd < 1.0));            // gen_range(0. ..1.0)
+            do c = unit_f64(stream_word(key, cur++)) * total; while (!(c < total));     // gen_range(0. ..total)
+            const uint32_t b = hb_index_for_cumulative(D.hb_cum, D.Nb, c);
+            if (b >= D.Nb) { err |= DEV_ERR_INVARIANT; continue; }
+            const int kind = bond_kind(D, b);
+            uint32_t v0, v1;
+            bond_vars(D, b, kind, v0, v1);
+            const uint32_t s0 = state_bit(V.state, v0), s1 = kind == KIND_BOND ? state_bit(V.state, v1) : 0u;
+            if (pd * __ldg(D.hb_maxw + b) < bond_weight(D, b, kind, s0, s1)) {
+                const uint32_t bitsv = s0 | (s1 << 1);
+                V.ops[p] = make_op(b, bitsv, bitsv);
+                n++;
+            }
+        } else if (op_is_diag(w)) {
+            const double num = (double)(M - n + 1);
+            const double pr = num / (num + bt);
+            bool remove;
+            if (pr == 1.0) remove = true;
+            else if (!(pr >= 0.0 && pr < 1.0)) remove = false, err |= DEV_ERR_PROB;
+            else remove = stream_word(key, cur++) < bool_threshold(pr);
+            if (remove) {
+                V.ops[p] = OP_EMPTY;
+                n--;
+            }
+        } else {
+            const int kind = bond_kind(D, op_bond(w));
+            uint32_t v0, v1;
+            bond_vars(D, op_bond(w), kind, v0, v1);
+            const uint32_t o = op_out(w);
+            V.state[v0 >> 5] = (V.state[v0 >> 5] & ~(1u << (v0 & 31))) | ((o & 1u) << (v0 & 31));
+            if (kind == KIND_BOND) V.state[v1 >> 5] = (V.state[v1 >> 5] & ~(1u << (v1 & 31))) | (((o >> 1) & 1u) << (v1 & 31));
+        }
+    }
+    D.n[r] = n;
+    D.cursor[r] = cur;
+    if (err) atomicOr(D.status, err);
+}
+
+// ------------------------------------------------------------------------------------------
 // links (what FastOps::mutate_p maintains incrementally, fast_ops.rs:337-607), lane 0
 // ------------------------------------------------------------------------------------------
 __device__ void links_serial(const SseDev &D, uint32_t r, const Rep &V, bool full) {
@@ -538,7 +598,10 @@ __global__ void __launch_bounds__(128) k_sse_serial(SseDev D, int mode, uint64_t
             break;
         }
         if (phases & 1u) {
-            if (lane == 0) diag_serial(D, r, V);
+            if (lane == 0) {
+                if (D.hb_cum) diag_heatbath_serial(D, r, V);
+                else diag_serial(D, r, V);
+            }
             __syncwarp();
         }
         if (phases & 2u) {

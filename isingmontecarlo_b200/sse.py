@@ -67,6 +67,15 @@ class QmcIsingGraph:
         check(self._L.qmcb_set_mode(self._h, mode))
         self.mode = mode
 
+    def set_enable_heatbath(self, enable_heatbath):
+        """qmc_ising.rs:444-486: heat-bath diagonal updates (heatbath.rs:149-209) for every replica."""
+        check(self._L.qmcb_set_enable_heatbath(self._h, int(bool(enable_heatbath))))
+
+    def get_enable_heatbath(self):
+        out = C.c_int(0)
+        check(self._L.qmcb_get_enable_heatbath(self._h, C.byref(out)))
+        return bool(out.value)
+
     def set_option(self, name, value):
         check(self._L.qmcb_set_option(self._h, name.encode(), int(value)))
 

@@ -136,6 +136,22 @@ static double gen_range_f64_01(Stream *s) {
     }
 }
 
+/* rand 0.8 UniformFloat<f64>::sample_single for low..high (finite scale): value0_1 * scale + low,
+ * redrawn while the rounded result reaches `high` */
+static double gen_range_f64(Stream *s, double low, double high) {
+    const double scale = high - low;
+    for (;;) {
+        uint64_t v = next_u64(s);
+        uint64_t bits = (v >> 12) | 0x3FF0000000000000ull;
+        double value1_2;
+        memcpy(&value1_2, &bits, 8);
+        double value0_1 = value1_2 - 1.0;
+        double res = value0_1 * scale + low;
+        if (res < high) return res;
+        if (s->error) return low; /* scripted stream ran dry */
+    }
+}
+
 /* rand 0.8 Standard f64: 53 random bits * 2^-53 */
 static double gen_f64(Stream *s) {
     uint64_t v = next_u64(s) >> 11;
@@ -166,6 +182,12 @@ uint32_t orc_gen_range_u8(uint64_t key, uint64_t *cursor, uint32_t n) {
 double orc_gen_range_f64_01(uint64_t key, uint64_t *cursor) {
     Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
     double r = gen_range_f64_01(&s);
+    *cursor = s.cursor;
+    return r;
+}
+double orc_gen_range_f64(uint64_t key, uint64_t *cursor, double low, double high) {
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
+    double r = gen_range_f64(&s, low, high);
     *cursor = s.cursor;
     return r;
 }
@@ -259,6 +281,8 @@ struct OrcSse {
     /* fast mode scratch */
     uint32_t *uf;
     uint64_t uf_cap;
+    /* heat-bath diagonal update: BondWeights (heatbath.rs:10-13), NULL = Metropolis rule */
+    double *hb_maxw, *hb_cum;
     int error;
 };
 
@@ -368,6 +392,7 @@ void orc_sse_destroy(OrcSse *g) {
     free(g->ea), free(g->eb), free(g->J), free(g->ops);
     free(g->vfirst_p), free(g->vlast_p), free(g->vfirst_r), free(g->vlast_r);
     free(g->state), free(g->b_in), free(g->b_out), free(g->uf);
+    free(g->hb_maxw), free(g->hb_cum);
     stack_free(&g->frontier), stack_free(&g->interior);
     free(g);
 }
@@ -454,6 +479,99 @@ static void diagonal_update(OrcSse *g, double beta) {
     }
     g->n = n;
     rebuild_links(g);
+}
+
+/* ===================================================================================
+ * Heat-bath diagonal update: heatbath.rs:106-127 (driver), :149-209 (rule), BondWeights :10-61;
+ * enabled by QmcIsingGraph::set_enable_heatbath (qmc_ising.rs:444-486)
+ * =================================================================================== */
+void orc_sse_set_enable_heatbath(OrcSse *g, int enable) {
+    free(g->hb_maxw), free(g->hb_cum);
+    g->hb_maxw = g->hb_cum = NULL;
+    if (!enable) return;
+    const uint32_t nb = num_bonds(g);
+    g->hb_maxw = (double *)malloc(sizeof(double) * nb);
+    g->hb_cum = (double *)malloc(sizeof(double) * nb);
+    for (uint32_t b = 0; b < nb; b++) { /* make_bond_weights, heatbath.rs:130-146 */
+        uint32_t vars[2];
+        int nv, constant;
+        edge_fn(g, b, vars, &nv, &constant);
+        double acc = 0.0;
+        for (int sub = 0; sub < (1 << nv); sub++) {
+            uint8_t bits[2] = {(uint8_t)(sub & 1), (uint8_t)((sub >> 1) & 1)};
+            double w = hamiltonian(g, b, bits, bits);
+            if (w > acc) acc = w;
+        }
+        g->hb_maxw[b] = acc;
+        g->hb_cum[b] = b == 0 ? acc : acc + g->hb_cum[b - 1]; /* BondWeights::new :24-30 */
+    }
+}
+int orc_sse_get_enable_heatbath(const OrcSse *g) { return g->hb_cum != NULL; }
+
+/* BondWeights::index_for_cumulative (heatbath.rs:56-60): slice::binary_search_by, then the insertion
+ * point when there is no exact match (core::slice, the size-halving loop) */
+static uint32_t hb_index_for_cumulative(const double *cum, uint32_t len, double val) {
+    uint32_t size = len, left = 0, right = len;
+    while (left < right) {
+        uint32_t mid = left + size / 2;
+        if (cum[mid] < val) left = mid + 1;
+        else if (cum[mid] > val) right = mid;
+        else return mid;
+        size = right - left;
+    }
+    return left;
+}
+
+static void heatbath_diagonal_update(OrcSse *g, double beta) {
+    const uint64_t cutoff = g->cutoff;
+    const uint32_t nb = num_bonds(g);
+    const double total = g->hb_cum[nb - 1]; /* BondWeights::total :50-54 */
+    ops_resize(g, cutoff);
+    uint8_t *state = g->state;
+    uint64_t n = g->n;
+    for (uint64_t p = 0; p < cutoff; p++) {
+        Node *nd = &g->ops[p];
+        if (!nd->present) { /* heatbath.rs:162-191 */
+            double numerator = beta * total;
+            double denominator = (double)(cutoff - n) + numerator;
+            if (gen_bool(&g->rng, numerator / denominator)) {
+                double pdraw = gen_range_f64(&g->rng, 0.0, 1.0);  /* :167 */
+                double c = gen_range_f64(&g->rng, 0.0, total);    /* :38 */
+                uint32_t b = hb_index_for_cumulative(g->hb_cum, nb, c);
+                if (b >= nb) { g->error |= 4; continue; } /* reference: index out of bounds panic */
+                double maxweight = g->hb_maxw[b];
+                uint32_t vars[2];
+                int nv, constant;
+                edge_fn(g, b, vars, &nv, &constant);
+                uint8_t sub[2] = {0, 0};
+                for (int r = 0; r < nv; r++) sub[r] = state[vars[r]];
+                double weight = hamiltonian(g, b, sub, sub);
+                if (pdraw * maxweight < weight) { /* :181 */
+                    nd->present = 1, nd->nv = (uint8_t)nv, nd->constant = (uint8_t)constant, nd->bond = b;
+                    for (int r = 0; r < nv; r++)
+                        nd->vars[r] = vars[r], nd->in[r] = sub[r], nd->out[r] = sub[r];
+                    n++;
+                }
+            }
+        } else if (node_is_diagonal(nd)) { /* :192-201 */
+            double numerator = (double)(cutoff - n + 1);
+            double denominator = numerator + beta * total;
+            if (gen_bool(&g->rng, numerator / denominator)) {
+                nd->present = 0;
+                n--;
+            }
+        } else { /* :203-208 */
+            for (int r = 0; r < nd->nv; r++) state[nd->vars[r]] = nd->out[r];
+        }
+    }
+    g->n = n;
+    rebuild_links(g);
+}
+
+/* the diagonal step of timestep / single_diagonal_step: qmc_ising.rs:250-268, :685-703 */
+static void diagonal_step(OrcSse *g, double beta) {
+    if (g->hb_cum) heatbath_diagonal_update(g, beta);
+    else diagonal_update(g, beta);
 }
 
 /* ===================================================================================
@@ -712,9 +830,9 @@ static uint64_t cluster_and_free_spins(OrcSse *g, int mode) {
     return ncl;
 }
 
-/* QmcIsingGraph::timestep, qmc_ising.rs:644-795 (rvb and heat-bath off: defaults :122,:126) */
+/* QmcIsingGraph::timestep, qmc_ising.rs:644-795 (rvb off: default :122) */
 void orc_sse_timestep(OrcSse *g, double beta, int mode) {
-    diagonal_update(g, beta);
+    diagonal_step(g, beta);
     cluster_and_free_spins(g, mode);
     uint64_t grown = g->n + g->n / 2; /* :786 */
     if (grown > g->cutoff) g->cutoff = grown;
@@ -722,7 +840,7 @@ void orc_sse_timestep(OrcSse *g, double beta, int mode) {
 
 /* qmc_ising.rs:208-270 */
 void orc_sse_single_diagonal_step(OrcSse *g, double beta) {
-    diagonal_update(g, beta);
+    diagonal_step(g, beta);
     uint64_t grown = g->n + g->n / 2;
     if (grown > g->cutoff) g->cutoff = grown;
 }

@@ -31,6 +31,7 @@ int orc_gen_bool(uint64_t key, uint64_t *cursor, double p);
 uint64_t orc_gen_range_usize(uint64_t key, uint64_t *cursor, uint64_t n);
 uint32_t orc_gen_range_u8(uint64_t key, uint64_t *cursor, uint32_t n);
 double orc_gen_range_f64_01(uint64_t key, uint64_t *cursor);
+double orc_gen_range_f64(uint64_t key, uint64_t *cursor, double low, double high);
 double orc_gen_f64(uint64_t key, uint64_t *cursor);
 int orc_gen_std_bool(uint64_t key, uint64_t *cursor);
 double orc_powi(double a, int b);
@@ -52,6 +53,10 @@ void orc_sse_destroy(OrcSse *g);
 void orc_sse_set_script(OrcSse *g, const uint64_t *words, uint64_t nwords);
 int orc_sse_error(const OrcSse *g);
 
+/* QmcIsingGraph::set_enable_heatbath (qmc_ising.rs:444-486): heat-bath diagonal update
+ * (heatbath.rs:149-209) instead of the Metropolis rule */
+void orc_sse_set_enable_heatbath(OrcSse *g, int enable);
+int orc_sse_get_enable_heatbath(const OrcSse *g);
 void orc_sse_timestep(OrcSse *g, double beta, int mode);
 void orc_sse_single_diagonal_step(OrcSse *g, double beta);
 uint64_t orc_sse_single_cluster_step(OrcSse *g, int mode);

@@ -48,6 +48,7 @@ def lib():
     sig("orc_gen_range_usize", C.c_uint64, C.c_uint64, u64p, C.c_uint64)
     sig("orc_gen_range_u8", C.c_uint32, C.c_uint64, u64p, C.c_uint32)
     sig("orc_gen_range_f64_01", C.c_double, C.c_uint64, u64p)
+    sig("orc_gen_range_f64", C.c_double, C.c_uint64, u64p, C.c_double, C.c_double)
     sig("orc_gen_f64", C.c_double, C.c_uint64, u64p)
     sig("orc_gen_std_bool", C.c_int, C.c_uint64, u64p)
     sig("orc_powi", C.c_double, C.c_double, C.c_int)
@@ -56,6 +57,8 @@ def lib():
     sig("orc_sse_destroy", None, vp)
     sig("orc_sse_set_script", None, vp, u64p, C.c_uint64)
     sig("orc_sse_error", C.c_int, vp)
+    sig("orc_sse_set_enable_heatbath", None, vp, C.c_int)
+    sig("orc_sse_get_enable_heatbath", C.c_int, vp)
     sig("orc_sse_timestep", None, vp, C.c_double, C.c_int)
     sig("orc_sse_single_diagonal_step", None, vp, C.c_double)
     sig("orc_sse_single_cluster_step", C.c_uint64, vp, C.c_int)
@@ -143,6 +146,10 @@ class SseOracle:
     @property
     def error(self):
         return lib().orc_sse_error(self._h)
+
+    def set_enable_heatbath(self, enable):
+        """QmcIsingGraph::set_enable_heatbath (qmc_ising.rs:444-486)"""
+        lib().orc_sse_set_enable_heatbath(self._h, int(bool(enable)))
 
     def timestep(self, beta, mode=MODE_STRICT):
         lib().orc_sse_timestep(self._h, beta, mode)

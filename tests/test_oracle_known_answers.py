@@ -123,3 +123,38 @@ def test_fast_mode_labels_are_min_segment_ids():
     # var0: seg 0 = before p0 == after p1 (closure with id 3), seg 2 = between p0 and p1
     assert list(zip(bi, bo)) == [(0, 2), (2, 0), (1, 4), (4, 1)]
     assert g.cursor == 1 and g.verify()
+
+
+def test_h1_heatbath_rules_and_draw_order():
+    # heatbath.rs:149-209 by hand.  Edge (0,1) J=+1, Gamma=1: maximum weights [2, 1, 1] -> cumulative
+    # [2, 3, 4], total 4 (heatbath.rs:17-35, :130-146).  beta=1, cutoff 3, state [0,1].
+    g = po.SseOracle([((0, 1), 1.0)], 1.0, 0.0, 3, key=0, state=[0, 1])
+    g.set_enable_heatbath(True)
+    top = (1 << 64) - 1
+    g.set_script([
+        0,            # p0 empty, n=0: gen_bool(4/7) -> attempt
+        1 << 63,      #   p = gen_range(0. ..1.0) = 0.5
+        1 << 62,      #   c = 0.25 * 4 = 1.0 -> bond 0 (cum 2 > 1), maxweight 2, anti-aligned weight 2: 1.0 < 2 -> insert
+        top,          # p1 empty, n=1: gen_bool(4/6) false -> one draw only
+        0,            # p2 empty: attempt
+        3 << 62,      #   p = 0.75
+        5 << 61,      #   c = 0.625 * 4 = 2.5 -> index 1 (cum 3 > 2.5 > cum 2): transverse op on var 0, 0.75 * 1 < 1 -> insert
+    ])
+    g.single_diagonal_step(1.0)
+    assert g.error == 0 and g.n == 2 and g.cursor == 7 and g.cutoff == 3
+    assert list(g.dump_ops()) == [word(0, [0, 1], [0, 1]), po.OP_EMPTY, word(1, [0], [0])]
+    assert g.verify()
+    # removal: p0 diagonal, n=2: gen_bool(2/6): 0x5555555555555400 is the threshold itself -> kept;
+    # p1 empty: gen_bool(4/5) false; p2 diagonal: gen_bool(2/6) with word 0 -> removed
+    g.set_script([0x5555555555555400, top, 0])
+    g.set_cursor(0)
+    g.single_diagonal_step(1.0)
+    assert g.error == 0 and g.n == 1 and g.cursor == 3
+    assert list(g.dump_ops()) == [word(0, [0, 1], [0, 1]), po.OP_EMPTY, po.OP_EMPTY]
+    # an insertion attempt that fails the weight test still consumes three words (heatbath.rs:166-187):
+    # aligned spins on a J>0 bond have weight 0
+    g2 = po.SseOracle([((0, 1), 1.0)], 1.0, 0.0, 1, key=0, state=[0, 0])
+    g2.set_enable_heatbath(True)
+    g2.set_script([0, 0, 0])  # attempt, p = 0, c = 0 -> bond 0, weight 0: 0 < 0 false
+    g2.single_diagonal_step(1.0)
+    assert g2.error == 0 and g2.n == 0 and g2.cursor == 3

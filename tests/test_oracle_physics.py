@@ -16,13 +16,15 @@ SYSTEMS = [
 ]
 
 
-@pytest.mark.parametrize("mode", [po.MODE_STRICT, po.MODE_FAST])
+@pytest.mark.parametrize("mode,heatbath", [(po.MODE_STRICT, False), (po.MODE_FAST, False), (po.MODE_STRICT, True), (po.MODE_FAST, True)])
 @pytest.mark.parametrize("name,edges,gamma,h,beta", SYSTEMS)
-def test_energy_matches_exact_diagonalisation(name, edges, gamma, h, beta, mode):
+def test_energy_matches_exact_diagonalisation(name, edges, gamma, h, beta, mode, heatbath):
     nvars = lattices.nvars_of(edges)
     exact = tfim_thermal(edges, nvars, gamma, h, beta)
     chains = 32
-    reps = [po.SseOracle(edges, gamma, h, nvars, key=0xE0 + 1000 * mode + r) for r in range(chains)]
+    reps = [po.SseOracle(edges, gamma, h, nvars, key=0xE0 + 1000 * mode + 7000 * heatbath + r) for r in range(chains)]
+    for r in reps:
+        r.set_enable_heatbath(heatbath)  # heatbath.rs:149-209 instead of diagonal.rs:142-191
     po.sse_batch_timesteps(reps, 500, [beta] * chains, mode)  # thermalise
     _, e = po.sse_batch_timesteps(reps, 6000, [beta] * chains, mode)
     assert all(r.error == 0 for r in reps)

@@ -123,3 +123,20 @@ def test_powi_is_compiler_rt_square_and_multiply():
     for a in (0.5, 0.9375, 1.0625, 16.0 / 15.5, 0.999):
         for b in (0, 1, -1, 2, 3, -7, 100, -1234, 5000):
             assert L.orc_powi(a, b) == powidf2(a, b)
+
+
+def test_gen_range_f64_general():
+    # UniformFloat<f64>::sample_single: (52-bit fraction) * (high - low) + low, one word
+    L = po.lib()
+    import ctypes as C
+    for w, lo, hi, want in [(1 << 62, 0.0, 4.0, 1.0), (5 << 61, 0.0, 4.0, 2.5), (1 << 63, 1.0, 3.0, 2.0)]:
+        key, cur = 12345, C.c_uint64(0)
+        # find the value through the scripted path instead: use the unit fraction identity
+        frac = ((w >> 12) / float(1 << 52))
+        assert frac * (hi - lo) + lo == want
+    cur = C.c_uint64(7)
+    x = L.orc_gen_range_f64(99, C.byref(cur), 0.0, 7209.92)
+    assert cur.value == 8 and 0.0 <= x < 7209.92
+    cur2 = C.c_uint64(7)
+    u = L.orc_gen_range_f64_01(99, C.byref(cur2))
+    assert x == u * 7209.92
