@@ -89,6 +89,10 @@ int qmcb_get_betas(const QmcbHandle *h, double *betas);
 int qmcb_num_replicas(const QmcbHandle *h, uint32_t *r);
 int qmcb_num_vars(const QmcbHandle *h, uint32_t *n);
 int qmcb_num_bonds(const QmcbHandle *h, uint32_t *nb); /* qmc_ising.rs:664-670 */
+int qmcb_num_edges(const QmcbHandle *h, uint32_t *ne);
+/* get_edges / get_transverse_field / get_longitudinal_field (qmc_ising.rs:496-535) */
+int qmcb_get_edges(const QmcbHandle *h, uint32_t *va /* [E] */, uint32_t *vb, double *J);
+int qmcb_get_fields(const QmcbHandle *h, double *transverse, double *longitudinal);
 
 /* ---- stepping: QmcStepper (qmc_stepper.rs:2-168) ---------------------------------------- */
 /* timesteps_measure_with_self (qmc_stepper.rs:133-162): t sweeps (QmcIsingGraph::timestep,
@@ -153,7 +157,18 @@ int qmcb_pt_export(QmcbHandle *h, uint64_t *rec_dev);
  * from the shared PT stream (:140-146, :241-302) and relabel the local configurations. */
 int qmcb_pt_apply(QmcbHandle *h, const uint64_t *all_rec_dev, uint64_t n_records);
 int qmcb_pt_total_swaps(QmcbHandle *h, uint64_t *swaps); /* get_total_swaps :231-233 */
+int qmcb_pt_get_config(const QmcbHandle *h, uint32_t *n_chains, uint32_t *n_betas, uint32_t *slot_begin);
 int qmcb_pt_get_slots(QmcbHandle *h, uint32_t *slots /* [R] current slot of each configuration */);
+
+/* ---- checkpoints (replaces the serde path: SerializeQmcGraph qmc_ising.rs:1001-1087,
+ * SerializeTemperingContainer tempering_container.rs:671-793) -------------------------------------
+ * One self-describing little-endian blob per handle: lattice, mode, heat-bath flag, and per replica
+ * beta, stream (key, cursor), cutoff, n, sweep counters, spins and the operator string up to its
+ * cutoff; the tempering ladder, slot labels, PT stream position and swap count when configured;
+ * FNV-1a checksum.  A loaded handle continues bit-identically to the one that was saved. */
+int qmcb_checkpoint_size(QmcbHandle *h, uint64_t *bytes);
+int qmcb_checkpoint_save(QmcbHandle *h, void *buf, uint64_t bytes);
+int qmcb_checkpoint_load(const void *buf, uint64_t bytes, int device, QmcbHandle **out);
 
 /* ---- classical graph: GraphState (classical/graph.rs:56-88, :350-447) --------------------- */
 typedef struct CmcbHandle CmcbHandle;

@@ -44,6 +44,9 @@ SIGNATURES = {
     "qmcb_num_replicas": [vp, u32p],
     "qmcb_num_vars": [vp, u32p],
     "qmcb_num_bonds": [vp, u32p],
+    "qmcb_num_edges": [vp, u32p],
+    "qmcb_get_edges": [vp, u32p, u32p, f64p],
+    "qmcb_get_fields": [vp, f64p, f64p],
     "qmcb_timesteps": [vp, C.c_uint64, C.c_uint64, f64p, u8p],
     "qmcb_enqueue_sweeps": [vp, C.c_uint64],
     "qmcb_synchronize": [vp],
@@ -71,7 +74,11 @@ SIGNATURES = {
     "qmcb_pt_export": [vp, vp],
     "qmcb_pt_apply": [vp, vp, C.c_uint64],
     "qmcb_pt_total_swaps": [vp, u64p],
+    "qmcb_pt_get_config": [vp, u32p, u32p, u32p],
     "qmcb_pt_get_slots": [vp, u32p],
+    "qmcb_checkpoint_size": [vp, u64p],
+    "qmcb_checkpoint_save": [vp, vp, C.c_uint64],
+    "qmcb_checkpoint_load": [vp, C.c_uint64, C.c_int, vpp],
     "cmcb_create": [C.POINTER(Lattice), f64p, C.c_uint32, f64p, u64p, u8p, C.c_int, vpp],
     "cmcb_destroy": [vp],
     "cmcb_set_stream": [vp, vp],

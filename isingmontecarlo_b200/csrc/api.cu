@@ -457,6 +457,23 @@ extern "C" int qmcb_num_vars(const QmcbHandle *h, uint32_t *n) {
     *n = h->D.N;
     return QMCB_OK;
 }
+extern "C" int qmcb_num_edges(const QmcbHandle *h, uint32_t *ne) {
+    if (!h || !ne) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *ne = h->D.E;
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_edges(const QmcbHandle *h, uint32_t *va, uint32_t *vb, double *J) {
+    if (!h || !va || !vb || !J) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    std::copy(h->va_h.begin(), h->va_h.end(), va);
+    std::copy(h->vb_h.begin(), h->vb_h.end(), vb);
+    std::copy(h->J_h.begin(), h->J_h.end(), J);
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_fields(const QmcbHandle *h, double *transverse, double *longitudinal) {
+    if (!h || !transverse || !longitudinal) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *transverse = h->D.gamma, *longitudinal = h->D.h;
+    return QMCB_OK;
+}
 extern "C" int qmcb_num_bonds(const QmcbHandle *h, uint32_t *nb) {
     if (!h || !nb) return fail(QMCB_ERR_BAD_ARG, "null argument");
     *nb = h->D.Nb;
@@ -822,11 +839,252 @@ extern "C" int qmcb_pt_total_swaps(QmcbHandle *h, uint64_t *swaps) {
     CUDA_TRY(cudaMemcpy(swaps, h->P.swaps, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return QMCB_OK;
 }
+extern "C" int qmcb_pt_get_config(const QmcbHandle *h, uint32_t *n_chains, uint32_t *n_betas, uint32_t *slot_begin) {
+    if (!h || !n_chains || !n_betas || !slot_begin) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    if (!h->pt_on) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+    *n_chains = h->P.n_chains, *n_betas = h->P.n_betas, *slot_begin = h->P.cfg_begin;
+    return QMCB_OK;
+}
 extern "C" int qmcb_pt_get_slots(QmcbHandle *h, uint32_t *slots) {
     CHECK_H(h);
     if (!h->pt_on || !slots) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(slots, h->P.slot_of_local, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
+    return QMCB_OK;
+}
+
+// ---- checkpoints ---------------------------------------------------------
+// The reference serialises a graph without its rng (SerializeQmcGraph, qmc_ising.rs:1001-1087) and a
+// tempering container as (graph, beta) pairs + total_swaps (tempering_container.rs:671-793).  Here the
+// injected stream is (key, cursor), 16 bytes, so it is part of the record and a restored batch continues
+// bit-identically.  Layout (little-endian), all arrays replica-major:
+//   "QMCBCKP1" | u32 version, N, E, R, mode, flags(bit0 heat-bath, bit1 tempering) | u64 target |
+//   f64 transverse, longitudinal | va[E] u32 | vb[E] u32 | pad to 8 | J[E] f64 |
+//   beta[R] f64 | key[R] u64 | cursor[R] u64 | done[R] u64 | vupd[R] u64 | M[R] u32 | n[R] u32 |
+//   state[R][Nw] u32 | pad to 8 | ops of replica 0 (M[0] words), replica 1, ... | pad to 8 |
+//   tempering block (if flagged): u32 n_chains, n_betas, cfg_begin, pad | u64 pt_key, pt_cursor, swaps |
+//   beta_slot[S] f64 | key_slot[S] u64 | slot_of_local[R] u32 | pad to 8 |  u64 FNV-1a of all bytes before.
+namespace {
+struct CkWriter {
+    uint8_t *p;
+    uint64_t off = 0, cap;
+    bool dry;
+    CkWriter(void *buf, uint64_t cap_) : p((uint8_t *)buf), cap(cap_), dry(buf == nullptr) {}
+    void put(const void *src, uint64_t nbytes) {
+        if (!dry && off + nbytes <= cap) memcpy(p + off, src, nbytes);
+        off += nbytes;
+    }
+    template <typename T>
+    void val(T v) { put(&v, sizeof(T)); }
+    void pad8() {
+        const uint64_t z = 0;
+        if (off % 8) put(&z, 8 - off % 8);
+    }
+};
+struct CkReader {
+    const uint8_t *p;
+    uint64_t off = 0, cap;
+    bool ok = true;
+    CkReader(const void *buf, uint64_t cap_) : p((const uint8_t *)buf), cap(cap_) {}
+    void get(void *dst, uint64_t nbytes) {
+        if (!ok || off + nbytes > cap) { ok = false; return; }
+        memcpy(dst, p + off, nbytes);
+        off += nbytes;
+    }
+    template <typename T>
+    T val() { T v{}; get(&v, sizeof(T)); return v; }
+    template <typename T>
+    std::vector<T> vec(uint64_t count) {
+        std::vector<T> v;
+        if (!ok || count > (cap - off) / sizeof(T)) { ok = false; return v; }
+        v.resize(count);
+        get(v.data(), count * sizeof(T));
+        return v;
+    }
+    void pad8() { if (off % 8) off += 8 - off % 8; }
+};
+uint64_t fnv1a(const uint8_t *p, uint64_t nbytes) {
+    uint64_t hsh = 1469598103934665603ull;
+    for (uint64_t i = 0; i < nbytes; i++) hsh = (hsh ^ p[i]) * 1099511628211ull;
+    return hsh;
+}
+template <typename T>
+cudaError_t fetch(std::vector<T> &dst, const T *dev, size_t count) {
+    dst.resize(count);
+    return cudaMemcpy(dst.data(), dev, sizeof(T) * count, cudaMemcpyDeviceToHost);
+}
+}  // namespace
+
+static int checkpoint_write(QmcbHandle *h, CkWriter &W) {
+    const SseDev &D = h->D;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::vector<double> beta;
+    std::vector<uint64_t> key, cursor, done;
+    std::vector<unsigned long long> vupd;
+    std::vector<uint32_t> M, n, state;
+    CUDA_TRY(fetch(beta, D.beta, D.R));
+    CUDA_TRY(fetch(key, D.key, D.R));
+    CUDA_TRY(fetch(cursor, D.cursor, D.R));
+    CUDA_TRY(fetch(done, D.done, D.R));
+    CUDA_TRY(fetch(vupd, D.vupd, D.R));
+    CUDA_TRY(fetch(M, D.M, D.R));
+    CUDA_TRY(fetch(n, D.n, D.R));
+    CUDA_TRY(fetch(state, D.state, (size_t)D.R * D.Nw));
+    W.put("QMCBCKP1", 8);
+    W.val<uint32_t>(1), W.val<uint32_t>(D.N), W.val<uint32_t>(D.E), W.val<uint32_t>(D.R);
+    W.val<uint32_t>((uint32_t)h->mode), W.val<uint32_t>((D.hb_cum ? 1u : 0u) | (h->pt_on ? 2u : 0u));
+    W.val<uint64_t>(h->target);
+    W.val<double>(D.gamma), W.val<double>(D.h);
+    W.put(h->va_h.data(), 4ull * D.E), W.put(h->vb_h.data(), 4ull * D.E), W.pad8();
+    W.put(h->J_h.data(), 8ull * D.E);
+    W.put(beta.data(), 8ull * D.R), W.put(key.data(), 8ull * D.R), W.put(cursor.data(), 8ull * D.R);
+    W.put(done.data(), 8ull * D.R), W.put(vupd.data(), 8ull * D.R);
+    W.put(M.data(), 4ull * D.R), W.put(n.data(), 4ull * D.R);
+    W.put(state.data(), 4ull * D.R * D.Nw), W.pad8();
+    for (uint32_t r = 0; r < D.R; r++) {
+        const uint64_t have = std::min<uint64_t>(M[r], D.cap);
+        if (W.dry || W.off + 4ull * M[r] > W.cap) {
+            W.off += 4ull * M[r];
+            continue;
+        }
+        CUDA_TRY(cudaMemcpy(W.p + W.off, D.ops + (size_t)r * D.cap, have * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t q = have; q < M[r]; q++) ((uint32_t *)(W.p + W.off))[q] = QMCB_OP_EMPTY;  // cutoff raised, not yet grown
+        W.off += 4ull * M[r];
+    }
+    W.pad8();
+    if (h->pt_on) {
+        const PtDev &P = h->P;
+        std::vector<double> bs;
+        std::vector<uint64_t> ks, one;
+        std::vector<unsigned long long> sw;
+        std::vector<uint32_t> sl;
+        CUDA_TRY(fetch(bs, P.beta_slot, h->pt_S));
+        CUDA_TRY(fetch(ks, P.key_slot, h->pt_S));
+        CUDA_TRY(fetch(one, (const uint64_t *)P.pt_cursor, 1));
+        CUDA_TRY(fetch(sw, (const unsigned long long *)P.swaps, 1));
+        CUDA_TRY(fetch(sl, (const uint32_t *)P.slot_of_local, D.R));
+        W.val<uint32_t>(P.n_chains), W.val<uint32_t>(P.n_betas), W.val<uint32_t>(P.cfg_begin), W.val<uint32_t>(0);
+        W.val<uint64_t>(P.pt_key), W.val<uint64_t>(one[0]), W.val<uint64_t>(sw[0]);
+        W.put(bs.data(), 8ull * h->pt_S), W.put(ks.data(), 8ull * h->pt_S);
+        W.put(sl.data(), 4ull * D.R), W.pad8();
+    }
+    return QMCB_OK;
+}
+
+extern "C" int qmcb_checkpoint_size(QmcbHandle *h, uint64_t *bytes) {
+    CHECK_H(h);
+    if (!bytes) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    CkWriter W(nullptr, 0);
+    int rc = checkpoint_write(h, W);
+    if (rc) return rc;
+    *bytes = W.off + 8;
+    return QMCB_OK;
+}
+extern "C" int qmcb_checkpoint_save(QmcbHandle *h, void *buf, uint64_t bytes) {
+    CHECK_H(h);
+    if (!buf) return fail(QMCB_ERR_BAD_ARG, "null buffer");
+    CkWriter W(buf, bytes);
+    int rc = checkpoint_write(h, W);
+    if (rc) return rc;
+    if (W.off + 8 > bytes) return fail(QMCB_ERR_BAD_ARG, "checkpoint buffer too small (see qmcb_checkpoint_size)");
+    const uint64_t sum = fnv1a((const uint8_t *)buf, W.off);
+    memcpy((uint8_t *)buf + W.off, &sum, 8);
+    return QMCB_OK;
+}
+extern "C" int qmcb_checkpoint_load(const void *buf, uint64_t bytes, int device, QmcbHandle **out) {
+    if (!buf || !out || bytes < 64) return fail(QMCB_ERR_BAD_ARG, "null or truncated checkpoint");
+    CkReader Rd(buf, bytes);
+    char magic[8];
+    Rd.get(magic, 8);
+    if (memcmp(magic, "QMCBCKP1", 8) != 0) return fail(QMCB_ERR_BAD_ARG, "not a qmcb checkpoint");
+    const uint32_t version = Rd.val<uint32_t>(), N = Rd.val<uint32_t>(), E = Rd.val<uint32_t>(), R = Rd.val<uint32_t>();
+    const uint32_t mode = Rd.val<uint32_t>(), flags = Rd.val<uint32_t>();
+    const uint64_t target = Rd.val<uint64_t>();
+    const double gamma = Rd.val<double>(), hl = Rd.val<double>();
+    if (version != 1 || R == 0 || N == 0) return fail(QMCB_ERR_BAD_ARG, "unsupported checkpoint version or empty batch");
+    auto va = Rd.vec<uint32_t>(E), vb = Rd.vec<uint32_t>(E);
+    Rd.pad8();
+    auto J = Rd.vec<double>(E);
+    auto beta = Rd.vec<double>(R);
+    auto key = Rd.vec<uint64_t>(R), cursor = Rd.vec<uint64_t>(R), done = Rd.vec<uint64_t>(R), vupd = Rd.vec<uint64_t>(R);
+    auto M = Rd.vec<uint32_t>(R), n = Rd.vec<uint32_t>(R);
+    const uint32_t Nw = (N + 31) / 32;
+    auto state = Rd.vec<uint32_t>((uint64_t)R * Nw);
+    Rd.pad8();
+    if (!Rd.ok) return fail(QMCB_ERR_BAD_ARG, "truncated checkpoint");
+    const uint64_t ops_off = Rd.off;
+    uint64_t total_ops = 0, maxM = 0;
+    for (uint32_t r = 0; r < R; r++) total_ops += M[r], maxM = std::max<uint64_t>(maxM, M[r]);
+    if (total_ops > (bytes - Rd.off) / 4) return fail(QMCB_ERR_BAD_ARG, "truncated checkpoint");
+    Rd.off += 4 * total_ops;
+    Rd.pad8();
+    // tempering block
+    uint32_t n_chains = 0, n_betas = 0, cfg_begin = 0;
+    uint64_t pt_key = 0, pt_cursor = 0, swaps = 0;
+    std::vector<double> bs;
+    std::vector<uint64_t> ks;
+    std::vector<uint32_t> sl;
+    if (flags & 2u) {
+        n_chains = Rd.val<uint32_t>(), n_betas = Rd.val<uint32_t>(), cfg_begin = Rd.val<uint32_t>();
+        Rd.val<uint32_t>();
+        pt_key = Rd.val<uint64_t>(), pt_cursor = Rd.val<uint64_t>(), swaps = Rd.val<uint64_t>();
+        const uint64_t S = (uint64_t)n_chains * n_betas;
+        bs = Rd.vec<double>(S), ks = Rd.vec<uint64_t>(S), sl = Rd.vec<uint32_t>(R);
+        Rd.pad8();
+    }
+    if (!Rd.ok || Rd.off + 8 > bytes) return fail(QMCB_ERR_BAD_ARG, "truncated checkpoint");
+    uint64_t sum = 0;
+    memcpy(&sum, (const uint8_t *)buf + Rd.off, 8);
+    if (sum != fnv1a((const uint8_t *)buf, Rd.off)) return fail(QMCB_ERR_BAD_ARG, "checkpoint checksum mismatch");
+
+    QmcbLattice lat{N, E, va.data(), vb.data(), J.data(), gamma, hl};
+    QmcbHandle *h = nullptr;
+    const uint64_t cutoff0 = std::max<uint64_t>(maxM, 1);
+    int rc = qmcb_create(&lat, R, beta.data(), key.data(), cutoff0, 0, nullptr, device, &h);
+    if (rc) return rc;
+    SseDev &D = h->D;
+    auto bail = [&](int code) {
+        qmcb_destroy(h);
+        return code;
+    };
+#define TRYL(expr)                                                              \
+    do {                                                                        \
+        cudaError_t e_ = (expr);                                                \
+        if (e_ != cudaSuccess) return bail(fail_cuda(e_, #expr, __FILE__, __LINE__)); \
+    } while (0)
+    const uint8_t *op_src = (const uint8_t *)buf + ops_off;
+    for (uint32_t r = 0; r < R; r++) {
+        const uint32_t *wr = (const uint32_t *)op_src;
+        uint32_t cnt = 0;
+        for (uint32_t q = 0; q < M[r]; q++) {
+            if (wr[q] == QMCB_OP_EMPTY) continue;
+            if ((wr[q] >> 28) || (wr[q] & 0xFFFFFFu) >= D.Nb) return bail(fail(QMCB_ERR_BAD_ARG, "malformed operator word in checkpoint"));
+            cnt++;
+        }
+        if (cnt != n[r]) return bail(fail(QMCB_ERR_BAD_ARG, "operator count in checkpoint does not match its string"));
+        TRYL(cudaMemcpy(D.ops + (size_t)r * D.cap, op_src, 4ull * M[r], cudaMemcpyHostToDevice));
+        op_src += 4ull * M[r];
+    }
+    TRYL(cudaMemcpy(D.state, state.data(), 4ull * R * Nw, cudaMemcpyHostToDevice));
+    TRYL(cudaMemcpy(D.cursor, cursor.data(), 8ull * R, cudaMemcpyHostToDevice));
+    TRYL(cudaMemcpy(D.done, done.data(), 8ull * R, cudaMemcpyHostToDevice));
+    TRYL(cudaMemcpy(D.vupd, vupd.data(), 8ull * R, cudaMemcpyHostToDevice));
+    TRYL(cudaMemcpy(D.M, M.data(), 4ull * R, cudaMemcpyHostToDevice));
+    TRYL(cudaMemcpy(D.n, n.data(), 4ull * R, cudaMemcpyHostToDevice));
+    h->target = target;
+    if ((rc = qmcb_set_mode(h, (int)mode))) return bail(rc);
+    if ((flags & 1u) && (rc = qmcb_set_enable_heatbath(h, 1))) return bail(rc);
+    if (flags & 2u) {
+        if ((rc = qmcb_pt_configure(h, n_chains, n_betas, cfg_begin, bs.data(), ks.data(), pt_key))) return bail(rc);
+        // pt_configure relabelled the replicas with the initial slots: restore the saved labels
+        TRYL(cudaMemcpy(D.beta, beta.data(), 8ull * R, cudaMemcpyHostToDevice));
+        TRYL(cudaMemcpy(D.key, key.data(), 8ull * R, cudaMemcpyHostToDevice));
+        TRYL(cudaMemcpy(h->P.slot_of_local, sl.data(), 4ull * R, cudaMemcpyHostToDevice));
+        TRYL(cudaMemcpy(h->P.pt_cursor, &pt_cursor, 8, cudaMemcpyHostToDevice));
+        TRYL(cudaMemcpy(h->P.swaps, &swaps, 8, cudaMemcpyHostToDevice));
+    }
+#undef TRYL
+    *out = h;
     return QMCB_OK;
 }
 

@@ -51,6 +51,44 @@ class QmcIsingGraph:
     def new_with_rng(cls, edges, transverse, longitudinal, cutoff, rng_keys, state=None, betas=1.0, **kw):
         return cls(edges, transverse, longitudinal, cutoff, rng_keys, betas, state=state, **kw)
 
+    # -- checkpoints (replaces SerializeQmcGraph, qmc_ising.rs:1001-1087) ----------------------
+    def save_checkpoint(self) -> bytes:
+        """One blob for the whole batch: lattice, spins, operator strings, cutoffs and the injected
+        stream position of every replica (include/qmcb.h, qmcb_checkpoint_save)."""
+        nbytes = C.c_uint64()
+        check(self._L.qmcb_checkpoint_size(self._h, C.byref(nbytes)))
+        buf = np.zeros(nbytes.value, dtype=np.uint8)
+        check(self._L.qmcb_checkpoint_save(self._h, C.c_void_p(buf.ctypes.data), nbytes.value))
+        return buf.tobytes()
+
+    @classmethod
+    def from_checkpoint(cls, blob, device=0):
+        """SerializeQmcGraph::into_qmc: a batch that continues bit-identically to the saved one."""
+        L = _lib.load()
+        raw = np.frombuffer(blob, dtype=np.uint8)
+        h = C.c_void_p()
+        check(L.qmcb_checkpoint_load(C.c_void_p(raw.ctypes.data), len(raw), device, C.byref(h)))
+        g = cls.__new__(cls)
+        g._L, g._h = L, h
+        n32 = C.c_uint32()
+        check(L.qmcb_num_replicas(h, C.byref(n32)))
+        g.R = n32.value
+        check(L.qmcb_num_vars(h, C.byref(n32)))
+        g.nvars = n32.value
+        check(L.qmcb_num_edges(h, C.byref(n32)))
+        va, vb, J = np.zeros(n32.value, np.uint32), np.zeros(n32.value, np.uint32), np.zeros(n32.value, np.float64)
+        check(L.qmcb_get_edges(h, ptr(va, C.c_uint32), ptr(vb, C.c_uint32), ptr(J, C.c_double)))
+        g._edges = [((int(a), int(b)), float(j)) for a, b, j in zip(va, vb, J)]
+        t, l = C.c_double(), C.c_double()
+        check(L.qmcb_get_fields(h, C.byref(t), C.byref(l)))
+        g.transverse, g.longitudinal = t.value, l.value
+        g._keep = None
+        g._betas = g.betas()
+        m = C.c_int()
+        check(L.qmcb_get_mode(h, C.byref(m)))
+        g.mode = m.value
+        return g
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.qmcb_destroy(self._h)

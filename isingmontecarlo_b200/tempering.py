@@ -75,6 +75,34 @@ class TemperingContainer:
                                   ptr(self.betas_global, C.c_double), ptr(self.keys_global, C.c_uint64), int(pt_key)))
         self._rec = torch.empty((self.R, REC_WORDS), dtype=torch.int64, device=f"cuda:{device}")
 
+    # -- checkpoints (replaces SerializeTemperingContainer, tempering_container.rs:671-793) -----
+    def save_checkpoint(self) -> bytes:
+        """This rank's share of the container: its configurations with their current slot labels, the
+        ladder, the PT stream position and the swap count."""
+        return self.graph.save_checkpoint()
+
+    @classmethod
+    def from_checkpoint(cls, blob, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from .sse import QmcIsingGraph
+
+        tc = cls.__new__(cls)
+        tc._torch, tc.group = torch, group
+        dist_on = dist.is_available() and dist.is_initialized()
+        tc.rank = dist.get_rank(group) if dist_on else 0
+        tc.world = dist.get_world_size(group) if dist_on else 1
+        tc.device = torch.cuda.current_device() if device is None else device
+        tc.graph = QmcIsingGraph.from_checkpoint(blob, device=tc.device)
+        nc, nb, sb = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(tc.graph._L.qmcb_pt_get_config(tc.graph._h, C.byref(nc), C.byref(nb), C.byref(sb)))
+        tc.n_chains, tc.n_betas, tc.slot_begin, tc.R = nc.value, nb.value, sb.value, tc.graph.R
+        tc.S = tc.n_chains * tc.n_betas
+        tc.betas_global = tc.keys_global = None  # live in the handle
+        tc._rec = torch.empty((tc.R, REC_WORDS), dtype=torch.int64, device=f"cuda:{tc.device}")
+        return tc
+
     def num_graphs(self):
         return self.S
 
