@@ -80,6 +80,15 @@ int qmcb_get_mode(const QmcbHandle *h, int *mode);
  * gen_bool, then gen_range(0. ..1.0) and gen_range(0. ..total) when an insertion is attempted. */
 int qmcb_set_enable_heatbath(QmcbHandle *h, int enable);
 int qmcb_get_enable_heatbath(const QmcbHandle *h, int *enabled);
+/* Replicas with unequal Hamiltonians in one batch (what the reference expresses as graphs with different
+ * couplings in one TemperingContainer, tempering_traits.rs:122-154).  J_tab [n_ham][E], transverse[n_ham],
+ * longitudinal[n_ham]; ham_of_replica[R] picks each replica's row.  Rows must satisfy can_swap_managers
+ * (qmc_ising.rs:563-590): couplings of the same sign per edge, longitudinal fields of the same sign. */
+int qmcb_set_hamiltonians(QmcbHandle *h, uint32_t n_ham, const double *J_tab, const double *transverse,
+                          const double *longitudinal, const uint32_t *ham_of_replica);
+int qmcb_num_hamiltonians(const QmcbHandle *h, uint32_t *n_ham);
+int qmcb_get_hamiltonian_index(QmcbHandle *h, uint32_t *ham_of_replica /* [R] */);
+int qmcb_get_offsets(QmcbHandle *h, double *offsets /* [R]: get_offset of each replica's Hamiltonian */);
 /* tuning knobs; "impl": 0 = warp-parallel kernels where available (default), 1 = serial-order kernels only */
 int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value);
 /* event counters of the SSE kernels (after qmcb_set_option(h, "debug_counters", 1)); diagnostics only */
@@ -149,8 +158,16 @@ int qmcb_get_boundaries(QmcbHandle *h, uint32_t r, uint32_t *b_in, uint32_t *b_o
 int qmcb_pt_configure(QmcbHandle *h, uint32_t n_chains_global, uint32_t n_betas,
                       uint32_t slot_begin, const double *betas_global /* [n_chains*n_betas] */,
                       const uint64_t *keys_global, uint64_t pt_key);
+/* Hamiltonian row (qmcb_set_hamiltonians) of every slot of the ladder: a label of the slot, like beta
+ * (swap_manager_and_state leaves couplings where they are).  Pairs of slots that are not ham_eq
+ * (tempering_traits.rs:122-124) swap with the relative_weight factors of tempering_container.rs:286-292. */
+int qmcb_pt_set_slot_hamiltonians(QmcbHandle *h, const uint32_t *ham_of_slot /* [n_chains*n_betas] */);
+/* uint64 words per record of qmcb_pt_export: 4 {slot, n, cursor, cutoff}; 8 with slot Hamiltonians
+ * (+ three relative weights as f64 bits: first-pass partner, second-pass partner if the configuration
+ * stays, second-pass partner if it moves; + pad) */
+int qmcb_pt_record_words(const QmcbHandle *h, uint32_t *words);
 /* step 1 of tempering_step: write this rank's per-configuration record for the all-gather;
- * rec_dev is DEVICE memory, [R] records of 4 x uint64: {slot, n, cursor, cutoff}. */
+ * rec_dev is DEVICE memory, [R] records of qmcb_pt_record_words() x uint64. */
 int qmcb_pt_export(QmcbHandle *h, uint64_t *rec_dev);
 /* step 2: given ALL ranks' records (device, [n_chains*n_betas] records in any order), set every
  * cutoff to the global max (tempering_container.rs:129-137), evaluate the swaps of every ladder

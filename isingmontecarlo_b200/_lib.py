@@ -37,6 +37,10 @@ SIGNATURES = {
     "qmcb_get_mode": [vp, C.POINTER(C.c_int)],
     "qmcb_set_enable_heatbath": [vp, C.c_int],
     "qmcb_get_enable_heatbath": [vp, C.POINTER(C.c_int)],
+    "qmcb_set_hamiltonians": [vp, C.c_uint32, f64p, f64p, f64p, u32p],
+    "qmcb_num_hamiltonians": [vp, u32p],
+    "qmcb_get_hamiltonian_index": [vp, u32p],
+    "qmcb_get_offsets": [vp, f64p],
     "qmcb_set_option": [vp, C.c_char_p, C.c_int64],
     "qmcb_get_debug_counters": [vp, u64p],
     "qmcb_set_betas": [vp, f64p],
@@ -71,6 +75,8 @@ SIGNATURES = {
     "qmcb_verify": [vp, C.c_uint32, C.POINTER(C.c_int)],
     "qmcb_get_boundaries": [vp, C.c_uint32, u32p, u32p, C.c_uint64],
     "qmcb_pt_configure": [vp, C.c_uint32, C.c_uint32, C.c_uint32, f64p, u64p, C.c_uint64],
+    "qmcb_pt_set_slot_hamiltonians": [vp, u32p],
+    "qmcb_pt_record_words": [vp, u32p],
     "qmcb_pt_export": [vp, vp],
     "qmcb_pt_apply": [vp, vp, C.c_uint64],
     "qmcb_pt_total_swaps": [vp, u64p],

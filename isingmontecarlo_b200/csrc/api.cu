@@ -23,7 +23,7 @@ void launch_sse_recount(const SseDev &D, uint32_t r, cudaStream_t st);
 void launch_sse_init_state(const SseDev &D, cudaStream_t st);
 int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
-void launch_pt_export(const SseDev &D, const PtDev &P, uint64_t *rec, cudaStream_t st);
+int launch_pt_export(const SseDev &D, const PtDev &P, uint64_t *rec, cudaStream_t st);
 void launch_pt_apply(const SseDev &D, const PtDev &P, const uint64_t *rec, uint32_t S, cudaStream_t st);
 void launch_cls_generic(const ClsDev &D, uint32_t colour, uint32_t cstart, uint32_t ccount, uint64_t sweep, cudaStream_t st);
 void launch_cls_square(const ClsDev &D, uint32_t colour, uint64_t sweep, cudaStream_t st);
@@ -97,7 +97,11 @@ struct QmcbHandle {
     // host copy of the lattice (heat-bath tables, checkpoints)
     std::vector<uint32_t> va_h, vb_h;
     std::vector<double> J_h;
-    double *hb_cum_dev = nullptr, *hb_maxw_dev = nullptr;
+    double *hb_cum_dev = nullptr, *hb_maxw_dev = nullptr, *hb_total_dev = nullptr;
+    // per-replica Hamiltonians (qmcb_set_hamiltonians): row 0 of the tables is the lattice given at creation
+    uint32_t H = 1;
+    std::vector<double> Jtab_h, gam_h, hl_h, offset_h;  // [H][E], [H], [H], [H]
+    std::vector<uint32_t> ham_slot_h;                   // [S] tempering: Hamiltonian row of each slot
 };
 
 #define CHECK_H(h)                                              \
@@ -283,6 +287,7 @@ extern "C" int qmcb_create(const QmcbLattice *lat, uint32_t R, const double *bet
     TRYC(cudaMemcpy(J, lat->J, sizeof(double) * D.E, cudaMemcpyHostToDevice));
     D.va = va, D.vb = vb, D.J = J;
     h->va_h.assign(lat->va, lat->va + D.E), h->vb_h.assign(lat->vb, lat->vb + D.E), h->J_h.assign(lat->J, lat->J + D.E);
+    h->Jtab_h = h->J_h, h->gam_h = {lat->transverse}, h->hl_h = {lat->longitudinal}, h->offset_h = {h->offset};
     TRYC(h->pool.alloc(&D.ops, (size_t)R * D.cap));
     TRYC(cudaMemset(D.ops, 0xFF, (size_t)R * D.cap * 4));
     TRYC(h->pool.alloc(&D.state, (size_t)R * D.Nw));
@@ -365,31 +370,117 @@ extern "C" int qmcb_set_enable_heatbath(QmcbHandle *h, int enable) {
         return QMCB_OK;
     }
     if (!h->hb_cum_dev) {
-        std::vector<double> maxw(D.Nb), cum(D.Nb);
-        for (uint32_t b = 0; b < D.Nb; b++) {
-            double acc = 0.0;
-            if (b < D.E) {  // two_site_hamiltonian, qmc_ising.rs:863-875, over the four diagonal substates
-                const double j = h->J_h[b], cand[2] = {std::fabs(j) - j, std::fabs(j) + j};
-                for (double w : cand)
-                    if (w > acc) acc = w;
-            } else if (b < D.E + D.N) {
-                if (D.gamma > acc) acc = D.gamma;
-            } else {
-                const double cand[2] = {std::fabs(D.h) - D.h, std::fabs(D.h) + D.h};
-                for (double w : cand)
-                    if (w > acc) acc = w;
+        const uint32_t H = h->H;
+        std::vector<double> maxw((size_t)H * D.Nb), cum((size_t)H * D.Nb), tot(H);
+        for (uint32_t hi = 0; hi < H; hi++) {
+            double *mw = maxw.data() + (size_t)hi * D.Nb, *cm = cum.data() + (size_t)hi * D.Nb;
+            const double gam = h->gam_h[hi], hl = h->hl_h[hi];
+            for (uint32_t b = 0; b < D.Nb; b++) {
+                double acc = 0.0;
+                if (b < D.E) {  // two_site_hamiltonian, qmc_ising.rs:863-875, over the four diagonal substates
+                    const double j = h->Jtab_h[(size_t)hi * D.E + b], cand[2] = {std::fabs(j) - j, std::fabs(j) + j};
+                    for (double w : cand)
+                        if (w > acc) acc = w;
+                } else if (b < D.E + D.N) {
+                    if (gam > acc) acc = gam;
+                } else {
+                    const double cand[2] = {std::fabs(hl) - hl, std::fabs(hl) + hl};
+                    for (double w : cand)
+                        if (w > acc) acc = w;
+                }
+                mw[b] = acc;
+                cm[b] = b == 0 ? acc : acc + cm[b - 1];
             }
-            maxw[b] = acc;
-            cum[b] = b == 0 ? acc : acc + cum[b - 1];
+            tot[hi] = cm[D.Nb - 1];
+            if (!(tot[hi] > 0.0)) return fail(QMCB_ERR_BAD_ARG, "heat-bath update needs a non-zero total bond weight");
         }
-        if (!(cum[D.Nb - 1] > 0.0)) return fail(QMCB_ERR_BAD_ARG, "heat-bath update needs a non-zero total bond weight");
-        CUDA_TRY(h->pool.alloc(&h->hb_cum_dev, D.Nb));
-        CUDA_TRY(h->pool.alloc(&h->hb_maxw_dev, D.Nb));
-        CUDA_TRY(cudaMemcpy(h->hb_cum_dev, cum.data(), sizeof(double) * D.Nb, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(h->hb_maxw_dev, maxw.data(), sizeof(double) * D.Nb, cudaMemcpyHostToDevice));
-        D.hb_total = cum[D.Nb - 1];
+        CUDA_TRY(h->pool.alloc(&h->hb_cum_dev, (size_t)H * D.Nb));
+        CUDA_TRY(h->pool.alloc(&h->hb_maxw_dev, (size_t)H * D.Nb));
+        CUDA_TRY(h->pool.alloc(&h->hb_total_dev, H));
+        CUDA_TRY(cudaMemcpy(h->hb_cum_dev, cum.data(), sizeof(double) * cum.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->hb_maxw_dev, maxw.data(), sizeof(double) * maxw.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->hb_total_dev, tot.data(), sizeof(double) * H, cudaMemcpyHostToDevice));
+        D.hb_total = tot[0];
     }
+    D.hb_cum_tab = h->hb_cum_dev, D.hb_maxw_tab = h->hb_maxw_dev, D.hb_total_tab = h->hb_total_dev;
     D.hb_cum = h->hb_cum_dev, D.hb_maxw = h->hb_maxw_dev;
+    return QMCB_OK;
+}
+// f64::signum
+static double signum(double x) { return x != x ? x : (std::signbit(x) ? -1.0 : 1.0); }
+
+// Replicas of one batch with unequal Hamiltonians: what the reference expresses as graphs built with
+// different couplings in one TemperingContainer.  The rows must pass SwapManagers::can_swap_graphs
+// (qmc_ising.rs:563-590: same edges -- given, one lattice per handle -- couplings of the same sign per edge,
+// longitudinal fields of the same sign); the bond-index space additionally needs |h| > eps in all rows or none.
+extern "C" int qmcb_set_hamiltonians(QmcbHandle *h, uint32_t n_ham, const double *J_tab, const double *transverse,
+                                     const double *longitudinal, const uint32_t *ham_of_replica) {
+    CHECK_H(h);
+    SseDev &D = h->D;
+    if (!n_ham || (D.E && !J_tab) || !transverse || !longitudinal || !ham_of_replica) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    for (uint32_t hi = 0; hi < n_ham; hi++) {
+        if (!(transverse[hi] >= 0.0)) return fail(QMCB_ERR_BAD_ARG, "transverse field must be >= 0");
+        if ((std::fabs(longitudinal[hi]) > DBL_EPSILON) != (D.has_h != 0))
+            return fail(QMCB_ERR_BAD_ARG, "longitudinal field must be non-zero in all Hamiltonians of a batch or in none");
+        if (signum(longitudinal[hi]) != signum(longitudinal[0]))
+            return fail(QMCB_ERR_BAD_ARG, "Longitudinal fields are not of the same sign");  // qmc_ising.rs:581-586
+        for (uint32_t e = 0; e < D.E; e++)
+            if (signum(J_tab[(size_t)hi * D.E + e]) != signum(J_tab[e]))
+                return fail(QMCB_ERR_BAD_ARG, "bonds must be of same sign");  // qmc_ising.rs:572-577
+    }
+    for (uint32_t r = 0; r < D.R; r++)
+        if (ham_of_replica[r] >= n_ham) return fail(QMCB_ERR_BAD_ARG, "Hamiltonian index out of range");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const bool hb = D.hb_cum != nullptr;
+    h->H = n_ham;
+    h->Jtab_h.assign(J_tab, J_tab + (size_t)n_ham * D.E);
+    h->gam_h.assign(transverse, transverse + n_ham), h->hl_h.assign(longitudinal, longitudinal + n_ham);
+    h->offset_h.resize(n_ham);
+    for (uint32_t hi = 0; hi < n_ham; hi++) {  // qmc_ising.rs:97-99
+        double edge_offset = 0.0;
+        for (uint32_t e = 0; e < D.E; e++) edge_offset += std::fabs(J_tab[(size_t)hi * D.E + e]);
+        h->offset_h[hi] = edge_offset + (double)D.N * (transverse[hi] + std::fabs(longitudinal[hi]));
+    }
+    double *jt, *gt, *ht;
+    uint32_t *hr;
+    CUDA_TRY(h->pool.alloc(&jt, (size_t)n_ham * D.E));
+    CUDA_TRY(h->pool.alloc(&gt, n_ham));
+    CUDA_TRY(h->pool.alloc(&ht, n_ham));
+    CUDA_TRY(h->pool.alloc(&hr, D.R));
+    CUDA_TRY(cudaMemcpy(jt, J_tab, sizeof(double) * (size_t)n_ham * D.E, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(gt, transverse, sizeof(double) * n_ham, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ht, longitudinal, sizeof(double) * n_ham, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(hr, ham_of_replica, sizeof(uint32_t) * D.R, cudaMemcpyHostToDevice));
+    h->pool.release((void *)D.J_tab), h->pool.release((void *)D.gam_tab), h->pool.release((void *)D.h_tab), h->pool.release((void *)D.ham);
+    D.J_tab = jt, D.gam_tab = gt, D.h_tab = ht, D.ham = hr;
+    // the heat-bath tables are per Hamiltonian: rebuild them
+    h->pool.release(h->hb_cum_dev), h->pool.release(h->hb_maxw_dev), h->pool.release(h->hb_total_dev);
+    h->hb_cum_dev = h->hb_maxw_dev = h->hb_total_dev = nullptr;
+    D.hb_cum = D.hb_maxw = nullptr;
+    return hb ? qmcb_set_enable_heatbath(h, 1) : QMCB_OK;
+}
+extern "C" int qmcb_num_hamiltonians(const QmcbHandle *h, uint32_t *n_ham) {
+    if (!h || !n_ham) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *n_ham = h->H;
+    return QMCB_OK;
+}
+// Hamiltonian row of every replica (moves with the slot label under tempering)
+extern "C" int qmcb_get_hamiltonian_index(QmcbHandle *h, uint32_t *ham_of_replica) {
+    CHECK_H(h);
+    if (!ham_of_replica) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!h->D.ham) std::fill(ham_of_replica, ham_of_replica + h->D.R, 0u);
+    else CUDA_TRY(cudaMemcpy(ham_of_replica, h->D.ham, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
+    return QMCB_OK;
+}
+// get_offset of every replica's current Hamiltonian (qmc_ising.rs:97-99, :556-559)
+extern "C" int qmcb_get_offsets(QmcbHandle *h, double *offsets) {
+    CHECK_H(h);
+    if (!offsets) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    std::vector<uint32_t> hr(h->D.R);
+    int rc = qmcb_get_hamiltonian_index(h, hr.data());
+    if (rc) return rc;
+    for (uint32_t r = 0; r < h->D.R; r++) offsets[r] = h->offset_h[hr[r]];
     return QMCB_OK;
 }
 extern "C" int qmcb_get_enable_heatbath(const QmcbHandle *h, int *enabled) {
@@ -505,14 +596,16 @@ extern "C" int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t freq, double *
     if (rc == QMCB_OK && energy_out) {
         std::vector<unsigned long long> sn(D.R);
         std::vector<double> beta(D.R);
+        std::vector<uint32_t> hr(D.R, 0u);
         cudaError_t e = cudaMemcpyAsync(sn.data(), D.sum_n, sizeof(uint64_t) * D.R, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && D.ham) e = cudaMemcpyAsync(hr.data(), D.ham, sizeof(uint32_t) * D.R, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(beta.data(), D.beta, sizeof(double) * D.R, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail_cuda(e, "copy estimators", __FILE__, __LINE__);
         else
             for (uint32_t r = 0; r < D.R; r++) {  // qmc_stepper.rs:160-161, qmc_ising.rs:805-809
                 double average_n = (double)sn[r] / (double)spr;
-                energy_out[r] = -(average_n / beta[r]) + h->offset;
+                energy_out[r] = -(average_n / beta[r]) + h->offset_h[hr[r]];
             }
     }
     if (rc == QMCB_OK && samples_dev) {
@@ -816,10 +909,52 @@ extern "C" int qmcb_pt_configure(QmcbHandle *h, uint32_t n_chains, uint32_t n_be
     h->pt_S = (uint32_t)S;
     return QMCB_OK;
 }
+// Hamiltonian of every slot of the ladder (rows of qmcb_set_hamiltonians' tables): like beta it is a label of
+// the SLOT, configurations move between slots (swap_manager_and_state, qmc_ising.rs:593-602, leaves edges and
+// fields where they are).  Swaps between slots whose rows are not ham_eq (tempering_traits.rs:122-124; NB it
+// compares edges and transverse field only) get the relative_weight factors of tempering_container.rs:286-292.
+extern "C" int qmcb_pt_set_slot_hamiltonians(QmcbHandle *h, const uint32_t *ham_of_slot) {
+    CHECK_H(h);
+    SseDev &D = h->D;
+    PtDev &P = h->P;
+    if (!h->pt_on || !ham_of_slot) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+    if (!D.ham) return fail(QMCB_ERR_BAD_ARG, "call qmcb_set_hamiltonians first");
+    const uint32_t S = h->pt_S, H = h->H;
+    for (uint32_t s = 0; s < S; s++)
+        if (ham_of_slot[s] >= H) return fail(QMCB_ERR_BAD_ARG, "Hamiltonian index out of range");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::vector<uint8_t> eq((size_t)H * H);
+    for (uint32_t a = 0; a < H; a++)
+        for (uint32_t b = 0; b < H; b++)  // HamInfo::eq, qmc_ising.rs:899-903
+            eq[(size_t)a * H + b] = h->gam_h[a] == h->gam_h[b] &&
+                                    std::equal(h->Jtab_h.begin() + (size_t)a * D.E, h->Jtab_h.begin() + (size_t)(a + 1) * D.E, h->Jtab_h.begin() + (size_t)b * D.E);
+    uint32_t *hs;
+    uint8_t *he;
+    CUDA_TRY(h->pool.alloc(&hs, S));
+    CUDA_TRY(h->pool.alloc(&he, (size_t)H * H));
+    CUDA_TRY(cudaMemcpy(hs, ham_of_slot, sizeof(uint32_t) * S, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(he, eq.data(), eq.size(), cudaMemcpyHostToDevice));
+    h->pool.release((void *)P.ham_slot), h->pool.release((void *)P.ham_eq), h->pool.release(P.counts), h->pool.release(P.oslot_cfg);
+    P.ham_slot = hs, P.ham_eq = he, P.H = H;
+    CUDA_TRY(h->pool.alloc(&P.counts, (size_t)D.R * D.Nb));
+    CUDA_TRY(h->pool.alloc(&P.oslot_cfg, S));
+    h->ham_slot_h.assign(ham_of_slot, ham_of_slot + S);
+    // the local configurations take the label of the slot they are in
+    std::vector<uint32_t> slots(D.R), hr(D.R);
+    CUDA_TRY(cudaMemcpy(slots.data(), P.slot_of_local, sizeof(uint32_t) * D.R, cudaMemcpyDeviceToHost));
+    for (uint32_t r = 0; r < D.R; r++) hr[r] = ham_of_slot[slots[r]];
+    CUDA_TRY(cudaMemcpy((void *)D.ham, hr.data(), sizeof(uint32_t) * D.R, cudaMemcpyHostToDevice));
+    return QMCB_OK;
+}
+extern "C" int qmcb_pt_record_words(const QmcbHandle *h, uint32_t *words) {
+    if (!h || !words) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *words = h->P.ham_slot ? PT_REC_WORDS_MH : PT_REC_WORDS_EQ;
+    return QMCB_OK;
+}
 extern "C" int qmcb_pt_export(QmcbHandle *h, uint64_t *rec_dev) {
     CHECK_H(h);
     if (!h->pt_on || !rec_dev) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
-    launch_pt_export(h->D, h->P, rec_dev, h->stream);
+    h->launches += (uint64_t)launch_pt_export(h->D, h->P, rec_dev, h->stream) - 1;
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return QMCB_OK;
@@ -827,6 +962,7 @@ extern "C" int qmcb_pt_export(QmcbHandle *h, uint64_t *rec_dev) {
 extern "C" int qmcb_pt_apply(QmcbHandle *h, const uint64_t *all_rec_dev, uint64_t n_records) {
     CHECK_H(h);
     if (!h->pt_on || !all_rec_dev || n_records != h->pt_S) return fail(QMCB_ERR_BAD_ARG, "record count does not match the ladder");
+    if (h->D.ham && !h->P.ham_slot) return fail(QMCB_ERR_BAD_ARG, "replicas have their own Hamiltonians: call qmcb_pt_set_slot_hamiltonians before tempering");
     launch_pt_apply(h->D, h->P, all_rec_dev, h->pt_S, h->stream);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -858,12 +994,14 @@ extern "C" int qmcb_pt_get_slots(QmcbHandle *h, uint32_t *slots) {
 // tempering container as (graph, beta) pairs + total_swaps (tempering_container.rs:671-793).  Here the
 // injected stream is (key, cursor), 16 bytes, so it is part of the record and a restored batch continues
 // bit-identically.  Layout (little-endian), all arrays replica-major:
-//   "QMCBCKP1" | u32 version, N, E, R, mode, flags(bit0 heat-bath, bit1 tempering) | u64 target |
+//   "QMCBCKP1" | u32 version, N, E, R, mode, flags(bit0 heat-bath, bit1 tempering, bit2 Hamiltonian table) | u64 target |
 //   f64 transverse, longitudinal | va[E] u32 | vb[E] u32 | pad to 8 | J[E] f64 |
 //   beta[R] f64 | key[R] u64 | cursor[R] u64 | done[R] u64 | vupd[R] u64 | M[R] u32 | n[R] u32 |
 //   state[R][Nw] u32 | pad to 8 | ops of replica 0 (M[0] words), replica 1, ... | pad to 8 |
 //   tempering block (if flagged): u32 n_chains, n_betas, cfg_begin, pad | u64 pt_key, pt_cursor, swaps |
-//   beta_slot[S] f64 | key_slot[S] u64 | slot_of_local[R] u32 | pad to 8 |  u64 FNV-1a of all bytes before.
+//   beta_slot[S] f64 | key_slot[S] u64 | slot_of_local[R] u32 | pad to 8 |
+//   Hamiltonian block (if flagged): u32 H, has_slot_table | J_tab[H][E] f64 | transverse[H] | longitudinal[H] |
+//   ham[R] u32 | ham_slot[S] u32 (if has_slot_table) | pad to 8 |  u64 FNV-1a of all bytes before.
 namespace {
 struct CkWriter {
     uint8_t *p;
@@ -932,7 +1070,7 @@ static int checkpoint_write(QmcbHandle *h, CkWriter &W) {
     CUDA_TRY(fetch(state, D.state, (size_t)D.R * D.Nw));
     W.put("QMCBCKP1", 8);
     W.val<uint32_t>(1), W.val<uint32_t>(D.N), W.val<uint32_t>(D.E), W.val<uint32_t>(D.R);
-    W.val<uint32_t>((uint32_t)h->mode), W.val<uint32_t>((D.hb_cum ? 1u : 0u) | (h->pt_on ? 2u : 0u));
+    W.val<uint32_t>((uint32_t)h->mode), W.val<uint32_t>((D.hb_cum ? 1u : 0u) | (h->pt_on ? 2u : 0u) | (D.ham ? 4u : 0u));
     W.val<uint64_t>(h->target);
     W.val<double>(D.gamma), W.val<double>(D.h);
     W.put(h->va_h.data(), 4ull * D.E), W.put(h->vb_h.data(), 4ull * D.E), W.pad8();
@@ -967,6 +1105,15 @@ static int checkpoint_write(QmcbHandle *h, CkWriter &W) {
         W.val<uint64_t>(P.pt_key), W.val<uint64_t>(one[0]), W.val<uint64_t>(sw[0]);
         W.put(bs.data(), 8ull * h->pt_S), W.put(ks.data(), 8ull * h->pt_S);
         W.put(sl.data(), 4ull * D.R), W.pad8();
+    }
+    if (D.ham) {
+        std::vector<uint32_t> hr;
+        CUDA_TRY(fetch(hr, D.ham, D.R));
+        W.val<uint32_t>(h->H), W.val<uint32_t>(h->ham_slot_h.empty() ? 0u : 1u);
+        W.put(h->Jtab_h.data(), 8ull * h->H * D.E), W.put(h->gam_h.data(), 8ull * h->H), W.put(h->hl_h.data(), 8ull * h->H);
+        W.put(hr.data(), 4ull * D.R);
+        if (!h->ham_slot_h.empty()) W.put(h->ham_slot_h.data(), 4ull * h->ham_slot_h.size());
+        W.pad8();
     }
     return QMCB_OK;
 }
@@ -1032,6 +1179,16 @@ extern "C" int qmcb_checkpoint_load(const void *buf, uint64_t bytes, int device,
         bs = Rd.vec<double>(S), ks = Rd.vec<uint64_t>(S), sl = Rd.vec<uint32_t>(R);
         Rd.pad8();
     }
+    uint32_t H = 0, has_slot_tab = 0;
+    std::vector<double> Jtab, gtab, htab;
+    std::vector<uint32_t> hrep, hslot;
+    if (flags & 4u) {
+        H = Rd.val<uint32_t>(), has_slot_tab = Rd.val<uint32_t>();
+        Jtab = Rd.vec<double>((uint64_t)H * E), gtab = Rd.vec<double>(H), htab = Rd.vec<double>(H);
+        hrep = Rd.vec<uint32_t>(R);
+        if (has_slot_tab) hslot = Rd.vec<uint32_t>((uint64_t)n_chains * n_betas);
+        Rd.pad8();
+    }
     if (!Rd.ok || Rd.off + 8 > bytes) return fail(QMCB_ERR_BAD_ARG, "truncated checkpoint");
     uint64_t sum = 0;
     memcpy(&sum, (const uint8_t *)buf + Rd.off, 8);
@@ -1072,6 +1229,7 @@ extern "C" int qmcb_checkpoint_load(const void *buf, uint64_t bytes, int device,
     TRYL(cudaMemcpy(D.M, M.data(), 4ull * R, cudaMemcpyHostToDevice));
     TRYL(cudaMemcpy(D.n, n.data(), 4ull * R, cudaMemcpyHostToDevice));
     h->target = target;
+    if ((flags & 4u) && (rc = qmcb_set_hamiltonians(h, H, Jtab.data(), gtab.data(), htab.data(), hrep.data()))) return bail(rc);
     if ((rc = qmcb_set_mode(h, (int)mode))) return bail(rc);
     if ((flags & 1u) && (rc = qmcb_set_enable_heatbath(h, 1))) return bail(rc);
     if (flags & 2u) {
@@ -1082,6 +1240,10 @@ extern "C" int qmcb_checkpoint_load(const void *buf, uint64_t bytes, int device,
         TRYL(cudaMemcpy(h->P.slot_of_local, sl.data(), 4ull * R, cudaMemcpyHostToDevice));
         TRYL(cudaMemcpy(h->P.pt_cursor, &pt_cursor, 8, cudaMemcpyHostToDevice));
         TRYL(cudaMemcpy(h->P.swaps, &swaps, 8, cudaMemcpyHostToDevice));
+        if (has_slot_tab) {
+            if ((rc = qmcb_pt_set_slot_hamiltonians(h, hslot.data()))) return bail(rc);
+            TRYL(cudaMemcpy((void *)D.ham, hrep.data(), 4ull * R, cudaMemcpyHostToDevice));
+        }
     }
 #undef TRYL
     *out = h;

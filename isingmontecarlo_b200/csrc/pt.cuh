@@ -16,4 +16,12 @@ struct PtDev {
     uint64_t *cursor_slot;
     uint32_t *cfg_slot;
     uint32_t *maxM_chain;         // [n_chains]
+    // unequal Hamiltonians (GraphWeights, tempering_traits.rs:122-154); ham_slot == NULL: all slots equal
+    const uint32_t *ham_slot;     // [S] Hamiltonian row of each slot (a label, like beta)
+    const uint8_t *ham_eq;        // [H][H] GraphWeights::ham_eq of two rows
+    uint32_t H;
+    uint32_t *counts;             // [R][Nb] bond counters of the local configurations (scratch)
+    uint32_t *oslot_cfg;          // [S] slot each configuration held when the step began (scratch)
 };
+#define PT_REC_WORDS_EQ 4  // {slot, n, cursor, cutoff}
+#define PT_REC_WORDS_MH 8  // ... + three relative weights (f64 bits) + pad

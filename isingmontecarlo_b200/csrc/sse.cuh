@@ -43,7 +43,36 @@ struct SseDev {
     // heat-bath diagonal update (heatbath.rs:10-61 BondWeights); NULL = Metropolis rule
     const double *hb_cum, *hb_maxw;  // [Nb] cumulative / per-bond maximum diagonal weight
     double hb_total;
+    // per-replica Hamiltonians (tempering between unequal Hamiltonians, tempering_traits.rs:122-154;
+    // same edges, couplings of the same sign: qmc_ising.rs:563-590).  NULL = every replica uses J/gamma/h.
+    const uint32_t *ham;                     // [R] table row of each replica
+    const double *J_tab;                     // [H][E]
+    const double *gam_tab, *h_tab;           // [H]
+    const double *hb_cum_tab, *hb_maxw_tab;  // [H][Nb] (heat-bath on)
+    const double *hb_total_tab;              // [H]
 };
+
+// the Hamiltonian one replica is updated with
+struct Ham {
+    const double *J;
+    double gamma, h;
+    const double *hb_cum, *hb_maxw;
+    double hb_total;
+};
+template <bool MH>
+__device__ __forceinline__ Ham ham_view(const SseDev &D, uint32_t r) {
+    Ham m;
+    if (MH && D.ham) {
+        const uint32_t hi = D.ham[r];
+        m.J = D.J_tab + (size_t)hi * D.E, m.gamma = D.gam_tab[hi], m.h = D.h_tab[hi];
+        m.hb_cum = D.hb_cum ? D.hb_cum_tab + (size_t)hi * D.Nb : nullptr;
+        m.hb_maxw = D.hb_cum ? D.hb_maxw_tab + (size_t)hi * D.Nb : nullptr;
+        m.hb_total = D.hb_cum ? D.hb_total_tab[hi] : 0.0;
+    } else {
+        m.J = D.J, m.gamma = D.gamma, m.h = D.h, m.hb_cum = D.hb_cum, m.hb_maxw = D.hb_maxw, m.hb_total = D.hb_total;
+    }
+    return m;
+}
 
 enum { KIND_BOND = 0, KIND_SITE = 1, KIND_LONG = 2 };
 
@@ -59,13 +88,13 @@ __device__ __forceinline__ void bond_vars(const SseDev &D, uint32_t b, int kind,
     }
 }
 // diagonal matrix element <s|H_b|s>: qmc_ising.rs:863-888 with inputs == outputs
-__device__ __forceinline__ double bond_weight(const SseDev &D, uint32_t b, int kind, uint32_t s0, uint32_t s1) {
+__device__ __forceinline__ double bond_weight(const Ham &Hm, uint32_t b, int kind, uint32_t s0, uint32_t s1) {
     if (kind == KIND_BOND) {
-        double j = __ldg(D.J + b);
+        double j = __ldg(Hm.J + b);
         return fabs(j) + (s0 == s1 ? -j : j);
     }
-    if (kind == KIND_SITE) return D.gamma;
-    return fabs(D.h) + (s0 ? D.h : -D.h);
+    if (kind == KIND_SITE) return Hm.gamma;
+    return fabs(Hm.h) + (s0 ? Hm.h : -Hm.h);
 }
 // BondWeights::index_for_cumulative (heatbath.rs:56-60): slice::binary_search_by, insertion point
 // when no element compares equal

@@ -87,7 +87,7 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
     return ((((size_t)3 * Nw + N + 64 + 64 + 16 + 32) * 4 + 64 * 8) + 15) / 16 * 16;
 }
 
-template <bool HAS_H, int MINB, bool HB>
+template <bool HAS_H, int MINB, bool HB, bool MH>
 __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
                                                   uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
     uint32_t *frz = D.frozen + (size_t)r * bstride;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint64_t key = D.key[r];
+    const Ham Hm = ham_view<MH>(D, r);
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     const uint64_t range = D.Nb;
     const uint64_t zone = (range << __clzll((long long)range)) - 1ull;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                     // of the n interval the round can span; the rare word in between ends the resolved prefix
                     // (EMPTY lanes: it moves the cursor) or is settled in lane order with the exact n (DIAG lanes).
                     // A round that cannot resolve its first lane evaluates that lane literally.
-                    const double total = D.hb_total, bt = D.beta[r] * total;
+                    const double total = Hm.hb_total, bt = D.beta[r] * total;
                     auto spin_here = [&](uint32_t v) -> uint32_t {  // spin of v as seen by my slot
                         uint32_t sv = state_bit(S.st, v);
                         if (state_bit(S.cd, v))
@@ -183,13 +184,13 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                     auto try_insert = [&](uint64_t wp, uint64_t wc, uint32_t &nw) -> bool {  // heatbath.rs:166-187
                         const double pd = unit_f64(wp), c = unit_f64(wc) * total;
                         if (!(pd < 1.0) || !(c < total)) { err |= DEV_ERR_INVARIANT; return false; }
-                        const uint32_t b = hb_index_for_cumulative(D.hb_cum, D.Nb, c);
+                        const uint32_t b = hb_index_for_cumulative(Hm.hb_cum, D.Nb, c);
                         if (b >= D.Nb) { err |= DEV_ERR_INVARIANT; return false; }
                         const int kind = bond_kind(D, b);
                         uint32_t v0, v1;
                         bond_vars(D, b, kind, v0, v1);
                         const uint32_t s0 = spin_here(v0), s1 = kind == KIND_BOND ? spin_here(v1) : 0u;
-                        if (!(pd * __ldg(D.hb_maxw + b) < bond_weight(D, b, kind, s0, s1))) return false;
+                        if (!(pd * __ldg(Hm.hb_maxw + b) < bond_weight(Hm, b, kind, s0, s1))) return false;
                         const uint32_t bitsv = s0 | (s1 << 1);
                         nw = make_op(b, bitsv, bitsv);
                         return true;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                     }
                 }
                 double dnum = 0.0;  // num of an existing diagonal op does not depend on (cursor, n)
-                if (!HB && type == T_DIAG) dnum = bn * bond_weight(D, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
+                if (!HB && type == T_DIAG) dnum = bn * bond_weight(Hm, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
                 bool try_fast = true;
                 TICK(1);  // load, classify, decode of existing ops, flip list
                 while (!HB && rem) {
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                                 bond_vars(D, b, kind, v0, v1);
                                 const uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
                                 hz = state_bit(S.cd, v0) || (kind == KIND_BOND && state_bit(S.cd, v1));
-                                const double num = bn * bond_weight(D, b, kind, s0, s1);
+                                const double num = bn * bond_weight(Hm, b, kind, s0, s1);
                                 const uint32_t bitsv = s0 | (s1 << 1);
                                 opw = make_op(b, bitsv, bitsv);
                                 if (num >= dhiA) ok = true;                      // inserted without a second word
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                                 const uint32_t fv = S.fl[__ffs(m2) - 1];
                                 s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
                             }
-                            const double num = bn * bond_weight(D, b, kind, s0, s1);
+                            const double num = bn * bond_weight(Hm, b, kind, s0, s1);
                             const uint32_t bitsv = s0 | (s1 << 1);
                             bool ok = false, ex = false, fail = false;
                             if (num >= dhiA) ok = true;
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                                             const uint32_t fv = S.fl[__ffs(m) - 1];
                                             s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
                                         }
-                                        const double num = bn * bond_weight(D, b, kind, s0, s1);
+                                        const double num = bn * bond_weight(Hm, b, kind, s0, s1);
                                         const double den = (double)(M - ni);
                                         bool accept = num > den;
                                         if (!accept) {
@@ -858,13 +859,16 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
     const uint32_t blocks = (D.R + warps - 1) / warps;
     typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t);
     Kern kern;
-    if (D.hb_cum) kern = D.has_h ? k_sse_fast<true, 7, true> : k_sse_fast<false, 7, true>;
+    if (D.ham) {
+        if (D.hb_cum) kern = D.has_h ? k_sse_fast<true, 7, true, true> : k_sse_fast<false, 7, true, true>;
+        else kern = D.has_h ? k_sse_fast<true, 7, false, true> : k_sse_fast<false, 7, false, true>;
+    } else if (D.hb_cum) kern = D.has_h ? k_sse_fast<true, 7, true, false> : k_sse_fast<false, 7, true, false>;
     else
         switch (g_sse_fast_minblocks) {
-            case 4: kern = D.has_h ? k_sse_fast<true, 4, false> : k_sse_fast<false, 4, false>; break;
-            case 6: kern = D.has_h ? k_sse_fast<true, 6, false> : k_sse_fast<false, 6, false>; break;
-            case 8: kern = D.has_h ? k_sse_fast<true, 8, false> : k_sse_fast<false, 8, false>; break;
-            default: kern = D.has_h ? k_sse_fast<true, 7, false> : k_sse_fast<false, 7, false>; break;
+            case 4: kern = D.has_h ? k_sse_fast<true, 4, false, false> : k_sse_fast<false, 4, false, false>; break;
+            case 6: kern = D.has_h ? k_sse_fast<true, 6, false, false> : k_sse_fast<false, 6, false, false>; break;
+            case 8: kern = D.has_h ? k_sse_fast<true, 8, false, false> : k_sse_fast<false, 8, false, false>; break;
+            default: kern = D.has_h ? k_sse_fast<true, 7, false, false> : k_sse_fast<false, 7, false, false>; break;
         }
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     kern<<<blocks, warps * 32, smem, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep);

@@ -54,6 +54,7 @@ __device__ void diag_serial(const SseDev &D, uint32_t r, const Rep &V) {
     uint64_t cur = D.cursor[r];
     const uint64_t key = D.key[r];
     const double bn = D.beta[r] * (double)D.Nb;  // diagonal.rs:168, left-to-right product
+    const Ham Hm = ham_view<true>(D, r);
     const uint64_t range = D.Nb;
     const uint64_t zone = (range << __clzll((long long)range)) - 1ull;
     int err = 0;
@@ -82,7 +83,7 @@ __device__ void diag_serial(const SseDev &D, uint32_t r, const Rep &V) {
         uint32_t v0, v1;
         bond_vars(D, b, kind, v0, v1);
         uint32_t s0 = state_bit(V.state, v0), s1 = kind == KIND_BOND ? state_bit(V.state, v1) : 0u;
-        double num = bn * bond_weight(D, b, kind, s0, s1);
+        double num = bn * bond_weight(Hm, b, kind, s0, s1);
         double den = (double)(M - n);
         if (w == OP_EMPTY) {
             bool accept = num > den;
@@ -125,7 +126,8 @@ __device__ void diag_heatbath_serial(const SseDev &D, uint32_t r, const Rep &V) 
     uint32_t n = D.n[r];
     uint64_t cur = D.cursor[r];
     const uint64_t key = D.key[r];
-    const double total = D.hb_total;
+    const Ham Hm = ham_view<true>(D, r);
+    const double total = Hm.hb_total;
     const double bt = D.beta[r] * total;  // heatbath.rs:163,194
     int err = 0;
     for (uint32_t p = 0; p < M; p++) {
@@ -141,13 +143,13 @@ __device__ void diag_heatbath_serial(const SseDev &D, uint32_t r, const Rep &V) 
             double pd, c;
             do pd = unit_f64(stream_word(key, cur++)); while (!(pd < 1.0));            // gen_range(0. ..1.0)
             do c = unit_f64(stream_word(key, cur++)) * total; while (!(c < total));     // gen_range(0. ..total)
-            const uint32_t b = hb_index_for_cumulative(D.hb_cum, D.Nb, c);
+            const uint32_t b = hb_index_for_cumulative(Hm.hb_cum, D.Nb, c);
             if (b >= D.Nb) { err |= DEV_ERR_INVARIANT; continue; }
             const int kind = bond_kind(D, b);
             uint32_t v0, v1;
             bond_vars(D, b, kind, v0, v1);
             const uint32_t s0 = state_bit(V.state, v0), s1 = kind == KIND_BOND ? state_bit(V.state, v1) : 0u;
-            if (pd * __ldg(D.hb_maxw + b) < bond_weight(D, b, kind, s0, s1)) {
+            if (pd * __ldg(Hm.hb_maxw + b) < bond_weight(Hm, b, kind, s0, s1)) {
                 const uint32_t bitsv = s0 | (s1 << 1);
                 V.ops[p] = make_op(b, bitsv, bitsv);
                 n++;
@@ -645,6 +647,7 @@ __global__ void __launch_bounds__(128) k_sse_serial(SseDev D, int mode, uint64_t
 __global__ void k_sse_verify(SseDev D, uint32_t r, int *ok_out, uint32_t *scratch) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const Rep V = rep_view(D, r);
+    const Ham Hm = ham_view<true>(D, r);
     uint32_t *roll = scratch;
     for (uint32_t j = 0; j < D.Nw; j++) roll[j] = V.state[j];
     int ok = 1;
@@ -663,8 +666,8 @@ __global__ void k_sse_verify(SseDev D, uint32_t r, int *ok_out, uint32_t *scratc
         uint32_t in = op_in(w), out = op_out(w);
         if (kind != KIND_SITE) {
             if (in != out) ok = 0;  // off-diagonal two-site / longitudinal ops have zero weight
-            else if (!(fabs(bond_weight(D, b, kind, in & 1u, (in >> 1) & 1u)) > 2.220446049250313e-16)) ok = 0;
-        } else if (!(fabs(D.gamma) > 2.220446049250313e-16)) ok = 0;
+            else if (!(fabs(bond_weight(Hm, b, kind, in & 1u, (in >> 1) & 1u)) > 2.220446049250313e-16)) ok = 0;
+        } else if (!(fabs(Hm.gamma) > 2.220446049250313e-16)) ok = 0;
         if (state_bit(roll, v0) != (in & 1u)) ok = 0;
         roll[v0 >> 5] = (roll[v0 >> 5] & ~(1u << (v0 & 31))) | ((out & 1u) << (v0 & 31));
         if (kind == KIND_BOND) {

@@ -114,6 +114,29 @@ class QmcIsingGraph:
         check(self._L.qmcb_get_enable_heatbath(self._h, C.byref(out)))
         return bool(out.value)
 
+    def set_hamiltonians(self, J_tab, transverse, longitudinal, ham_of_replica):
+        """Replicas with their own couplings (the reference builds one graph per Hamiltonian): J_tab[H][E],
+        transverse[H], longitudinal[H]; ham_of_replica[R] picks the row.  can_swap_managers
+        (qmc_ising.rs:563-590) must hold between rows."""
+        J = np.ascontiguousarray(J_tab, dtype=np.float64).reshape(len(transverse), -1)
+        t = np.ascontiguousarray(transverse, dtype=np.float64)
+        l = np.ascontiguousarray(longitudinal, dtype=np.float64)
+        hr = np.ascontiguousarray(ham_of_replica, dtype=np.uint32)
+        if J.shape[1] != len(self._edges) or len(l) != len(t) or len(hr) != self.R:
+            raise ValueError("Hamiltonian table shapes do not match the batch")
+        check(self._L.qmcb_set_hamiltonians(self._h, len(t), ptr(J, C.c_double), ptr(t, C.c_double), ptr(l, C.c_double),
+                                            ptr(hr, C.c_uint32)))
+
+    def hamiltonian_index(self):
+        out = np.zeros(self.R, dtype=np.uint32)
+        check(self._L.qmcb_get_hamiltonian_index(self._h, ptr(out, C.c_uint32)))
+        return out
+
+    def get_offsets(self):
+        out = np.zeros(self.R, dtype=np.float64)
+        check(self._L.qmcb_get_offsets(self._h, ptr(out, C.c_double)))
+        return out
+
     def set_option(self, name, value):
         check(self._L.qmcb_set_option(self._h, name.encode(), int(value)))
 

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from ._lib import MODE_FAST, check, ptr
 
-REC_WORDS = 4  # {slot, n, cursor, cutoff} as uint64 (int64 on the wire)
+REC_WORDS = 4  # {slot, n, cursor, cutoff} as uint64 (int64 on the wire); 8 with per-slot Hamiltonians
 
 
 def partition_slots(n_slots: int, world_size: int, rank: int):
@@ -45,7 +45,7 @@ class TemperingContainer:
     the whole ladder at construction (all slots share one lattice, so can_swap_graphs holds)."""
 
     def __init__(self, edges, transverse, longitudinal, cutoff, betas, n_chains=1, rng_keys=None, pt_key=0x9E37,
-                 mode=MODE_FAST, device=None, group=None, capacity=0):
+                 mode=MODE_FAST, device=None, group=None, capacity=0, slot_hamiltonians=None):
         import torch
         import torch.distributed as dist
 
@@ -73,7 +73,24 @@ class TemperingContainer:
         L = self.graph._L
         check(L.qmcb_pt_configure(self.graph._h, self.n_chains, self.n_betas, self.slot_begin,
                                   ptr(self.betas_global, C.c_double), ptr(self.keys_global, C.c_uint64), int(pt_key)))
-        self._rec = torch.empty((self.R, REC_WORDS), dtype=torch.int64, device=f"cuda:{device}")
+        if slot_hamiltonians is not None:
+            # one Hamiltonian per ladder position, as graphs with their own couplings handed to add_qmc_stepper
+            # (tempering_container.rs:62-75); swaps use GraphWeights::relative_weight (tempering_traits.rs:126-154)
+            if len(slot_hamiltonians) != self.n_betas:
+                raise ValueError("one (J, transverse, longitudinal) per ladder position")
+            J0 = np.array([e[1] for e in edges], dtype=np.float64)
+            J_tab = np.stack([J0 if hj is None else np.asarray(hj, dtype=np.float64) for hj, _, _ in slot_hamiltonians])
+            tr = [t for _, t, _ in slot_hamiltonians]
+            lo = [l for _, _, l in slot_hamiltonians]
+            ham_of_slot = np.ascontiguousarray(np.tile(np.arange(self.n_betas, dtype=np.uint32), self.n_chains))
+            self.graph.set_hamiltonians(J_tab, tr, lo, ham_of_slot[sl])
+            check(L.qmcb_pt_set_slot_hamiltonians(self.graph._h, ptr(ham_of_slot, C.c_uint32)))
+        self._alloc_records()
+
+    def _alloc_records(self):
+        w = C.c_uint32()
+        check(self.graph._L.qmcb_pt_record_words(self.graph._h, C.byref(w)))
+        self._rec = self._torch.empty((self.R, w.value), dtype=self._torch.int64, device=f"cuda:{self.device}")
 
     # -- checkpoints (replaces SerializeTemperingContainer, tempering_container.rs:671-793) -----
     def save_checkpoint(self) -> bytes:
@@ -100,7 +117,7 @@ class TemperingContainer:
         tc.n_chains, tc.n_betas, tc.slot_begin, tc.R = nc.value, nb.value, sb.value, tc.graph.R
         tc.S = tc.n_chains * tc.n_betas
         tc.betas_global = tc.keys_global = None  # live in the handle
-        tc._rec = torch.empty((tc.R, REC_WORDS), dtype=torch.int64, device=f"cuda:{tc.device}")
+        tc._alloc_records()
         return tc
 
     def num_graphs(self):

@@ -992,14 +992,68 @@ static void swap_manager_and_state(OrcSse *a, OrcSse *b) {
 #undef SWAPF
 }
 
+/* GraphWeights::ham_eq (tempering_traits.rs:122-124) -> HamInfo::eq (qmc_ising.rs:899-903): edges and
+ * transverse field only; the longitudinal field is NOT compared */
+static int ham_eq(const OrcSse *a, const OrcSse *b) {
+    if (a->nedges != b->nedges || a->transverse != b->transverse) return 0;
+    for (uint32_t e = 0; e < a->nedges; e++)
+        if (a->ea[e] != b->ea[e] || a->eb[e] != b->eb[e] || a->J[e] != b->J[e]) return 0;
+    return 1;
+}
+
+/* GraphWeights::relative_weight (tempering_traits.rs:126-154): weight of self's operators under h's
+ * couplings relative to self's own */
+static double relative_weight(const OrcSse *self, const OrcSse *h) {
+    const uint32_t nb = self->nedges + 2 * self->nvars;
+    uint64_t *count = (uint64_t *)calloc(nb, sizeof(uint64_t)); /* get_count, fast_ops.rs:1281-1294 */
+    for (uint64_t p = 0; p < self->ops_len; p++)
+        if (self->ops[p].present) count[self->ops[p].bond]++;
+    double bond_ratio = 1.0; /* Iterator::product */
+    for (uint32_t b = 0; b < self->nedges; b++) {
+        double ja = h->J[b], jb = self->J[b]; /* h.get_edges().zip(self.get_edges()) */
+        bond_ratio = bond_ratio * orc_powi(ja / jb, (int32_t)count[b]);
+    }
+    uint64_t t_count = 0;
+    for (uint32_t v = 0; v < self->nvars; v++) t_count += count[v + self->nedges];
+    double transverse_ratio = orc_powi(h->transverse / self->transverse, (int32_t)t_count);
+    double res;
+    if (fabs(self->longitudinal) > DBL_EPSILON) {
+        uint64_t l_count = 0;
+        for (uint32_t v = 0; v < self->nvars; v++) l_count += count[v + self->nvars + self->nedges];
+        double longitudinal_ratio = orc_powi(h->longitudinal / self->longitudinal, (int32_t)l_count);
+        res = bond_ratio * transverse_ratio * longitudinal_ratio;
+    } else {
+        res = bond_ratio * transverse_ratio;
+    }
+    free(count);
+    return res;
+}
+
+/* SwapManagers::can_swap_graphs -> can_swap_managers (qmc_ising.rs:563-590); 0 = ok */
+int orc_sse_can_swap(const OrcSse *a, const OrcSse *b) {
+    if (a->nedges != b->nedges) return 1;
+    for (uint32_t e = 0; e < a->nedges; e++) {
+        if (a->ea[e] != b->ea[e] || a->eb[e] != b->eb[e]) return 1;
+        if (signbit(a->J[e]) != signbit(b->J[e])) return 2;
+    }
+    if (signbit(a->longitudinal) != signbit(b->longitudinal)) return 3;
+    return 0;
+}
+
 static uint64_t perform_swaps(Stream *rng, OrcSse **graphs, const double *betas, uint32_t len) {
-    /* tempering_container.rs:241-260; all Hamiltonians equal => rel_h_weight = 1.0 (:286-292) */
+    /* tempering_container.rs:241-260, swap_on_chunks :274-302 */
     uint64_t swaps = 0;
     for (uint32_t i = 0; i + 1 < len; i += 2) {
         double p = gen_range_f64_01(rng); /* :255 */
         OrcSse *ga = graphs[i], *gb = graphs[i + 1];
+        double rel_h_weight = 1.0; /* :286-292; hameqs :109-119 */
+        if (!ham_eq(ga, gb)) {
+            double rel_bstate = relative_weight(ga, gb);
+            double rel_astate = relative_weight(gb, ga);
+            rel_h_weight = rel_bstate * rel_astate;
+        }
         double temp_swap = orc_powi(betas[i] / betas[i + 1], (int32_t)gb->n - (int32_t)ga->n); /* :294 */
-        double p_swap = temp_swap * 1.0;
+        double p_swap = temp_swap * rel_h_weight;
         if (p_swap > p) { /* :296-301 */
             swap_manager_and_state(ga, gb);
             swaps++;

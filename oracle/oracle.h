@@ -91,6 +91,8 @@ uint64_t orc_sse_batch_timesteps(OrcSse **reps, uint32_t nreps, uint64_t t, cons
 /* ---- parallel tempering (TemperingContainer) ---------------------------------- */
 /* one tempering_step over slots[0..nslots); swaps op strings + states between slots.
  * Returns the number of swaps performed; *pt_cursor advances over the PT stream. */
+/* can_swap_managers (qmc_ising.rs:563-590): 0 ok, 1 edges differ, 2 bond signs differ, 3 field signs differ */
+int orc_sse_can_swap(const OrcSse *a, const OrcSse *b);
 uint64_t orc_pt_step(OrcSse **slots, uint32_t nslots, const double *betas, uint64_t pt_key,
                      uint64_t *pt_cursor);
 

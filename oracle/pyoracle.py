@@ -79,6 +79,7 @@ def lib():
     sig("orc_sse_verify", C.c_int, vp)
     sig("orc_sse_get_boundaries", None, vp, i64p, i64p, C.c_uint64)
     sig("orc_sse_batch_timesteps", C.c_uint64, C.POINTER(vp), C.c_uint32, C.c_uint64, f64p, C.c_int, f64p, C.c_int)
+    sig("orc_sse_can_swap", C.c_int, vp, vp)
     sig("orc_pt_step", C.c_uint64, C.POINTER(vp), C.c_uint32, f64p, C.c_uint64, u64p)
     sig("orc_cls_create", vp, C.c_uint32, C.c_uint32, u32p, u32p, f64p, f64p, C.c_uint64, u8p)
     sig("orc_cls_destroy", None, vp)

@@ -54,7 +54,8 @@ def test_checkpoint_rejects_corruption_and_truncation():
         QmcIsingGraph.from_checkpoint(bytes(blob))
 
 
-def test_tempering_checkpoint_round_trip():
+@pytest.mark.parametrize("unequal", [False, True])
+def test_tempering_checkpoint_round_trip(unequal):
     import torch
 
     from isingmontecarlo_b200.tempering import TemperingContainer
@@ -62,7 +63,8 @@ def test_tempering_checkpoint_round_trip():
     torch.cuda.set_device(0)
     edges = lattices.square_periodic(4, -1.0)
     betas = np.geomspace(0.3, 3.0, 6)
-    tc = TemperingContainer(edges, 2.0, 0.0, 16, betas, n_chains=2, pt_key=0xABCD, mode=MODE_FAST)
+    hams = [(None, 2.0 + 0.1 * k, 0.0) for k in range(6)] if unequal else None
+    tc = TemperingContainer(edges, 2.0, 0.0, 16, betas, n_chains=2, pt_key=0xABCD, mode=MODE_FAST, slot_hamiltonians=hams)
     for _ in range(12):
         tc.timesteps(2)
         tc.tempering_step()
@@ -72,12 +74,13 @@ def test_tempering_checkpoint_round_trip():
         for _ in range(8):
             c.timesteps(2)
             c.tempering_step()
-        return snapshot(c.graph), c.slots().copy(), c.get_total_swaps(), c.graph.betas().copy()
+        return snapshot(c.graph), c.slots().copy(), c.get_total_swaps(), c.graph.betas().copy(), c.graph.hamiltonian_index().copy()
 
     a = cont(tc)
     tc2 = TemperingContainer.from_checkpoint(blob)
     assert tc2.S == 12 and tc2.n_betas == 6
     b = cont(tc2)
     assert a[2] == b[2] and a[2] > 0
-    assert np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    assert unequal == (len(set(a[4])) > 1)
     assert same_snapshot(a[0], b[0])

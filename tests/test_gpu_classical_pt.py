@@ -145,3 +145,86 @@ def test_tempering_over_nccl_two_ranks():
                          capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert res.stdout.count(" ok ") == 2
+
+
+@pytest.mark.parametrize("mode", [MODE_STRICT, MODE_FAST])
+@pytest.mark.parametrize("with_h,heatbath", [(False, False), (True, False), (True, True)])
+def test_tempering_between_unequal_hamiltonians_matches_reference(with_h, heatbath, mode):
+    """GraphWeights::relative_weight / ham_eq (tempering_traits.rs:122-154) in swap_on_chunks
+    (tempering_container.rs:274-302): every ladder position has its own couplings."""
+    from isingmontecarlo_b200.tempering import TemperingContainer
+
+    edges = lattices.two_d_periodic_mixed(4)
+    n_chains, n_betas = 2, 5
+    betas = np.linspace(0.6, 1.4, n_betas)
+    J0 = np.array([j for _, j in edges])
+    # positions 0 and 1 share a Hamiltonian (ham_eq true -> factor 1); 1 -> 2 changes Gamma only; 2 -> 3 rescales
+    # the couplings; 3 -> 4 changes the longitudinal field only (which ham_eq ignores, qmc_ising.rs:899-903)
+    hl = (lambda x: x) if with_h else (lambda x: 0.0)
+    hams = [(J0, 1.0, hl(0.5)), (J0, 1.0, hl(0.5)), (J0, 1.2, hl(0.5)), (1.1 * J0, 1.2, hl(0.45)), (1.1 * J0, 1.2, hl(0.6))]
+    S = n_chains * n_betas
+    keys = 0x55E10000 + np.arange(S, dtype=np.uint64)
+    pt_key = 0xFEED
+    tc = TemperingContainer(edges, hams[0][1], hams[0][2], 16, betas, n_chains=n_chains, rng_keys=keys, pt_key=pt_key, mode=mode,
+                            slot_hamiltonians=hams)
+    tc.graph.set_enable_heatbath(heatbath)
+
+    def ref_graph(c, k):
+        ek = [(e, float(j)) for (e, _), j in zip(edges, hams[k][0])]
+        g = po.SseOracle(ek, hams[k][1], hams[k][2], 16, key=int(keys[c * n_betas + k]))
+        g.set_enable_heatbath(heatbath)
+        return g
+
+    slots = [[ref_graph(c, k) for k in range(n_betas)] for c in range(n_chains)]
+    assert np.array_equal(tc.graph.get_offsets(), [slots[s // n_betas][s % n_betas].offset for s in range(S)])
+    cursors = [0] * n_chains
+    swaps_ref = 0
+    for step in range(14):
+        e_gpu = tc.timesteps(3)
+        slot_before = tc.slots()
+        for c in range(n_chains):
+            for k in range(n_betas):
+                e_ref = slots[c][k].timesteps(3, float(betas[k]), mode)
+                s_local = int(np.where(slot_before == c * n_betas + k)[0][0])
+                assert e_gpu[s_local] == e_ref  # offsets follow the slot's Hamiltonian
+        tc.tempering_step()
+        for c in range(n_chains):
+            s, cursors[c] = po.pt_step(slots[c], betas, pt_key + c, cursors[c])
+            swaps_ref += s
+        g = tc.graph
+        n, cut, cur, st, hidx = g.get_n(), g.get_cutoff(), g.rng_cursors(), g.state_ref(), g.hamiltonian_index()
+        for s_local, slot in enumerate(tc.slots()):
+            ref = slots[slot // n_betas][slot % n_betas]
+            assert hidx[s_local] == slot % n_betas
+            assert int(n[s_local]) == ref.n and int(cut[s_local]) == ref.cutoff and int(cur[s_local]) == ref.cursor
+            assert np.array_equal(st[s_local], ref.state())
+            assert np.array_equal(g.dump_ops(s_local), ref.dump_ops())
+        assert tc.get_total_swaps() == swaps_ref
+    assert swaps_ref > 0 and tc.verify() and all(r.error == 0 for row in slots for r in row)
+
+
+def test_can_swap_graphs_is_enforced():
+    from isingmontecarlo_b200 import QmcbError
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.two_d_periodic_mixed(4)
+    J0 = np.array([j for _, j in edges])
+    g = QmcIsingGraph(edges, 1.0, 0.5, 16, [1, 2], 1.0, mode=MODE_FAST)
+    Jbad = J0.copy()
+    Jbad[3] = -Jbad[3]
+    with pytest.raises(QmcbError, match="same sign"):  # qmc_ising.rs:572-577
+        g.set_hamiltonians([J0, Jbad], [1.0, 1.0], [0.5, 0.5], [0, 1])
+    with pytest.raises(QmcbError, match="same sign"):  # qmc_ising.rs:581-586
+        g.set_hamiltonians([J0, J0], [1.0, 1.0], [0.5, -0.5], [0, 1])
+    a = po.SseOracle(edges, 1.0, 0.5, 16)
+    b = po.SseOracle([(e, -j) for e, j in edges], 1.0, 0.5, 16)
+    c = po.SseOracle(edges, 2.0, -0.5, 16)
+    L = po.lib()
+    assert L.orc_sse_can_swap(a._h, a._h) == 0 and L.orc_sse_can_swap(a._h, b._h) == 2 and L.orc_sse_can_swap(a._h, c._h) == 3
+    g.set_hamiltonians([J0, 2 * J0], [1.0, 3.0], [0.5, 0.25], [1, 0])
+    assert list(g.hamiltonian_index()) == [1, 0]
+    refs = [po.SseOracle([(e, 2 * j) for e, j in edges], 3.0, 0.25, 16, key=1), po.SseOracle(edges, 1.0, 0.5, 16, key=2)]
+    e = g.timesteps(20, 1.0)
+    for r, ref in enumerate(refs):
+        assert e[r] == ref.timesteps(20, 1.0, MODE_FAST)
+        assert np.array_equal(g.dump_ops(r), ref.dump_ops()) and np.array_equal(g.state_ref()[r], ref.state())
