@@ -79,12 +79,13 @@ struct WarpSmem {
     uint32_t *fl;   // [32] variable flipped by the off-diagonal op of lane j (or NONE32)
     uint32_t *sv;   // [32] variable cut by the site op of lane j (or NONE32)
     uint32_t *opw;  // [64] op word an empty slot would insert from window word y
-    unsigned char *G;  // [64] cursor after an empty slot that starts reading at window position x
-    unsigned char *wk, *wx, *wg, *wl;  // [32] walk: gap before, start cursor, cursor after, lane of the k-th EMPTY lane
+    unsigned char *G;  // [80] cursor after an empty slot that starts reading at window position x; G[64] = 255
+    unsigned char *wk, *wl;  // [32] walk: draws of diagonal ops since the previous EMPTY lane, lane of the k-th EMPTY lane
+    unsigned short *wxg;     // [32] walk: start cursor | cursor after << 8 of the k-th EMPTY lane
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
-    return ((((size_t)3 * Nw + N + 64 + 64 + 16 + 32) * 4 + 64 * 8) + 15) / 16 * 16;
+    return ((((size_t)3 * Nw + N + 64 + 64 + 20 + 32) * 4 + 64 * 8) + 15) / 16 * 16;
 }
 
 template <bool HAS_H, int MINB, bool HB, bool MH>
@@ -100,7 +101,8 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
         unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(N, Nw);
         S.win = (unsigned long long *)base;
         uint32_t *u = (uint32_t *)(base + 64 * 8);
-        S.st = u, S.tb = u + Nw, S.cd = u + 2 * Nw, S.rep = u + 3 * Nw, S.fl = u + 3 * Nw + N, S.sv = S.fl + 32, S.opw = S.sv + 32, S.G = (unsigned char *)(S.opw + 64), S.wk = S.G + 64, S.wx = S.wk + 32, S.wg = S.wx + 32, S.wl = S.wg + 32;
+        S.st = u, S.tb = u + Nw, S.cd = u + 2 * Nw, S.rep = u + 3 * Nw, S.fl = u + 3 * Nw + N, S.sv = S.fl + 32, S.opw = S.sv + 32, S.G = (unsigned char *)(S.opw + 64), S.wk = S.G + 80, S.wl = S.wk + 32, S.wxg = (unsigned short *)(S.wl + 32);
+        if (lane < 16) S.G[64 + lane] = 255;  // positions past the window: exhausted (absorbing state of the walk)
     }
     uint32_t *ops = D.ops + (size_t)r * D.cap;
     uint32_t *gstate = D.state + (size_t)r * Nw;
@@ -235,16 +237,16 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                                     break;
                                 }
                                 x = xs + 1u + 2u * (uint32_t)((ATT >> xs) & 1ull);
-                                S.wx[k] = (unsigned char)xs, S.wg[k] = (unsigned char)x;
+                                S.wxg[k] = (unsigned short)(xs | (x << 8));
                             }
                             __syncwarp();
                             const uint32_t kstop = k;
                             uint32_t myx = 0;
                             bool res = false;
-                            if (inrem && type == T_EMPTY) res = kidx < kstop, myx = res ? (uint32_t)S.wx[kidx] : 0u;
+                            if (inrem && type == T_EMPTY) res = kidx < kstop, myx = res ? (uint32_t)S.wxg[kidx] & 255u : 0u;
                             else if (inrem) {
                                 res = kidx <= kstop && (uint32_t)lane < stop;
-                                myx = (kidx == 0 ? x0 : (res ? (uint32_t)S.wg[kidx - 1] : 0u)) + dcount;
+                                myx = (kidx == 0 ? x0 : (res ? (uint32_t)S.wxg[kidx - 1] >> 8 : 0u)) + dcount;
                             }
                             const uint32_t ovD = __ballot_sync(FULL, res && type == T_DIAG && myx >= 64u);
                             if (ovD) stop = min(stop, (uint32_t)__ffs(ovD) - 1u);
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                             bool unres = false;
                             if ((resolved >> lane) & 1u) {
                                 if (type == T_EMPTY) {
-                                    dc = (uint32_t)S.wg[kidx] - myx;
+                                    dc = ((uint32_t)S.wxg[kidx] >> 8) - myx;
                                     neww = OP_EMPTY;
                                     if (dc == 3u && try_insert(S.win[myx + 1], S.win[myx + 2], neww)) dn = 1;
                                 } else {
@@ -424,19 +426,26 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                         const uint32_t nE = (uint32_t)__popc(stopA < 32u ? (remE & ((1u << stopA) - 1u)) : remE);
                         uint32_t k = 0;
                         for (;;) {
-                            uint32_t hz_x = 0xFFFFFFFFu;
-                            for (; k < nE; k++) {  // tight loop; the rare hazard is handled outside
-                                const uint32_t xs = x + S.wk[k];
-                                const uint32_t g = xs < 64u ? (uint32_t)S.G[xs] : 255u;
-                                if (g >= 254u) {
-                                    if (g == 255u) stop = S.wl[k];
-                                    else hz_x = xs;
-                                    break;
-                                }
-                                S.wx[k] = (unsigned char)xs, S.wg[k] = (unsigned char)g;
-                                x = g;
+                            // branch-free: a hazard (254) or an exhausted window (255) is absorbing, since every later
+                            // start is clamped to G[64] = 255; the first such k is found afterwards with one ballot
+                            const uint32_t kbeg = k;
+#pragma unroll 4
+                            for (uint32_t kk = kbeg; kk < nE; kk++) {
+                                const uint32_t xs = min(x + (uint32_t)S.wk[kk], 64u);
+                                x = S.G[xs];
+                                S.wxg[kk] = (unsigned short)(xs | (x << 8));
                             }
-                            if (hz_x == 0xFFFFFFFFu) break;
+                            __syncwarp();
+                            const uint32_t mine = ((uint32_t)lane >= kbeg && (uint32_t)lane < nE) ? (uint32_t)S.wxg[lane] : 0u;
+                            const uint32_t badm = __ballot_sync(FULL, (mine >> 8) >= 254u);
+                            k = badm ? (uint32_t)__ffs(badm) - 1u : nE;
+                            if (!badm) break;
+                            const uint32_t first = __shfl_sync(FULL, mine, (int)k);
+                            if ((first >> 8) == 255u) {
+                                stop = S.wl[k];
+                                break;
+                            }
+                            const uint32_t hz_x = first & 255u;
                             // hazard: the word's spins are flipped inside this step -> evaluate for that lane
                             DBG(12, 1);
                             const uint32_t i = S.wl[k], xs = hz_x;
@@ -464,7 +473,8 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                             if (fail) { stop = i, hz_fail = true; break; }
                             const uint32_t g = y + 1u + (ex ? 1u : 0u);
                             if ((uint32_t)lane == i) overridden = true, neww = ok ? make_op(b, bitsv, bitsv) : OP_EMPTY, dn = ok, dc = g - xs;
-                            S.wx[k] = (unsigned char)xs, S.wg[k] = (unsigned char)g;
+                            __syncwarp();
+                            S.wxg[k] = (unsigned short)(xs | (g << 8));
                             x = g;
                             k++;
                         }
@@ -473,8 +483,8 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                         // after their last EMPTY predecessor plus the diagonal draws in between
                         TICK(4);  // successor table + walk
                         const uint32_t kstop = k;  // EMPTY lanes with index >= kstop are unresolved
-                        if (type == T_EMPTY) myx = kidx < kstop ? (uint32_t)S.wx[kidx] : 0u;
-                        else myx = (kidx == 0 ? x0 : (kidx <= kstop ? (uint32_t)S.wg[kidx - 1] : 0u)) + dcount;
+                        if (type == T_EMPTY) myx = kidx < kstop ? (uint32_t)S.wxg[kidx] & 255u : 0u;
+                        else myx = (kidx == 0 ? x0 : (kidx <= kstop ? (uint32_t)S.wxg[kidx - 1] >> 8 : 0u)) + dcount;
                         if (stop >= 32u && kstop < nE) stop = S.wl[kstop];
                         if (stop >= 32u && stopA < 32u) stop = stopA;
                         bool need_exact = hz_fail || (stopA < 32u && stop == stopA);
