@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "_build", "libqmcb.so")
+SO_PATH = os.environ.get("QMCB_LIB") or os.path.join(_HERE, "_build", "libqmcb.so")  # QMCB_LIB: kernel experiments only
 
 OK, ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_UNSUPPORTED, ERR_INTERNAL = 0, -1, -2, -3, -4, -5
 MODE_STRICT, MODE_FAST = 0, 1

@@ -286,6 +286,15 @@ extern "C" int qmcb_create(const QmcbLattice *lat, uint32_t R, const double *bet
     TRYC(cudaMemcpy(vb, lat->vb, sizeof(uint32_t) * D.E, cudaMemcpyHostToDevice));
     TRYC(cudaMemcpy(J, lat->J, sizeof(double) * D.E, cudaMemcpyHostToDevice));
     D.va = va, D.vb = vb, D.J = J;
+    {
+        std::vector<uint2> vab(D.E);
+        for (uint32_t e = 0; e < D.E; e++) vab[e] = make_uint2(lat->va[e], lat->vb[e]);
+        uint2 *vab_dev;
+        TRYC(h->pool.alloc(&vab_dev, D.E));
+        TRYC(cudaMemcpy(vab_dev, vab.data(), sizeof(uint2) * D.E, cudaMemcpyHostToDevice));
+        D.vab = vab_dev;
+        D.zone = ((uint64_t)D.Nb << __builtin_clzll((uint64_t)D.Nb)) - 1ull;
+    }
     h->va_h.assign(lat->va, lat->va + D.E), h->vb_h.assign(lat->vb, lat->vb + D.E), h->J_h.assign(lat->J, lat->J + D.E);
     h->Jtab_h = h->J_h, h->gam_h = {lat->transverse}, h->hl_h = {lat->longitudinal}, h->offset_h = {h->offset};
     TRYC(h->pool.alloc(&D.ops, (size_t)R * D.cap));

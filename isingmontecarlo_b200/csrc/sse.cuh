@@ -10,7 +10,9 @@ struct SseDev {
     uint32_t N, E, Nb, Nw;  // variables, edges, bond-index count (qmc_ising.rs:664-670), state words
     int has_h;              // |h| > f64::EPSILON
     const uint32_t *va, *vb;
+    const uint2 *vab;       // [E] both variables of an edge in one 8-byte word
     const double *J;
+    uint64_t zone;          // rand 0.8 gen_range(0..Nb) acceptance zone: (Nb << lzcnt(Nb)) - 1
     double gamma, h;
     // batch
     uint32_t R;
@@ -82,7 +84,12 @@ __device__ __forceinline__ int bond_kind(const SseDev &D, uint32_t b) {
 }
 __device__ __forceinline__ void bond_vars(const SseDev &D, uint32_t b, int kind, uint32_t &v0, uint32_t &v1) {
     if (kind == KIND_BOND) {
+#ifdef QMCB_SPLIT_EDGES
         v0 = __ldg(D.va + b), v1 = __ldg(D.vb + b);
+#else
+        const uint2 e = __ldg(D.vab + b);
+        v0 = e.x, v1 = e.y;
+#endif
     } else {
         v0 = b - D.E - (kind == KIND_LONG ? D.N : 0u), v1 = v0;
     }

@@ -70,52 +70,84 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
     return x - v;
 }
 
+// lattice helpers specialised on HAS_H: without a longitudinal field there are no KIND_LONG bonds
+template <bool HAS_H>
+__device__ __forceinline__ int bkind(const SseDev &D, uint32_t b) {
+    return b < D.E ? KIND_BOND : ((!HAS_H || b < D.E + D.N) ? KIND_SITE : KIND_LONG);
+}
+template <bool HAS_H>
+__device__ __forceinline__ double bweight(const Ham &Hm, uint32_t b, int kind, uint32_t s0, uint32_t s1) {
+    if (kind == KIND_BOND) {
+        const double j = __ldg(Hm.J + b);
+        return fabs(j) + (s0 == s1 ? -j : j);
+    }
+    if (!HAS_H || kind == KIND_SITE) return Hm.gamma;
+    return fabs(Hm.h) + (s0 ? Hm.h : -Hm.h);
+}
+
+// shared memory of one replica (= one block of one warp).  The fixed-size tables sit at constant offsets from the
+// start of the block's shared memory, so that their addresses are immediates; the lattice-sized ones follow.
 struct WarpSmem {
-    uint32_t *st;   // [Nw] spin bits at the current p
-    uint32_t *tb;   // [Nw] variable has at least one op
-    uint32_t *cd;   // [Nw] P3: flip decision of the segment currently open on each variable
-    uint32_t *rep;  // [N]  P1: a member of the set of the segment currently open on each variable
     unsigned long long *win;  // [64] stream words of this step
     uint32_t *fl;   // [32] variable flipped by the off-diagonal op of lane j (or NONE32)
-    uint32_t *sv;   // [32] variable cut by the site op of lane j (or NONE32)
     uint32_t *opw;  // [64] op word an empty slot would insert from window word y
     unsigned char *G;  // [80] cursor after an empty slot that starts reading at window position x; G[64] = 255
     unsigned char *wk, *wl;  // [32] walk: draws of diagonal ops since the previous EMPTY lane, lane of the k-th EMPTY lane
     unsigned short *wxg;     // [32] walk: start cursor | cursor after << 8 of the k-th EMPTY lane
+    uint32_t *st;   // [Nw] spin bits at the current p
+    uint32_t *tb;   // [Nw] variable has at least one op
+    uint32_t *cd;   // [Nw] P1: variable is flipped inside this step; P3: flip decision of the segment open on each variable
+    uint32_t *rep;  // [N]  P1: a member of the set of the segment currently open on each variable
 };
+#define SM_WIN 0
+#define SM_FL 512
+#define SM_OPW 640
+#define SM_G 896
+#define SM_WK 976
+#define SM_WL 1008
+#define SM_WXG 1040
+#define SM_VAR 1104  // st, tb, cd, rep
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
-    return ((((size_t)3 * Nw + N + 64 + 64 + 20 + 32) * 4 + 64 * 8) + 15) / 16 * 16;
+    return (SM_VAR + ((size_t)3 * Nw + N) * 4 + 15) / 16 * 16;
 }
 
+#ifndef QMCB_WPB
+#define QMCB_WPB 4  // warps (= replicas) per block: one per scheduler of the SM (1 or 2 per block measured 8-12% slower)
+#endif
 template <bool HAS_H, int MINB, bool HB, bool MH>
-__global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
-                                                  uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + wib;
+__global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
+                                                  uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, uint32_t smem_stride) {
+    extern __shared__ __align__(16) unsigned char smem_all[];
+#if QMCB_WPB == 1
+    unsigned char *const smem_raw = smem_all;
+    const int lane = threadIdx.x;
+    const uint32_t r = blockIdx.x;
+#else
+    unsigned char *const smem_raw = smem_all + (threadIdx.x >> 5) * smem_stride;
+    const int lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * QMCB_WPB + (threadIdx.x >> 5);
+#endif
     if (r >= D.R) return;
     const uint32_t N = D.N, Nw = D.Nw;
     WarpSmem S;
-    {
-        unsigned char *base = smem_raw + (size_t)wib * warp_smem_bytes(N, Nw);
-        S.win = (unsigned long long *)base;
-        uint32_t *u = (uint32_t *)(base + 64 * 8);
-        S.st = u, S.tb = u + Nw, S.cd = u + 2 * Nw, S.rep = u + 3 * Nw, S.fl = u + 3 * Nw + N, S.sv = S.fl + 32, S.opw = S.sv + 32, S.G = (unsigned char *)(S.opw + 64), S.wk = S.G + 80, S.wl = S.wk + 32, S.wxg = (unsigned short *)(S.wl + 32);
-        if (lane < 16) S.G[64 + lane] = 255;  // positions past the window: exhausted (absorbing state of the walk)
-    }
+    S.win = (unsigned long long *)(smem_raw + SM_WIN), S.fl = (uint32_t *)(smem_raw + SM_FL), S.opw = (uint32_t *)(smem_raw + SM_OPW);
+    S.G = smem_raw + SM_G, S.wk = smem_raw + SM_WK, S.wl = smem_raw + SM_WL, S.wxg = (unsigned short *)(smem_raw + SM_WXG);
+    S.st = (uint32_t *)(smem_raw + SM_VAR), S.tb = S.st + Nw, S.cd = S.st + 2 * Nw, S.rep = S.st + 3 * Nw;
+    if (lane < 16) S.G[64 + lane] = 255;  // positions past the window: exhausted (absorbing state of the walk)
     uint32_t *ops = D.ops + (size_t)r * D.cap;
     uint32_t *gstate = D.state + (size_t)r * Nw;
     uint32_t *P = D.parent + (size_t)r * (N + D.cap + 1);
     const size_t bstride = (size_t)(D.cap / 32 + 2 + N / 32);
     uint32_t *decb = D.bits + (size_t)r * bstride;
     uint32_t *frz = D.frozen + (size_t)r * bstride;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     const uint64_t key = D.key[r];
     const Ham Hm = ham_view<MH>(D, r);
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     const uint64_t range = D.Nb;
-    const uint64_t zone = (range << __clzll((long long)range)) - 1ull;
+    const uint64_t zone = D.zone;
 #ifdef QMCB_PHASE_TIMERS
     long long tick_ = clock64();
 #endif
@@ -159,7 +191,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
             uint32_t ov0 = 0, ov1 = 0;
             int okind = KIND_BOND;
             if (type >= T_DIAG) {
-                okind = bond_kind(D, op_bond(w));
+                okind = bkind<HAS_H>(D, op_bond(w));
                 bond_vars(D, op_bond(w), okind, ov0, ov1);
             }
             if (do_diag) {
@@ -188,11 +220,11 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                         if (!(pd < 1.0) || !(c < total)) { err |= DEV_ERR_INVARIANT; return false; }
                         const uint32_t b = hb_index_for_cumulative(Hm.hb_cum, D.Nb, c);
                         if (b >= D.Nb) { err |= DEV_ERR_INVARIANT; return false; }
-                        const int kind = bond_kind(D, b);
+                        const int kind = bkind<HAS_H>(D, b);
                         uint32_t v0, v1;
                         bond_vars(D, b, kind, v0, v1);
                         const uint32_t s0 = spin_here(v0), s1 = kind == KIND_BOND ? spin_here(v1) : 0u;
-                        if (!(pd * __ldg(Hm.hb_maxw + b) < bond_weight(Hm, b, kind, s0, s1))) return false;
+                        if (!(pd * __ldg(Hm.hb_maxw + b) < bweight<HAS_H>(Hm, b, kind, s0, s1))) return false;
                         const uint32_t bitsv = s0 | (s1 << 1);
                         nw = make_op(b, bitsv, bitsv);
                         return true;
@@ -315,7 +347,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                     }
                 }
                 double dnum = 0.0;  // num of an existing diagonal op does not depend on (cursor, n)
-                if (!HB && type == T_DIAG) dnum = bn * bond_weight(Hm, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
+                if (!HB && type == T_DIAG) dnum = bn * bweight<HAS_H>(Hm, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
                 bool try_fast = true;
                 TICK(1);  // load, classify, decode of existing ops, flip list
                 while (!HB && rem) {
@@ -374,12 +406,12 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                             uint32_t opw = OP_EMPTY;
                             if (acc) {
                                 const uint32_t b = (uint32_t)hi;
-                                const int kind = bond_kind(D, b);
+                                const int kind = bkind<HAS_H>(D, b);
                                 uint32_t v0, v1;
                                 bond_vars(D, b, kind, v0, v1);
                                 const uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
                                 hz = state_bit(S.cd, v0) || (kind == KIND_BOND && state_bit(S.cd, v1));
-                                const double num = bn * bond_weight(Hm, b, kind, s0, s1);
+                                const double num = bn * bweight<HAS_H>(Hm, b, kind, s0, s1);
                                 const uint32_t bitsv = s0 | (s1 << 1);
                                 opw = make_op(b, bitsv, bitsv);
                                 if (num >= dhiA) ok = true;                      // inserted without a second word
@@ -451,7 +483,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                             const uint32_t i = S.wl[k], xs = hz_x;
                             const uint32_t y = xs + (uint32_t)__ffsll((long long)(ACC >> xs)) - 1u;
                             const uint32_t b = op_bond(S.opw[y]);
-                            const int kind = bond_kind(D, b);
+                            const int kind = bkind<HAS_H>(D, b);
                             uint32_t v0, v1;
                             bond_vars(D, b, kind, v0, v1);
                             uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
@@ -459,7 +491,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                                 const uint32_t fv = S.fl[__ffs(m2) - 1];
                                 s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
                             }
-                            const double num = bn * bond_weight(Hm, b, kind, s0, s1);
+                            const double num = bn * bweight<HAS_H>(Hm, b, kind, s0, s1);
                             const uint32_t bitsv = s0 | (s1 << 1);
                             bool ok = false, ex = false, fail = false;
                             if (num >= dhiA) ok = true;
@@ -565,7 +597,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                                     }
                                     if (!novf) {
                                         const uint32_t b = (uint32_t)hi;
-                                        const int kind = bond_kind(D, b);
+                                        const int kind = bkind<HAS_H>(D, b);
                                         uint32_t v0, v1;
                                         bond_vars(D, b, kind, v0, v1);
                                         uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
@@ -573,7 +605,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                                             const uint32_t fv = S.fl[__ffs(m) - 1];
                                             s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
                                         }
-                                        const double num = bn * bond_weight(Hm, b, kind, s0, s1);
+                                        const double num = bn * bweight<HAS_H>(Hm, b, kind, s0, s1);
                                         const double den = (double)(M - ni);
                                         bool accept = num > den;
                                         if (!accept) {
@@ -639,7 +671,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                 int kind = -1;
                 uint32_t v0 = 0, v1 = 0;
                 if (valid && fw != OP_EMPTY) {
-                    kind = bond_kind(D, op_bond(fw));
+                    kind = bkind<HAS_H>(D, op_bond(fw));
                     bond_vars(D, op_bond(fw), kind, v0, v1);
                 }
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
@@ -774,7 +806,7 @@ __global__ void __launch_bounds__(128, MINB) k_sse_fast(SseDev D, uint64_t targe
                 int kind = -1;
                 uint32_t v0 = 0, v1 = 0;
                 if (w != OP_EMPTY) {
-                    kind = bond_kind(D, op_bond(w));
+                    kind = bkind<HAS_H>(D, op_bond(w));
                     bond_vars(D, op_bond(w), kind, v0, v1);
                 }
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
@@ -853,21 +885,12 @@ int g_sse_fast_minblocks = 7;  // resident blocks per SM the kernel is compiled 
 // returns the number of kernel launches, or -1 if this shape is not supported by the warp kernels
 int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
-    const size_t per_warp = warp_smem_bytes(D.N, D.Nw);
-    // warps per block: the choice that keeps most warps resident per SM (227 KB of shared memory, 1 KB
-    // reserved per block); large lattices need one warp per block
-    int warps = 0;
-    size_t best = 0;
-    for (int wpb = 4; wpb >= 1; wpb >>= 1) {
-        const size_t blk = per_warp * wpb + 1024;
-        if (blk > 227 * 1024) continue;
-        size_t resident = std::min<size_t>((227 * 1024) / blk, 32) * wpb;
-        if (resident > best) best = resident, warps = wpb;
-    }
-    if (!warps) return -1;
-    const size_t smem = per_warp * warps;
-    const uint32_t blocks = (D.R + warps - 1) / warps;
-    typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t);
+    // one warp per block: up to 32 blocks are resident per SM, each with its own shared memory
+    const size_t smem = warp_smem_bytes(D.N, D.Nw);
+    if (smem + 1024 > 227 * 1024) return -1;
+    const uint32_t blocks = (D.R + QMCB_WPB - 1) / QMCB_WPB;
+    if (smem * QMCB_WPB + 1024 > 227 * 1024) return -1;
+    typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t, uint32_t);
     Kern kern;
     if (D.ham) {
         if (D.hb_cum) kern = D.has_h ? k_sse_fast<true, 7, true, true> : k_sse_fast<false, 7, true, true>;
@@ -881,6 +904,6 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
             default: kern = D.has_h ? k_sse_fast<true, 7, false, false> : k_sse_fast<false, 7, false, false>; break;
         }
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    kern<<<blocks, warps * 32, smem, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep);
+    kern<<<blocks, 32 * QMCB_WPB, smem * QMCB_WPB, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem);
     return 1;
 }
