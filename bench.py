@@ -240,6 +240,20 @@ def bench_sse(args, world, rank, local):
             g.set_mode(MODE_FAST)
         except Exception as ex:  # e.g. out of memory for the link workspace
             out["strict"] = {"error": str(ex)[:200]}
+    # ---- heat-bath diagonal update (the reference's two_d_heatbath benches) sample
+    if args.heatbath_sweeps > 0 and world == 1:
+        g.set_enable_heatbath(True)
+        g.enqueue_sweeps(1)
+        g.synchronize()
+        vu3 = g.total_vertex_updates()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.enqueue_sweeps(args.heatbath_sweeps)
+        e1.record()
+        g.synchronize()
+        out["heatbath"] = {"value": (g.total_vertex_updates() - vu3) / (e0.elapsed_time(e1) * 1e-3), "unit": "vertex_updates/s",
+                           "sweeps": args.heatbath_sweeps, "note": "set_enable_heatbath(true): heatbath.rs:149-209 diagonal rule, FAST cluster order"}
+        g.set_enable_heatbath(False)
     return out
 
 
@@ -468,6 +482,7 @@ def main():
     ap.add_argument("--therm", type=int, default=120, help="untimed SSE thermalisation sweeps (GPU arm)")
     ap.add_argument("--ref-therm", type=int, default=80, help="untimed thermalisation sweeps of the CPU arm")
     ap.add_argument("--strict-sweeps", type=int, default=2)
+    ap.add_argument("--heatbath-sweeps", type=int, default=3)
     ap.add_argument("--sse-replicas", type=int, default=0)
     ap.add_argument("--cls-replicas", type=int, default=0)
     ap.add_argument("--cls-sweeps-per-step", type=int, default=10)
@@ -492,8 +507,9 @@ def main():
                           "replicas_per_gpu": c["replicas"], "mean_n": s["n_mean"], "mean_cutoff": s["cutoff_mean"],
                           "thermalisation_sweeps": args.therm, "l2": "inputs larger than L2 (operator strings: "
                           f"{c['replicas'] * s['cutoff_mean'] * 4 / 2**30:.1f} GiB per GPU)", "parallelism": f"replicas x{world}"}
-        if "strict" in s:
-            line["strict"] = s["strict"]
+        for extra in ("strict", "heatbath"):
+            if extra in s:
+                line[extra] = s[extra]
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sse(g, c)
         g.close()

@@ -135,6 +135,13 @@ int qmcb_set_cutoff(QmcbHandle *h, uint32_t r, uint64_t cutoff);           /* se
 int qmcb_get_capacity(const QmcbHandle *h, uint64_t *capacity);
 int qmcb_get_offset(const QmcbHandle *h, double *offset);                  /* get_offset */
 int qmcb_get_bond_counts(QmcbHandle *h, uint32_t r, uint64_t *counts /* [num_bonds] */);
+/* imaginary_time_fold (qmc_stepper.rs:165-168, qmc_ising.rs:815-821, OpContainer::itime_fold fast_ops.rs:1296-1315).
+ * A C ABI cannot take the reference's closure, so the fold is offered two ways: (1) on the device with the
+ * magnetisation fold, for every replica at once: per-site m = mean_v (2 s_v - 1) of the propagated state before each
+ * of the M slots, averaged over the slots as <m>, <m^2>, <|m|> (any output may be NULL); (2) the propagated state
+ * before slot p of one replica, for folds evaluated by the caller. */
+int qmcb_itime_magnetization(QmcbHandle *h, double *m_mean /* [R] */, double *m_sq, double *m_abs);
+int qmcb_itime_state(QmcbHandle *h, uint32_t r, uint64_t p, uint8_t *state /* [N] */);
 int qmcb_get_rng_cursors(QmcbHandle *h, uint64_t *cursors /* [R] */);
 int qmcb_set_rng_cursor(QmcbHandle *h, uint32_t r, uint64_t cursor);
 int qmcb_get_rng_keys(QmcbHandle *h, uint64_t *keys /* [R] */);

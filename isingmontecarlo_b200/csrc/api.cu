@@ -20,6 +20,8 @@ void launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phas
 void launch_sse_verify(const SseDev &D, uint32_t r, int *ok_dev, uint32_t *scratch_dev, cudaStream_t st);
 void launch_sse_bond_counts(const SseDev &D, uint32_t r, unsigned long long *counts_dev, cudaStream_t st);
 void launch_sse_recount(const SseDev &D, uint32_t r, cudaStream_t st);
+void launch_sse_itime_magnetization(const SseDev &D, long long *sums_dev, cudaStream_t st);
+void launch_sse_itime_state(const SseDev &D, uint32_t r, uint64_t p_at, uint32_t *out_dev, cudaStream_t st);
 void launch_sse_init_state(const SseDev &D, cudaStream_t st);
 int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
@@ -780,6 +782,46 @@ extern "C" int qmcb_get_bond_counts(QmcbHandle *h, uint32_t r, uint64_t *counts)
     cudaFree(dev);
     if (e != cudaSuccess) return fail_cuda(e, "bond counts", __FILE__, __LINE__);
     for (uint32_t b = 0; b < D.Nb; b++) counts[b] = host[b];
+    return QMCB_OK;
+}
+// imaginary_time_fold (qmc_stepper.rs:165-168, qmc_ising.rs:815-821) with the magnetisation fold, all replicas
+extern "C" int qmcb_itime_magnetization(QmcbHandle *h, double *m_mean, double *m_sq, double *m_abs) {
+    CHECK_H(h);
+    const SseDev &D = h->D;
+    long long *dev = nullptr;
+    CUDA_TRY(cudaMalloc(&dev, sizeof(long long) * 3 * D.R));
+    launch_sse_itime_magnetization(D, dev, h->stream);
+    h->launches++;
+    std::vector<long long> s(3 * (size_t)D.R);
+    std::vector<uint32_t> M(D.R);
+    cudaError_t e = cudaMemcpyAsync(s.data(), dev, sizeof(long long) * s.size(), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(M.data(), D.M, sizeof(uint32_t) * D.R, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail_cuda(e, "itime magnetization", __FILE__, __LINE__);
+    for (uint32_t r = 0; r < D.R; r++) {  // per-site magnetisation averaged over the M imaginary-time slices
+        const double slots = (double)M[r], nv = (double)D.N;
+        if (m_mean) m_mean[r] = (double)s[3 * (size_t)r] / slots / nv;
+        if (m_sq) m_sq[r] = (double)s[3 * (size_t)r + 1] / slots / (nv * nv);
+        if (m_abs) m_abs[r] = (double)s[3 * (size_t)r + 2] / slots / nv;
+    }
+    return QMCB_OK;
+}
+// the state the fold closure of imaginary_time_fold is handed at slot p (fast_ops.rs:1300-1311)
+extern "C" int qmcb_itime_state(QmcbHandle *h, uint32_t r, uint64_t p, uint8_t *state) {
+    CHECK_H(h);
+    const SseDev &D = h->D;
+    if (!state || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
+    uint32_t *dev = nullptr;
+    CUDA_TRY(cudaMalloc(&dev, sizeof(uint32_t) * D.Nw));
+    launch_sse_itime_state(D, r, p, dev, h->stream);
+    h->launches++;
+    std::vector<uint32_t> packed(D.Nw);
+    cudaError_t e = cudaMemcpyAsync(packed.data(), dev, sizeof(uint32_t) * D.Nw, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail_cuda(e, "itime state", __FILE__, __LINE__);
+    for (uint32_t v = 0; v < D.N; v++) state[v] = (packed[v >> 5] >> (v & 31)) & 1u;
     return QMCB_OK;
 }
 extern "C" int qmcb_get_rng_cursors(QmcbHandle *h, uint64_t *cursors) {

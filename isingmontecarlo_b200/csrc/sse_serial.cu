@@ -681,6 +681,62 @@ __global__ void k_sse_verify(SseDev D, uint32_t r, int *ok_out, uint32_t *scratc
     *ok_out = ok;
 }
 
+// imaginary_time_fold (qmc_ising.rs:815-821; OpContainer::itime_fold fast_ops.rs:1296-1315) with the magnetisation
+// fold, one warp per replica: the fold sees the state before the op at p; only off-diagonal (transverse) ops change
+// it, so m_p = m_0 + exclusive prefix sum of the flips.  sums[r] = {sum m, sum m^2, sum |m|} over p in [0, M).
+__global__ void k_sse_itime_magnetization(SseDev D, long long *sums) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= D.R) return;
+    const uint32_t *ops = D.ops + (size_t)r * D.cap, *st = D.state + (size_t)r * D.Nw;
+    const uint32_t M = D.M[r];
+    int up = 0;
+    for (uint32_t j = lane; j < D.Nw; j += 32) up += __popc(st[j]);
+    up = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)up);
+    long long m = 2ll * up - (long long)D.N, s1 = 0, s2 = 0, s3 = 0;
+    for (uint32_t base = 0; base < M; base += 32) {
+        const uint32_t p = base + lane;
+        const uint32_t w = (p < M && p < D.cap) ? ops[p] : OP_EMPTY;
+        int f = 0;  // change of m made by my op
+        if (w != OP_EMPTY && !op_is_diag(w)) {
+            f = 2 * ((int)(op_out(w) & 1u) - (int)(op_in(w) & 1u));
+            if (bond_kind(D, op_bond(w)) == KIND_BOND) f += 2 * ((int)((op_out(w) >> 1) & 1u) - (int)((op_in(w) >> 1) & 1u));
+        }
+        int incl = f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const long long mine = m + (incl - f);
+        if (p < M) s1 += mine, s2 += mine * mine, s3 += mine < 0 ? -mine : mine;
+        m += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    for (int d = 16; d; d >>= 1) {
+        s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, d), s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, d), s3 += __shfl_xor_sync(0xFFFFFFFFu, s3, d);
+    }
+    if (lane == 0) sums[3 * (size_t)r] = s1, sums[3 * (size_t)r + 1] = s2, sums[3 * (size_t)r + 2] = s3;
+}
+// propagated state of replica r before slot p_at, one warp
+__global__ void k_sse_itime_state(SseDev D, uint32_t r, uint64_t p_at, uint32_t *out) {
+    const int lane = threadIdx.x;
+    const uint32_t *ops = D.ops + (size_t)r * D.cap, *st = D.state + (size_t)r * D.Nw;
+    for (uint32_t j = lane; j < D.Nw; j += 32) out[j] = st[j];
+    __syncwarp();
+    const uint64_t lim = p_at < D.cap ? p_at : D.cap;
+    for (uint64_t base = 0; base < lim; base += 32) {
+        const uint64_t p = base + lane;
+        const uint32_t w = p < lim ? ops[p] : OP_EMPTY;
+        if (w != OP_EMPTY && !op_is_diag(w)) {  // transverse ops act on one variable; XOR commutes within the step
+            const int kind = bond_kind(D, op_bond(w));
+            uint32_t v0, v1;
+            bond_vars(D, op_bond(w), kind, v0, v1);
+            if ((op_in(w) ^ op_out(w)) & 1u) atomicXor(&out[v0 >> 5], 1u << (v0 & 31));
+            if (kind == KIND_BOND && ((op_in(w) ^ op_out(w)) & 2u)) atomicXor(&out[v1 >> 5], 1u << (v1 & 31));
+        }
+    }
+}
+
 // per-bond counts of replica r (fast_ops.rs:1281-1294)
 __global__ void k_sse_bond_counts(SseDev D, uint32_t r, unsigned long long *counts) {
     const uint32_t *ops = D.ops + (size_t)r * D.cap;
@@ -733,6 +789,13 @@ void launch_sse_verify(const SseDev &D, uint32_t r, int *ok_dev, uint32_t *scrat
 }
 void launch_sse_bond_counts(const SseDev &D, uint32_t r, unsigned long long *counts_dev, cudaStream_t st) {
     k_sse_bond_counts<<<64, 256, 0, st>>>(D, r, counts_dev);
+}
+void launch_sse_itime_magnetization(const SseDev &D, long long *sums_dev, cudaStream_t st) {
+    const int threads = 128;
+    k_sse_itime_magnetization<<<(uint32_t)(((uint64_t)D.R * 32 + threads - 1) / threads), threads, 0, st>>>(D, sums_dev);
+}
+void launch_sse_itime_state(const SseDev &D, uint32_t r, uint64_t p_at, uint32_t *out_dev, cudaStream_t st) {
+    k_sse_itime_state<<<1, 32, 0, st>>>(D, r, p_at, out_dev);
 }
 void launch_sse_recount(const SseDev &D, uint32_t r, cudaStream_t st) { k_sse_recount<<<1, 256, 0, st>>>(D, r); }
 void launch_sse_init_state(const SseDev &D, cudaStream_t st) {

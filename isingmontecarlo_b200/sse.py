@@ -259,6 +259,23 @@ class QmcIsingGraph:
         st = np.ascontiguousarray(state, dtype=np.uint8)
         check(self._L.qmcb_set_state(self._h, r, ptr(st, C.c_uint8)))
 
+    def imaginary_time_magnetization(self):
+        """imaginary_time_fold (qmc_ising.rs:815-821) with the magnetisation fold on the device: per replica
+        (<m>, <m^2>, <|m|>) of the per-site magnetisation over the M imaginary-time slices."""
+        out = np.zeros((3, self.R), dtype=np.float64)
+        check(self._L.qmcb_itime_magnetization(self._h, ptr(out[0], C.c_double), ptr(out[1], C.c_double), ptr(out[2], C.c_double)))
+        return out[0], out[1], out[2]
+
+    def imaginary_time_fold(self, r, fold_fn, init, stride=1):
+        """The reference's closure form for one replica, evaluated on the host: fold_fn(acc, state) over the
+        propagated states before slots 0, stride, 2*stride, ... (stride 1 = the reference's fold)."""
+        acc = init
+        st = np.zeros(self.nvars, dtype=np.uint8)
+        for p in range(0, int(self.get_cutoff()[r]), stride):
+            check(self._L.qmcb_itime_state(self._h, r, p, ptr(st, C.c_uint8)))
+            acc = fold_fn(acc, st)
+        return acc
+
     def get_bond_counts(self, r):
         out = np.zeros(self.num_bonds(), dtype=np.uint64)
         check(self._L.qmcb_get_bond_counts(self._h, r, ptr(out, C.c_uint64)))

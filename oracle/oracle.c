@@ -883,6 +883,34 @@ uint64_t orc_sse_get_bond_count(const OrcSse *g, uint32_t bond) { /* fast_ops.rs
     return c;
 }
 
+/* OpContainer::itime_fold (fast_ops.rs:1296-1315) through QmcIsingGraph::imaginary_time_fold
+ * (qmc_ising.rs:815-821) with the fold "accumulate the magnetisation of the propagated state":
+ * for p in 0..cutoff the fold sees the state BEFORE the op at p.  sums[0] = sum_p m_p, sums[1] = sum_p m_p^2,
+ * sums[2] = sum_p |m_p| with the integer m_p = sum_v (2 s_v - 1); returns the number of slots folded. */
+uint64_t orc_sse_itime_magnetization(const OrcSse *g, int64_t sums[3]) {
+    uint8_t *state = (uint8_t *)malloc(g->nvars);
+    memcpy(state, g->state, g->nvars);
+    sums[0] = sums[1] = sums[2] = 0;
+    for (uint64_t p = 0; p < g->cutoff; p++) {
+        int64_t m = 0;
+        for (uint32_t v = 0; v < g->nvars; v++) m += state[v] ? 1 : -1;
+        sums[0] += m, sums[1] += m * m, sums[2] += m < 0 ? -m : m;
+        if (p < g->ops_len && g->ops[p].present) {
+            const Node *nd = &g->ops[p];
+            for (int r = 0; r < nd->nv; r++) state[nd->vars[r]] = nd->out[r];
+        }
+    }
+    free(state);
+    return g->cutoff;
+}
+/* the propagated state before slot p (what the fold closure is handed at step p) */
+void orc_sse_itime_state(const OrcSse *g, uint64_t p_at, uint8_t *out) {
+    memcpy(out, g->state, g->nvars);
+    for (uint64_t p = 0; p < p_at && p < g->ops_len; p++)
+        if (g->ops[p].present)
+            for (int r = 0; r < g->ops[p].nv; r++) out[g->ops[p].vars[r]] = g->ops[p].out[r];
+}
+
 void orc_sse_dump_ops(const OrcSse *g, uint32_t *words) {
     for (uint64_t p = 0; p < g->cutoff; p++) {
         const Node *nd = p < g->ops_len ? &g->ops[p] : NULL;

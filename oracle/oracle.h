@@ -75,6 +75,9 @@ double orc_sse_get_offset(const OrcSse *g);
 void orc_sse_get_state(const OrcSse *g, uint8_t *out);
 void orc_sse_set_state(OrcSse *g, const uint8_t *in);
 uint64_t orc_sse_get_bond_count(const OrcSse *g, uint32_t bond);
+/* imaginary_time_fold (qmc_ising.rs:815-821, fast_ops.rs:1296-1315) with the magnetisation fold */
+uint64_t orc_sse_itime_magnetization(const OrcSse *g, int64_t sums[3]);
+void orc_sse_itime_state(const OrcSse *g, uint64_t p_at, uint8_t *out);
 /* op words in p order, [cutoff] entries (format: SURVEY.md Appendix D). */
 void orc_sse_dump_ops(const OrcSse *g, uint32_t *words);
 /* FastOps::new_from_ops equivalent: install a string given as op words + state. */

@@ -74,6 +74,8 @@ def lib():
     sig("orc_sse_get_state", None, vp, u8p)
     sig("orc_sse_set_state", None, vp, u8p)
     sig("orc_sse_get_bond_count", C.c_uint64, vp, C.c_uint32)
+    sig("orc_sse_itime_magnetization", C.c_uint64, vp, i64p)
+    sig("orc_sse_itime_state", None, vp, C.c_uint64, u8p)
     sig("orc_sse_dump_ops", None, vp, u32p)
     sig("orc_sse_load_ops", C.c_int, vp, u32p, C.c_uint64, u8p)
     sig("orc_sse_verify", C.c_int, vp)
@@ -195,6 +197,17 @@ class SseOracle:
 
     def bond_count(self, b):
         return lib().orc_sse_get_bond_count(self._h, b)
+
+    def itime_magnetization(self):
+        """imaginary_time_fold with the magnetisation fold: (slots, sum m, sum m^2, sum |m|), m = sum_v (2 s_v - 1)"""
+        sums = np.zeros(3, dtype=np.int64)
+        slots = lib().orc_sse_itime_magnetization(self._h, _p(sums, C.c_int64))
+        return slots, int(sums[0]), int(sums[1]), int(sums[2])
+
+    def itime_state(self, p):
+        out = np.zeros(self.nvars, dtype=np.uint8)
+        lib().orc_sse_itime_state(self._h, int(p), _p(out, C.c_uint8))
+        return out
 
     def dump_ops(self):
         out = np.zeros(self.cutoff, dtype=np.uint32)

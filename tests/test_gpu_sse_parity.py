@@ -177,3 +177,30 @@ def test_cpp_host_mirror_runs_the_reference_integration_tests():
     res = subprocess.run([os.path.join(root, "isingmontecarlo_b200", "_build", "test_mirror")], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "cpp mirror ok" in res.stdout
+
+
+def test_imaginary_time_fold_matches():
+    # qmc_ising.rs:815-821 / fast_ops.rs:1296-1315: magnetisation fold on the device vs the literal fold
+    edges = lattices.two_d_periodic_mixed(4)
+    g, refs = make_pair(edges, 1.0, 0.3, 16, 2.0, MODE_FAST, R=4)
+    g.timesteps(30, 2.0)
+    for ref in refs:
+        ref.timesteps(30, 2.0, MODE_FAST)
+    assert_same(g, refs, "before fold")
+    m1, m2, mabs = g.imaginary_time_magnetization()
+    nv = 16.0
+    for r, ref in enumerate(refs):
+        slots, s1, s2, s3 = ref.itime_magnetization()
+        assert slots == ref.cutoff
+        assert m1[r] == s1 / slots / nv and m2[r] == s2 / slots / (nv * nv) and mabs[r] == s3 / slots / nv
+        for p in (0, 1, ref.cutoff // 2, ref.cutoff - 1, ref.cutoff):
+            st = np.zeros(16, dtype=np.uint8)
+            from isingmontecarlo_b200._lib import check, ptr
+            import ctypes as C
+            check(g._L.qmcb_itime_state(g._h, r, p, ptr(st, C.c_uint8)))
+            assert np.array_equal(st, ref.itime_state(p)), (r, p)
+    # closure form on the host: count slices with positive magnetisation, against the oracle states
+    pos = g.imaginary_time_fold(0, lambda acc, s: acc + (2 * int(s.sum()) > 16), 0)
+    assert pos == sum(2 * int(refs[0].itime_state(p).sum()) > 16 for p in range(refs[0].cutoff))
+    # the fold returns to the p = 0 state after the last slot (periodic in imaginary time)
+    assert np.array_equal(refs[0].itime_state(refs[0].cutoff), refs[0].state())
