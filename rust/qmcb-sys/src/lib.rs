@@ -29,6 +29,12 @@ extern "C" {
     pub fn qmcb_destroy(h: *mut QmcbHandle) -> c_int;
     pub fn qmcb_set_stream(h: *mut QmcbHandle, cuda_stream: *mut c_void) -> c_int;
     pub fn qmcb_set_mode(h: *mut QmcbHandle, mode: c_int) -> c_int;
+    pub fn qmcb_set_enable_heatbath(h: *mut QmcbHandle, enable: c_int) -> c_int;
+    pub fn qmcb_get_enable_heatbath(h: *const QmcbHandle, enabled: *mut c_int) -> c_int;
+    pub fn qmcb_set_hamiltonians(h: *mut QmcbHandle, n_ham: u32, j_tab: *const f64, transverse: *const f64,
+                                 longitudinal: *const f64, ham_of_replica: *const u32) -> c_int;
+    pub fn qmcb_get_hamiltonian_index(h: *mut QmcbHandle, ham_of_replica: *mut u32) -> c_int;
+    pub fn qmcb_get_offsets(h: *mut QmcbHandle, offsets: *mut f64) -> c_int;
     pub fn qmcb_set_betas(h: *mut QmcbHandle, betas: *const f64) -> c_int;
     pub fn qmcb_timesteps(h: *mut QmcbHandle, t: u64, sampling_freq: u64, energy_out: *mut f64, samples_out: *mut u8) -> c_int;
     pub fn qmcb_single_diagonal_step(h: *mut QmcbHandle) -> c_int;
@@ -45,9 +51,16 @@ extern "C" {
     pub fn qmcb_verify(h: *mut QmcbHandle, r: u32, ok: *mut c_int) -> c_int;
     pub fn qmcb_pt_configure(h: *mut QmcbHandle, n_chains_global: u32, n_betas: u32, slot_begin: u32,
                              betas_global: *const f64, keys_global: *const u64, pt_key: u64) -> c_int;
+    pub fn qmcb_pt_set_slot_hamiltonians(h: *mut QmcbHandle, ham_of_slot: *const u32) -> c_int;
+    pub fn qmcb_pt_record_words(h: *const QmcbHandle, words: *mut u32) -> c_int;
     pub fn qmcb_pt_export(h: *mut QmcbHandle, rec_dev: *mut u64) -> c_int;
     pub fn qmcb_pt_apply(h: *mut QmcbHandle, all_rec_dev: *const u64, n_records: u64) -> c_int;
     pub fn qmcb_pt_total_swaps(h: *mut QmcbHandle, swaps: *mut u64) -> c_int;
+    pub fn qmcb_itime_magnetization(h: *mut QmcbHandle, m_mean: *mut f64, m_sq: *mut f64, m_abs: *mut f64) -> c_int;
+    pub fn qmcb_itime_state(h: *mut QmcbHandle, r: u32, p: u64, state: *mut u8) -> c_int;
+    pub fn qmcb_checkpoint_size(h: *mut QmcbHandle, bytes: *mut u64) -> c_int;
+    pub fn qmcb_checkpoint_save(h: *mut QmcbHandle, buf: *mut c_void, bytes: u64) -> c_int;
+    pub fn qmcb_checkpoint_load(buf: *const c_void, bytes: u64, device: c_int, out: *mut *mut QmcbHandle) -> c_int;
     pub fn cmcb_create(lattice: *const QmcbLattice, biases: *const f64, n_replicas: u32, betas: *const f64,
                        rng_keys: *const u64, init_state: *const u8, device: c_int, out: *mut *mut CmcbHandle) -> c_int;
     pub fn cmcb_destroy(h: *mut CmcbHandle) -> c_int;

@@ -76,6 +76,31 @@ impl BatchedQmcIsingGraph {
         let s = raw.chunks(k * self.nvars).map(|r| r.chunks(self.nvars).map(|c| c.iter().map(|b| *b != 0).collect()).collect()).collect();
         Ok((s, e))
     }
+    /// QmcIsingGraph::set_enable_heatbath (qmc_ising.rs:444-486)
+    pub fn set_enable_heatbath(&mut self, enable_heatbath: bool) -> Result<(), String> {
+        check(unsafe { sys::qmcb_set_enable_heatbath(self.h, enable_heatbath as i32) })
+    }
+    /// serde replacement (SerializeQmcGraph, qmc_ising.rs:1001-1087): the whole batch, stream position included
+    pub fn to_bytes(&mut self) -> Result<Vec<u8>, String> {
+        let mut n = 0u64;
+        check(unsafe { sys::qmcb_checkpoint_size(self.h, &mut n) })?;
+        let mut buf = vec![0u8; n as usize];
+        check(unsafe { sys::qmcb_checkpoint_save(self.h, buf.as_mut_ptr() as *mut _, n) })?;
+        Ok(buf)
+    }
+    /// QmcStepper::imaginary_time_fold (qmc_stepper.rs:165-168) with the closure evaluated on the host
+    pub fn imaginary_time_fold<F, T>(&mut self, r: usize, fold_fn: F, init: T) -> Result<T, String>
+    where F: Fn(T, &[bool]) -> T {
+        let mut cut = vec![0u64; self.replicas];
+        check(unsafe { sys::qmcb_get_cutoffs(self.h, cut.as_mut_ptr()) })?;
+        let (mut acc, mut raw) = (init, vec![0u8; self.nvars]);
+        for p in 0..cut[r] {
+            check(unsafe { sys::qmcb_itime_state(self.h, r as u32, p, raw.as_mut_ptr()) })?;
+            let st: Vec<bool> = raw.iter().map(|b| *b != 0).collect();
+            acc = fold_fn(acc, &st);
+        }
+        Ok(acc)
+    }
     pub fn get_n(&mut self) -> Result<Vec<u64>, String> {
         let mut n = vec![0u64; self.replicas];
         check(unsafe { sys::qmcb_get_n(self.h, n.as_mut_ptr()) })?;
