@@ -233,6 +233,7 @@ class SseOracle:
 
 
 def sse_batch_timesteps(reps, t, betas, mode=MODE_STRICT, nthreads=0):
+    nthreads = nthreads or max_threads()
     arr = (C.c_void_p * len(reps))(*[r._h for r in reps])
     b = np.ascontiguousarray(betas, dtype=np.float64)
     e = np.zeros(len(reps), dtype=np.float64)
@@ -296,6 +297,7 @@ class ClassicalOracle:
 
 
 def cls_batch_checkerboard(reps, betas, colours, nsweeps, nthreads=0):
+    nthreads = nthreads or max_threads()
     arr = (C.c_void_p * len(reps))(*[r._h for r in reps])
     b = np.ascontiguousarray(betas, dtype=np.float64)
     col = np.ascontiguousarray(colours, dtype=np.uint32)
@@ -303,6 +305,7 @@ def cls_batch_checkerboard(reps, betas, colours, nsweeps, nthreads=0):
 
 
 def cls_batch_spin_flips(reps, betas, count, nthreads=0):
+    nthreads = nthreads or max_threads()
     arr = (C.c_void_p * len(reps))(*[r._h for r in reps])
     b = np.ascontiguousarray(betas, dtype=np.float64)
     lib().orc_cls_batch_spin_flips(arr, len(reps), _p(b, C.c_double), count, nthreads)
@@ -313,4 +316,9 @@ def cls_threshold(beta, delta_e):
 
 
 def max_threads():
-    return lib().orc_max_threads()
+    """Host cores this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which would silently turn the all-core CPU baseline into a one-core one."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
