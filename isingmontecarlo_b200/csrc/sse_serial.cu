@@ -48,7 +48,7 @@ __device__ __forceinline__ Rep rep_view(const SseDev &D, uint32_t r) {
 // ------------------------------------------------------------------------------------------
 // diagonal update (diagonal.rs:114-135, :142-191; slot loop fast_ops.rs:611-637), lane 0
 // ------------------------------------------------------------------------------------------
-__device__ void diag_serial(const SseDev &D, uint32_t r, const Rep &V) {
+__device__ __noinline__ void diag_serial(const SseDev &D, uint32_t r, const Rep &V) {
     const uint32_t M = D.M[r];
     uint32_t n = D.n[r];
     uint64_t cur = D.cursor[r];
@@ -121,7 +121,7 @@ __device__ void diag_serial(const SseDev &D, uint32_t r, const Rep &V) {
 // ------------------------------------------------------------------------------------------
 // heat-bath diagonal update (heatbath.rs:106-127, :149-209), lane 0
 // ------------------------------------------------------------------------------------------
-__device__ void diag_heatbath_serial(const SseDev &D, uint32_t r, const Rep &V) {
+__device__ __noinline__ void diag_heatbath_serial(const SseDev &D, uint32_t r, const Rep &V) {
     const uint32_t M = D.M[r];
     uint32_t n = D.n[r];
     uint64_t cur = D.cursor[r];
@@ -584,7 +584,9 @@ __device__ void free_spins(const SseDev &D, uint32_t r, const Rep &V, int lane) 
 // phases: bit0 diagonal update, bit1 cluster update + free spins, bit2 cutoff growth,
 // bit3 bookkeeping of a full timestep (done counter, estimators, sampling),
 // bit4 run only the single step that takes the replica from target - 1 to target
-__global__ void __launch_bounds__(128) k_sse_serial(SseDev D, int mode, uint64_t target, uint32_t phases,
+// 7 blocks of 4 warps per SM (72 registers): 4096 replicas are resident in one wave, which is what this
+// latency-bound kernel needs (at 80 registers it ran in two waves: 467 ms instead of 290 ms per sweep on config #3)
+__global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint64_t target, uint32_t phases,
                                                     uint64_t sample_freq, uint64_t sample_origin,
                                                     uint8_t *samples, uint64_t samples_per_rep, int par_links) {
     extern __shared__ uint32_t smem_last[];  // [warps per block][N] when par_links
