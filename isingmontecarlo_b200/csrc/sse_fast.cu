@@ -48,9 +48,20 @@ __device__ __forceinline__ uint32_t uf_find_cg(uint32_t *P, uint32_t x) {
     }
     return x;
 }
+// The kernel is bound by the latency of dependent loads, so both chains are climbed in lockstep: the two parent
+// loads of a round are in flight together (one L2 round trip per level instead of two).  The start nodes are
+// pointed at the root they reached (compression of the nodes that are looked up again: S.rep entries).
 __device__ __forceinline__ uint32_t uf_union_cg(uint32_t *P, uint32_t a, uint32_t b) {
     for (;;) {
-        a = uf_find_cg(P, a), b = uf_find_cg(P, b);
+        const uint32_t a0 = a, b0 = b;
+        uint32_t pa = ld_cg(P + a), pb = ld_cg(P + b);
+        const uint32_t pa0 = pa, pb0 = pb;
+        while (pa != a || pb != b) {
+            a = pa, b = pb;
+            pa = ld_cg(P + a), pb = ld_cg(P + b);
+        }
+        if (pa0 != a) st_cg(P + a0, a);  // a stale value is still an ancestor
+        if (pb0 != b) st_cg(P + b0, b);
         if (a == b) return a;
         if (a > b) {
             uint32_t t = a;
@@ -675,6 +686,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                     bond_vars(D, op_bond(fw), kind, v0, v1);
                 }
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
+                TICK(11);  // decode of the final ops
                 const uint32_t myid = N + nsite + (uint32_t)__popc(smask & lt_mask);
                 if (kind == KIND_SITE) st_cg(P + myid, myid);
                 if (kind >= 0) {
@@ -700,13 +712,15 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                     if (kind == KIND_BOND && mb) rb = N + nsite + (uint32_t)__popc(smask & ((1u << (31 - __clz(mb))) - 1u)), fb = false;
                 }
                 __syncwarp();  // new ids are initialised before anyone follows them
-                if (kind == KIND_BOND) {
-                    if (ra != rb) {
-                        const uint32_t root = uf_union_cg(P, ra, rb);
-                        if (fa) atomicCAS(&S.rep[v0], oa, root);  // cache the root: equal roots skip the union
-                        if (fb) atomicCAS(&S.rep[v1], ob, root);
-                    }
-                } else if (HAS_H && kind == KIND_LONG) {
+                TICK(12);  // touched bits, representatives, same-step site ops (match)
+                if (kind == KIND_BOND && ra != rb) {
+                    // (an atomic-free variant -- match the roots, lowest lane stores, others retry -- measured 4 % slower)
+                    const uint32_t root = uf_union_cg(P, ra, rb);
+                    if (fa) atomicCAS(&S.rep[v0], oa, root);  // cache the root: equal roots skip the union
+                    if (fb) atomicCAS(&S.rep[v1], ob, root);
+                }
+                TICK(13);  // unions
+                if (HAS_H && kind == KIND_LONG) {
                     atomicOr(&frz[ra >> 5], 1u << (ra & 31));
                     anylong = true;
                 }
@@ -799,6 +813,12 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
             __syncwarp();
             uint32_t ks = 0;
             uint32_t w3next = lane < M ? ld_cg(ops + lane) : OP_EMPTY;
+            // the site ops of one step have consecutive ids: their flip bits sit in two consecutive words of decb.
+            // A sliding window of three words is kept in registers (loaded one step before it can be needed), so
+            // that no L2 round trip sits on the step's dependent chain.
+            const uint32_t dlast = (uint32_t)bstride - 1u;
+            uint32_t wi = N >> 5;
+            uint32_t dw0 = ld_cg(decb + min(wi, dlast)), dw1 = ld_cg(decb + min(wi + 1u, dlast)), dw2 = ld_cg(decb + min(wi + 2u, dlast));
             for (uint32_t base = 0; base < M; base += 32) {
                 const uint32_t p = base + lane;
                 const uint32_t w = w3next;
@@ -813,7 +833,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                 bool outdec = false;
                 if (kind == KIND_SITE) {
                     const uint32_t id = N + ks + (uint32_t)__popc(smask & lt_mask);
-                    outdec = (ld_cg(decb + (id >> 5)) >> (id & 31)) & 1u;
+                    outdec = (((id >> 5) == wi ? dw0 : dw1) >> (id & 31)) & 1u;
                 }
                 const uint32_t odmask = __ballot_sync(FULL, outdec);
                 bool din = kind >= 0 ? ((S.cd[v0 >> 5] >> (v0 & 31)) & 1u) : false;
@@ -831,6 +851,10 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                     else atomicAnd(&S.cd[v0 >> 5], ~(1u << (v0 & 31)));
                 }
                 ks += (uint32_t)__popc(smask);
+                if (((N + ks) >> 5) != wi) {  // at most one word per step
+                    wi++;
+                    dw0 = dw1, dw1 = dw2, dw2 = ld_cg(decb + min(wi + 2u, dlast));
+                }
                 __syncwarp();
             }
             TICK(10);  // P3
@@ -880,7 +904,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     if (err) atomicOr(D.status, err);
 }
 
-int g_sse_fast_minblocks = 7;  // resident blocks per SM the kernel is compiled for (register cap)
+int g_sse_fast_minblocks = 0;  // resident blocks per SM the kernel is compiled for (register cap); 0 = choose by occupancy
 
 // returns the number of kernel launches, or -1 if this shape is not supported by the warp kernels
 int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
@@ -891,18 +915,31 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
     const uint32_t blocks = (D.R + QMCB_WPB - 1) / QMCB_WPB;
     if (smem * QMCB_WPB + 1024 > 227 * 1024) return -1;
     typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t, uint32_t);
+    // register budget: the kernel is bound by the latency of each warp's dependent chain, so when shared memory or the
+    // number of replicas keeps few blocks resident anyway, the 120-register build (no spills) is 10-20 % faster per
+    // warp; with many replicas 72 registers keep 4096 of them (28 warps per SM) in one wave
+    int minb = g_sse_fast_minblocks;
+    if (minb <= 0) {
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+        const size_t by_smem = (227 * 1024) / (smem * QMCB_WPB + 1024);
+        const size_t wanted = (blocks + nsm - 1) / nsm;
+        const size_t resident = std::min(by_smem, wanted);
+        minb = resident <= 4 ? 4 : (resident <= 6 ? 6 : 7);
+    }
     Kern kern;
+#define PICK(HB_, MH_)                                                                                            \
+    switch (minb) {                                                                                               \
+        case 4: kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_> : k_sse_fast<false, 4, HB_, MH_>; break;            \
+        case 6: kern = D.has_h ? k_sse_fast<true, 6, HB_, MH_> : k_sse_fast<false, 6, HB_, MH_>; break;            \
+        case 8: kern = (!HB_ && !MH_) ? (D.has_h ? k_sse_fast<true, 8, false, false> : k_sse_fast<false, 8, false, false>) \
+                                      : (D.has_h ? k_sse_fast<true, 7, HB_, MH_> : k_sse_fast<false, 7, HB_, MH_>); break; \
+        default: kern = D.has_h ? k_sse_fast<true, 7, HB_, MH_> : k_sse_fast<false, 7, HB_, MH_>; break;           \
+    }
     if (D.ham) {
-        if (D.hb_cum) kern = D.has_h ? k_sse_fast<true, 7, true, true> : k_sse_fast<false, 7, true, true>;
-        else kern = D.has_h ? k_sse_fast<true, 7, false, true> : k_sse_fast<false, 7, false, true>;
-    } else if (D.hb_cum) kern = D.has_h ? k_sse_fast<true, 7, true, false> : k_sse_fast<false, 7, true, false>;
-    else
-        switch (g_sse_fast_minblocks) {
-            case 4: kern = D.has_h ? k_sse_fast<true, 4, false, false> : k_sse_fast<false, 4, false, false>; break;
-            case 6: kern = D.has_h ? k_sse_fast<true, 6, false, false> : k_sse_fast<false, 6, false, false>; break;
-            case 8: kern = D.has_h ? k_sse_fast<true, 8, false, false> : k_sse_fast<false, 8, false, false>; break;
-            default: kern = D.has_h ? k_sse_fast<true, 7, false, false> : k_sse_fast<false, 7, false, false>; break;
-        }
+        if (D.hb_cum) { PICK(true, true) } else { PICK(false, true) }
+    } else if (D.hb_cum) { PICK(true, false) } else { PICK(false, false) }
+#undef PICK
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     kern<<<blocks, 32 * QMCB_WPB, smem * QMCB_WPB, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem);
     return 1;

@@ -38,7 +38,7 @@ if os.environ.get('PROF_DBG'):
     c = g.debug_counters()
     print('dbg: chunks', c[0], 'fast', c[1], 'fast_fail_first', c[2], 'slow', c[3], 'why[delta|empty<<1|amb<<2]', list(c[4:12]))
     names = ["between steps", "load+classify", "philox window", "thresholds+decode", "table+walk", "decisions+commit", "store+flips",
-             "segment ids+union-find", "closure", "P2", "P3"]
+             "rest of segment step", "closure", "P2", "P3", "final-op decode", "tb/rep/match", "unions"]
     t = c[32:32 + len(names)].astype(float)
     if t.sum() == 0:
         print('(build with EXTRA=-DQMCB_PHASE_TIMERS to get phase timers)')
