@@ -63,6 +63,15 @@ int main() {
             ASSERT(mean > -4.6 && mean < -3.6);  // exact -4.055 (DESIGN / SURVEY Appendix E)
             ASSERT(g.verify());
         }
+        {  // the reference's heat-bath benches (benches/end_to_end.rs:168-258): same lattice, set_enable_heatbath(true)
+            auto g = qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 1}, -1.0}, {{1, 2}, 1.0}, {{2, 3}, 1.0}, {{3, 0}, 1.0}}, 1.0, 0.0, 3, seeds, nullptr, mode);
+            g.set_enable_heatbath(true);
+            auto e = g.timesteps(1000, 1.0);
+            double mean = 0;
+            for (double x : e) mean += x / e.size();
+            ASSERT(mean > -4.6 && mean < -3.6);
+            ASSERT(g.verify());
+        }
         {  // convert_test.rs lattice: timestep returns the state, sampling shape
             std::vector<bool> st(3, true);
             auto ising = qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 1}, 1.0}, {{1, 2}, 1.0}, {{2, 0}, 1.0}}, 1.0, 0.0, 3, {1234}, &st, mode);
