@@ -132,6 +132,7 @@ static int alloc_fast_ws(QmcbHandle *h) {
 // re-layout every per-slot array for a larger per-replica capacity
 static int grow(QmcbHandle *h, uint64_t newcap) {
     SseDev &D = h->D;
+    newcap = (newcap + 31) / 32 * 32;  // rows stay 128-byte aligned (the sweep kernels copy whole lines)
     if (newcap <= D.cap) return QMCB_OK;
     if (newcap >= (1ull << 29)) return fail(QMCB_ERR_CAPACITY, "operator string capacity above 2^29 slots per replica");
     uint32_t *nops = nullptr;

@@ -81,6 +81,25 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
     return x - v;
 }
 
+// Software prefetch of the next 128-byte line of the operator string WITHOUT a register: held in a register across a
+// whole step, the value was spilled right after the load was issued (register cap), and the spill store waited for the
+// DRAM round trip at the top of every step.  Lanes 0..7 copy 16 bytes each straight into shared memory (cp.async.cg:
+// through L2 like ld.cg); the line is picked up at the top of the next step.  Rows are 128-byte aligned (cap % 32 == 0).
+__device__ __forceinline__ void fetch_line(uint32_t *line_smem, const uint32_t *src, int lane) {
+    if (lane < 8) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(line_smem + 4 * lane);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * lane) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t take_line(const uint32_t *line_smem, int lane) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const uint32_t w = line_smem[lane];
+    __syncwarp();  // everyone has read the line before the next copy may land in it
+    return w;
+}
+
 // lattice helpers specialised on HAS_H: without a longitudinal field there are no KIND_LONG bonds
 template <bool HAS_H>
 __device__ __forceinline__ int bkind(const SseDev &D, uint32_t b) {
@@ -105,6 +124,7 @@ struct WarpSmem {
     unsigned char *G;  // [80] cursor after an empty slot that starts reading at window position x; G[64] = 255
     unsigned char *wk, *wl;  // [32] walk: draws of diagonal ops since the previous EMPTY lane, lane of the k-th EMPTY lane
     unsigned short *wxg;     // [32] walk: start cursor | cursor after << 8 of the k-th EMPTY lane
+    uint32_t *line;          // [32] next line of the operator string (asynchronous copy, see fetch_line)
     uint32_t *st;   // [Nw] spin bits at the current p
     uint32_t *tb;   // [Nw] variable has at least one op
     uint32_t *cd;   // [Nw] P1: variable is flipped inside this step; P3: flip decision of the segment open on each variable
@@ -117,7 +137,8 @@ struct WarpSmem {
 #define SM_WK 976
 #define SM_WL 1008
 #define SM_WXG 1040
-#define SM_VAR 1104  // st, tb, cd, rep
+#define SM_LINE 1104  // [32] the next 128-byte line of the operator string, filled by cp.async
+#define SM_VAR 1232   // st, tb, cd, rep
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
     return (SM_VAR + ((size_t)3 * Nw + N) * 4 + 15) / 16 * 16;
@@ -135,15 +156,20 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     const int lane = threadIdx.x;
     const uint32_t r = blockIdx.x;
 #else
-    unsigned char *const smem_raw = smem_all + (threadIdx.x >> 5) * smem_stride;
+    // the warp index goes through a warp reduction so that the compiler knows it (and everything derived from it: the
+    // shared-memory base, the replica index and the replica's global pointers) is warp-uniform and keeps it in the
+    // uniform register file instead of rematerialising it from %tid under register pressure
+    const uint32_t wib = __reduce_max_sync(0xFFFFFFFFu, threadIdx.x >> 5);
+    unsigned char *const smem_raw = smem_all + wib * smem_stride;
     const int lane = threadIdx.x & 31;
-    const uint32_t r = blockIdx.x * QMCB_WPB + (threadIdx.x >> 5);
+    const uint32_t r = blockIdx.x * QMCB_WPB + wib;
 #endif
     if (r >= D.R) return;
     const uint32_t N = D.N, Nw = D.Nw;
     WarpSmem S;
     S.win = (unsigned long long *)(smem_raw + SM_WIN), S.fl = (uint32_t *)(smem_raw + SM_FL), S.opw = (uint32_t *)(smem_raw + SM_OPW);
     S.G = smem_raw + SM_G, S.wk = smem_raw + SM_WK, S.wl = smem_raw + SM_WL, S.wxg = (unsigned short *)(smem_raw + SM_WXG);
+    S.line = (uint32_t *)(smem_raw + SM_LINE);
     S.st = (uint32_t *)(smem_raw + SM_VAR), S.tb = S.st + Nw, S.cd = S.st + 2 * Nw, S.rep = S.st + 3 * Nw;
     if (lane < 16) S.G[64 + lane] = 255;  // positions past the window: exhausted (absorbing state of the walk)
     uint32_t *ops = D.ops + (size_t)r * D.cap;
@@ -188,12 +214,13 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
         bool anylong = false;
 
         // =========================== P1: diagonal update + unions ===========================
-        uint32_t wnext = lane < M ? ld_cg(ops + lane) : OP_EMPTY;  // software prefetch of the next 128-byte line
+        if (M) fetch_line(S.line, ops, lane);  // software prefetch of the next 128-byte line
         for (uint32_t base = 0; base < M; base += 32) {
             const uint32_t p = base + lane;
             const bool valid = p < M;
-            uint32_t w = wnext;
-            wnext = p + 32 < M ? ld_cg(ops + p + 32) : OP_EMPTY;
+            uint32_t w = take_line(S.line, lane);
+            if (!valid) w = OP_EMPTY;
+            if (base + 32 < M) fetch_line(S.line, ops + base + 32, lane);
             DBG(0, 1);
             TICK(0);  // between steps
             int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
@@ -812,7 +839,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
             for (uint32_t j = lane; j < Nw; j += 32) S.cd[j] = ld_cg(decb + j);
             __syncwarp();
             uint32_t ks = 0;
-            uint32_t w3next = lane < M ? ld_cg(ops + lane) : OP_EMPTY;
+            if (M) fetch_line(S.line, ops, lane);
             // the site ops of one step have consecutive ids: their flip bits sit in two consecutive words of decb.
             // A sliding window of three words is kept in registers (loaded one step before it can be needed), so
             // that no L2 round trip sits on the step's dependent chain.
@@ -821,8 +848,9 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
             uint32_t dw0 = ld_cg(decb + min(wi, dlast)), dw1 = ld_cg(decb + min(wi + 1u, dlast)), dw2 = ld_cg(decb + min(wi + 2u, dlast));
             for (uint32_t base = 0; base < M; base += 32) {
                 const uint32_t p = base + lane;
-                const uint32_t w = w3next;
-                w3next = p + 32 < M ? ld_cg(ops + p + 32) : OP_EMPTY;
+                uint32_t w = take_line(S.line, lane);
+                if (p >= M) w = OP_EMPTY;
+                if (base + 32 < M) fetch_line(S.line, ops + base + 32, lane);
                 int kind = -1;
                 uint32_t v0 = 0, v1 = 0;
                 if (w != OP_EMPTY) {
