@@ -297,6 +297,26 @@ extern "C" int qmcb_create(const QmcbLattice *lat, uint32_t R, const double *bet
         TRYC(cudaMemcpy(vab_dev, vab.data(), sizeof(uint2) * D.E, cudaMemcpyHostToDevice));
         D.vab = vab_dev;
         D.zone = ((uint64_t)D.Nb << __builtin_clzll((uint64_t)D.Nb)) - 1ull;
+        // packed edge table (see sse.cuh): only when it can represent the lattice exactly
+        std::vector<double> dict;
+        std::vector<uint32_t> epk(D.E);
+        bool ok = D.N <= 16384;
+        for (uint32_t e = 0; e < D.E && ok; e++) {
+            size_t c = 0;
+            while (c < dict.size() && memcmp(&dict[c], &lat->J[e], sizeof(double)) != 0) c++;  // bitwise: -0.0 != 0.0
+            if (c == dict.size()) {
+                if (dict.size() == 16) ok = false;
+                else dict.push_back(lat->J[e]);
+            }
+            epk[e] = lat->va[e] | (lat->vb[e] << 14) | ((uint32_t)c << 28);
+        }
+        if (ok && D.E) {
+            uint32_t *epk_dev;
+            TRYC(h->pool.alloc(&epk_dev, D.E));
+            TRYC(cudaMemcpy(epk_dev, epk.data(), sizeof(uint32_t) * D.E, cudaMemcpyHostToDevice));
+            D.epk = epk_dev;
+            for (size_t c = 0; c < dict.size(); c++) D.jdict[c] = dict[c];
+        }
     }
     h->va_h.assign(lat->va, lat->va + D.E), h->vb_h.assign(lat->vb, lat->vb + D.E), h->J_h.assign(lat->J, lat->J + D.E);
     h->Jtab_h = h->J_h, h->gam_h = {lat->transverse}, h->hl_h = {lat->longitudinal}, h->offset_h = {h->offset};
@@ -465,6 +485,7 @@ extern "C" int qmcb_set_hamiltonians(QmcbHandle *h, uint32_t n_ham, const double
     CUDA_TRY(cudaMemcpy(hr, ham_of_replica, sizeof(uint32_t) * D.R, cudaMemcpyHostToDevice));
     h->pool.release((void *)D.J_tab), h->pool.release((void *)D.gam_tab), h->pool.release((void *)D.h_tab), h->pool.release((void *)D.ham);
     D.J_tab = jt, D.gam_tab = gt, D.h_tab = ht, D.ham = hr;
+    D.epk = nullptr;  // couplings differ between replicas: no shared packed table
     // the heat-bath tables are per Hamiltonian: rebuild them
     h->pool.release(h->hb_cum_dev), h->pool.release(h->hb_maxw_dev), h->pool.release(h->hb_total_dev);
     h->hb_cum_dev = h->hb_maxw_dev = h->hb_total_dev = nullptr;
@@ -509,6 +530,11 @@ extern "C" int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value) {
     if (!h || !name) return fail(QMCB_ERR_BAD_ARG, "null argument");
     if (!strcmp(name, "impl")) {
         h->impl = (int)value;
+        return QMCB_OK;
+    }
+    if (!strcmp(name, "shared_edge_table")) {
+        extern int g_sse_fast_epk;
+        g_sse_fast_epk = (int)value;
         return QMCB_OK;
     }
     if (!strcmp(name, "minblocks")) {

@@ -11,6 +11,10 @@ struct SseDev {
     int has_h;              // |h| > f64::EPSILON
     const uint32_t *va, *vb;
     const uint2 *vab;       // [E] both variables of an edge in one 8-byte word
+    // packed edge table for the block-shared copy in shared memory (sse_fast.cu): v0 | v1 << 14 | coupling code << 28,
+    // couplings from the 16-entry dictionary; NULL when N > 16384, more than 16 distinct couplings, or per-replica rows
+    const uint32_t *epk;
+    double jdict[16];
     const double *J;
     uint64_t zone;          // rand 0.8 gen_range(0..Nb) acceptance zone: (Nb << lzcnt(Nb)) - 1
     double gamma, h;

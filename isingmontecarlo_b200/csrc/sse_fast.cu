@@ -147,10 +147,21 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
 #ifndef QMCB_WPB
 #define QMCB_WPB 4  // warps (= replicas) per block: one per scheduler of the SM (1 or 2 per block measured 8-12% slower)
 #endif
-template <bool HAS_H, int MINB, bool HB, bool MH>
+template <bool HAS_H, int MINB, bool HB, bool MH, bool PK>
 __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
-                                                  uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, uint32_t smem_stride) {
+                                                  uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, uint32_t smem_stride,
+                                                  uint32_t epk_off) {
     extern __shared__ __align__(16) unsigned char smem_all[];
+    // block-shared copy of the packed edge table (variables and coupling code of every bond): the look-ups on the
+    // step's dependent chain become shared-memory loads instead of L1/L2 loads.  Compiled in (PK) only for the
+    // low-occupancy builds: with 28 warps per SM the table shrinks L1 below what spills and the other tables need
+    // (measured +8 % time on config #3, -20 % on L = 64 ladders).
+    if (PK) {
+        uint32_t *dst = (uint32_t *)(smem_all + epk_off);
+        for (uint32_t i = threadIdx.x; i < D.E; i += blockDim.x) dst[i] = __ldg(D.epk + i);
+        __syncthreads();
+    }
+    const uint32_t *const epk_s = (const uint32_t *)(smem_all + epk_off);
 #if QMCB_WPB == 1
     unsigned char *const smem_raw = smem_all;
     const int lane = threadIdx.x;
@@ -182,6 +193,23 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     const uint64_t key = D.key[r];
     const Ham Hm = ham_view<MH>(D, r);
+    // variables of bond b; returns the packed table word (coupling code in the top 4 bits) when the table is in use
+    auto evars = [&](uint32_t b, int kind, uint32_t &v0, uint32_t &v1) -> uint32_t {
+        if (PK && kind == KIND_BOND) {
+            const uint32_t e = epk_s[b];
+            v0 = e & 0x3FFFu, v1 = (e >> 14) & 0x3FFFu;
+            return e;
+        }
+        bond_vars(D, b, kind, v0, v1);
+        return 0u;
+    };
+    auto ewt = [&](uint32_t e, uint32_t b, int kind, uint32_t s0, uint32_t s1) -> double {
+        if (PK && kind == KIND_BOND) {
+            const double j = D.jdict[e >> 28];
+            return fabs(j) + (s0 == s1 ? -j : j);
+        }
+        return bweight<HAS_H>(Hm, b, kind, s0, s1);
+    };
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     const uint64_t range = D.Nb;
     const uint64_t zone = D.zone;
@@ -226,11 +254,11 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
             int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
             uint32_t neww = w;
             // variables / stored bits of an existing op
-            uint32_t ov0 = 0, ov1 = 0;
+            uint32_t ov0 = 0, ov1 = 0, oe = 0;
             int okind = KIND_BOND;
             if (type >= T_DIAG) {
                 okind = bkind<HAS_H>(D, op_bond(w));
-                bond_vars(D, op_bond(w), okind, ov0, ov1);
+                oe = evars(op_bond(w), okind, ov0, ov1);
             }
             if (do_diag) {
                 S.fl[lane] = type == T_OFFD ? ov0 : NONE32;
@@ -260,9 +288,9 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                         if (b >= D.Nb) { err |= DEV_ERR_INVARIANT; return false; }
                         const int kind = bkind<HAS_H>(D, b);
                         uint32_t v0, v1;
-                        bond_vars(D, b, kind, v0, v1);
+                        const uint32_t e = evars(b, kind, v0, v1);
                         const uint32_t s0 = spin_here(v0), s1 = kind == KIND_BOND ? spin_here(v1) : 0u;
-                        if (!(pd * __ldg(Hm.hb_maxw + b) < bweight<HAS_H>(Hm, b, kind, s0, s1))) return false;
+                        if (!(pd * __ldg(Hm.hb_maxw + b) < ewt(e, b, kind, s0, s1))) return false;
                         const uint32_t bitsv = s0 | (s1 << 1);
                         nw = make_op(b, bitsv, bitsv);
                         return true;
@@ -385,7 +413,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                     }
                 }
                 double dnum = 0.0;  // num of an existing diagonal op does not depend on (cursor, n)
-                if (!HB && type == T_DIAG) dnum = bn * bweight<HAS_H>(Hm, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
+                if (!HB && type == T_DIAG) dnum = bn * ewt(oe, op_bond(w), okind, op_in(w) & 1u, (op_in(w) >> 1) & 1u);
                 bool try_fast = true;
                 TICK(1);  // load, classify, decode of existing ops, flip list
                 while (!HB && rem) {
@@ -446,10 +474,10 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                                 const uint32_t b = (uint32_t)hi;
                                 const int kind = bkind<HAS_H>(D, b);
                                 uint32_t v0, v1;
-                                bond_vars(D, b, kind, v0, v1);
+                                const uint32_t eb = evars(b, kind, v0, v1);
                                 const uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
                                 hz = state_bit(S.cd, v0) || (kind == KIND_BOND && state_bit(S.cd, v1));
-                                const double num = bn * bweight<HAS_H>(Hm, b, kind, s0, s1);
+                                const double num = bn * ewt(eb, b, kind, s0, s1);
                                 const uint32_t bitsv = s0 | (s1 << 1);
                                 opw = make_op(b, bitsv, bitsv);
                                 if (num >= dhiA) ok = true;                      // inserted without a second word
@@ -523,13 +551,13 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                             const uint32_t b = op_bond(S.opw[y]);
                             const int kind = bkind<HAS_H>(D, b);
                             uint32_t v0, v1;
-                            bond_vars(D, b, kind, v0, v1);
+                            const uint32_t eb = evars(b, kind, v0, v1);
                             uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
                             for (uint32_t m2 = __ballot_sync(FULL, type == T_OFFD) & ((1u << i) - 1u); m2; m2 &= m2 - 1) {
                                 const uint32_t fv = S.fl[__ffs(m2) - 1];
                                 s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
                             }
-                            const double num = bn * bweight<HAS_H>(Hm, b, kind, s0, s1);
+                            const double num = bn * ewt(eb, b, kind, s0, s1);
                             const uint32_t bitsv = s0 | (s1 << 1);
                             bool ok = false, ex = false, fail = false;
                             if (num >= dhiA) ok = true;
@@ -637,13 +665,13 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                                         const uint32_t b = (uint32_t)hi;
                                         const int kind = bkind<HAS_H>(D, b);
                                         uint32_t v0, v1;
-                                        bond_vars(D, b, kind, v0, v1);
+                                        const uint32_t eb = evars(b, kind, v0, v1);
                                         uint32_t s0 = state_bit(S.st, v0), s1 = kind == KIND_BOND ? state_bit(S.st, v1) : 0u;
                                         for (uint32_t m = fmask_lt; m; m &= m - 1) {  // flips by earlier lanes of this step
                                             const uint32_t fv = S.fl[__ffs(m) - 1];
                                             s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
                                         }
-                                        const double num = bn * bweight<HAS_H>(Hm, b, kind, s0, s1);
+                                        const double num = bn * ewt(eb, b, kind, s0, s1);
                                         const double den = (double)(M - ni);
                                         bool accept = num > den;
                                         if (!accept) {
@@ -710,7 +738,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                 uint32_t v0 = 0, v1 = 0;
                 if (valid && fw != OP_EMPTY) {
                     kind = bkind<HAS_H>(D, op_bond(fw));
-                    bond_vars(D, op_bond(fw), kind, v0, v1);
+                    evars(op_bond(fw), kind, v0, v1);
                 }
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
                 TICK(11);  // decode of the final ops
@@ -855,7 +883,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                 uint32_t v0 = 0, v1 = 0;
                 if (w != OP_EMPTY) {
                     kind = bkind<HAS_H>(D, op_bond(w));
-                    bond_vars(D, op_bond(w), kind, v0, v1);
+                    evars(op_bond(w), kind, v0, v1);
                 }
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
                 bool outdec = false;
@@ -932,6 +960,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     if (err) atomicOr(D.status, err);
 }
 
+int g_sse_fast_epk = 1;  // 0: never use the shared-memory edge table (A/B measurements)
 int g_sse_fast_minblocks = 0;  // resident blocks per SM the kernel is compiled for (register cap); 0 = choose by occupancy
 
 // returns the number of kernel launches, or -1 if this shape is not supported by the warp kernels
@@ -942,33 +971,44 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
     if (smem + 1024 > 227 * 1024) return -1;
     const uint32_t blocks = (D.R + QMCB_WPB - 1) / QMCB_WPB;
     if (smem * QMCB_WPB + 1024 > 227 * 1024) return -1;
-    typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t, uint32_t);
+    typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t, uint32_t, uint32_t);
     // register budget: the kernel is bound by the latency of each warp's dependent chain, so when shared memory or the
     // number of replicas keeps few blocks resident anyway, the 120-register build (no spills) is 10-20 % faster per
     // warp; with many replicas 72 registers keep 4096 of them (28 warps per SM) in one wave
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+    const size_t wanted = (blocks + nsm - 1) / nsm;
     int minb = g_sse_fast_minblocks;
     if (minb <= 0) {
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
-        const size_t by_smem = (227 * 1024) / (smem * QMCB_WPB + 1024);
-        const size_t wanted = (blocks + nsm - 1) / nsm;
-        const size_t resident = std::min(by_smem, wanted);
+        const size_t resident = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + 1024), wanted);
         minb = resident <= 4 ? 4 : (resident <= 6 ? 6 : 7);
     }
+    // block-shared packed edge table: low-occupancy build only, and only if it does not cost a resident block
+    size_t epk_bytes = 0;
+    if (minb == 4 && D.epk && !D.ham && g_sse_fast_epk) {
+        const size_t want = ((size_t)D.E * 4 + 15) / 16 * 16;
+        const size_t without = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + 1024), wanted);
+        const size_t with = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + want + 1024), wanted);
+        if (with >= 1 && with >= std::min<size_t>(without, 4)) epk_bytes = want;
+    }
     Kern kern;
-#define PICK(HB_, MH_)                                                                                            \
-    switch (minb) {                                                                                               \
-        case 4: kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_> : k_sse_fast<false, 4, HB_, MH_>; break;            \
-        case 6: kern = D.has_h ? k_sse_fast<true, 6, HB_, MH_> : k_sse_fast<false, 6, HB_, MH_>; break;            \
-        case 8: kern = (!HB_ && !MH_) ? (D.has_h ? k_sse_fast<true, 8, false, false> : k_sse_fast<false, 8, false, false>) \
-                                      : (D.has_h ? k_sse_fast<true, 7, HB_, MH_> : k_sse_fast<false, 7, HB_, MH_>); break; \
-        default: kern = D.has_h ? k_sse_fast<true, 7, HB_, MH_> : k_sse_fast<false, 7, HB_, MH_>; break;           \
+#define PICK(HB_, MH_)                                                                                                  \
+    switch (minb) {                                                                                                     \
+        case 4:                                                                                                         \
+            if (epk_bytes) kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, true> : k_sse_fast<false, 4, HB_, MH_, true>;  \
+            else kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, false> : k_sse_fast<false, 4, HB_, MH_, false>;         \
+            break;                                                                                                      \
+        case 6: kern = D.has_h ? k_sse_fast<true, 6, HB_, MH_, false> : k_sse_fast<false, 6, HB_, MH_, false>; break;    \
+        case 8: kern = (!HB_ && !MH_) ? (D.has_h ? k_sse_fast<true, 8, false, false, false> : k_sse_fast<false, 8, false, false, false>) \
+                                      : (D.has_h ? k_sse_fast<true, 7, HB_, MH_, false> : k_sse_fast<false, 7, HB_, MH_, false>); break; \
+        default: kern = D.has_h ? k_sse_fast<true, 7, HB_, MH_, false> : k_sse_fast<false, 7, HB_, MH_, false>; break;   \
     }
     if (D.ham) {
         if (D.hb_cum) { PICK(true, true) } else { PICK(false, true) }
     } else if (D.hb_cum) { PICK(true, false) } else { PICK(false, false) }
 #undef PICK
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    kern<<<blocks, 32 * QMCB_WPB, smem * QMCB_WPB, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem);
+    kern<<<blocks, 32 * QMCB_WPB, smem * QMCB_WPB + epk_bytes, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem,
+                                                                  epk_bytes ? (uint32_t)(smem * QMCB_WPB) : 0u);
     return 1;
 }

@@ -24,6 +24,8 @@ print(f"therm {therm} sweeps: {time.perf_counter() - t0:.3f} s, <n>={g.get_n().m
 g.set_mode(mode)
 if os.environ.get('PROF_MINB'):
     g.set_option('minblocks', int(os.environ['PROF_MINB']))
+if os.environ.get('PROF_EPK'):
+    g.set_option('shared_edge_table', int(os.environ['PROF_EPK']))
 if os.environ.get('PROF_DBG'):
     g.set_option('debug_counters', 1)
 for k in range(sweeps):
