@@ -91,7 +91,8 @@ int qmcb_get_hamiltonian_index(QmcbHandle *h, uint32_t *ham_of_replica /* [R] */
 int qmcb_get_offsets(QmcbHandle *h, double *offsets /* [R]: get_offset of each replica's Hamiltonian */);
 /* tuning knobs; "impl": 0 = warp-parallel kernels where available (default), 1 = serial-order kernels only */
 int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value);
-/* event counters of the SSE kernels (after qmcb_set_option(h, "debug_counters", 1)); diagnostics only */
+/* event counters and phase timers of the SSE kernels (after qmcb_set_option(h, "debug_counters", 1)); diagnostics
+ * only, and only counted by a library built with -DQMCB_PHASE_TIMERS (the production build compiles them out) */
 int qmcb_get_debug_counters(QmcbHandle *h, uint64_t *out64 /* [64] */);
 int qmcb_set_betas(QmcbHandle *h, const double *betas);
 int qmcb_get_betas(const QmcbHandle *h, double *betas);

@@ -24,7 +24,13 @@
 #define T_EMPTY 1
 #define T_DIAG 2
 #define T_OFFD 3
+// event counters (qmcb_get_debug_counters) and phase timers are compiled in with -DQMCB_PHASE_TIMERS only: even a
+// never-taken `if (D.dbg)` costs three instructions and a branch at eight places of every step
+#ifdef QMCB_PHASE_TIMERS
 #define DBG(i, v) do { if (D.dbg && lane == 0) atomicAdd(D.dbg + (i), (unsigned long long)(v)); } while (0)
+#else
+#define DBG(i, v) do { } while (0)
+#endif
 // phase timers, compiled in with -DQMCB_PHASE_TIMERS (tools/prof_sse.py prints them): TICK(k) adds the cycles
 // since the previous TICK to dbg[32 + k]
 #ifdef QMCB_PHASE_TIMERS
