@@ -228,3 +228,31 @@ def test_can_swap_graphs_is_enforced():
     for r, ref in enumerate(refs):
         assert e[r] == ref.timesteps(20, 1.0, MODE_FAST)
         assert np.array_equal(g.dump_ops(r), ref.dump_ops()) and np.array_equal(g.state_ref()[r], ref.state())
+
+
+@pytest.mark.parametrize("minblocks", [7, 4])
+@pytest.mark.parametrize("heatbath", [False, True])
+def test_per_replica_hamiltonians_in_every_kernel_build(minblocks, heatbath):
+    """set_hamiltonians + both diagonal rules through the 72-register and the 120-register builds (the launcher would
+    pick the latter for so few replicas)."""
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.two_d_periodic_mixed(4)
+    J0 = np.array([j for _, j in edges])
+    g = QmcIsingGraph(edges, 1.0, 0.5, 16, [11, 12, 13], 1.0, mode=MODE_FAST)
+    try:
+        g.set_option("minblocks", minblocks)
+        g.set_hamiltonians([J0, 2 * J0, 0.5 * J0], [1.0, 3.0, 0.7], [0.5, 0.25, 0.9], [1, 0, 2])
+        g.set_enable_heatbath(heatbath)
+        rows = [(2 * J0, 3.0, 0.25), (J0, 1.0, 0.5), (0.5 * J0, 0.7, 0.9)]
+        refs = []
+        for k, (jr, gam, hl) in zip([11, 12, 13], rows):
+            ref = po.SseOracle([(e, float(j)) for (e, _), j in zip(edges, jr)], gam, hl, 16, key=k)
+            ref.set_enable_heatbath(heatbath)
+            refs.append(ref)
+        e = g.timesteps(25, 1.0)
+        for r, ref in enumerate(refs):
+            assert e[r] == ref.timesteps(25, 1.0, MODE_FAST)
+            assert np.array_equal(g.dump_ops(r), ref.dump_ops()) and np.array_equal(g.state_ref()[r], ref.state())
+    finally:
+        g.set_option("minblocks", 0)

@@ -89,3 +89,33 @@ def test_small_beta_regime_takes_the_second_word_paths():
             for r, ref in enumerate(refs):
                 ref.timesteps(chunk, 0.05, mode)
                 assert same(g, r, ref), (mode, chunk, r)
+
+
+@pytest.mark.parametrize("heatbath", [False, True])
+@pytest.mark.parametrize("minblocks,shared_edges", [(7, 1), (8, 1), (6, 1), (4, 0), (4, 1)])
+def test_every_kernel_build_is_bit_exact(minblocks, shared_edges, heatbath):
+    """The launcher picks the register budget (72-register build for many replicas, 120-register build with the
+    shared-memory edge table when few blocks are resident) from the batch shape; tests have few replicas, so force
+    each compiled variant in turn and check it against the oracle from a thermalised config #3 state."""
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.square_periodic(32, -1.0)
+    R = 12
+    g = QmcIsingGraph(edges, 3.04, 0.0, 1024, 0x0B100000 + np.arange(R, dtype=np.uint64), 8.0, mode=MODE_FAST)
+    try:
+        g.set_option("minblocks", minblocks)
+        g.set_option("shared_edge_table", shared_edges)
+        g.set_enable_heatbath(heatbath)
+        g.timesteps(30, 8.0)
+        refs = {r: to_oracle(g, r, edges, 3.04, 0.0) for r in (0, 5, R - 1)}
+        for ref in refs.values():
+            ref.set_enable_heatbath(heatbath)
+        e = g.timesteps(3, 8.0)
+        for r, ref in refs.items():
+            e_ref = ref.timesteps(3, 8.0, MODE_FAST)
+            assert ref.error == 0 and same(g, r, ref), (minblocks, shared_edges, r)
+            assert e[r] == e_ref
+        assert g.verify()
+    finally:
+        g.set_option("minblocks", 0)  # process-wide tuning knobs: back to automatic
+        g.set_option("shared_edge_table", 1)
