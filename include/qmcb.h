@@ -143,6 +143,13 @@ int qmcb_get_bond_counts(QmcbHandle *h, uint32_t r, uint64_t *counts /* [num_bon
  * before slot p of one replica, for folds evaluated by the caller. */
 int qmcb_itime_magnetization(QmcbHandle *h, double *m_mean /* [R] */, double *m_sq, double *m_abs);
 int qmcb_itime_state(QmcbHandle *h, uint32_t r, uint64_t p, uint8_t *state /* [N] */);
+/* QmcAutoCorrelations::calculate_variable_autocorrelation (autocorrelations.rs:48-61; fft_autocorrelation :99-133):
+ * runs t sweeps sampling every sampling_freq (T = t / sampling_freq samples), returns per replica the circular
+ * autocorrelation of the mean-removed, normalised +-1 series of every variable, averaged over the variables
+ * (autocorr_out [R][T], entry 0 is 1).  Computed exactly on the device from bit-packed time series instead of an
+ * FFT.  samples_out ([R][T][N] bytes) and energy_out ([R]) are optional, as in qmcb_timesteps. */
+int qmcb_variable_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t sampling_freq, double *autocorr_out,
+                                  uint8_t *samples_out, double *energy_out);
 int qmcb_get_rng_cursors(QmcbHandle *h, uint64_t *cursors /* [R] */);
 int qmcb_set_rng_cursor(QmcbHandle *h, uint32_t r, uint64_t cursor);
 int qmcb_get_rng_keys(QmcbHandle *h, uint64_t *keys /* [R] */);

@@ -22,6 +22,8 @@ void launch_sse_bond_counts(const SseDev &D, uint32_t r, unsigned long long *cou
 void launch_sse_recount(const SseDev &D, uint32_t r, cudaStream_t st);
 void launch_sse_itime_magnetization(const SseDev &D, long long *sums_dev, cudaStream_t st);
 void launch_sse_itime_state(const SseDev &D, uint32_t r, uint64_t p_at, uint32_t *out_dev, cudaStream_t st);
+void launch_autocorrelation(const uint8_t *samples, uint32_t R, uint32_t N, uint32_t T, uint32_t *bits, uint32_t *ones, double *out,
+                            cudaStream_t st);
 void launch_sse_init_state(const SseDev &D, cudaStream_t st);
 int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
@@ -609,14 +611,13 @@ extern "C" int qmcb_num_bonds(const QmcbHandle *h, uint32_t *nb) {
     return QMCB_OK;
 }
 
-extern "C" int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t freq, double *energy_out, uint8_t *samples_out) {
-    CHECK_H(h);
+static int timesteps_impl(QmcbHandle *h, uint64_t t, uint64_t freq, double *energy_out, uint8_t *samples_out, bool keep_device_samples) {
     if (freq == 0) freq = 1;
     const SseDev &D = h->D;
     const uint64_t spr = t / freq;
     uint8_t *samples_dev = nullptr;
     int rc = QMCB_OK;
-    if (samples_out && spr) {
+    if ((samples_out || keep_device_samples) && spr) {
         const size_t need = (size_t)D.R * spr * D.N;
         if (need > h->samples_cap) {
             if (h->samples_dev) h->pool.release(h->samples_dev);
@@ -646,12 +647,47 @@ extern "C" int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t freq, double *
                 energy_out[r] = -(average_n / beta[r]) + h->offset_h[hr[r]];
             }
     }
-    if (rc == QMCB_OK && samples_dev) {
+    if (rc == QMCB_OK && samples_dev && samples_out) {
         cudaError_t e = cudaMemcpyAsync(samples_out, samples_dev, (size_t)D.R * spr * D.N, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail_cuda(e, "copy samples", __FILE__, __LINE__);
     }
     return rc;
+}
+extern "C" int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t freq, double *energy_out, uint8_t *samples_out) {
+    CHECK_H(h);
+    return timesteps_impl(h, t, freq, energy_out, samples_out, false);
+}
+
+// QmcAutoCorrelations::calculate_variable_autocorrelation (autocorrelations.rs:48-61, fft_autocorrelation :99-133):
+// t sweeps sampled every sampling_freq, every variable's +-1 time series mean-removed and normalised, circular
+// autocorrelation averaged over the variables.  The reference goes through an FFT; here the circular correlation of
+// a +-1 series is counted exactly with XOR + popcount on bit-packed time series (C[tau] = T - 2 * mismatches).
+extern "C" int qmcb_variable_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t freq, double *autocorr_out, uint8_t *samples_out,
+                                             double *energy_out) {
+    CHECK_H(h);
+    if (!autocorr_out) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    if (freq == 0) freq = 1;
+    const SseDev &D = h->D;
+    const uint64_t T = t / freq;
+    if (T == 0 || T > (1u << 20)) return fail(QMCB_ERR_BAD_ARG, "need between 1 and 2^20 samples");
+    int rc = timesteps_impl(h, t, freq, energy_out, samples_out, true);
+    if (rc) return rc;
+    const uint32_t Tw = (uint32_t)((T + 31) / 32);
+    uint32_t *bits = nullptr, *ones = nullptr;
+    double *out_dev = nullptr;
+    cudaError_t e = cudaMalloc(&bits, sizeof(uint32_t) * (size_t)D.R * D.N * (2 * Tw + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&ones, sizeof(uint32_t) * (size_t)D.R * D.N);
+    if (e == cudaSuccess) e = cudaMalloc(&out_dev, sizeof(double) * (size_t)D.R * T);
+    if (e == cudaSuccess) {
+        launch_autocorrelation(h->samples_dev, D.R, D.N, (uint32_t)T, bits, ones, out_dev, h->stream);
+        h->launches += 2;
+        e = cudaMemcpyAsync(autocorr_out, out_dev, sizeof(double) * (size_t)D.R * T, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(bits), cudaFree(ones), cudaFree(out_dev);
+    if (e != cudaSuccess) return fail_cuda(e, "autocorrelation", __FILE__, __LINE__);
+    return QMCB_OK;
 }
 
 extern "C" int qmcb_enqueue_sweeps(QmcbHandle *h, uint64_t t) {

@@ -799,6 +799,61 @@ void launch_sse_itime_magnetization(const SseDev &D, long long *sums_dev, cudaSt
 void launch_sse_itime_state(const SseDev &D, uint32_t r, uint64_t p_at, uint32_t *out_dev, cudaStream_t st) {
     k_sse_itime_state<<<1, 32, 0, st>>>(D, r, p_at, out_dev);
 }
+// ---- variable autocorrelation (autocorrelations.rs:48-61, :99-133) ---------------------------------------------
+// pass 1: samples [R][T][N] bytes -> per (replica, variable) the time series as bits, stored twice back to back
+// (2 T bits + padding) so that a circular shift is a plain window, and the number of ones
+__global__ void k_ac_pack(const uint8_t *samples, uint32_t R, uint32_t N, uint32_t T, uint32_t Tw, uint32_t *bits, uint32_t *ones) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (v >= N) return;
+    const uint8_t *src = samples + (size_t)r * T * N + v;
+    uint32_t *dst = bits + ((size_t)r * N + v) * (2 * Tw + 1);
+    for (uint32_t w = 0; w < 2 * Tw + 1; w++) dst[w] = 0;
+    uint32_t cnt = 0;
+    for (uint32_t t = 0; t < T; t++) {
+        if (src[(size_t)t * N]) {
+            cnt++;
+            dst[t >> 5] |= 1u << (t & 31);
+            const uint32_t u = t + T;
+            dst[u >> 5] |= 1u << (u & 31);
+        }
+    }
+    ones[(size_t)r * N + v] = cnt;
+}
+// pass 2: out[r][tau] = (1/N) sum_v (C_v[tau] - T m_v^2) / (T (1 - m_v^2)), C_v[tau] = sum_t s_t s_{t+tau mod T} = T - 2 mismatches.
+// One block per (tau, replica); the sum over the variables is a fixed-shape tree, so the result does not depend on timing.
+__global__ void __launch_bounds__(256) k_ac_corr(uint32_t N, uint32_t T, uint32_t Tw, const uint32_t *bits, const uint32_t *ones, double *out) {
+    __shared__ double part[256];
+    const uint32_t tau = blockIdx.x, r = blockIdx.y;
+    double acc = 0.0;
+    for (uint32_t v = threadIdx.x; v < N; v += blockDim.x) {
+        const uint32_t *x = bits + ((size_t)r * N + v) * (2 * Tw + 1);
+        uint32_t mism = 0;
+        for (uint32_t w = 0; w < Tw; w++) {
+            const uint32_t a = x[w];
+            const uint32_t pos = 32 * w + tau, wi = pos >> 5, sh = pos & 31;
+            const uint32_t b = sh ? __funnelshift_r(x[wi], x[wi + 1], sh) : x[wi];
+            uint32_t d = a ^ b;
+            if (w == Tw - 1 && (T & 31u)) d &= (1u << (T & 31u)) - 1u;
+            mism += __popc(d);
+        }
+        const double Td = (double)T, m = (2.0 * (double)ones[(size_t)r * N + v] - Td) / Td;
+        const double c = Td - 2.0 * (double)mism;
+        acc += (c - Td * m * m) / (Td * (1.0 - m * m));  // 0/0 = NaN for a variable that never changed, as the reference
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = 128; s; s >>= 1) {
+        if (threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[(size_t)r * T + tau] = part[0] / (double)N;
+}
+void launch_autocorrelation(const uint8_t *samples, uint32_t R, uint32_t N, uint32_t T, uint32_t *bits, uint32_t *ones, double *out,
+                            cudaStream_t st) {
+    const uint32_t Tw = (T + 31) / 32;
+    k_ac_pack<<<dim3((N + 127) / 128, R), 128, 0, st>>>(samples, R, N, T, Tw, bits, ones);
+    k_ac_corr<<<dim3(T, R), 256, 0, st>>>(N, T, Tw, bits, ones, out);
+}
 void launch_sse_recount(const SseDev &D, uint32_t r, cudaStream_t st) { k_sse_recount<<<1, 256, 0, st>>>(D, r); }
 void launch_sse_init_state(const SseDev &D, cudaStream_t st) {
     const int threads = 128;

@@ -259,6 +259,18 @@ class QmcIsingGraph:
         st = np.ascontiguousarray(state, dtype=np.uint8)
         check(self._L.qmcb_set_state(self._h, r, ptr(st, C.c_uint8)))
 
+    def calculate_variable_autocorrelation(self, timesteps, beta=None, sampling_freq=None, return_samples=False):
+        """QmcAutoCorrelations::calculate_variable_autocorrelation (autocorrelations.rs:48-61): [R][T] array, T =
+        timesteps // sampling_freq; optionally also the samples it was computed from."""
+        self._set_beta(beta)
+        freq = 1 if sampling_freq is None else int(sampling_freq)
+        T = int(timesteps) // freq
+        out = np.zeros((self.R, T), dtype=np.float64)
+        smp = np.zeros((self.R, T, self.nvars), dtype=np.uint8) if return_samples else None
+        check(self._L.qmcb_variable_autocorrelation(self._h, int(timesteps), freq, ptr(out, C.c_double),
+                                                    None if smp is None else ptr(smp, C.c_uint8), None))
+        return (out, smp) if return_samples else out
+
     def imaginary_time_magnetization(self):
         """imaginary_time_fold (qmc_ising.rs:815-821) with the magnetisation fold on the device: per replica
         (<m>, <m^2>, <|m|>) of the per-site magnetisation over the M imaginary-time slices."""

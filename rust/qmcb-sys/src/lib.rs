@@ -58,6 +58,8 @@ extern "C" {
     pub fn qmcb_pt_total_swaps(h: *mut QmcbHandle, swaps: *mut u64) -> c_int;
     pub fn qmcb_itime_magnetization(h: *mut QmcbHandle, m_mean: *mut f64, m_sq: *mut f64, m_abs: *mut f64) -> c_int;
     pub fn qmcb_itime_state(h: *mut QmcbHandle, r: u32, p: u64, state: *mut u8) -> c_int;
+    pub fn qmcb_variable_autocorrelation(h: *mut QmcbHandle, t: u64, sampling_freq: u64, autocorr_out: *mut f64,
+                                         samples_out: *mut u8, energy_out: *mut f64) -> c_int;
     pub fn qmcb_checkpoint_size(h: *mut QmcbHandle, bytes: *mut u64) -> c_int;
     pub fn qmcb_checkpoint_save(h: *mut QmcbHandle, buf: *mut c_void, bytes: u64) -> c_int;
     pub fn qmcb_checkpoint_load(buf: *const c_void, bytes: u64, device: c_int, out: *mut *mut QmcbHandle) -> c_int;

@@ -204,3 +204,28 @@ def test_imaginary_time_fold_matches():
     assert pos == sum(2 * int(refs[0].itime_state(p).sum()) > 16 for p in range(refs[0].cutoff))
     # the fold returns to the p = 0 state after the last slot (periodic in imaginary time)
     assert np.array_equal(refs[0].itime_state(refs[0].cutoff), refs[0].state())
+
+
+def fft_autocorrelation(samples):
+    """literal numpy restatement of fft_autocorrelation (autocorrelations.rs:99-133); samples [T][n] floats"""
+    tmax, n = samples.shape
+    x = samples - samples.mean(axis=0)
+    x = x / np.sqrt((x * x).sum(axis=0))
+    f = np.fft.fft(x.astype(np.complex128), axis=0)
+    r = np.fft.ifft(np.abs(f) ** 2, axis=0).real * tmax  # rustfft's inverse is unnormalised
+    return r.sum(axis=1) / (n * tmax)
+
+
+@pytest.mark.parametrize("T,freq", [(256, 1), (100, 3), (37, 2)])
+def test_variable_autocorrelation_matches_fft_restatement(T, freq):
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.square_periodic(4, -1.0)
+    g = QmcIsingGraph(edges, 2.0, 0.0, 16, [5, 6, 7], 1.0, mode=MODE_FAST)
+    g.timesteps(50, 1.0)
+    ac, samples = g.calculate_variable_autocorrelation(T * freq, 1.0, freq, return_samples=True)
+    assert ac.shape == (3, T) and samples.shape == (3, T, 16)
+    for r in range(3):
+        want = fft_autocorrelation(2.0 * samples[r].astype(np.float64) - 1.0)
+        assert np.allclose(ac[r], want, rtol=0, atol=1e-10), np.abs(ac[r] - want).max()  # tolerance: FFT rounding in the restatement
+        assert abs(ac[r][0] - 1.0) < 1e-12
