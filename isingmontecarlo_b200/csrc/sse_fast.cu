@@ -134,6 +134,7 @@ struct WarpSmem {
     uint32_t *st;   // [Nw] spin bits at the current p
     uint32_t *tb;   // [Nw] variable has at least one op
     uint32_t *cd;   // [Nw] P1: variable is flipped inside this step; P3: flip decision of the segment open on each variable
+    uint32_t *sb;   // [Nw] low-occupancy build only: variable is cut by a site op of this step (cleared at the end of the step)
     uint32_t *rep;  // [N]  P1: a member of the set of the segment currently open on each variable
 };
 #define SM_WIN 0
@@ -146,8 +147,11 @@ struct WarpSmem {
 #define SM_LINE 1104  // [32] the next 128-byte line of the operator string, filled by cp.async
 #define SM_VAR 1232   // st, tb, cd, rep
 
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw) {
-    return (SM_VAR + ((size_t)3 * Nw + N) * 4 + 15) / 16 * 16;
+// NB the 72-register build runs 7 blocks per SM and its shared memory (7 x (4 x 5712 + 1024) B at N = 1024) just fits
+// the 164 KiB carve-out: 128 B more per block and the driver moves to 196 KiB, L1 shrinks from 92 to 60 KiB and the
+// sweep takes 6 % longer (measured by padding; 228 KiB: +14 %).  Shared memory is not free here even when it fits.
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw, bool lowocc) {
+    return (SM_VAR + ((size_t)(lowocc ? 4 : 3) * Nw + N) * 4 + 15) / 16 * 16;
 }
 
 #ifndef QMCB_WPB
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     S.win = (unsigned long long *)(smem_raw + SM_WIN), S.fl = (uint32_t *)(smem_raw + SM_FL), S.opw = (uint32_t *)(smem_raw + SM_OPW);
     S.G = smem_raw + SM_G, S.wk = smem_raw + SM_WK, S.wl = smem_raw + SM_WL, S.wxg = (unsigned short *)(smem_raw + SM_WXG);
     S.line = (uint32_t *)(smem_raw + SM_LINE);
-    S.st = (uint32_t *)(smem_raw + SM_VAR), S.tb = S.st + Nw, S.cd = S.st + 2 * Nw, S.rep = S.st + 3 * Nw;
+    S.st = (uint32_t *)(smem_raw + SM_VAR), S.tb = S.st + Nw, S.cd = S.st + 2 * Nw, S.sb = S.st + 3 * Nw, S.rep = S.st + (MINB <= 4 ? 4 : 3) * Nw;
     if (lane < 16) S.G[64 + lane] = 255;  // positions past the window: exhausted (absorbing state of the walk)
     uint32_t *ops = D.ops + (size_t)r * D.cap;
     uint32_t *gstate = D.state + (size_t)r * Nw;
@@ -237,6 +241,8 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
         uint64_t cur = D.cursor[r];
         const double bn = D.beta[r] * (double)D.Nb;
         for (uint32_t j = lane; j < Nw; j += 32) S.st[j] = gstate[j], S.tb[j] = 0, S.cd[j] = 0;
+        if (MINB <= 4)
+            for (uint32_t j = lane; j < Nw; j += 32) S.sb[j] = 0;
         const bool do_diag = phases & 1u, do_clus = phases & 2u;
         if (do_clus) {
             for (uint32_t v = lane; v < N; v += 32) S.rep[v] = v, st_cg(P + v, v);
@@ -763,7 +769,20 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                     oa = ra = S.rep[v0], fa = true;
                     if (kind == KIND_BOND) ob = rb = S.rep[v1], fb = true;
                 }
-                {
+                // Does a site op of this step cut one of my variables at an earlier lane?  The lanes match their keys
+                // against each other (two MATCH.ANY of ~350 cycles each on the dependent chain).  In the low-occupancy
+                // build, where that latency is exposed, the site ops first mark their variable in a bitmap and the
+                // joining ops look their two variables up: only about a quarter of the steps have a hit and need the
+                // match (-7 % time there; the 72-register build has no shared memory to spare for the bitmap).
+                constexpr bool LOWOCC = MINB <= 4;
+                bool need_match = true;
+                if (LOWOCC) {
+                    if (kind == KIND_SITE) atomicOr(&S.sb[v0 >> 5], 1u << (v0 & 31));
+                    __syncwarp();
+                    const bool hit = joins && (state_bit(S.sb, v0) || (kind == KIND_BOND && state_bit(S.sb, v1)));
+                    need_match = __any_sync(FULL, hit);
+                }
+                if (need_match) {
                     // lanes with the same key see each other: site ops publish their variable in both rounds,
                     // joining ops ask for v0 then v1; the nearest earlier site op on the variable wins
                     const uint32_t nokey = 0x80000000u | (uint32_t)lane;
@@ -772,7 +791,8 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                     if (joins && ma) ra = N + nsite + (uint32_t)__popc(smask & ((1u << (31 - __clz(ma))) - 1u)), fa = false;
                     if (kind == KIND_BOND && mb) rb = N + nsite + (uint32_t)__popc(smask & ((1u << (31 - __clz(mb))) - 1u)), fb = false;
                 }
-                __syncwarp();  // new ids are initialised before anyone follows them
+                __syncwarp();  // new ids are initialised before anyone follows them; bitmap reads are done
+                if (LOWOCC && kind == KIND_SITE) atomicAnd(&S.sb[v0 >> 5], ~(1u << (v0 & 31)));
                 TICK(12);  // touched bits, representatives, same-step site ops (match)
                 if (kind == KIND_BOND && ra != rb) {
                     // (an atomic-free variant -- match the roots, lowest lane stores, others retry -- measured 4 % slower)
@@ -966,6 +986,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     if (err) atomicOr(D.status, err);
 }
 
+int g_sse_fast_pad = 0, g_sse_fast_carveout = -1;  // experiments: extra dynamic shared memory per block, carve-out preference
 int g_sse_fast_epk = 1;  // 0: never use the shared-memory edge table (A/B measurements)
 int g_sse_fast_minblocks = 0;  // resident blocks per SM the kernel is compiled for (register cap); 0 = choose by occupancy
 
@@ -973,8 +994,8 @@ int g_sse_fast_minblocks = 0;  // resident blocks per SM the kernel is compiled 
 int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
     // one warp per block: up to 32 blocks are resident per SM, each with its own shared memory
-    const size_t smem = warp_smem_bytes(D.N, D.Nw);
-    if (smem + 1024 > 227 * 1024) return -1;
+    size_t smem = warp_smem_bytes(D.N, D.Nw, false);
+    if (warp_smem_bytes(D.N, D.Nw, true) * QMCB_WPB + 1024 > 227 * 1024) return -1;
     const uint32_t blocks = (D.R + QMCB_WPB - 1) / QMCB_WPB;
     if (smem * QMCB_WPB + 1024 > 227 * 1024) return -1;
     typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t, uint32_t, uint32_t);
@@ -989,6 +1010,7 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
         const size_t resident = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + 1024), wanted);
         minb = resident <= 4 ? 4 : (resident <= 6 ? 6 : 7);
     }
+    if (minb <= 4) smem = warp_smem_bytes(D.N, D.Nw, true);  // the low-occupancy layout carries the site-op bitmap
     // block-shared packed edge table: low-occupancy build only, and only if it does not cost a resident block
     size_t epk_bytes = 0;
     if (minb == 4 && D.epk && !D.ham && g_sse_fast_epk) {
@@ -1014,7 +1036,8 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
     } else if (D.hb_cum) { PICK(true, false) } else { PICK(false, false) }
 #undef PICK
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    kern<<<blocks, 32 * QMCB_WPB, smem * QMCB_WPB + epk_bytes, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem,
+    if (g_sse_fast_carveout >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_sse_fast_carveout);
+    kern<<<blocks, 32 * QMCB_WPB, smem * QMCB_WPB + epk_bytes + g_sse_fast_pad, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem,
                                                                   epk_bytes ? (uint32_t)(smem * QMCB_WPB) : 0u);
     return 1;
 }

@@ -24,6 +24,9 @@ print(f"therm {therm} sweeps: {time.perf_counter() - t0:.3f} s, <n>={g.get_n().m
 g.set_mode(mode)
 if os.environ.get('PROF_MINB'):
     g.set_option('minblocks', int(os.environ['PROF_MINB']))
+for knob in ('smem_pad', 'smem_carveout'):
+    if os.environ.get('PROF_' + knob.upper()):
+        g.set_option(knob, int(os.environ['PROF_' + knob.upper()]))
 if os.environ.get('PROF_EPK'):
     g.set_option('shared_edge_table', int(os.environ['PROF_EPK']))
 if os.environ.get('PROF_DBG'):
