@@ -157,7 +157,7 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw, bool 
 #ifndef QMCB_WPB
 #define QMCB_WPB 4  // warps (= replicas) per block: one per scheduler of the SM (1 or 2 per block measured 8-12% slower)
 #endif
-template <bool HAS_H, int MINB, bool HB, bool MH, bool PK>
+template <bool HAS_H, int MINB, bool HB, bool MH, int PK>  // PK: 0 plain edge tables, 1 packed table in shared memory, 2 packed table through L1
 __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
                                                   uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, uint32_t smem_stride,
                                                   uint32_t epk_off) {
@@ -166,12 +166,12 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     // step's dependent chain become shared-memory loads instead of L1/L2 loads.  Compiled in (PK) only for the
     // low-occupancy builds: with 28 warps per SM the table shrinks L1 below what spills and the other tables need
     // (measured +8 % time on config #3, -20 % on L = 64 ladders).
-    if (PK) {
+    if (PK == 1) {
         uint32_t *dst = (uint32_t *)(smem_all + epk_off);
         for (uint32_t i = threadIdx.x; i < D.E; i += blockDim.x) dst[i] = __ldg(D.epk + i);
         __syncthreads();
     }
-    const uint32_t *const epk_s = (const uint32_t *)(smem_all + epk_off);
+    const uint32_t *const epk_s = PK == 2 ? D.epk : (const uint32_t *)(smem_all + epk_off);
 #if QMCB_WPB == 1
     unsigned char *const smem_raw = smem_all;
     const int lane = threadIdx.x;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     // variables of bond b; returns the packed table word (coupling code in the top 4 bits) when the table is in use
     auto evars = [&](uint32_t b, int kind, uint32_t &v0, uint32_t &v1) -> uint32_t {
         if (PK && kind == KIND_BOND) {
-            const uint32_t e = epk_s[b];
+            const uint32_t e = PK == 2 ? __ldg(epk_s + b) : epk_s[b];
             v0 = e & 0x3FFFu, v1 = (e >> 14) & 0x3FFFu;
             return e;
         }
@@ -1019,17 +1019,22 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
         const size_t with = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + want + 1024), wanted);
         if (with >= 1 && with >= std::min<size_t>(without, 4)) epk_bytes = want;
     }
+    // with many resident warps the packed table is still used, through L1: 8 KB instead of 32 KB of tables at config #3
+    const bool pk_l1 = !epk_bytes && D.epk && !D.ham && g_sse_fast_epk && minb == 7;
     Kern kern;
 #define PICK(HB_, MH_)                                                                                                  \
     switch (minb) {                                                                                                     \
         case 4:                                                                                                         \
-            if (epk_bytes) kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, true> : k_sse_fast<false, 4, HB_, MH_, true>;  \
-            else kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, false> : k_sse_fast<false, 4, HB_, MH_, false>;         \
+            if (epk_bytes) kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, 1> : k_sse_fast<false, 4, HB_, MH_, 1>;        \
+            else kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, 0> : k_sse_fast<false, 4, HB_, MH_, 0>;                 \
             break;                                                                                                      \
-        case 6: kern = D.has_h ? k_sse_fast<true, 6, HB_, MH_, false> : k_sse_fast<false, 6, HB_, MH_, false>; break;    \
-        case 8: kern = (!HB_ && !MH_) ? (D.has_h ? k_sse_fast<true, 8, false, false, false> : k_sse_fast<false, 8, false, false, false>) \
-                                      : (D.has_h ? k_sse_fast<true, 7, HB_, MH_, false> : k_sse_fast<false, 7, HB_, MH_, false>); break; \
-        default: kern = D.has_h ? k_sse_fast<true, 7, HB_, MH_, false> : k_sse_fast<false, 7, HB_, MH_, false>; break;   \
+        case 6: kern = D.has_h ? k_sse_fast<true, 6, HB_, MH_, 0> : k_sse_fast<false, 6, HB_, MH_, 0>; break;            \
+        case 8: kern = (!HB_ && !MH_) ? (D.has_h ? k_sse_fast<true, 8, false, false, 0> : k_sse_fast<false, 8, false, false, 0>) \
+                                      : (D.has_h ? k_sse_fast<true, 7, HB_, MH_, 0> : k_sse_fast<false, 7, HB_, MH_, 0>); break; \
+        default:                                                                                                        \
+            if (pk_l1 && !MH_) kern = D.has_h ? k_sse_fast<true, 7, HB_, false, 2> : k_sse_fast<false, 7, HB_, false, 2>; \
+            else kern = D.has_h ? k_sse_fast<true, 7, HB_, MH_, 0> : k_sse_fast<false, 7, HB_, MH_, 0>;                 \
+            break;                                                                                                      \
     }
     if (D.ham) {
         if (D.hb_cum) { PICK(true, true) } else { PICK(false, true) }

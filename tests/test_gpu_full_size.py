@@ -92,7 +92,7 @@ def test_small_beta_regime_takes_the_second_word_paths():
 
 
 @pytest.mark.parametrize("heatbath", [False, True])
-@pytest.mark.parametrize("minblocks,shared_edges", [(7, 1), (8, 1), (6, 1), (4, 0), (4, 1)])
+@pytest.mark.parametrize("minblocks,shared_edges", [(7, 1), (7, 0), (8, 1), (6, 1), (4, 0), (4, 1)])
 def test_every_kernel_build_is_bit_exact(minblocks, shared_edges, heatbath):
     """The launcher picks the register budget (72-register build for many replicas, 120-register build with the
     shared-memory edge table when few blocks are resident) from the batch shape; tests have few replicas, so force
