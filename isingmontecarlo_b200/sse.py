@@ -184,6 +184,33 @@ class QmcIsingGraph:
         check(self._L.qmcb_timesteps(self._h, int(t), freq, ptr(e, C.c_double), ptr(s, C.c_uint8)))
         return s[:, :k], e
 
+    def timesteps_measure(self, timesteps, beta, init_t, state_fold, sampling_freq=None):
+        """qmc_stepper.rs:85-103: fold `state_fold(acc, states)` over the sampled states; here `states` is the
+        [R][N] array of all replicas at one sampling time.  Returns (acc, energies[R])."""
+        samples, e = self.timesteps_sample(timesteps, beta, sampling_freq)
+        acc = init_t
+        for k in range(samples.shape[1]):
+            acc = state_fold(acc, samples[:, k])
+        return acc, e
+
+    def timesteps_sample_iter(self, t, beta, sampling_freq, iter_fn):
+        """qmc_stepper.rs:43-56: call iter_fn(states[R][N]) at every sampling time; returns the energies."""
+        _, e = self.timesteps_measure(t, beta, None, lambda _acc, st: iter_fn(st), sampling_freq)
+        return e
+
+    def timesteps_sample_iter_zip(self, t, beta, sampling_freq, zip_with, iter_fn):
+        """qmc_stepper.rs:59-77: iter_fn(item, states) for the items of zip_with, one per sampling time."""
+        it = iter(zip_with)
+
+        def step(_acc, st):
+            try:
+                iter_fn(next(it), st)
+            except StopIteration:
+                pass
+
+        _, e = self.timesteps_measure(t, beta, None, step, sampling_freq)
+        return e
+
     def enqueue_sweeps(self, t):
         check(self._L.qmcb_enqueue_sweeps(self._h, int(t)))
 

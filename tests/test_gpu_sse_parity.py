@@ -229,3 +229,22 @@ def test_variable_autocorrelation_matches_fft_restatement(T, freq):
         want = fft_autocorrelation(2.0 * samples[r].astype(np.float64) - 1.0)
         assert np.allclose(ac[r], want, rtol=0, atol=1e-10), np.abs(ac[r] - want).max()  # tolerance: FFT rounding in the restatement
         assert abs(ac[r][0] - 1.0) < 1e-12
+
+
+def test_stepper_iteration_helpers():
+    # QmcStepper::timesteps_measure / timesteps_sample_iter / timesteps_sample_iter_zip (qmc_stepper.rs:43-103)
+    edges = lattices.small_qmc_ring()
+    g, refs = make_pair(edges, 1.0, 0.0, 3, 1.0, MODE_FAST, R=3)
+    acc, e = g.timesteps_measure(12, 1.0, 0, lambda a, st: a + int(st.sum()), 3)
+    seen = []
+    e2 = g.timesteps_sample_iter(6, 1.0, 2, lambda st: seen.append(st.copy()))
+    tagged = []
+    g.timesteps_sample_iter_zip(6, 1.0, 1, ["a", "b"], lambda tag, st: tagged.append(tag))
+    want = 0
+    for ref in refs:
+        s, _ = ref.timesteps_sample(12, 1.0, 3, MODE_FAST)
+        want += int(s.sum())
+    assert acc == want and len(seen) == 3 and seen[0].shape == (3, 4) and tagged == ["a", "b"]
+    for r, ref in enumerate(refs):
+        s, e_ref = ref.timesteps_sample(6, 1.0, 2, MODE_FAST)
+        assert e2[r] == e_ref and all(np.array_equal(seen[k][r], s[k]) for k in range(3))
