@@ -539,6 +539,11 @@ extern "C" int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value) {
         (name[5] == 'p' ? g_sse_fast_pad : g_sse_fast_carveout) = (int)value;
         return QMCB_OK;
     }
+    if (!strcmp(name, "pipeline")) {
+        extern int g_sse_fast_pipe;
+        g_sse_fast_pipe = (int)value;
+        return QMCB_OK;
+    }
     if (!strcmp(name, "shared_edge_table")) {
         extern int g_sse_fast_epk;
         g_sse_fast_epk = (int)value;

@@ -151,14 +151,19 @@ struct WarpSmem {
 // the 164 KiB carve-out: 128 B more per block and the driver moves to 196 KiB, L1 shrinks from 92 to 60 KiB and the
 // sweep takes 6 % longer (measured by padding; 228 KiB: +14 %).  Shared memory is not free here even when it fits.
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t N, uint32_t Nw, bool lowocc) {
-    return (SM_VAR + ((size_t)(lowocc ? 4 : 3) * Nw + N) * 4 + 15) / 16 * 16;
+    return (SM_VAR + ((size_t)(lowocc ? 4 : 3) * Nw + N + (lowocc ? 72 : 0)) * 4 + 15) / 16 * 16;  // + ring[2][32] + 8 exchange words
 }
 
 #ifndef QMCB_WPB
 #define QMCB_WPB 4  // warps (= replicas) per block: one per scheduler of the SM (1 or 2 per block measured 8-12% slower)
 #endif
-template <bool HAS_H, int MINB, bool HB, bool MH, int PK>  // PK: 0 plain edge tables, 1 packed table in shared memory, 2 packed table through L1
-__global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
+// PK: 0 plain edge tables, 1 packed table in shared memory, 2 packed table through L1.
+// PIPE: two warps per replica.  The sweep of a long operator string is one dependent chain, and when few replicas
+// are resident (tempering ladders, big lattices) nothing hides it.  Role 0 runs the diagonal update of step k while
+// role 1 does the segment bookkeeping and unions of step k - 1 (final op words handed over through a two-slot ring in
+// shared memory, one named barrier per step); role 1 then does the closure and P2, role 0 P3 and the rest.
+template <bool HAS_H, int MINB, bool HB, bool MH, int PK, bool PIPE>
+__global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2 : 4 * MINB / QMCB_WPB) k_sse_fast(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq,
                                                   uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, uint32_t smem_stride,
                                                   uint32_t epk_off) {
     extern __shared__ __align__(16) unsigned char smem_all[];
@@ -180,10 +185,16 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     // the warp index goes through a warp reduction so that the compiler knows it (and everything derived from it: the
     // shared-memory base, the replica index and the replica's global pointers) is warp-uniform and keeps it in the
     // uniform register file instead of rematerialising it from %tid under register pressure
-    const uint32_t wib = __reduce_max_sync(0xFFFFFFFFu, threadIdx.x >> 5);
+    const uint32_t wraw = __reduce_max_sync(0xFFFFFFFFu, threadIdx.x >> 5);
+    const uint32_t wib = PIPE ? wraw >> 1 : wraw;
     unsigned char *const smem_raw = smem_all + wib * smem_stride;
     const int lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * QMCB_WPB + wib;
+    const bool roleA = !PIPE || (wraw & 1u) == 0, roleB = !PIPE || (wraw & 1u) == 1;  // diagonal update + P3 / segments + P2
+#define PAIR_SYNC()                                                                        \
+    do {                                                                                   \
+        if (PIPE) asm volatile("bar.sync %0, 64;" ::"r"(wib + 1u) : "memory");             \
+    } while (0)
 #endif
     if (r >= D.R) return;
     const uint32_t N = D.N, Nw = D.Nw;
@@ -193,6 +204,8 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
     S.line = (uint32_t *)(smem_raw + SM_LINE);
     S.st = (uint32_t *)(smem_raw + SM_VAR), S.tb = S.st + Nw, S.cd = S.st + 2 * Nw, S.sb = S.st + 3 * Nw, S.rep = S.st + (MINB <= 4 ? 4 : 3) * Nw;
     if (lane < 16) S.G[64 + lane] = 255;  // positions past the window: exhausted (absorbing state of the walk)
+    uint32_t *const ring = S.rep + N;                                     // PIPE: [2][32] final op words of a step
+    volatile uint32_t *const xchg = (volatile uint32_t *)(ring + 64);  // PIPE: n, cursor, cluster count between the roles
     uint32_t *ops = D.ops + (size_t)r * D.cap;
     uint32_t *gstate = D.state + (size_t)r * Nw;
     uint32_t *P = D.parent + (size_t)r * (N + D.cap + 1);
@@ -240,31 +253,38 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
         uint32_t n = D.n[r];
         uint64_t cur = D.cursor[r];
         const double bn = D.beta[r] * (double)D.Nb;
-        for (uint32_t j = lane; j < Nw; j += 32) S.st[j] = gstate[j], S.tb[j] = 0, S.cd[j] = 0;
-        if (MINB <= 4)
+        if (roleA)
+            for (uint32_t j = lane; j < Nw; j += 32) S.st[j] = gstate[j], S.cd[j] = 0;
+        if (roleB)
+            for (uint32_t j = lane; j < Nw; j += 32) S.tb[j] = 0;
+        if (MINB <= 4 && roleB)
             for (uint32_t j = lane; j < Nw; j += 32) S.sb[j] = 0;
         const bool do_diag = phases & 1u, do_clus = phases & 2u;
-        if (do_clus) {
+        if (do_clus && roleB) {
             for (uint32_t v = lane; v < N; v += 32) S.rep[v] = v, st_cg(P + v, v);
             if (HAS_H)
                 for (uint32_t j = lane; j < (uint32_t)bstride; j += 32) st_cg(frz + j, 0u);
         }
         __syncwarp();
+        PAIR_SYNC();
         uint32_t nsite = 0;
         bool anylong = false;
 
         // =========================== P1: diagonal update + unions ===========================
-        if (M) fetch_line(S.line, ops, lane);  // software prefetch of the next 128-byte line
-        for (uint32_t base = 0; base < M; base += 32) {
-            const uint32_t p = base + lane;
-            const bool valid = p < M;
+        if (M && roleA) fetch_line(S.line, ops, lane);  // software prefetch of the next 128-byte line
+        const uint32_t nit = (M + 31) / 32;
+        for (uint32_t it = 0; it < nit + (PIPE ? 1u : 0u); it++) {
+          uint32_t base = it * 32, p = base + lane;
+          bool valid = p < M;
+          uint32_t neww = OP_EMPTY;
+          if (roleA && it < nit) {
             uint32_t w = take_line(S.line, lane);
             if (!valid) w = OP_EMPTY;
             if (base + 32 < M) fetch_line(S.line, ops + base + 32, lane);
             DBG(0, 1);
             TICK(0);  // between steps
             int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
-            uint32_t neww = w;
+            neww = w;
             // variables / stored bits of an existing op
             uint32_t ov0 = 0, ov1 = 0, oe = 0;
             int okind = KIND_BOND;
@@ -743,7 +763,13 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                 __syncwarp();
             }
             TICK(6);  // store + state flips
-            if (do_clus) {
+            if (PIPE) ring[(it & 1u) * 32 + lane] = neww;
+          }
+            if (PIPE) {  // role 1 works on the step role 0 finished one iteration ago
+                base = (it - 1u) * 32, p = base + lane, valid = it >= 1 && p < M;
+                if (roleB && it >= 1) neww = ring[((it - 1u) & 1u) * 32 + lane];
+            }
+            if (do_clus && roleB && (!PIPE || it >= 1)) {
                 // ---- segments and unions on the final ops of this step
                 const uint32_t fw = neww;
                 int kind = -1;
@@ -811,11 +837,19 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
                 __syncwarp();
                 TICK(7);  // segment ids + union-find
             }
+            PAIR_SYNC();
         }
-        if (do_diag && lane == 0) D.n[r] = n;
+        if (do_diag && lane == 0 && roleA) D.n[r] = n;
+        if (PIPE) {  // role 1 needs n and the stream position for the closure and P2
+            if (roleA && lane == 0) xchg[0] = n, xchg[1] = (uint32_t)cur, xchg[2] = (uint32_t)(cur >> 32);
+            PAIR_SYNC();
+            if (!roleA) n = xchg[0], cur = ((uint64_t)xchg[2] << 32) | xchg[1];
+        }
 
         uint32_t ncl = 0;
         if (do_clus && n > 0) {
+          const uint64_t c0 = cur;
+          if (roleB) {
             // periodic closure: the segment open at the end of variable v is the one crossing p = 0
             for (uint32_t v = lane; v < N; v += 32) {
                 const uint32_t rp = S.rep[v];
@@ -824,7 +858,6 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
             __syncwarp();
             __threadfence_block();
             TICK(8);  // closure
-            const uint64_t c0 = cur;
             const uint32_t nseg = N + nsite;
             const uint32_t nwords = (nseg + 31) / 32;
             bool frozen_all = false;
@@ -887,8 +920,13 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
             }
             untouched = __reduce_add_sync(FULL, untouched);
             ncl = nsite == 0 ? 1u : nroots - untouched;
+            if (PIPE && lane == 0) xchg[3] = ncl;
 
             TICK(9);  // P2
+          }
+          PAIR_SYNC();  // the flip bits are complete
+          if (roleA) {
+            if (PIPE) ncl = xchg[3];
             // =========================== P3: apply the flips ===========================
             for (uint32_t j = lane; j < Nw; j += 32) S.cd[j] = ld_cg(decb + j);
             __syncwarp();
@@ -944,8 +982,9 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
             for (uint32_t j = lane; j < Nw; j += 32) S.st[j] ^= ld_cg(decb + j) & S.tb[j];
             cur = c0 + 1;
             __syncwarp();
+          }
         }
-        if (do_clus) {
+        if (do_clus && roleA) {
             // free spins: qmc_ising.rs:780-784
             for (uint32_t base = 0; base < N; base += 32) {
                 const uint32_t v = base + lane;
@@ -960,8 +999,9 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
             __syncwarp();
             if (lane == 0) D.ncl[r] = ncl;
         }
-        for (uint32_t j = lane; j < Nw; j += 32) gstate[j] = S.st[j];
-        if (lane == 0) {
+        if (roleA)
+            for (uint32_t j = lane; j < Nw; j += 32) gstate[j] = S.st[j];
+        if (lane == 0 && roleA) {
             D.cursor[r] = cur;
             if (phases & 4u) {
                 const uint32_t grown = n + n / 2;  // qmc_ising.rs:786
@@ -971,22 +1011,24 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB) k_sse_fast
         if (phases & 8u) {
             done++;
             const uint64_t idx = done - sample_origin;
-            if (lane == 0) D.vupd[r] += n;
-            if (idx % sample_freq == 0) {
+            if (lane == 0 && roleA) D.vupd[r] += n;
+            if (idx % sample_freq == 0 && roleA) {
                 if (lane == 0) D.sum_n[r] += n;
                 if (samples) {
                     uint8_t *dst = samples + ((size_t)r * samples_per_rep + (idx / sample_freq - 1)) * N;
                     for (uint32_t v = lane; v < N; v += 32) dst[v] = (uint8_t)state_bit(S.st, v);
                 }
             }
-            if (lane == 0) D.done[r] = done;
+            if (lane == 0 && roleA) D.done[r] = done;
         }
         __syncwarp();
+        PAIR_SYNC();  // role 1 re-initialises its tables only after role 0 is done with them
     }
     if (err) atomicOr(D.status, err);
 }
 
 int g_sse_fast_pad = 0, g_sse_fast_carveout = -1;  // experiments: extra dynamic shared memory per block, carve-out preference
+int g_sse_fast_pipe = 1;  // 0: never use two warps per replica
 int g_sse_fast_epk = 1;  // 0: never use the shared-memory edge table (A/B measurements)
 int g_sse_fast_minblocks = 0;  // resident blocks per SM the kernel is compiled for (register cap); 0 = choose by occupancy
 
@@ -1021,19 +1063,24 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
     }
     // with many resident warps the packed table is still used, through L1: 8 KB instead of 32 KB of tables at config #3
     const bool pk_l1 = !epk_bytes && D.epk && !D.ham && g_sse_fast_epk && minb == 7;
+    // two warps per replica (PIPE) when at most two blocks of four replicas per SM are wanted and fit
+    const bool pipe = minb == 4 && g_sse_fast_pipe && wanted <= 2 && (size_t)(227 * 1024) / (smem * QMCB_WPB + epk_bytes + 1024) >= wanted;
     Kern kern;
 #define PICK(HB_, MH_)                                                                                                  \
     switch (minb) {                                                                                                     \
         case 4:                                                                                                         \
-            if (epk_bytes) kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, 1> : k_sse_fast<false, 4, HB_, MH_, 1>;        \
-            else kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, 0> : k_sse_fast<false, 4, HB_, MH_, 0>;                 \
+            if (pipe) {                                                                                                 \
+                if (epk_bytes) kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, 1, true> : k_sse_fast<false, 4, HB_, MH_, 1, true>; \
+                else kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, 0, true> : k_sse_fast<false, 4, HB_, MH_, 0, true>;  \
+            } else if (epk_bytes) kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, 1, false> : k_sse_fast<false, 4, HB_, MH_, 1, false>; \
+            else kern = D.has_h ? k_sse_fast<true, 4, HB_, MH_, 0, false> : k_sse_fast<false, 4, HB_, MH_, 0, false>;    \
             break;                                                                                                      \
-        case 6: kern = D.has_h ? k_sse_fast<true, 6, HB_, MH_, 0> : k_sse_fast<false, 6, HB_, MH_, 0>; break;            \
-        case 8: kern = (!HB_ && !MH_) ? (D.has_h ? k_sse_fast<true, 8, false, false, 0> : k_sse_fast<false, 8, false, false, 0>) \
-                                      : (D.has_h ? k_sse_fast<true, 7, HB_, MH_, 0> : k_sse_fast<false, 7, HB_, MH_, 0>); break; \
+        case 6: kern = D.has_h ? k_sse_fast<true, 6, HB_, MH_, 0, false> : k_sse_fast<false, 6, HB_, MH_, 0, false>; break; \
+        case 8: kern = (!HB_ && !MH_) ? (D.has_h ? k_sse_fast<true, 8, false, false, 0, false> : k_sse_fast<false, 8, false, false, 0, false>) \
+                                      : (D.has_h ? k_sse_fast<true, 7, HB_, MH_, 0, false> : k_sse_fast<false, 7, HB_, MH_, 0, false>); break; \
         default:                                                                                                        \
-            if (pk_l1 && !MH_) kern = D.has_h ? k_sse_fast<true, 7, HB_, false, 2> : k_sse_fast<false, 7, HB_, false, 2>; \
-            else kern = D.has_h ? k_sse_fast<true, 7, HB_, MH_, 0> : k_sse_fast<false, 7, HB_, MH_, 0>;                 \
+            if (pk_l1 && !MH_) kern = D.has_h ? k_sse_fast<true, 7, HB_, false, 2, false> : k_sse_fast<false, 7, HB_, false, 2, false>; \
+            else kern = D.has_h ? k_sse_fast<true, 7, HB_, MH_, 0, false> : k_sse_fast<false, 7, HB_, MH_, 0, false>;    \
             break;                                                                                                      \
     }
     if (D.ham) {
@@ -1042,7 +1089,7 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
 #undef PICK
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (g_sse_fast_carveout >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_sse_fast_carveout);
-    kern<<<blocks, 32 * QMCB_WPB, smem * QMCB_WPB + epk_bytes + g_sse_fast_pad, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem,
+    kern<<<blocks, (pipe ? 64 : 32) * QMCB_WPB, smem * QMCB_WPB + epk_bytes + g_sse_fast_pad, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem,
                                                                   epk_bytes ? (uint32_t)(smem * QMCB_WPB) : 0u);
     return 1;
 }

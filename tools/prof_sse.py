@@ -24,7 +24,7 @@ print(f"therm {therm} sweeps: {time.perf_counter() - t0:.3f} s, <n>={g.get_n().m
 g.set_mode(mode)
 if os.environ.get('PROF_MINB'):
     g.set_option('minblocks', int(os.environ['PROF_MINB']))
-for knob in ('smem_pad', 'smem_carveout'):
+for knob in ('smem_pad', 'smem_carveout', 'pipeline'):
     if os.environ.get('PROF_' + knob.upper()):
         g.set_option(knob, int(os.environ['PROF_' + knob.upper()]))
 if os.environ.get('PROF_EPK'):
