@@ -92,7 +92,8 @@ int qmcb_get_offsets(QmcbHandle *h, double *offsets /* [R]: get_offset of each r
 /* tuning knobs.  Per handle: "impl" 0 = warp-parallel kernels where available (default), 1 = serial-order kernels only;
  * "auto_capacity" 1 = grow the strings on demand even if a capacity was given; "debug_counters".  Process-wide
  * (kernel selection, for measurements and tests): "minblocks" 0 = choose the register budget from the batch shape
- * (default), 4/6/7/8 = force that build; "shared_edge_table" 0/1; "smem_pad", "smem_carveout" (experiments). */
+ * (default), 4/6/7/8 = force that build; "shared_edge_table" 0/1; "pipeline" 0/1 (two warps per replica when few
+ * replicas are resident); "smem_pad", "smem_carveout" (experiments). */
 int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value);
 /* event counters and phase timers of the SSE kernels (after qmcb_set_option(h, "debug_counters", 1)); diagnostics
  * only, and only counted by a library built with -DQMCB_PHASE_TIMERS (the production build compiles them out) */

@@ -92,8 +92,8 @@ def test_small_beta_regime_takes_the_second_word_paths():
 
 
 @pytest.mark.parametrize("heatbath", [False, True])
-@pytest.mark.parametrize("minblocks,shared_edges", [(7, 1), (7, 0), (8, 1), (6, 1), (4, 0), (4, 1)])
-def test_every_kernel_build_is_bit_exact(minblocks, shared_edges, heatbath):
+@pytest.mark.parametrize("minblocks,shared_edges,pipeline", [(7, 1, 1), (7, 0, 1), (8, 1, 1), (6, 1, 1), (4, 0, 1), (4, 1, 1), (4, 0, 0), (4, 1, 0)])
+def test_every_kernel_build_is_bit_exact(minblocks, shared_edges, pipeline, heatbath):
     """The launcher picks the register budget (72-register build for many replicas, 120-register build with the
     shared-memory edge table when few blocks are resident) from the batch shape; tests have few replicas, so force
     each compiled variant in turn and check it against the oracle from a thermalised config #3 state."""
@@ -105,6 +105,7 @@ def test_every_kernel_build_is_bit_exact(minblocks, shared_edges, heatbath):
     try:
         g.set_option("minblocks", minblocks)
         g.set_option("shared_edge_table", shared_edges)
+        g.set_option("pipeline", pipeline)
         g.set_enable_heatbath(heatbath)
         g.timesteps(30, 8.0)
         refs = {r: to_oracle(g, r, edges, 3.04, 0.0) for r in (0, 5, R - 1)}
@@ -119,3 +120,4 @@ def test_every_kernel_build_is_bit_exact(minblocks, shared_edges, heatbath):
     finally:
         g.set_option("minblocks", 0)  # process-wide tuning knobs: back to automatic
         g.set_option("shared_edge_table", 1)
+        g.set_option("pipeline", 1)
