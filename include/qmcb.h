@@ -192,6 +192,9 @@ int qmcb_pt_export(QmcbHandle *h, uint64_t *rec_dev);
  * cutoff to the global max (tempering_container.rs:129-137), evaluate the swaps of every ladder
  * from the shared PT stream (:140-146, :241-302) and relabel the local configurations. */
 int qmcb_pt_apply(QmcbHandle *h, const uint64_t *all_rec_dev, uint64_t n_records);
+/* tempering_step (tempering_container.rs:121-149) when the whole container lives on this handle (slot_begin = 0 and
+ * R = n_chains * n_betas): steps 1 and 2 back to back on the device */
+int qmcb_pt_step_local(QmcbHandle *h);
 int qmcb_pt_total_swaps(QmcbHandle *h, uint64_t *swaps); /* get_total_swaps :231-233 */
 int qmcb_pt_get_config(const QmcbHandle *h, uint32_t *n_chains, uint32_t *n_betas, uint32_t *slot_begin);
 int qmcb_pt_get_slots(QmcbHandle *h, uint32_t *slots /* [R] current slot of each configuration */);

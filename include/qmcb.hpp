@@ -166,9 +166,92 @@ public:
     }
     void set_mode(int mode) { check(qmcb_set_mode(h_, mode)); }
     void set_enable_heatbath(bool enable) { check(qmcb_set_enable_heatbath(h_, enable ? 1 : 0)); }  // qmc_ising.rs:444-486
+    // graphs with their own couplings in one batch (tempering_traits.rs:122-154): rows of (J[E], transverse, longitudinal)
+    void set_hamiltonians(const std::vector<std::vector<double>> &j_rows, const std::vector<double> &transverse,
+                          const std::vector<double> &longitudinal, const std::vector<uint32_t> &ham_of_replica) {
+        std::vector<double> flat;
+        for (auto &row : j_rows) flat.insert(flat.end(), row.begin(), row.end());
+        check(qmcb_set_hamiltonians(h_, (uint32_t)transverse.size(), flat.data(), transverse.data(), longitudinal.data(), ham_of_replica.data()));
+    }
+    // QmcStepper::imaginary_time_fold (qmc_stepper.rs:165-168) for replica r, the closure evaluated on the host
+    template <typename F, typename T>
+    T imaginary_time_fold(size_t r, F fold_fn, T init) {
+        std::vector<uint64_t> cut(replicas_);
+        check(qmcb_get_cutoffs(h_, cut.data()));
+        std::vector<uint8_t> raw(nvars_);
+        std::vector<bool> st(nvars_);
+        T acc = init;
+        for (uint64_t p = 0; p < cut[r]; p++) {
+            check(qmcb_itime_state(h_, (uint32_t)r, p, raw.data()));
+            for (size_t v = 0; v < nvars_; v++) st[v] = raw[v] != 0;
+            acc = fold_fn(acc, st);
+        }
+        return acc;
+    }
+    // QmcAutoCorrelations::calculate_variable_autocorrelation (autocorrelations.rs:48-61): [replica][lag]
+    std::vector<std::vector<double>> calculate_variable_autocorrelation(size_t timesteps, double beta, size_t sampling_freq = 1) {
+        set_beta(beta);
+        const size_t T = timesteps / sampling_freq;
+        std::vector<double> flat(replicas_ * T);
+        check(qmcb_variable_autocorrelation(h_, timesteps, sampling_freq, flat.data(), nullptr, nullptr));
+        std::vector<std::vector<double>> out(replicas_);
+        for (size_t r = 0; r < replicas_; r++) out[r].assign(flat.begin() + r * T, flat.begin() + (r + 1) * T);
+        return out;
+    }
+    // serde replacement (qmc_ising.rs:1001-1087): the whole batch, stream positions included
+    std::vector<uint8_t> to_bytes() {
+        uint64_t n = 0;
+        check(qmcb_checkpoint_size(h_, &n));
+        std::vector<uint8_t> buf(n);
+        check(qmcb_checkpoint_save(h_, buf.data(), n));
+        return buf;
+    }
+    static QmcIsingGraph from_bytes(const std::vector<uint8_t> &buf, int device = 0) {
+        QmcIsingGraph g;
+        check(qmcb_checkpoint_load(buf.data(), buf.size(), device, &g.h_));
+        uint32_t r = 0, n = 0;
+        check(qmcb_num_replicas(g.h_, &r));
+        check(qmcb_num_vars(g.h_, &n));
+        g.replicas_ = r, g.nvars_ = n;
+        g.betas_.resize(r);
+        check(qmcb_get_betas(g.h_, g.betas_.data()));
+        return g;
+    }
+    std::vector<uint64_t> rng_cursors() {
+        std::vector<uint64_t> c(replicas_);
+        check(qmcb_get_rng_cursors(h_, c.data()));
+        return c;
+    }
     QmcbHandle *raw() { return h_; }
 };
 using DefaultQmcIsingGraph = QmcIsingGraph;
+
+// qmc::sse::parallel_tempering::TemperingContainer (tempering_container.rs:19-302) on one GPU: n_chains ladders of
+// betas.size() slots; add_qmc_stepper is replaced by giving the whole ladder at construction.
+class TemperingContainer {
+    QmcIsingGraph g_;
+    size_t n_betas_ = 0, n_chains_ = 0;
+
+public:
+    TemperingContainer(const std::vector<Edge> &edges, double transverse, double longitudinal, size_t cutoff, const std::vector<double> &betas,
+                       size_t n_chains, const std::vector<uint64_t> &rng_keys, uint64_t pt_key, int mode = QMCB_MODE_FAST)
+        : g_(QmcIsingGraph::new_with_rng(edges, transverse, longitudinal, cutoff, rng_keys, nullptr, mode)), n_betas_(betas.size()), n_chains_(n_chains) {
+        std::vector<double> all;
+        for (size_t c = 0; c < n_chains; c++) all.insert(all.end(), betas.begin(), betas.end());
+        if (all.size() != rng_keys.size()) throw Error(QMCB_ERR_BAD_ARG, "one rng key per slot");
+        check(qmcb_pt_configure(g_.raw(), (uint32_t)n_chains, (uint32_t)betas.size(), 0, all.data(), rng_keys.data(), pt_key));
+    }
+    size_t num_graphs() const { return n_betas_ * n_chains_; }
+    void timesteps(size_t t) { check(qmcb_timesteps(g_.raw(), t, 1, nullptr, nullptr)); }  // :76-81
+    void tempering_step() { check(qmcb_pt_step_local(g_.raw())); }                          // :121-149
+    uint64_t get_total_swaps() {                                                            // :231-233
+        uint64_t s = 0;
+        check(qmcb_pt_total_swaps(g_.raw(), &s));
+        return s;
+    }
+    bool verify() { return g_.verify(); }
+    QmcIsingGraph &graph() { return g_; }
+};
 
 class GraphState {
     CmcbHandle *h_ = nullptr;

@@ -82,6 +82,7 @@ SIGNATURES = {
     "qmcb_pt_record_words": [vp, u32p],
     "qmcb_pt_export": [vp, vp],
     "qmcb_pt_apply": [vp, vp, C.c_uint64],
+    "qmcb_pt_step_local": [vp],
     "qmcb_pt_total_swaps": [vp, u64p],
     "qmcb_pt_get_config": [vp, u32p, u32p, u32p],
     "qmcb_pt_get_slots": [vp, u32p],

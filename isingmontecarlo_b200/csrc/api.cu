@@ -106,6 +106,7 @@ struct QmcbHandle {
     uint32_t H = 1;
     std::vector<double> Jtab_h, gam_h, hl_h, offset_h;  // [H][E], [H], [H], [H]
     std::vector<uint32_t> ham_slot_h;                   // [S] tempering: Hamiltonian row of each slot
+    uint64_t *pt_rec_dev = nullptr;                     // record buffer of qmcb_pt_step_local
 };
 
 #define CHECK_H(h)                                              \
@@ -1091,6 +1092,16 @@ extern "C" int qmcb_pt_apply(QmcbHandle *h, const uint64_t *all_rec_dev, uint64_
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return QMCB_OK;
+}
+// tempering_step for a container that lives on ONE handle (every slot of every ladder is local): export + apply with
+// a record buffer owned by the handle, no host plumbing in between
+extern "C" int qmcb_pt_step_local(QmcbHandle *h) {
+    CHECK_H(h);
+    if (!h->pt_on) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+    if (h->P.cfg_begin != 0 || h->D.R != h->pt_S) return fail(QMCB_ERR_BAD_ARG, "the ladder is spread over several handles: use qmcb_pt_export + all-gather + qmcb_pt_apply");
+    if (!h->pt_rec_dev) CUDA_TRY(h->pool.alloc(&h->pt_rec_dev, (size_t)h->pt_S * PT_REC_WORDS_MH));
+    int rc = qmcb_pt_export(h, h->pt_rec_dev);
+    return rc ? rc : qmcb_pt_apply(h, h->pt_rec_dev, h->pt_S);
 }
 extern "C" int qmcb_pt_total_swaps(QmcbHandle *h, uint64_t *swaps) {
     CHECK_H(h);

@@ -55,6 +55,7 @@ extern "C" {
     pub fn qmcb_pt_record_words(h: *const QmcbHandle, words: *mut u32) -> c_int;
     pub fn qmcb_pt_export(h: *mut QmcbHandle, rec_dev: *mut u64) -> c_int;
     pub fn qmcb_pt_apply(h: *mut QmcbHandle, all_rec_dev: *const u64, n_records: u64) -> c_int;
+    pub fn qmcb_pt_step_local(h: *mut QmcbHandle) -> c_int;
     pub fn qmcb_pt_total_swaps(h: *mut QmcbHandle, swaps: *mut u64) -> c_int;
     pub fn qmcb_itime_magnetization(h: *mut QmcbHandle, m_mean: *mut f64, m_sq: *mut f64, m_abs: *mut f64) -> c_int;
     pub fn qmcb_itime_state(h: *mut QmcbHandle, r: u32, p: u64, state: *mut u8) -> c_int;

@@ -80,6 +80,33 @@ int main() {
             ASSERT(se.first[0].size() == 4 && se.first[0][0].size() == 3);
         }
     }
+    {  // tempering_container.rs tests (:600-667 run ladders and check verify()): swaps happen, invariants hold
+        std::vector<double> betas;
+        for (int k = 0; k < 6; k++) betas.push_back(0.4 + 0.3 * k);
+        std::vector<uint64_t> keys;
+        for (uint64_t s = 0; s < 12; s++) keys.push_back(0x7E00 + s);
+        qmcb::TemperingContainer tc(two_d_periodic(4), 1.0, 0.0, 16, betas, 2, keys, 0xBEEF);
+        for (int i = 0; i < 30; i++) {
+            tc.timesteps(3);
+            tc.tempering_step();
+        }
+        ASSERT(tc.num_graphs() == 12 && tc.get_total_swaps() > 0 && tc.verify());
+    }
+    {  // serde round trip (qmc_ising.rs serialize_test): a restored batch continues identically
+        auto g = qmcb::DefaultQmcIsingGraph::new_with_rng(two_d_periodic(3), 1.0, 0.3, 9, {21, 22, 23}, nullptr, QMCB_MODE_FAST);
+        g.timesteps(50, 1.0);
+        auto blob = g.to_bytes();
+        auto e1 = g.timesteps(20, 1.0);
+        auto g2 = qmcb::DefaultQmcIsingGraph::from_bytes(blob);
+        auto e2 = g2.timesteps(20, 1.0);
+        ASSERT(e1 == e2 && g.state_ref() == g2.state_ref() && g.rng_cursors() == g2.rng_cursors());
+        // imaginary_time_fold with a closure: the propagated state returns to the p = 0 state only at the end, and
+        // the number of slices seen equals the cutoff
+        size_t slices = g2.imaginary_time_fold(0, [](size_t acc, const std::vector<bool> &) { return acc + 1; }, (size_t)0);
+        ASSERT(slices == g2.get_cutoff()[0]);
+        auto ac = g2.calculate_variable_autocorrelation(64, 1.0, 1);
+        ASSERT(ac.size() == 3 && ac[0].size() == 64 && std::abs(ac[0][0] - 1.0) < 1e-12);
+    }
     {  // error behaviour: status codes become exceptions, never aborts
         bool threw = false;
         try {
