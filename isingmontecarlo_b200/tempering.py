@@ -130,6 +130,9 @@ class TemperingContainer:
     def tempering_step(self):
         """tempering_container.rs:121-149 (parallel_tempering_step :373-402)"""
         L, g = self.graph._L, self.graph
+        if self.world == 1:  # the whole container lives on this handle: no host plumbing between the two halves
+            check(L.qmcb_pt_step_local(g._h))
+            return
         check(L.qmcb_pt_export(g._h, C.c_void_p(self._rec.data_ptr())))
         check(L.qmcb_synchronize(g._h))
         allrec = gather_records(self._rec, self.group)
