@@ -359,4 +359,79 @@ class QmcIsingGraph:
         return t.value
 
 
+class Qmc:
+    """`qmc::sse::Qmc` (qmc_runner.rs:22-403) as far as it is reachable from the hot path: the instance that
+    `QmcIsingGraph::into_qmc` (qmc_ising.rs:943-976) builds -- diagonal two-site interactions [-J, J, J, -J] with
+    their offset and a constant single-site interaction [G, G, G, G] per variable.  Its `timestep` (qmc_runner.rs:
+    363-377: diagonal update, cluster update when the interactions keep the Ising symmetry, free bits) draws the
+    stream exactly as QmcIsingGraph::timestep does, which is what tests/convert_test.rs asserts; the energy offset
+    only carries the bond terms (qmc_runner.rs:124-133), so energies are shifted by -N * G.  General interactions
+    (`make_interaction` with other matrices, loop updates) are not on this path: QMCB_ERR_UNSUPPORTED."""
+
+    def __init__(self, graph):
+        self._g = graph
+        self.do_loop_updates = False
+
+    def get_bonds(self):
+        bonds = [(list(e), [-j, j, j, -j], "diagonal") for e, j in self._g.get_edges()]
+        t = self._g.transverse
+        return bonds + [([v], [t, t, t, t], "constant") for v in range(self._g.nvars)]
+
+    def make_interaction(self, mat, variables):
+        raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "general Qmc interactions are not on the GPU hot path (SURVEY 8(f) N3)")
+
+    make_interaction_and_offset = make_diagonal_interaction = make_diagonal_interaction_and_offset = make_interaction
+
+    def set_do_loop_updates(self, flag):
+        if flag:
+            raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "directed-loop updates are not on the GPU hot path")
+
+    def should_do_cluster_update(self):
+        return True  # constant single-site interactions exist and nothing breaks the Ising symmetry
+
+    def get_offset(self):
+        return float(sum(abs(j) for _, j in self._g.get_edges()))  # qmc_runner.rs:124-133: bond offsets only
+
+    def timestep(self, beta):
+        return self._g.timestep(beta)
+
+    def timesteps(self, t, beta):
+        shift = self._g.get_offset() - self.get_offset()
+        return self._g.timesteps(t, beta) - shift
+
+    def timesteps_sample(self, t, beta, sampling_freq=None):
+        samples, e = self._g.timesteps_sample(t, beta, sampling_freq)
+        return samples, e - (self._g.get_offset() - self.get_offset())
+
+    def state_ref(self):
+        return self._g.state_ref()
+
+    def get_n(self):
+        return self._g.get_n()
+
+    def get_cutoff(self):
+        return self._g.get_cutoff()
+
+    def get_manager_ref(self):
+        return self._g
+
+    def verify(self):
+        return self._g.verify()
+
+
+def _into_qmc(self):
+    """QmcIsingGraph::into_qmc (qmc_ising.rs:943-976).  The reference builds the longitudinal interactions with a
+    negative matrix entry, which Interaction::new rejects (qmc_runner.rs:524-526), so it only succeeds for h = 0."""
+    if abs(self.longitudinal) > np.finfo(np.float64).eps:
+        raise _lib.QmcbError(_lib.ERR_BAD_ARG, "Interaction contains negative weights")  # the reference's unwrap() panics here
+    return Qmc(self)
+
+
+def _clone(self, device=0):
+    """QmcIsingGraph::clone (qmc_ising.rs:909-933): an independent batch in the same state, stream positions included"""
+    return QmcIsingGraph.from_checkpoint(self.save_checkpoint(), device=device)
+
+
+QmcIsingGraph.into_qmc = _into_qmc
+QmcIsingGraph.clone = _clone
 DefaultQmcIsingGraph = QmcIsingGraph

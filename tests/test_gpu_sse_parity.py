@@ -248,3 +248,26 @@ def test_stepper_iteration_helpers():
     for r, ref in enumerate(refs):
         s, e_ref = ref.timesteps_sample(6, 1.0, 2, MODE_FAST)
         assert e2[r] == e_ref and all(np.array_equal(seen[k][r], s[k]) for k in range(3))
+
+
+def test_convert_and_run():
+    """tests/convert_test.rs:9-31: `ising.clone().into_qmc()` and `ising` stepped 10 times from the same rng agree."""
+    from isingmontecarlo_b200 import QmcbError
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.one_d_periodic(3, 1.0)
+    ising = QmcIsingGraph.new_with_rng(edges, 1.0, 0.0, 3, [1234, 1235], state=[1, 1, 1], betas=1.0, mode=MODE_STRICT)
+    qmc = ising.clone().into_qmc()
+    for _ in range(10):
+        ising.timestep(1.0)
+        qmc.timestep(1.0)
+    assert np.array_equal(ising.state_ref(), qmc.state_ref())
+    assert np.array_equal(ising.get_n(), qmc.get_n()) and qmc.verify()
+    # the Qmc energy offset carries the bond terms only (qmc_runner.rs:124-133)
+    e_i, e_q = ising.timesteps(50, 1.0), qmc.timesteps(50, 1.0)
+    assert np.allclose(e_i - e_q, 3 * 1.0) and qmc.get_offset() == 3.0
+    assert len(qmc.get_bonds()) == 6 and qmc.should_do_cluster_update()
+    with pytest.raises(QmcbError):
+        qmc.make_interaction([1.0, 0.5, 0.5, 1.0], [0])
+    with pytest.raises(QmcbError, match="negative weights"):
+        QmcIsingGraph.new_with_rng(edges, 1.0, 0.5, 3, [1], betas=1.0).into_qmc()
