@@ -174,13 +174,17 @@ class QmcIsingGraph:
         check(self._L.qmcb_timesteps(self._h, int(t), 1, ptr(e, C.c_double), None))
         return e
 
-    def timesteps_sample(self, t, beta=None, sampling_freq=None):
-        """qmc_stepper.rs:23-40: returns (samples[R][t // freq][N], energies[R])."""
+    def timesteps_sample(self, t, beta=None, sampling_freq=None, out_samples=None, out_energies=None):
+        """qmc_stepper.rs:23-40: returns (samples[R][t // freq][N], energies[R]).  out_samples / out_energies: optional
+        caller-owned buffers of exactly those shapes (e.g. pinned host memory) that the results are written into."""
         self._set_beta(beta)
         freq = 1 if sampling_freq is None else int(sampling_freq)
         k = int(t) // freq
-        e = np.zeros(self.R, dtype=np.float64)
-        s = np.zeros((self.R, max(k, 1), self.nvars), dtype=np.uint8)
+        e = np.zeros(self.R, dtype=np.float64) if out_energies is None else out_energies
+        s = np.zeros((self.R, max(k, 1), self.nvars), dtype=np.uint8) if out_samples is None else out_samples
+        if e.shape != (self.R,) or e.dtype != np.float64 or s.shape != (self.R, max(k, 1), self.nvars) or s.dtype != np.uint8 \
+                or not (e.flags.c_contiguous and s.flags.c_contiguous):
+            raise ValueError("output buffers must be C-contiguous float64[R] and uint8[R][t // freq][N]")
         check(self._L.qmcb_timesteps(self._h, int(t), freq, ptr(e, C.c_double), ptr(s, C.c_uint8)))
         return s[:, :k], e
 
