@@ -27,7 +27,8 @@ typedef enum {
     QMCB_ERR_CAPACITY = -2, /* operator string would outgrow `capacity` (see qmcb_create) */
     QMCB_ERR_CUDA = -3,
     QMCB_ERR_UNSUPPORTED = -4,
-    QMCB_ERR_INTERNAL = -5 /* a device-side invariant failed (reference: unreachable!/panic) */
+    QMCB_ERR_INTERNAL = -5, /* a device-side invariant failed (reference: unreachable!/panic) */
+    QMCB_ERR_NCCL = -6      /* libnccl missing or a collective failed (multi-GPU tempering only) */
 } QmcbStatus;
 
 /* Cluster-update order (DESIGN.md "Two orders").
@@ -90,8 +91,8 @@ int qmcb_num_hamiltonians(const QmcbHandle *h, uint32_t *n_ham);
 int qmcb_get_hamiltonian_index(QmcbHandle *h, uint32_t *ham_of_replica /* [R] */);
 int qmcb_get_offsets(QmcbHandle *h, double *offsets /* [R]: get_offset of each replica's Hamiltonian */);
 /* tuning knobs.  Per handle: "impl" 0 = warp-parallel kernels where available (default), 1 = serial-order kernels only;
- * "auto_capacity" 1 = grow the strings on demand even if a capacity was given; "debug_counters".  Process-wide
- * (kernel selection, for measurements and tests): "minblocks" 0 = choose the register budget from the batch shape
+ * "auto_capacity" 1 = grow the strings on demand even if a capacity was given; "debug_counters".  Kernel selection
+ * (also per handle; for measurements and tests): "minblocks" 0 = choose the register budget from the batch shape
  * (default), 4/6/7/8 = force that build; "shared_edge_table" 0/1; "pipeline" 0/1 (two warps per replica when few
  * replicas are resident); "smem_pad", "smem_carveout" (experiments). */
 int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value);
@@ -195,6 +196,29 @@ int qmcb_pt_apply(QmcbHandle *h, const uint64_t *all_rec_dev, uint64_t n_records
 /* tempering_step (tempering_container.rs:121-149) when the whole container lives on this handle (slot_begin = 0 and
  * R = n_chains * n_betas): steps 1 and 2 back to back on the device */
 int qmcb_pt_step_local(QmcbHandle *h);
+/* ---- the same step with the exchange inside the library (qmcb_pt_create(..., ncclComm_t) / qmcb_pt_step /
+ * qmcb_pt_timesteps_sample).  NCCL is bound at run time (dlopen of libnccl.so.2, or $QMCB_NCCL_LIB); without it these
+ * return QMCB_ERR_NCCL and the single-handle paths are unaffected.
+ * qmcb_pt_comm_unique_id: ncclGetUniqueId -- rank 0 calls it and hands the 128 bytes to the other ranks by any means
+ * (MPI, files, torch.distributed broadcast).  qmcb_pt_comm_init: ncclCommInitRank on this handle's device, collective
+ * over the ranks; the handle owns the communicator.  qmcb_pt_comm_attach: use the caller's ncclComm_t instead. */
+int qmcb_pt_comm_unique_id(uint8_t *id128 /* [128] */);
+int qmcb_pt_comm_init(QmcbHandle *h, const uint8_t *id128, int nranks, int rank);
+int qmcb_pt_comm_attach(QmcbHandle *h, void *nccl_comm /* ncclComm_t or NULL to detach */, int nranks, int rank);
+/* TemperingContainer::tempering_step / parallel_tempering_step (tempering_container.rs:121-149, :373-402) wherever the
+ * ladder lives: on this handle alone, or block-partitioned over the ranks of the attached communicator -- then export,
+ * ONE ncclAllGather of the records (32 or 64 B per slot) and apply are enqueued on the handle's stream with no host
+ * synchronisation in between. */
+int qmcb_pt_step(QmcbHandle *h);
+/* bytes the all-gather of one qmcb_pt_step moves per rank (0 when the ladder is local) */
+int qmcb_pt_collective_bytes(const QmcbHandle *h, uint64_t *bytes_per_step);
+/* TemperingContainer::timesteps_sample / parallel_timesteps_sample (tempering_container.rs:166-208, :411-453).
+ * energy_acc [n_chains*n_betas], by global SLOT: sum over the segments of (mean energy of the segment x its length), the
+ * reference's energy_acc (identical on every rank).  samples_out (or NULL): [R][timesteps / sampling_freq][N] bytes by
+ * LOCAL configuration; sample_slots_out (or NULL) [R][timesteps / sampling_freq]: the slot each of those samples
+ * belongs to (the reference files samples under the graph = slot). */
+int qmcb_pt_timesteps_sample(QmcbHandle *h, uint64_t timesteps, uint64_t replica_swap_freq, uint64_t sampling_freq,
+                             double *energy_acc, uint8_t *samples_out, uint32_t *sample_slots_out);
 int qmcb_pt_total_swaps(QmcbHandle *h, uint64_t *swaps); /* get_total_swaps :231-233 */
 int qmcb_pt_get_config(const QmcbHandle *h, uint32_t *n_chains, uint32_t *n_betas, uint32_t *slot_begin);
 int qmcb_pt_get_slots(QmcbHandle *h, uint32_t *slots /* [R] current slot of each configuration */);

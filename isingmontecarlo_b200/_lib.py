@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("QMCB_LIB") or os.path.join(_HERE, "_build", "libqmcb.so")  # QMCB_LIB: kernel experiments only
 
-OK, ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_UNSUPPORTED, ERR_INTERNAL = 0, -1, -2, -3, -4, -5
+OK, ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_UNSUPPORTED, ERR_INTERNAL, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 MODE_STRICT, MODE_FAST = 0, 1
 OP_EMPTY = 0xFFFFFFFF
 
@@ -83,6 +83,12 @@ SIGNATURES = {
     "qmcb_pt_export": [vp, vp],
     "qmcb_pt_apply": [vp, vp, C.c_uint64],
     "qmcb_pt_step_local": [vp],
+    "qmcb_pt_comm_unique_id": [u8p],
+    "qmcb_pt_comm_init": [vp, u8p, C.c_int, C.c_int],
+    "qmcb_pt_comm_attach": [vp, vp, C.c_int, C.c_int],
+    "qmcb_pt_step": [vp],
+    "qmcb_pt_collective_bytes": [vp, u64p],
+    "qmcb_pt_timesteps_sample": [vp, C.c_uint64, C.c_uint64, C.c_uint64, f64p, u8p, u32p],
     "qmcb_pt_total_swaps": [vp, u64p],
     "qmcb_pt_get_config": [vp, u32p, u32p, u32p],
     "qmcb_pt_get_slots": [vp, u32p],

@@ -5,7 +5,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,7 +27,7 @@ void launch_sse_itime_state(const SseDev &D, uint32_t r, uint64_t p_at, uint32_t
 void launch_autocorrelation(const uint8_t *samples, uint32_t R, uint32_t N, uint32_t T, uint32_t *bits, uint32_t *ones, double *out,
                             cudaStream_t st);
 void launch_sse_init_state(const SseDev &D, cudaStream_t st);
-int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
+int launch_sse_fast(const SseDev &D, const SseTuning &T, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
 int launch_pt_export(const SseDev &D, const PtDev &P, uint64_t *rec, cudaStream_t st);
 void launch_pt_apply(const SseDev &D, const PtDev &P, const uint64_t *rec, uint32_t S, cudaStream_t st);
@@ -107,8 +109,17 @@ struct QmcbHandle {
     std::vector<double> Jtab_h, gam_h, hl_h, offset_h;  // [H][E], [H], [H], [H]
     std::vector<uint32_t> ham_slot_h;                   // [S] tempering: Hamiltonian row of each slot
     uint64_t *pt_rec_dev = nullptr;                     // record buffer of qmcb_pt_step_local
+    // multi-GPU tempering: NCCL communicator (qmcb_pt_comm_init / qmcb_pt_comm_attach)
+    void *comm = nullptr;
+    bool own_comm = false;
+    int comm_rank = 0, comm_nranks = 1;
+    uint64_t *pt_rec_all_dev = nullptr;  // [S] gathered records
+    double *pt_energy_dev = nullptr;     // [S] per-segment energies of qmcb_pt_timesteps_sample
+    // kernel-selection knobs of the warp-parallel sweep (qmcb_set_option), per handle
+    SseTuning tune{};
 };
 
+static void pt_comm_release(QmcbHandle *h);
 #define CHECK_H(h)                                              \
     if (!(h)) return fail(QMCB_ERR_BAD_ARG, "null handle");     \
     CUDA_TRY(cudaSetDevice((h)->device))
@@ -138,33 +149,32 @@ static int grow(QmcbHandle *h, uint64_t newcap) {
     newcap = (newcap + 31) / 32 * 32;  // rows stay 128-byte aligned (the sweep kernels copy whole lines)
     if (newcap <= D.cap) return QMCB_OK;
     if (newcap >= (1ull << 29)) return fail(QMCB_ERR_CAPACITY, "operator string capacity above 2^29 slots per replica");
-    uint32_t *nops = nullptr;
+    // every new buffer is allocated before the old layout is touched: a failed growth (it typically happens near the
+    // end of device memory) leaves the handle exactly as it was
+    const bool s = h->strict_ws, f = h->fast_ws;
+    SseDev Dn = D;
+    Dn.cap = newcap;
+    uint32_t *nops = nullptr, *nbits = nullptr, *nfrozen = nullptr, *nrec = nullptr, *nfrontier = nullptr, *ninterior = nullptr, *nparent = nullptr;
     cudaError_t e = h->pool.alloc(&nops, (size_t)D.R * newcap);
+    if (e == cudaSuccess) e = h->pool.alloc(&nbits, (size_t)D.R * bits_stride(Dn));
+    if (e == cudaSuccess) e = h->pool.alloc(&nfrozen, (size_t)D.R * bits_stride(Dn));
+    if (e == cudaSuccess && s) e = h->pool.alloc(&nrec, (size_t)D.R * newcap * 8);
+    if (e == cudaSuccess && s) e = h->pool.alloc(&nfrontier, (size_t)D.R * (2 * newcap + 16));
+    if (e == cudaSuccess && s) e = h->pool.alloc(&ninterior, (size_t)D.R * (4 * newcap + 16));
+    if (e == cudaSuccess && f) e = h->pool.alloc(&nparent, (size_t)D.R * (D.N + newcap + 1));
+    if (e == cudaSuccess) e = cudaMemsetAsync(nops, 0xFF, (size_t)D.R * newcap * 4, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(nops, newcap * 4, D.ops, D.cap * 4, D.cap * 4, D.R, cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
+        h->pool.release(nops), h->pool.release(nbits), h->pool.release(nfrozen), h->pool.release(nrec);
+        h->pool.release(nfrontier), h->pool.release(ninterior), h->pool.release(nparent);
         return fail(QMCB_ERR_CAPACITY, "out of device memory while growing the operator strings");
     }
-    CUDA_TRY(cudaMemsetAsync(nops, 0xFF, (size_t)D.R * newcap * 4, h->stream));
-    CUDA_TRY(cudaMemcpy2DAsync(nops, newcap * 4, D.ops, D.cap * 4, D.cap * 4, D.R, cudaMemcpyDeviceToDevice, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    h->pool.release(D.ops);
-    D.ops = nops;
-    const bool s = h->strict_ws, f = h->fast_ws;
-    h->pool.release(D.rec), h->pool.release(D.frontier), h->pool.release(D.interior);
+    h->pool.release(D.ops), h->pool.release(D.rec), h->pool.release(D.frontier), h->pool.release(D.interior);
     h->pool.release(D.parent), h->pool.release(D.bits), h->pool.release(D.frozen);
-    D.rec = D.frontier = D.interior = D.parent = D.bits = D.frozen = nullptr;
-    h->strict_ws = h->fast_ws = false;
+    D.ops = nops, D.bits = nbits, D.frozen = nfrozen, D.rec = nrec, D.frontier = nfrontier, D.interior = ninterior, D.parent = nparent;
     D.cap = newcap;
-    CUDA_TRY(h->pool.alloc(&D.bits, (size_t)D.R * bits_stride(D)));
-    CUDA_TRY(h->pool.alloc(&D.frozen, (size_t)D.R * bits_stride(D)));
-    if (s) {
-        int rc = alloc_strict_ws(h);
-        if (rc) return rc;
-    }
-    if (f) {
-        int rc = alloc_fast_ws(h);
-        if (rc) return rc;
-    }
     return QMCB_OK;
 }
 
@@ -194,7 +204,7 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
             if ((rc = alloc_fast_ws(h))) return rc;
             bool ok = true;
             for (uint64_t tgt = origin + 1; tgt <= h->target && ok; tgt++) {
-                int nl = launch_sse_fast(h->D, tgt, 1u | 16u, freq, origin, nullptr, 0, h->stream);
+                int nl = launch_sse_fast(h->D, h->tune, tgt, 1u | 16u, freq, origin, nullptr, 0, h->stream);
                 if (nl < 0) { ok = false; break; }
                 launch_sse_serial(h->D, 0, tgt, 2u | 4u | 8u | 16u, freq, origin, samples_dev, spr, h->stream);
                 h->launches += (uint64_t)nl + 1;
@@ -208,7 +218,7 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
         h->launches += 1;
     } else {
         if ((rc = alloc_fast_ws(h))) return rc;
-        int nl = h->impl == 1 ? -1 : launch_sse_fast(h->D, h->target, phases, freq, origin, samples_dev, spr, h->stream);
+        int nl = h->impl == 1 ? -1 : launch_sse_fast(h->D, h->tune, h->target, phases, freq, origin, samples_dev, spr, h->stream);
         if (nl < 0) {
             launch_sse_serial(h->D, 1, h->target, phases, freq, origin, samples_dev, spr, h->stream);
             nl = 1;
@@ -241,6 +251,7 @@ static int run_to_target(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
 extern "C" int qmcb_create(const QmcbLattice *lat, uint32_t R, const double *betas, const uint64_t *keys, uint64_t cutoff0,
                            uint64_t capacity, const uint8_t *init_state, int device, QmcbHandle **out) {
     if (!lat || !betas || !keys || !out || R == 0) return fail(QMCB_ERR_BAD_ARG, "null argument or zero replicas");
+    if (R > 65535) return fail(QMCB_ERR_UNSUPPORTED, "at most 65535 replicas per handle (the per-replica kernels index them with gridDim.y)");
     if (lat->nvars == 0) return fail(QMCB_ERR_BAD_ARG, "lattice without variables");
     if (lat->nedges && (!lat->va || !lat->vb || !lat->J)) return fail(QMCB_ERR_BAD_ARG, "edge arrays missing");
     if (!(lat->transverse >= 0.0)) return fail(QMCB_ERR_BAD_ARG, "transverse field must be >= 0");
@@ -254,6 +265,7 @@ extern "C" int qmcb_create(const QmcbLattice *lat, uint32_t R, const double *bet
     CUDA_TRY(cudaSetDevice(device));
     QmcbHandle *h = new QmcbHandle();
     h->device = device;
+    cudaDeviceGetAttribute(&h->tune.nsm, cudaDevAttrMultiProcessorCount, device);
     SseDev &D = h->D;
     D.N = lat->nvars, D.E = lat->nedges, D.Nw = (lat->nvars + 31) / 32;
     D.has_h = std::fabs(lat->longitudinal) > DBL_EPSILON;
@@ -376,6 +388,7 @@ extern "C" int qmcb_destroy(QmcbHandle *h) {
     if (!h) return QMCB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    pt_comm_release(h);
     h->pool.release_all();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -535,24 +548,25 @@ extern "C" int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value) {
         h->impl = (int)value;
         return QMCB_OK;
     }
-    if (!strcmp(name, "smem_pad") || !strcmp(name, "smem_carveout")) {
-        extern int g_sse_fast_pad, g_sse_fast_carveout;
-        (name[5] == 'p' ? g_sse_fast_pad : g_sse_fast_carveout) = (int)value;
+    if (!strcmp(name, "smem_pad")) {
+        h->tune.pad = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 227 * 1024);
+        return QMCB_OK;
+    }
+    if (!strcmp(name, "smem_carveout")) {
+        h->tune.carveout = (int)value;
         return QMCB_OK;
     }
     if (!strcmp(name, "pipeline")) {
-        extern int g_sse_fast_pipe;
-        g_sse_fast_pipe = (int)value;
+        h->tune.pipe = (int)value;
         return QMCB_OK;
     }
     if (!strcmp(name, "shared_edge_table")) {
-        extern int g_sse_fast_epk;
-        g_sse_fast_epk = (int)value;
+        h->tune.epk = (int)value;
         return QMCB_OK;
     }
     if (!strcmp(name, "minblocks")) {
-        extern int g_sse_fast_minblocks;
-        g_sse_fast_minblocks = (int)value;
+        if (value != 0 && value != 4 && value != 6 && value != 7 && value != 8) return fail(QMCB_ERR_BAD_ARG, "minblocks must be 0, 4, 6, 7 or 8");
+        h->tune.minblocks = (int)value;
         return QMCB_OK;
     }
     if (!strcmp(name, "debug_counters")) {
@@ -824,8 +838,20 @@ extern "C" int qmcb_set_cutoff(QmcbHandle *h, uint32_t r, uint64_t cutoff) {
         int rc = grow(h, cutoff + cutoff / 2);
         if (rc) return rc;
     }
-    // QmcIsingGraph::set_cutoff (qmc_ising.rs:537-540) sets the cutoff unconditionally; ops above a
-    // smaller cutoff would be orphaned exactly as in the reference, so refuse to shrink below n's reach.
+    // QmcIsingGraph::set_cutoff (qmc_ising.rs:537-540) sets the cutoff unconditionally and the reference then panics
+    // on the usize underflow of M - n.  Here shrinking below the last occupied slot is refused: the diagonal update
+    // would compute M - n on wrapped integers and ops above the cutoff would be orphaned.
+    {
+        uint32_t Mold = 0;
+        CUDA_TRY(cudaMemcpy(&Mold, h->D.M + r, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (cutoff < Mold) {
+            const uint64_t lim = std::min<uint64_t>(Mold, h->D.cap);
+            std::vector<uint32_t> tail(lim - cutoff);
+            CUDA_TRY(cudaMemcpy(tail.data(), h->D.ops + (size_t)r * h->D.cap + cutoff, 4 * (lim - cutoff), cudaMemcpyDeviceToHost));
+            for (uint32_t w : tail)
+                if (w != QMCB_OP_EMPTY) return fail(QMCB_ERR_BAD_ARG, "cutoff below the last occupied slot of the operator string");
+        }
+    }
     uint32_t c = (uint32_t)cutoff;
     CUDA_TRY(cudaMemcpy(h->D.M + r, &c, sizeof(uint32_t), cudaMemcpyHostToDevice));
     return QMCB_OK;
@@ -932,15 +958,20 @@ extern "C" int qmcb_dump_ops(QmcbHandle *h, uint32_t r, uint32_t *words, uint64_
     for (uint64_t p = have; p < nwords; p++) words[p] = QMCB_OP_EMPTY;
     return QMCB_OK;
 }
+// a well-formed non-identity operator word: bond index in range, no stray bits, no second-leg bits on a one-variable op
+static bool op_word_ok(const SseDev &D, uint32_t w) {
+    const uint32_t b = w & 0xFFFFFFu;
+    if ((w >> 28) || b >= D.Nb) return false;
+    if (b >= D.E && (((w >> 25) & 1u) || ((w >> 27) & 1u))) return false;
+    return true;
+}
 extern "C" int qmcb_load_ops(QmcbHandle *h, uint32_t r, const uint32_t *words, uint64_t nwords, const uint8_t *state) {
     CHECK_H(h);
     SseDev &D = h->D;
     if (!words || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
     for (uint64_t p = 0; p < nwords; p++) {
         if (words[p] == QMCB_OP_EMPTY) continue;
-        uint32_t b = words[p] & 0xFFFFFFu;
-        if ((words[p] >> 28) || b >= D.E + D.N + (D.has_h ? D.N : 0)) return fail(QMCB_ERR_BAD_ARG, "malformed operator word");
-        if (b >= D.E && ((words[p] >> 25) & 1u || (words[p] >> 27) & 1u)) return fail(QMCB_ERR_BAD_ARG, "one-variable op with second-leg bits");
+        if (!op_word_ok(D, words[p])) return fail(QMCB_ERR_BAD_ARG, "malformed operator word (bond out of range, stray bits, or second-leg bits on a one-variable op)");
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (nwords > D.cap) {
@@ -1102,6 +1133,178 @@ extern "C" int qmcb_pt_step_local(QmcbHandle *h) {
     if (!h->pt_rec_dev) CUDA_TRY(h->pool.alloc(&h->pt_rec_dev, (size_t)h->pt_S * PT_REC_WORDS_MH));
     int rc = qmcb_pt_export(h, h->pt_rec_dev);
     return rc ? rc : qmcb_pt_apply(h, h->pt_rec_dev, h->pt_S);
+}
+// ---- multi-GPU tempering: the all-gather of tempering_step inside the library ----------------------------
+// NCCL is bound at run time (dlopen): libqmcb.so has no link-time dependency on it, and inside a process that
+// already carries an NCCL (torch) the same copy is used.  Only the five entry points below are needed.
+namespace {
+struct NcclUid { char internal[128]; };  // ncclUniqueId
+typedef int (*nccl_get_uid_t)(NcclUid *);
+typedef int (*nccl_init_rank_t)(void **, int, NcclUid, int);
+typedef int (*nccl_allgather_t)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*nccl_allreduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_destroy_t)(void *);
+typedef const char *(*nccl_errstr_t)(int);
+struct NcclApi {
+    void *lib = nullptr;
+    nccl_get_uid_t get_uid = nullptr;
+    nccl_init_rank_t init_rank = nullptr;
+    nccl_allgather_t allgather = nullptr;
+    nccl_allreduce_t allreduce = nullptr;
+    nccl_destroy_t destroy = nullptr;
+    nccl_errstr_t errstr = nullptr;
+};
+const int NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("QMCB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm || !*nm) continue;
+            void *l = dlopen(nm, RTLD_NOW | RTLD_NOLOAD);  // the copy the process already has (torch's), if any
+            if (!l) l = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (l) { api.lib = l; break; }
+        }
+        if (!api.lib) return;
+        api.get_uid = (nccl_get_uid_t)dlsym(api.lib, "ncclGetUniqueId");
+        api.init_rank = (nccl_init_rank_t)dlsym(api.lib, "ncclCommInitRank");
+        api.allgather = (nccl_allgather_t)dlsym(api.lib, "ncclAllGather");
+        api.allreduce = (nccl_allreduce_t)dlsym(api.lib, "ncclAllReduce");
+        api.destroy = (nccl_destroy_t)dlsym(api.lib, "ncclCommDestroy");
+        api.errstr = (nccl_errstr_t)dlsym(api.lib, "ncclGetErrorString");
+        if (!api.get_uid || !api.init_rank || !api.allgather || !api.allreduce || !api.destroy) api.lib = nullptr;
+    });
+    return api.lib ? &api : nullptr;
+}
+int fail_nccl(NcclApi *A, int rc, const char *what) {
+    return fail(QMCB_ERR_NCCL, std::string("NCCL error in ") + what + ": " + (A && A->errstr ? A->errstr(rc) : "?"));
+}
+}  // namespace
+
+static void pt_comm_release(QmcbHandle *h) {
+    if (h->comm && h->own_comm && nccl_api()) nccl_api()->destroy(h->comm);
+    h->comm = nullptr, h->own_comm = false;
+}
+extern "C" int qmcb_pt_comm_unique_id(uint8_t *id128) {
+    if (!id128) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    NcclApi *A = nccl_api();
+    if (!A) return fail(QMCB_ERR_NCCL, "libnccl.so.2 not found (set QMCB_NCCL_LIB)");
+    NcclUid u;
+    int rc = A->get_uid(&u);
+    if (rc) return fail_nccl(A, rc, "ncclGetUniqueId");
+    memcpy(id128, u.internal, 128);
+    return QMCB_OK;
+}
+extern "C" int qmcb_pt_comm_init(QmcbHandle *h, const uint8_t *id128, int nranks, int rank) {
+    CHECK_H(h);
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(QMCB_ERR_BAD_ARG, "bad communicator shape");
+    if (h->comm) return fail(QMCB_ERR_BAD_ARG, "a communicator is already attached");
+    NcclApi *A = nccl_api();
+    if (!A) return fail(QMCB_ERR_NCCL, "libnccl.so.2 not found (set QMCB_NCCL_LIB)");
+    NcclUid u;
+    memcpy(u.internal, id128, 128);
+    void *comm = nullptr;
+    int rc = A->init_rank(&comm, nranks, u, rank);
+    if (rc) return fail_nccl(A, rc, "ncclCommInitRank");
+    h->comm = comm, h->own_comm = true, h->comm_rank = rank, h->comm_nranks = nranks;
+    return QMCB_OK;
+}
+extern "C" int qmcb_pt_comm_attach(QmcbHandle *h, void *nccl_comm, int nranks, int rank) {
+    CHECK_H(h);
+    if (h->comm && h->own_comm) return fail(QMCB_ERR_BAD_ARG, "the handle owns a communicator already");
+    if (nccl_comm && !nccl_api()) return fail(QMCB_ERR_NCCL, "libnccl.so.2 not found (set QMCB_NCCL_LIB)");
+    h->comm = nccl_comm, h->own_comm = false, h->comm_rank = rank, h->comm_nranks = nccl_comm ? nranks : 1;
+    return QMCB_OK;
+}
+// tempering_step / parallel_tempering_step (tempering_container.rs:121-149, :373-402) wherever the ladder lives: on this
+// handle alone (export + apply), or spread over the ranks of the attached communicator (export, ONE ncclAllGather of
+// the per-configuration records, apply).  Everything is enqueued on the handle's stream; nothing synchronises the host.
+extern "C" int qmcb_pt_step(QmcbHandle *h) {
+    CHECK_H(h);
+    if (!h->pt_on) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+    if (h->P.cfg_begin == 0 && h->D.R == h->pt_S) return qmcb_pt_step_local(h);
+    if (!h->comm) return fail(QMCB_ERR_BAD_ARG, "the ladder is spread over several handles: attach a communicator (qmcb_pt_comm_init) or use qmcb_pt_export + all-gather + qmcb_pt_apply");
+    if ((uint64_t)h->D.R * (uint64_t)h->comm_nranks != h->pt_S || h->P.cfg_begin != (uint32_t)h->comm_rank * h->D.R)
+        return fail(QMCB_ERR_BAD_ARG, "slots must be block-partitioned evenly over the ranks of the communicator");
+    NcclApi *A = nccl_api();
+    uint32_t words = 0;
+    qmcb_pt_record_words(h, &words);
+    if (!h->pt_rec_dev) CUDA_TRY(h->pool.alloc(&h->pt_rec_dev, (size_t)h->pt_S * PT_REC_WORDS_MH));
+    if (!h->pt_rec_all_dev) CUDA_TRY(h->pool.alloc(&h->pt_rec_all_dev, (size_t)h->pt_S * PT_REC_WORDS_MH));
+    int rc = qmcb_pt_export(h, h->pt_rec_dev);
+    if (rc) return rc;
+    int nrc = A->allgather(h->pt_rec_dev, h->pt_rec_all_dev, (size_t)h->D.R * words, NCCL_UINT64, h->comm, h->stream);
+    if (nrc) return fail_nccl(A, nrc, "ncclAllGather");
+    return qmcb_pt_apply(h, h->pt_rec_all_dev, h->pt_S);
+}
+extern "C" int qmcb_pt_collective_bytes(const QmcbHandle *h, uint64_t *bytes_per_step) {
+    if (!h || !bytes_per_step) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    if (!h->pt_on) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+    uint32_t words = 0;
+    qmcb_pt_record_words(h, &words);
+    *bytes_per_step = (h->P.cfg_begin == 0 && h->D.R == h->pt_S) ? 0 : (uint64_t)h->pt_S * words * 8;
+    return QMCB_OK;
+}
+
+static int timesteps_impl(QmcbHandle *h, uint64_t t, uint64_t freq, double *energy_out, uint8_t *samples_out, bool keep_device_samples);
+// TemperingContainer::timesteps_sample / parallel_timesteps_sample (tempering_container.rs:166-208, :411-453)
+extern "C" int qmcb_pt_timesteps_sample(QmcbHandle *h, uint64_t timesteps, uint64_t replica_swap_freq, uint64_t sampling_freq,
+                                        double *energy_acc, uint8_t *samples_out, uint32_t *sample_slots_out) {
+    CHECK_H(h);
+    if (!h->pt_on) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+    if (!energy_acc || replica_swap_freq == 0 || sampling_freq == 0) return fail(QMCB_ERR_BAD_ARG, "null energies or zero frequency");
+    const SseDev &D = h->D;
+    const uint32_t S = h->pt_S, R = D.R;
+    const uint64_t T = timesteps / sampling_freq;
+    const bool spread = !(h->P.cfg_begin == 0 && R == S);
+    if (spread && !h->comm) return fail(QMCB_ERR_BAD_ARG, "the ladder is spread over several handles: attach a communicator first");
+    NcclApi *A = spread ? nccl_api() : nullptr;
+    std::vector<double> e(R), eseg(S);
+    std::vector<uint32_t> slots(R);
+    std::fill(energy_acc, energy_acc + S, 0.0);
+    uint64_t remaining = timesteps, to_swap = replica_swap_freq, to_sample = sampling_freq, k = 0;
+    int rc;
+    while (remaining > 0) {
+        const uint64_t t = std::min(std::min(to_sample, to_swap), remaining);
+        if ((rc = qmcb_pt_get_slots(h, slots.data()))) return rc;
+        if ((rc = timesteps_impl(h, t, 1, e.data(), nullptr, false))) return rc;  // g.timesteps(t, beta): mean energy of the t sweeps
+        std::fill(eseg.begin(), eseg.end(), 0.0);
+        for (uint32_t r = 0; r < R; r++) eseg[slots[r]] = e[r];
+        if (spread) {  // every slot has exactly one owner: the sum is exact, and the accumulation below stays in slot order on every rank
+            if (!h->pt_energy_dev) CUDA_TRY(h->pool.alloc(&h->pt_energy_dev, (size_t)S));
+            CUDA_TRY(cudaMemcpyAsync(h->pt_energy_dev, eseg.data(), sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+            int nrc = A->allreduce(h->pt_energy_dev, h->pt_energy_dev, S, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+            if (nrc) return fail_nccl(A, nrc, "ncclAllReduce");
+            CUDA_TRY(cudaMemcpyAsync(eseg.data(), h->pt_energy_dev, sizeof(double) * S, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+        }
+        for (uint32_t s = 0; s < S; s++) energy_acc[s] += eseg[s] * (double)t;  // *e += te * t as f64
+        to_sample -= t, to_swap -= t, remaining -= t;
+        if (to_swap == 0) {
+            if ((rc = qmcb_pt_step(h))) return rc;
+            to_swap = replica_swap_freq;
+        }
+        if (to_sample == 0) {
+            if (k < T) {
+                if (sample_slots_out) {
+                    if ((rc = qmcb_pt_get_slots(h, slots.data()))) return rc;
+                    for (uint32_t r = 0; r < R; r++) sample_slots_out[(size_t)r * T + k] = slots[r];
+                }
+                if (samples_out) {
+                    std::vector<uint32_t> packed((size_t)R * D.Nw);
+                    CUDA_TRY(cudaStreamSynchronize(h->stream));
+                    CUDA_TRY(cudaMemcpy(packed.data(), D.state, packed.size() * 4, cudaMemcpyDeviceToHost));
+                    for (uint32_t r = 0; r < R; r++)
+                        for (uint32_t v = 0; v < D.N; v++)
+                            samples_out[((size_t)r * T + k) * D.N + v] = (packed[(size_t)r * D.Nw + (v >> 5)] >> (v & 31)) & 1u;
+                }
+                k++;
+            }
+            to_sample = sampling_freq;
+        }
+    }
+    return QMCB_OK;
 }
 extern "C" int qmcb_pt_total_swaps(QmcbHandle *h, uint64_t *swaps) {
     CHECK_H(h);
@@ -1350,7 +1553,7 @@ extern "C" int qmcb_checkpoint_load(const void *buf, uint64_t bytes, int device,
         uint32_t cnt = 0;
         for (uint32_t q = 0; q < M[r]; q++) {
             if (wr[q] == QMCB_OP_EMPTY) continue;
-            if ((wr[q] >> 28) || (wr[q] & 0xFFFFFFu) >= D.Nb) return bail(fail(QMCB_ERR_BAD_ARG, "malformed operator word in checkpoint"));
+            if (!op_word_ok(D, wr[q])) return bail(fail(QMCB_ERR_BAD_ARG, "malformed operator word in checkpoint"));
             cnt++;
         }
         if (cnt != n[r]) return bail(fail(QMCB_ERR_BAD_ARG, "operator count in checkpoint does not match its string"));
@@ -1368,6 +1571,17 @@ extern "C" int qmcb_checkpoint_load(const void *buf, uint64_t bytes, int device,
     if ((rc = qmcb_set_mode(h, (int)mode))) return bail(rc);
     if ((flags & 1u) && (rc = qmcb_set_enable_heatbath(h, 1))) return bail(rc);
     if (flags & 2u) {
+        // slot labels index the per-slot tables of the swap kernels: every one must be a slot of the ladder, no two alike
+        const uint64_t S = (uint64_t)n_chains * n_betas;
+        if ((uint64_t)cfg_begin + R > S) return bail(fail(QMCB_ERR_BAD_ARG, "checkpoint: configurations do not fit the ladder"));
+        std::vector<uint8_t> taken(S, 0);
+        for (uint32_t r = 0; r < R; r++) {
+            if (sl[r] >= S || taken[sl[r]]) return bail(fail(QMCB_ERR_BAD_ARG, "checkpoint: slot label out of range or duplicated"));
+            taken[sl[r]] = 1;
+        }
+        if (has_slot_tab)
+            for (uint32_t r = 0; r < R; r++)
+                if (hrep[r] >= H) return bail(fail(QMCB_ERR_BAD_ARG, "checkpoint: Hamiltonian index out of range"));
         if ((rc = qmcb_pt_configure(h, n_chains, n_betas, cfg_begin, bs.data(), ks.data(), pt_key))) return bail(rc);
         // pt_configure relabelled the replicas with the initial slots: restore the saved labels
         TRYL(cudaMemcpy(D.beta, beta.data(), 8ull * R, cudaMemcpyHostToDevice));
@@ -1418,6 +1632,7 @@ static uint64_t metropolis_threshold(double beta, double delta_e) {
 extern "C" int cmcb_create(const QmcbLattice *lat, const double *biases, uint32_t R, const double *betas, const uint64_t *keys,
                            const uint8_t *init_state, int device, CmcbHandle **out) {
     if (!lat || !biases || !betas || !keys || !out || R == 0 || lat->nvars == 0) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    if (R > 65535) return fail(QMCB_ERR_UNSUPPORTED, "at most 65535 replicas per handle (the per-replica kernels index them with gridDim.y)");
     const uint32_t N = lat->nvars, E = lat->nedges;
     for (uint32_t e = 0; e < E; e++)
         if (lat->va[e] >= N || lat->vb[e] >= N || lat->va[e] == lat->vb[e]) return fail(QMCB_ERR_BAD_ARG, "edge endpoint out of range or self-loop");

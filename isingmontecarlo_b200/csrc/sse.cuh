@@ -58,6 +58,17 @@ struct SseDev {
     const double *hb_total_tab;              // [H]
 };
 
+// kernel-selection knobs of the warp-parallel sweep, owned by the handle (qmcb_set_option); nsm is the SM count of the
+// handle's device, queried once at creation
+struct SseTuning {
+    int minblocks = 0;   // resident blocks per SM the kernel is compiled for (register cap); 0 = choose by occupancy
+    int pipe = 1;        // 0: never use two warps per replica
+    int epk = 1;         // 0: never use the packed edge table
+    int pad = 0;         // experiments: extra dynamic shared memory per block
+    int carveout = -1;   // experiments: shared-memory carve-out preference (-1 = driver default)
+    int nsm = 148;
+};
+
 // the Hamiltonian one replica is updated with
 struct Ham {
     const double *J;

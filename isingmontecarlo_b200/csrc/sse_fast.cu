@@ -16,6 +16,8 @@
 //  P3  apply the flips to the operator words (second streaming pass) and to the spins.
 // Contract of the FAST order: oracle.c cluster_update_fast / DESIGN.md.
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 #include "sse.cuh"
 
@@ -1027,13 +1029,8 @@ __global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2
     if (err) atomicOr(D.status, err);
 }
 
-int g_sse_fast_pad = 0, g_sse_fast_carveout = -1;  // experiments: extra dynamic shared memory per block, carve-out preference
-int g_sse_fast_pipe = 1;  // 0: never use two warps per replica
-int g_sse_fast_epk = 1;  // 0: never use the shared-memory edge table (A/B measurements)
-int g_sse_fast_minblocks = 0;  // resident blocks per SM the kernel is compiled for (register cap); 0 = choose by occupancy
-
 // returns the number of kernel launches, or -1 if this shape is not supported by the warp kernels
-int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
+int launch_sse_fast(const SseDev &D, const SseTuning &T, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
     // one warp per block: up to 32 blocks are resident per SM, each with its own shared memory
     size_t smem = warp_smem_bytes(D.N, D.Nw, false);
@@ -1044,10 +1041,9 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
     // register budget: the kernel is bound by the latency of each warp's dependent chain, so when shared memory or the
     // number of replicas keeps few blocks resident anyway, the 120-register build (no spills) is 10-20 % faster per
     // warp; with many replicas 72 registers keep 4096 of them (28 warps per SM) in one wave
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+    const int nsm = T.nsm > 0 ? T.nsm : 148;
     const size_t wanted = (blocks + nsm - 1) / nsm;
-    int minb = g_sse_fast_minblocks;
+    int minb = T.minblocks;
     if (minb <= 0) {
         const size_t resident = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + 1024), wanted);
         minb = resident <= 4 ? 4 : (resident <= 6 ? 6 : 7);
@@ -1055,16 +1051,16 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
     if (minb <= 4) smem = warp_smem_bytes(D.N, D.Nw, true);  // the low-occupancy layout carries the site-op bitmap
     // block-shared packed edge table: low-occupancy build only, and only if it does not cost a resident block
     size_t epk_bytes = 0;
-    if (minb == 4 && D.epk && !D.ham && g_sse_fast_epk) {
+    if (minb == 4 && D.epk && !D.ham && T.epk) {
         const size_t want = ((size_t)D.E * 4 + 15) / 16 * 16;
         const size_t without = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + 1024), wanted);
         const size_t with = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + want + 1024), wanted);
         if (with >= 1 && with >= std::min<size_t>(without, 4)) epk_bytes = want;
     }
     // with many resident warps the packed table is still used, through L1: 8 KB instead of 32 KB of tables at config #3
-    const bool pk_l1 = !epk_bytes && D.epk && !D.ham && g_sse_fast_epk && minb == 7;
+    const bool pk_l1 = !epk_bytes && D.epk && !D.ham && T.epk && minb == 7;
     // two warps per replica (PIPE) when at most two blocks of four replicas per SM are wanted and fit
-    const bool pipe = minb == 4 && g_sse_fast_pipe && wanted <= 2 && (size_t)(227 * 1024) / (smem * QMCB_WPB + epk_bytes + 1024) >= wanted;
+    const bool pipe = minb == 4 && T.pipe && wanted <= 2 && (size_t)(227 * 1024) / (smem * QMCB_WPB + epk_bytes + 1024) >= wanted;
     Kern kern;
 #define PICK(HB_, MH_)                                                                                                  \
     switch (minb) {                                                                                                     \
@@ -1087,9 +1083,22 @@ int launch_sse_fast(const SseDev &D, uint64_t target, uint32_t phases, uint64_t 
         if (D.hb_cum) { PICK(true, true) } else { PICK(false, true) }
     } else if (D.hb_cum) { PICK(true, false) } else { PICK(false, false) }
 #undef PICK
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (g_sse_fast_carveout >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g_sse_fast_carveout);
-    kern<<<blocks, (pipe ? 64 : 32) * QMCB_WPB, smem * QMCB_WPB + epk_bytes + g_sse_fast_pad, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem,
+    // function attributes are set once per kernel instance (and again only when the carve-out knob changes)
+    {
+        static std::mutex mu;
+        static std::map<std::pair<const void *, int>, int> done;  // (kernel, device) -> carve-out last set
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = done.find({(const void *)kern, dev});
+        if (it == done.end()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (T.carveout >= 0 && (it == done.end() || it->second != T.carveout))
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, T.carveout);
+        done[{(const void *)kern, dev}] = T.carveout;
+    }
+    size_t dyn = smem * QMCB_WPB + epk_bytes + (size_t)std::max(T.pad, 0);
+    if (dyn > 227 * 1024) dyn = 227 * 1024;  // the padding knob never pushes the block past the hardware limit
+    kern<<<blocks, (pipe ? 64 : 32) * QMCB_WPB, dyn, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem,
                                                                   epk_bytes ? (uint32_t)(smem * QMCB_WPB) : 0u);
     return 1;
 }

@@ -45,7 +45,7 @@ class TemperingContainer:
     the whole ladder at construction (all slots share one lattice, so can_swap_graphs holds)."""
 
     def __init__(self, edges, transverse, longitudinal, cutoff, betas, n_chains=1, rng_keys=None, pt_key=0x9E37,
-                 mode=MODE_FAST, device=None, group=None, capacity=0, slot_hamiltonians=None):
+                 mode=MODE_FAST, device=None, group=None, capacity=0, slot_hamiltonians=None, collective="library"):
         import torch
         import torch.distributed as dist
 
@@ -86,6 +86,36 @@ class TemperingContainer:
             self.graph.set_hamiltonians(J_tab, tr, lo, ham_of_slot[sl])
             check(L.qmcb_pt_set_slot_hamiltonians(self.graph._h, ptr(ham_of_slot, C.c_uint32)))
         self._alloc_records()
+        self._init_collective(collective)
+
+    def _init_collective(self, collective):
+        """collective="library": the all-gather runs inside libqmcb.so (ncclAllGather on the handle's stream, no host
+        synchronisation: qmcb_pt_step); the ncclUniqueId of rank 0 is broadcast over the torch.distributed group.
+        collective="torch": qmcb_pt_export + torch.distributed.all_gather_into_tensor + qmcb_pt_apply (the path a host
+        with its own communication layer uses; also what runs over gloo)."""
+        import torch.distributed as dist
+
+        self.collective = collective if self.world > 1 else "local"
+        if self.collective != "library":
+            return
+        if dist.get_backend(self.group) != "nccl":
+            self.collective = "torch"
+            return
+        L, torch = self.graph._L, self._torch
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{self.device}")
+        if self.rank == 0:
+            buf = np.zeros(128, dtype=np.uint8)
+            check(L.qmcb_pt_comm_unique_id(ptr(buf, C.c_uint8)))
+            uid.copy_(torch.from_numpy(buf))
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.broadcast(uid, src=src, group=self.group)
+        buf = np.ascontiguousarray(uid.cpu().numpy())
+        check(L.qmcb_pt_comm_init(self.graph._h, ptr(buf, C.c_uint8), self.world, self.rank))
+
+    def collective_bytes(self):
+        b = C.c_uint64()
+        check(self.graph._L.qmcb_pt_collective_bytes(self.graph._h, C.byref(b)))
+        return b.value
 
     def _alloc_records(self):
         w = C.c_uint32()
@@ -118,6 +148,7 @@ class TemperingContainer:
         tc.S = tc.n_chains * tc.n_betas
         tc.betas_global = tc.keys_global = None  # live in the handle
         tc._alloc_records()
+        tc._init_collective("library")
         return tc
 
     def num_graphs(self):
@@ -130,8 +161,8 @@ class TemperingContainer:
     def tempering_step(self):
         """tempering_container.rs:121-149 (parallel_tempering_step :373-402)"""
         L, g = self.graph._L, self.graph
-        if self.world == 1:  # the whole container lives on this handle: no host plumbing between the two halves
-            check(L.qmcb_pt_step_local(g._h))
+        if self.collective in ("local", "library"):  # export, (ncclAllGather,) apply on the handle's stream: no host plumbing
+            check(L.qmcb_pt_step(g._h))
             return
         check(L.qmcb_pt_export(g._h, C.c_void_p(self._rec.data_ptr())))
         check(L.qmcb_synchronize(g._h))
@@ -156,6 +187,18 @@ class TemperingContainer:
         """tempering_container.rs:166-208: returns (states, energy_acc) indexed by GLOBAL slot.
         states[slot] is a list of sampled configurations (filled for the slots whose configuration
         lives on this rank at sampling time); energy_acc is summed over ranks."""
+        if self.collective in ("local", "library"):  # the whole loop runs behind the C ABI
+            T = int(timesteps) // int(sampling_freq)
+            energy_acc = np.zeros(self.S, dtype=np.float64)
+            samples = np.zeros((self.R, T, self.graph.nvars), dtype=np.uint8)
+            sslots = np.zeros((self.R, T), dtype=np.uint32)
+            check(self.graph._L.qmcb_pt_timesteps_sample(self.graph._h, int(timesteps), int(replica_swap_freq), int(sampling_freq),
+                                                         ptr(energy_acc, C.c_double), ptr(samples, C.c_uint8), ptr(sslots, C.c_uint32)))
+            states = [[] for _ in range(self.S)]
+            for k in range(T):
+                for r in range(self.R):
+                    states[sslots[r, k]].append(samples[r, k].astype(bool))
+            return states, energy_acc
         states = [[] for _ in range(self.S)]
         energy_acc = np.zeros(self.S, dtype=np.float64)
         remaining, to_swap, to_sample = int(timesteps), int(replica_swap_freq), int(sampling_freq)
