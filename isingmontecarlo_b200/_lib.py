@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("QMCB_LIB") or os.path.join(_HERE, "_build", "libqmcb.so")  # QMCB_LIB: kernel experiments only
 
 OK, ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_UNSUPPORTED, ERR_INTERNAL, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
-MODE_STRICT, MODE_FAST = 0, 1
+MODE_STRICT, MODE_FAST, MODE_COUNTER = 0, 1, 2
 OP_EMPTY = 0xFFFFFFFF
 
 

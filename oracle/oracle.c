@@ -482,6 +482,75 @@ static void diagonal_update(OrcSse *g, double beta) {
 }
 
 /* ===================================================================================
+ * Diagonal update, COUNTER mode (builder-defined draw source): the rule of diagonal.rs:142-191 -- the
+ * same numerator / denominator arithmetic, the same live n -- but the uniform words of slot p do not come from the
+ * sequential stream: they are the two 64-bit halves of ONE Philox block per slot,
+ *     (x, y, z, w) = Philox4x32-10(ctr = (p, c_lo, c_hi, 'DIAG'), key),  wA = y << 32 | x,  wB = w << 32 | z,
+ * c = stream cursor at the start of the step (the step then advances the cursor by 1, like the FAST cluster step).
+ *   empty slot:   b = (wA * Nb) >> 64 (multiply-shift without rand's zone rejection: non-uniformity <= Nb * 2^-64);
+ *                 insert iff num > den, or num / den == 1.0, or wB < (num / den * 2^64) as u64
+ *   diagonal op:  remove iff den + 1 > num, or (den + 1) / num == 1.0, or wA < ((den + 1) / num * 2^64) as u64
+ *   off-diagonal: state[vars] = outputs (no draw)
+ * so that every slot can be decided independently once n before it is known.
+ * =================================================================================== */
+#define TAG_DIAG 0x44494147u
+
+static int bernoulli_word(OrcSse *g, uint64_t word, double p) { /* gen_bool(p) fed with a given word */
+    if (!(p >= 0.0 && p < 1.0)) {
+        if (p == 1.0) return 1;
+        g->rng.error = 2; /* the reference panics here */
+        return 0;
+    }
+    return word < orc_bool_threshold(p);
+}
+
+static void diagonal_update_counter(OrcSse *g, double beta) {
+    const uint64_t cutoff = g->cutoff;
+    const uint32_t nb = num_bonds(g);
+    ops_resize(g, cutoff);
+    uint8_t *state = g->state;
+    uint64_t n = g->n;
+    const uint64_t c0 = g->rng.cursor;
+    const uint32_t k[2] = {(uint32_t)g->rng.key, (uint32_t)(g->rng.key >> 32)};
+    for (uint64_t p = 0; p < cutoff; p++) {
+        Node *nd = &g->ops[p];
+        if (nd->present && !node_is_diagonal(nd)) {
+            for (int r = 0; r < nd->nv; r++) state[nd->vars[r]] = nd->out[r];
+            continue;
+        }
+        const uint32_t ctr[4] = {(uint32_t)p, (uint32_t)c0, (uint32_t)(c0 >> 32), TAG_DIAG};
+        uint32_t x[4];
+        orc_philox4x32_10(ctr, k, x);
+        const uint64_t wA = ((uint64_t)x[1] << 32) | x[0], wB = ((uint64_t)x[3] << 32) | x[2];
+        const uint32_t b = nd->present ? nd->bond : (uint32_t)(((unsigned __int128)wA * nb) >> 64);
+        uint32_t vars[2];
+        int nv, constant;
+        edge_fn(g, b, vars, &nv, &constant);
+        uint8_t sub[2] = {0, 0};
+        for (int r = 0; r < nv; r++) sub[r] = state[vars[r]];
+        const double numerator = beta * (double)nb * hamiltonian(g, b, sub, sub);
+        double denominator = (double)(cutoff - n);
+        if (!nd->present) {
+            if (numerator > denominator || bernoulli_word(g, wB, numerator / denominator)) {
+                nd->present = 1, nd->nv = (uint8_t)nv, nd->constant = (uint8_t)constant, nd->bond = b;
+                for (int r = 0; r < nv; r++)
+                    nd->vars[r] = vars[r], nd->in[r] = sub[r], nd->out[r] = sub[r];
+                n++;
+            }
+        } else {
+            denominator = denominator + 1.0;
+            if (denominator > numerator || bernoulli_word(g, wA, denominator / numerator)) {
+                nd->present = 0;
+                n--;
+            }
+        }
+    }
+    g->n = n;
+    g->rng.cursor = c0 + 1;
+    rebuild_links(g);
+}
+
+/* ===================================================================================
  * Heat-bath diagonal update: heatbath.rs:106-127 (driver), :149-209 (rule), BondWeights :10-61;
  * enabled by QmcIsingGraph::set_enable_heatbath (qmc_ising.rs:444-486)
  * =================================================================================== */
@@ -569,8 +638,11 @@ static void heatbath_diagonal_update(OrcSse *g, double beta) {
 }
 
 /* the diagonal step of timestep / single_diagonal_step: qmc_ising.rs:250-268, :685-703 */
-static void diagonal_step(OrcSse *g, double beta) {
-    if (g->hb_cum) heatbath_diagonal_update(g, beta);
+static void diagonal_step(OrcSse *g, double beta, int mode) {
+    if (mode == ORC_MODE_COUNTER) {
+        if (g->hb_cum) g->error |= 16; /* the heat-bath rule has no COUNTER-mode contract */
+        else diagonal_update_counter(g, beta);
+    } else if (g->hb_cum) heatbath_diagonal_update(g, beta);
     else diagonal_update(g, beta);
 }
 
@@ -823,7 +895,7 @@ static uint64_t cluster_update_fast(OrcSse *g, int has_weights) {
 /* single_cluster_step qmc_ising.rs:273-320 / timestep :754-784 */
 static uint64_t cluster_and_free_spins(OrcSse *g, int mode) {
     int has_weights = fabs(g->longitudinal) > DBL_EPSILON;
-    uint64_t ncl = mode == ORC_MODE_FAST ? cluster_update_fast(g, has_weights)
+    uint64_t ncl = mode != ORC_MODE_STRICT ? cluster_update_fast(g, has_weights)
                                          : cluster_update_strict(g, has_weights);
     for (uint32_t v = 0; v < g->nvars; v++) /* qmc_ising.rs:780-784 */
         if (g->vfirst_p[v] == NONE) g->state[v] = (uint8_t)gen_bool(&g->rng, 0.5);
@@ -832,15 +904,16 @@ static uint64_t cluster_and_free_spins(OrcSse *g, int mode) {
 
 /* QmcIsingGraph::timestep, qmc_ising.rs:644-795 (rvb off: default :122) */
 void orc_sse_timestep(OrcSse *g, double beta, int mode) {
-    diagonal_step(g, beta);
+    diagonal_step(g, beta, mode);
     cluster_and_free_spins(g, mode);
     uint64_t grown = g->n + g->n / 2; /* :786 */
     if (grown > g->cutoff) g->cutoff = grown;
 }
 
 /* qmc_ising.rs:208-270 */
-void orc_sse_single_diagonal_step(OrcSse *g, double beta) {
-    diagonal_step(g, beta);
+void orc_sse_single_diagonal_step(OrcSse *g, double beta) { orc_sse_single_diagonal_step_mode(g, beta, ORC_MODE_STRICT); }
+void orc_sse_single_diagonal_step_mode(OrcSse *g, double beta, int mode) {
+    diagonal_step(g, beta, mode);
     uint64_t grown = g->n + g->n / 2;
     if (grown > g->cutoff) g->cutoff = grown;
 }

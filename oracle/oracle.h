@@ -42,6 +42,7 @@ typedef struct OrcSse OrcSse;
 
 #define ORC_MODE_STRICT 0 /* reference order: LIFO DFS cluster numbering, sequential draws */
 #define ORC_MODE_FAST 1   /* canonical order: min-id cluster roots, counter-based flip bits */
+#define ORC_MODE_COUNTER 2 /* FAST cluster order + one Philox block per SLOT for the diagonal update (oracle.c) */
 
 #define ORC_OP_EMPTY 0xFFFFFFFFu /* op word of the identity */
 
@@ -59,6 +60,7 @@ void orc_sse_set_enable_heatbath(OrcSse *g, int enable);
 int orc_sse_get_enable_heatbath(const OrcSse *g);
 void orc_sse_timestep(OrcSse *g, double beta, int mode);
 void orc_sse_single_diagonal_step(OrcSse *g, double beta);
+void orc_sse_single_diagonal_step_mode(OrcSse *g, double beta, int mode);
 uint64_t orc_sse_single_cluster_step(OrcSse *g, int mode);
 /* QmcStepper::timesteps_measure_with_self; samples_or_null is [t/freq][nvars] bytes. */
 double orc_sse_timesteps(OrcSse *g, uint64_t t, double beta, uint64_t sampling_freq, int mode,

@@ -16,6 +16,7 @@ _SO = os.path.join(_HERE, "_build", "liboracle.so")
 
 MODE_STRICT = 0
 MODE_FAST = 1
+MODE_COUNTER = 2
 OP_EMPTY = 0xFFFFFFFF
 
 
@@ -61,6 +62,7 @@ def lib():
     sig("orc_sse_get_enable_heatbath", C.c_int, vp)
     sig("orc_sse_timestep", None, vp, C.c_double, C.c_int)
     sig("orc_sse_single_diagonal_step", None, vp, C.c_double)
+    sig("orc_sse_single_diagonal_step_mode", None, vp, C.c_double, C.c_int)
     sig("orc_sse_single_cluster_step", C.c_uint64, vp, C.c_int)
     sig("orc_sse_timesteps", C.c_double, vp, C.c_uint64, C.c_double, C.c_uint64, C.c_int, u8p)
     sig("orc_sse_nvars", C.c_uint32, vp)
@@ -157,8 +159,8 @@ class SseOracle:
     def timestep(self, beta, mode=MODE_STRICT):
         lib().orc_sse_timestep(self._h, beta, mode)
 
-    def single_diagonal_step(self, beta):
-        lib().orc_sse_single_diagonal_step(self._h, beta)
+    def single_diagonal_step(self, beta, mode=MODE_STRICT):
+        lib().orc_sse_single_diagonal_step_mode(self._h, beta, mode)
 
     def single_cluster_step(self, mode=MODE_STRICT):
         return lib().orc_sse_single_cluster_step(self._h, mode)

@@ -16,7 +16,8 @@ SYSTEMS = [
 ]
 
 
-@pytest.mark.parametrize("mode,heatbath", [(po.MODE_STRICT, False), (po.MODE_FAST, False), (po.MODE_STRICT, True), (po.MODE_FAST, True)])
+@pytest.mark.parametrize("mode,heatbath", [(po.MODE_STRICT, False), (po.MODE_FAST, False), (po.MODE_STRICT, True), (po.MODE_FAST, True),
+                                           (po.MODE_COUNTER, False)])
 @pytest.mark.parametrize("name,edges,gamma,h,beta", SYSTEMS)
 def test_energy_matches_exact_diagonalisation(name, edges, gamma, h, beta, mode, heatbath):
     nvars = lattices.nvars_of(edges)
@@ -47,7 +48,7 @@ def test_longitudinal_crash_lattices_verify():
              (lattices.two_d_periodic_mixed(4), 1.0, 1.0, 16, None), (lattices.two_unit_cell(), 1.0, 1.0, 8, None)]
     for edges, g, h, cutoff, state in cases:
         for seed in range(8):
-            for mode in (po.MODE_STRICT, po.MODE_FAST):
+            for mode in (po.MODE_STRICT, po.MODE_FAST, po.MODE_COUNTER):
                 q = po.SseOracle(edges, g, h, cutoff, key=seed, state=state)
                 q.timesteps(300, 1.0, mode)
                 assert q.error == 0 and q.verify()
@@ -61,7 +62,7 @@ def test_dump_load_round_trip():
     b.load_ops(a.dump_ops(), a.state())
     b.set_cursor(a.cursor)
     assert b.n == a.n and b.verify()
-    for mode in (po.MODE_STRICT, po.MODE_FAST):
+    for mode in (po.MODE_STRICT, po.MODE_FAST, po.MODE_COUNTER):
         a.timestep(2.0, mode), b.timestep(2.0, mode)
         assert np.array_equal(a.dump_ops(), b.dump_ops()) and np.array_equal(a.state(), b.state())
         assert a.cursor == b.cursor
