@@ -37,9 +37,15 @@ typedef enum {
  *         path under the same injected stream.
  * FAST:   clusters are keyed by their smallest segment id and flip on a counter-based Philox bit;
  *         same Markov kernel, labelled by a parallel union-find.  Bit-exact with the oracle's
- *         FAST mode; statistically equivalent to STRICT. */
+ *         FAST mode; statistically equivalent to STRICT.
+ * COUNTER: the FAST cluster order, plus a diagonal update whose uniform words are one Philox block per SLOT,
+ *         Philox(key, (p, c_lo, c_hi, 'DIAG')) with c the stream cursor at the start of the step, instead of
+ *         positions in the sequential stream: the acceptance arithmetic is the reference's (diagonal.rs:142-191),
+ *         only n couples the slots.  Bit-exact with the oracle's COUNTER mode; statistically equivalent to STRICT
+ *         (exact diagonalisation tests).  Metropolis rule only (no heat-bath contract). */
 #define QMCB_MODE_STRICT 0
 #define QMCB_MODE_FAST 1
+#define QMCB_MODE_COUNTER 2
 
 /* Operator word (one uint32 per slot p of the operator string; replaces BasicOp,
  * op_container.rs:224-237): bits 0..23 bond index, bits 24,25 input spins of leg 0,1,

@@ -3,7 +3,7 @@ Renmusxd/IsingMonteCarlo (SSE transverse-field Ising sweeps, classical checkerbo
 parallel-tempering swaps).  The compute path is the CUDA library behind include/qmcb.h; this
 package is the thin host-side mirror of the reference's interface for that path."""
 from . import lattices  # noqa: F401
-from ._lib import MODE_FAST, MODE_STRICT, OP_EMPTY, QmcbError  # noqa: F401
+from ._lib import MODE_COUNTER, MODE_FAST, MODE_STRICT, OP_EMPTY, QmcbError  # noqa: F401
 
 
 def __getattr__(name):

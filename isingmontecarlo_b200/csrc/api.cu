@@ -29,6 +29,8 @@ void launch_autocorrelation(const uint8_t *samples, uint32_t R, uint32_t N, uint
 void launch_sse_init_state(const SseDev &D, cudaStream_t st);
 int launch_sse_fast(const SseDev &D, const SseTuning &T, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
+int launch_sse_counter(const SseDev &D, const SseTuning &T, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
+                       uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
 int launch_pt_export(const SseDev &D, const PtDev &P, uint64_t *rec, cudaStream_t st);
 void launch_pt_apply(const SseDev &D, const PtDev &P, const uint64_t *rec, uint32_t S, cudaStream_t st);
 void launch_cls_generic(const ClsDev &D, uint32_t colour, uint32_t cstart, uint32_t ccount, uint64_t sweep, cudaStream_t st);
@@ -91,7 +93,7 @@ struct QmcbHandle {
     double offset = 0.0;
     uint64_t target = 0;  // sweeps requested so far
     uint64_t launches = 0;
-    bool strict_ws = false, fast_ws = false;
+    bool strict_ws = false, fast_ws = false, counter_ws = false;
     bool auto_capacity = false;
     double beta_max = 0.0;
     // tempering
@@ -143,6 +145,14 @@ static int alloc_fast_ws(QmcbHandle *h) {
     return QMCB_OK;
 }
 
+static int alloc_counter_ws(QmcbHandle *h) {
+    if (h->counter_ws) return QMCB_OK;
+    SseDev &D = h->D;
+    CUDA_TRY(h->pool.alloc(&D.sid, (size_t)D.R * D.cap));
+    h->counter_ws = true;
+    return QMCB_OK;
+}
+
 // re-layout every per-slot array for a larger per-replica capacity
 static int grow(QmcbHandle *h, uint64_t newcap) {
     SseDev &D = h->D;
@@ -151,10 +161,10 @@ static int grow(QmcbHandle *h, uint64_t newcap) {
     if (newcap >= (1ull << 29)) return fail(QMCB_ERR_CAPACITY, "operator string capacity above 2^29 slots per replica");
     // every new buffer is allocated before the old layout is touched: a failed growth (it typically happens near the
     // end of device memory) leaves the handle exactly as it was
-    const bool s = h->strict_ws, f = h->fast_ws;
+    const bool s = h->strict_ws, f = h->fast_ws, c = h->counter_ws;
     SseDev Dn = D;
     Dn.cap = newcap;
-    uint32_t *nops = nullptr, *nbits = nullptr, *nfrozen = nullptr, *nrec = nullptr, *nfrontier = nullptr, *ninterior = nullptr, *nparent = nullptr;
+    uint32_t *nops = nullptr, *nbits = nullptr, *nfrozen = nullptr, *nrec = nullptr, *nfrontier = nullptr, *ninterior = nullptr, *nparent = nullptr, *nsid = nullptr;
     cudaError_t e = h->pool.alloc(&nops, (size_t)D.R * newcap);
     if (e == cudaSuccess) e = h->pool.alloc(&nbits, (size_t)D.R * bits_stride(Dn));
     if (e == cudaSuccess) e = h->pool.alloc(&nfrozen, (size_t)D.R * bits_stride(Dn));
@@ -162,18 +172,19 @@ static int grow(QmcbHandle *h, uint64_t newcap) {
     if (e == cudaSuccess && s) e = h->pool.alloc(&nfrontier, (size_t)D.R * (2 * newcap + 16));
     if (e == cudaSuccess && s) e = h->pool.alloc(&ninterior, (size_t)D.R * (4 * newcap + 16));
     if (e == cudaSuccess && f) e = h->pool.alloc(&nparent, (size_t)D.R * (D.N + newcap + 1));
+    if (e == cudaSuccess && c) e = h->pool.alloc(&nsid, (size_t)D.R * newcap);
     if (e == cudaSuccess) e = cudaMemsetAsync(nops, 0xFF, (size_t)D.R * newcap * 4, h->stream);
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(nops, newcap * 4, D.ops, D.cap * 4, D.cap * 4, D.R, cudaMemcpyDeviceToDevice, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         h->pool.release(nops), h->pool.release(nbits), h->pool.release(nfrozen), h->pool.release(nrec);
-        h->pool.release(nfrontier), h->pool.release(ninterior), h->pool.release(nparent);
+        h->pool.release(nfrontier), h->pool.release(ninterior), h->pool.release(nparent), h->pool.release(nsid);
         return fail(QMCB_ERR_CAPACITY, "out of device memory while growing the operator strings");
     }
     h->pool.release(D.ops), h->pool.release(D.rec), h->pool.release(D.frontier), h->pool.release(D.interior);
-    h->pool.release(D.parent), h->pool.release(D.bits), h->pool.release(D.frozen);
-    D.ops = nops, D.bits = nbits, D.frozen = nfrozen, D.rec = nrec, D.frontier = nfrontier, D.interior = ninterior, D.parent = nparent;
+    h->pool.release(D.parent), h->pool.release(D.bits), h->pool.release(D.frozen), h->pool.release(D.sid);
+    D.ops = nops, D.bits = nbits, D.frozen = nfrozen, D.rec = nrec, D.frontier = nfrontier, D.interior = ninterior, D.parent = nparent, D.sid = nsid;
     D.cap = newcap;
     return QMCB_OK;
 }
@@ -216,6 +227,14 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
         }
         launch_sse_serial(h->D, 0, h->target, phases, freq, origin, samples_dev, spr, h->stream);
         h->launches += 1;
+    } else if (h->mode == QMCB_MODE_COUNTER) {
+        if ((rc = alloc_fast_ws(h)) || (rc = alloc_counter_ws(h))) return rc;
+        int nl = h->impl == 1 ? -1 : launch_sse_counter(h->D, h->tune, h->target, phases, freq, origin, samples_dev, spr, h->stream);
+        if (nl < 0) {
+            launch_sse_serial(h->D, 2, h->target, phases, freq, origin, samples_dev, spr, h->stream);
+            nl = 1;
+        }
+        h->launches += (uint64_t)nl;
     } else {
         if ((rc = alloc_fast_ws(h))) return rc;
         int nl = h->impl == 1 ? -1 : launch_sse_fast(h->D, h->tune, h->target, phases, freq, origin, samples_dev, spr, h->stream);
@@ -403,7 +422,8 @@ extern "C" int qmcb_set_stream(QmcbHandle *h, void *s) {
 }
 extern "C" int qmcb_set_mode(QmcbHandle *h, int mode) {
     CHECK_H(h);
-    if (mode != QMCB_MODE_STRICT && mode != QMCB_MODE_FAST) return fail(QMCB_ERR_BAD_ARG, "unknown mode");
+    if (mode != QMCB_MODE_STRICT && mode != QMCB_MODE_FAST && mode != QMCB_MODE_COUNTER) return fail(QMCB_ERR_BAD_ARG, "unknown mode");
+    if (mode == QMCB_MODE_COUNTER && h->D.hb_cum) return fail(QMCB_ERR_UNSUPPORTED, "the heat-bath diagonal update has no COUNTER-mode contract (use FAST or STRICT)");
     h->mode = mode;
     return QMCB_OK;
 }
@@ -417,6 +437,7 @@ extern "C" int qmcb_set_enable_heatbath(QmcbHandle *h, int enable) {
         D.hb_cum = D.hb_maxw = nullptr;
         return QMCB_OK;
     }
+    if (h->mode == QMCB_MODE_COUNTER) return fail(QMCB_ERR_UNSUPPORTED, "the heat-bath diagonal update has no COUNTER-mode contract (use FAST or STRICT)");
     if (!h->hb_cum_dev) {
         const uint32_t H = h->H;
         std::vector<double> maxw((size_t)H * D.Nb), cum((size_t)H * D.Nb), tot(H);

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #define QMCB_TAG_CLUS 0x434C5553u  // counter word 3 of the FAST-mode cluster bits
+#define QMCB_TAG_DIAG 0x44494147u  // counter word 3 of the COUNTER-mode diagonal update: one block per slot
 #define QMCB_TAG_CB 0x43420000u    // counter word 3 (| colour) of the checkerboard draws, high 16 bits
 #define QMCB_TAG_CB2 0x43430000u   // ... low 16 bits
 #define OP_EMPTY 0xFFFFFFFFu

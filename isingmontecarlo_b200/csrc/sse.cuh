@@ -46,6 +46,7 @@ struct SseDev {
     uint32_t *frozen;    // [R][cap/32+2] cluster holds a longitudinal op
     // FAST workspace
     uint32_t *parent;    // [R][N+cap+1] union-find parents over segment ids
+    uint32_t *sid;       // [R][cap] COUNTER mode: a member of the cluster on the input side of each op (sse_counter.cu)
     // heat-bath diagonal update (heatbath.rs:10-61 BondWeights); NULL = Metropolis rule
     const double *hb_cum, *hb_maxw;  // [Nb] cumulative / per-bond maximum diagonal weight
     double hb_total;

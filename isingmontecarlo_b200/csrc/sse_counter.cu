@@ -1,0 +1,521 @@
+// sse_counter.cu -- warp-parallel SSE sweep, COUNTER mode (QMCB_MODE_COUNTER): the FAST cluster order with a diagonal
+// update whose uniform words are a function of (key, step nonce, SLOT) instead of positions in the sequential stream
+// (contract: oracle.c diagonal_update_counter / DESIGN.md 3.8).  The acceptance arithmetic is the reference's
+// (diagonal.rs:142-191, same numerator / denominator, same live n); what changes is where the words come from, and with
+// it the only thing that made the pass sequential apart from n: a slot no longer has to know how many words the slots
+// before it consumed.  One warp per replica, 32 slots per step:
+//  P1  every lane draws its slot's Philox block, proposes / weighs its op and classifies its decision against
+//      conservative thresholds valid for every n the step can reach at that lane; the (rare) lane whose word falls
+//      between them is settled in lane order with the exact division at the exact n.  Result: bit-identical to the
+//      sequential loop.  Fused in the same pass, as in sse_fast.cu: world-line segments, their union-find, and -- new --
+//      a per-slot record `sid` of a member of the cluster on the input side of every op.
+//  P2  one flip bit per segment id (parent id < child id), as sse_fast.cu.
+//  P3  stateless apply: op word + sid -> flip bits looked up per slot; no per-variable state, no lattice tables, no
+//      match; four lines in flight per iteration.
+#include <algorithm>
+#include <map>
+#include <mutex>
+
+#include "sse.cuh"
+#include "sse_warp.cuh"
+
+#define T_NONE 0
+#define T_EMPTY 1
+#define T_DIAG 2
+#define T_OFFD 3
+
+// shared memory of one replica; fixed-size tables first (compile-time offsets), lattice-sized ones after
+#define CT_NUM 0      // [36] f64: beta * Nb * <s|H_b|s> per weight class (2 * coupling code + (s0 != s1); 32 site; 33 + s long)
+#define CT_RNUM 288   // [36] f64: 1 / num
+#define CT_FL 576     // [32] u32: variable flipped by the off-diagonal op of lane j
+#define CT_LINE 704   // [32] u32: next line of the operator string (cp.async)
+#define CT_VAR 832    // st, tb, cd, sb [Nw each], rep [N]
+#define CLS_SITE 32u
+#define CLS_LONG 33u
+
+__host__ __device__ inline size_t cnt_smem_bytes(uint32_t N, uint32_t Nw) { return (CT_VAR + ((size_t)4 * Nw + N) * 4 + 15) / 16 * 16; }
+
+#ifndef QMCB_WPB
+#define QMCB_WPB 4
+#endif
+
+template <bool HAS_H, int MINB, bool MH, int PK>
+__global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
+    k_sse_counter(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin, uint8_t *samples,
+                  uint64_t samples_per_rep, uint32_t smem_stride, uint32_t epk_off) {
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    if (PK == 1) {  // block-shared copy of the packed edge table (low-occupancy build)
+        uint32_t *dst = (uint32_t *)(smem_all + epk_off);
+        for (uint32_t i = threadIdx.x; i < D.E; i += blockDim.x) dst[i] = __ldg(D.epk + i);
+        __syncthreads();
+    }
+    const uint32_t *const epk_s = PK == 2 ? D.epk : (const uint32_t *)(smem_all + epk_off);
+    const uint32_t wib = __reduce_max_sync(FULL, threadIdx.x >> 5);  // warp-uniform by construction (uniform registers)
+    unsigned char *const smem_raw = smem_all + wib * smem_stride;
+    const int lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * QMCB_WPB + wib;
+    if (r >= D.R) return;
+    const uint32_t N = D.N, Nw = D.Nw;
+    double *const numtab = (double *)(smem_raw + CT_NUM), *const rnumtab = (double *)(smem_raw + CT_RNUM);
+    uint32_t *const s_fl = (uint32_t *)(smem_raw + CT_FL), *const s_line = (uint32_t *)(smem_raw + CT_LINE);
+    uint32_t *const s_st = (uint32_t *)(smem_raw + CT_VAR), *const s_tb = s_st + Nw, *const s_cd = s_st + 2 * Nw, *const s_sb = s_st + 3 * Nw;
+    uint32_t *const s_rep = s_st + 4 * Nw;
+    uint32_t *ops = D.ops + (size_t)r * D.cap;
+    uint32_t *sid = D.sid + (size_t)r * D.cap;
+    uint32_t *gstate = D.state + (size_t)r * Nw;
+    uint32_t *P = D.parent + (size_t)r * (N + D.cap + 1);
+    const size_t bstride = (size_t)(D.cap / 32 + 2 + N / 32);
+    uint32_t *decb = D.bits + (size_t)r * bstride;
+    uint32_t *frz = D.frozen + (size_t)r * bstride;
+    uint32_t lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    const uint64_t key = D.key[r];
+    const Ham Hm = ham_view<MH>(D, r);
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    const uint32_t E = D.E, Nb = D.Nb;
+    auto evars = [&](uint32_t b, int kind, uint32_t &v0, uint32_t &v1) -> uint32_t {
+        if (PK && kind == KIND_BOND) {
+            const uint32_t e = PK == 2 ? __ldg(epk_s + b) : epk_s[b];
+            v0 = e & 0x3FFFu, v1 = (e >> 14) & 0x3FFFu;
+            return e;
+        }
+        bond_vars(D, b, kind, v0, v1);
+        return 0u;
+    };
+    // weight class of (packed table word, kind, spins) and the numerator of the acceptance ratio
+    auto wclass = [&](uint32_t e, int kind, uint32_t s0, uint32_t s1) -> uint32_t {
+        return kind == KIND_BOND ? 2u * (e >> 28) + (s0 ^ s1) : ((!HAS_H || kind == KIND_SITE) ? CLS_SITE : CLS_LONG + s0);
+    };
+    const double G_LO = 1.0 - 9.094947017729282e-13, G_HI = 1.0 + 9.094947017729282e-13;  // 1 -+ 2^-40: guard of the reciprocal bounds
+
+    uint64_t done = D.done[r];
+    const uint64_t nsteps = (phases & 16u) ? (done + 1 == target ? 1 : 0) : ((phases & 8u) ? (target > done ? target - done : 0) : 1);
+    int err = 0;
+
+    for (uint64_t sw = 0; sw < nsteps; sw++) {
+        const uint32_t M = D.M[r];
+        if (M > D.cap) {
+            if (lane == 0) atomicOr(D.status, DEV_ERR_CAPACITY);
+            break;
+        }
+        uint32_t n = D.n[r];
+        uint64_t cur = D.cursor[r];
+        const double bn = D.beta[r] * (double)Nb;  // diagonal.rs:168, left-to-right product
+        const bool do_diag = phases & 1u, do_clus = phases & 2u;
+        for (uint32_t j = lane; j < Nw; j += 32) s_st[j] = gstate[j], s_cd[j] = 0, s_tb[j] = 0, s_sb[j] = 0;
+        if (PK) {
+            for (uint32_t c = lane; c < 36; c += 32) {
+                double wgt = 0.0;
+                if (c < 32) {
+                    const double j = D.jdict[c >> 1];
+                    wgt = fabs(j) + ((c & 1u) ? j : -j);
+                } else if (c == CLS_SITE) wgt = Hm.gamma;
+                else if (HAS_H && c < 35) wgt = fabs(Hm.h) + (c == CLS_LONG + 1 ? Hm.h : -Hm.h);
+                const double num = bn * wgt;
+                numtab[c] = num, rnumtab[c] = 1.0 / num;
+            }
+        }
+        if (do_clus) {
+            for (uint32_t v = lane; v < N; v += 32) s_rep[v] = v, st_cg(P + v, v);
+            if (HAS_H)
+                for (uint32_t j = lane; j < (uint32_t)bstride; j += 32) st_cg(frz + j, 0u);
+        }
+        __syncwarp();
+        uint32_t nsite = 0;
+        bool anylong = false, alltb = false;
+        const uint64_t cdiag = cur;  // nonce of this diagonal step
+        if (do_diag) cur += 1;
+
+        // =========================== P1: diagonal update + segments + unions ===========================
+        if (M) fetch_line(s_line, ops, lane);
+        const uint32_t nit = (M + 31) / 32;
+        for (uint32_t it = 0; it < nit; it++) {
+            const uint32_t base = it * 32, p = base + lane;
+            const bool valid = p < M;
+            uint32_t w = take_line(s_line, lane);
+            if (!valid) w = OP_EMPTY;
+            if (base + 32 < M) fetch_line(s_line, ops + base + 32, lane);
+            const int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
+            // op of this slot after the diagonal update: kind (-1 none), variables, packed table word
+            int kind = -1;
+            uint32_t v0 = 0, v1 = 0, ee = 0, neww = w;
+            if (type >= T_DIAG) {
+                kind = bkind<HAS_H>(D, op_bond(w));
+                ee = evars(op_bond(w), kind, v0, v1);
+            }
+            if (do_diag) {
+                const bool offd = type == T_OFFD;
+                const uint32_t fmask = __ballot_sync(FULL, offd);
+                if (fmask) {  // off-diagonal ops flip their variable for the later lanes of this step
+                    s_fl[lane] = offd ? v0 : NONE32;
+                    if (offd) atomicOr(&s_cd[v0 >> 5], 1u << (v0 & 31));
+                    __syncwarp();
+                }
+                // the slot's words: one Philox block per slot
+                uint64_t wA = 0, wB = 0;
+                if (type == T_EMPTY || type == T_DIAG) {
+                    const Philox4 o = philox4x32_10(p, (uint32_t)cdiag, (uint32_t)(cdiag >> 32), QMCB_TAG_DIAG, k0, k1);
+                    wA = ((uint64_t)o.y << 32) | o.x, wB = ((uint64_t)o.w << 32) | o.z;
+                }
+                double num = 0.0, rn = 0.0;
+                uint32_t pb = 0, pbits = 0, pv0 = 0, pv1 = 0, pe = 0;
+                int pkind = KIND_BOND;
+                if (type == T_EMPTY) {  // proposal: bond by multiply-shift, weight from the propagated state at this slot
+                    pb = (uint32_t)__umul64hi(wA, (uint64_t)Nb);
+                    pkind = bkind<HAS_H>(D, pb);
+                    pe = evars(pb, pkind, pv0, pv1);
+                    uint32_t s0 = state_bit(s_st, pv0), s1 = pkind == KIND_BOND ? state_bit(s_st, pv1) : 0u;
+                    if ((fmask & lt_mask) && (state_bit(s_cd, pv0) || (pkind == KIND_BOND && state_bit(s_cd, pv1))))
+                        for (uint32_t m = fmask & lt_mask; m; m &= m - 1) {
+                            const uint32_t fv = s_fl[__ffs(m) - 1];
+                            s0 ^= (fv == pv0), s1 ^= (pkind == KIND_BOND && fv == pv1);
+                        }
+                    pbits = s0 | (s1 << 1);
+                    if (PK) num = numtab[wclass(pe, pkind, s0, s1)];
+                    else num = bn * bweight<HAS_H>(Hm, pb, pkind, s0, s1);
+                } else if (type == T_DIAG) {
+                    const uint32_t s0 = op_in(w) & 1u, s1 = (op_in(w) >> 1) & 1u;
+                    if (PK) {
+                        const uint32_t c = wclass(ee, kind, s0, s1);
+                        num = numtab[c], rn = rnumtab[c];
+                    } else {
+                        num = bn * bweight<HAS_H>(Hm, op_bond(w), kind, s0, s1);
+                        rn = 1.0 / num;
+                    }
+                }
+                // conservative classification over the n interval this lane can see (the rules are monotone in den)
+                const uint32_t emask = __ballot_sync(FULL, type == T_EMPTY), dmask = __ballot_sync(FULL, type == T_DIAG);
+                const double dlo = (double)(M - (n + (uint32_t)__popc(emask & lt_mask)));
+                const double dhi = (double)(M - (n - (uint32_t)__popc(dmask & lt_mask)));
+                int dec = 0;  // +1 insert, -1 remove
+                bool amb = false, needdiv = false;
+                if (type == T_EMPTY) {
+                    if (num > dhi) dec = 1;
+                    else if (num > 0.0) needdiv = true;
+                } else if (type == T_DIAG) {
+                    if (dlo + 1.0 > num) dec = -1;
+                    else {
+                        const double q_lo = (dlo + 1.0) * rn * G_LO, q_hi = (dhi + 1.0) * rn * G_HI;
+                        if (wA < bool_threshold(q_lo)) dec = -1;
+                        else if (!(q_hi < 1.0 && wA >= bool_threshold(q_hi))) amb = true;
+                    }
+                }
+                if (__any_sync(FULL, needdiv)) {
+                    // insertion with num <= den: bounds from the two reciprocals of the step's den interval
+                    const double DLO = (double)(M - (n + (uint32_t)__popc(emask))), DHI = (double)(M - (n - (uint32_t)__popc(dmask)));
+                    const double rA = 1.0 / DLO, rB = 1.0 / DHI;
+                    if (needdiv) {
+                        const double q_lo = num * rB * G_LO, q_hi = num * rA * G_HI;
+                        if (wB < bool_threshold(q_lo)) dec = 1;
+                        else if (!(q_hi < 1.0 && wB >= bool_threshold(q_hi))) amb = true;
+                    }
+                }
+                uint32_t insm = __ballot_sync(FULL, dec == 1), remm = __ballot_sync(FULL, dec == -1);
+                for (uint32_t ambm = __ballot_sync(FULL, amb); ambm; ambm &= ambm - 1) {
+                    // the exact rule at the exact n, in lane order (earlier lanes are final)
+                    const int u = __ffs(ambm) - 1;
+                    if (lane == u) {
+                        const uint32_t nl = n + (uint32_t)__popc(insm & lt_mask) - (uint32_t)__popc(remm & lt_mask);
+                        if (type == T_EMPTY) {
+                            const double den = (double)(M - nl);
+                            bool acc = num > den;
+                            if (!acc) {
+                                const double pr = num / den;
+                                if (pr == 1.0) acc = true;
+                                else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                                else acc = wB < bool_threshold(pr);
+                            }
+                            dec = acc ? 1 : 0;
+                        } else {
+                            const double den = (double)(M - nl) + 1.0;
+                            bool rem = den > num;
+                            if (!rem) {
+                                const double pr = den / num;
+                                if (pr == 1.0) rem = true;
+                                else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                                else rem = wA < bool_threshold(pr);
+                            }
+                            dec = rem ? -1 : 0;
+                        }
+                    }
+                    const int du = __shfl_sync(FULL, dec, u);
+                    if (du == 1) insm |= 1u << u;
+                    else if (du == -1) remm |= 1u << u;
+                }
+                n += (uint32_t)__popc(insm) - (uint32_t)__popc(remm);
+                if (dec == 1) neww = make_op(pb, pbits, pbits), kind = pkind, v0 = pv0, v1 = pv1, ee = pe;
+                else if (dec == -1) neww = OP_EMPTY, kind = -1;
+                if (insm | remm) {
+                    if (neww != w) st_cg(ops + p, neww);
+                }
+                if (fmask) {
+                    if (offd) atomicXor(&s_st[v0 >> 5], 1u << (v0 & 31)), atomicAnd(&s_cd[v0 >> 5], ~(1u << (v0 & 31)));
+                    __syncwarp();
+                }
+            }
+            if (do_clus) {
+                // ---- segments and unions on the final ops of this step
+                const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
+                const uint32_t myid = N + nsite + (uint32_t)__popc(smask & lt_mask);
+                bool collide = false;
+                if (kind == KIND_SITE) {
+                    st_cg(P + myid, myid);
+                    const uint32_t bit = 1u << (v0 & 31);
+                    collide = atomicOr(&s_sb[v0 >> 5], bit) & bit;  // another site op of this step on the same variable
+                }
+                if (!alltb && kind >= 0) {
+                    if (!state_bit(s_tb, v0)) atomicOr(&s_tb[v0 >> 5], 1u << (v0 & 31));
+                    if (kind == KIND_BOND && !state_bit(s_tb, v1)) atomicOr(&s_tb[v1 >> 5], 1u << (v1 & 31));
+                }
+                // a member of the set of the segment open on my variables before my slot: the table entry, unless a
+                // site op of this step cuts the variable at an earlier lane
+                uint32_t ra = 0, rb = 0, oa = 0, ob = 0;
+                bool fa = false, fb = false;
+                if (kind >= 0) {
+                    oa = ra = s_rep[v0], fa = true;
+                    if (kind == KIND_BOND) ob = rb = s_rep[v1], fb = true;
+                }
+                __syncwarp();
+                const bool hit = collide || (kind >= 0 && kind != KIND_SITE && (state_bit(s_sb, v0) || (kind == KIND_BOND && state_bit(s_sb, v1))));
+                if (__any_sync(FULL, hit)) {
+                    const uint32_t nokey = 0x80000000u | (uint32_t)lane;
+                    const uint32_t ma = __match_any_sync(FULL, kind >= 0 ? v0 : nokey) & smask & lt_mask;
+                    const uint32_t mb = __match_any_sync(FULL, kind == KIND_BOND ? v1 : (kind == KIND_SITE ? v0 : nokey)) & smask & lt_mask;
+                    if (kind >= 0 && ma) ra = N + nsite + (uint32_t)__popc(smask & ((1u << (31 - __clz(ma))) - 1u)), fa = false;
+                    if (kind == KIND_BOND && mb) rb = N + nsite + (uint32_t)__popc(smask & ((1u << (31 - __clz(mb))) - 1u)), fb = false;
+                }
+                __syncwarp();  // new ids are initialised before anyone follows them; bitmap reads are done
+                if (kind == KIND_SITE) atomicAnd(&s_sb[v0 >> 5], ~(1u << (v0 & 31)));
+                if (kind >= 0) st_cg(sid + p, ra);  // P3 looks the input-side flip up through this id
+                if (kind == KIND_BOND && ra != rb) {
+                    const uint32_t root = uf_union_cg(P, ra, rb);
+                    if (fa) atomicCAS(&s_rep[v0], oa, root);  // cache the root: equal roots skip the union
+                    if (fb) atomicCAS(&s_rep[v1], ob, root);
+                }
+                if (HAS_H && kind == KIND_LONG) {
+                    atomicOr(&frz[ra >> 5], 1u << (ra & 31));
+                    anylong = true;
+                }
+                if (kind == KIND_SITE) atomicMax(&s_rep[v0], myid);  // the site op with the highest lane owns the variable from here on
+                nsite += (uint32_t)__popc(smask);
+                if (!alltb && (it & 31u) == 31u) {  // once every variable has an op the touched bits need no more updates
+                    uint32_t cnt = 0;
+                    for (uint32_t j = lane; j < Nw; j += 32) cnt += (uint32_t)__popc(s_tb[j]);
+                    alltb = __reduce_add_sync(FULL, cnt) == N;
+                }
+                __syncwarp();
+            }
+        }
+        if (do_diag && lane == 0) D.n[r] = n;
+
+        uint32_t ncl = 0;
+        if (do_clus && n > 0) {
+            const uint64_t c0 = cur;
+            // periodic closure: the segment open at the end of variable v is the one crossing p = 0
+            for (uint32_t v = lane; v < N; v += 32) {
+                const uint32_t rp = s_rep[v];
+                if (rp != v) uf_union_cg(P, v, rp);
+            }
+            __syncwarp();
+            __threadfence_block();
+            const uint32_t nseg = N + nsite;
+            const uint32_t nwords = (nseg + 31) / 32;
+            bool frozen_all = false;
+            if (HAS_H) {
+                frozen_all = __any_sync(FULL, anylong);
+                for (int32_t wd = (int32_t)nwords - 1; wd >= 0; wd--) {  // push frozen marks up to the roots: descending ids, parents are smaller
+                    const uint32_t x = (uint32_t)wd * 32 + lane;
+                    const uint32_t par = x < nseg ? ld_cg(P + x) : x;
+                    for (;;) {
+                        const uint32_t fzw = *(volatile uint32_t *)&frz[wd];
+                        const bool mine = x < nseg && ((fzw >> lane) & 1u) && par != x;
+                        bool changed = false;
+                        if (mine) {
+                            const uint32_t old = atomicOr(&frz[par >> 5], 1u << (par & 31));
+                            changed = ((old >> (par & 31)) & 1u) == 0 && (par >> 5) == (uint32_t)wd;
+                        }
+                        if (!__any_sync(FULL, changed)) break;
+                    }
+                    __syncwarp();
+                }
+            }
+            // =========================== P2: one flip bit per segment ===========================
+            uint32_t nroots = 0;
+            Philox4 rb4 = {0, 0, 0, 0};
+            for (uint32_t wd = 0; wd < nwords; wd++) {
+                const uint32_t x = wd * 32 + lane;
+                if ((wd & 3u) == 0) rb4 = philox4x32_10(wd >> 2, (uint32_t)c0, (uint32_t)(c0 >> 32), QMCB_TAG_CLUS, k0, k1);
+                const uint32_t rword = (wd & 3u) == 0 ? rb4.x : ((wd & 3u) == 1 ? rb4.y : ((wd & 3u) == 2 ? rb4.z : rb4.w));
+                uint32_t par = x < nseg ? ld_cg(P + x) : x;
+                if (nsite == 0) par = x < nseg ? 0u : x;  // cluster.rs:98-107: no cluster edge => one cluster
+                const bool root = x < nseg && par == x;
+                nroots += (uint32_t)__popc(__ballot_sync(FULL, root));
+                bool dec = false, known = root || x >= nseg;
+                if (root) {
+                    dec = (rword >> lane) & 1u;
+                    if (HAS_H) dec = dec && !((nsite == 0) ? frozen_all : ((ld_cg(frz + wd) >> lane) & 1u));
+                } else if (x < nseg && par < wd * 32) {
+                    dec = (ld_cg(decb + (par >> 5)) >> (par & 31)) & 1u;
+                    known = true;
+                }
+                for (;;) {  // parents inside this word: resolve by rounds (parent id < child id)
+                    const uint32_t kmask = __ballot_sync(FULL, known), dmask = __ballot_sync(FULL, dec);
+                    if (kmask == FULL) {
+                        if (lane == 0) st_cg(decb + wd, dmask);
+                        break;
+                    }
+                    if (!known) {
+                        const uint32_t pl = par - wd * 32;
+                        if ((kmask >> pl) & 1u) dec = (dmask >> pl) & 1u, known = true;
+                    }
+                }
+                __syncwarp();
+            }
+            uint32_t untouched = 0;
+            for (uint32_t j = lane; j < Nw; j += 32) {
+                const uint32_t validm = (j == Nw - 1 && (N & 31u)) ? ((1u << (N & 31u)) - 1u) : FULL;
+                untouched += (uint32_t)__popc(~s_tb[j] & validm);
+            }
+            untouched = __reduce_add_sync(FULL, untouched);
+            ncl = nsite == 0 ? 1u : nroots - untouched;
+            __threadfence_block();
+            __syncwarp();
+
+            // =========================== P3: apply the flips (stateless) ===========================
+            uint32_t ks = 0;
+            const uint32_t EN = E + N;
+            for (uint32_t base = 0; base < M; base += 128) {
+                uint32_t w4[4], s4[4], sm4[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t p = base + 32u * j + lane;
+                    w4[j] = p < M ? ld_cg(ops + p) : OP_EMPTY;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t p = base + 32u * j + lane;
+                    s4[j] = w4[j] != OP_EMPTY ? ld_cg(sid + p) : 0u;
+                    const uint32_t b = op_bond(w4[j]);
+                    sm4[j] = __ballot_sync(FULL, w4[j] != OP_EMPTY && b >= E && b < EN);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t p = base + 32u * j + lane, w = w4[j];
+                    if (w != OP_EMPTY) {
+                        const uint32_t b = op_bond(w);
+                        const bool site = (sm4[j] >> lane) & 1u;
+                        const uint32_t si = s4[j];
+                        const bool din = (ld_cg(decb + (si >> 5)) >> (si & 31)) & 1u;
+                        bool dout = din;
+                        if (site) {
+                            const uint32_t id = N + ks + (uint32_t)__popc(sm4[j] & lt_mask);
+                            dout = (ld_cg(decb + (id >> 5)) >> (id & 31)) & 1u;
+                        }
+                        if (din || dout) {
+                            const uint32_t mask = b < E ? 3u : 1u;
+                            st_cg(ops + p, make_op(b, op_in(w) ^ (din ? mask : 0u), op_out(w) ^ (dout ? mask : 0u)));
+                        }
+                    }
+                    ks += (uint32_t)__popc(sm4[j]);
+                }
+            }
+            // spins: the segment of variable v crossing p = 0 has id v
+            for (uint32_t j = lane; j < Nw; j += 32) s_st[j] ^= ld_cg(decb + j) & s_tb[j];
+            cur = c0 + 1;
+            __syncwarp();
+        }
+        if (do_clus) {
+            // free spins: qmc_ising.rs:780-784
+            for (uint32_t base = 0; base < N; base += 32) {
+                const uint32_t v = base + lane;
+                const bool fr = v < N && !((s_tb[v >> 5] >> (v & 31)) & 1u);
+                const uint32_t m = __ballot_sync(FULL, fr);
+                bool bit = false;
+                if (fr) bit = stream_word(key, cur + __popc(m & lt_mask)) < 0x8000000000000000ull;
+                const uint32_t setm = __ballot_sync(FULL, bit);
+                if (lane == 0 && m) s_st[base >> 5] = (s_st[base >> 5] & ~m) | setm;
+                cur += __popc(m);
+            }
+            __syncwarp();
+            if (lane == 0) D.ncl[r] = ncl;
+        }
+        for (uint32_t j = lane; j < Nw; j += 32) gstate[j] = s_st[j];
+        if (lane == 0) {
+            D.cursor[r] = cur;
+            if (phases & 4u) {
+                const uint32_t grown = n + n / 2;  // qmc_ising.rs:786
+                if (grown > M) D.M[r] = grown;
+            }
+        }
+        if (phases & 8u) {
+            done++;
+            const uint64_t idx = done - sample_origin;
+            if (lane == 0) D.vupd[r] += n;
+            if (idx % sample_freq == 0) {
+                if (lane == 0) D.sum_n[r] += n;
+                if (samples) {
+                    uint8_t *dst = samples + ((size_t)r * samples_per_rep + (idx / sample_freq - 1)) * N;
+                    for (uint32_t v = lane; v < N; v += 32) dst[v] = (uint8_t)state_bit(s_st, v);
+                }
+            }
+            if (lane == 0) D.done[r] = done;
+        }
+        __syncwarp();
+    }
+    if (err) atomicOr(D.status, err);
+}
+
+// returns the number of kernel launches, or -1 if this shape is not supported by the warp kernels
+int launch_sse_counter(const SseDev &D, const SseTuning &T, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
+                       uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
+    if (D.hb_cum) return -1;  // the heat-bath rule has no COUNTER-mode contract
+    const size_t smem = cnt_smem_bytes(D.N, D.Nw);
+    if (smem * QMCB_WPB + 1024 > 227 * 1024) return -1;
+    const uint32_t blocks = (D.R + QMCB_WPB - 1) / QMCB_WPB;
+    typedef void (*Kern)(SseDev, uint64_t, uint32_t, uint64_t, uint64_t, uint8_t *, uint64_t, uint32_t, uint32_t);
+    const int nsm = T.nsm > 0 ? T.nsm : 148;
+    const size_t wanted = (blocks + nsm - 1) / nsm;
+    int minb = T.minblocks;
+    if (minb <= 0) {
+        const size_t resident = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + 1024), wanted);
+        minb = resident <= 4 ? 4 : 7;
+    }
+    if (minb != 4) minb = 7;
+    const bool have_epk = D.epk && !D.ham && T.epk;
+    size_t epk_bytes = 0;
+    if (minb == 4 && have_epk) {  // block-shared packed edge table if it does not cost a resident block
+        const size_t want = ((size_t)D.E * 4 + 15) / 16 * 16;
+        const size_t without = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + 1024), wanted);
+        const size_t with = std::min((size_t)(227 * 1024) / (smem * QMCB_WPB + want + 1024), wanted);
+        if (with >= 1 && with >= std::min<size_t>(without, 4)) epk_bytes = want;
+    }
+    const int pk = !have_epk ? 0 : (epk_bytes ? 1 : 2);
+    Kern kern;
+#define PICKC(MINB_, MH_)                                                                                             \
+    switch (pk) {                                                                                                     \
+        case 1: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 1> : k_sse_counter<false, MINB_, MH_, 1>; break;     \
+        case 2: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 2> : k_sse_counter<false, MINB_, MH_, 2>; break;     \
+        default: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 0> : k_sse_counter<false, MINB_, MH_, 0>; break;    \
+    }
+    if (D.ham) {
+        if (minb == 4) { PICKC(4, true) } else { PICKC(7, true) }
+    } else if (minb == 4) { PICKC(4, false) } else { PICKC(7, false) }
+#undef PICKC
+    {
+        static std::mutex mu;
+        static std::map<std::pair<const void *, int>, int> done;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = done.find({(const void *)kern, dev});
+        if (it == done.end()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (T.carveout >= 0 && (it == done.end() || it->second != T.carveout))
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, T.carveout);
+        done[{(const void *)kern, dev}] = T.carveout;
+    }
+    size_t dyn = smem * QMCB_WPB + epk_bytes + (size_t)std::max(T.pad, 0);
+    if (dyn > 227 * 1024) dyn = 227 * 1024;
+    kern<<<blocks, 32 * QMCB_WPB, dyn, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem,
+                                            epk_bytes ? (uint32_t)(smem * QMCB_WPB) : 0u);
+    return 1;
+}

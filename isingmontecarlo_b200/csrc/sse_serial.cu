@@ -119,6 +119,71 @@ __device__ __noinline__ void diag_serial(const SseDev &D, uint32_t r, const Rep 
 }
 
 // ------------------------------------------------------------------------------------------
+// COUNTER-mode diagonal update, literal (oracle.c diagonal_update_counter), lane 0: the fallback for shapes the warp
+// kernel does not take and its on-device cross-check ("impl" = 1)
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void diag_counter_serial(const SseDev &D, uint32_t r, const Rep &V) {
+    const uint32_t M = D.M[r];
+    uint32_t n = D.n[r];
+    const uint64_t c0 = D.cursor[r];
+    const uint64_t key = D.key[r];
+    const double bn = D.beta[r] * (double)D.Nb;
+    const Ham Hm = ham_view<true>(D, r);
+    int err = 0;
+    for (uint32_t p = 0; p < M; p++) {
+        const uint32_t w = V.ops[p];
+        if (w != OP_EMPTY && !op_is_diag(w)) {
+            const int kind = bond_kind(D, op_bond(w));
+            uint32_t v0, v1;
+            bond_vars(D, op_bond(w), kind, v0, v1);
+            const uint32_t o = op_out(w);
+            V.state[v0 >> 5] = (V.state[v0 >> 5] & ~(1u << (v0 & 31))) | ((o & 1u) << (v0 & 31));
+            if (kind == KIND_BOND) V.state[v1 >> 5] = (V.state[v1 >> 5] & ~(1u << (v1 & 31))) | (((o >> 1) & 1u) << (v1 & 31));
+            continue;
+        }
+        const Philox4 o = philox4x32_10(p, (uint32_t)c0, (uint32_t)(c0 >> 32), QMCB_TAG_DIAG, (uint32_t)key, (uint32_t)(key >> 32));
+        const uint64_t wA = ((uint64_t)o.y << 32) | o.x, wB = ((uint64_t)o.w << 32) | o.z;
+        const uint32_t b = w == OP_EMPTY ? (uint32_t)__umul64hi(wA, (uint64_t)D.Nb) : op_bond(w);
+        const int kind = bond_kind(D, b);
+        uint32_t v0, v1;
+        bond_vars(D, b, kind, v0, v1);
+        const uint32_t s0 = state_bit(V.state, v0), s1 = kind == KIND_BOND ? state_bit(V.state, v1) : 0u;
+        const double num = bn * bond_weight(Hm, b, kind, s0, s1);
+        double den = (double)(M - n);
+        if (w == OP_EMPTY) {
+            bool accept = num > den;
+            if (!accept) {
+                const double pr = num / den;
+                if (pr == 1.0) accept = true;
+                else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                else accept = wB < bool_threshold(pr);
+            }
+            if (accept) {
+                const uint32_t bitsv = s0 | (s1 << 1);
+                V.ops[p] = make_op(b, bitsv, bitsv);
+                n++;
+            }
+        } else {
+            den = den + 1.0;
+            bool remove = den > num;
+            if (!remove) {
+                const double pr = den / num;
+                if (pr == 1.0) remove = true;
+                else if (!(pr >= 0.0 && pr < 1.0)) err |= DEV_ERR_PROB;
+                else remove = wA < bool_threshold(pr);
+            }
+            if (remove) {
+                V.ops[p] = OP_EMPTY;
+                n--;
+            }
+        }
+    }
+    D.n[r] = n;
+    D.cursor[r] = c0 + 1;
+    if (err) atomicOr(D.status, err);
+}
+
+// ------------------------------------------------------------------------------------------
 // heat-bath diagonal update (heatbath.rs:106-127, :149-209), lane 0
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void diag_heatbath_serial(const SseDev &D, uint32_t r, const Rep &V) {
@@ -603,7 +668,8 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
         }
         if (phases & 1u) {
             if (lane == 0) {
-                if (D.hb_cum) diag_heatbath_serial(D, r, V);
+                if (mode == 2) diag_counter_serial(D, r, V);
+                else if (D.hb_cum) diag_heatbath_serial(D, r, V);
                 else diag_serial(D, r, V);
             }
             __syncwarp();

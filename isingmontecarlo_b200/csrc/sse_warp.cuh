@@ -1,0 +1,89 @@
+// sse_warp.cuh -- helpers shared by the warp-per-replica sweep kernels (sse_fast.cu, sse_counter.cu): the lock-free
+// min-root union-find over global memory, the asynchronous line prefetch, lattice helpers specialised on HAS_H.
+#pragma once
+#include "sse.cuh"
+
+#define FULL 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
+
+// lock-free union-find over global memory; roots are minima, parent[x] <= x always
+__device__ __forceinline__ uint32_t uf_find_cg(uint32_t *P, uint32_t x) {
+    uint32_t p = ld_cg(P + x);
+    while (p != x) {
+        uint32_t gp = ld_cg(P + p);
+        if (gp == p) return p;
+        st_cg(P + x, gp);  // path halving; a stale value is still an ancestor
+        x = gp;
+        p = ld_cg(P + x);
+    }
+    return x;
+}
+// The kernel is bound by the latency of dependent loads, so both chains are climbed in lockstep: the two parent
+// loads of a round are in flight together (one L2 round trip per level instead of two).  The start nodes are
+// pointed at the root they reached (compression of the nodes that are looked up again: S.rep entries).
+__device__ __forceinline__ uint32_t uf_union_cg(uint32_t *P, uint32_t a, uint32_t b) {
+    for (;;) {
+        const uint32_t a0 = a, b0 = b;
+        uint32_t pa = ld_cg(P + a), pb = ld_cg(P + b);
+        const uint32_t pa0 = pa, pb0 = pb;
+        while (pa != a || pb != b) {
+            a = pa, b = pb;
+            pa = ld_cg(P + a), pb = ld_cg(P + b);
+        }
+        if (pa0 != a) st_cg(P + a0, a);  // a stale value is still an ancestor
+        if (pb0 != b) st_cg(P + b0, b);
+        if (a == b) return a;
+        if (a > b) {
+            uint32_t t = a;
+            a = b, b = t;
+        }
+        if (atomicCAS(P + b, b, a) == b) return a;
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    return x - v;
+}
+
+// Software prefetch of the next 128-byte line of the operator string WITHOUT a register: held in a register across a
+// whole step, the value was spilled right after the load was issued (register cap), and the spill store waited for the
+// DRAM round trip at the top of every step.  Lanes 0..7 copy 16 bytes each straight into shared memory (cp.async.cg:
+// through L2 like ld.cg); the line is picked up at the top of the next step.  Rows are 128-byte aligned (cap % 32 == 0).
+__device__ __forceinline__ void fetch_line(uint32_t *line_smem, const uint32_t *src, int lane) {
+    if (lane < 8) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(line_smem + 4 * lane);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * lane) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t take_line(const uint32_t *line_smem, int lane) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const uint32_t w = line_smem[lane];
+    __syncwarp();  // everyone has read the line before the next copy may land in it
+    return w;
+}
+
+// lattice helpers specialised on HAS_H: without a longitudinal field there are no KIND_LONG bonds
+template <bool HAS_H>
+__device__ __forceinline__ int bkind(const SseDev &D, uint32_t b) {
+    return b < D.E ? KIND_BOND : ((!HAS_H || b < D.E + D.N) ? KIND_SITE : KIND_LONG);
+}
+template <bool HAS_H>
+__device__ __forceinline__ double bweight(const Ham &Hm, uint32_t b, int kind, uint32_t s0, uint32_t s1) {
+    if (kind == KIND_BOND) {
+        const double j = __ldg(Hm.J + b);
+        return fabs(j) + (s0 == s1 ? -j : j);
+    }
+    if (!HAS_H || kind == KIND_SITE) return Hm.gamma;
+    return fabs(Hm.h) + (s0 ? Hm.h : -Hm.h);
+}
+

@@ -7,17 +7,17 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from isingmontecarlo_b200 import MODE_FAST, MODE_STRICT, lattices  # noqa: E402
+from isingmontecarlo_b200 import MODE_COUNTER, MODE_FAST, MODE_STRICT, lattices  # noqa: E402
 from isingmontecarlo_b200.sse import QmcIsingGraph  # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 therm = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 sweeps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-mode = MODE_STRICT if len(sys.argv) > 4 and sys.argv[4] == "strict" else MODE_FAST
+mode = {"strict": MODE_STRICT, "counter": MODE_COUNTER}.get(sys.argv[4] if len(sys.argv) > 4 else "", MODE_FAST)
 L = int(os.environ.get("PROF_L", "32"))
 beta = float(os.environ.get("PROF_BETA", "16"))
 edges = lattices.square_periodic(L, -1.0)
-g = QmcIsingGraph(edges, 3.04, 0.0, L * L, 0x55E00000 + np.arange(R, dtype=np.uint64), beta, mode=MODE_FAST)
+g = QmcIsingGraph(edges, 3.04, 0.0, L * L, 0x55E00000 + np.arange(R, dtype=np.uint64), beta, mode=MODE_COUNTER if mode == MODE_COUNTER else MODE_FAST)
 t0 = time.perf_counter()
 g.timesteps(therm, beta)
 print(f"therm {therm} sweeps: {time.perf_counter() - t0:.3f} s, <n>={g.get_n().mean():.0f} <M>={g.get_cutoff().mean():.0f}")
