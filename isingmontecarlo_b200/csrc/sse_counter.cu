@@ -9,7 +9,7 @@
 //      between them is settled in lane order with the exact division at the exact n.  Result: bit-identical to the
 //      sequential loop.  Fused in the same pass, as in sse_fast.cu: world-line segments, their union-find, and -- new --
 //      a per-slot record `sid` of a member of the cluster on the input side of every op.
-//  P2  one flip bit per segment id (parent id < child id), as sse_fast.cu.
+//  P2  one flip bit per segment id (parent id < child id), four words per round.
 //  P3  stateless apply: op word + sid -> flip bits looked up per slot; no per-variable state, no lattice tables, no
 //      match; four lines in flight per iteration.
 #include <algorithm>
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
     auto wclass = [&](uint32_t e, int kind, uint32_t s0, uint32_t s1) -> uint32_t {
         return kind == KIND_BOND ? 2u * (e >> 28) + (s0 ^ s1) : ((!HAS_H || kind == KIND_SITE) ? CLS_SITE : CLS_LONG + s0);
     };
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     const double G_LO = 1.0 - 9.094947017729282e-13, G_HI = 1.0 + 9.094947017729282e-13;  // 1 -+ 2^-40: guard of the reciprocal bounds
 
     uint64_t done = D.done[r];
@@ -127,22 +128,29 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
         if (do_diag) cur += 1;
 
         // =========================== P1: diagonal update + segments + unions ===========================
-        if (M) fetch_line(s_line, ops, lane);
+        if (M) fetch_line_pol(s_line, ops, lane, pol_stream);
         const uint32_t nit = (M + 31) / 32;
         for (uint32_t it = 0; it < nit; it++) {
             const uint32_t base = it * 32, p = base + lane;
             const bool valid = p < M;
+            // the slot's words: one Philox block per slot.  Independent of the operator string, so it is computed while
+            // the line is still on its way.
+            uint64_t wA = 0, wB = 0;
+            uint32_t pb = 0;
+            if (do_diag) {
+                const Philox4 o = philox4x32_10(p, (uint32_t)cdiag, (uint32_t)(cdiag >> 32), QMCB_TAG_DIAG, k0, k1);
+                wA = ((uint64_t)o.y << 32) | o.x, wB = ((uint64_t)o.w << 32) | o.z;
+                pb = (uint32_t)__umul64hi(wA, (uint64_t)Nb);  // proposal of an empty slot: bond by multiply-shift
+            }
             uint32_t w = take_line(s_line, lane);
             if (!valid) w = OP_EMPTY;
-            if (base + 32 < M) fetch_line(s_line, ops + base + 32, lane);
+            if (base + 32 < M) fetch_line_pol(s_line, ops + base + 32, lane, pol_stream);
             const int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
-            // op of this slot after the diagonal update: kind (-1 none), variables, packed table word
-            int kind = -1;
-            uint32_t v0 = 0, v1 = 0, ee = 0, neww = w;
-            if (type >= T_DIAG) {
-                kind = bkind<HAS_H>(D, op_bond(w));
-                ee = evars(op_bond(w), kind, v0, v1);
-            }
+            // one decode for every lane: the op in the slot, or the op an empty slot proposes
+            const uint32_t beff = w == OP_EMPTY ? pb : op_bond(w);
+            int kind = bkind<HAS_H>(D, beff);
+            uint32_t v0, v1, neww = w;
+            const uint32_t ee = evars(beff, kind, v0, v1);
             if (do_diag) {
                 const bool offd = type == T_OFFD;
                 const uint32_t fmask = __ballot_sync(FULL, offd);
@@ -151,37 +159,24 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                     if (offd) atomicOr(&s_cd[v0 >> 5], 1u << (v0 & 31));
                     __syncwarp();
                 }
-                // the slot's words: one Philox block per slot
-                uint64_t wA = 0, wB = 0;
-                if (type == T_EMPTY || type == T_DIAG) {
-                    const Philox4 o = philox4x32_10(p, (uint32_t)cdiag, (uint32_t)(cdiag >> 32), QMCB_TAG_DIAG, k0, k1);
-                    wA = ((uint64_t)o.y << 32) | o.x, wB = ((uint64_t)o.w << 32) | o.z;
-                }
-                double num = 0.0, rn = 0.0;
-                uint32_t pb = 0, pbits = 0, pv0 = 0, pv1 = 0, pe = 0;
-                int pkind = KIND_BOND;
-                if (type == T_EMPTY) {  // proposal: bond by multiply-shift, weight from the propagated state at this slot
-                    pb = (uint32_t)__umul64hi(wA, (uint64_t)Nb);
-                    pkind = bkind<HAS_H>(D, pb);
-                    pe = evars(pb, pkind, pv0, pv1);
-                    uint32_t s0 = state_bit(s_st, pv0), s1 = pkind == KIND_BOND ? state_bit(s_st, pv1) : 0u;
-                    if ((fmask & lt_mask) && (state_bit(s_cd, pv0) || (pkind == KIND_BOND && state_bit(s_cd, pv1))))
+                // spins the weight looks at: the stored input bits of an existing op, the propagated state at this slot
+                // for a proposal
+                uint32_t s0 = op_in(w) & 1u, s1 = (op_in(w) >> 1) & 1u;
+                if (type == T_EMPTY) {
+                    s0 = state_bit(s_st, v0), s1 = kind == KIND_BOND ? state_bit(s_st, v1) : 0u;
+                    if ((fmask & lt_mask) && (state_bit(s_cd, v0) || (kind == KIND_BOND && state_bit(s_cd, v1))))
                         for (uint32_t m = fmask & lt_mask; m; m &= m - 1) {
                             const uint32_t fv = s_fl[__ffs(m) - 1];
-                            s0 ^= (fv == pv0), s1 ^= (pkind == KIND_BOND && fv == pv1);
+                            s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
                         }
-                    pbits = s0 | (s1 << 1);
-                    if (PK) num = numtab[wclass(pe, pkind, s0, s1)];
-                    else num = bn * bweight<HAS_H>(Hm, pb, pkind, s0, s1);
-                } else if (type == T_DIAG) {
-                    const uint32_t s0 = op_in(w) & 1u, s1 = (op_in(w) >> 1) & 1u;
-                    if (PK) {
-                        const uint32_t c = wclass(ee, kind, s0, s1);
-                        num = numtab[c], rn = rnumtab[c];
-                    } else {
-                        num = bn * bweight<HAS_H>(Hm, op_bond(w), kind, s0, s1);
-                        rn = 1.0 / num;
-                    }
+                }
+                double num, rn;
+                if (PK) {
+                    const uint32_t c = wclass(ee, kind, s0, s1);
+                    num = numtab[c], rn = rnumtab[c];
+                } else {
+                    num = bn * bweight<HAS_H>(Hm, beff, kind, s0, s1);
+                    rn = type == T_DIAG ? 1.0 / num : 0.0;
                 }
                 // conservative classification over the n interval this lane can see (the rules are monotone in den)
                 const uint32_t emask = __ballot_sync(FULL, type == T_EMPTY), dmask = __ballot_sync(FULL, type == T_DIAG);
@@ -243,23 +238,26 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                     else if (du == -1) remm |= 1u << u;
                 }
                 n += (uint32_t)__popc(insm) - (uint32_t)__popc(remm);
-                if (dec == 1) neww = make_op(pb, pbits, pbits), kind = pkind, v0 = pv0, v1 = pv1, ee = pe;
-                else if (dec == -1) neww = OP_EMPTY, kind = -1;
+                if (dec == 1) {
+                    const uint32_t pbits = s0 | (s1 << 1);
+                    neww = make_op(beff, pbits, pbits);
+                } else if (dec == -1) neww = OP_EMPTY;
                 if (insm | remm) {
-                    if (neww != w) st_cg(ops + p, neww);
+                    if (neww != w) st_cg_pol(ops + p, neww, pol_stream);
                 }
                 if (fmask) {
                     if (offd) atomicXor(&s_st[v0 >> 5], 1u << (v0 & 31)), atomicAnd(&s_cd[v0 >> 5], ~(1u << (v0 & 31)));
                     __syncwarp();
                 }
             }
+            if (neww == OP_EMPTY) kind = -1;  // no op in this slot after the diagonal update
             if (do_clus) {
                 // ---- segments and unions on the final ops of this step
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
                 const uint32_t myid = N + nsite + (uint32_t)__popc(smask & lt_mask);
                 bool collide = false;
                 if (kind == KIND_SITE) {
-                    st_cg(P + myid, myid);
+                    st_cg_pol(P + myid, myid, pol_keep);
                     const uint32_t bit = 1u << (v0 & 31);
                     collide = atomicOr(&s_sb[v0 >> 5], bit) & bit;  // another site op of this step on the same variable
                 }
@@ -286,9 +284,9 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                 }
                 __syncwarp();  // new ids are initialised before anyone follows them; bitmap reads are done
                 if (kind == KIND_SITE) atomicAnd(&s_sb[v0 >> 5], ~(1u << (v0 & 31)));
-                if (kind >= 0) st_cg(sid + p, ra);  // P3 looks the input-side flip up through this id
+                if (kind >= 0) st_cg_pol(sid + p, ra, pol_stream);  // P3 looks the input-side flip up through this id
                 if (kind == KIND_BOND && ra != rb) {
-                    const uint32_t root = uf_union_cg(P, ra, rb);
+                    const uint32_t root = uf_union_pol(P, ra, rb, pol_keep);
                     if (fa) atomicCAS(&s_rep[v0], oa, root);  // cache the root: equal roots skip the union
                     if (fb) atomicCAS(&s_rep[v1], ob, root);
                 }
@@ -296,7 +294,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                     atomicOr(&frz[ra >> 5], 1u << (ra & 31));
                     anylong = true;
                 }
-                if (kind == KIND_SITE) atomicMax(&s_rep[v0], myid);  // the site op with the highest lane owns the variable from here on
+                if (kind == KIND_SITE) atomicMax(&s_rep[v0], myid);  // the site op with the highest lane owns the variable from here on (roots are minima: a cached root is below every id of this step)
                 nsite += (uint32_t)__popc(smask);
                 if (!alltb && (it & 31u) == 31u) {  // once every variable has an op the touched bits need no more updates
                     uint32_t cnt = 0;
@@ -340,33 +338,56 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                 }
             }
             // =========================== P2: one flip bit per segment ===========================
+            // ascending ids (parent id < child id).  Four words (= one Philox block of flip bits) per round: their parents
+            // are loaded together, then the decisions of parents from earlier rounds, and only the parents inside the round
+            // are resolved in order -- two dependent L2 round trips per four words instead of two per word.
             uint32_t nroots = 0;
-            Philox4 rb4 = {0, 0, 0, 0};
-            for (uint32_t wd = 0; wd < nwords; wd++) {
-                const uint32_t x = wd * 32 + lane;
-                if ((wd & 3u) == 0) rb4 = philox4x32_10(wd >> 2, (uint32_t)c0, (uint32_t)(c0 >> 32), QMCB_TAG_CLUS, k0, k1);
-                const uint32_t rword = (wd & 3u) == 0 ? rb4.x : ((wd & 3u) == 1 ? rb4.y : ((wd & 3u) == 2 ? rb4.z : rb4.w));
-                uint32_t par = x < nseg ? ld_cg(P + x) : x;
-                if (nsite == 0) par = x < nseg ? 0u : x;  // cluster.rs:98-107: no cluster edge => one cluster
-                const bool root = x < nseg && par == x;
-                nroots += (uint32_t)__popc(__ballot_sync(FULL, root));
-                bool dec = false, known = root || x >= nseg;
-                if (root) {
-                    dec = (rword >> lane) & 1u;
-                    if (HAS_H) dec = dec && !((nsite == 0) ? frozen_all : ((ld_cg(frz + wd) >> lane) & 1u));
-                } else if (x < nseg && par < wd * 32) {
-                    dec = (ld_cg(decb + (par >> 5)) >> (par & 31)) & 1u;
-                    known = true;
+            const uint32_t nblk = (nwords + 3) >> 2;
+            for (uint32_t blk = 0; blk < nblk; blk++) {
+                const uint32_t wbot = blk * 4;
+                uint32_t par4[4], dw4[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t x = (wbot + j) * 32 + lane;
+                    par4[j] = x < nseg ? ld_cg(P + x) : x;
+                    if (nsite == 0 && x < nseg) par4[j] = 0u;  // cluster.rs:98-107: no cluster edge => one cluster
                 }
-                for (;;) {  // parents inside this word: resolve by rounds (parent id < child id)
-                    const uint32_t kmask = __ballot_sync(FULL, known), dmask = __ballot_sync(FULL, dec);
-                    if (kmask == FULL) {
-                        if (lane == 0) st_cg(decb + wd, dmask);
-                        break;
+                const uint32_t lo_edge = wbot * 32u;  // ids < lo_edge were decided in earlier rounds
+#pragma unroll
+                for (int j = 0; j < 4; j++) dw4[j] = par4[j] < lo_edge ? ld_cg(decb + (par4[j] >> 5)) : 0u;
+                const Philox4 rb4 = philox4x32_10(blk, (uint32_t)c0, (uint32_t)(c0 >> 32), QMCB_TAG_CLUS, k0, k1);
+                uint32_t out4[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t wd = wbot + j;
+                    const uint32_t x = wd * 32 + lane, par = par4[j];
+                    const uint32_t rword = j == 0 ? rb4.x : (j == 1 ? rb4.y : (j == 2 ? rb4.z : rb4.w));
+                    const bool root = x < nseg && par == x;
+                    nroots += (uint32_t)__popc(__ballot_sync(FULL, root));
+                    bool dec = false, known = root || x >= nseg;
+                    if (root) {
+                        dec = (rword >> lane) & 1u;
+                        if (HAS_H) dec = dec && !((nsite == 0) ? frozen_all : ((ld_cg(frz + wd) >> lane) & 1u));
+                    } else if (x < nseg && par < lo_edge) {
+                        dec = (dw4[j] >> (par & 31)) & 1u;
+                        known = true;
+                    } else if (x < nseg && (par >> 5) < wd) {  // parent in an earlier word of this round
+                        const uint32_t jj = (par >> 5) - wbot;
+                        const uint32_t pw = jj == 0 ? out4[0] : (jj == 1 ? out4[1] : out4[2]);
+                        dec = (pw >> (par & 31)) & 1u;
+                        known = true;
                     }
-                    if (!known) {
-                        const uint32_t pl = par - wd * 32;
-                        if ((kmask >> pl) & 1u) dec = (dmask >> pl) & 1u, known = true;
+                    for (;;) {  // parents inside this word: resolve by rounds
+                        const uint32_t kmask = __ballot_sync(FULL, known), dmask = __ballot_sync(FULL, dec);
+                        if (kmask == FULL) {
+                            out4[j] = dmask;
+                            if (lane == 0 && wd < nwords) st_cg(decb + wd, dmask);
+                            break;
+                        }
+                        if (!known) {
+                            const uint32_t pl = par - wd * 32;
+                            if ((kmask >> pl) & 1u) dec = (dmask >> pl) & 1u, known = true;
+                        }
                     }
                 }
                 __syncwarp();
@@ -384,39 +405,53 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
             // =========================== P3: apply the flips (stateless) ===========================
             uint32_t ks = 0;
             const uint32_t EN = E + N;
+            // software pipeline: the op words and records of the next four lines are requested before the flip bits of the
+            // current four are looked up, so one iteration waits for one round trip (the gathers), not three
+            uint32_t wN[4], sN[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t p = 32u * j + lane;
+                wN[j] = p < M ? ld_cg_pol(ops + p, pol_stream) : OP_EMPTY;
+                sN[j] = p < M ? ld_cg_pol(sid + p, pol_stream) : 0u;
+            }
             for (uint32_t base = 0; base < M; base += 128) {
-                uint32_t w4[4], s4[4], sm4[4];
+                uint32_t w4[4], s4[4], sm4[4], di4[4], do4[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) w4[j] = wN[j], s4[j] = sN[j];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const uint32_t p = base + 32u * j + lane;
-                    w4[j] = p < M ? ld_cg(ops + p) : OP_EMPTY;
+                    const uint32_t p = base + 128u + 32u * j + lane;
+                    wN[j] = p < M ? ld_cg_pol(ops + p, pol_stream) : OP_EMPTY;
+                    sN[j] = p < M ? ld_cg_pol(sid + p, pol_stream) : 0u;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const uint32_t p = base + 32u * j + lane;
-                    s4[j] = w4[j] != OP_EMPTY ? ld_cg(sid + p) : 0u;
                     const uint32_t b = op_bond(w4[j]);
                     sm4[j] = __ballot_sync(FULL, w4[j] != OP_EMPTY && b >= E && b < EN);
+                }
+                // every flip-bit word this iteration needs is requested before any is used (the stores below could
+                // alias them as far as the compiler knows, so the order is written out by hand)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool site = (sm4[j] >> lane) & 1u;
+                    const uint32_t id = N + ks + (uint32_t)__popc(sm4[j] & lt_mask);
+                    di4[j] = w4[j] != OP_EMPTY ? ld_cg(decb + (s4[j] >> 5)) : 0u;
+                    do4[j] = site ? ld_cg(decb + (id >> 5)) : 0u;
+                    s4[j] = (s4[j] & 31u) | ((id & 31u) << 8) | (site ? 0x10000u : 0u);
+                    ks += (uint32_t)__popc(sm4[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const uint32_t p = base + 32u * j + lane, w = w4[j];
                     if (w != OP_EMPTY) {
                         const uint32_t b = op_bond(w);
-                        const bool site = (sm4[j] >> lane) & 1u;
-                        const uint32_t si = s4[j];
-                        const bool din = (ld_cg(decb + (si >> 5)) >> (si & 31)) & 1u;
-                        bool dout = din;
-                        if (site) {
-                            const uint32_t id = N + ks + (uint32_t)__popc(sm4[j] & lt_mask);
-                            dout = (ld_cg(decb + (id >> 5)) >> (id & 31)) & 1u;
-                        }
+                        const bool din = (di4[j] >> (s4[j] & 31u)) & 1u;
+                        const bool dout = (s4[j] & 0x10000u) ? ((do4[j] >> ((s4[j] >> 8) & 31u)) & 1u) : din;
                         if (din || dout) {
                             const uint32_t mask = b < E ? 3u : 1u;
-                            st_cg(ops + p, make_op(b, op_in(w) ^ (din ? mask : 0u), op_out(w) ^ (dout ? mask : 0u)));
+                            st_cg_pol(ops + p, make_op(b, op_in(w) ^ (din ? mask : 0u), op_out(w) ^ (dout ? mask : 0u)), pol_stream);
                         }
                     }
-                    ks += (uint32_t)__popc(sm4[j]);
                 }
             }
             // spins: the segment of variable v crossing p = 0 has id v

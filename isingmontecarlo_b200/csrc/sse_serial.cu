@@ -540,7 +540,7 @@ __device__ __forceinline__ bool fast_flip_bit(uint64_t key, uint64_t c0, uint32_
     return (x >> (root & 31)) & 1u;
 }
 
-__device__ uint32_t cluster_fast_serial(const SseDev &D, uint32_t r, const Rep &V, int lane) {
+__device__ uint32_t cluster_fast_serial(const SseDev &D, uint32_t r, const Rep &V, int lane, bool maxroot) {
     const uint32_t n = D.n[r];
     if (n == 0) return 0;
     uint32_t ncl = 0;
@@ -559,18 +559,22 @@ __device__ uint32_t cluster_fast_serial(const SseDev &D, uint32_t r, const Rep &
                 V.cur[b - E] = id;
             } else if (b < E) {
                 uint32_t x = uf_find(uf, V.cur[__ldg(D.va + b)]), y = uf_find(uf, V.cur[__ldg(D.vb + b)]);
-                if (x < y) uf[y] = x;
-                else if (y < x) uf[x] = y;
+                if (x != y) {
+                    if ((x < y) != maxroot) uf[y] = x;
+                    else uf[x] = y;
+                }
             }
         }
         for (uint32_t v = 0; v < N; v++) {
             uint32_t x = uf_find(uf, v), y = uf_find(uf, V.cur[v]);
-            if (x < y) uf[y] = x;
-            else if (y < x) uf[x] = y;
+            if (x != y) {
+                if ((x < y) != maxroot) uf[y] = x;
+                else uf[x] = y;
+            }
         }
         const uint32_t nseg = N + nsite, nw = (nseg + 31) / 32;
         if (nsite == 0)
-            for (uint32_t x = 0; x < nseg; x++) uf[x] = 0;
+            for (uint32_t x = 0; x < nseg; x++) uf[x] = maxroot ? nseg - 1 : 0;
         // frozen roots, used roots
         for (uint32_t j = 0; j < nw; j++) V.frozen[j] = 0, V.bits[j] = 0;
         for (uint32_t v = 0; v < N; v++) V.cur[v] = v;
@@ -683,7 +687,7 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
                 if (lane == 0) links_serial(D, r, V, mode == 0);
                 __syncwarp();
             }
-            uint32_t ncl = mode == 0 ? cluster_strict(D, r, V, lane) : cluster_fast_serial(D, r, V, lane);
+            uint32_t ncl = mode == 0 ? cluster_strict(D, r, V, lane) : cluster_fast_serial(D, r, V, lane, false);
             if (lane == 0) D.ncl[r] = ncl;
             free_spins(D, r, V, lane);
         }

@@ -8,6 +8,27 @@
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ void st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
 
+// L2 eviction policies (createpolicy, carried in the load/store descriptor): the operator string and the per-slot
+// records stream through once per pass (evict first); the union-find parents are revisited (evict last)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ld_cg_pol(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cg_pol(uint32_t *p, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 // lock-free union-find over global memory; roots are minima, parent[x] <= x always
 __device__ __forceinline__ uint32_t uf_find_cg(uint32_t *P, uint32_t x) {
     uint32_t p = ld_cg(P + x);
@@ -23,7 +44,8 @@ __device__ __forceinline__ uint32_t uf_find_cg(uint32_t *P, uint32_t x) {
 // The kernel is bound by the latency of dependent loads, so both chains are climbed in lockstep: the two parent
 // loads of a round are in flight together (one L2 round trip per level instead of two).  The start nodes are
 // pointed at the root they reached (compression of the nodes that are looked up again: S.rep entries).
-__device__ __forceinline__ uint32_t uf_union_cg(uint32_t *P, uint32_t a, uint32_t b) {
+template <bool MAXROOT>
+__device__ __forceinline__ uint32_t uf_union_dir(uint32_t *P, uint32_t a, uint32_t b) {
     for (;;) {
         const uint32_t a0 = a, b0 = b;
         uint32_t pa = ld_cg(P + a), pb = ld_cg(P + b);
@@ -35,7 +57,32 @@ __device__ __forceinline__ uint32_t uf_union_cg(uint32_t *P, uint32_t a, uint32_
         if (pa0 != a) st_cg(P + a0, a);  // a stale value is still an ancestor
         if (pb0 != b) st_cg(P + b0, b);
         if (a == b) return a;
-        if (a > b) {
+        if (MAXROOT ? a < b : a > b) {  // b is hooked under a
+            uint32_t t = a;
+            a = b, b = t;
+        }
+        if (atomicCAS(P + b, b, a) == b) return a;
+    }
+}
+// roots are minima (FAST contract: a cluster is keyed by its smallest segment id)
+__device__ __forceinline__ uint32_t uf_union_cg(uint32_t *P, uint32_t a, uint32_t b) { return uf_union_dir<false>(P, a, b); }
+// roots are maxima: measured and dropped (profiles/README.md, round 2): a maximum changes whenever a newer segment joins
+// the cluster, so cached roots go stale and the climbs get longer (2.5 parent loads per step instead of 0.6)
+__device__ __forceinline__ uint32_t uf_union_max(uint32_t *P, uint32_t a, uint32_t b) { return uf_union_dir<true>(P, a, b); }
+// min-root union with an L2 eviction policy on the parent loads / stores
+__device__ __forceinline__ uint32_t uf_union_pol(uint32_t *P, uint32_t a, uint32_t b, uint64_t pol) {
+    for (;;) {
+        const uint32_t a0 = a, b0 = b;
+        uint32_t pa = ld_cg_pol(P + a, pol), pb = ld_cg_pol(P + b, pol);
+        const uint32_t pa0 = pa, pb0 = pb;
+        while (pa != a || pb != b) {
+            a = pa, b = pb;
+            pa = ld_cg_pol(P + a, pol), pb = ld_cg_pol(P + b, pol);
+        }
+        if (pa0 != a) st_cg_pol(P + a0, a, pol);
+        if (pb0 != b) st_cg_pol(P + b0, b, pol);
+        if (a == b) return a;
+        if (a > b) {  // b is hooked under a: roots are minima
             uint32_t t = a;
             a = b, b = t;
         }
@@ -61,6 +108,13 @@ __device__ __forceinline__ void fetch_line(uint32_t *line_smem, const uint32_t *
     if (lane < 8) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(line_smem + 4 * lane);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * lane) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void fetch_line_pol(uint32_t *line_smem, const uint32_t *src, int lane, uint64_t pol) {
+    if (lane < 8) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(line_smem + 4 * lane);
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + 4 * lane), "l"(pol) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }

@@ -797,7 +797,8 @@ static uint64_t cluster_update_strict(OrcSse *g, int has_weights) {
  *     starts at the output of the k-th site op (p order).
  *   * every two-variable op joins the two segments it touches; the segment after the last
  *     site op of v is joined with segment v (periodic closure).
- *   * cluster root = smallest segment id.  No site op at all => one cluster (cluster.rs:98-107).
+ *   * cluster root = smallest segment id, in FAST and COUNTER mode (a largest-id contract was tried for the GPU's
+ *     cache behaviour and dropped; uf_union keeps the switch).  No site op at all => one cluster (cluster.rs:98-107).
  *   * a cluster holding a longitudinal op never flips (weight 0, qmc_ising.rs:759-775);
  *     otherwise flip = bit (root & 127) of Philox(key, ctr = (root >> 7, c_lo, c_hi, 'CLUS')),
  *     c = stream cursor at the start of the step; the step then advances the cursor by 1.
@@ -811,10 +812,12 @@ static uint32_t uf_find(uint32_t *uf, uint32_t x) {
     }
     return x;
 }
-static void uf_union(uint32_t *uf, uint32_t a, uint32_t b) {
+/* maxroot = 0: the root of a set is its smallest id (FAST contract); 1: its largest id (COUNTER contract) */
+static void uf_union(uint32_t *uf, uint32_t a, uint32_t b, int maxroot) {
     a = uf_find(uf, a), b = uf_find(uf, b);
-    if (a < b) uf[b] = a;
-    else if (b < a) uf[a] = b;
+    if (a == b) return;
+    if ((a < b) != (maxroot != 0)) uf[b] = a;
+    else uf[a] = b;
 }
 
 static int fast_flip_bit(uint64_t key, uint64_t cursor, uint32_t root) {
@@ -825,7 +828,7 @@ static int fast_flip_bit(uint64_t key, uint64_t cursor, uint32_t root) {
     return (x[(root >> 5) & 3] >> (root & 31)) & 1u;
 }
 
-static uint64_t cluster_update_fast(OrcSse *g, int has_weights) {
+static uint64_t cluster_update_fast(OrcSse *g, int has_weights, int maxroot) {
     if (g->n == 0) return 0;
     const uint32_t N = g->nvars;
     const int64_t last_p = g->last_p;
@@ -852,13 +855,13 @@ static uint64_t cluster_update_fast(OrcSse *g, int has_weights) {
             g->b_out[p] = id;
         } else {
             g->b_in[p] = g->b_out[p] = cur[nd->vars[0]];
-            if (nd->nv == 2) uf_union(uf, cur[nd->vars[0]], cur[nd->vars[1]]);
+            if (nd->nv == 2) uf_union(uf, cur[nd->vars[0]], cur[nd->vars[1]], maxroot);
         }
     }
-    for (uint32_t v = 0; v < N; v++) uf_union(uf, v, cur[v]); /* periodic closure */
+    for (uint32_t v = 0; v < N; v++) uf_union(uf, v, cur[v], maxroot); /* periodic closure */
     const uint32_t nseg = N + nsite;
     if (nsite == 0) /* cluster.rs:98-107: no cluster edge => everything is one cluster */
-        for (uint32_t x = 0; x < nseg; x++) uf[x] = 0;
+        for (uint32_t x = 0; x < nseg; x++) uf[x] = maxroot ? nseg - 1 : 0;
     /* frozen clusters + cluster count (roots that own at least one leg) */
     uint8_t *frozen = (uint8_t *)calloc(nseg, 1), *used = (uint8_t *)calloc(nseg, 1);
     for (int64_t p = 0; p <= last_p; p++) {
@@ -895,7 +898,7 @@ static uint64_t cluster_update_fast(OrcSse *g, int has_weights) {
 /* single_cluster_step qmc_ising.rs:273-320 / timestep :754-784 */
 static uint64_t cluster_and_free_spins(OrcSse *g, int mode) {
     int has_weights = fabs(g->longitudinal) > DBL_EPSILON;
-    uint64_t ncl = mode != ORC_MODE_STRICT ? cluster_update_fast(g, has_weights)
+    uint64_t ncl = mode != ORC_MODE_STRICT ? cluster_update_fast(g, has_weights, 0)
                                          : cluster_update_strict(g, has_weights);
     for (uint32_t v = 0; v < g->nvars; v++) /* qmc_ising.rs:780-784 */
         if (g->vfirst_p[v] == NONE) g->state[v] = (uint8_t)gen_bool(&g->rng, 0.5);
