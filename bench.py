@@ -141,6 +141,12 @@ def sum_over_ranks(x, world):
 # ---------------------------------------------------------------------------------------------
 # SSE arm (ours)
 # ---------------------------------------------------------------------------------------------
+def sse_mode(args):
+    from isingmontecarlo_b200 import MODE_COUNTER, MODE_FAST
+
+    return (MODE_COUNTER, "COUNTER") if args.sse_mode == "counter" else (MODE_FAST, "FAST")
+
+
 def survey_bytes(sum_n, sum_m):
     """B_sweep = 8 M + 60 n bytes per replica and sweep (compact formats with materialised links)."""
     return 8.0 * sum_m + 60.0 * sum_n
@@ -224,13 +230,14 @@ def bench_sse(args, world, rank, local):
     from isingmontecarlo_b200 import MODE_FAST, MODE_STRICT, lattices
     from isingmontecarlo_b200.sse import QmcIsingGraph
 
+    mode, mode_name = sse_mode(args)
     c = dict(SSE)
     if args.sse_replicas:
         c["replicas"] = args.sse_replicas
     edges = lattices.square_periodic(c["L"], c["J"])
     R = c["replicas"]
     keys = c["key0"] + rank * R + np.arange(R, dtype=np.uint64)
-    g = QmcIsingGraph(edges, c["gamma"], c["h"], c["cutoff0"], keys, c["beta"], device=local, mode=MODE_FAST)
+    g = QmcIsingGraph(edges, c["gamma"], c["h"], c["cutoff0"], keys, c["beta"], device=local, mode=mode)
     stream = torch.cuda.Stream()  # a real (non-default) stream so that torch.cuda.Event sees the kernels
     torch.cuda.set_stream(stream)
     g.set_stream(stream.cuda_stream)
@@ -241,14 +248,28 @@ def bench_sse(args, world, rank, local):
         g.enqueue_sweeps(1)
     g.synchronize()
 
-    out = timed_sse_steps(g, lambda: g.enqueue_sweeps(1), args.steps, world, local, "k_sse_fast", "k_sse_fast")
+    kern = "k_sse_counter" if mode_name == "COUNTER" else "k_sse_fast"
+    out = timed_sse_steps(g, lambda: g.enqueue_sweeps(1), args.steps, world, local, kern, kern)
     out["e2e"] = e2e_timesteps_sample(g, c["beta"], max(3, min(args.steps, 10)), world)
+    out["mode"] = mode_name
     out.update({"therm_s": therm_s, "n_mean": out["mean_n"], "cutoff_mean": out["mean_cutoff"], "handle": g, "config": c})
     m_over_n = out["mean_cutoff"] / out["mean_n"]
     rf = out["roofline"]
-    rf["bytes_per_unit_this_layout"] = 16.0 * m_over_n + 8.0  # 2 passes x (4 B read + 4 B write) per slot + ~8 B/vertex union-find
+    # this layout: 2 passes x (4 B read + 4 B write) per slot + ~8 B/vertex union-find (+ 8 B/vertex of sid records in COUNTER mode)
+    rf["bytes_per_unit_this_layout"] = 16.0 * m_over_n + (16.0 if mode_name == "COUNTER" else 8.0)
     rf["achieved_this_layout"] = rf["achieved"] * rf["bytes_per_unit_this_layout"] / rf["bytes_per_unit"]
 
+    # ---- the round-1 FAST contract (sequential-stream diagonal update = the reference's, FAST cluster order) on the same replicas
+    if mode_name == "COUNTER" and args.fast_sweeps > 0:
+        g.set_mode(MODE_FAST)
+        g.enqueue_sweeps(2)
+        g.synchronize()
+        ft = timed_sse_steps(g, lambda: g.enqueue_sweeps(1), args.fast_sweeps, world, local, "k_sse_fast", "k_sse_fast")
+        ft["e2e"] = e2e_timesteps_sample(g, c["beta"], 3, world)
+        ft["note"] = "QMCB_MODE_FAST: the reference's diagonal update under the sequential stream, FAST cluster order; same replicas"
+        ft["steps"] = args.fast_sweeps
+        out["fast"] = ft
+        g.set_mode(mode)
     # ---- STRICT (reference-order, bit-exact with the reference's update path): a measured path of its own
     if args.strict_sweeps > 0:
         try:
@@ -261,12 +282,13 @@ def bench_sse(args, world, rank, local):
             st["note"] = "QMCB_MODE_STRICT: reference cluster numbering (cluster.rs:57-97), sequential draws; same replicas as the FAST line"
             st["steps"] = args.strict_sweeps
             out["strict"] = st
-            g.set_mode(MODE_FAST)
+            g.set_mode(mode)
         except Exception as ex:  # e.g. out of memory for the link workspace
             out["strict"] = {"error": str(ex)[:200]}
-            g.set_mode(MODE_FAST)
+            g.set_mode(mode)
     # ---- heat-bath diagonal update (the reference's two_d_heatbath benches) sample
     if args.heatbath_sweeps > 0 and world == 1:
+        g.set_mode(MODE_FAST)  # the heat-bath rule has no COUNTER-mode contract
         g.set_enable_heatbath(True)
         g.enqueue_sweeps(1)
         g.synchronize()
@@ -279,6 +301,7 @@ def bench_sse(args, world, rank, local):
         out["heatbath"] = {"value": (g.total_vertex_updates() - vu3) / (e0.elapsed_time(e1) * 1e-3), "unit": "vertex_updates/s",
                            "sweeps": args.heatbath_sweeps, "note": "set_enable_heatbath(true): heatbath.rs:149-209 diagonal rule, FAST cluster order"}
         g.set_enable_heatbath(False)
+        g.set_mode(mode)
     return out
 
 
@@ -439,7 +462,8 @@ def bench_pt(args, world, rank, local):
     edges = lattices.square_periodic(L, -1.0)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    tc = TemperingContainer(edges, 3.04, 0.0, L * L, betas, n_chains=n_chains, pt_key=0x9E37, mode=MODE_FAST, device=local)
+    mode, mode_name = sse_mode(args)
+    tc = TemperingContainer(edges, 3.04, 0.0, L * L, betas, n_chains=n_chains, pt_key=0x9E37, mode=mode, device=local)
     g = tc.graph
     g.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()
@@ -456,7 +480,8 @@ def bench_pt(args, world, rank, local):
         step()
     g.synchronize()
     sw0 = tc.get_total_swaps()
-    out = timed_sse_steps(g, step, args.pt_steps, world, local, "k_sse_fast (+ k_pt_export, ncclAllGather, k_pt_apply)")
+    out = timed_sse_steps(g, step, args.pt_steps, world, local, ("k_sse_counter" if mode_name == "COUNTER" else "k_sse_fast") + " (+ k_pt_export, ncclAllGather, k_pt_apply)")
+    out["mode"] = mode_name
     swaps_timed = tc.get_total_swaps() - sw0
     # e2e: the container's public call, energies per slot and one sampled state per slot back on the host
     k2 = max(2, min(args.pt_steps, 4))
@@ -506,7 +531,8 @@ def bench_cfg5(args, world, rank, local):
     L, R = c["L"], c["replicas"]
     edges = lattices.triangular_periodic(L, c["J"])
     keys = c["key0"] + rank * R + np.arange(R, dtype=np.uint64)
-    g = QmcIsingGraph(edges, c["gamma"], c["h"], L * L, keys, c["beta"], device=local, mode=MODE_FAST)
+    mode, mode_name = sse_mode(args)
+    g = QmcIsingGraph(edges, c["gamma"], c["h"], L * L, keys, c["beta"], device=local, mode=mode)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     g.set_stream(stream.cuda_stream)
@@ -516,12 +542,13 @@ def bench_cfg5(args, world, rank, local):
     for _ in range(max(args.warmup, 3)):
         g.enqueue_sweeps(1)
     g.synchronize()
-    out = timed_sse_steps(g, lambda: g.enqueue_sweeps(1), args.cfg5_steps, world, local, "k_sse_fast (longitudinal build)")
+    out = timed_sse_steps(g, lambda: g.enqueue_sweeps(1), args.cfg5_steps, world, local, ("k_sse_counter" if mode_name == "COUNTER" else "k_sse_fast") + " (longitudinal build)")
+    out["mode"] = mode_name
     out["e2e"] = e2e_timesteps_sample(g, c["beta"], 3, world)
     out.update({"metric": "sse_vertex_updates_per_sec", "steps": args.cfg5_steps, "therm_s": therm_s,
                 "verify_sampled_replicas": bool(all(g.verify(r) for r in range(0, R, max(1, R // 8)))),
                 "config": {"workload": f"SSE TFIM triangular L={L} J={c['J']} Gamma={c['gamma']} h={c['h']} beta={c['beta']} (BASELINE config #5), "
-                                       f"{R} replicas/GPU, diagonal + cluster update, FAST cluster order", "replicas_per_gpu": R,
+                                       f"{R} replicas/GPU, diagonal + cluster update, QMCB_MODE_{mode_name}", "replicas_per_gpu": R,
                            "thermalisation_sweeps": args.cfg5_therm, "capacity": int(g.get_capacity()), "parallelism": f"replicas x{world}"}})
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import pyoracle as po
@@ -589,6 +616,9 @@ def main():
     ap.add_argument("--cfg5-steps", type=int, default=10)
     ap.add_argument("--therm", type=int, default=120, help="untimed SSE thermalisation sweeps (GPU arm)")
     ap.add_argument("--ref-therm", type=int, default=80, help="untimed thermalisation sweeps of the CPU arm")
+    ap.add_argument("--sse-mode", default="counter", choices=["counter", "fast"],
+                    help="cluster/draw contract of the SSE lines: counter = QMCB_MODE_COUNTER (default), fast = QMCB_MODE_FAST (round-1 headline)")
+    ap.add_argument("--fast-sweeps", type=int, default=10, help="timed sweeps of the nested FAST-mode object (COUNTER runs)")
     ap.add_argument("--strict-sweeps", type=int, default=20)
     ap.add_argument("--heatbath-sweeps", type=int, default=3)
     ap.add_argument("--sse-replicas", type=int, default=0)
@@ -612,11 +642,12 @@ def main():
         g, c = s.pop("handle"), s.pop("config")
         line.update({k: s[k] for k in ("value", "ms_per_step", "gpu_launches", "e2e", "roofline", "clocks", "slots_per_s")})
         line["config"] = {"workload": f"SSE TFIM 2D square L={c['L']} J={c['J']} Gamma={c['gamma']} beta={c['beta']} "
-                                      f"(BASELINE config #3), {c['replicas']} replicas/GPU, diagonal + cluster update, FAST cluster order",
+                                      f"(BASELINE config #3), {c['replicas']} replicas/GPU, diagonal + cluster update, QMCB_MODE_{s['mode']}",
+                          "mode": s["mode"],
                           "replicas_per_gpu": c["replicas"], "mean_n": s["n_mean"], "mean_cutoff": s["cutoff_mean"],
                           "thermalisation_sweeps": args.therm, "l2": "inputs larger than L2 (operator strings: "
                           f"{c['replicas'] * s['cutoff_mean'] * 4 / 2**30:.1f} GiB per GPU)", "parallelism": f"replicas x{world}"}
-        for extra in ("strict", "heatbath"):
+        for extra in ("fast", "strict", "heatbath"):
             if extra in s:
                 line[extra] = s[extra]
         if rank == 0 and world == 1 and not args.no_cpu_baseline:

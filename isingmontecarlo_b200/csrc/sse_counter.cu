@@ -130,18 +130,19 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
         // =========================== P1: diagonal update + segments + unions ===========================
         if (M) fetch_line_pol(s_line, ops, lane, pol_stream);
         const uint32_t nit = (M + 31) / 32;
+        // the slot's words: one Philox block per slot.  Independent of the operator string, so the block of step k + 1 is
+        // computed at the end of step k, between issuing the step's union-find CAS and looking at its result.
+        uint64_t wA = 0, wB = 0;
+        uint32_t pb = 0;  // proposal of an empty slot: bond by multiply-shift
+        auto draw = [&](uint32_t slot) {
+            const Philox4 o = philox4x32_10(slot, (uint32_t)cdiag, (uint32_t)(cdiag >> 32), QMCB_TAG_DIAG, k0, k1);
+            wA = ((uint64_t)o.y << 32) | o.x, wB = ((uint64_t)o.w << 32) | o.z;
+            pb = (uint32_t)__umul64hi(wA, (uint64_t)Nb);
+        };
+        if (do_diag) draw((uint32_t)lane);
         for (uint32_t it = 0; it < nit; it++) {
             const uint32_t base = it * 32, p = base + lane;
             const bool valid = p < M;
-            // the slot's words: one Philox block per slot.  Independent of the operator string, so it is computed while
-            // the line is still on its way.
-            uint64_t wA = 0, wB = 0;
-            uint32_t pb = 0;
-            if (do_diag) {
-                const Philox4 o = philox4x32_10(p, (uint32_t)cdiag, (uint32_t)(cdiag >> 32), QMCB_TAG_DIAG, k0, k1);
-                wA = ((uint64_t)o.y << 32) | o.x, wB = ((uint64_t)o.w << 32) | o.z;
-                pb = (uint32_t)__umul64hi(wA, (uint64_t)Nb);  // proposal of an empty slot: bond by multiply-shift
-            }
             uint32_t w = take_line(s_line, lane);
             if (!valid) w = OP_EMPTY;
             if (base + 32 < M) fetch_line_pol(s_line, ops + base + 32, lane, pol_stream);
@@ -151,9 +152,18 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
             int kind = bkind<HAS_H>(D, beff);
             uint32_t v0, v1, neww = w;
             const uint32_t ee = evars(beff, kind, v0, v1);
+            uint32_t fmask = 0, flipv = NONE32;  // off-diagonal ops of this step; the variable mine flips
+            bool changed = false;
+#ifdef QMCB_PREFETCH_PARENTS
+            if (do_clus && w != OP_EMPTY && kind == KIND_BOND) {  // experiment: the parents the union stage will ask for, into L2
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P + s_rep[v0]));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P + s_rep[v1]));
+            }
+#endif
             if (do_diag) {
                 const bool offd = type == T_OFFD;
-                const uint32_t fmask = __ballot_sync(FULL, offd);
+                fmask = __ballot_sync(FULL, offd);
+                if (offd) flipv = v0;
                 if (fmask) {  // off-diagonal ops flip their variable for the later lanes of this step
                     s_fl[lane] = offd ? v0 : NONE32;
                     if (offd) atomicOr(&s_cd[v0 >> 5], 1u << (v0 & 31));
@@ -242,15 +252,19 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                     const uint32_t pbits = s0 | (s1 << 1);
                     neww = make_op(beff, pbits, pbits);
                 } else if (dec == -1) neww = OP_EMPTY;
-                if (insm | remm) {
-                    if (neww != w) st_cg_pol(ops + p, neww, pol_stream);
-                }
-                if (fmask) {
-                    if (offd) atomicXor(&s_st[v0 >> 5], 1u << (v0 & 31)), atomicAnd(&s_cd[v0 >> 5], ~(1u << (v0 & 31)));
-                    __syncwarp();
-                }
+                changed = neww != w;
             }
             if (neww == OP_EMPTY) kind = -1;  // no op in this slot after the diagonal update
+            // what is left of the diagonal step (store, state flips) and the words of the next step do not depend on the
+            // union-find: they run between the CAS and the look at its result
+            auto step_tail = [&]() {
+                if (changed) st_cg_pol(ops + p, neww, pol_stream);
+                if (fmask) {
+                    if (flipv != NONE32) atomicXor(&s_st[flipv >> 5], 1u << (flipv & 31)), atomicAnd(&s_cd[flipv >> 5], ~(1u << (flipv & 31)));
+                    __syncwarp();
+                }
+                if (do_diag && it + 1 < nit) draw(base + 32u + (uint32_t)lane);
+            };
             if (do_clus) {
                 // ---- segments and unions on the final ops of this step
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
@@ -285,16 +299,37 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                 __syncwarp();  // new ids are initialised before anyone follows them; bitmap reads are done
                 if (kind == KIND_SITE) atomicAnd(&s_sb[v0 >> 5], ~(1u << (v0 & 31)));
                 if (kind >= 0) st_cg_pol(sid + p, ra, pol_stream);  // P3 looks the input-side flip up through this id
+                uint32_t ua = 0, ub = 0, uold = 0;
+                bool casd = false;
                 if (kind == KIND_BOND && ra != rb) {
-                    const uint32_t root = uf_union_pol(P, ra, rb, pol_keep);
-                    if (fa) atomicCAS(&s_rep[v0], oa, root);  // cache the root: equal roots skip the union
-                    if (fb) atomicCAS(&s_rep[v1], ob, root);
+                    // lock-free min-root union (sse_warp.cuh uf_union_pol), split: climb, hook with a CAS -- and look at
+                    // the CAS result only after the independent tail of the step (a lost race is redone there)
+                    uint32_t a = ra, b = rb;
+                    uint32_t pa = ld_cg_pol(P + a, pol_keep), pq = ld_cg_pol(P + b, pol_keep);
+                    const uint32_t pa0 = pa, pq0 = pq;
+                    while (pa != a || pq != b) {
+                        a = pa, b = pq;
+                        pa = ld_cg_pol(P + a, pol_keep), pq = ld_cg_pol(P + b, pol_keep);
+                    }
+                    if (pa0 != a) st_cg_pol(P + ra, a, pol_keep);  // a stale value is still an ancestor
+                    if (pq0 != b) st_cg_pol(P + rb, b, pol_keep);
+                    if (a != b) {
+                        if (a > b) {
+                            const uint32_t t = a;
+                            a = b, b = t;
+                        }
+                        uold = atomicCAS(P + b, b, a), casd = true, ua = a, ub = b;
+                    }
+                    if (fa) atomicCAS(&s_rep[v0], oa, a);  // cache the root: equal roots skip the union
+                    if (fb) atomicCAS(&s_rep[v1], ob, a);
                 }
                 if (HAS_H && kind == KIND_LONG) {
                     atomicOr(&frz[ra >> 5], 1u << (ra & 31));
                     anylong = true;
                 }
                 if (kind == KIND_SITE) atomicMax(&s_rep[v0], myid);  // the site op with the highest lane owns the variable from here on (roots are minima: a cached root is below every id of this step)
+                step_tail();
+                if (casd && uold != ub) uf_union_pol(P, ua, ub, pol_keep);  // lost a race against a lane of this step: redo
                 nsite += (uint32_t)__popc(smask);
                 if (!alltb && (it & 31u) == 31u) {  // once every variable has an op the touched bits need no more updates
                     uint32_t cnt = 0;
@@ -302,7 +337,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                     alltb = __reduce_add_sync(FULL, cnt) == N;
                 }
                 __syncwarp();
-            }
+            } else step_tail();
         }
         if (do_diag && lane == 0) D.n[r] = n;
 
