@@ -28,8 +28,17 @@
 #define CT_NUM 0      // [36] f64: beta * Nb * <s|H_b|s> per weight class (2 * coupling code + (s0 != s1); 32 site; 33 + s long)
 #define CT_RNUM 288   // [36] f64: 1 / num
 #define CT_FL 576     // [32] u32: variable flipped by the off-diagonal op of lane j
-#define CT_LINE 704   // [32] u32: next line of the operator string (cp.async)
+// staging of the operator string: QMCB_BULK_LINES = 0: one 128-byte line ahead, copied by cp.async (8 lanes x 16 B);
+// L > 0: tiles of L lines copied by ONE cp.async.bulk (TMA) into a two-stage ring, completion on an mbarrier
+#ifndef QMCB_BULK_LINES
+#define QMCB_BULK_LINES 0
+#endif
+#define CT_LINE 704   // [32] u32 next line (cp.async)  |  2 mbarriers + ring [2][L][32] u32 (bulk)
+#if QMCB_BULK_LINES
+#define CT_VAR (704 + 16 + 2 * QMCB_BULK_LINES * 128)
+#else
 #define CT_VAR 832    // st, tb, cd, sb [Nw each], rep [N]
+#endif
 #define CLS_SITE 32u
 #define CLS_LONG 33u
 
@@ -89,6 +98,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     const double G_LO = 1.0 - 9.094947017729282e-13, G_HI = 1.0 + 9.094947017729282e-13;  // 1 -+ 2^-40: guard of the reciprocal bounds
 
+    uint32_t phase_bits = 0;  // bulk staging: parity of the next completion of each stage's mbarrier
     uint64_t done = D.done[r];
     const uint64_t nsteps = (phases & 16u) ? (done + 1 == target ? 1 : 0) : ((phases & 8u) ? (target > done ? target - done : 0) : 1);
     int err = 0;
@@ -128,8 +138,25 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
         if (do_diag) cur += 1;
 
         // =========================== P1: diagonal update + segments + unions ===========================
-        if (M) fetch_line_pol(s_line, ops, lane, pol_stream);
         const uint32_t nit = (M + 31) / 32;
+#if QMCB_BULK_LINES
+        constexpr uint32_t LPS = QMCB_BULK_LINES;
+        uint64_t *const bars = (uint64_t *)(smem_raw + CT_LINE);
+        uint32_t *const ring = (uint32_t *)(smem_raw + CT_LINE + 16);
+        const uint32_t ntile = (nit + LPS - 1) / LPS;
+        auto issue_tile = [&](uint32_t t) {  // lane 0: lines [t * LPS, (t + 1) * LPS) of the string into stage t & 1
+            const uint32_t first = t * LPS, cnt = min(LPS, nit - first);
+            bulk_fetch(ring + (t & 1u) * LPS * 32, ops + (size_t)first * 32, cnt * 128u, bars + (t & 1u), pol_stream);
+        };
+        if (lane == 0) {
+            if (sw == 0) mbar_init(bars, 1), mbar_init(bars + 1, 1), mbar_fence_init();
+            if (ntile > 0) issue_tile(0);
+            if (ntile > 1) issue_tile(1);
+        }
+        __syncwarp();
+#else
+        if (M) fetch_line_pol(s_line, ops, lane, pol_stream);
+#endif
         // the slot's words: one Philox block per slot.  Independent of the operator string, so the block of step k + 1 is
         // computed at the end of step k, between issuing the step's union-find CAS and looking at its result.
         uint64_t wA = 0, wB = 0;
@@ -143,9 +170,23 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
         for (uint32_t it = 0; it < nit; it++) {
             const uint32_t base = it * 32, p = base + lane;
             const bool valid = p < M;
+#if QMCB_BULK_LINES
+            const uint32_t tile = it / LPS, tl = it % LPS;
+            if (tl == 0) {  // the k-th completion of a stage's mbarrier has parity k & 1; the count runs across sweeps
+                mbar_wait(bars + (tile & 1u), (phase_bits >> (tile & 1u)) & 1u);
+                phase_bits ^= 1u << (tile & 1u);
+            }
+            uint32_t w = ring[((tile & 1u) * LPS + tl) * 32 + lane];
+            if (!valid) w = OP_EMPTY;
+            if (tl == LPS - 1 || it + 1 == nit) {  // the stage is consumed: refill it with the tile after next
+                __syncwarp();
+                if (lane == 0 && tile + 2 < ntile) issue_tile(tile + 2);
+            }
+#else
             uint32_t w = take_line(s_line, lane);
             if (!valid) w = OP_EMPTY;
             if (base + 32 < M) fetch_line_pol(s_line, ops + base + 32, lane, pol_stream);
+#endif
             const int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
             // one decode for every lane: the op in the slot, or the op an empty slot proposes
             const uint32_t beff = w == OP_EMPTY ? pb : op_bond(w);

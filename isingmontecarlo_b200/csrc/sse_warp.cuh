@@ -126,6 +126,36 @@ __device__ __forceinline__ uint32_t take_line(const uint32_t *line_smem, int lan
     return w;
 }
 
+// ---- bulk-asynchronous staging of the operator string (TMA bulk copy, no tensor map: the rows are contiguous) -----------
+// One lane issues cp.async.bulk.shared::cluster.global for a tile of several 128-byte lines; completion is signalled on an
+// mbarrier in shared memory (complete_tx), the consumers wait on its phase parity.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_fetch(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the buffer are done before the async proxy overwrites it
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(d), "l"(src),
+                 "r"(bytes), "r"(b), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+
 // lattice helpers specialised on HAS_H: without a longitudinal field there are no KIND_LONG bonds
 template <bool HAS_H>
 __device__ __forceinline__ int bkind(const SseDev &D, uint32_t b) {
