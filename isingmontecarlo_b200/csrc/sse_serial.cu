@@ -356,105 +356,153 @@ __device__ __forceinline__ uint32_t rec_link(const uint4 &lo, const uint4 &hi, u
     return li == 0 ? lo.y : (li == 1 ? lo.z : (li == 2 ? lo.w : hi.x));
 }
 
-__device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err) {
+// The walk itself runs on lane 0; the other lanes join for the unmapped-op scan (cluster.rs:82-88), 32 slots per ballot.
+// The tops of the two LIFO stacks live in shared memory (`stk`: STK_I interior entries, then a window of STK_F frontier
+// entries); what does not fit spills to the global-memory stacks, which keep the exact LIFO order.
+#define STK_I 192
+#define STK_F 128
+__device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err, int lane, uint32_t *stk) {
     const uint32_t last_p = V.ends[1], cp = V.ends[2];
     const uint32_t E = D.E, EN = D.E + D.N;
-    uint64_t flen = 0, ilen = 0;
-    V.frontier[flen++] = (cp << 1) | SIDE_OUT;  // cluster.rs:57-59
-    V.frontier[flen++] = (cp << 1) | SIDE_IN;
-    uint32_t cnum = 0, scan = 0;
-    for (;;) {
-        while (flen) {  // :62-80
-            uint32_t e = V.frontier[--flen];
-            uint32_t p0 = e >> 1, side0 = e & 1u;
-            {
-                const uint4 h0 = ld_rec_hi(V, p0);
-                if (h0.y != NONE32 && h0.z != NONE32) continue;
-            }
-            // ---- expand_whole_cluster(p0, (0, side0), cnum) :193-271
-            {
-                uint32_t b0 = op_bond(REC_OP(V, p0));
-                bool edge0 = b0 >= E && b0 < EN;
-                ilen = 0;
-                if (!edge0) {  // :205-211
-                    int nv = b0 < E ? 2 : 1;
-                    for (int k = 0; k < nv; k++) V.interior[ilen++] = (p0 << 2) | ((uint32_t)k << 1) | SIDE_IN;
-                    for (int k = 0; k < nv; k++) V.interior[ilen++] = (p0 << 2) | ((uint32_t)k << 1) | SIDE_OUT;
-                } else {
-                    V.interior[ilen++] = (p0 << 2) | side0;  // :212-215
-                }
-                while (ilen) {
-                    uint32_t it = V.interior[--ilen];
-                    uint32_t p = it >> 2, rel = (it >> 1) & 1u, side = it & 1u;
-                    const uint4 pl = ld_rec_lo(V, p), ph = ld_rec_hi(V, p);  // one sector: op, links, boundaries
-                    {  // set_boundary(p, side, cnum) :218, :289-306
-                        const uint32_t curb = side ? ph.z : ph.y;
-                        if (curb == NONE32) REC_BND(V, p, side) = cnum;
-                        else if (curb != cnum) err |= DEV_ERR_INVARIANT;  // unreachable!() in the reference
-                    }
-                    const uint32_t li = 2 * side + rel;
-                    uint32_t lk = rec_link(pl, ph, li);
-                    uint32_t sq = side ^ 1u;
-                    if (lk == NONE32) {  // wrap through the ends of the world line :224-241
-                        uint32_t b = op_bond(pl.x);
-                        int kind = bond_kind(D, b);
-                        uint32_t v0, v1;
-                        bond_vars(D, b, kind, v0, v1);
-                        uint32_t var = rel ? v1 : v0;
-                        lk = side == SIDE_IN ? V.vlast[var] : V.vfirst[var];
-                    }
-                    uint32_t q = lk >> 1, rq = lk & 1u;
-                    const uint4 ql = ld_rec_lo(V, q), qh = ld_rec_hi(V, q);
-                    uint32_t bq = op_bond(ql.x);
-                    if (bq >= E && bq < EN) {  // cluster edge :245-248
-                        const uint32_t mine = sq ? qh.z : qh.y, other = sq ? qh.y : qh.z;
-                        if (mine == NONE32) REC_BND(V, q, sq) = cnum;
-                        else if (mine != cnum) err |= DEV_ERR_INVARIANT;
-                        if (other == NONE32) {  // not both sides set: the other side starts a new cluster later
-                            if (flen >= V.fcap) { err |= DEV_ERR_STACK; } else V.frontier[flen++] = (q << 1) | (sq ^ 1u);
-                            prefetch_rec(V, rec_link(ql, qh, 2u * (sq ^ 1u)));
-                        }
-                    } else {  // interior op :249-268
-                        uint32_t a = qh.y, bb = qh.z;
-                        bool ok = (a == NONE32 && bb == NONE32) || (a == cnum && bb == NONE32) || (a == NONE32 && bb == cnum);
-                        if (ok) {
-                            REC_BND(V, q, 0) = cnum, REC_BND(V, q, 1) = cnum;
-                            int nvq = bq < E ? 2 : 1;
-                            if (ilen + 4 > V.icap) { err |= DEV_ERR_STACK; break; }
-                            for (int k = 0; k < nvq; k++)
-                                if (!((uint32_t)k == rq && sq == SIDE_IN)) {
-                                    V.interior[ilen++] = (q << 2) | ((uint32_t)k << 1) | SIDE_IN;
-                                    prefetch_rec(V, rec_link(ql, qh, (uint32_t)k));
-                                }
-                            for (int k = 0; k < nvq; k++)
-                                if (!((uint32_t)k == rq && sq == SIDE_OUT)) {
-                                    V.interior[ilen++] = (q << 2) | ((uint32_t)k << 1) | SIDE_OUT;
-                                    prefetch_rec(V, rec_link(ql, qh, 2u + (uint32_t)k));
-                                }
-                        }
-                    }
-                }
-            }
-            cnum++;
+    uint32_t *const ist = stk, *const fst = stk + STK_I;
+    uint64_t flen = 0, ilen = 0, fbase = 0;  // frontier entries [fbase, flen) are in fst, [0, fbase) in V.frontier
+    auto fpush = [&](uint32_t x) {
+        if (flen - fbase == STK_F) {  // window full: the lower half goes to global memory
+            for (uint32_t j = 0; j < STK_F / 2; j++) V.frontier[fbase + j] = fst[j];
+            for (uint32_t j = 0; j < STK_F / 2; j++) fst[j] = fst[j + STK_F / 2];
+            fbase += STK_F / 2;
         }
-        uint32_t unmapped = NONE32;  // :82-88 (the smallest unmapped p never decreases)
-        for (; scan <= last_p; scan++) {
-            if (V.ops[scan] == OP_EMPTY) continue;
-            const uint4 h = ld_rec_hi(V, scan);
-            if (h.y == NONE32 && h.z == NONE32) {
-                unmapped = scan;
-                break;
+        fst[flen - fbase] = x;
+        flen++;
+    };
+    auto fpop = [&]() -> uint32_t {
+        if (flen == fbase) {  // window empty: refill from global memory
+            const uint64_t take = fbase < STK_F / 2 ? fbase : STK_F / 2;
+            for (uint64_t j = 0; j < take; j++) fst[j] = V.frontier[fbase - take + j];
+            fbase -= take;
+        }
+        flen--;
+        return fst[flen - fbase];
+    };
+    auto ipush = [&](uint32_t x) {
+        if (ilen < STK_I) ist[ilen] = x;
+        else V.interior[ilen] = x;
+        ilen++;
+    };
+    auto ipop = [&]() -> uint32_t {
+        ilen--;
+        return ilen < STK_I ? ist[ilen] : V.interior[ilen];
+    };
+    if (lane == 0) {
+        fpush((cp << 1) | SIDE_OUT);  // cluster.rs:57-59
+        fpush((cp << 1) | SIDE_IN);
+    }
+    // Interior entries.  The reference stacks (p, leg, side) and, when it pops one, looks the leg's link up in p's node
+    // (cluster.rs:218-241).  p's record is in registers when its legs are pushed, so the link is resolved THEN and the
+    // entry holds where the leg lands: (q << 1 | leg of q) << 1 | side of q it arrives at -- one dependent record load
+    // per leg instead of two.  set_boundary(p, side) at pop time (:218) is a no-op for ops reached by the walk (both of
+    // their sides are set when they are reached, :252-254); it matters for the legs of a non-edge START op, whose sides
+    // are set leg by leg (which is what makes the reference push duplicates): those entries carry bit 31 and set
+    // boundary (p0, side ^ 1 of the entry) when popped.  Push and pop order are the reference's.
+    uint32_t cnum = 0, scan = 0;
+    auto push_leg = [&](const uint4 &lo, const uint4 &hi, uint32_t k, uint32_t side, uint32_t v0, uint32_t v1, uint32_t flag) {
+        uint32_t lk = rec_link(lo, hi, 2u * side + k);
+        if (lk == NONE32) {  // wrap through the ends of the world line :224-241
+            const uint32_t var = k ? v1 : v0;
+            lk = side == SIDE_IN ? V.vlast[var] : V.vfirst[var];
+        }
+        prefetch_rec(V, lk);
+        ipush((lk << 1) | (side ^ 1u) | flag);
+    };
+    for (;;) {
+        if (lane == 0) {
+            while (flen) {  // :62-80
+                const uint32_t e = fpop();
+                const uint32_t p0 = e >> 1, side0 = e & 1u;
+                const uint4 l0 = ld_rec_lo(V, p0), h0 = ld_rec_hi(V, p0);
+                if (h0.y != NONE32 && h0.z != NONE32) continue;
+                // ---- expand_whole_cluster(p0, (0, side0), cnum) :193-271
+                {
+                    const uint32_t b0 = op_bond(l0.x);
+                    const int kind0 = bond_kind(D, b0);
+                    uint32_t a0, a1;
+                    bond_vars(D, b0, kind0, a0, a1);
+                    ilen = 0;
+                    if (kind0 != KIND_SITE) {  // :205-211: every leg of the start op, boundaries set as the legs are popped
+                        const uint32_t nv = kind0 == KIND_BOND ? 2u : 1u;
+                        for (uint32_t k = 0; k < nv; k++) push_leg(l0, h0, k, SIDE_IN, a0, a1, 0x80000000u);
+                        for (uint32_t k = 0; k < nv; k++) push_leg(l0, h0, k, SIDE_OUT, a0, a1, 0x80000000u);
+                    } else {  // :212-215
+                        push_leg(l0, h0, 0u, side0, a0, a1, 0x80000000u);
+                    }
+                    while (ilen) {
+                        const uint32_t it = ipop();
+                        const uint32_t sq = it & 1u, lk = (it & 0x7FFFFFFFu) >> 1;
+                        if (it & 0x80000000u) {  // set_boundary(p0, side, cnum) :218, :289-306
+                            const uint32_t side = sq ^ 1u;
+                            const uint32_t curb = REC_BND(V, p0, side);
+                            if (curb == NONE32) REC_BND(V, p0, side) = cnum;
+                            else if (curb != cnum) err |= DEV_ERR_INVARIANT;  // unreachable!() in the reference
+                        }
+                        const uint32_t q = lk >> 1, rq = lk & 1u;
+                        const uint4 ql = ld_rec_lo(V, q), qh = ld_rec_hi(V, q);  // one sector: op, links, boundaries
+                        const uint32_t bq = op_bond(ql.x);
+                        if (bq >= E && bq < EN) {  // cluster edge :245-248
+                            const uint32_t mine = sq ? qh.z : qh.y, other = sq ? qh.y : qh.z;
+                            if (mine == NONE32) REC_BND(V, q, sq) = cnum;
+                            else if (mine != cnum) err |= DEV_ERR_INVARIANT;
+                            if (other == NONE32) {  // not both sides set: the other side starts a new cluster later
+                                if (flen >= V.fcap) { err |= DEV_ERR_STACK; } else fpush((q << 1) | (sq ^ 1u));
+                                prefetch_rec(V, rec_link(ql, qh, 2u * (sq ^ 1u)));
+                            }
+                        } else {  // interior op :249-268
+                            const uint32_t a = qh.y, bb = qh.z;
+                            const bool ok = (a == NONE32 && bb == NONE32) || (a == cnum && bb == NONE32) || (a == NONE32 && bb == cnum);
+                            if (ok) {
+                                REC_BND(V, q, 0) = cnum, REC_BND(V, q, 1) = cnum;
+                                const int kq = bond_kind(D, bq);
+                                uint32_t c0, c1;
+                                bond_vars(D, bq, kq, c0, c1);
+                                const uint32_t nvq = kq == KIND_BOND ? 2u : 1u;
+                                if (ilen + 4 > V.icap) { err |= DEV_ERR_STACK; break; }
+                                for (uint32_t k = 0; k < nvq; k++)
+                                    if (!(k == rq && sq == SIDE_IN)) push_leg(ql, qh, k, SIDE_IN, c0, c1, 0u);
+                                for (uint32_t k = 0; k < nvq; k++)
+                                    if (!(k == rq && sq == SIDE_OUT)) push_leg(ql, qh, k, SIDE_OUT, c0, c1, 0u);
+                            }
+                        }
+                    }
+                }
+                cnum++;
             }
+        }
+        __syncwarp();  // the boundaries lane 0 wrote are visible to the scanning lanes
+        // :82-88 the smallest unmapped op (it never decreases): 32 slots per round, whole lines of the string
+        uint32_t unmapped = NONE32;
+        scan = __shfl_sync(0xFFFFFFFFu, scan, 0);
+        for (uint32_t base = scan & ~31u; base <= last_p && unmapped == NONE32; base += 32) {
+            const uint32_t p = base + (uint32_t)lane;
+            bool un = false;
+            if (p >= scan && p <= last_p && V.ops[p] != OP_EMPTY) {
+                const uint4 h = ld_rec_hi(V, p);
+                un = h.y == NONE32 && h.z == NONE32;
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, un);
+            if (m) unmapped = base + (uint32_t)__ffs(m) - 1u;
+            else scan = base + 32;  // everything below is mapped for good
         }
         if (unmapped == NONE32) break;
-        V.frontier[flen++] = (unmapped << 1) | SIDE_OUT;  // :89-91
-        V.frontier[flen++] = (unmapped << 1) | SIDE_IN;
+        scan = unmapped;
+        if (lane == 0) {
+            fpush((unmapped << 1) | SIDE_OUT);  // :89-91
+            fpush((unmapped << 1) | SIDE_IN);
+        }
     }
-    return cnum;
+    return __shfl_sync(0xFFFFFFFFu, cnum, 0);
 }
 
 // flip_each_cluster_rng (cluster.rs:36-172), whole warp; returns n_clusters
-__device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, int lane) {
+__device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, int lane, uint32_t *stk) {
     const uint32_t n = D.n[r];
     if (n == 0) return 0;  // :46-48
     const uint32_t last_p = V.ends[1], cp = V.ends[2];
@@ -462,8 +510,7 @@ __device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, in
     uint32_t ncl = 1;
     int err = 0;
     if (cp != NONE32) {
-        if (lane == 0) ncl = label_strict(D, V, err);
-        ncl = __shfl_sync(0xFFFFFFFFu, ncl, 0);
+        ncl = label_strict(D, V, err, lane, stk);
     } else {  // :98-107 the whole thing is one cluster
         for (uint32_t p = lane; p <= last_p; p += 32)
             if (V.ops[p] != OP_EMPTY) REC_BND(V, p, 0) = 0, REC_BND(V, p, 1) = 0;
@@ -658,7 +705,8 @@ __device__ void free_spins(const SseDev &D, uint32_t r, const Rep &V, int lane) 
 __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint64_t target, uint32_t phases,
                                                     uint64_t sample_freq, uint64_t sample_origin,
                                                     uint8_t *samples, uint64_t samples_per_rep, int par_links) {
-    extern __shared__ uint32_t smem_last[];  // [warps per block][N] when par_links
+    extern __shared__ uint32_t smem_warp[];  // per warp: [STK_I + STK_F] stack tops of the STRICT walk, then [N] `last` table when par_links
+    uint32_t *const my_smem = smem_warp + (size_t)(threadIdx.x >> 5) * (STK_I + STK_F + (par_links ? D.N : 0u));
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= D.R) return;
@@ -680,14 +728,14 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
         }
         if (phases & 2u) {
             if (mode == 0 && par_links) {
-                links_parallel(D, r, V, lane, smem_last + (size_t)(threadIdx.x >> 5) * D.N);
+                links_parallel(D, r, V, lane, my_smem + STK_I + STK_F);
             } else {
                 for (uint32_t v = lane; v < D.N; v += 32) V.vfirst[v] = NONE32, V.vlast[v] = NONE32;
                 __syncwarp();
                 if (lane == 0) links_serial(D, r, V, mode == 0);
                 __syncwarp();
             }
-            uint32_t ncl = mode == 0 ? cluster_strict(D, r, V, lane) : cluster_fast_serial(D, r, V, lane, false);
+            uint32_t ncl = mode == 0 ? cluster_strict(D, r, V, lane, my_smem) : cluster_fast_serial(D, r, V, lane, false);
             if (lane == 0) D.ncl[r] = ncl;
             free_spins(D, r, V, lane);
         }
@@ -851,10 +899,12 @@ void launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phas
                        uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
     const int threads = 128;
     const uint32_t blocks = (uint32_t)(((uint64_t)D.R * 32 + threads - 1) / threads);
-    const size_t smem = (size_t)(threads / 32) * D.N * sizeof(uint32_t);
+    const size_t stk = (size_t)(threads / 32) * (STK_I + STK_F) * sizeof(uint32_t);
+    size_t smem = stk + (size_t)(threads / 32) * D.N * sizeof(uint32_t);
     const int par = mode == 0 && smem <= 160 * 1024;
-    if (par && smem > 48 * 1024) cudaFuncSetAttribute(k_sse_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_sse_serial<<<blocks, threads, par ? smem : 0, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep, par);
+    if (!par) smem = stk;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_sse_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_sse_serial<<<blocks, threads, smem, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep, par);
 }
 void launch_sse_verify(const SseDev &D, uint32_t r, int *ok_dev, uint32_t *scratch_dev, cudaStream_t st) {
     k_sse_verify<<<1, 32, 0, st>>>(D, r, ok_dev, scratch_dev);
