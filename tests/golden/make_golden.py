@@ -33,6 +33,14 @@ def digest(arr):
     return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
 
 
+def fnv1a64(arr):
+    """FNV-1a over the little-endian bytes of the op words: a hash the Rust parity kit can restate in three lines"""
+    h = 0xCBF29CE484222325
+    for b in np.ascontiguousarray(arr).astype("<u4").tobytes():
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
 def run_case(case, mode):
     name, (builder, args), gamma, h, cutoff, beta, sweeps, hb = case
     edges = getattr(lattices, builder)(*args)
@@ -45,17 +53,21 @@ def run_case(case, mode):
         ops = g.dump_ops()
         out.append({"key": k, "n": int(g.n), "cutoff": int(g.cutoff), "cursor": int(g.cursor), "energy_hex": float(e).hex(),
                     "state": "".join(str(int(b)) for b in g.state()), "ops_sha256": digest(ops.astype("<u4")),
-                    "ops_head": [int(w) for w in ops[:8]]})
+                    "ops_fnv1a64": "%016x" % fnv1a64(ops), "ops_head": [int(w) for w in ops[:8]]})
     return out
 
 
 def main():
     doc = {"_provenance": __doc__.split("Run from")[0].strip(), "cases": []}
     for case in CASES:
-        for mode, mname in ((po.MODE_STRICT, "strict"), (po.MODE_FAST, "fast")):
+        for mode, mname in ((po.MODE_STRICT, "strict"), (po.MODE_FAST, "fast"), (po.MODE_COUNTER, "counter")):
             name, (builder, args), gamma, h, cutoff, beta, sweeps, hb = case
+            if hb and mode == po.MODE_COUNTER:
+                continue  # the heat-bath rule has no COUNTER-mode contract
+            edges = getattr(lattices, builder)(*args)
             doc["cases"].append({"name": name, "builder": builder, "args": args, "gamma": gamma, "h": h, "cutoff": cutoff, "beta": beta,
-                                 "sweeps": sweeps, "heatbath": hb, "mode": mname, "replicas": run_case(case, mode)})
+                                 "sweeps": sweeps, "heatbath": hb, "mode": mname, "edges": [[a, b, j] for (a, b), j in edges],
+                                 "replicas": run_case(case, mode)})
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "sse_golden.json"), "w") as f:
         json.dump(doc, f, indent=1)
     print("wrote", len(doc["cases"]), "cases")
