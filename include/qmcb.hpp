@@ -243,7 +243,24 @@ public:
     }
     size_t num_graphs() const { return n_betas_ * n_chains_; }
     void timesteps(size_t t) { check(qmcb_timesteps(g_.raw(), t, 1, nullptr, nullptr)); }  // :76-81
-    void tempering_step() { check(qmcb_pt_step_local(g_.raw())); }                          // :121-149
+    void tempering_step() { check(qmcb_pt_step(g_.raw())); }                                // :121-149 (:373-402)
+    // timesteps_sample / parallel_timesteps_sample (:166-208, :411-453): (states, energy_acc) per slot
+    std::vector<std::pair<std::vector<std::vector<bool>>, double>> timesteps_sample(size_t timesteps, size_t replica_swap_freq, size_t sampling_freq) {
+        const size_t S = num_graphs(), T = timesteps / sampling_freq, N = g_.get_nvars();
+        std::vector<double> energy(S);
+        std::vector<uint8_t> raw(S * T * N);
+        std::vector<uint32_t> slots(S * T);
+        check(qmcb_pt_timesteps_sample(g_.raw(), timesteps, replica_swap_freq, sampling_freq, energy.data(), raw.data(), slots.data()));
+        std::vector<std::pair<std::vector<std::vector<bool>>, double>> out(S);
+        for (size_t s = 0; s < S; s++) out[s].second = energy[s];
+        for (size_t k = 0; k < T; k++)
+            for (size_t c = 0; c < S; c++) {
+                std::vector<bool> st(N);
+                for (size_t v = 0; v < N; v++) st[v] = raw[(c * T + k) * N + v] != 0;
+                out[slots[c * T + k]].first.push_back(std::move(st));
+            }
+        return out;
+    }
     uint64_t get_total_swaps() {                                                            // :231-233
         uint64_t s = 0;
         check(qmcb_pt_total_swaps(g_.raw(), &s));

@@ -1,5 +1,8 @@
-//! Safe wrappers with the shape of `qmc::sse::QmcIsingGraph` / `QmcStepper`
-//! (qmc_ising.rs:131-148, qmc_stepper.rs:2-168) over one batched GPU handle.
+//! Safe wrappers with the shape of the reference's host API for the hot path, over batched GPU handles:
+//! `BatchedQmcIsingGraph` + `BatchedQmcStepper` (`qmc::sse::QmcIsingGraph` / `QmcStepper`, qmc_ising.rs:131-148,
+//! qmc_stepper.rs:2-168), `TemperingContainer` (tempering_container.rs:19-302, :316-478; `SwapManagers` /
+//! `GraphWeights` / `StateGetter`, tempering_traits.rs:9-46, are what the handle does internally) and `GraphState`
+//! (classical/graph.rs:56-88, :350-447).  One handle = R replicas, so every per-graph return value becomes a Vec.
 //! SOURCE ONLY: not compiled in this repository (no Rust toolchain in the build image).
 use qmcb_sys as sys;
 use rand_core::{impls, Error, RngCore};
@@ -41,13 +44,29 @@ fn check(rc: i32) -> Result<(), String> {
     }
 }
 
-/// R replicas of one lattice; method names follow `QmcStepper`.
-pub struct BatchedQmcIsingGraph { h: *mut sys::QmcbHandle, nvars: usize, replicas: usize }
+/// Cluster / draw contract of a handle (include/qmcb.h).
+#[derive(Clone, Copy, PartialEq, Eq, Debug)]
+pub enum Mode { Strict = 0, Fast = 1, Counter = 2 }
+
+/// `QmcStepper` (qmc_stepper.rs:2-168) for a batch: the same method names, one value per replica.
+pub trait BatchedQmcStepper {
+    /// timestep(beta) -> state_ref of every replica
+    fn timestep(&mut self) -> Result<Vec<Vec<bool>>, String>;
+    fn timesteps(&mut self, t: usize) -> Result<Vec<f64>, String>;
+    fn timesteps_sample(&mut self, t: usize, sampling_freq: Option<usize>) -> Result<(Vec<Vec<Vec<bool>>>, Vec<f64>), String>;
+    fn get_n(&mut self) -> Result<Vec<u64>, String>;
+    fn state_ref(&mut self) -> Result<Vec<Vec<bool>>, String>;
+    fn get_bond_count(&mut self, r: usize) -> Result<Vec<u64>, String>;
+    fn get_energy_for_average_n(&self, average_n: f64, beta: f64) -> f64;
+}
+
+/// R replicas of one lattice; method names follow `QmcIsingGraph` / `QmcStepper`.
+pub struct BatchedQmcIsingGraph { h: *mut sys::QmcbHandle, nvars: usize, replicas: usize, offset: f64 }
 
 impl BatchedQmcIsingGraph {
     /// qmc_ising.rs:131-148 with one rng key and beta per replica.
     pub fn new_with_rng(edges: Vec<((usize, usize), f64)>, transverse: f64, longitudinal: f64, cutoff: usize,
-                        rng_keys: &[u64], betas: &[f64], state: Option<Vec<bool>>) -> Result<Self, String> {
+                        rng_keys: &[u64], betas: &[f64], state: Option<Vec<bool>>, mode: Mode, device: i32) -> Result<Self, String> {
         let nvars = edges.iter().map(|((a, b), _)| *a.max(b)).max().unwrap() + 1;
         let va: Vec<u32> = edges.iter().map(|((a, _), _)| *a as u32).collect();
         let vb: Vec<u32> = edges.iter().map(|((_, b), _)| *b as u32).collect();
@@ -57,28 +76,46 @@ impl BatchedQmcIsingGraph {
         let init: Option<Vec<u8>> = state.map(|s| (0..rng_keys.len()).flat_map(|_| s.iter().map(|b| *b as u8)).collect());
         let mut h = std::ptr::null_mut();
         check(unsafe { sys::qmcb_create(&lat, rng_keys.len() as u32, betas.as_ptr(), rng_keys.as_ptr(), cutoff as u64, 0,
-                                        init.as_ref().map_or(std::ptr::null(), |v| v.as_ptr()), 0, &mut h) })?;
-        Ok(Self { h, nvars, replicas: rng_keys.len() })
+                                        init.as_ref().map_or(std::ptr::null(), |v| v.as_ptr()), device, &mut h) })?;
+        let mut g = Self { h, nvars, replicas: rng_keys.len(), offset: 0.0 };
+        check(unsafe { sys::qmcb_set_mode(g.h, mode as i32) })?;
+        check(unsafe { sys::qmcb_get_offset(g.h, &mut g.offset) })?;
+        Ok(g)
     }
-    /// QmcStepper::timesteps (qmc_stepper.rs:17-20): average energy per replica.
-    pub fn timesteps(&mut self, t: usize) -> Result<Vec<f64>, String> {
-        let mut e = vec![0.0; self.replicas];
-        check(unsafe { sys::qmcb_timesteps(self.h, t as u64, 1, e.as_mut_ptr(), std::ptr::null_mut()) })?;
-        Ok(e)
-    }
-    /// QmcStepper::timesteps_sample (qmc_stepper.rs:23-40): samples[replica][k][var].
-    pub fn timesteps_sample(&mut self, t: usize, sampling_freq: Option<usize>) -> Result<(Vec<Vec<Vec<bool>>>, Vec<f64>), String> {
-        let f = sampling_freq.unwrap_or(1);
-        let k = t / f;
-        let mut e = vec![0.0; self.replicas];
-        let mut raw = vec![0u8; self.replicas * k * self.nvars];
-        check(unsafe { sys::qmcb_timesteps(self.h, t as u64, f as u64, e.as_mut_ptr(), raw.as_mut_ptr()) })?;
-        let s = raw.chunks(k * self.nvars).map(|r| r.chunks(self.nvars).map(|c| c.iter().map(|b| *b != 0).collect()).collect()).collect();
-        Ok((s, e))
+    pub fn raw(&self) -> *mut sys::QmcbHandle { self.h }
+    pub fn num_replicas(&self) -> usize { self.replicas }
+    pub fn get_nvars(&self) -> usize { self.nvars }
+    pub fn get_offset(&self) -> f64 { self.offset }
+    pub fn set_mode(&mut self, mode: Mode) -> Result<(), String> { check(unsafe { sys::qmcb_set_mode(self.h, mode as i32) }) }
+    pub fn set_betas(&mut self, betas: &[f64]) -> Result<(), String> {
+        assert_eq!(betas.len(), self.replicas);
+        check(unsafe { sys::qmcb_set_betas(self.h, betas.as_ptr()) })
     }
     /// QmcIsingGraph::set_enable_heatbath (qmc_ising.rs:444-486)
     pub fn set_enable_heatbath(&mut self, enable_heatbath: bool) -> Result<(), String> {
         check(unsafe { sys::qmcb_set_enable_heatbath(self.h, enable_heatbath as i32) })
+    }
+    /// single_diagonal_step / single_cluster_step (qmc_ising.rs:208-320)
+    pub fn single_diagonal_step(&mut self) -> Result<(), String> { check(unsafe { sys::qmcb_single_diagonal_step(self.h) }) }
+    pub fn single_cluster_step(&mut self) -> Result<Vec<u64>, String> {
+        let mut n = vec![0u64; self.replicas];
+        check(unsafe { sys::qmcb_single_cluster_step(self.h, n.as_mut_ptr()) })?;
+        Ok(n)
+    }
+    pub fn get_cutoff(&mut self) -> Result<Vec<u64>, String> {
+        let mut c = vec![0u64; self.replicas];
+        check(unsafe { sys::qmcb_get_cutoffs(self.h, c.as_mut_ptr()) })?;
+        Ok(c)
+    }
+    pub fn set_cutoff(&mut self, r: usize, cutoff: usize) -> Result<(), String> {
+        check(unsafe { sys::qmcb_set_cutoff(self.h, r as u32, cutoff as u64) })
+    }
+    /// the operator string of replica r as op words (include/qmcb.h), what `get_manager_ref().get_pth(p)` walks
+    pub fn dump_ops(&mut self, r: usize) -> Result<Vec<u32>, String> {
+        let m = self.get_cutoff()?[r] as usize;
+        let mut w = vec![0u32; m];
+        check(unsafe { sys::qmcb_dump_ops(self.h, r as u32, w.as_mut_ptr(), m as u64) })?;
+        Ok(w)
     }
     /// serde replacement (SerializeQmcGraph, qmc_ising.rs:1001-1087): the whole batch, stream position included
     pub fn to_bytes(&mut self) -> Result<Vec<u8>, String> {
@@ -88,11 +125,19 @@ impl BatchedQmcIsingGraph {
         check(unsafe { sys::qmcb_checkpoint_save(self.h, buf.as_mut_ptr() as *mut _, n) })?;
         Ok(buf)
     }
+    pub fn from_bytes(blob: &[u8], device: i32) -> Result<Self, String> {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::qmcb_checkpoint_load(blob.as_ptr() as *const _, blob.len() as u64, device, &mut h) })?;
+        let (mut r, mut n, mut off) = (0u32, 0u32, 0.0);
+        check(unsafe { sys::qmcb_num_replicas(h, &mut r) })?;
+        check(unsafe { sys::qmcb_num_vars(h, &mut n) })?;
+        check(unsafe { sys::qmcb_get_offset(h, &mut off) })?;
+        Ok(Self { h, nvars: n as usize, replicas: r as usize, offset: off })
+    }
     /// QmcStepper::imaginary_time_fold (qmc_stepper.rs:165-168) with the closure evaluated on the host
     pub fn imaginary_time_fold<F, T>(&mut self, r: usize, fold_fn: F, init: T) -> Result<T, String>
     where F: Fn(T, &[bool]) -> T {
-        let mut cut = vec![0u64; self.replicas];
-        check(unsafe { sys::qmcb_get_cutoffs(self.h, cut.as_mut_ptr()) })?;
+        let cut = self.get_cutoff()?;
         let (mut acc, mut raw) = (init, vec![0u8; self.nvars]);
         for p in 0..cut[r] {
             check(unsafe { sys::qmcb_itime_state(self.h, r as u32, p, raw.as_mut_ptr()) })?;
@@ -101,15 +146,166 @@ impl BatchedQmcIsingGraph {
         }
         Ok(acc)
     }
-    pub fn get_n(&mut self) -> Result<Vec<u64>, String> {
-        let mut n = vec![0u64; self.replicas];
-        check(unsafe { sys::qmcb_get_n(self.h, n.as_mut_ptr()) })?;
-        Ok(n)
-    }
+    /// Verify::verify (op_container.rs:137-159, qmc_ising.rs:829-860), replayed on the device
     pub fn verify(&mut self, r: usize) -> Result<bool, String> {
         let mut ok = 0;
         check(unsafe { sys::qmcb_verify(self.h, r as u32, &mut ok) })?;
         Ok(ok != 0)
     }
 }
+
+impl BatchedQmcStepper for BatchedQmcIsingGraph {
+    fn timestep(&mut self) -> Result<Vec<Vec<bool>>, String> {
+        check(unsafe { sys::qmcb_timesteps(self.h, 1, 1, std::ptr::null_mut(), std::ptr::null_mut()) })?;
+        self.state_ref()
+    }
+    /// QmcStepper::timesteps (qmc_stepper.rs:17-20): average energy per replica.
+    fn timesteps(&mut self, t: usize) -> Result<Vec<f64>, String> {
+        let mut e = vec![0.0; self.replicas];
+        check(unsafe { sys::qmcb_timesteps(self.h, t as u64, 1, e.as_mut_ptr(), std::ptr::null_mut()) })?;
+        Ok(e)
+    }
+    /// QmcStepper::timesteps_sample (qmc_stepper.rs:23-40): samples[replica][k][var].
+    fn timesteps_sample(&mut self, t: usize, sampling_freq: Option<usize>) -> Result<(Vec<Vec<Vec<bool>>>, Vec<f64>), String> {
+        let f = sampling_freq.unwrap_or(1);
+        let k = t / f;
+        let mut e = vec![0.0; self.replicas];
+        let mut raw = vec![0u8; self.replicas * k * self.nvars];
+        check(unsafe { sys::qmcb_timesteps(self.h, t as u64, f as u64, e.as_mut_ptr(), raw.as_mut_ptr()) })?;
+        let s = raw.chunks(k * self.nvars).map(|r| r.chunks(self.nvars).map(|c| c.iter().map(|b| *b != 0).collect()).collect()).collect();
+        Ok((s, e))
+    }
+    fn get_n(&mut self) -> Result<Vec<u64>, String> {
+        let mut n = vec![0u64; self.replicas];
+        check(unsafe { sys::qmcb_get_n(self.h, n.as_mut_ptr()) })?;
+        Ok(n)
+    }
+    fn state_ref(&mut self) -> Result<Vec<Vec<bool>>, String> {
+        let mut raw = vec![0u8; self.replicas * self.nvars];
+        check(unsafe { sys::qmcb_get_states(self.h, raw.as_mut_ptr()) })?;
+        Ok(raw.chunks(self.nvars).map(|c| c.iter().map(|b| *b != 0).collect()).collect())
+    }
+    fn get_bond_count(&mut self, r: usize) -> Result<Vec<u64>, String> {
+        let mut nb = 0u32;
+        check(unsafe { sys::qmcb_num_bonds(self.h, &mut nb) })?;
+        let mut c = vec![0u64; nb as usize];
+        check(unsafe { sys::qmcb_get_bond_counts(self.h, r as u32, c.as_mut_ptr()) })?;
+        Ok(c)
+    }
+    /// qmc_ising.rs:805-809
+    fn get_energy_for_average_n(&self, average_n: f64, beta: f64) -> f64 { -(average_n / beta) + self.offset }
+}
 impl Drop for BatchedQmcIsingGraph { fn drop(&mut self) { unsafe { sys::qmcb_destroy(self.h); } } }
+
+/// `TemperingContainer` (tempering_container.rs:19-302; parallel variants :316-478) over one handle per rank:
+/// `n_chains` independent ladders of `betas.len()` slots.  `add_qmc_stepper` is replaced by giving the ladder at
+/// construction (all slots share one lattice, so `can_swap_graphs` holds; unequal Hamiltonians per ladder position
+/// go through `qmcb_set_hamiltonians` / `qmcb_pt_set_slot_hamiltonians`).  On several GPUs every rank owns a
+/// contiguous block of slots and `init_comm` makes `tempering_step` exchange the slot records with one
+/// ncclAllGather inside the library.
+pub struct TemperingContainer { graph: BatchedQmcIsingGraph, n_slots: usize }
+
+impl TemperingContainer {
+    #[allow(clippy::too_many_arguments)]
+    pub fn new(edges: Vec<((usize, usize), f64)>, transverse: f64, longitudinal: f64, cutoff: usize, betas: &[f64], n_chains: usize,
+               rng_keys: &[u64], pt_key: u64, mode: Mode, device: i32, rank: usize, world: usize) -> Result<Self, String> {
+        let n_slots = betas.len() * n_chains;
+        assert_eq!(rng_keys.len(), n_slots);
+        assert_eq!(n_slots % world, 0, "slots must divide evenly over the ranks");
+        let per = n_slots / world;
+        let betas_global: Vec<f64> = (0..n_chains).flat_map(|_| betas.iter().copied()).collect();
+        let (lo, hi) = (rank * per, (rank + 1) * per);
+        let graph = BatchedQmcIsingGraph::new_with_rng(edges, transverse, longitudinal, cutoff, &rng_keys[lo..hi], &betas_global[lo..hi],
+                                                       None, mode, device)?;
+        check(unsafe { sys::qmcb_pt_configure(graph.h, n_chains as u32, betas.len() as u32, lo as u32, betas_global.as_ptr(),
+                                              rng_keys.as_ptr(), pt_key) })?;
+        Ok(Self { graph, n_slots })
+    }
+    /// rank 0: the 128-byte ncclUniqueId to hand to the other ranks (MPI, files, ...)
+    pub fn comm_unique_id() -> Result<[u8; 128], String> {
+        let mut id = [0u8; 128];
+        check(unsafe { sys::qmcb_pt_comm_unique_id(id.as_mut_ptr()) })?;
+        Ok(id)
+    }
+    /// collective over the ranks: ncclCommInitRank on this handle's device
+    pub fn init_comm(&mut self, id: &[u8; 128], world: usize, rank: usize) -> Result<(), String> {
+        check(unsafe { sys::qmcb_pt_comm_init(self.graph.h, id.as_ptr(), world as i32, rank as i32) })
+    }
+    pub fn num_graphs(&self) -> usize { self.n_slots }
+    pub fn graph_mut(&mut self) -> &mut BatchedQmcIsingGraph { &mut self.graph }
+    /// tempering_container.rs:76-81 / parallel_timesteps :366-371
+    pub fn timesteps(&mut self, t: usize) -> Result<Vec<f64>, String> { self.graph.timesteps(t) }
+    /// tempering_step / parallel_tempering_step (tempering_container.rs:121-149, :373-402)
+    pub fn tempering_step(&mut self) -> Result<(), String> { check(unsafe { sys::qmcb_pt_step(self.graph.h) }) }
+    /// timesteps_sample / parallel_timesteps_sample (tempering_container.rs:166-208, :411-453): (states, energy_acc)
+    /// per SLOT; states[slot] holds the samples taken while a configuration of this rank sat in that slot.
+    pub fn timesteps_sample(&mut self, timesteps: usize, replica_swap_freq: usize, sampling_freq: usize)
+                            -> Result<Vec<(Vec<Vec<bool>>, f64)>, String> {
+        let (r, n, t) = (self.graph.replicas, self.graph.nvars, timesteps / sampling_freq);
+        let mut energy = vec![0.0; self.n_slots];
+        let mut raw = vec![0u8; r * t * n];
+        let mut slots = vec![0u32; r * t];
+        check(unsafe { sys::qmcb_pt_timesteps_sample(self.graph.h, timesteps as u64, replica_swap_freq as u64, sampling_freq as u64,
+                                                     energy.as_mut_ptr(), raw.as_mut_ptr(), slots.as_mut_ptr()) })?;
+        let mut out: Vec<(Vec<Vec<bool>>, f64)> = energy.into_iter().map(|e| (Vec::new(), e)).collect();
+        for k in 0..t {
+            for c in 0..r {
+                let s = &raw[(c * t + k) * n..(c * t + k + 1) * n];
+                out[slots[c * t + k] as usize].0.push(s.iter().map(|b| *b != 0).collect());
+            }
+        }
+        Ok(out)
+    }
+    /// get_total_swaps (tempering_container.rs:231-233)
+    pub fn get_total_swaps(&mut self) -> Result<u64, String> {
+        let mut s = 0u64;
+        check(unsafe { sys::qmcb_pt_total_swaps(self.graph.h, &mut s) })?;
+        Ok(s)
+    }
+    /// the slot each local configuration currently holds (StateGetter / SwapManagers seen from the configuration's side)
+    pub fn slots(&mut self) -> Result<Vec<u32>, String> {
+        let mut s = vec![0u32; self.graph.replicas];
+        check(unsafe { sys::qmcb_pt_get_slots(self.graph.h, s.as_mut_ptr()) })?;
+        Ok(s)
+    }
+}
+
+/// `GraphState` (classical/graph.rs:56-88, :350-447) for R replicas; the schedule is a checkerboard sweep (every site
+/// once per sweep) instead of random sites, the per-site rule is the reference's (`do_spin_flip`, `should_flip`).
+pub struct GraphState { h: *mut sys::CmcbHandle, nvars: usize, replicas: usize }
+
+impl GraphState {
+    /// GraphState::new / new_with_state_and_rng (graph.rs:56-88)
+    pub fn new(edges: &[((usize, usize), f64)], biases: &[f64], rng_keys: &[u64], betas: &[f64], state: Option<&[bool]>, device: i32)
+               -> Result<Self, String> {
+        let va: Vec<u32> = edges.iter().map(|((a, _), _)| *a as u32).collect();
+        let vb: Vec<u32> = edges.iter().map(|((_, b), _)| *b as u32).collect();
+        let j: Vec<f64> = edges.iter().map(|(_, j)| *j).collect();
+        let lat = sys::QmcbLattice { nvars: biases.len() as u32, nedges: edges.len() as u32, va: va.as_ptr(), vb: vb.as_ptr(), j: j.as_ptr(),
+                                     transverse: 0.0, longitudinal: 0.0 };
+        let init: Option<Vec<u8>> = state.map(|s| (0..rng_keys.len()).flat_map(|_| s.iter().map(|b| *b as u8)).collect());
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::cmcb_create(&lat, biases.as_ptr(), rng_keys.len() as u32, betas.as_ptr(), rng_keys.as_ptr(),
+                                        init.as_ref().map_or(std::ptr::null(), |v| v.as_ptr()), device, &mut h) })?;
+        Ok(Self { h, nvars: biases.len(), replicas: rng_keys.len() })
+    }
+    /// do_time_step (graph.rs:350-406): `sweeps` checkerboard sweeps of every replica
+    pub fn do_time_step(&mut self, sweeps: usize) -> Result<(), String> { check(unsafe { sys::cmcb_sweeps(self.h, sweeps as u64) }) }
+    /// get_energy (graph.rs:430-447)
+    pub fn get_energy(&mut self) -> Result<Vec<f64>, String> {
+        let mut e = vec![0.0; self.replicas];
+        check(unsafe { sys::cmcb_energy(self.h, e.as_mut_ptr()) })?;
+        Ok(e)
+    }
+    pub fn state_ref(&mut self) -> Result<Vec<Vec<bool>>, String> {
+        let mut raw = vec![0u8; self.replicas * self.nvars];
+        check(unsafe { sys::cmcb_get_states(self.h, raw.as_mut_ptr()) })?;
+        Ok(raw.chunks(self.nvars).map(|c| c.iter().map(|b| *b != 0).collect()).collect())
+    }
+    pub fn set_state(&mut self, states: &[Vec<bool>]) -> Result<(), String> {
+        let raw: Vec<u8> = states.iter().flat_map(|s| s.iter().map(|b| *b as u8)).collect();
+        assert_eq!(raw.len(), self.replicas * self.nvars);
+        check(unsafe { sys::cmcb_set_states(self.h, raw.as_ptr()) })
+    }
+}
+impl Drop for GraphState { fn drop(&mut self) { unsafe { sys::cmcb_destroy(self.h); } } }

@@ -36,7 +36,7 @@ static std::vector<Edge> two_unit_cell() {  // :25-37
 int main() {
     std::vector<uint64_t> seeds;
     for (uint64_t i = 0; i < 16; i++) seeds.push_back(i);
-    for (int mode : {QMCB_MODE_STRICT, QMCB_MODE_FAST}) {
+    for (int mode : {QMCB_MODE_STRICT, QMCB_MODE_FAST, QMCB_MODE_COUNTER}) {
         {  // run_simple :39-55
             std::vector<bool> st(2, false);
             auto ising = qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 1}, 1.0}}, 1.0, 1.0, 2, seeds, &st, mode);
@@ -63,7 +63,7 @@ int main() {
             ASSERT(mean > -4.6 && mean < -3.6);  // exact -4.055 (DESIGN / SURVEY Appendix E)
             ASSERT(g.verify());
         }
-        {  // the reference's heat-bath benches (benches/end_to_end.rs:168-258): same lattice, set_enable_heatbath(true)
+        if (mode != QMCB_MODE_COUNTER) {  // the reference's heat-bath benches (benches/end_to_end.rs:168-258): same lattice, set_enable_heatbath(true)
             auto g = qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 1}, -1.0}, {{1, 2}, 1.0}, {{2, 3}, 1.0}, {{3, 0}, 1.0}}, 1.0, 0.0, 3, seeds, nullptr, mode);
             g.set_enable_heatbath(true);
             auto e = g.timesteps(1000, 1.0);
@@ -91,6 +91,9 @@ int main() {
             tc.tempering_step();
         }
         ASSERT(tc.num_graphs() == 12 && tc.get_total_swaps() > 0 && tc.verify());
+        auto se = tc.timesteps_sample(12, 2, 3);  // tempering_container.rs:166-208
+        ASSERT(se.size() == 12);
+        for (auto &slot : se) ASSERT(slot.first.size() == 4 && slot.first[0].size() == 16 && slot.second == slot.second);
     }
     {  // serde round trip (qmc_ising.rs serialize_test): a restored batch continues identically
         auto g = qmcb::DefaultQmcIsingGraph::new_with_rng(two_d_periodic(3), 1.0, 0.3, 9, {21, 22, 23}, nullptr, QMCB_MODE_FAST);

@@ -148,3 +148,63 @@ def test_tempering_gather_plumbing_gloo_world2(tmp_path):
                           "--master-port", "29531", str(script), ROOT], capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_rust_sys_crate_binds_every_exported_symbol():
+    """rust/qmcb-sys/src/lib.rs is generated from include/qmcb.h (tools/gen_rust_sys.py): it must be up to date, declare
+    every function the header declares with the same arity, and the safe crate must only call symbols that exist."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "tools", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    src, protos = gen.generate()
+    assert open(gen.OUT).read() == src, "run python tools/gen_rust_sys.py"
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "qmcb.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b((?:qmcb|cmcb)_[a-z0-9_]+)\s*\(", header))
+    bound = {m.group(1): m.group(2) for m in re.finditer(r"pub fn ((?:qmcb|cmcb)_\w+)\((.*?)\) ->", src)}
+    assert set(bound) == declared
+    for ret, name, params in protos:
+        assert bound[name].count(":") == len(params), name
+    safe = open(os.path.join(ROOT, "rust", "qmcb", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::((?:qmcb|cmcb)_\w+)", safe))
+    assert used <= declared and len(used) > 35, used - declared
+    for t in ("parity.rs", "rand_kat.rs"):
+        assert os.path.exists(os.path.join(ROOT, "rust", "qmcb", "tests", t))
+
+
+def test_rand_known_answer_fixture_is_what_the_oracle_computes():
+    """tests/golden/rand_kat.json freezes the oracle's restatement of rand 0.8; rust/qmcb/tests/rand_kat.rs checks the
+    same file against rand itself on a machine with cargo.  Also re-derived here with Python integers, independently
+    of oracle.c, for the integer mappings."""
+    import ctypes as C
+    import json
+
+    from oracle import pyoracle as po
+
+    with open(os.path.join(ROOT, "tests", "golden", "rand_kat.json")) as f:
+        kat = json.load(f)
+    L, key = po.lib(), kat["key"]
+    words = [int(w, 16) for w in kat["words_hex"]]
+    assert words == [int(L.orc_stream_word(key, c)) for c in range(64)]
+    for case in kat["gen_bool"]:
+        p = float.fromhex(case["p_hex"])
+        thr = int(p * 2.0 ** 64)  # (p * 2^64) as u64: exact in Python for p < 1
+        assert case["results"] == [int(w < thr) for w in words]
+        assert case["results"] == [int(L.orc_gen_bool(key, C.byref(C.c_uint64(c)), p)) for c in range(64)]
+    for case in kat["gen_range_usize"]:
+        n = case["n"]
+        zone = ((n << (64 - n.bit_length())) - 1) & (2 ** 64 - 1)
+        cur, calls = 0, []
+        while cur < 64:
+            while cur < 64 and ((words[cur] * n) & (2 ** 64 - 1)) > zone:
+                cur += 1
+            if cur >= 64:
+                break
+            calls.append([(words[cur] * n) >> 64, cur + 1])
+            cur += 1
+        assert calls[:len(case["calls"])] == case["calls"] and len(calls) - len(case["calls"]) <= 1
+    assert kat["gen_std_bool"] == [int((w >> 32) >= 2 ** 31) for w in words]
+    assert kat["gen_f64"] == [float((w >> 11) * 2.0 ** -53).hex() for w in words]
+    unit = [(float.fromhex("0x1." + "%013x" % (w >> 12) + "p+0") - 1.0).hex() for w in words]
+    assert [v for v, _ in kat["gen_range_f64_unit"]] == unit
