@@ -247,6 +247,9 @@ int cmcb_create(const QmcbLattice *lattice /* transverse/longitudinal ignored */
                 const uint64_t *rng_keys, const uint8_t *init_state, int device, CmcbHandle **out);
 int cmcb_destroy(CmcbHandle *h);
 int cmcb_set_stream(CmcbHandle *h, void *cuda_stream);
+/* "fused" 1 (default): the bit-packed square layout runs both colours of many sweeps in ONE launch (the blocks of a
+ * replica meet at a per-replica barrier between colour passes); 0: one launch per colour pass.  Same results. */
+int cmcb_set_option(CmcbHandle *h, const char *name, int64_t value);
 /* nsweeps checkerboard sweeps: every site once per sweep, colour by colour, with the reference's
  * per-site rule (do_spin_flip delta_e graph.rs:98-115, should_flip :339-347). */
 int cmcb_sweeps(CmcbHandle *h, uint64_t nsweeps);

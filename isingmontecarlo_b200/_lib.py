@@ -98,6 +98,7 @@ SIGNATURES = {
     "cmcb_create": [C.POINTER(Lattice), f64p, C.c_uint32, f64p, u64p, u8p, C.c_int, vpp],
     "cmcb_destroy": [vp],
     "cmcb_set_stream": [vp, vp],
+    "cmcb_set_option": [vp, C.c_char_p, C.c_int64],
     "cmcb_sweeps": [vp, C.c_uint64],
     "cmcb_enqueue_sweeps": [vp, C.c_uint64],
     "cmcb_synchronize": [vp],

@@ -51,6 +51,9 @@ class GraphState:
     def set_stream(self, cuda_stream_ptr):
         check(self._L.cmcb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_option(self, name, value):
+        check(self._L.cmcb_set_option(self._h, name.encode(), int(value)))
+
     def do_time_step(self, nsweeps=1):
         """One checkerboard sweep = every site once (the reference's do_time_step makes N/2 random
         single-spin attempts, graph.rs:350-406; the schedule differs, the per-site rule does not)."""

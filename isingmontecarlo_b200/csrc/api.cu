@@ -35,6 +35,8 @@ int launch_pt_export(const SseDev &D, const PtDev &P, uint64_t *rec, cudaStream_
 void launch_pt_apply(const SseDev &D, const PtDev &P, const uint64_t *rec, uint32_t S, cudaStream_t st);
 void launch_cls_generic(const ClsDev &D, uint32_t colour, uint32_t cstart, uint32_t ccount, uint64_t sweep, cudaStream_t st);
 void launch_cls_square(const ClsDev &D, uint32_t colour, uint64_t sweep, cudaStream_t st);
+int launch_cls_square_fused(const ClsDev &D, uint64_t sweep0, uint32_t nsweeps, unsigned int *bar, unsigned int *bar_count, int nsm,
+                            cudaStream_t st);  // returns #launches, <0 if the blocks of a replica cannot be co-resident
 void launch_cls_square_measure(const ClsDev &D, unsigned long long *unsat, unsigned long long *up, cudaStream_t st);
 void launch_cls_square_pack(const ClsDev &D, const uint8_t *bytes, cudaStream_t st);
 void launch_cls_square_unpack(const ClsDev &D, uint8_t *bytes, cudaStream_t st);
@@ -1635,6 +1637,11 @@ struct CmcbHandle {
     double J_uniform = 0.0, bias_uniform = 0.0;
     double *adj_j_dev = nullptr, *biases_dev = nullptr;
     uint8_t *bytes_dev = nullptr;  // staging for the square layout
+    // fused multi-sweep launches of the square layout: per-replica barrier counters and how far they have advanced
+    unsigned int *bar_dev = nullptr;
+    unsigned int bar_count = 0;
+    int nsm = 148;
+    int fused = 1;  // cmcb_set_option("fused", 0): one launch per colour pass (round-1 behaviour, A/B measurements)
 };
 
 #define CHECK_C(h)                                              \
@@ -1890,8 +1897,34 @@ extern "C" int cmcb_set_stream(CmcbHandle *h, void *s) {
     h->stream = s ? (cudaStream_t)s : h->own_stream;
     return QMCB_OK;
 }
+extern "C" int cmcb_set_option(CmcbHandle *h, const char *name, int64_t value) {
+    if (!h || !name) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    if (!strcmp(name, "fused")) {
+        h->fused = value != 0;
+        return QMCB_OK;
+    }
+    return fail(QMCB_ERR_BAD_ARG, "unknown option");
+}
 extern "C" int cmcb_enqueue_sweeps(CmcbHandle *h, uint64_t nsweeps) {
     CHECK_C(h);
+    if (h->square && h->fused && nsweeps) {
+        // both colours of up to 4096 sweeps per launch; the blocks of a replica meet at a barrier between colour passes
+        if (!h->bar_dev) {
+            CUDA_TRY(h->pool.alloc(&h->bar_dev, h->D.R));
+            CUDA_TRY(cudaMemsetAsync(h->bar_dev, 0, sizeof(unsigned int) * h->D.R, h->stream));
+            cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, h->device);
+        }
+        uint64_t left = nsweeps;
+        while (left) {
+            const uint32_t chunk = (uint32_t)std::min<uint64_t>(left, 4096);
+            const int nl = launch_cls_square_fused(h->D, h->sweeps, chunk, h->bar_dev, &h->bar_count, h->nsm, h->stream);
+            if (nl < 0) break;  // not co-resident on this device: fall through to the per-pass launches
+            h->launches += (uint64_t)nl, h->sweeps += chunk, left -= chunk;
+        }
+        CUDA_TRY(cudaGetLastError());
+        if (!left) return QMCB_OK;
+        nsweeps = left;
+    }
     for (uint64_t s = 0; s < nsweeps; s++, h->sweeps++) {
         for (uint32_t c = 0; c < h->ncolours; c++) {
             if (h->square) launch_cls_square(h->D, c, h->sweeps, h->stream);

@@ -17,6 +17,8 @@
 //    group of 32 ranks of a colour, threshold table per (replica, site class).
 //  * L x L periodic square lattice, uniform J and bias: spins bit-packed in two colour planes,
 //    one thread per 32 sites: neighbour counts by bit-sliced adders, 4 Philox calls, no divergence.
+#include <algorithm>
+
 #include "classical.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -81,103 +83,155 @@ __device__ __forceinline__ void philox_rk(uint32_t c0, uint32_t c1, uint32_t c2,
 // threshold bit of every site is muxed from the block-uniform masks of its class group (G logic ops),
 // then lt |= eq & ~p & t;  eq &= ~(p ^ t)  (3 logic ops) decide all 32 sites, ties included.
 template <int G>
-__global__ void __launch_bounds__(256, 4) k_cls_square(ClsDev D, uint32_t colour, uint64_t sweep) {
-    __shared__ uint32_t s_rk[20];
-    __shared__ uint32_t s_tk[G > 0 ? G : 1][32];  // s_tk[g][k]: bit (31 - k) of the threshold of group g as a mask
-    __shared__ __align__(16) uint32_t s_cmsk[G + 1][12];  // [set][own * 5 + cnt] class membership as masks; set G = always-flip
-    const uint32_t r = blockIdx.y;
-    {
-        const uint64_t key = D.key[r];
-        if (threadIdx.x < 10) {
-            s_rk[2 * threadIdx.x] = (uint32_t)key + 0x9E3779B9u * threadIdx.x;
-            s_rk[2 * threadIdx.x + 1] = (uint32_t)(key >> 32) + 0xBB67AE85u * threadIdx.x;
-        }
-        for (uint32_t i = threadIdx.x; i < (uint32_t)G * 32; i += blockDim.x) {
-            const uint32_t T = D.sq_gT[(size_t)r * SQ_MAXG + (i >> 5)];
-            s_tk[i >> 5][i & 31] = (T >> (31 - (i & 31))) & 1u;  // 0/1: used as a multiplier (FMA pipe), not a mask
-        }
-        for (uint32_t i = threadIdx.x; i < (uint32_t)(G + 1) * 10; i += blockDim.x) {
-            const uint32_t set = i / 10, j = i % 10;  // j = own * 5 + cnt  ->  class bit own * 8 + cnt
-            const uint32_t members = set < (uint32_t)G ? D.sq_gmem[(size_t)r * SQ_MAXG + set] : D.sq_always[r];
-            s_cmsk[set][j] = ((members >> ((j / 5) * 8 + (j % 5))) & 1u) ? 0xFFFFFFFFu : 0u;
-        }
+struct SqTables {
+    uint32_t rk[20];
+    uint32_t tk[G > 0 ? G : 1][32];               // tk[g][k]: bit (31 - k) of the threshold of group g (0/1: a multiplier, FMA pipe)
+    __align__(16) uint32_t cmsk[G + 1][12];       // [set][own * 5 + cnt] class membership as masks; set G = always-flip
+};
+template <int G>
+__device__ __forceinline__ void sq_load_tables(const ClsDev &D, uint32_t r, SqTables<G> &S) {
+    const uint64_t key = D.key[r];
+    if (threadIdx.x < 10) {
+        S.rk[2 * threadIdx.x] = (uint32_t)key + 0x9E3779B9u * threadIdx.x;
+        S.rk[2 * threadIdx.x + 1] = (uint32_t)(key >> 32) + 0xBB67AE85u * threadIdx.x;
     }
-    __syncthreads();
-    const uint32_t WPR = D.L >> 6;                  // 32-bit words per row of one colour plane
-    const uint32_t words_per_plane = D.L * WPR;
-    uint32_t *mine = D.planes + ((size_t)r * 2 + colour) * words_per_plane;
-    const uint32_t *other = D.planes + ((size_t)r * 2 + (colour ^ 1u)) * words_per_plane;
-    // a block walks over several chunks of 256 words so that the set-up above is paid once
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < words_per_plane; t += gridDim.x * blockDim.x) {
-        uint32_t y, w;
-        if (D.sq_wpr_shift >= 0) y = t >> D.sq_wpr_shift, w = t & (WPR - 1u);
-        else y = t / WPR, w = t - y * WPR;
-        const uint32_t yu = y == 0 ? D.L - 1 : y - 1, yd = y + 1 == D.L ? 0 : y + 1;
-        const uint32_t own = mine[t];
-        const uint32_t same = other[t];
-        const uint32_t up = other[yu * WPR + w], dn = other[yd * WPR + w];
-        uint32_t side;
-        if ((y + colour) & 1u) {  // my x is odd: the second horizontal neighbour has compressed index xc + 1
-            const uint32_t nxt = other[w + 1 == WPR ? t + 1 - WPR : t + 1];
-            side = (same >> 1) | (nxt << 31);
-        } else {  // my x is even: neighbour xc - 1
-            const uint32_t prv = other[w == 0 ? t + WPR - 1 : t - 1];
-            side = (same << 1) | (prv >> 31);
-        }
-        // bit-sliced count of anti-aligned neighbours: cnt = lo + 2 mid + 4 hi, then one-hot masks
-        const uint32_t a = own ^ same, b = own ^ side, c = own ^ up, d = own ^ dn;
-        const uint32_t s1 = a ^ b ^ c, c1 = (a & b) | (c & (a ^ b));
-        const uint32_t lo = s1 ^ d, c2 = s1 & d;
-        const uint32_t mid = c1 ^ c2, hi = c1 & c2;
-        uint32_t cm[5];
-        cm[0] = ~(lo | mid | hi), cm[1] = lo & ~mid, cm[2] = mid & ~lo, cm[3] = lo & mid, cm[4] = hi;
-        // sites of a set of classes: the membership of class (own, cnt) is a block-uniform mask in shared memory
-        auto class_sites = [&](const uint32_t *mk) -> uint32_t {
-            uint32_t m0 = 0, m1 = 0;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)G * 32; i += blockDim.x) {
+        const uint32_t T = D.sq_gT[(size_t)r * SQ_MAXG + (i >> 5)];
+        S.tk[i >> 5][i & 31] = (T >> (31 - (i & 31))) & 1u;
+    }
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(G + 1) * 10; i += blockDim.x) {
+        const uint32_t set = i / 10, j = i % 10;  // j = own * 5 + cnt  ->  class bit own * 8 + cnt
+        const uint32_t members = set < (uint32_t)G ? D.sq_gmem[(size_t)r * SQ_MAXG + set] : D.sq_always[r];
+        S.cmsk[set][j] = ((members >> ((j / 5) * 8 + (j % 5))) & 1u) ? 0xFFFFFFFFu : 0u;
+    }
+}
+// the update of one word (32 sites of one colour) at sweep `sweep`.  CG: the planes are read through L2 (another SM
+// wrote the neighbouring rows earlier in the same launch).
+template <int G, bool CG>
+__device__ __forceinline__ void sq_update_word(const ClsDev &D, const SqTables<G> &S, uint32_t *mine, const uint32_t *other, uint32_t t,
+                                               uint32_t colour, uint64_t sweep) {
+    auto ld = [](const uint32_t *p) -> uint32_t { return CG ? __ldcg(p) : *p; };
+    const uint32_t WPR = D.L >> 6;
+    uint32_t y, w;
+    if (D.sq_wpr_shift >= 0) y = t >> D.sq_wpr_shift, w = t & (WPR - 1u);
+    else y = t / WPR, w = t - y * WPR;
+    const uint32_t yu = y == 0 ? D.L - 1 : y - 1, yd = y + 1 == D.L ? 0 : y + 1;
+    const uint32_t own = ld(mine + t);
+    const uint32_t same = ld(other + t);
+    const uint32_t up = ld(other + yu * WPR + w), dn = ld(other + yd * WPR + w);
+    uint32_t side;
+    if ((y + colour) & 1u) {  // my x is odd: the second horizontal neighbour has compressed index xc + 1
+        const uint32_t nxt = ld(other + (w + 1 == WPR ? t + 1 - WPR : t + 1));
+        side = (same >> 1) | (nxt << 31);
+    } else {  // my x is even: neighbour xc - 1
+        const uint32_t prv = ld(other + (w == 0 ? t + WPR - 1 : t - 1));
+        side = (same << 1) | (prv >> 31);
+    }
+    // bit-sliced count of anti-aligned neighbours: cnt = lo + 2 mid + 4 hi, then one-hot masks
+    const uint32_t a = own ^ same, b = own ^ side, c = own ^ up, d = own ^ dn;
+    const uint32_t s1 = a ^ b ^ c, c1 = (a & b) | (c & (a ^ b));
+    const uint32_t lo = s1 ^ d, c2 = s1 & d;
+    const uint32_t mid = c1 ^ c2, hi = c1 & c2;
+    uint32_t cm[5];
+    cm[0] = ~(lo | mid | hi), cm[1] = lo & ~mid, cm[2] = mid & ~lo, cm[3] = lo & mid, cm[4] = hi;
+    // sites of a set of classes: the membership of class (own, cnt) is a block-uniform mask in shared memory
+    auto class_sites = [&](const uint32_t *mk) -> uint32_t {
+        uint32_t m0 = 0, m1 = 0;
 #pragma unroll
-            for (int cc = 0; cc < 5; cc++) m0 |= cm[cc] & mk[cc], m1 |= cm[cc] & mk[5 + cc];
-            return (~own & m0) | (own & m1);
-        };
-        uint32_t flip = class_sites(s_cmsk[G]);  // delta_e <= 0 (threshold 2^32): always
-        if (G > 0) {
-            uint32_t sel[G > 0 ? G : 1], eq = 0;
+        for (int cc = 0; cc < 5; cc++) m0 |= cm[cc] & mk[cc], m1 |= cm[cc] & mk[5 + cc];
+        return (~own & m0) | (own & m1);
+    };
+    uint32_t flip = class_sites(S.cmsk[G]);  // delta_e <= 0 (threshold 2^32): always
+    if (G > 0) {
+        uint32_t sel[G > 0 ? G : 1], eq = 0;
 #pragma unroll
-            for (int g = 0; g < G; g++) sel[g] = class_sites(s_cmsk[g]), eq |= sel[g];
-            uint32_t lt = 0;
-            uint32_t pl[4];
-            // planes 0..11 always; 12..15 and 16..31 only while some site still ties with its threshold
-            // (p = 2^-12 resp. 2^-16 per site), so most words need three Philox calls
+        for (int g = 0; g < G; g++) sel[g] = class_sites(S.cmsk[g]), eq |= sel[g];
+        uint32_t lt = 0;
+        uint32_t pl[4];
+        // planes 0..11 always; 12..15 and 16..31 only while some site still ties with its threshold
+        // (p = 2^-12 resp. 2^-16 per site), so most words need three Philox calls
 #define RIPPLE_PLANE(k)                                              \
     {                                                                \
         uint32_t tk = 0;                                             \
-        _Pragma("unroll") for (int g = 0; g < G; g++) tk = sel[g] * s_tk[g][k] + tk; /* disjoint sel: mux by multiply-add */ \
+        _Pragma("unroll") for (int g = 0; g < G; g++) tk = sel[g] * S.tk[g][k] + tk; /* disjoint sel: mux by multiply-add */ \
         const uint32_t p = pl[(k) & 3];                              \
         lt |= eq & ~p & tk;                                          \
         eq &= ~(p ^ tk);                                             \
     }
 #pragma unroll
-            for (int q = 0; q < 3; q++) {
-                philox_rk(4 * t + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, s_rk, pl);
+        for (int q = 0; q < 3; q++) {
+            philox_rk(4 * t + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
 #pragma unroll
-                for (int i = 0; i < 4; i++) RIPPLE_PLANE(4 * q + i)
-            }
+            for (int i = 0; i < 4; i++) RIPPLE_PLANE(4 * q + i)
+        }
+        if (eq) {
+            philox_rk(4 * t + 3, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
+#pragma unroll
+            for (int i = 0; i < 4; i++) RIPPLE_PLANE(12 + i)
             if (eq) {
-                philox_rk(4 * t + 3, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, s_rk, pl);
-#pragma unroll
-                for (int i = 0; i < 4; i++) RIPPLE_PLANE(12 + i)
-                if (eq) {
 #pragma unroll 1
-                    for (int q = 0; q < 4; q++) {
-                        philox_rk(4 * t + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB2 | colour, s_rk, pl);
+                for (int q = 0; q < 4; q++) {
+                    philox_rk(4 * t + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB2 | colour, S.rk, pl);
 #pragma unroll
-                        for (int i = 0; i < 4; i++) RIPPLE_PLANE(16 + 4 * q + i)
-                    }
+                    for (int i = 0; i < 4; i++) RIPPLE_PLANE(16 + 4 * q + i)
                 }
             }
-#undef RIPPLE_PLANE
-            flip |= lt;
         }
-        mine[t] = own ^ flip;
+#undef RIPPLE_PLANE
+        flip |= lt;
+    }
+    if (CG) __stcg(mine + t, own ^ flip);
+    else mine[t] = own ^ flip;
+}
+
+// one colour pass of one sweep per launch
+template <int G>
+__global__ void __launch_bounds__(256, 4) k_cls_square(ClsDev D, uint32_t colour, uint64_t sweep) {
+    __shared__ SqTables<G> S;
+    const uint32_t r = blockIdx.y;
+    sq_load_tables<G>(D, r, S);
+    __syncthreads();
+    const uint32_t words_per_plane = D.L * (D.L >> 6);
+    uint32_t *mine = D.planes + ((size_t)r * 2 + colour) * words_per_plane;
+    const uint32_t *other = D.planes + ((size_t)r * 2 + (colour ^ 1u)) * words_per_plane;
+    // a block walks over several chunks of 256 words so that the set-up above is paid once
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < words_per_plane; t += gridDim.x * blockDim.x)
+        sq_update_word<G, false>(D, S, mine, other, t, colour, sweep);
+}
+
+// FUSED: both colours of `nsweeps` sweeps in one launch.  SQ_BPR blocks share a replica (each owns a band of rows) and
+// meet at a per-replica barrier in global memory between colour passes -- only the blocks of one replica exchange rows,
+// so nothing waits for the whole grid.  All blocks of the launch are co-resident (cooperative launch).
+#define SQ_BPR 4
+template <int G>
+__global__ void __launch_bounds__(128, 8) k_cls_square_sweeps(ClsDev D, uint32_t r0, uint64_t sweep0, uint32_t nsweeps, unsigned int *bar,
+                                                               unsigned int bar_base) {
+    __shared__ SqTables<G> S;
+    const uint32_t r = r0 + blockIdx.y;
+    sq_load_tables<G>(D, r, S);
+    __syncthreads();
+    const uint32_t words_per_plane = D.L * (D.L >> 6);
+    const uint32_t per = (words_per_plane + SQ_BPR - 1) / SQ_BPR;
+    const uint32_t t0 = blockIdx.x * per, t1 = min(t0 + per, words_per_plane);
+    uint32_t *plane0 = D.planes + (size_t)r * 2 * words_per_plane;
+    unsigned int arrivals = bar_base;
+    for (uint32_t s = 0; s < nsweeps; s++) {
+#pragma unroll 1
+        for (uint32_t colour = 0; colour < 2; colour++) {
+            uint32_t *mine = plane0 + colour * words_per_plane;
+            const uint32_t *other = plane0 + (colour ^ 1u) * words_per_plane;
+            for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) sq_update_word<G, true>(D, S, mine, other, t, colour, sweep0 + s);
+            // per-replica barrier: my rows are visible before the neighbours' next pass reads them
+            __syncthreads();
+            arrivals += SQ_BPR;
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(bar + r, 1u);
+                while ((int)(*(volatile unsigned int *)(bar + r) - arrivals) < 0) __nanosleep(32);
+                __threadfence();
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -274,6 +328,41 @@ void launch_cls_square(const ClsDev &D, uint32_t colour, uint64_t sweep, cudaStr
         case 5: k_cls_square<5><<<grid, 256, 0, st>>>(D, colour, sweep); break;
         case 6: k_cls_square<6><<<grid, 256, 0, st>>>(D, colour, sweep); break;
         default: k_cls_square<SQ_MAXG><<<grid, 256, 0, st>>>(D, colour, sweep); break;
+    }
+}
+// returns 0, or -1 if the fused kernel cannot hold a replica's blocks co-resident on this device
+template <int G>
+static int launch_sq_fused(const ClsDev &D, uint64_t sweep0, uint32_t nsweeps, unsigned int *bar, unsigned int *bar_count, int nsm, cudaStream_t st) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cls_square_sweeps<G>, 128, 0) != cudaSuccess || per_sm <= 0) return -1;
+    const uint32_t slots = (uint32_t)per_sm * (uint32_t)nsm;
+    const uint32_t rmax = slots / SQ_BPR;  // replicas one launch can hold co-resident
+    if (rmax == 0) return -1;
+    for (uint32_t r0 = 0; r0 < D.R; r0 += rmax) {
+        const uint32_t nr = std::min(rmax, D.R - r0);
+        ClsDev Dc = D;
+        uint32_t r0v = r0, ns = nsweeps;
+        uint64_t sw = sweep0;
+        unsigned int base = *bar_count;
+        void *args[] = {&Dc, &r0v, &sw, &ns, &bar, &base};
+        if (cudaLaunchCooperativeKernel((const void *)k_cls_square_sweeps<G>, dim3(SQ_BPR, nr), dim3(128), args, 0, st) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+    }
+    *bar_count += 2u * SQ_BPR * nsweeps;  // every replica's counter advances by the same amount (wraps modulo 2^32)
+    return (int)((D.R + rmax - 1) / rmax);
+}
+int launch_cls_square_fused(const ClsDev &D, uint64_t sweep0, uint32_t nsweeps, unsigned int *bar, unsigned int *bar_count, int nsm, cudaStream_t st) {
+    switch (D.sq_ngroups) {
+        case 0: return launch_sq_fused<0>(D, sweep0, nsweeps, bar, bar_count, nsm, st);
+        case 1: return launch_sq_fused<1>(D, sweep0, nsweeps, bar, bar_count, nsm, st);
+        case 2: return launch_sq_fused<2>(D, sweep0, nsweeps, bar, bar_count, nsm, st);
+        case 3: return launch_sq_fused<3>(D, sweep0, nsweeps, bar, bar_count, nsm, st);
+        case 4: return launch_sq_fused<4>(D, sweep0, nsweeps, bar, bar_count, nsm, st);
+        case 5: return launch_sq_fused<5>(D, sweep0, nsweeps, bar, bar_count, nsm, st);
+        case 6: return launch_sq_fused<6>(D, sweep0, nsweeps, bar, bar_count, nsm, st);
+        default: return launch_sq_fused<SQ_MAXG>(D, sweep0, nsweeps, bar, bar_count, nsm, st);
     }
 }
 void launch_cls_square_measure(const ClsDev &D, unsigned long long *unsat, unsigned long long *up, cudaStream_t st) {

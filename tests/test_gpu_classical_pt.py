@@ -256,3 +256,29 @@ def test_per_replica_hamiltonians_in_every_kernel_build(minblocks, heatbath):
             assert np.array_equal(g.dump_ops(r), ref.dump_ops()) and np.array_equal(g.state_ref()[r], ref.state())
     finally:
         g.set_option("minblocks", 0)
+
+
+def test_square_fused_launches_equal_per_pass_launches():
+    """cmcb_set_option("fused"): both colours of many sweeps in one cooperative launch (per-replica barrier between
+    colour passes) against one launch per colour pass, on a lattice whose row bands span several blocks; and more
+    replicas than one launch can hold co-resident (the launcher splits them)."""
+    from isingmontecarlo_b200.classical import GraphState
+
+    for L, R, sweeps in ((256, 5, 9), (64, 310, 4)):
+        edges = lattices.square_periodic(L, -1.0)
+        keys = 0xB2100000 + np.arange(R, dtype=np.uint64)
+        betas = np.linspace(0.3, 0.6, R)
+        a = GraphState(edges, np.zeros(L * L), keys, betas)
+        b = GraphState(edges, np.zeros(L * L), keys, betas)
+        b.set_option("fused", 0)
+        for chunk in (1, sweeps):
+            a.do_time_step(chunk), b.do_time_step(chunk)
+            assert np.array_equal(a.state_ref(), b.state_ref()), (L, chunk)
+        assert np.array_equal(a.get_energy(), b.get_energy())
+        assert a.launch_count() < b.launch_count()
+        if L == 256:  # and against the oracle
+            col, _ = a.colours()
+            ref = po.ClassicalOracle(edges, np.zeros(L * L), key=int(keys[2]))
+            ref.checkerboard_sweeps(float(betas[2]), col, 1 + sweeps)
+            assert np.array_equal(a.state_ref()[2], ref.state())
+        a.close(), b.close()
