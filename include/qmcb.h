@@ -161,6 +161,14 @@ int qmcb_itime_state(QmcbHandle *h, uint32_t r, uint64_t p, uint8_t *state /* [N
  * FFT.  samples_out ([R][T][N] bytes) and energy_out ([R]) are optional, as in qmcb_timesteps. */
 int qmcb_variable_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t sampling_freq, double *autocorr_out,
                                   uint8_t *samples_out, double *energy_out);
+/* calculate_spin_product_autocorrelation (autocorrelations.rs:53-71): the series are products of spins; product k is over
+ * product_vars[product_offsets[k] .. product_offsets[k+1]).  calculate_bond_autocorrelation (:80-97, value_for_bond
+ * qmc_ising.rs:988-997): one series per edge (whether the bond is satisfied).  autocorr_out [R][T] as above. */
+int qmcb_spin_product_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t sampling_freq, uint32_t n_products,
+                                      const uint32_t *product_offsets /* [n_products + 1] */, const uint32_t *product_vars,
+                                      double *autocorr_out, uint8_t *samples_out, double *energy_out);
+int qmcb_bond_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t sampling_freq, double *autocorr_out, uint8_t *samples_out,
+                              double *energy_out);
 int qmcb_get_rng_cursors(QmcbHandle *h, uint64_t *cursors /* [R] */);
 int qmcb_set_rng_cursor(QmcbHandle *h, uint32_t r, uint64_t cursor);
 int qmcb_get_rng_keys(QmcbHandle *h, uint64_t *keys /* [R] */);

@@ -70,6 +70,8 @@ SIGNATURES = {
     "qmcb_itime_magnetization": [vp, f64p, f64p, f64p],
     "qmcb_itime_state": [vp, C.c_uint32, C.c_uint64, u8p],
     "qmcb_variable_autocorrelation": [vp, C.c_uint64, C.c_uint64, f64p, u8p, f64p],
+    "qmcb_spin_product_autocorrelation": [vp, C.c_uint64, C.c_uint64, C.c_uint32, u32p, u32p, f64p, u8p, f64p],
+    "qmcb_bond_autocorrelation": [vp, C.c_uint64, C.c_uint64, f64p, u8p, f64p],
     "qmcb_get_rng_cursors": [vp, u64p],
     "qmcb_set_rng_cursor": [vp, C.c_uint32, C.c_uint64],
     "qmcb_get_rng_keys": [vp, u64p],

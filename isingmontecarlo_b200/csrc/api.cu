@@ -26,6 +26,8 @@ void launch_sse_itime_magnetization(const SseDev &D, long long *sums_dev, cudaSt
 void launch_sse_itime_state(const SseDev &D, uint32_t r, uint64_t p_at, uint32_t *out_dev, cudaStream_t st);
 void launch_autocorrelation(const uint8_t *samples, uint32_t R, uint32_t N, uint32_t T, uint32_t *bits, uint32_t *ones, double *out,
                             cudaStream_t st);
+void launch_spin_products(const uint8_t *samples, uint32_t R, uint32_t N, uint32_t T, uint32_t K, const uint32_t *offsets, const uint32_t *vars,
+                          uint8_t *derived, cudaStream_t st);
 void launch_sse_init_state(const SseDev &D, cudaStream_t st);
 int launch_sse_fast(const SseDev &D, const SseTuning &T, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
@@ -113,6 +115,11 @@ struct QmcbHandle {
     std::vector<double> Jtab_h, gam_h, hl_h, offset_h;  // [H][E], [H], [H], [H]
     std::vector<uint32_t> ham_slot_h;                   // [S] tempering: Hamiltonian row of each slot
     uint64_t *pt_rec_dev = nullptr;                     // record buffer of qmcb_pt_step_local
+    // autocorrelation work buffers (reused between calls)
+    uint32_t *ac_bits = nullptr, *ac_ones = nullptr, *ac_lists = nullptr;
+    double *ac_out = nullptr;
+    uint8_t *ac_derived = nullptr;
+    size_t ac_bits_cap = 0, ac_ones_cap = 0, ac_out_cap = 0, ac_derived_cap = 0, ac_lists_cap = 0;
     // multi-GPU tempering: NCCL communicator (qmcb_pt_comm_init / qmcb_pt_comm_attach)
     void *comm = nullptr;
     bool own_comm = false;
@@ -707,35 +714,85 @@ extern "C" int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t freq, double *
     return timesteps_impl(h, t, freq, energy_out, samples_out, false);
 }
 
-// QmcAutoCorrelations::calculate_variable_autocorrelation (autocorrelations.rs:48-61, fft_autocorrelation :99-133):
-// t sweeps sampled every sampling_freq, every variable's +-1 time series mean-removed and normalised, circular
-// autocorrelation averaged over the variables.  The reference goes through an FFT; here the circular correlation of
-// a +-1 series is counted exactly with XOR + popcount on bit-packed time series (C[tau] = T - 2 * mismatches).
-extern "C" int qmcb_variable_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t freq, double *autocorr_out, uint8_t *samples_out,
-                                             double *energy_out) {
-    CHECK_H(h);
+// QmcAutoCorrelations (autocorrelations.rs:48-97; fft_autocorrelation :99-133): t sweeps sampled every sampling_freq, every
+// series mean-removed and normalised, circular autocorrelation averaged over the series.  The reference goes through an
+// FFT; here the circular correlation of a two-valued series is counted exactly with XOR + popcount on bit-packed time
+// series (C[tau] = T - 2 * mismatches).  Series: the variables themselves (n_products = 0), or products of spins
+// (calculate_spin_product_autocorrelation :53-71; a product of +-1 values is the parity of the spins, and the
+// normalisation makes the sign convention irrelevant), of which calculate_bond_autocorrelation (:80-97, value_for_bond
+// qmc_ising.rs:988-997) is the instance "one product per edge".  Work buffers belong to the handle and are reused.
+static int autocorrelation_impl(QmcbHandle *h, uint64_t t, uint64_t freq, uint32_t n_products, const uint32_t *offsets, const uint32_t *vars,
+                                double *autocorr_out, uint8_t *samples_out, double *energy_out) {
     if (!autocorr_out) return fail(QMCB_ERR_BAD_ARG, "null argument");
     if (freq == 0) freq = 1;
     const SseDev &D = h->D;
     const uint64_t T = t / freq;
     if (T == 0 || T > (1u << 20)) return fail(QMCB_ERR_BAD_ARG, "need between 1 and 2^20 samples");
+    uint32_t nv_total = 0;
+    if (n_products) {
+        if (!offsets || !vars || offsets[0] != 0) return fail(QMCB_ERR_BAD_ARG, "product lists missing");
+        for (uint32_t k = 0; k < n_products; k++)
+            if (offsets[k + 1] < offsets[k]) return fail(QMCB_ERR_BAD_ARG, "product offsets must not decrease");
+        nv_total = offsets[n_products];
+        for (uint32_t i = 0; i < nv_total; i++)
+            if (vars[i] >= D.N) return fail(QMCB_ERR_BAD_ARG, "product variable out of range");
+    }
     int rc = timesteps_impl(h, t, freq, energy_out, samples_out, true);
     if (rc) return rc;
+    const uint32_t K = n_products ? n_products : D.N;  // number of series per replica
     const uint32_t Tw = (uint32_t)((T + 31) / 32);
-    uint32_t *bits = nullptr, *ones = nullptr;
-    double *out_dev = nullptr;
-    cudaError_t e = cudaMalloc(&bits, sizeof(uint32_t) * (size_t)D.R * D.N * (2 * Tw + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&ones, sizeof(uint32_t) * (size_t)D.R * D.N);
-    if (e == cudaSuccess) e = cudaMalloc(&out_dev, sizeof(double) * (size_t)D.R * T);
-    if (e == cudaSuccess) {
-        launch_autocorrelation(h->samples_dev, D.R, D.N, (uint32_t)T, bits, ones, out_dev, h->stream);
-        h->launches += 2;
-        e = cudaMemcpyAsync(autocorr_out, out_dev, sizeof(double) * (size_t)D.R * T, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    const size_t need_bits = (size_t)D.R * K * (2 * Tw + 1), need_ones = (size_t)D.R * K, need_out = (size_t)D.R * T;
+    const size_t need_der = n_products ? (size_t)D.R * T * K : 0, need_lists = n_products ? (size_t)n_products + 1 + nv_total : 0;
+    auto ensure = [&](auto **ptr, size_t &cap, size_t need) -> cudaError_t {
+        if (need <= cap) return cudaSuccess;
+        if (*ptr) h->pool.release(*ptr);
+        *ptr = nullptr, cap = 0;
+        cudaError_t e = h->pool.alloc(ptr, need);
+        if (e == cudaSuccess) cap = need;
+        return e;
+    };
+    cudaError_t e = ensure(&h->ac_bits, h->ac_bits_cap, need_bits);
+    if (e == cudaSuccess) e = ensure(&h->ac_ones, h->ac_ones_cap, need_ones);
+    if (e == cudaSuccess) e = ensure(&h->ac_out, h->ac_out_cap, need_out);
+    if (e == cudaSuccess) e = ensure(&h->ac_derived, h->ac_derived_cap, need_der);
+    if (e == cudaSuccess) e = ensure(&h->ac_lists, h->ac_lists_cap, need_lists);
+    if (e != cudaSuccess) return fail_cuda(e, "autocorrelation buffers", __FILE__, __LINE__);
+    const uint8_t *series = h->samples_dev;
+    if (n_products) {
+        e = cudaMemcpyAsync(h->ac_lists, offsets, sizeof(uint32_t) * (n_products + 1), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess && nv_total)
+            e = cudaMemcpyAsync(h->ac_lists + n_products + 1, vars, sizeof(uint32_t) * nv_total, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "copy product lists", __FILE__, __LINE__);
+        launch_spin_products(h->samples_dev, D.R, D.N, (uint32_t)T, n_products, h->ac_lists, h->ac_lists + n_products + 1, h->ac_derived, h->stream);
+        h->launches += 1;
+        series = h->ac_derived;
     }
-    cudaFree(bits), cudaFree(ones), cudaFree(out_dev);
+    launch_autocorrelation(series, D.R, K, (uint32_t)T, h->ac_bits, h->ac_ones, h->ac_out, h->stream);
+    h->launches += 2;
+    e = cudaMemcpyAsync(autocorr_out, h->ac_out, sizeof(double) * (size_t)D.R * T, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) return fail_cuda(e, "autocorrelation", __FILE__, __LINE__);
     return QMCB_OK;
+}
+extern "C" int qmcb_variable_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t freq, double *autocorr_out, uint8_t *samples_out,
+                                             double *energy_out) {
+    CHECK_H(h);
+    return autocorrelation_impl(h, t, freq, 0, nullptr, nullptr, autocorr_out, samples_out, energy_out);
+}
+extern "C" int qmcb_spin_product_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t freq, uint32_t n_products, const uint32_t *product_offsets,
+                                                 const uint32_t *product_vars, double *autocorr_out, uint8_t *samples_out, double *energy_out) {
+    CHECK_H(h);
+    if (n_products == 0) return fail(QMCB_ERR_BAD_ARG, "no products given");
+    return autocorrelation_impl(h, t, freq, n_products, product_offsets, product_vars, autocorr_out, samples_out, energy_out);
+}
+extern "C" int qmcb_bond_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t freq, double *autocorr_out, uint8_t *samples_out, double *energy_out) {
+    CHECK_H(h);
+    const uint32_t E = h->D.E;  // n_bonds() = edges.len() (qmc_ising.rs:984-986)
+    if (E == 0) return fail(QMCB_ERR_BAD_ARG, "lattice without edges");
+    std::vector<uint32_t> off(E + 1), vars(2 * (size_t)E);
+    for (uint32_t b = 0; b < E; b++) off[b] = 2 * b, vars[2 * b] = h->va_h[b], vars[2 * b + 1] = h->vb_h[b];
+    off[E] = 2 * E;
+    return autocorrelation_impl(h, t, freq, E, off.data(), vars.data(), autocorr_out, samples_out, energy_out);
 }
 
 extern "C" int qmcb_enqueue_sweeps(QmcbHandle *h, uint64_t t) {

@@ -8,6 +8,8 @@
 // pass, free-spin draws and sampling use all 32 lanes with coalesced accesses.
 // It also carries a serial FAST-order cluster step used as the on-device cross-check of the
 // warp-parallel FAST kernels in sse_fast.cu.
+#include <algorithm>
+
 #include "sse.cuh"
 
 #define SIDE_IN 0u
@@ -967,6 +969,23 @@ __global__ void __launch_bounds__(256) k_ac_corr(uint32_t N, uint32_t T, uint32_
         __syncthreads();
     }
     if (threadIdx.x == 0) out[(size_t)r * T + tau] = part[0] / (double)N;
+}
+// series of spin products (autocorrelations.rs:53-71): derived[r][t][k] = 1 iff an even number of the spins of product k is
+// true (the sign convention drops out of the normalised autocorrelation)
+__global__ void k_ac_products(const uint8_t *samples, uint32_t N, uint32_t T, uint32_t K, const uint32_t *offsets, const uint32_t *vars, uint8_t *derived) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y, r = blockIdx.z;
+    if (k >= K) return;
+    const uint8_t *s = samples + ((size_t)r * T + t) * N;
+    uint32_t par = 0;
+    for (uint32_t i = offsets[k]; i < offsets[k + 1]; i++) par ^= s[vars[i]] & 1u;
+    derived[((size_t)r * T + t) * K + k] = (uint8_t)(par ^ 1u);
+}
+void launch_spin_products(const uint8_t *samples, uint32_t R, uint32_t N, uint32_t T, uint32_t K, const uint32_t *offsets, const uint32_t *vars,
+                          uint8_t *derived, cudaStream_t st) {
+    for (uint32_t t0 = 0; t0 < T; t0 += 65535) {  // gridDim.y limit
+        const uint32_t nt = std::min(T - t0, 65535u);
+        k_ac_products<<<dim3((K + 127) / 128, nt, R), 128, 0, st>>>(samples + (size_t)t0 * N, N, T, K, offsets, vars, derived + (size_t)t0 * K);
+    }
 }
 void launch_autocorrelation(const uint8_t *samples, uint32_t R, uint32_t N, uint32_t T, uint32_t *bits, uint32_t *ones, double *out,
                             cudaStream_t st) {

@@ -302,6 +302,31 @@ class QmcIsingGraph:
                                                     None if smp is None else ptr(smp, C.c_uint8), None))
         return (out, smp) if return_samples else out
 
+    def calculate_spin_product_autocorrelation(self, timesteps, beta, var_products, sampling_freq=None, return_samples=False):
+        """QmcAutoCorrelations::calculate_spin_product_autocorrelation (autocorrelations.rs:53-71): var_products is a list
+        of variable lists; [R][T] array."""
+        self._set_beta(beta)
+        freq = 1 if sampling_freq is None else int(sampling_freq)
+        T = int(timesteps) // freq
+        off = np.zeros(len(var_products) + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(p) for p in var_products])
+        vs = np.ascontiguousarray([v for p in var_products for v in p], dtype=np.uint32)
+        out = np.zeros((self.R, T), dtype=np.float64)
+        smp = np.zeros((self.R, T, self.nvars), dtype=np.uint8) if return_samples else None
+        check(self._L.qmcb_spin_product_autocorrelation(self._h, int(timesteps), freq, len(var_products), ptr(off, C.c_uint32), ptr(vs, C.c_uint32),
+                                                        ptr(out, C.c_double), None if smp is None else ptr(smp, C.c_uint8), None))
+        return (out, smp) if return_samples else out
+
+    def calculate_bond_autocorrelation(self, timesteps, beta=None, sampling_freq=None, return_samples=False):
+        """QmcBondAutoCorrelations::calculate_bond_autocorrelation (autocorrelations.rs:80-97)"""
+        self._set_beta(beta)
+        freq = 1 if sampling_freq is None else int(sampling_freq)
+        T = int(timesteps) // freq
+        out = np.zeros((self.R, T), dtype=np.float64)
+        smp = np.zeros((self.R, T, self.nvars), dtype=np.uint8) if return_samples else None
+        check(self._L.qmcb_bond_autocorrelation(self._h, int(timesteps), freq, ptr(out, C.c_double), None if smp is None else ptr(smp, C.c_uint8), None))
+        return (out, smp) if return_samples else out
+
     def imaginary_time_magnetization(self):
         """imaginary_time_fold (qmc_ising.rs:815-821) with the magnetisation fold on the device: per replica
         (<m>, <m^2>, <|m|>) of the per-site magnetisation over the M imaginary-time slices."""

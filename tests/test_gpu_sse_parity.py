@@ -216,6 +216,31 @@ def fft_autocorrelation(samples):
     return r.sum(axis=1) / (n * tmax)
 
 
+def test_product_and_bond_autocorrelations_match_fft_restatement():
+    """calculate_spin_product_autocorrelation / calculate_bond_autocorrelation (autocorrelations.rs:53-97) against the
+    literal FFT restatement fed with the reference's own sample mappers (value_for_bond qmc_ising.rs:988-997)."""
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.two_d_periodic_mixed(4)
+    g = QmcIsingGraph(edges, 2.0, 0.0, 16, [5, 6, 7], 1.0, mode=MODE_FAST)
+    g.timesteps(50, 1.0)
+    prods = [[0, 1], [2, 5, 9], [3], [4, 8, 12, 15]]
+    ac, samples = g.calculate_spin_product_autocorrelation(96, 1.0, prods, 2, return_samples=True)
+    for r in range(3):
+        pm = 2.0 * samples[r].astype(np.float64) - 1.0
+        want = fft_autocorrelation(np.stack([pm[:, p].prod(axis=1) for p in prods], axis=1))
+        assert np.allclose(ac[r], want, rtol=0, atol=1e-10)
+    ac, samples = g.calculate_bond_autocorrelation(96, 1.0, 2, return_samples=True)
+    for r in range(3):
+        s = samples[r].astype(bool)
+        vals = []
+        for (a, b), j in edges:
+            even = ((s[:, a].astype(int) + s[:, b].astype(int)) % 2) == 0
+            vals.append(np.where(even if j < 0.0 else ~even, 1.0, -1.0))
+        want = fft_autocorrelation(np.stack(vals, axis=1))
+        assert np.allclose(ac[r], want, rtol=0, atol=1e-10, equal_nan=True)
+
+
 @pytest.mark.parametrize("T,freq", [(256, 1), (100, 3), (37, 2)])
 def test_variable_autocorrelation_matches_fft_restatement(T, freq):
     from isingmontecarlo_b200.sse import QmcIsingGraph
