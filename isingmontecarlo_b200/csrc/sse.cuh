@@ -47,6 +47,10 @@ struct SseDev {
     // FAST workspace
     uint32_t *parent;    // [R][N+cap+1] union-find parents over segment ids
     uint32_t *sid;       // [R][cap] COUNTER mode: a member of the cluster on the input side of each op (sse_counter.cu)
+    // generic interactions (Qmc, qmc_runner.rs:113-156): diagonal matrix elements from tables instead of (J, Gamma, h).
+    // g_w2[4 b + (s0 | s1 << 1)] for the two-variable interaction b, g_gam[v] for the constant one-variable op of
+    // variable v, stored at its bond index: g_gam[E + v].  NULL = the transverse-field Ising weights of qmc_ising.rs:863-888.
+    const double *g_w2, *g_gam;
     // heat-bath diagonal update (heatbath.rs:10-61 BondWeights); NULL = Metropolis rule
     const double *hb_cum, *hb_maxw;  // [Nb] cumulative / per-bond maximum diagonal weight
     double hb_total;
@@ -73,6 +77,7 @@ struct SseTuning {
 // the Hamiltonian one replica is updated with
 struct Ham {
     const double *J;
+    const double *gw2, *ggam;  // generic interaction tables (Interaction::at for in == out), or NULL
     double gamma, h;
     const double *hb_cum, *hb_maxw;
     double hb_total;
@@ -80,6 +85,7 @@ struct Ham {
 template <bool MH>
 __device__ __forceinline__ Ham ham_view(const SseDev &D, uint32_t r) {
     Ham m;
+    m.gw2 = D.g_w2, m.ggam = D.g_gam;
     if (MH && D.ham) {
         const uint32_t hi = D.ham[r];
         m.J = D.J_tab + (size_t)hi * D.E, m.gamma = D.gam_tab[hi], m.h = D.h_tab[hi];
@@ -112,6 +118,7 @@ __device__ __forceinline__ void bond_vars(const SseDev &D, uint32_t b, int kind,
 }
 // diagonal matrix element <s|H_b|s>: qmc_ising.rs:863-888 with inputs == outputs
 __device__ __forceinline__ double bond_weight(const Ham &Hm, uint32_t b, int kind, uint32_t s0, uint32_t s1) {
+    if (Hm.gw2) return kind == KIND_BOND ? __ldg(Hm.gw2 + 4 * (size_t)b + (s0 | (s1 << 1))) : __ldg(Hm.ggam + b);
     if (kind == KIND_BOND) {
         double j = __ldg(Hm.J + b);
         return fabs(j) + (s0 == s1 ? -j : j);

@@ -163,6 +163,7 @@ __device__ __forceinline__ int bkind(const SseDev &D, uint32_t b) {
 }
 template <bool HAS_H>
 __device__ __forceinline__ double bweight(const Ham &Hm, uint32_t b, int kind, uint32_t s0, uint32_t s1) {
+    if (Hm.gw2) return kind == KIND_BOND ? __ldg(Hm.gw2 + 4 * (size_t)b + (s0 | (s1 << 1))) : __ldg(Hm.ggam + b);  // generic interactions
     if (kind == KIND_BOND) {
         const double j = __ldg(Hm.J + b);
         return fabs(j) + (s0 == s1 ? -j : j);

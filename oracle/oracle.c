@@ -284,15 +284,35 @@ struct OrcSse {
     /* heat-bath diagonal update: BondWeights (heatbath.rs:10-13), NULL = Metropolis rule */
     double *hb_maxw, *hb_cum;
     int error;
+    /* generic Qmc (qmc_runner.rs:22-45): a list of interactions instead of (edges, transverse, longitudinal) */
+    struct OrcInteraction *inter;
+    uint32_t ninter;
+    int is_qmc, has_cluster_edges, breaks_ising_symmetry;
 };
 
+/* Interaction, qmc_runner.rs:406-421: type Full(constant) | Diagonal, mat, n, vars, constant_along_diagonal */
+typedef struct OrcInteraction {
+    int diagonal;  /* InteractionType::Diagonal */
+    int constant;  /* InteractionType::Full(true) */
+    int constant_along_diagonal;
+    uint32_t n, vars[2];
+    double mat[16];
+    uint32_t len;
+} OrcInteraction;
+
 static uint32_t num_bonds(const OrcSse *g) {
+    if (g->is_qmc) return g->ninter; /* qmc_runner.rs:177 */
     /* qmc_ising.rs:664-670 */
     return g->nedges + g->nvars + (fabs(g->longitudinal) > DBL_EPSILON ? g->nvars : 0u);
 }
 
 /* bonds_fn, qmc_ising.rs:671-681 */
 static void edge_fn(const OrcSse *g, uint32_t b, uint32_t vars[2], int *nv, int *constant) {
+    if (g->is_qmc) { /* bonds_fn, qmc_runner.rs:178 */
+        const OrcInteraction *it = &g->inter[b];
+        vars[0] = it->vars[0], vars[1] = it->vars[1], *nv = (int)it->n, *constant = it->constant;
+        return;
+    }
     if (b < g->nedges) {
         vars[0] = g->ea[b], vars[1] = g->eb[b], *nv = 2, *constant = 0;
     } else if (b < g->nedges + g->nvars) {
@@ -328,7 +348,9 @@ static double longitudinal_hamiltonian(int in, int out, double longitudinal) {
     return fabs(longitudinal) + t;
 }
 /* QmcIsingGraph::hamiltonian, qmc_ising.rs:179-205 */
+static double interaction_at(const OrcInteraction *it, const uint8_t *in, const uint8_t *out);
 static double hamiltonian(const OrcSse *g, uint32_t bond, const uint8_t *in, const uint8_t *out) {
+    if (g->is_qmc) return interaction_at(&g->inter[bond], in, out); /* qmc_runner.rs:172-174 */
     if (bond < g->nedges) return two_site_hamiltonian(in[0], in[1], out[0], out[1], g->J[bond]);
     if (bond < g->nedges + g->nvars) return transverse_hamiltonian(in[0], out[0], g->transverse);
     return longitudinal_hamiltonian(in[0], out[0], g->longitudinal);
@@ -392,10 +414,102 @@ void orc_sse_destroy(OrcSse *g) {
     free(g->ea), free(g->eb), free(g->J), free(g->ops);
     free(g->vfirst_p), free(g->vlast_p), free(g->vfirst_r), free(g->vlast_r);
     free(g->state), free(g->b_in), free(g->b_out), free(g->uf);
-    free(g->hb_maxw), free(g->hb_cum);
+    free(g->hb_maxw), free(g->hb_cum), free(g->inter);
     stack_free(&g->frontier), stack_free(&g->interior);
     free(g);
 }
+
+/* ===================================================================================
+ * Generic Qmc: qmc_runner.rs:46-156 (construction, interactions), :363-377 (timestep), :406-680 (Interaction)
+ * =================================================================================== */
+/* index_from_iter over outputs then inputs, last bit least significant (qmc_runner.rs:650-664) */
+static uint32_t index_from_state(const uint8_t *in, const uint8_t *out, uint32_t n, int with_outputs) {
+    uint32_t acc = 0;
+    if (with_outputs)
+        for (uint32_t k = 0; k < n; k++) acc = (acc << 1) | (out[k] ? 1u : 0u);
+    for (uint32_t k = 0; k < n; k++) acc = (acc << 1) | (in[k] ? 1u : 0u);
+    return acc;
+}
+/* Interaction::at, qmc_runner.rs:560-600 */
+static double interaction_at(const OrcInteraction *it, const uint8_t *in, const uint8_t *out) {
+    if (!it->diagonal && it->constant) return it->mat[0];
+    if (!it->diagonal) return it->mat[index_from_state(in, out, it->n, 1)];
+    for (uint32_t k = 0; k < it->n; k++)
+        if (in[k] != out[k]) return 0.0;
+    return it->mat[index_from_state(in, out, it->n, 0)];
+}
+static int all_equal(const double *v, uint32_t len, uint32_t stride) {
+    for (uint32_t k = 1; k < len; k++) /* try_fold: every item against the one before it, |old - item| < EPSILON */
+        if (!(fabs(v[(k - 1) * stride] - v[k * stride]) < DBL_EPSILON)) return 0;
+    return 1;
+}
+/* Interaction::sym_under_ising, qmc_runner.rs:626-648 */
+static int sym_under_ising(const OrcInteraction *it) {
+    if (!it->diagonal && it->constant) return 1;
+    if (it->diagonal && it->constant_along_diagonal) return 1;
+    if (!it->diagonal) {
+        const uint32_t mask = (1u << (it->n << 1)) - 1u;
+        for (uint32_t x = 0; x < (1u << it->n); x++)
+            if (!(fabs(it->mat[x] - it->mat[(~x) & mask]) < DBL_EPSILON)) return 0;
+        return 1;
+    }
+    const uint32_t mask = (1u << it->n) - 1u;
+    for (uint32_t x = 0; x < (1u << (it->n >> 1)); x++)
+        if (!(fabs(it->mat[x] - it->mat[(~x) & mask]) < DBL_EPSILON)) return 0;
+    return 1;
+}
+
+/* Qmc::new_with_state (qmc_runner.rs:54-87): cutoff = nvars; state drawn from the stream when NULL (Qmc::new :48-51) */
+OrcSse *orc_qmc_create(uint32_t nvars, uint64_t rng_key, const uint8_t *state_or_null) {
+    uint32_t dummy = 0;
+    double dj = 0.0;
+    OrcSse *g = orc_sse_create(nvars, 0, &dummy, &dummy, &dj, 0.0, 0.0, nvars, rng_key, state_or_null);
+    g->is_qmc = 1, g->offset = 0.0;
+    return g;
+}
+/* make_interaction / make_interaction_and_offset / make_diagonal_interaction / make_diagonal_interaction_and_offset
+ * (qmc_runner.rs:113-156) with Interaction::new / new_offset / new_diagonal / new_diagonal_offset (:424-558).
+ * Returns 0, or 1 "Matrix size must be power of 2", 2 "Given x vars, expected n", 3 "Interaction contains negative
+ * weights", 4 more than two variables (not restated). */
+int orc_qmc_make_interaction(OrcSse *g, const double *mat, uint32_t len, const uint32_t *vars, uint32_t nvars_given, int diagonal, int and_offset) {
+    OrcInteraction it;
+    memset(&it, 0, sizeof it);
+    uint32_t pw = 0;
+    while ((1u << pw) < len) pw++;
+    if ((1u << pw) != len || len > 16) return len > 16 ? 4 : 1;
+    it.n = diagonal ? pw : pw >> 1;
+    if (nvars_given > 2 || it.n > 2) return 4;
+    memcpy(it.mat, mat, sizeof(double) * len);
+    it.len = len, it.diagonal = diagonal;
+    double min_diag = 0.0;
+    if (and_offset) { /* new_offset :508-521 / new_diagonal_offset :424-436 */
+        const uint32_t tn = 1u << it.n, stride = diagonal ? 1u : tn + 1u;
+        min_diag = DBL_MAX;
+        for (uint32_t k = 0; k < tn; k++) min_diag = min_diag < it.mat[k * stride] ? min_diag : it.mat[k * stride];
+        for (uint32_t k = 0; k < tn; k++) it.mat[k * stride] -= min_diag;
+    }
+    if (!diagonal) {
+        for (uint32_t k = 0; k < len; k++)
+            if (it.mat[k] < 0.0) return 3;
+        if (it.n != nvars_given) return 2;
+        it.constant = all_equal(it.mat, len, 1);
+        it.constant_along_diagonal = all_equal(it.mat, 1u << it.n, (1u << it.n) + 1u);
+    } else {
+        it.constant_along_diagonal = all_equal(it.mat, len, 1);
+        if (it.n != nvars_given) return 2;
+    }
+    for (uint32_t k = 0; k < nvars_given; k++) it.vars[k] = vars[k];
+    /* add_interaction :90-105 */
+    if (it.constant && it.n == 1) g->has_cluster_edges = 1;
+    if (!sym_under_ising(&it)) g->breaks_ising_symmetry = 1;
+    g->inter = (OrcInteraction *)realloc(g->inter, sizeof(OrcInteraction) * (g->ninter + 1));
+    g->inter[g->ninter++] = it;
+    free(g->hb_maxw), free(g->hb_cum);
+    g->hb_maxw = g->hb_cum = NULL;
+    if (and_offset) g->offset -= min_diag;
+    return 0;
+}
+int orc_qmc_flags(const OrcSse *g) { return (g->has_cluster_edges ? 1 : 0) | (g->breaks_ising_symmetry ? 2 : 0); }
 
 void orc_sse_set_script(OrcSse *g, const uint64_t *words, uint64_t nwords) {
     g->rng.script = words, g->rng.script_len = nwords, g->rng.cursor = 0;
@@ -905,8 +1019,27 @@ static uint64_t cluster_and_free_spins(OrcSse *g, int mode) {
     return ncl;
 }
 
+/* Qmc::timestep, qmc_runner.rs:363-377: diagonal_update (:158-201, the cutoff grows there), cluster_update with Ising
+ * symmetry and no weights when should_do_cluster_update (:223-238, :278-281), flip_free_bits (:241-256).  Loop updates
+ * (directed_loop.rs) are not restated. */
+void orc_qmc_timestep(OrcSse *g, double beta, int mode) {
+    diagonal_step(g, beta, mode);
+    uint64_t grown = g->n + g->n / 2; /* :195 */
+    if (grown > g->cutoff) g->cutoff = grown;
+    if (!g->breaks_ising_symmetry && g->has_cluster_edges) {
+        if (mode != ORC_MODE_STRICT) cluster_update_fast(g, 0, 0);
+        else cluster_update_strict(g, 0);
+    }
+    for (uint32_t v = 0; v < g->nvars; v++)
+        if (g->vfirst_p[v] == NONE) g->state[v] = (uint8_t)gen_bool(&g->rng, 0.5);
+}
+
 /* QmcIsingGraph::timestep, qmc_ising.rs:644-795 (rvb off: default :122) */
 void orc_sse_timestep(OrcSse *g, double beta, int mode) {
+    if (g->is_qmc) {
+        orc_qmc_timestep(g, beta, mode);
+        return;
+    }
     diagonal_step(g, beta, mode);
     cluster_and_free_spins(g, mode);
     uint64_t grown = g->n + g->n / 2; /* :786 */
@@ -949,6 +1082,7 @@ void orc_sse_set_cutoff(OrcSse *g, uint64_t cutoff) { /* qmc_ising.rs:537-540 */
 uint64_t orc_sse_get_cursor(const OrcSse *g) { return g->rng.cursor; }
 void orc_sse_set_cursor(OrcSse *g, uint64_t cursor) { g->rng.cursor = cursor; }
 void orc_sse_set_key(OrcSse *g, uint64_t key) { g->rng.key = key; }
+uint64_t orc_sse_get_key(const OrcSse *g) { return g->rng.key; }
 double orc_sse_get_offset(const OrcSse *g) { return g->offset; }
 void orc_sse_get_state(const OrcSse *g, uint8_t *out) { memcpy(out, g->state, g->nvars); }
 void orc_sse_set_state(OrcSse *g, const uint8_t *in) { memcpy(g->state, in, g->nvars); }
@@ -1008,7 +1142,7 @@ int orc_sse_load_ops(OrcSse *g, const uint32_t *words, uint64_t nwords, const ui
         uint32_t w = words[p];
         if (w == ORC_OP_EMPTY) continue;
         uint32_t b = w & 0xFFFFFFu;
-        if (b >= g->nedges + 2 * g->nvars) return -1;
+        if (b >= (g->is_qmc ? g->ninter : g->nedges + 2 * g->nvars)) return -1;
         Node *nd = &g->ops[p];
         int nv, constant;
         edge_fn(g, b, nd->vars, &nv, &constant);

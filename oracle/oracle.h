@@ -59,6 +59,12 @@ int orc_sse_error(const OrcSse *g);
 void orc_sse_set_enable_heatbath(OrcSse *g, int enable);
 int orc_sse_get_enable_heatbath(const OrcSse *g);
 void orc_sse_timestep(OrcSse *g, double beta, int mode);
+/* generic Qmc (qmc_runner.rs): interactions of one or two variables; handles are OrcSse handles and every orc_sse_*
+ * accessor works on them */
+OrcSse *orc_qmc_create(uint32_t nvars, uint64_t rng_key, const uint8_t *state_or_null);
+int orc_qmc_make_interaction(OrcSse *g, const double *mat, uint32_t len, const uint32_t *vars, uint32_t nvars_given, int diagonal, int and_offset);
+int orc_qmc_flags(const OrcSse *g); /* bit 0 has_cluster_edges, bit 1 breaks_ising_symmetry */
+void orc_qmc_timestep(OrcSse *g, double beta, int mode);
 void orc_sse_single_diagonal_step(OrcSse *g, double beta);
 void orc_sse_single_diagonal_step_mode(OrcSse *g, double beta, int mode);
 uint64_t orc_sse_single_cluster_step(OrcSse *g, int mode);
@@ -73,6 +79,7 @@ void orc_sse_set_cutoff(OrcSse *g, uint64_t cutoff);
 uint64_t orc_sse_get_cursor(const OrcSse *g);
 void orc_sse_set_cursor(OrcSse *g, uint64_t cursor);
 void orc_sse_set_key(OrcSse *g, uint64_t key);
+uint64_t orc_sse_get_key(const OrcSse *g);
 double orc_sse_get_offset(const OrcSse *g);
 void orc_sse_get_state(const OrcSse *g, uint8_t *out);
 void orc_sse_set_state(OrcSse *g, const uint8_t *in);

@@ -61,6 +61,9 @@ def lib():
     sig("orc_sse_set_enable_heatbath", None, vp, C.c_int)
     sig("orc_sse_get_enable_heatbath", C.c_int, vp)
     sig("orc_sse_timestep", None, vp, C.c_double, C.c_int)
+    sig("orc_qmc_create", vp, C.c_uint32, C.c_uint64, u8p)
+    sig("orc_qmc_make_interaction", C.c_int, vp, f64p, C.c_uint32, u32p, C.c_uint32, C.c_int, C.c_int)
+    sig("orc_qmc_flags", C.c_int, vp)
     sig("orc_sse_single_diagonal_step", None, vp, C.c_double)
     sig("orc_sse_single_diagonal_step_mode", None, vp, C.c_double, C.c_int)
     sig("orc_sse_single_cluster_step", C.c_uint64, vp, C.c_int)
@@ -72,6 +75,7 @@ def lib():
     sig("orc_sse_get_cursor", C.c_uint64, vp)
     sig("orc_sse_set_cursor", None, vp, C.c_uint64)
     sig("orc_sse_set_key", None, vp, C.c_uint64)
+    sig("orc_sse_get_key", C.c_uint64, vp)
     sig("orc_sse_get_offset", C.c_double, vp)
     sig("orc_sse_get_state", None, vp, u8p)
     sig("orc_sse_set_state", None, vp, u8p)
@@ -324,3 +328,64 @@ def max_threads():
         return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
         return max(1, os.cpu_count() or 1)
+
+
+class QmcOracle(SseOracle):
+    """Generic Qmc<R, FastOps> (qmc_runner.rs:22-403): interactions of one or two variables given as matrices;
+    timestep = diagonal update, cluster update with Ising symmetry (when the interactions allow it), free-spin flips.
+    Every SseOracle accessor works on it."""
+
+    ERRORS = {1: "Matrix size must be power of 2", 2: "Given vars do not match the matrix size", 3: "Interaction contains negative weights",
+              4: "interactions of more than two variables are not restated"}
+
+    def __init__(self, nvars, key=0, state=None):
+        self.nvars = int(nvars)
+        st = None if state is None else np.ascontiguousarray(state, dtype=np.uint8)
+        self._h = lib().orc_qmc_create(self.nvars, key, None if st is None else _p(st, C.c_uint8))
+        self._script = None
+
+    def _make(self, mat, vars_, diagonal, and_offset):
+        m = np.ascontiguousarray(mat, dtype=np.float64)
+        v = np.ascontiguousarray(list(vars_) + [0, 0], dtype=np.uint32)
+        rc = lib().orc_qmc_make_interaction(self._h, _p(m, C.c_double), len(m), _p(v, C.c_uint32), len(vars_), int(diagonal), int(and_offset))
+        if rc:
+            raise ValueError(self.ERRORS.get(rc, str(rc)))
+
+    def make_interaction(self, mat, vars_):  # qmc_runner.rs:113-122
+        self._make(mat, vars_, False, False)
+
+    def make_interaction_and_offset(self, mat, vars_):  # :125-135
+        self._make(mat, vars_, False, True)
+
+    def make_diagonal_interaction(self, mat, vars_):  # :138-146
+        self._make(mat, vars_, True, False)
+
+    def make_diagonal_interaction_and_offset(self, mat, vars_):  # :149-156
+        self._make(mat, vars_, True, True)
+
+    @property
+    def has_cluster_edges(self):
+        return bool(lib().orc_qmc_flags(self._h) & 1)
+
+    @property
+    def breaks_ising_symmetry(self):
+        return bool(lib().orc_qmc_flags(self._h) & 2)
+
+
+def into_qmc(ising, edges, transverse, longitudinal):
+    """IntoQmc::into_qmc (qmc_ising.rs:943-976) for an SseOracle built from (edges, transverse, longitudinal): the same
+    stream, state, cutoff and operator string, the Hamiltonian restated as generic interactions."""
+    nvars = ising.nvars
+    q = QmcOracle(nvars, key=lib().orc_sse_get_key(ising._h), state=ising.state())
+    for (a, b), j in edges:
+        q.make_diagonal_interaction_and_offset([-j, j, j, -j], [a, b])
+    for v in range(nvars):
+        q.make_interaction([transverse] * 4, [v])
+    if abs(longitudinal) > np.finfo(np.float64).eps:
+        for v in range(nvars):
+            q.make_interaction([longitudinal, 0.0, 0.0, -longitudinal], [v])
+    q.load_ops(ising.dump_ops(), ising.state())  # increase_cutoff_to(self.cutoff) + set_manager(self.op_manager)
+    if q.cutoff < ising.cutoff:
+        lib().orc_sse_set_cutoff(q._h, ising.cutoff)
+    q.set_cursor(ising.cursor)
+    return q
