@@ -53,7 +53,7 @@ def dense_energy(nvars, inters, beta):
 def test_generic_interactions_match_exact_diagonalisation(mode):
     inters = [([0.3, 1.0, 1.0, 0.3], [0, 1], True), ([2.0, 0.5, 0.5, 2.0], [1, 2], True), ([0.2, 0.9, 0.9, 0.2], [2, 3], True),
               ([0.6, 1.4, 1.4, 0.6], [3, 0], True)] + [([g] * 4, [v], False) for v, g in enumerate([0.5, 1.0, 1.5, 0.8])]
-    beta, chains = 1.5, 48
+    beta, chains = 1.5, 256
     exact = dense_energy(4, inters, beta)
     reps = []
     for r in range(chains):
@@ -63,7 +63,7 @@ def test_generic_interactions_match_exact_diagonalisation(mode):
         assert q.has_cluster_edges and not q.breaks_ising_symmetry
         reps.append(q)
     po.sse_batch_timesteps(reps, 1000, [beta] * chains, mode)
-    _, e = po.sse_batch_timesteps(reps, 12000, [beta] * chains, mode)
+    _, e = po.sse_batch_timesteps(reps, 8000, [beta] * chains, mode)
     assert all(q.error == 0 and q.verify() for q in reps)
     mean, err = e.mean(), e.std(ddof=1) / np.sqrt(chains)
     assert abs(mean - exact) < 3.5 * err + 1e-9, (mean, err, exact)
