@@ -76,6 +76,28 @@ typedef struct QmcbHandle QmcbHandle;
 int qmcb_create(const QmcbLattice *lattice, uint32_t n_replicas, const double *betas,
                 const uint64_t *rng_keys, uint64_t cutoff0, uint64_t capacity,
                 const uint8_t *init_state, int device, QmcbHandle **out);
+/* ---- generic interactions: Qmc (qmc_runner.rs:22-403), IntoQmc::into_qmc (qmc_ising.rs:943-976) -------------------
+ * Interactions as the reference's make_interaction / make_diagonal_interaction take them: matrices in Interaction::at
+ * indexing (qmc_runner.rs:560-664: first variable most significant, outputs more significant than inputs), 2^nv entries
+ * for a diagonal interaction, 4^nv for a full one.  The weights of the diagonal update come from these tables (a
+ * different code path from the (J, Gamma, h) arithmetic of qmcb_create); Qmc::timestep = diagonal update, cluster
+ * update with Ising symmetry, free-spin flips (:363-377).  Supported shape (anything else: QMCB_ERR_UNSUPPORTED with the
+ * reason): E interactions of two variables, each symmetric under the global flip, followed by exactly one CONSTANT
+ * one-variable interaction per variable, in variable order -- what into_qmc builds, with arbitrary two-variable
+ * weights and per-variable transverse weights.  Loop updates (directed_loop.rs) are not offered.
+ * `offset`: what Qmc::get_offset returns (the *_and_offset constructors accumulate it on the host side). */
+typedef struct {
+    uint32_t nvars;
+    uint32_t n_interactions;
+    const uint32_t *nv;      /* [n] variables of each interaction (1 or 2) */
+    const uint32_t *vars;    /* [2 n] */
+    const uint32_t *mat_len; /* [n] 2^nv (diagonal) or 4^nv (full) */
+    const double *mats;      /* the matrices, concatenated */
+    double offset;
+    int do_loop_updates;     /* must be 0 */
+} QmcbInteractions;
+int qmcb_create_qmc(const QmcbInteractions *interactions, uint32_t n_replicas, const double *betas, const uint64_t *rng_keys,
+                    uint64_t cutoff0, uint64_t capacity, const uint8_t *init_state, int device, QmcbHandle **out);
 int qmcb_destroy(QmcbHandle *h);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = handle's own stream */
 int qmcb_set_stream(QmcbHandle *h, void *cuda_stream);

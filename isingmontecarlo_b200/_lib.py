@@ -26,11 +26,18 @@ class Lattice(C.Structure):
 
 
 u8p, u32p, u64p, f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_double))
+
+
+class Interactions(C.Structure):
+    _fields_ = [("nvars", C.c_uint32), ("n_interactions", C.c_uint32), ("nv", u32p), ("vars", u32p), ("mat_len", u32p), ("mats", f64p),
+                ("offset", C.c_double), ("do_loop_updates", C.c_int)]
+
 vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
 
 # name -> (argtypes); every function returns int except the two string getters
 SIGNATURES = {
     "qmcb_create": [C.POINTER(Lattice), C.c_uint32, f64p, u64p, C.c_uint64, C.c_uint64, u8p, C.c_int, vpp],
+    "qmcb_create_qmc": [C.POINTER(Interactions), C.c_uint32, f64p, u64p, C.c_uint64, C.c_uint64, u8p, C.c_int, vpp],
     "qmcb_destroy": [vp],
     "qmcb_set_stream": [vp, vp],
     "qmcb_set_mode": [vp, C.c_int],

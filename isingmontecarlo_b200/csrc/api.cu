@@ -126,6 +126,8 @@ struct QmcbHandle {
     int comm_rank = 0, comm_nranks = 1;
     uint64_t *pt_rec_all_dev = nullptr;  // [S] gathered records
     double *pt_energy_dev = nullptr;     // [S] per-segment energies of qmcb_pt_timesteps_sample
+    bool generic = false;  // created by qmcb_create_qmc: weights from interaction tables
+    std::vector<double> gw2_h, ggam_h;
     // kernel-selection knobs of the warp-parallel sweep (qmcb_set_option), per handle
     SseTuning tune{};
 };
@@ -412,6 +414,78 @@ extern "C" int qmcb_create(const QmcbLattice *lat, uint32_t R, const double *bet
     return QMCB_OK;
 }
 
+// Qmc with generic interactions (qmc_runner.rs:46-156, :406-680; into_qmc qmc_ising.rs:943-976)
+extern "C" int qmcb_create_qmc(const QmcbInteractions *I, uint32_t R, const double *betas, const uint64_t *keys, uint64_t cutoff0,
+                               uint64_t capacity, const uint8_t *init_state, int device, QmcbHandle **out) {
+    if (!I || !out || !I->nv || !I->vars || !I->mat_len || !I->mats || I->nvars == 0) return fail(QMCB_ERR_BAD_ARG, "null argument or no variables");
+    if (I->do_loop_updates) return fail(QMCB_ERR_UNSUPPORTED, "loop updates (directed_loop.rs:103-301) are not offered: do_loop_updates must be false");
+    const uint32_t N = I->nvars, n = I->n_interactions;
+    if (n < N) return fail(QMCB_ERR_UNSUPPORTED, "need one constant one-variable interaction per variable (cluster edges) after the two-variable ones");
+    const uint32_t E = n - N;
+    std::vector<uint32_t> va(E), vb(E);
+    std::vector<double> w2(4 * (size_t)E), gam((size_t)n, 0.0), Jz(E, 0.0);
+    const double *m = I->mats;
+    const double EPS = 2.220446049250313e-16;
+    for (uint32_t b = 0; b < n; b++) {
+        const uint32_t nv = I->nv[b], len = I->mat_len[b];
+        if (nv != 1 && nv != 2) return fail(QMCB_ERR_UNSUPPORTED, "interactions of more than two variables are not offered");
+        const bool diagonal = len == (1u << nv);
+        if (!diagonal && len != (1u << (2 * nv))) return fail(QMCB_ERR_BAD_ARG, "Matrix size must be power of 2 matching the variables");  // get_mat_var_size :666-680
+        if (!diagonal)
+            for (uint32_t k = 0; k < len; k++)
+                if (m[k] < 0.0) return fail(QMCB_ERR_BAD_ARG, "Interaction contains negative weights");  // Interaction::new :527-529
+        for (uint32_t k = 0; k < nv; k++)
+            if (I->vars[2 * b + k] >= N) return fail(QMCB_ERR_BAD_ARG, "interaction variable out of range");
+        if (b < E) {
+            if (nv != 2) return fail(QMCB_ERR_UNSUPPORTED, "interaction order: the two-variable interactions come first, then one constant one-variable interaction per variable");
+            if (I->vars[2 * b] == I->vars[2 * b + 1]) return fail(QMCB_ERR_BAD_ARG, "interaction with a repeated variable");
+            double d[4];  // diagonal elements by Interaction::at index (in0 << 1 | in1)
+            for (uint32_t x = 0; x < 4; x++) d[x] = diagonal ? m[x] : m[(x << 2) + x];
+            for (uint32_t x = 0; x < 4; x++)
+                if (d[x] < 0.0) return fail(QMCB_ERR_BAD_ARG, "negative diagonal weight (use the *_and_offset constructor)");
+            // sym_under_ising :626-648 on the diagonal, and no off-diagonal elements (they only matter for loop updates)
+            if (!(std::fabs(d[0] - d[3]) < EPS && std::fabs(d[1] - d[2]) < EPS))
+                return fail(QMCB_ERR_UNSUPPORTED, "a two-variable interaction breaks the Ising symmetry: the reference then runs no cluster update (qmc_runner.rs:278-281); not offered");
+            if (!diagonal)
+                for (uint32_t o = 0; o < 4; o++)
+                    for (uint32_t i = 0; i < 4; i++)
+                        if (o != i && m[(o << 2) + i] != 0.0) return fail(QMCB_ERR_UNSUPPORTED, "off-diagonal two-variable matrix elements need loop updates (not offered)");
+            va[b] = I->vars[2 * b], vb[b] = I->vars[2 * b + 1];
+            for (uint32_t s0 = 0; s0 < 2; s0++)
+                for (uint32_t s1 = 0; s1 < 2; s1++) w2[4 * (size_t)b + (s0 | (s1 << 1))] = d[(s0 << 1) | s1];
+        } else {
+            const uint32_t v = b - E;
+            if (nv != 1 || I->vars[2 * b] != v)
+                return fail(QMCB_ERR_UNSUPPORTED, "interaction order: after the two-variable interactions, exactly one one-variable interaction per variable, in variable order");
+            bool constant = !diagonal;  // InteractionType::Full(true): every matrix element equal
+            for (uint32_t k = 1; constant && k < len; k++) constant = std::fabs(m[k - 1] - m[k]) < EPS;
+            if (!constant) return fail(QMCB_ERR_UNSUPPORTED, "one-variable interactions must be constant (cluster edges, cluster.rs:284-286)");
+            gam[b] = m[0];
+        }
+        m += len;
+    }
+    QmcbLattice lat{N, E, va.data(), vb.data(), Jz.data(), gam[E], 0.0};
+    QmcbHandle *h = nullptr;
+    int rc = qmcb_create(&lat, R, betas, keys, cutoff0, capacity, init_state, device, &h);
+    if (rc) return rc;
+    SseDev &D = h->D;
+    double *w2_dev = nullptr, *gam_dev = nullptr;
+    cudaError_t e = h->pool.alloc(&w2_dev, w2.size());
+    if (e == cudaSuccess) e = h->pool.alloc(&gam_dev, gam.size());
+    if (e == cudaSuccess) e = cudaMemcpy(w2_dev, w2.data(), sizeof(double) * w2.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(gam_dev, gam.data(), sizeof(double) * gam.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        qmcb_destroy(h);
+        return fail_cuda(e, "interaction tables", __FILE__, __LINE__);
+    }
+    D.g_w2 = w2_dev, D.g_gam = gam_dev;
+    D.epk = nullptr;  // the packed (J, Gamma) tables of the Ising path do not describe this handle
+    h->generic = true, h->gw2_h = w2, h->ggam_h = gam;
+    h->offset = I->offset, h->offset_h = {I->offset};
+    *out = h;
+    return QMCB_OK;
+}
+
 extern "C" int qmcb_destroy(QmcbHandle *h) {
     if (!h) return QMCB_OK;
     cudaSetDevice(h->device);
@@ -455,7 +529,11 @@ extern "C" int qmcb_set_enable_heatbath(QmcbHandle *h, int enable) {
             const double gam = h->gam_h[hi], hl = h->hl_h[hi];
             for (uint32_t b = 0; b < D.Nb; b++) {
                 double acc = 0.0;
-                if (b < D.E) {  // two_site_hamiltonian, qmc_ising.rs:863-875, over the four diagonal substates
+                if (h->generic) {  // make_bond_weights (heatbath.rs:130-146) over the interaction's diagonal substates
+                    if (b < D.E) {
+                        for (int x = 0; x < 4; x++) acc = std::max(acc, h->gw2_h[4 * (size_t)b + x]);
+                    } else acc = h->ggam_h[b];
+                } else if (b < D.E) {  // two_site_hamiltonian, qmc_ising.rs:863-875, over the four diagonal substates
                     const double j = h->Jtab_h[(size_t)hi * D.E + b], cand[2] = {std::fabs(j) - j, std::fabs(j) + j};
                     for (double w : cand)
                         if (w > acc) acc = w;
@@ -495,6 +573,7 @@ extern "C" int qmcb_set_hamiltonians(QmcbHandle *h, uint32_t n_ham, const double
                                      const double *longitudinal, const uint32_t *ham_of_replica) {
     CHECK_H(h);
     SseDev &D = h->D;
+    if (h->generic) return fail(QMCB_ERR_UNSUPPORTED, "per-replica Hamiltonians are (J, Gamma, h) rows: not available for a handle with generic interactions");
     if (!n_ham || (D.E && !J_tab) || !transverse || !longitudinal || !ham_of_replica) return fail(QMCB_ERR_BAD_ARG, "null argument");
     for (uint32_t hi = 0; hi < n_ham; hi++) {
         if (!(transverse[hi] >= 0.0)) return fail(QMCB_ERR_BAD_ARG, "transverse field must be >= 0");
@@ -1473,6 +1552,7 @@ cudaError_t fetch(std::vector<T> &dst, const T *dev, size_t count) {
 
 static int checkpoint_write(QmcbHandle *h, CkWriter &W) {
     const SseDev &D = h->D;
+    if (h->generic) return fail(QMCB_ERR_UNSUPPORTED, "checkpoints of handles with generic interactions are not offered");
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     std::vector<double> beta;
     std::vector<uint64_t> key, cursor, done;

@@ -388,72 +388,146 @@ class QmcIsingGraph:
         return t.value
 
 
-class Qmc:
-    """`qmc::sse::Qmc` (qmc_runner.rs:22-403) as far as it is reachable from the hot path: the instance that
-    `QmcIsingGraph::into_qmc` (qmc_ising.rs:943-976) builds -- diagonal two-site interactions [-J, J, J, -J] with
-    their offset and a constant single-site interaction [G, G, G, G] per variable.  Its `timestep` (qmc_runner.rs:
-    363-377: diagonal update, cluster update when the interactions keep the Ising symmetry, free bits) draws the
-    stream exactly as QmcIsingGraph::timestep does, which is what tests/convert_test.rs asserts; the energy offset
-    only carries the bond terms (qmc_runner.rs:124-133), so energies are shifted by -N * G.  General interactions
-    (`make_interaction` with other matrices, loop updates) are not on this path: QMCB_ERR_UNSUPPORTED."""
+class Qmc(QmcIsingGraph):
+    """`qmc::sse::Qmc` (qmc_runner.rs:22-403) for a batch of replicas: interactions are given as matrices
+    (`make_interaction`, `make_diagonal_interaction`, the `*_and_offset` variants, :113-156) and the diagonal update takes
+    its weights from those tables -- `qmcb_create_qmc`, a different code path from the (J, Gamma, h) arithmetic of
+    QmcIsingGraph.  `timestep` is Qmc::timestep (:363-377): diagonal update, cluster update with Ising symmetry, free
+    bits.  The handle is created when the first step (or accessor) needs it; the shape the engine takes is stated in
+    include/qmcb.h (two-variable interactions first, then one constant one-variable interaction per variable).  Loop
+    updates (directed_loop.rs) are not offered: QMCB_ERR_UNSUPPORTED.  Every QmcIsingGraph accessor works on it."""
 
-    def __init__(self, graph):
-        self._g = graph
-        self.do_loop_updates = False
+    def __init__(self, nvars, rng_keys, betas=1.0, state=None, do_loop_updates=False, mode=MODE_STRICT, device=0, capacity=0):
+        self._L = _lib.load()
+        self._h = None
+        self.nvars = int(nvars)
+        self._keys = np.ascontiguousarray(rng_keys, dtype=np.uint64)
+        self.R = len(self._keys)
+        self._betas = np.ascontiguousarray(np.broadcast_to(np.asarray(betas, dtype=np.float64), (self.R,)))
+        self._state0 = None if state is None else np.ascontiguousarray(np.broadcast_to(np.asarray(state, dtype=np.uint8), (self.R, self.nvars)))
+        self._bonds = []  # (matrix, vars, diagonal)
+        self._offset = 0.0
+        self._cutoff0 = self.nvars  # Qmc::new_with_state: cutoff = nvars (qmc_runner.rs:77)
+        self._mode0, self._device, self._capacity = mode, device, capacity
+        self.mode = mode
+        self.do_loop_updates = bool(do_loop_updates)
+        self.transverse = self.longitudinal = None
+        self._edges = []
 
-    def get_bonds(self):
-        bonds = [(list(e), [-j, j, j, -j], "diagonal") for e, j in self._g.get_edges()]
-        t = self._g.transverse
-        return bonds + [([v], [t, t, t, t], "constant") for v in range(self._g.nvars)]
+    # -- interactions (qmc_runner.rs:113-156; Interaction::new / new_offset / new_diagonal / new_diagonal_offset :424-558)
+    def _add(self, mat, variables, diagonal, and_offset):
+        if self._h is not None:
+            raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "interactions are fixed once the batch has been stepped")
+        mat, variables = [float(x) for x in mat], [int(v) for v in variables]
+        n = len(variables)
+        if len(mat) != (1 << n if diagonal else 1 << (2 * n)):
+            raise ValueError(f"Given {n} vars, matrix of {len(mat)} entries")
+        if and_offset:  # subtract the smallest diagonal element and remember it
+            idx = range(1 << n) if diagonal else [((1 << n) + 1) * k for k in range(1 << n)]
+            lo = min(mat[i] for i in idx)
+            for i in idx:
+                mat[i] -= lo
+            self._offset -= lo
+        if not diagonal and any(x < 0.0 for x in mat):
+            raise ValueError("Interaction contains negative weights")
+        self._bonds.append((mat, variables, diagonal))
 
     def make_interaction(self, mat, variables):
-        raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "general Qmc interactions are not on the GPU hot path (SURVEY 8(f) N3)")
+        self._add(mat, variables, False, False)
 
-    make_interaction_and_offset = make_diagonal_interaction = make_diagonal_interaction_and_offset = make_interaction
+    def make_interaction_and_offset(self, mat, variables):
+        self._add(mat, variables, False, True)
+
+    def make_diagonal_interaction(self, mat, variables):
+        self._add(mat, variables, True, False)
+
+    def make_diagonal_interaction_and_offset(self, mat, variables):
+        self._add(mat, variables, True, True)
+
+    def get_bonds(self):
+        return [(list(v), list(m), "diagonal" if d else "full") for m, v, d in self._bonds]
+
+    def get_offset(self):
+        return self._offset
+
+    def increase_cutoff_to(self, cutoff):  # qmc_runner.rs:307-309
+        if self._h is None:
+            self._cutoff0 = max(self._cutoff0, int(cutoff))
+        else:
+            cur = self.get_cutoff()
+            for r in range(self.R):
+                if cur[r] < cutoff:
+                    self.set_cutoff(int(cutoff), r)
 
     def set_do_loop_updates(self, flag):
         if flag:
-            raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "directed-loop updates are not on the GPU hot path")
+            raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "directed-loop updates are not offered on the GPU path")
 
     def should_do_cluster_update(self):
-        return True  # constant single-site interactions exist and nothing breaks the Ising symmetry
+        self._ensure()
+        return True  # the shapes qmcb_create_qmc accepts have cluster edges and keep the Ising symmetry
 
-    def get_offset(self):
-        return float(sum(abs(j) for _, j in self._g.get_edges()))  # qmc_runner.rs:124-133: bond offsets only
+    def _ensure(self):
+        if self._h is not None:
+            return
+        n = len(self._bonds)
+        nv = np.ascontiguousarray([len(v) for _, v, _ in self._bonds], dtype=np.uint32)
+        vs = np.zeros(2 * max(n, 1), dtype=np.uint32)
+        for b, (_, v, _) in enumerate(self._bonds):
+            vs[2 * b:2 * b + len(v)] = v[:2]
+        ml = np.ascontiguousarray([len(m) for m, _, _ in self._bonds], dtype=np.uint32)
+        mats = np.ascontiguousarray([x for m, _, _ in self._bonds for x in m], dtype=np.float64)
+        ints = _lib.Interactions(self.nvars, n, ptr(nv, C.c_uint32), ptr(vs, C.c_uint32), ptr(ml, C.c_uint32), ptr(mats, C.c_double),
+                                 float(self._offset), int(self.do_loop_updates))
+        h = C.c_void_p()
+        check(self._L.qmcb_create_qmc(C.byref(ints), self.R, ptr(self._betas, C.c_double), ptr(self._keys, C.c_uint64), int(self._cutoff0),
+                                      int(self._capacity), None if self._state0 is None else ptr(self._state0, C.c_uint8), self._device, C.byref(h)))
+        self._h = h
+        self._edges = [((int(v[0]), int(v[1])), 0.0) for _, v, _ in self._bonds if len(v) == 2]
+        QmcIsingGraph.set_mode(self, self._mode0)
 
-    def timestep(self, beta):
-        return self._g.timestep(beta)
+    def __getattribute__(self, name):
+        # any call that reaches the C ABI needs the handle: build it on first use
+        if name == "_L" and object.__getattribute__(self, "_h") is None and object.__getattribute__(self, "_bonds"):
+            object.__getattribute__(self, "_ensure_guarded")()
+        return object.__getattribute__(self, name)
 
-    def timesteps(self, t, beta):
-        shift = self._g.get_offset() - self.get_offset()
-        return self._g.timesteps(t, beta) - shift
+    def _ensure_guarded(self):
+        if not object.__getattribute__(self, "__dict__").get("_building"):
+            self.__dict__["_building"] = True
+            try:
+                self._ensure()
+            finally:
+                self.__dict__["_building"] = False
 
-    def timesteps_sample(self, t, beta, sampling_freq=None):
-        samples, e = self._g.timesteps_sample(t, beta, sampling_freq)
-        return samples, e - (self._g.get_offset() - self.get_offset())
-
-    def state_ref(self):
-        return self._g.state_ref()
-
-    def get_n(self):
-        return self._g.get_n()
-
-    def get_cutoff(self):
-        return self._g.get_cutoff()
-
-    def get_manager_ref(self):
-        return self._g
-
-    def verify(self):
-        return self._g.verify()
+    def set_mode(self, mode):
+        self._mode0 = mode
+        self.mode = mode
+        if self._h is not None:
+            QmcIsingGraph.set_mode(self, mode)
 
 
 def _into_qmc(self):
-    """QmcIsingGraph::into_qmc (qmc_ising.rs:943-976).  The reference builds the longitudinal interactions with a
-    negative matrix entry, which Interaction::new rejects (qmc_runner.rs:524-526), so it only succeeds for h = 0."""
+    """IntoQmc::into_qmc (qmc_ising.rs:943-976): the same streams, states, cutoffs and operator strings; the
+    Hamiltonian restated as interactions -- [-J, J, J, -J] (with its offset) per edge, [G, G, G, G] per variable.  The
+    longitudinal interactions [h, 0, 0, -h] have a negative entry, which Interaction::new rejects (qmc_runner.rs:
+    527-529): the reference's unwrap() panics there, this raises."""
+    q = Qmc(self.nvars, self.rng_keys(), self.betas(), state=self.state_ref(), mode=self.mode)
+    for (a, b), j in self.get_edges():
+        q.make_diagonal_interaction_and_offset([-j, j, j, -j], [a, b])
+    for v in range(self.nvars):
+        q.make_interaction([self.transverse] * 4, [v])
     if abs(self.longitudinal) > np.finfo(np.float64).eps:
-        raise _lib.QmcbError(_lib.ERR_BAD_ARG, "Interaction contains negative weights")  # the reference's unwrap() panics here
-    return Qmc(self)
+        for v in range(self.nvars):
+            q.make_interaction([self.longitudinal, 0.0, 0.0, -self.longitudinal], [v])
+    cut, cur = self.get_cutoff(), self.rng_cursors()
+    q.increase_cutoff_to(int(cut.max()))
+    q._ensure()
+    for r in range(self.R):  # set_manager(self.op_manager) + the rng moves with the graph
+        q.load_ops(r, self.dump_ops(r))
+        q.set_cutoff(int(cut[r]), r)
+        q.set_rng_cursor(r, int(cur[r]))
+    return q
 
 
 def _clone(self, device=0):

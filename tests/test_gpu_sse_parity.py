@@ -275,24 +275,90 @@ def test_stepper_iteration_helpers():
         assert e2[r] == e_ref and all(np.array_equal(seen[k][r], s[k]) for k in range(3))
 
 
-def test_convert_and_run():
-    """tests/convert_test.rs:9-31: `ising.clone().into_qmc()` and `ising` stepped 10 times from the same rng agree."""
+@pytest.mark.parametrize("mode", [MODE_STRICT, MODE_FAST, 2])
+def test_convert_and_run(mode):
+    """tests/convert_test.rs:9-31: `ising.clone().into_qmc()` and `ising` stepped 10 times from the same rng agree.  The
+    two run DIFFERENT code paths here as they do in the reference: `ising` takes its weights from (J, Gamma) arithmetic
+    (qmcb_create), `qmc` from the interaction tables (qmcb_create_qmc)."""
     from isingmontecarlo_b200 import QmcbError
-    from isingmontecarlo_b200.sse import QmcIsingGraph
+    from isingmontecarlo_b200.sse import Qmc, QmcIsingGraph
 
     edges = lattices.one_d_periodic(3, 1.0)
-    ising = QmcIsingGraph.new_with_rng(edges, 1.0, 0.0, 3, [1234, 1235], state=[1, 1, 1], betas=1.0, mode=MODE_STRICT)
+    ising = QmcIsingGraph.new_with_rng(edges, 1.0, 0.0, 3, [1234, 1235], state=[1, 1, 1], betas=1.0, mode=mode)
     qmc = ising.clone().into_qmc()
+    assert isinstance(qmc, Qmc) and qmc._h.value != ising._h.value
     for _ in range(10):
         ising.timestep(1.0)
         qmc.timestep(1.0)
+        for r in range(2):
+            assert np.array_equal(ising.dump_ops(r), qmc.dump_ops(r))
     assert np.array_equal(ising.state_ref(), qmc.state_ref())
-    assert np.array_equal(ising.get_n(), qmc.get_n()) and qmc.verify()
+    assert np.array_equal(ising.get_n(), qmc.get_n()) and np.array_equal(ising.rng_cursors(), qmc.rng_cursors()) and qmc.verify()
     # the Qmc energy offset carries the bond terms only (qmc_runner.rs:124-133)
     e_i, e_q = ising.timesteps(50, 1.0), qmc.timesteps(50, 1.0)
     assert np.allclose(e_i - e_q, 3 * 1.0) and qmc.get_offset() == 3.0
     assert len(qmc.get_bonds()) == 6 and qmc.should_do_cluster_update()
-    with pytest.raises(QmcbError):
-        qmc.make_interaction([1.0, 0.5, 0.5, 1.0], [0])
-    with pytest.raises(QmcbError, match="negative weights"):
+    with pytest.raises(QmcbError, match="fixed"):
+        qmc.make_interaction([1.0, 1.0, 1.0, 1.0], [0])
+    with pytest.raises(ValueError, match="negative weights"):  # qmc_ising.rs:966-969: the reference's unwrap() panics
         QmcIsingGraph.new_with_rng(edges, 1.0, 0.5, 3, [1], betas=1.0).into_qmc()
+    # a bigger lattice, every kernel path the launcher can pick for the table-driven weights
+    edges = lattices.two_d_periodic_mixed(4)
+    ising = QmcIsingGraph.new_with_rng(edges, 0.8, 0.0, 16, [77, 78, 79], betas=1.5, mode=mode)
+    ising.timesteps(20, 1.5)
+    for impl, minblocks in ((0, 7), (0, 4), (1, 0)):
+        qmc = ising.clone().into_qmc()
+        qmc.set_option("impl", impl), qmc.set_option("minblocks", minblocks)
+        a = ising.clone()
+        a.timesteps(15, 1.5), qmc.timesteps(15, 1.5)
+        for r in range(3):
+            assert np.array_equal(a.dump_ops(r), qmc.dump_ops(r)), (impl, minblocks)
+        assert np.array_equal(a.state_ref(), qmc.state_ref())
+
+
+@pytest.mark.parametrize("mode", [MODE_STRICT, MODE_FAST, 2])
+def test_generic_qmc_interactions_bit_exact(mode):
+    """Qmc with interactions that are NOT a transverse-field Ising model (unequal two-variable weights, a full matrix with
+    its offset, per-variable transverse weights), both diagonal rules, against the oracle's restatement of
+    qmc_runner.rs; and the shapes the engine does not take."""
+    from isingmontecarlo_b200 import QmcbError
+    from isingmontecarlo_b200.sse import Qmc
+
+    def build(target):
+        target.make_diagonal_interaction_and_offset([0.3, 1.0, 1.0, 0.3], [0, 1])
+        target.make_diagonal_interaction([2.0, 0.5, 0.5, 2.0], [1, 2])
+        target.make_interaction_and_offset([0.6, 0, 0, 0, 0, 1.1, 0, 0, 0, 0, 1.1, 0, 0, 0, 0, 0.6], [2, 3])
+        target.make_diagonal_interaction([0.6, 1.4, 1.4, 0.6], [3, 0])
+        for v, gam in enumerate([0.5, 1.0, 1.5, 0.8]):
+            target.make_interaction([gam] * 4, [v])
+
+    keys = [0x9E0 + r for r in range(4)]
+    for heatbath in ((False, True) if mode != 2 else (False,)):
+        q = Qmc(4, keys, 1.2, mode=mode)
+        build(q)
+        q.set_enable_heatbath(heatbath)
+        refs = []
+        for k in keys:
+            ref = po.QmcOracle(4, key=k)
+            build(ref)
+            ref.set_enable_heatbath(heatbath)
+            refs.append(ref)
+        assert q.get_offset() == refs[0].offset == -0.3 - 0.6
+        for chunk in (1, 2, 10, 30):
+            e = q.timesteps(chunk, 1.2)
+            e_ref = [ref.timesteps(chunk, 1.2, mode) for ref in refs]
+            assert_same(q, refs, f"generic +{chunk}")
+            assert np.array_equal(e, np.array(e_ref))
+        assert q.verify()
+    bad = Qmc(3, [1], 1.0)
+    bad.make_interaction([0.5] * 4, [0])  # one-variable interaction before the two-variable ones
+    bad.make_diagonal_interaction([1.0, 0.2, 0.2, 1.0], [0, 1])
+    with pytest.raises(QmcbError, match="interaction order|one constant"):
+        bad.timestep(1.0)
+    asym = Qmc(2, [1], 1.0)
+    asym.make_diagonal_interaction([1.0, 0.2, 0.3, 1.0], [0, 1])
+    asym.make_interaction([0.5] * 4, [0]), asym.make_interaction([0.5] * 4, [1])
+    with pytest.raises(QmcbError, match="Ising symmetry"):
+        asym.timestep(1.0)
+    with pytest.raises(QmcbError, match="loop"):
+        Qmc(2, [1], 1.0).set_do_loop_updates(True)
