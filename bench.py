@@ -393,17 +393,22 @@ def bench_classical(args, world, rank, local):
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
     peak, peak_src = measured_peaks()
     ach = value / world * SURVEY_CLS_BYTES_PER_FLIP / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_cls_square", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+    roofline = {"bound": "hbm", "kernel": "k_cls_square_sweeps", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "peak_source": peak_src, "traffic": None, "bytes_per_unit": SURVEY_CLS_BYTES_PER_FLIP,
                 "layout": "bit-packed colour planes (0.125 B/spin, 32 MiB per 256 replicas: L2-resident), so HBM does not bind; "
-                          "the kernel is integer-issue bound (Philox4x32-10, one 32-bit draw per site)",
-                "avg_launch_ms": ms / max(launches, 1)}
+                          "the kernel is bound by the integer (ALU) pipe: Philox4x32-10 + bit-plane ripple, one 32-bit draw per site",
+                "avg_launch_ms": ms / max(launches, 1), "sweeps_per_launch": spp}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:
-            tr = json.load(f).get("k_cls_square")
+            tr = json.load(f).get("k_cls_square_sweeps")
             roofline["traffic"] = tr["bytes_per_launch"] if tr else None
-            roofline["traffic_note"] = "ncu dram__bytes_read+write per launch (profiles/%s)" % tr["source"] if tr else None
+            roofline["traffic_note"] = ("ncu dram__bytes_read+write per launch (profiles/%s): one read of the state, independent of the "
+                                        "sweeps per launch" % tr["source"]) if tr else None
+            if tr:  # the honest bound: pipe utilisation from the same capture
+                roofline["alu_pipe_frac"] = tr.get("alu_pipe_pct", 0.0) / 100.0
+                roofline["alu_pipe_note"] = ("sm__inst_executed_pipe_alu %.1f %% of peak, FMA pipe %.1f %%, IPC %.2f (ncu); the INT32 pipe issues one warp "
+                                             "instruction every other cycle" % (tr.get("alu_pipe_pct", 0.0), tr.get("fma_pipe_pct", 0.0), tr.get("ipc", 0.0)))
     out = {"metric": "classical_spin_flips_per_sec", "value": value, "unit": "spin_flip_attempts/s", "ms_per_step": ms / args.steps,
            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
            "e2e": {"value": flips / e2e_s, "unit": "spin_flip_attempts/s", "h2d_bytes_per_step": 0,
