@@ -202,20 +202,20 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
             }
 #endif
             if (do_diag) {
-                const bool offd = type == T_OFFD;
+                // (written with selects rather than branches: the lanes of a step are a mix of empty slots, diagonal and
+                // off-diagonal ops, so every branch on the slot type would be executed both ways anyway)
+                const bool isE = type == T_EMPTY, isD = type == T_DIAG, offd = type == T_OFFD;
                 fmask = __ballot_sync(FULL, offd);
-                if (offd) flipv = v0;
+                flipv = offd ? v0 : NONE32;
+                // spins the weight looks at: the stored input bits of an existing op, the propagated state at this slot
+                // for a proposal (v1 == v0 for one-variable ops, so both loads are always in range)
+                const uint32_t bit0 = state_bit(s_st, v0), bit1 = kind == KIND_BOND ? state_bit(s_st, v1) : 0u;
+                uint32_t s0 = isE ? bit0 : (op_in(w) & 1u), s1 = isE ? bit1 : ((op_in(w) >> 1) & 1u);
                 if (fmask) {  // off-diagonal ops flip their variable for the later lanes of this step
-                    s_fl[lane] = offd ? v0 : NONE32;
+                    s_fl[lane] = flipv;
                     if (offd) atomicOr(&s_cd[v0 >> 5], 1u << (v0 & 31));
                     __syncwarp();
-                }
-                // spins the weight looks at: the stored input bits of an existing op, the propagated state at this slot
-                // for a proposal
-                uint32_t s0 = op_in(w) & 1u, s1 = (op_in(w) >> 1) & 1u;
-                if (type == T_EMPTY) {
-                    s0 = state_bit(s_st, v0), s1 = kind == KIND_BOND ? state_bit(s_st, v1) : 0u;
-                    if ((fmask & lt_mask) && (state_bit(s_cd, v0) || (kind == KIND_BOND && state_bit(s_cd, v1))))
+                    if (isE && (fmask & lt_mask) && (state_bit(s_cd, v0) || (kind == KIND_BOND && state_bit(s_cd, v1))))
                         for (uint32_t m = fmask & lt_mask; m; m &= m - 1) {
                             const uint32_t fv = s_fl[__ffs(m) - 1];
                             s0 ^= (fv == v0), s1 ^= (kind == KIND_BOND && fv == v1);
@@ -227,25 +227,22 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                     num = numtab[c], rn = rnumtab[c];
                 } else {
                     num = bn * bweight<HAS_H>(Hm, beff, kind, s0, s1);
-                    rn = type == T_DIAG ? 1.0 / num : 0.0;
+                    rn = isD ? 1.0 / num : 0.0;
                 }
                 // conservative classification over the n interval this lane can see (the rules are monotone in den)
-                const uint32_t emask = __ballot_sync(FULL, type == T_EMPTY), dmask = __ballot_sync(FULL, type == T_DIAG);
+                const uint32_t emask = __ballot_sync(FULL, isE), dmask = __ballot_sync(FULL, isD);
                 const double dlo = (double)(M - (n + (uint32_t)__popc(emask & lt_mask)));
                 const double dhi = (double)(M - (n - (uint32_t)__popc(dmask & lt_mask)));
-                int dec = 0;  // +1 insert, -1 remove
-                bool amb = false, needdiv = false;
-                if (type == T_EMPTY) {
-                    if (num > dhi) dec = 1;
-                    else if (num > 0.0) needdiv = true;
-                } else if (type == T_DIAG) {
-                    if (dlo + 1.0 > num) dec = -1;
-                    else {
-                        const double q_lo = (dlo + 1.0) * rn * G_LO, q_hi = (dhi + 1.0) * rn * G_HI;
-                        if (wA < bool_threshold(q_lo)) dec = -1;
-                        else if (!(q_hi < 1.0 && wA >= bool_threshold(q_hi))) amb = true;
-                    }
-                }
+                // removal of a diagonal op: sure if den + 1 > num at the smallest den or the word is below the lower
+                // threshold; surely kept if it is at or above the upper one; in between: the exact rule below
+                const double q_lo = (dlo + 1.0) * rn * G_LO, q_hi = (dhi + 1.0) * rn * G_HI;
+                const bool d_rm = (dlo + 1.0 > num) || (wA < bool_threshold(q_lo));
+                const bool d_keep = q_hi < 1.0 && wA >= bool_threshold(q_hi);
+                // insertion into an empty slot: sure if num > den at the largest den
+                const bool e_ins = num > dhi;
+                const bool needdiv = isE && !e_ins && num > 0.0;
+                int dec = isE ? (e_ins ? 1 : 0) : ((isD && d_rm) ? -1 : 0);  // +1 insert, -1 remove
+                bool amb = isD && !d_rm && !d_keep;
                 if (__any_sync(FULL, needdiv)) {
                     // insertion with num <= den: bounds from the two reciprocals of the step's den interval
                     const double DLO = (double)(M - (n + (uint32_t)__popc(emask))), DHI = (double)(M - (n - (uint32_t)__popc(dmask)));
@@ -289,10 +286,8 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                     else if (du == -1) remm |= 1u << u;
                 }
                 n += (uint32_t)__popc(insm) - (uint32_t)__popc(remm);
-                if (dec == 1) {
-                    const uint32_t pbits = s0 | (s1 << 1);
-                    neww = make_op(beff, pbits, pbits);
-                } else if (dec == -1) neww = OP_EMPTY;
+                const uint32_t pbits = s0 | (s1 << 1);
+                neww = dec == 1 ? make_op(beff, pbits, pbits) : (dec == -1 ? OP_EMPTY : w);
                 changed = neww != w;
             }
             if (neww == OP_EMPTY) kind = -1;  // no op in this slot after the diagonal update
