@@ -387,7 +387,7 @@ def bench_classical(args, world, rank, local):
     barrier_sync(world)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        g.do_time_step(spp)
+        g.sweeps(spp)
         en, mg = g.get_energy(), g.magnetization()
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
@@ -413,7 +413,7 @@ def bench_classical(args, world, rank, local):
            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
            "e2e": {"value": flips / e2e_s, "unit": "spin_flip_attempts/s", "h2d_bytes_per_step": 0,
                    "d2h_bytes_per_step": int(16 * R * world),
-                   "call": f"GraphState.do_time_step({spp}) + get_energy() + magnetization()"},
+                   "call": f"GraphState.sweeps({spp}) + get_energy() + magnetization()"},
            "energy_per_site": float(np.mean(en) / (L * L)), "abs_magnetization": float(np.mean(np.abs(mg))),
            "config": {"workload": f"classical 2D square L={L} J={c['J']} checkerboard Metropolis at T_c, {R} replicas/GPU",
                       "sweeps_per_step": spp, "draw": "one 32-bit Philox4x32-10 word per site and sweep",

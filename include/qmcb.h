@@ -290,6 +290,22 @@ int cmcb_get_states(CmcbHandle *h, uint8_t *states /* [R*N] */);
 int cmcb_set_states(CmcbHandle *h, const uint8_t *states /* [R*N] */);
 int cmcb_energy(CmcbHandle *h, double *energy /* [R] */);               /* get_energy :430-447 */
 int cmcb_magnetization(CmcbHandle *h, double *m /* [R], mean of +-1 */);
+/* The reference's OWN schedule, replica-parallel (one thread per replica, each under its sequential stream; serial
+ * by construction, so this is the reference-exact path, not the throughput path):
+ * GraphState::do_time_step (graph.rs:350-406): one u8 draw picks spin flips (do_spin_flip :91-119), edge flips
+ * (do_edge_flip :122-153) or -- unless only_basic_moves -- worm flips with doubles (do_worm_flip :179-318); counts of
+ * UINT64_MAX stand for None (max(1, N/2), max(1, |E|/2), 1).  beta is the replica's.  choices_out [R] or NULL
+ * receives the move each replica drew.  The three moves are also callable directly, as the reference's tests do
+ * (graph.rs:481-647).  BAD_ARG where the reference panics (edge move with no edges / non-positive total weight). */
+int cmcb_do_time_step(CmcbHandle *h, uint64_t nspinupdates, uint64_t nedgeupdates, uint64_t nwormupdates,
+                      int only_basic_moves, uint8_t *choices_out);
+int cmcb_spin_flips(CmcbHandle *h, uint64_t count);
+int cmcb_edge_flips(CmcbHandle *h, uint64_t count);
+int cmcb_worm_flips(CmcbHandle *h, uint64_t count, int allow_doubles);
+int cmcb_enable_edge_importance_sampling(CmcbHandle *h, int enable);    /* graph.rs:321-336 */
+/* position of every replica in its sequential stream (N after a stream-drawn initial state, graph.rs:451-453) */
+int cmcb_get_rng_cursors(CmcbHandle *h, uint64_t *cursors /* [R] */);
+int cmcb_set_rng_cursors(CmcbHandle *h, const uint64_t *cursors /* [R] */);
 int cmcb_get_colours(const CmcbHandle *h, uint32_t *colours /* [N] */, uint32_t *ncolours);
 int cmcb_get_sweep_count(const CmcbHandle *h, uint64_t *sweeps);
 int cmcb_set_sweep_count(CmcbHandle *h, uint64_t sweeps);

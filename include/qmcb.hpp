@@ -277,18 +277,32 @@ class GraphState {
 public:
     // GraphState::new (graph.rs:56-59); betas per replica because the sweep needs them at creation
     static GraphState create(const std::vector<Edge> &edges, const std::vector<double> &biases, const std::vector<uint64_t> &rng_keys,
-                             const std::vector<double> &betas, int device = 0) {
+                             const std::vector<double> &betas, int device = 0, const std::vector<bool> *state = nullptr) {
         GraphState g;
         detail::Lat lat(edges, 0.0, 0.0, biases.size());
         g.nvars_ = biases.size(), g.replicas_ = rng_keys.size();
-        check(cmcb_create(&lat.l, biases.data(), (uint32_t)rng_keys.size(), betas.data(), rng_keys.data(), nullptr, device, &g.h_));
+        std::vector<uint8_t> init;  // new_with_state_and_rng (graph.rs:62-88): the same state for every replica
+        if (state)
+            for (size_t r = 0; r < g.replicas_; r++)
+                for (bool b : *state) init.push_back(b);
+        check(cmcb_create(&lat.l, biases.data(), (uint32_t)rng_keys.size(), betas.data(), rng_keys.data(), state ? init.data() : nullptr,
+                          device, &g.h_));
         return g;
     }
     GraphState() = default;
     GraphState(GraphState &&o) noexcept { std::swap(h_, o.h_), std::swap(nvars_, o.nvars_), std::swap(replicas_, o.replicas_); }
     GraphState(const GraphState &) = delete;
     ~GraphState() { cmcb_destroy(h_); }
-    void do_time_step(size_t nsweeps = 1) { check(cmcb_sweeps(h_, nsweeps)); }  // graph.rs:350-406 (checkerboard schedule)
+    void sweeps(size_t nsweeps = 1) { check(cmcb_sweeps(h_, nsweeps)); }  // checkerboard schedule, the throughput path
+    // GraphState::do_time_step (graph.rs:350-406), the reference's own schedule; SIZE_MAX = None.  Returns the move drawn per replica.
+    std::vector<uint8_t> do_time_step(size_t nspinupdates = SIZE_MAX, size_t nedgeupdates = SIZE_MAX, size_t nwormupdates = SIZE_MAX,
+                                      bool only_basic_moves = false) {
+        std::vector<uint8_t> choice(replicas_);
+        check(cmcb_do_time_step(h_, nspinupdates, nedgeupdates, nwormupdates, only_basic_moves, choice.data()));
+        return choice;
+    }
+    void do_worm_flip(size_t count, bool allow_doubles) { check(cmcb_worm_flips(h_, count, allow_doubles)); }  // graph.rs:179-318
+    void enable_edge_importance_sampling(bool enable) { check(cmcb_enable_edge_importance_sampling(h_, enable)); }  // :321-336
     std::vector<double> get_energy() {                                           // graph.rs:430-447
         std::vector<double> e(replicas_);
         check(cmcb_energy(h_, e.data()));

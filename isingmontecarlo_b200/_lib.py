@@ -116,6 +116,13 @@ SIGNATURES = {
     "cmcb_set_states": [vp, u8p],
     "cmcb_energy": [vp, f64p],
     "cmcb_magnetization": [vp, f64p],
+    "cmcb_do_time_step": [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, u8p],
+    "cmcb_spin_flips": [vp, C.c_uint64],
+    "cmcb_edge_flips": [vp, C.c_uint64],
+    "cmcb_worm_flips": [vp, C.c_uint64, C.c_int],
+    "cmcb_enable_edge_importance_sampling": [vp, C.c_int],
+    "cmcb_get_rng_cursors": [vp, u64p],
+    "cmcb_set_rng_cursors": [vp, u64p],
     "cmcb_get_colours": [vp, u32p, u32p],
     "cmcb_get_sweep_count": [vp, u64p],
     "cmcb_set_sweep_count": [vp, C.c_uint64],

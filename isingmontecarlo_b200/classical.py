@@ -54,12 +54,43 @@ class GraphState:
     def set_option(self, name, value):
         check(self._L.cmcb_set_option(self._h, name.encode(), int(value)))
 
-    def do_time_step(self, nsweeps=1):
-        """One checkerboard sweep = every site once (the reference's do_time_step makes N/2 random
-        single-spin attempts, graph.rs:350-406; the schedule differs, the per-site rule does not)."""
+    def sweeps(self, nsweeps=1):
+        """Checkerboard sweeps = every site once per sweep (the throughput path; the schedule is builder-defined,
+        the per-site rule is the reference's)."""
         check(self._L.cmcb_sweeps(self._h, int(nsweeps)))
 
-    sweeps = do_time_step
+    def do_time_step(self, nspinupdates=None, nedgeupdates=None, nwormupdates=None, only_basic_moves=None):
+        """GraphState::do_time_step (graph.rs:350-406) for every replica under its own sequential stream, at the
+        replica's beta: one draw picks spin flips, edge flips or (unless only_basic_moves) worm flips.  Returns the
+        move each replica drew."""
+        none = 2**64 - 1
+        out = np.zeros(self.R, dtype=np.uint8)
+        check(self._L.cmcb_do_time_step(self._h, none if nspinupdates is None else int(nspinupdates),
+                                        none if nedgeupdates is None else int(nedgeupdates),
+                                        none if nwormupdates is None else int(nwormupdates),
+                                        int(bool(only_basic_moves)), ptr(out, C.c_uint8)))
+        return out
+
+    def do_spin_flip(self, count=1):  # graph.rs:91-119
+        check(self._L.cmcb_spin_flips(self._h, int(count)))
+
+    def do_edge_flip(self, count=1):  # graph.rs:122-153
+        check(self._L.cmcb_edge_flips(self._h, int(count)))
+
+    def do_worm_flip(self, count=1, allow_doubles=True):  # graph.rs:179-318
+        check(self._L.cmcb_worm_flips(self._h, int(count), int(bool(allow_doubles))))
+
+    def enable_edge_importance_sampling(self, enable=True):  # graph.rs:321-336
+        check(self._L.cmcb_enable_edge_importance_sampling(self._h, int(bool(enable))))
+
+    def rng_cursors(self):
+        out = np.zeros(self.R, dtype=np.uint64)
+        check(self._L.cmcb_get_rng_cursors(self._h, ptr(out, C.c_uint64)))
+        return out
+
+    def set_rng_cursors(self, cursors):
+        c = np.ascontiguousarray(np.broadcast_to(np.asarray(cursors, dtype=np.uint64), (self.R,)))
+        check(self._L.cmcb_set_rng_cursors(self._h, ptr(c, C.c_uint64)))
 
     def enqueue_sweeps(self, nsweeps):
         check(self._L.cmcb_enqueue_sweeps(self._h, int(nsweeps)))

@@ -44,6 +44,8 @@ void launch_cls_square_pack(const ClsDev &D, const uint8_t *bytes, cudaStream_t 
 void launch_cls_square_unpack(const ClsDev &D, uint8_t *bytes, cudaStream_t st);
 void launch_cls_init_bytes(const ClsDev &D, uint8_t *bytes, cudaStream_t st);
 void launch_cls_generic_energy(const ClsDev &D, const double *adj_j, const double *biases, double *energy, double *mag, cudaStream_t st);
+void launch_cls_ref_moves(const ClsRefDev &D, int move, uint64_t nspin, uint64_t nedge, uint64_t nworm, int only_basic,
+                          int allow_doubles, uint8_t *choice_out, cudaStream_t st);
 
 static thread_local std::string g_err;
 
@@ -1779,6 +1781,14 @@ struct CmcbHandle {
     unsigned int bar_count = 0;
     int nsm = 148;
     int fused = 1;  // cmcb_set_option("fused", 0): one launch per colour pass (round-1 behaviour, A/B measurements)
+    // reference-schedule moves (classical_ref.cu): host copies of what the reference's GraphState holds, uploaded on first use
+    std::vector<uint32_t> h_start, h_idx, h_ea, h_eb;
+    std::vector<double> h_aj, h_bias, h_ej, h_beta;
+    uint64_t cursor0 = 0;  // words the constructor drew (make_random_spin_state: one per spin)
+    ClsRefDev Rf{};
+    bool ref_ready = false;
+    double *cum_dev = nullptr;
+    uint8_t *choice_dev = nullptr;
 };
 
 #define CHECK_C(h)                                              \
@@ -1832,6 +1842,14 @@ extern "C" int cmcb_create(const QmcbLattice *lat, const double *biases, uint32_
     CmcbHandle *h = new CmcbHandle();
     h->device = device;
     h->colours = colour, h->ncolours = ncol;
+    h->h_start.assign(N + 1, 0);
+    for (uint32_t i = 0; i < N; i++) {
+        h->h_start[i + 1] = h->h_start[i] + (uint32_t)adj[i].size();
+        for (auto &nb : adj[i]) h->h_idx.push_back(nb.first), h->h_aj.push_back(nb.second);
+    }
+    h->h_ea.assign(lat->va, lat->va + E), h->h_eb.assign(lat->vb, lat->vb + E), h->h_ej.assign(lat->J, lat->J + E);
+    h->h_bias.assign(biases, biases + N), h->h_beta.assign(betas, betas + R);
+    h->cursor0 = init_state ? 0 : N;
     ClsDev &D = h->D;
     D.N = N, D.R = R;
 #define TRYC(expr)                                   \
@@ -2162,6 +2180,123 @@ extern "C" int cmcb_energy(CmcbHandle *h, double *energy) {
 extern "C" int cmcb_magnetization(CmcbHandle *h, double *m) {
     CHECK_C(h);
     return m ? cls_measure(h, nullptr, m) : fail(QMCB_ERR_BAD_ARG, "null argument");
+}
+// ---- the reference's own schedule: do_time_step with spin / edge / worm moves (graph.rs:91-406) --------------
+static int cls_ref_ensure(CmcbHandle *h) {
+    if (h->ref_ready) return QMCB_OK;
+    ClsRefDev &F = h->Rf;
+    const uint32_t N = h->D.N, R = h->D.R, E = (uint32_t)h->h_ea.size();
+    F.N = N, F.R = R, F.E = E, F.key = h->D.key;
+    uint32_t *d_start, *d_idx, *d_ea, *d_eb;
+    double *d_aj, *d_bias, *d_beta;
+    CUDA_TRY(h->pool.alloc(&d_start, h->h_start.size()));
+    CUDA_TRY(h->pool.alloc(&d_idx, std::max<size_t>(h->h_idx.size(), 1)));
+    CUDA_TRY(h->pool.alloc(&d_aj, std::max<size_t>(h->h_aj.size(), 1)));
+    CUDA_TRY(h->pool.alloc(&d_ea, std::max<size_t>(E, 1)));
+    CUDA_TRY(h->pool.alloc(&d_eb, std::max<size_t>(E, 1)));
+    CUDA_TRY(h->pool.alloc(&d_bias, N));
+    CUDA_TRY(h->pool.alloc(&d_beta, R));
+    CUDA_TRY(h->pool.alloc(&F.cursor, R));
+    CUDA_TRY(h->pool.alloc(&F.path, (size_t)R * 2 * ((size_t)N + 2)));
+    CUDA_TRY(h->pool.alloc(&F.status, 1));
+    CUDA_TRY(h->pool.alloc(&h->choice_dev, R));
+    CUDA_TRY(cudaMemcpy(d_start, h->h_start.data(), h->h_start.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_idx, h->h_idx.data(), h->h_idx.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_aj, h->h_aj.data(), h->h_aj.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_ea, h->h_ea.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_eb, h->h_eb.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_bias, h->h_bias.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_beta, h->h_beta.data(), (size_t)R * 8, cudaMemcpyHostToDevice));
+    std::vector<uint64_t> cur(R, h->cursor0);
+    CUDA_TRY(cudaMemcpy(F.cursor, cur.data(), (size_t)R * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(F.status, 0, sizeof(int)));
+    F.adj_start = d_start, F.adj_idx = d_idx, F.adj_j = d_aj, F.ea = d_ea, F.eb = d_eb, F.biases = d_bias, F.beta = d_beta;
+    F.cum_w = nullptr, F.total_w = 0.0;
+    F.spins = h->square ? h->bytes_dev : h->D.spins;
+    h->ref_ready = true;
+    return QMCB_OK;
+}
+static int cls_ref_run(CmcbHandle *h, int move, uint64_t nspin, uint64_t nedge, uint64_t nworm, int only_basic, int allow_doubles,
+                       uint8_t *choices_out) {
+    int rc = cls_ref_ensure(h);
+    if (rc) return rc;
+    const uint64_t none = ~0ull;  // None: the reference's defaults, graph.rs:361-363
+    if (nspin == none) nspin = std::max<uint64_t>(1, h->D.N / 2);
+    if (nedge == none) nedge = std::max<uint64_t>(1, h->h_ea.size() / 2);
+    if (nworm == none) nworm = 1;
+    if (h->square) {
+        launch_cls_square_unpack(h->D, h->bytes_dev, h->stream);
+        h->launches++;
+    }
+    launch_cls_ref_moves(h->Rf, move, nspin, nedge, nworm, only_basic, allow_doubles, h->choice_dev, h->stream);
+    h->launches++;
+    if (h->square) {
+        launch_cls_square_pack(h->D, h->bytes_dev, h->stream);
+        h->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    int status = 0;
+    CUDA_TRY(cudaMemcpyAsync(&status, h->Rf.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (choices_out) CUDA_TRY(cudaMemcpyAsync(choices_out, h->choice_dev, h->D.R, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (status) {
+        cudaMemset(h->Rf.status, 0, sizeof(int));
+        return fail(QMCB_ERR_BAD_ARG, "edge move without edges or with a non-positive total edge weight (the reference panics: empty range)");
+    }
+    return QMCB_OK;
+}
+extern "C" int cmcb_do_time_step(CmcbHandle *h, uint64_t nspinupdates, uint64_t nedgeupdates, uint64_t nwormupdates, int only_basic_moves,
+                                 uint8_t *choices_out) {
+    CHECK_C(h);
+    return cls_ref_run(h, 3, nspinupdates, nedgeupdates, nwormupdates, only_basic_moves != 0, 1, choices_out);
+}
+extern "C" int cmcb_spin_flips(CmcbHandle *h, uint64_t count) {
+    CHECK_C(h);
+    return cls_ref_run(h, 0, count, 0, 0, 0, 0, nullptr);
+}
+extern "C" int cmcb_edge_flips(CmcbHandle *h, uint64_t count) {
+    CHECK_C(h);
+    return cls_ref_run(h, 1, 0, count, 0, 0, 0, nullptr);
+}
+extern "C" int cmcb_worm_flips(CmcbHandle *h, uint64_t count, int allow_doubles) {
+    CHECK_C(h);
+    return cls_ref_run(h, 2, 0, 0, count, 0, allow_doubles != 0, nullptr);
+}
+extern "C" int cmcb_enable_edge_importance_sampling(CmcbHandle *h, int enable) {
+    CHECK_C(h);
+    int rc = cls_ref_ensure(h);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!enable) {
+        h->Rf.cum_w = nullptr, h->Rf.total_w = 0.0;
+        return QMCB_OK;
+    }
+    const size_t E = h->h_ej.size();
+    std::vector<double> cum(std::max<size_t>(E, 1), 0.0);
+    double acc = 0.0;  // graph.rs:323-331: running sums in edge order
+    for (size_t e = 0; e < E; e++) acc = acc + h->h_ej[e], cum[e] = acc;
+    if (!h->cum_dev) CUDA_TRY(h->pool.alloc(&h->cum_dev, cum.size()));
+    CUDA_TRY(cudaMemcpy(h->cum_dev, cum.data(), cum.size() * 8, cudaMemcpyHostToDevice));
+    h->Rf.cum_w = h->cum_dev, h->Rf.total_w = acc;
+    return QMCB_OK;
+}
+extern "C" int cmcb_get_rng_cursors(CmcbHandle *h, uint64_t *cursors) {
+    CHECK_C(h);
+    if (!cursors) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    int rc = cls_ref_ensure(h);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(cursors, h->Rf.cursor, (size_t)h->D.R * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
+}
+extern "C" int cmcb_set_rng_cursors(CmcbHandle *h, const uint64_t *cursors) {
+    CHECK_C(h);
+    if (!cursors) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    int rc = cls_ref_ensure(h);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->Rf.cursor, cursors, (size_t)h->D.R * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QMCB_OK;
 }
 extern "C" int cmcb_get_colours(const CmcbHandle *h, uint32_t *colours, uint32_t *ncolours) {
     if (!h) return fail(QMCB_ERR_BAD_ARG, "null handle");

@@ -24,3 +24,19 @@ struct ClsDev {
     uint32_t sq_ngroups;       // max number of groups over the replicas
     int sq_wpr_shift;          // log2(L / 64) if that is a power of two, else -1
 };
+
+// reference-schedule moves (classical_ref.cu): GraphState::do_time_step with spin, edge and worm flips
+struct ClsRefDev {
+    uint32_t N, R, E;
+    const uint64_t *key;   // [R]
+    uint64_t *cursor;      // [R] position in the replica's sequential stream
+    const double *beta;    // [R]
+    uint8_t *spins;        // [R][N] bytes
+    const uint32_t *adj_start, *adj_idx;  // binding_mat as CSR, neighbours sorted by index (graph.rs:69-78)
+    const double *adj_j, *biases;
+    const uint32_t *ea, *eb;  // edges in construction order
+    const double *cum_w;      // enable_edge_importance_sampling (graph.rs:321-336), nullptr when off
+    double total_w;
+    uint32_t *path;           // [R][2 (N + 2)] visit_path of the worm move
+    int *status;
+};

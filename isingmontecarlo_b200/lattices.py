@@ -49,6 +49,21 @@ def triangular_periodic(l: int, j: float = 1.0):
     return e
 
 
+def bathroom_unit_cells(l: int):
+    """classical/graph.rs:605-625: four-site unit cells (one +1 bond per cell), joined right and down"""
+    edges = []
+    for x in range(l):
+        for y in range(l):
+            for i in range(4):
+                va, vb = y * l * 4 + x * 4 + i, y * l * 4 + x * 4 + (i + 1) % 4
+                edges.append(((min(va, vb), max(va, vb)), 1.0 if i == 0 else -1.0))
+            va, vb = y * l * 4 + x * 4 + 1, y * l * 4 + ((x + 1) % l) * 4 + 3
+            edges.append(((min(va, vb), max(va, vb)), -1.0))
+            va, vb = y * l * 4 + x * 4, ((y + 1) % l) * l * 4 + x * 4 + 2
+            edges.append(((min(va, vb), max(va, vb)), -1.0))
+    return edges
+
+
 def nvars_of(edges) -> int:
     """qmc_ising.rs:92"""
     return max(max(a, b) for (a, b), _ in edges) + 1

@@ -1338,6 +1338,12 @@ struct OrcCls {
     uint8_t *state;
     Stream rng;
     uint64_t sweep; /* checkerboard sweep counter */
+    uint32_t nedges; /* edges in construction order (graph.rs:9, :81) */
+    uint32_t *ea, *eb;
+    double *ej;
+    double *cum_w; /* enable_edge_importance_sampling :321-336, NULL when off */
+    double total_w;
+    int error; /* the reference returns Err / panics: 1 empty range */
 };
 
 OrcCls *orc_cls_create(uint32_t nvars, uint32_t nedges, const uint32_t *ea, const uint32_t *eb,
@@ -1352,6 +1358,12 @@ OrcCls *orc_cls_create(uint32_t nvars, uint32_t nedges, const uint32_t *ea, cons
         for (uint32_t v = 0; v < nvars; v++) g->state[v] = (uint8_t)gen_std_bool(&g->rng); /* :57, :451-453 */
     g->biases = (double *)malloc(sizeof(double) * nvars);
     memcpy(g->biases, biases, sizeof(double) * nvars);
+    g->nedges = nedges;
+    g->ea = (uint32_t *)malloc(sizeof(uint32_t) * (nedges ? nedges : 1));
+    g->eb = (uint32_t *)malloc(sizeof(uint32_t) * (nedges ? nedges : 1));
+    g->ej = (double *)malloc(sizeof(double) * (nedges ? nedges : 1));
+    memcpy(g->ea, ea, sizeof(uint32_t) * nedges), memcpy(g->eb, eb, sizeof(uint32_t) * nedges);
+    memcpy(g->ej, J, sizeof(double) * nedges);
     g->adj_start = (uint32_t *)calloc((size_t)nvars + 1, sizeof(uint32_t));
     for (uint32_t e = 0; e < nedges; e++) g->adj_start[ea[e] + 1]++, g->adj_start[eb[e] + 1]++;
     for (uint32_t v = 0; v < nvars; v++) g->adj_start[v + 1] += g->adj_start[v];
@@ -1384,6 +1396,7 @@ OrcCls *orc_cls_create(uint32_t nvars, uint32_t nedges, const uint32_t *ea, cons
 void orc_cls_destroy(OrcCls *g) {
     if (!g) return;
     free(g->adj_start), free(g->adj_idx), free(g->adj_j), free(g->biases), free(g->state);
+    free(g->ea), free(g->eb), free(g->ej), free(g->cum_w);
     free(g);
 }
 
@@ -1412,6 +1425,206 @@ void orc_cls_spin_flips(OrcCls *g, double beta, uint64_t count) {
         if (flip) g->state[i] = !g->state[i];
     }
 }
+
+/* ---- the reference's own schedule: do_time_step with spin, edge and worm moves (graph.rs:121-406) ---- */
+
+/* GraphState::delta_e, graph.rs:155-176: no bias term; the edge to `omit` is left out (omit < 0: none) */
+static double cls_delta_e_omit(const OrcCls *g, uint32_t v, int64_t omit) {
+    int curr = g->state[v];
+    double delta_e = 0.0;
+    for (uint32_t k = g->adj_start[v]; k < g->adj_start[v + 1]; k++) {
+        if ((int64_t)g->adj_idx[k] == omit) continue;
+        double old_coupling = !(curr ^ g->state[g->adj_idx[k]]) ? 1.0 : -1.0;
+        delta_e += -2.0 * g->adj_j[k] * old_coupling;
+    }
+    return delta_e;
+}
+
+/* should_flip, graph.rs:339-347 */
+static int cls_should_flip(OrcCls *g, double beta, double delta_e) {
+    if (delta_e > 0.0) {
+        double chance = exp(-beta * delta_e);
+        return gen_f64(&g->rng) < chance;
+    }
+    return 1;
+}
+
+/* enable_edge_importance_sampling, graph.rs:321-336: running sums of the edge weights in edge order */
+void orc_cls_enable_edge_importance_sampling(OrcCls *g, int enable) {
+    free(g->cum_w);
+    g->cum_w = NULL, g->total_w = 0.0;
+    if (!enable) return;
+    g->cum_w = (double *)malloc(sizeof(double) * (g->nedges ? g->nedges : 1));
+    double acc = 0.0;
+    for (uint32_t e = 0; e < g->nedges; e++) acc = acc + g->ej[e], g->cum_w[e] = acc;
+    g->total_w = acc;
+}
+
+/* slice::binary_search_by (core 1.5x..): any index with an equal element, else the insertion point */
+static uint32_t cls_binary_search(const double *a, uint32_t n, double p) {
+    uint32_t size = n, left = 0, right = n;
+    while (left < right) {
+        uint32_t mid = left + size / 2;
+        if (a[mid] < p) left = mid + 1;
+        else if (a[mid] > p) right = mid;
+        else return mid;
+        size = right - left;
+    }
+    return left;
+}
+
+/* do_edge_flip, graph.rs:122-153 */
+void orc_cls_edge_flips(OrcCls *g, double beta, uint64_t count) {
+    for (uint64_t t = 0; t < count; t++) {
+        uint32_t indx_edge;
+        if (g->cum_w) {
+            if (!(0.0 < g->total_w)) { g->error = 1; return; } /* gen_range panics on an empty range */
+            double p = gen_range_f64(&g->rng, 0.0, g->total_w);
+            indx_edge = cls_binary_search(g->cum_w, g->nedges, p);
+        } else {
+            if (g->nedges == 0) { g->error = 1; return; }
+            indx_edge = (uint32_t)gen_range_usize(&g->rng, g->nedges);
+        }
+        if (indx_edge >= g->nedges) { g->error = 1; return; } /* index out of bounds panic */
+        uint32_t va = g->ea[indx_edge], vb = g->eb[indx_edge];
+        double da = cls_delta_e_omit(g, va, vb) + (2.0 * g->biases[va] * (g->state[va] ? 1.0 : -1.0));
+        double db = cls_delta_e_omit(g, vb, va) + (2.0 * g->biases[vb] * (g->state[vb] ? 1.0 : -1.0));
+        double delta_e = da + db;
+        if (cls_should_flip(g, beta, delta_e)) g->state[va] = !g->state[va], g->state[vb] = !g->state[vb];
+    }
+}
+
+/* WormMove (graph.rs:46-50): Single(a) is (a, NONE), Double(a, b) is (a, b) */
+#define WM_NONE 0xFFFFFFFFu
+typedef struct { uint32_t a, b; } Worm;
+static double worm_delta_e(const OrcCls *g, Worm m) { /* :191-199 */
+    if (m.b == WM_NONE) return cls_delta_e_omit(g, m.a, -1);
+    double de = cls_delta_e_omit(g, m.a, m.b);
+    return de + cls_delta_e_omit(g, m.b, m.a);
+}
+static int cmp_u32(const void *x, const void *y) {
+    uint32_t a = *(const uint32_t *)x, b = *(const uint32_t *)y;
+    return a < b ? -1 : a > b;
+}
+#define EPS_F64 2.220446049250313e-16
+
+/* do_worm_flip, graph.rs:179-318 */
+void orc_cls_worm_flips(OrcCls *g, double beta, uint64_t count, int allow_doubles) {
+    const uint32_t N = g->nvars;
+    uint32_t maxdeg = 0;
+    for (uint32_t v = 0; v < N; v++)
+        if (g->adj_start[v + 1] - g->adj_start[v] > maxdeg) maxdeg = g->adj_start[v + 1] - g->adj_start[v];
+    Worm *path = (Worm *)malloc(sizeof(Worm) * ((size_t)N + 2));
+    Worm *sm = (Worm *)malloc(sizeof(Worm) * ((size_t)maxdeg * (maxdeg + 1) + 1));
+    double *sde = (double *)malloc(sizeof(double) * ((size_t)maxdeg * (maxdeg + 1) + 1));
+    uint32_t *flat = (uint32_t *)malloc(sizeof(uint32_t) * 2 * ((size_t)N + 2));
+    for (uint64_t t = 0; t < count; t++) {
+        uint32_t start_index = (uint32_t)gen_range_usize(&g->rng, N); /* :187 */
+        size_t plen = 0;
+        path[plen++] = (Worm){start_index, WM_NONE};
+        uint32_t last_index = start_index;
+        double starting_e = worm_delta_e(g, (Worm){start_index, WM_NONE});
+        g->state[start_index] = !g->state[start_index];
+        int update_failed = 0;
+        for (;;) {
+            uint32_t ns = 0;
+            Worm sel_move = path[plen - 1];
+            uint32_t sel_var = sel_move.b == WM_NONE ? sel_move.a : sel_move.b;
+            int any_resolve = 0;
+            for (uint32_t k = g->adj_start[sel_var]; k < g->adj_start[sel_var + 1]; k++) { /* :214-242 */
+                uint32_t ov = g->adj_idx[k];
+                if (ov == last_index) continue;
+                double de = worm_delta_e(g, (Worm){ov, WM_NONE});
+                if (fabs(de) < EPS_F64) {
+                    sm[ns] = (Worm){ov, WM_NONE}, sde[ns++] = de;
+                } else if (fabs(de + starting_e) < EPS_F64) {
+                    sm[ns] = (Worm){ov, WM_NONE}, sde[ns++] = de;
+                    any_resolve = 1;
+                }
+                if (allow_doubles) { /* jumps from ov as if ov were flipped :225-240 */
+                    g->state[ov] = !g->state[ov];
+                    for (uint32_t kk = g->adj_start[ov]; kk < g->adj_start[ov + 1]; kk++) {
+                        uint32_t oov = g->adj_idx[kk];
+                        if (oov != ov && oov != sel_var) {
+                            double de2 = worm_delta_e(g, (Worm){oov, WM_NONE}) + de;
+                            if (fabs(de2) < EPS_F64) {
+                                sm[ns] = (Worm){ov, oov}, sde[ns++] = de2;
+                            } else if (fabs(de2 + starting_e) < EPS_F64) {
+                                sm[ns] = (Worm){ov, oov}, sde[ns++] = de2;
+                                any_resolve = 1;
+                            }
+                        }
+                    }
+                    g->state[ov] = !g->state[ov];
+                }
+            }
+            if (any_resolve) { /* retain :243-245 */
+                uint32_t w = 0;
+                for (uint32_t i = 0; i < ns; i++)
+                    if (fabs(sde[i] + starting_e) < EPS_F64) sm[w] = sm[i], sde[w++] = sde[i];
+                ns = w;
+            }
+            Worm ov;
+            double de;
+            if (ns) { /* :247-251 */
+                uint32_t choice = (uint32_t)gen_range_usize(&g->rng, ns);
+                ov = sm[choice], de = sde[choice];
+                path[plen++] = ov;
+            } else { /* turn around, undo the last move :252-262 */
+                ov = sel_move.b == WM_NONE ? sel_move : (Worm){sel_move.b, sel_move.a};
+                path[plen++] = ov;
+                de = worm_delta_e(g, ov);
+            }
+            g->state[ov.a] = !g->state[ov.a]; /* :263-271 */
+            if (ov.b != WM_NONE) g->state[ov.b] = !g->state[ov.b];
+            if (ov.b != WM_NONE) last_index = ov.a; /* :272-276, against the move selected at the top of the round */
+            else last_index = sel_move.b == WM_NONE ? sel_move.a : sel_move.b;
+            if (fabs(de + starting_e) < EPS_F64) break; /* back at the initial energy :277-280 */
+            if (plen > N) { /* :282-285 */
+                update_failed = 1;
+                break;
+            }
+        }
+        size_t nf = 0; /* :287-298: flatten, sort, drop pairs (a variable visited twice is back where it was) */
+        for (size_t i = 0; i < plen; i++) {
+            flat[nf++] = path[i].a;
+            if (path[i].b != WM_NONE) flat[nf++] = path[i].b;
+        }
+        qsort(flat, nf, sizeof(uint32_t), cmp_u32);
+        size_t ii = 0, jj = 0; /* util/vec_help.rs:2-24 */
+        while (jj + 1 < nf) {
+            if (flat[jj] == flat[jj + 1]) jj += 2;
+            else flat[ii++] = flat[jj++];
+        }
+        if (jj < nf) flat[ii++] = flat[jj++];
+        nf = ii;
+        int undo = update_failed;
+        if (!update_failed) { /* :300-311 */
+            double total_he = 0.0;
+            for (size_t i = 0; i < nf; i++) total_he += 2.0 * g->biases[flat[i]] * (g->state[flat[i]] ? 1.0 : -1.0);
+            undo = !cls_should_flip(g, beta, total_he);
+        }
+        if (undo)
+            for (size_t i = 0; i < nf; i++) g->state[flat[i]] = !g->state[flat[i]];
+    }
+    free(path), free(sm), free(sde), free(flat);
+}
+
+/* do_time_step, graph.rs:350-406.  A count of UINT64_MAX stands for None. */
+int orc_cls_do_time_step(OrcCls *g, double beta, uint64_t nspinupdates, uint64_t nedgeupdates,
+                         uint64_t nwormupdates, int only_basic_moves) {
+    if (nspinupdates == UINT64_MAX) nspinupdates = g->nvars / 2 > 1 ? g->nvars / 2 : 1;
+    if (nedgeupdates == UINT64_MAX) nedgeupdates = g->nedges / 2 > 1 ? g->nedges / 2 : 1;
+    if (nwormupdates == UINT64_MAX) nwormupdates = 1;
+    uint32_t t = only_basic_moves ? 2 : 3;
+    uint32_t choice = gen_range_u8(&g->rng, t); /* :365 */
+    if (choice == 0) orc_cls_spin_flips(g, beta, nspinupdates);
+    else if (choice == 1) orc_cls_edge_flips(g, beta, nedgeupdates);
+    else orc_cls_worm_flips(g, beta, nwormupdates, 1);
+    return (int)choice;
+}
+int orc_cls_get_error(const OrcCls *g) { return g->error; }
+void orc_cls_set_cursor(OrcCls *g, uint64_t cursor) { g->rng.cursor = cursor, g->rng.blk_valid = 0; }
 
 uint64_t orc_cls_threshold(double beta, double delta_e) {
     if (!(delta_e > 0.0)) return 4294967296ull;

@@ -116,6 +116,14 @@ OrcCls *orc_cls_create(uint32_t nvars, uint32_t nedges, const uint32_t *ea, cons
 void orc_cls_destroy(OrcCls *g);
 /* `count` calls of GraphState::do_spin_flip (random-site Metropolis, reference schedule) */
 void orc_cls_spin_flips(OrcCls *g, double beta, uint64_t count);
+/* the reference's other moves and its schedule, graph.rs:121-406 (counts of UINT64_MAX = None) */
+void orc_cls_enable_edge_importance_sampling(OrcCls *g, int enable);
+void orc_cls_edge_flips(OrcCls *g, double beta, uint64_t count);
+void orc_cls_worm_flips(OrcCls *g, double beta, uint64_t count, int allow_doubles);
+int orc_cls_do_time_step(OrcCls *g, double beta, uint64_t nspinupdates, uint64_t nedgeupdates,
+                         uint64_t nwormupdates, int only_basic_moves); /* returns the move type drawn */
+int orc_cls_get_error(const OrcCls *g);
+void orc_cls_set_cursor(OrcCls *g, uint64_t cursor);
 /* checkerboard sweeps (builder-defined schedule, reference per-site rule); colours[nvars]. */
 void orc_cls_checkerboard_sweeps(OrcCls *g, double beta, const uint32_t *colours,
                                  uint32_t ncolours, uint64_t nsweeps);

@@ -92,6 +92,12 @@ def lib():
     sig("orc_cls_create", vp, C.c_uint32, C.c_uint32, u32p, u32p, f64p, f64p, C.c_uint64, u8p)
     sig("orc_cls_destroy", None, vp)
     sig("orc_cls_spin_flips", None, vp, C.c_double, C.c_uint64)
+    sig("orc_cls_enable_edge_importance_sampling", None, vp, C.c_int)
+    sig("orc_cls_edge_flips", None, vp, C.c_double, C.c_uint64)
+    sig("orc_cls_worm_flips", None, vp, C.c_double, C.c_uint64, C.c_int)
+    sig("orc_cls_do_time_step", C.c_int, vp, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int)
+    sig("orc_cls_get_error", C.c_int, vp)
+    sig("orc_cls_set_cursor", None, vp, C.c_uint64)
     sig("orc_cls_checkerboard_sweeps", None, vp, C.c_double, u32p, C.c_uint32, C.c_uint64)
     sig("orc_cls_energy", C.c_double, vp)
     sig("orc_cls_magnetization", C.c_double, vp)
@@ -275,6 +281,27 @@ class ClassicalOracle:
 
     def spin_flips(self, beta, count):
         lib().orc_cls_spin_flips(self._h, beta, count)
+
+    # the reference's other moves and its own schedule (graph.rs:121-406)
+    def enable_edge_importance_sampling(self, enable=True):
+        lib().orc_cls_enable_edge_importance_sampling(self._h, int(bool(enable)))
+
+    def edge_flips(self, beta, count):
+        lib().orc_cls_edge_flips(self._h, beta, count)
+
+    def worm_flips(self, beta, count=1, allow_doubles=True):
+        lib().orc_cls_worm_flips(self._h, beta, count, int(bool(allow_doubles)))
+
+    def do_time_step(self, beta, nspinupdates=None, nedgeupdates=None, nwormupdates=None, only_basic_moves=False):
+        none = 2**64 - 1
+        return lib().orc_cls_do_time_step(self._h, beta, none if nspinupdates is None else nspinupdates,
+                                          none if nedgeupdates is None else nedgeupdates,
+                                          none if nwormupdates is None else nwormupdates, int(bool(only_basic_moves)))
+
+    error = property(lambda s: lib().orc_cls_get_error(s._h))
+
+    def set_cursor(self, c):
+        lib().orc_cls_set_cursor(self._h, int(c))
 
     def checkerboard_sweeps(self, beta, colours, nsweeps=1):
         col = np.ascontiguousarray(colours, dtype=np.uint32)

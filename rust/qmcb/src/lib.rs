@@ -289,8 +289,26 @@ impl GraphState {
                                         init.as_ref().map_or(std::ptr::null(), |v| v.as_ptr()), device, &mut h) })?;
         Ok(Self { h, nvars: biases.len(), replicas: rng_keys.len() })
     }
-    /// do_time_step (graph.rs:350-406): `sweeps` checkerboard sweeps of every replica
-    pub fn do_time_step(&mut self, sweeps: usize) -> Result<(), String> { check(unsafe { sys::cmcb_sweeps(self.h, sweeps as u64) }) }
+    /// `sweeps` checkerboard sweeps of every replica (the throughput path; builder-defined schedule, reference per-site rule)
+    pub fn sweeps(&mut self, sweeps: usize) -> Result<(), String> { check(unsafe { sys::cmcb_sweeps(self.h, sweeps as u64) }) }
+    /// do_time_step (graph.rs:350-406), the reference's own schedule under each replica's sequential stream: one draw
+    /// picks spin flips, edge flips or worm flips.  Returns the move every replica drew.
+    pub fn do_time_step(&mut self, nspinupdates: Option<usize>, nedgeupdates: Option<usize>, nwormupdates: Option<usize>,
+                        only_basic_moves: Option<bool>) -> Result<Vec<u8>, String> {
+        let f = |x: Option<usize>| x.map_or(u64::MAX, |v| v as u64);
+        let mut choice = vec![0u8; self.replicas];
+        check(unsafe { sys::cmcb_do_time_step(self.h, f(nspinupdates), f(nedgeupdates), f(nwormupdates),
+                                              only_basic_moves.unwrap_or(false) as i32, choice.as_mut_ptr()) })?;
+        Ok(choice)
+    }
+    /// do_worm_flip (graph.rs:179-318)
+    pub fn do_worm_flip(&mut self, count: usize, allow_doubles: bool) -> Result<(), String> {
+        check(unsafe { sys::cmcb_worm_flips(self.h, count as u64, allow_doubles as i32) })
+    }
+    /// enable_edge_importance_sampling (graph.rs:321-336)
+    pub fn enable_edge_importance_sampling(&mut self, enable: bool) -> Result<(), String> {
+        check(unsafe { sys::cmcb_enable_edge_importance_sampling(self.h, enable as i32) })
+    }
     /// get_energy (graph.rs:430-447)
     pub fn get_energy(&mut self) -> Result<Vec<f64>, String> {
         let mut e = vec![0.0; self.replicas];

@@ -128,8 +128,22 @@ int main() {
                 edges.push_back({{j * L + i, ((j + 1) % L) * L + i}, -1.0});
             }
         auto g = qmcb::GraphState::create(edges, std::vector<double>(L * L, 0.0), {1, 2, 3}, {2.0, 2.0, 2.0});
-        g.do_time_step(200);
+        g.sweeps(200);
         for (double e : g.get_energy()) ASSERT(e < -80.0);  // quench into the ordered phase: -128 (uniform) or -96 (one stripe)
+        for (int t = 0; t < 5; t++) g.do_time_step();       // the reference's own schedule keeps a cold system cold
+        for (double e : g.get_energy()) ASSERT(e < -80.0);
+    }
+    {  // classical/graph.rs:481-498 test_worm_flip and :564-581 test_worm_flip_doubles, on every replica
+        std::vector<Edge> tri = {{{0, 1}, 1.0}, {{1, 2}, 1.0}, {{2, 0}, 1.0}};
+        std::vector<bool> zeros(3, false);
+        std::vector<uint64_t> keys = {1, 2, 3, 4, 5, 6, 7, 8};
+        std::vector<double> betas(keys.size(), 1.0);
+        auto g = qmcb::GraphState::create(tri, {0., 0., 0.}, keys, betas, 0, &zeros);
+        g.do_worm_flip(1, false);
+        for (auto &s : g.state_ref()) ASSERT(s[0] && s[1] && s[2]);
+        auto g2 = qmcb::GraphState::create(tri, {0., 0., 0.}, keys, betas, 0, &zeros);
+        g2.do_worm_flip(1, true);
+        for (auto &s : g2.state_ref()) ASSERT(s[0] == s[1] && s[1] == s[2]);
     }
     std::printf("cpp mirror ok\n");
     return 0;

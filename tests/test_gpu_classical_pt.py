@@ -18,7 +18,7 @@ def run_classical(edges, biases, betas, sweeps, keys, state=None):
     for r, ref in enumerate(refs):
         assert np.array_equal(st0[r], ref.state()), "stream-drawn initial state"
     for chunk in (1, 2, sweeps - 3):
-        g.do_time_step(chunk)
+        g.sweeps(chunk)
         st = g.state_ref()
         e, m = g.get_energy(), g.magnetization()
         for r, ref in enumerate(refs):
@@ -81,10 +81,10 @@ def test_classical_energy_matches_onsager(beta):
     edges = lattices.square_periodic(L, -1.0)
     state = None if beta < 0.44 else np.zeros((R, L * L), dtype=np.uint8)
     g = GraphState(edges, np.zeros(L * L), 0xB2000000 + np.arange(R), beta, state=state)
-    g.do_time_step(500)
+    g.sweeps(500)
     es = []
     for _ in range(40):
-        g.do_time_step(10)
+        g.sweeps(10)
         es.append(g.get_energy() / (L * L))
     e = np.mean(es, axis=0)
     err = e.std(ddof=1) / np.sqrt(R)
@@ -272,7 +272,7 @@ def test_square_fused_launches_equal_per_pass_launches():
         b = GraphState(edges, np.zeros(L * L), keys, betas)
         b.set_option("fused", 0)
         for chunk in (1, sweeps):
-            a.do_time_step(chunk), b.do_time_step(chunk)
+            a.sweeps(chunk), b.sweeps(chunk)
             assert np.array_equal(a.state_ref(), b.state_ref()), (L, chunk)
         assert np.array_equal(a.get_energy(), b.get_energy())
         assert a.launch_count() < b.launch_count()

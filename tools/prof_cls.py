@@ -17,9 +17,9 @@ L = 1024
 g = GraphState(lattices.square_periodic(L, -1.0), np.zeros(L * L), 0xB2000000 + np.arange(R, dtype=np.uint64), 0.44068679350977147)
 if os.environ.get("PROF_UNFUSED"):
     g.set_option("fused", 0)
-g.do_time_step(spl)
+g.sweeps(spl)
 for k in range(launches):
     t0 = time.perf_counter()
-    g.do_time_step(spl)
+    g.sweeps(spl)
     dt = time.perf_counter() - t0
     print(f"launch {k}: {dt * 1e3:.2f} ms, {R * L * L * spl / dt:.3e} flip attempts/s")

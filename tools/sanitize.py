@@ -27,7 +27,7 @@ g.calculate_variable_autocorrelation(16, 2.0, 1)
 g.set_option("minblocks", 0)
 g.close()
 c = GraphState(lattices.square_periodic(64, -1.0), np.zeros(64 * 64), [1, 2], 0.44)
-c.do_time_step(3)
+c.sweeps(3)
 c.get_energy()
 c.close()
 print("sanitize run ok")
