@@ -17,8 +17,8 @@
 #include "sse.cuh"
 
 // kernels (sse_serial.cu, sse_fast.cu, classical.cu, pt.cu)
-void launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phases, uint64_t sample_freq,
-                       uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);
+int launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phases, uint64_t sample_freq,
+                      uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, int layout, cudaStream_t st);
 void launch_sse_verify(const SseDev &D, uint32_t r, int *ok_dev, uint32_t *scratch_dev, cudaStream_t st);
 void launch_sse_bond_counts(const SseDev &D, uint32_t r, unsigned long long *counts_dev, cudaStream_t st);
 void launch_sse_recount(const SseDev &D, uint32_t r, cudaStream_t st);
@@ -96,6 +96,8 @@ struct QmcbHandle {
     Pool pool;
     int mode = QMCB_MODE_STRICT;
     int impl = 0;  // 0 auto (warp-parallel FAST kernels where supported), 1 serial kernels only
+    int strict_layout = 1;  // STRICT cluster step: 1 world-line arrays (default), 0 one record per slot (qmcb_set_option "strict_layout")
+    bool strict_wl_last = false;  // which layout the last STRICT cluster step left in the workspace (qmcb_get_boundaries)
     double offset = 0.0;
     uint64_t target = 0;  // sweeps requested so far
     uint64_t launches = 0;
@@ -144,7 +146,8 @@ static size_t bits_stride(const SseDev &D) { return (size_t)(D.cap / 32 + 2 + D.
 static int alloc_strict_ws(QmcbHandle *h) {
     if (h->strict_ws) return QMCB_OK;
     SseDev &D = h->D;
-    CUDA_TRY(h->pool.alloc(&D.rec, (size_t)D.R * D.cap * 8));
+    CUDA_TRY(h->pool.alloc(&D.rec, (size_t)D.R * strict_rec_stride(D)));
+    CUDA_TRY(h->pool.alloc(&D.ent, (size_t)D.R * D.cap));
     CUDA_TRY(h->pool.alloc(&D.frontier, (size_t)D.R * (2 * D.cap + 16)));
     CUDA_TRY(h->pool.alloc(&D.interior, (size_t)D.R * (4 * D.cap + 16)));
     h->strict_ws = true;
@@ -178,10 +181,12 @@ static int grow(QmcbHandle *h, uint64_t newcap) {
     SseDev Dn = D;
     Dn.cap = newcap;
     uint32_t *nops = nullptr, *nbits = nullptr, *nfrozen = nullptr, *nrec = nullptr, *nfrontier = nullptr, *ninterior = nullptr, *nparent = nullptr, *nsid = nullptr;
+    uint32_t *nent = nullptr;
     cudaError_t e = h->pool.alloc(&nops, (size_t)D.R * newcap);
     if (e == cudaSuccess) e = h->pool.alloc(&nbits, (size_t)D.R * bits_stride(Dn));
     if (e == cudaSuccess) e = h->pool.alloc(&nfrozen, (size_t)D.R * bits_stride(Dn));
-    if (e == cudaSuccess && s) e = h->pool.alloc(&nrec, (size_t)D.R * newcap * 8);
+    if (e == cudaSuccess && s) e = h->pool.alloc(&nrec, (size_t)D.R * strict_rec_stride(Dn));
+    if (e == cudaSuccess && s) e = h->pool.alloc(&nent, (size_t)D.R * newcap);
     if (e == cudaSuccess && s) e = h->pool.alloc(&nfrontier, (size_t)D.R * (2 * newcap + 16));
     if (e == cudaSuccess && s) e = h->pool.alloc(&ninterior, (size_t)D.R * (4 * newcap + 16));
     if (e == cudaSuccess && f) e = h->pool.alloc(&nparent, (size_t)D.R * (D.N + newcap + 1));
@@ -192,11 +197,12 @@ static int grow(QmcbHandle *h, uint64_t newcap) {
     if (e != cudaSuccess) {
         cudaGetLastError();
         h->pool.release(nops), h->pool.release(nbits), h->pool.release(nfrozen), h->pool.release(nrec);
-        h->pool.release(nfrontier), h->pool.release(ninterior), h->pool.release(nparent), h->pool.release(nsid);
+        h->pool.release(nfrontier), h->pool.release(ninterior), h->pool.release(nparent), h->pool.release(nsid), h->pool.release(nent);
         return fail(QMCB_ERR_CAPACITY, "out of device memory while growing the operator strings");
     }
     h->pool.release(D.ops), h->pool.release(D.rec), h->pool.release(D.frontier), h->pool.release(D.interior);
-    h->pool.release(D.parent), h->pool.release(D.bits), h->pool.release(D.frozen), h->pool.release(D.sid);
+    h->pool.release(D.parent), h->pool.release(D.bits), h->pool.release(D.frozen), h->pool.release(D.sid), h->pool.release(D.ent);
+    D.ent = nent;
     D.ops = nops, D.bits = nbits, D.frozen = nfrozen, D.rec = nrec, D.frontier = nfrontier, D.interior = ninterior, D.parent = nparent, D.sid = nsid;
     D.cap = newcap;
     return QMCB_OK;
@@ -230,7 +236,7 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
             for (uint64_t tgt = origin + 1; tgt <= h->target && ok; tgt++) {
                 int nl = launch_sse_fast(h->D, h->tune, tgt, 1u | 16u, freq, origin, nullptr, 0, h->stream);
                 if (nl < 0) { ok = false; break; }
-                launch_sse_serial(h->D, 0, tgt, 2u | 4u | 8u | 16u, freq, origin, samples_dev, spr, h->stream);
+                h->strict_wl_last = launch_sse_serial(h->D, 0, tgt, 2u | 4u | 8u | 16u, freq, origin, samples_dev, spr, h->strict_layout, h->stream) != 0;
                 h->launches += (uint64_t)nl + 1;
             }
             if (ok) {
@@ -238,13 +244,14 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
                 return QMCB_OK;
             }
         }
-        launch_sse_serial(h->D, 0, h->target, phases, freq, origin, samples_dev, spr, h->stream);
+        const int wl = launch_sse_serial(h->D, 0, h->target, phases, freq, origin, samples_dev, spr, h->impl == 1 ? 0 : h->strict_layout, h->stream);
+        if (phases & 2u) h->strict_wl_last = wl != 0;
         h->launches += 1;
     } else if (h->mode == QMCB_MODE_COUNTER) {
         if ((rc = alloc_fast_ws(h)) || (rc = alloc_counter_ws(h))) return rc;
         int nl = h->impl == 1 ? -1 : launch_sse_counter(h->D, h->tune, h->target, phases, freq, origin, samples_dev, spr, h->stream);
         if (nl < 0) {
-            launch_sse_serial(h->D, 2, h->target, phases, freq, origin, samples_dev, spr, h->stream);
+            launch_sse_serial(h->D, 2, h->target, phases, freq, origin, samples_dev, spr, 0, h->stream);
             nl = 1;
         }
         h->launches += (uint64_t)nl;
@@ -252,7 +259,7 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
         if ((rc = alloc_fast_ws(h))) return rc;
         int nl = h->impl == 1 ? -1 : launch_sse_fast(h->D, h->tune, h->target, phases, freq, origin, samples_dev, spr, h->stream);
         if (nl < 0) {
-            launch_sse_serial(h->D, 1, h->target, phases, freq, origin, samples_dev, spr, h->stream);
+            launch_sse_serial(h->D, 1, h->target, phases, freq, origin, samples_dev, spr, 0, h->stream);
             nl = 1;
         }
         h->launches += (uint64_t)nl;
@@ -655,6 +662,16 @@ extern "C" int qmcb_get_mode(const QmcbHandle *h, int *mode) {
 }
 extern "C" int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value) {
     if (!h || !name) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    if (!strcmp(name, "strict_layout")) {
+        if (value < 0 || value > 3 || value == 2) return fail(QMCB_ERR_BAD_ARG, "strict_layout is 0 (one record per slot), 1 (world-line arrays) or 3 (world-line arrays + next-line prefetch)");
+        h->strict_layout = (int)value;
+        return QMCB_OK;
+    }
+    if (!strcmp(name, "l2_fetch_granularity")) {  // device-wide: bytes the L2 fetches from DRAM per miss (32, 64 or 128)
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+        return QMCB_OK;
+    }
     if (!strcmp(name, "impl")) {
         h->impl = (int)value;
         return QMCB_OK;
@@ -1178,10 +1195,21 @@ extern "C" int qmcb_get_boundaries(QmcbHandle *h, uint32_t r, uint32_t *b_in, ui
     if (!b_in || !b_out || r >= D.R) return fail(QMCB_ERR_BAD_ARG, "bad replica index");
     if (!h->strict_ws) return fail(QMCB_ERR_BAD_ARG, "no STRICT cluster step has run yet");
     uint64_t k = std::min<uint64_t>(nslots, D.cap);
-    std::vector<uint32_t> b(8 * k), ow(k);
+    std::vector<uint32_t> ow(k);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    CUDA_TRY(cudaMemcpy(b.data(), D.rec + (size_t)r * D.cap * 8, 32 * k, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(ow.data(), D.ops + (size_t)r * D.cap, 4 * k, cudaMemcpyDeviceToHost));
+    if (h->strict_wl_last) {  // world-line layout: the boundaries sit in the entry of leg 0, ent[p]
+        std::vector<uint32_t> wl(strict_rec_stride(D)), ent(k);
+        CUDA_TRY(cudaMemcpy(wl.data(), D.rec + (size_t)r * strict_rec_stride(D), 4 * wl.size(), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(ent.data(), D.ent + (size_t)r * D.cap, 4 * k, cudaMemcpyDeviceToHost));
+        for (uint64_t p = 0; p < nslots; p++) {
+            const bool has = p < k && ow[p] != QMCB_OP_EMPTY;
+            b_in[p] = has ? wl[4 * (size_t)ent[p] + 2] : NONE32, b_out[p] = has ? wl[4 * (size_t)ent[p] + 3] : NONE32;
+        }
+        return QMCB_OK;
+    }
+    std::vector<uint32_t> b(8 * k);
+    CUDA_TRY(cudaMemcpy(b.data(), D.rec + (size_t)r * strict_rec_stride(D), 32 * k, cudaMemcpyDeviceToHost));
     for (uint64_t p = 0; p < nslots; p++) {
         const bool has = p < k && ow[p] != QMCB_OP_EMPTY;  // records of empty slots are stale
         b_in[p] = has ? b[8 * p + 5] : NONE32, b_out[p] = has ? b[8 * p + 6] : NONE32;

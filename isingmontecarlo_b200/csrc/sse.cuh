@@ -39,7 +39,9 @@ struct SseDev {
     uint32_t *vfirst, *vlast;  // [R][N] first / last leg (p << 1 | rel) on each variable, or NONE32
     uint32_t *cur;             // [R][N] FAST: current segment id per variable
     // STRICT workspace (allocated on demand)
-    uint32_t *rec;       // [R][cap][8] one 32-byte record per slot: op word, 4 links, 2 cluster ids (sse_serial.cu)
+    uint32_t *rec;       // [R][strict_rec_stride] STRICT workspace: one 32-byte record per slot (op word, 4 links, 2 cluster ids), or
+                         // the world-line layout: one 16-byte entry per leg + two sentinels per variable (sse_serial.cu)
+    uint32_t *ent;       // [R][cap] world-line layout: entry of leg 0 of the op in each slot
     uint32_t *frontier;  // [R][2*cap+16]
     uint32_t *interior;  // [R][4*cap+16]
     uint32_t *bits;      // [R][cap/32+2] flip bit per cluster (STRICT) / per segment (FAST)
@@ -62,6 +64,9 @@ struct SseDev {
     const double *hb_cum_tab, *hb_maxw_tab;  // [H][Nb] (heat-bath on)
     const double *hb_total_tab;              // [H]
 };
+
+// u32 words of one replica's STRICT workspace row: 8 per slot (two legs per slot at most) + the sentinels of every variable
+__host__ __device__ __forceinline__ size_t strict_rec_stride(const SseDev &D) { return 8 * ((size_t)D.cap + D.N + 1); }
 
 // kernel-selection knobs of the warp-parallel sweep, owned by the handle (qmcb_set_option); nsm is the SM count of the
 // handle's device, queried once at creation

@@ -23,9 +23,37 @@
 #define REC_LINK(V, p, i) ((V).rec[8 * (size_t)(p) + 1 + (i)])
 #define REC_BND(V, p, side) ((V).rec[8 * (size_t)(p) + 5 + (side)])
 
+// phase timers of the STRICT cluster step (-DQMCB_PHASE_TIMERS + qmcb_set_option("debug_counters")): cycles of lane 0
+// summed over replicas and sweeps in dbg[48..]: 0 links, 1 labelling walk, 2 flip bits, 3 apply, 4 free spins;
+// dbg[56..]: 0 interior pops, 1 site arrivals, 2 interior-op arrivals that were labelled, 3 world-line wraps, 4 frontier pops
+#ifdef QMCB_PHASE_TIMERS
+#define ST_MARK(i)                                                                   \
+    do {                                                                             \
+        __syncwarp();                                                                \
+        if (lane == 0 && D.dbg) {                                                    \
+            const long long t_ = clock64();                                          \
+            atomicAdd(&D.dbg[48 + (i)], (unsigned long long)(t_ - st_t));            \
+            st_t = t_;                                                               \
+        }                                                                            \
+    } while (0)
+#define ST_COUNT(i) (cnt_[i]++)
+#define ST_COUNT_DECL unsigned long long cnt_[5] = {0, 0, 0, 0, 0}
+#define ST_COUNT_FLUSH                                                               \
+    do {                                                                             \
+        if (D.dbg)                                                                   \
+            for (int i_ = 0; i_ < 5; i_++) atomicAdd(&D.dbg[56 + i_], cnt_[i_]);     \
+    } while (0)
+#else
+#define ST_MARK(i) ((void)0)
+#define ST_COUNT(i) ((void)0)
+#define ST_COUNT_DECL ((void)0)
+#define ST_COUNT_FLUSH ((void)0)
+#endif
+
 struct Rep {
     uint32_t *ops, *state, *vfirst, *vlast, *cur, *rec, *frontier, *interior, *bits, *frozen, *parent;
-    uint32_t *ends;
+    uint32_t *ends, *ent;
+    uint4 *wl;  // world-line layout of the STRICT workspace: the same buffer as rec
     uint64_t fcap, icap;
 };
 
@@ -36,7 +64,9 @@ __device__ __forceinline__ Rep rep_view(const SseDev &D, uint32_t r) {
     v.vfirst = D.vfirst + (size_t)r * D.N;
     v.vlast = D.vlast + (size_t)r * D.N;
     v.cur = D.cur + (size_t)r * D.N;
-    v.rec = D.rec ? D.rec + (size_t)r * D.cap * 8 : nullptr;
+    v.rec = D.rec ? D.rec + (size_t)r * strict_rec_stride(D) : nullptr;
+    v.wl = reinterpret_cast<uint4 *>(v.rec);
+    v.ent = D.ent ? D.ent + (size_t)r * D.cap : nullptr;
     v.fcap = 2 * D.cap + 16, v.icap = 4 * D.cap + 16;
     v.frontier = D.frontier ? D.frontier + (size_t)r * v.fcap : nullptr;
     v.interior = D.interior ? D.interior + (size_t)r * v.icap : nullptr;
@@ -407,6 +437,7 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err, int la
     // are set leg by leg (which is what makes the reference push duplicates): those entries carry bit 31 and set
     // boundary (p0, side ^ 1 of the entry) when popped.  Push and pop order are the reference's.
     uint32_t cnum = 0, scan = 0;
+    ST_COUNT_DECL;
     auto push_leg = [&](const uint4 &lo, const uint4 &hi, uint32_t k, uint32_t side, uint32_t v0, uint32_t v1, uint32_t flag) {
         uint32_t lk = rec_link(lo, hi, 2u * side + k);
         if (lk == NONE32) {  // wrap through the ends of the world line :224-241
@@ -420,6 +451,7 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err, int la
         if (lane == 0) {
             while (flen) {  // :62-80
                 const uint32_t e = fpop();
+                ST_COUNT(4);
                 const uint32_t p0 = e >> 1, side0 = e & 1u;
                 const uint4 l0 = ld_rec_lo(V, p0), h0 = ld_rec_hi(V, p0);
                 if (h0.y != NONE32 && h0.z != NONE32) continue;
@@ -439,6 +471,7 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err, int la
                     }
                     while (ilen) {
                         const uint32_t it = ipop();
+                        ST_COUNT(0);
                         const uint32_t sq = it & 1u, lk = (it & 0x7FFFFFFFu) >> 1;
                         if (it & 0x80000000u) {  // set_boundary(p0, side, cnum) :218, :289-306
                             const uint32_t side = sq ^ 1u;
@@ -450,6 +483,7 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err, int la
                         const uint4 ql = ld_rec_lo(V, q), qh = ld_rec_hi(V, q);  // one sector: op, links, boundaries
                         const uint32_t bq = op_bond(ql.x);
                         if (bq >= E && bq < EN) {  // cluster edge :245-248
+                            ST_COUNT(1);
                             const uint32_t mine = sq ? qh.z : qh.y, other = sq ? qh.y : qh.z;
                             if (mine == NONE32) REC_BND(V, q, sq) = cnum;
                             else if (mine != cnum) err |= DEV_ERR_INVARIANT;
@@ -461,6 +495,7 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err, int la
                             const uint32_t a = qh.y, bb = qh.z;
                             const bool ok = (a == NONE32 && bb == NONE32) || (a == cnum && bb == NONE32) || (a == NONE32 && bb == cnum);
                             if (ok) {
+                                ST_COUNT(2);
                                 REC_BND(V, q, 0) = cnum, REC_BND(V, q, 1) = cnum;
                                 const int kq = bond_kind(D, bq);
                                 uint32_t c0, c1;
@@ -500,11 +535,12 @@ __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err, int la
             fpush((unmapped << 1) | SIDE_IN);
         }
     }
+    if (lane == 0) ST_COUNT_FLUSH;
     return __shfl_sync(0xFFFFFFFFu, cnum, 0);
 }
 
 // flip_each_cluster_rng (cluster.rs:36-172), whole warp; returns n_clusters
-__device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, int lane, uint32_t *stk) {
+__device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, int lane, uint32_t *stk, long long &st_t) {
     const uint32_t n = D.n[r];
     if (n == 0) return 0;  // :46-48
     const uint32_t last_p = V.ends[1], cp = V.ends[2];
@@ -519,6 +555,7 @@ __device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, in
     }
     if (err) atomicOr(D.status, err);
     __syncwarp();
+    ST_MARK(1);
     // flips: one gen_bool per cluster in id order (:111-137).  With a longitudinal field the
     // weight product is 0.0 for a cluster holding a longitudinal op (qmc_ising.rs:759-775):
     // gen_bool(0.0) still consumes its word and returns false.
@@ -544,6 +581,7 @@ __device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, in
         if (lane == 0) V.bits[base >> 5] = D.has_h ? (word & ~V.frozen[base >> 5]) : word;
     }
     __syncwarp();
+    ST_MARK(2);
     // apply (:139-167)
     for (uint32_t p = lane; p <= last_p; p += 32) {
         uint32_t w = V.ops[p];
@@ -569,6 +607,329 @@ __device__ uint32_t cluster_strict(const SseDev &D, uint32_t r, const Rep &V, in
     }
     if (lane == 0) D.cursor[r] = c0 + ncl;
     __syncwarp();
+    ST_MARK(3);
+    return ncl;
+}
+
+// ------------------------------------------------------------------------------------------
+// STRICT cluster step on WORLD-LINE ARRAYS (round 2, second layout; `layout` = 1 of k_sse_serial)
+// ------------------------------------------------------------------------------------------
+// The per-slot records above make every step of the walk a jump of ~1000 slots (the next op on a variable is that
+// far away in imaginary time): one DRAM sector per leg.  Here the legs of a replica are stored per VARIABLE, in p
+// order, so that following a world line is index +-1 in an array (the same 128-byte line most of the time) and only
+// a two-variable op jumps -- to the entry of its other leg, whose two neighbours are again adjacent.
+//   entry (uint4), one per leg:  x = p << 4 | first-on-its-line << 3 | leg k << 2 | kind (0 bond, 1 site, 2 longitudinal)
+//                                y = bond op: entry of the other leg << 1 | that leg is first on its line
+//                                z, w = cluster of the inputs / outputs (boundaries, cluster.rs:50-52); the two
+//                                       entries of a bond op carry the same pair
+//   variable v owns [head sentinel][its entries][tail sentinel]; a sentinel is kind 3 with y = the entry the line
+//   continues at (periodic imaginary time: the wrap of cluster.rs:224-241), so the walk needs no per-variable table.
+// ent[p] = entry of leg 0 of the op in slot p.  The order of pushes and pops -- hence the cluster numbering -- is the
+// reference's, exactly as in label_strict above; only where a leg's neighbour is found differs.
+#define WL_KIND(x) ((x) & 3u)
+#define WL_SENT 3u
+
+__device__ void links_wl(const SseDev &D, uint32_t r, const Rep &V, int lane, uint32_t *fill) {
+    const uint32_t M = D.M[r];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint32_t v = lane; v < D.N; v += 32) fill[v] = 0;
+    __syncwarp();
+    uint32_t first_p = NONE32, last_p = NONE32, first_site = NONE32;
+    for (uint32_t base = 0; base < M; base += 32) {  // pass A: legs per variable
+        const uint32_t p = base + lane;
+        const uint32_t w = p < M ? V.ops[p] : OP_EMPTY;
+        int kind = -1;
+        if (w != OP_EMPTY) {
+            uint32_t v0, v1;
+            kind = bond_kind(D, op_bond(w));
+            bond_vars(D, op_bond(w), kind, v0, v1);
+            atomicAdd(&fill[v0], 1u);
+            if (kind == KIND_BOND) atomicAdd(&fill[v1], 1u);
+        }
+        const uint32_t hasm = __ballot_sync(0xFFFFFFFFu, kind >= 0), sitem = __ballot_sync(0xFFFFFFFFu, kind == KIND_SITE);
+        if (hasm) {
+            if (first_p == NONE32) first_p = base + (uint32_t)__ffs(hasm) - 1u;
+            last_p = base + 31u - (uint32_t)__clz(hasm);
+        }
+        if (sitem && first_site == NONE32) first_site = base + (uint32_t)__ffs(sitem) - 1u;
+    }
+    __syncwarp();
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < D.N; base += 32) {  // blocks of the variables, sentinels
+        const uint32_t v = base + lane;
+        const uint32_t c = v < D.N ? fill[v] : 0u, tot = v < D.N ? c + 2u : 0u;
+        uint32_t incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const uint32_t s0 = running + incl - tot;
+        if (v < D.N) {
+            V.wl[s0] = make_uint4(WL_SENT, s0 + c, NONE32, NONE32);
+            V.wl[s0 + c + 1] = make_uint4(WL_SENT, s0 + 1, NONE32, NONE32);
+            fill[v] = (s0 + 1) | 0x80000000u;  // next entry of v; bit 31: nothing written yet
+            V.vfirst[v] = c ? 0u : NONE32;     // free_spins: does_var_have_ops
+        }
+        running += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < M; base += 32) {  // pass B: entries in p order
+        const uint32_t p = base + lane;
+        const uint32_t w = p < M ? V.ops[p] : OP_EMPTY;
+        int kind = -1;
+        uint32_t v0 = 0, v1 = 0;
+        if (w != OP_EMPTY) {
+            kind = bond_kind(D, op_bond(w));
+            bond_vars(D, op_bond(w), kind, v0, v1);
+        }
+        if (!__ballot_sync(0xFFFFFFFFu, kind >= 0)) continue;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {  // 16 slots = 32 legs, one lane per leg (lane = 2 slot + leg)
+            const int sl = 16 * half + (lane >> 1);
+            const uint32_t rel = (uint32_t)lane & 1u;
+            const int sk = __shfl_sync(0xFFFFFFFFu, kind, sl);
+            const uint32_t sv0 = __shfl_sync(0xFFFFFFFFu, v0, sl), sv1 = __shfl_sync(0xFFFFFFFFu, v1, sl);
+            const bool legvalid = sk >= 0 && (rel == 0 || sk == KIND_BOND);
+            const uint32_t sv = rel ? sv1 : sv0;
+            const uint32_t legm = __ballot_sync(0xFFFFFFFFu, legvalid);
+            const uint32_t m = __match_any_sync(0xFFFFFFFFu, legvalid ? sv : (0x80000000u | (uint32_t)lane)) & legm;
+            uint32_t idx = 0, first = 0;
+            if (legvalid) {
+                const uint32_t f = fill[sv], rank = (uint32_t)__popc(m & lt_mask);
+                idx = (f & 0x7FFFFFFFu) + rank;
+                first = (f >> 31) & (rank == 0 ? 1u : 0u);
+            }
+            __syncwarp();
+            if (legvalid && (m & ~lt_mask & ~(1u << lane)) == 0) fill[sv] = idx + 1;  // last leg of the half-step on this variable
+            const uint32_t xidx = __shfl_xor_sync(0xFFFFFFFFu, idx, 1), xfirst = __shfl_xor_sync(0xFFFFFFFFu, first, 1);
+            if (legvalid) {
+                const uint32_t ps = base + (uint32_t)sl;
+                V.wl[idx] = make_uint4((ps << 4) | (first << 3) | (rel << 2) | (uint32_t)sk, sk == KIND_BOND ? ((xidx << 1) | xfirst) : 0u, NONE32, NONE32);
+                if (rel == 0) V.ent[ps] = idx;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) V.ends[0] = first_p, V.ends[1] = last_p, V.ends[2] = first_site;
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t *wl_bnd(const Rep &V, uint32_t idx, uint32_t side) {
+    return reinterpret_cast<uint32_t *>(V.wl + idx) + 2 + side;
+}
+
+template <bool PF>
+__device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int lane, uint32_t *stk) {
+    const uint32_t last_p = V.ends[1], cp = V.ends[2];
+    uint32_t *const ist = stk, *const fst = stk + STK_I;
+    uint64_t flen = 0, ilen = 0, fbase = 0;
+    auto fpush = [&](uint32_t x) {
+        if (flen - fbase == STK_F) {
+            for (uint32_t j = 0; j < STK_F / 2; j++) V.frontier[fbase + j] = fst[j];
+            for (uint32_t j = 0; j < STK_F / 2; j++) fst[j] = fst[j + STK_F / 2];
+            fbase += STK_F / 2;
+        }
+        fst[flen - fbase] = x;
+        flen++;
+    };
+    auto fpop = [&]() -> uint32_t {
+        if (flen == fbase) {
+            const uint64_t take = fbase < STK_F / 2 ? fbase : STK_F / 2;
+            for (uint64_t j = 0; j < take; j++) fst[j] = V.frontier[fbase - take + j];
+            fbase -= take;
+        }
+        flen--;
+        return fst[flen - fbase];
+    };
+    auto ipush = [&](uint32_t x) {
+        if (ilen < STK_I) ist[ilen] = x;
+        else V.interior[ilen] = x;
+        ilen++;
+    };
+    auto ipop = [&]() -> uint32_t {
+        ilen--;
+        return ilen < STK_I ? ist[ilen] : V.interior[ilen];
+    };
+    // an interior entry is where the leg LANDS: (neighbouring entry << 1 | side it arrives at) [| bit 31: leg of the start op]
+    auto push_leg = [&](uint32_t idx, uint32_t side, uint32_t flag) { ipush((((side == SIDE_IN ? idx - 1u : idx + 1u) << 1) | (side ^ 1u)) | flag); };
+    if (lane == 0) {
+        const uint32_t e0 = V.ent[cp];
+        fpush((e0 << 1) | SIDE_OUT);  // cluster.rs:57-59
+        fpush((e0 << 1) | SIDE_IN);
+    }
+    uint32_t cnum = 0, scan = 0;
+    ST_COUNT_DECL;
+    for (;;) {
+        if (lane == 0) {
+            while (flen) {  // :62-80
+                const uint32_t fe = fpop();
+                ST_COUNT(4);
+                const uint32_t i0 = fe >> 1, side0 = fe & 1u;
+                const uint4 E0 = V.wl[i0];
+                if (E0.z != NONE32 && E0.w != NONE32) continue;
+                const uint32_t kind0 = WL_KIND(E0.x), x0 = E0.y >> 1;
+                ilen = 0;
+                if (kind0 != KIND_SITE) {  // :205-211 (i0 is the entry of leg 0: the scan below hands out ent[p])
+                    push_leg(i0, SIDE_IN, 0x80000000u);
+                    if (kind0 == KIND_BOND) push_leg(x0, SIDE_IN, 0x80000000u);
+                    push_leg(i0, SIDE_OUT, 0x80000000u);
+                    if (kind0 == KIND_BOND) push_leg(x0, SIDE_OUT, 0x80000000u);
+                } else {  // :212-215
+                    push_leg(i0, side0, 0x80000000u);
+                }
+                while (ilen) {
+                    const uint32_t it = ipop();
+                    ST_COUNT(0);
+                    const uint32_t sq = it & 1u;
+                    uint32_t q = (it & 0x7FFFFFFFu) >> 1;
+                    if (it & 0x80000000u) {  // set_boundary(p0, side, cnum) :218, :289-306
+                        uint32_t *b = wl_bnd(V, i0, sq ^ 1u);
+                        const uint32_t curb = *b;
+                        if (curb == NONE32) {
+                            *b = cnum;
+                            if (kind0 == KIND_BOND) *wl_bnd(V, x0, sq ^ 1u) = cnum;
+                        } else if (curb != cnum) err |= DEV_ERR_INVARIANT;
+                    }
+                    uint4 e = V.wl[q];
+                    if (WL_KIND(e.x) == WL_SENT) {  // end of the world line: continue at the other end :224-241
+                        q = e.y;
+                        e = V.wl[q];
+                        ST_COUNT(3);
+                    }
+                    const uint32_t kq = WL_KIND(e.x);
+                    if (PF) {  // the walk marches along the line: request the next 128-byte line (8 entries) in its direction
+                        if (sq == SIDE_IN ? (q & 7u) == 0u : (q & 7u) == 7u)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(V.wl + (sq == SIDE_IN ? q + 8u : q - 8u)));
+                    }
+                    if (kq == KIND_SITE) {  // cluster edge :245-248
+                        ST_COUNT(1);
+                        const uint32_t mine = sq ? e.w : e.z, other = sq ? e.z : e.w;
+                        if (mine == NONE32) *wl_bnd(V, q, sq) = cnum;
+                        else if (mine != cnum) err |= DEV_ERR_INVARIANT;
+                        if (other == NONE32) {
+                            if (flen >= V.fcap) err |= DEV_ERR_STACK;
+                            else fpush((q << 1) | (sq ^ 1u));
+                        }
+                    } else {  // interior op :249-268
+                        const uint32_t a = e.z, bb = e.w;
+                        const bool ok = (a == NONE32 && bb == NONE32) || (a == cnum && bb == NONE32) || (a == NONE32 && bb == cnum);
+                        if (ok) {
+                            ST_COUNT(2);
+                            const uint32_t xq = e.y >> 1, kme = (e.x >> 2) & 1u;
+                            *reinterpret_cast<uint2 *>(wl_bnd(V, q, 0)) = make_uint2(cnum, cnum);
+                            if (ilen + 4 > V.icap) { err |= DEV_ERR_STACK; break; }
+                            if (kq == KIND_BOND) {
+                                *reinterpret_cast<uint2 *>(wl_bnd(V, xq, 0)) = make_uint2(cnum, cnum);
+                                if (PF) asm volatile("prefetch.global.L2 [%0];" ::"l"(V.wl + xq + (sq == SIDE_IN ? 4u : 0u) - 2u));
+                                const uint32_t i_k0 = kme ? xq : q, i_k1 = kme ? q : xq;
+                                if (!(kme == 0 && sq == SIDE_IN)) push_leg(i_k0, SIDE_IN, 0u);
+                                if (!(kme == 1 && sq == SIDE_IN)) push_leg(i_k1, SIDE_IN, 0u);
+                                if (!(kme == 0 && sq == SIDE_OUT)) push_leg(i_k0, SIDE_OUT, 0u);
+                                if (!(kme == 1 && sq == SIDE_OUT)) push_leg(i_k1, SIDE_OUT, 0u);
+                            } else {
+                                if (sq != SIDE_IN) push_leg(q, SIDE_IN, 0u);
+                                if (sq != SIDE_OUT) push_leg(q, SIDE_OUT, 0u);
+                            }
+                        }
+                    }
+                }
+                cnum++;
+            }
+        }
+        __syncwarp();
+        // :82-88 the smallest unmapped op (it never decreases), 32 slots per round
+        uint32_t unmapped = NONE32;
+        scan = __shfl_sync(0xFFFFFFFFu, scan, 0);
+        for (uint32_t base = scan & ~31u; base <= last_p && unmapped == NONE32; base += 32) {
+            const uint32_t p = base + (uint32_t)lane;
+            bool un = false;
+            if (p >= scan && p <= last_p && V.ops[p] != OP_EMPTY) {
+                const uint2 h = *reinterpret_cast<const uint2 *>(wl_bnd(V, V.ent[p], 0));
+                un = h.x == NONE32 && h.y == NONE32;
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, un);
+            if (m) unmapped = base + (uint32_t)__ffs(m) - 1u;
+            else scan = base + 32;
+        }
+        if (unmapped == NONE32) break;
+        scan = unmapped;
+        if (lane == 0) {
+            const uint32_t eu = V.ent[unmapped];
+            fpush((eu << 1) | SIDE_OUT);  // :89-91
+            fpush((eu << 1) | SIDE_IN);
+        }
+    }
+    if (lane == 0) ST_COUNT_FLUSH;
+    return __shfl_sync(0xFFFFFFFFu, cnum, 0);
+}
+
+// flip_each_cluster_rng (cluster.rs:36-172) on the world-line layout, whole warp; returns n_clusters
+__device__ uint32_t cluster_strict_wl(const SseDev &D, uint32_t r, const Rep &V, int lane, uint32_t *stk, long long &st_t, bool pf) {
+    const uint32_t n = D.n[r];
+    if (n == 0) return 0;
+    const uint32_t last_p = V.ends[1], cp = V.ends[2];
+    uint32_t ncl = 1;
+    int err = 0;
+    if (cp != NONE32) {
+        ncl = pf ? label_strict_wl<true>(D, V, err, lane, stk) : label_strict_wl<false>(D, V, err, lane, stk);
+    } else {  // :98-107 the whole thing is one cluster
+        for (uint32_t p = lane; p <= last_p; p += 32)
+            if (V.ops[p] != OP_EMPTY) *reinterpret_cast<uint2 *>(wl_bnd(V, V.ent[p], 0)) = make_uint2(0u, 0u);
+    }
+    if (err) atomicOr(D.status, err);
+    __syncwarp();
+    ST_MARK(1);
+    const uint32_t nwords = (ncl + 31) / 32;
+    const uint64_t key = D.key[r], c0 = D.cursor[r];
+    if (D.has_h) {
+        for (uint32_t j = lane; j < nwords; j += 32) V.frozen[j] = 0;
+        __syncwarp();
+        for (uint32_t p = lane; p <= last_p; p += 32) {
+            const uint32_t w = V.ops[p];
+            if (w != OP_EMPTY && op_bond(w) >= D.E + D.N) {
+                const uint32_t c = *wl_bnd(V, V.ent[p], 0);
+                atomicOr(&V.frozen[c >> 5], 1u << (c & 31));
+            }
+        }
+        __syncwarp();
+    }
+    for (uint32_t base = 0; base < ncl; base += 32) {  // one gen_bool per cluster in id order (:111-137)
+        const uint32_t k = base + lane;
+        bool f = false;
+        if (k < ncl) f = stream_word(key, c0 + k) < 0x8000000000000000ull;
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, f);
+        if (lane == 0) V.bits[base >> 5] = D.has_h ? (word & ~V.frozen[base >> 5]) : word;
+    }
+    __syncwarp();
+    ST_MARK(2);
+    for (uint32_t p = lane; p <= last_p; p += 32) {  // apply (:139-167)
+        const uint32_t w = V.ops[p];
+        if (w == OP_EMPTY) continue;
+        const uint4 e = V.wl[V.ent[p]];
+        const uint32_t ci = e.z, co = e.w;
+        const bool fi = (V.bits[ci >> 5] >> (ci & 31)) & 1u, fo = (V.bits[co >> 5] >> (co & 31)) & 1u;
+        if (!(fi || fo)) continue;
+        const uint32_t b = op_bond(w), kind = WL_KIND(e.x);
+        const uint32_t mask = kind == KIND_BOND ? 3u : 1u;
+        const uint32_t in = op_in(w) ^ (fi ? mask : 0u), out = op_out(w) ^ (fo ? mask : 0u);
+        if (fi && (((e.x >> 3) & 1u) | (e.y & 1u))) {  // a leg with no previous op on its world line: state at p = 0 changes
+            uint32_t vv[2];
+            bond_vars(D, b, (int)kind, vv[0], vv[1]);
+            const uint32_t firsts = ((e.x >> 3) & 1u) | ((e.y & 1u) << 1);
+            for (int k = 0; k < (kind == KIND_BOND ? 2 : 1); k++) {
+                if ((firsts >> k) & 1u) {
+                    const uint32_t v = vv[k], bit = 1u << (v & 31);
+                    if ((in >> k) & 1u) atomicOr(&V.state[v >> 5], bit);
+                    else atomicAnd(&V.state[v >> 5], ~bit);
+                }
+            }
+        }
+        V.ops[p] = make_op(b, in, out);
+    }
+    if (lane == 0) D.cursor[r] = c0 + ncl;
+    __syncwarp();
+    ST_MARK(3);
     return ncl;
 }
 
@@ -706,7 +1067,7 @@ __device__ void free_spins(const SseDev &D, uint32_t r, const Rep &V, int lane) 
 // latency-bound kernel needs (at 80 registers it ran in two waves: 467 ms instead of 290 ms per sweep on config #3)
 __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint64_t target, uint32_t phases,
                                                     uint64_t sample_freq, uint64_t sample_origin,
-                                                    uint8_t *samples, uint64_t samples_per_rep, int par_links) {
+                                                    uint8_t *samples, uint64_t samples_per_rep, int par_links, int layout) {
     extern __shared__ uint32_t smem_warp[];  // per warp: [STK_I + STK_F] stack tops of the STRICT walk, then [N] `last` table when par_links
     uint32_t *const my_smem = smem_warp + (size_t)(threadIdx.x >> 5) * (STK_I + STK_F + (par_links ? D.N : 0u));
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -729,7 +1090,11 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
             __syncwarp();
         }
         if (phases & 2u) {
-            if (mode == 0 && par_links) {
+            const bool wl = mode == 0 && par_links && (layout & 1);
+            long long st_t = clock64();
+            if (wl) {
+                links_wl(D, r, V, lane, my_smem + STK_I + STK_F);
+            } else if (mode == 0 && par_links) {
                 links_parallel(D, r, V, lane, my_smem + STK_I + STK_F);
             } else {
                 for (uint32_t v = lane; v < D.N; v += 32) V.vfirst[v] = NONE32, V.vlast[v] = NONE32;
@@ -737,9 +1102,12 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
                 if (lane == 0) links_serial(D, r, V, mode == 0);
                 __syncwarp();
             }
-            uint32_t ncl = mode == 0 ? cluster_strict(D, r, V, lane, my_smem) : cluster_fast_serial(D, r, V, lane, false);
+            ST_MARK(0);
+            uint32_t ncl = wl ? cluster_strict_wl(D, r, V, lane, my_smem, st_t, (layout & 2) != 0)
+                              : (mode == 0 ? cluster_strict(D, r, V, lane, my_smem, st_t) : cluster_fast_serial(D, r, V, lane, false));
             if (lane == 0) D.ncl[r] = ncl;
             free_spins(D, r, V, lane);
+            ST_MARK(4);
         }
         if (phases & 4u) {
             if (lane == 0) {  // qmc_ising.rs:786
@@ -897,16 +1265,19 @@ __global__ void k_sse_init_state(SseDev D) {
     if (lane == 0) D.cursor[r] = D.N;
 }
 
-void launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phases, uint64_t sample_freq,
-                       uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st) {
+// returns 1 when the STRICT cluster step ran on the world-line layout (layout = 1 and the per-variable table fits shared memory)
+int launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phases, uint64_t sample_freq,
+                      uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, int layout, cudaStream_t st) {
     const int threads = 128;
     const uint32_t blocks = (uint32_t)(((uint64_t)D.R * 32 + threads - 1) / threads);
     const size_t stk = (size_t)(threads / 32) * (STK_I + STK_F) * sizeof(uint32_t);
     size_t smem = stk + (size_t)(threads / 32) * D.N * sizeof(uint32_t);
     const int par = mode == 0 && smem <= 160 * 1024;
     if (!par) smem = stk;
+    if (D.cap >= (1ull << 27) || !D.ent) layout = 0;  // entry indices carry a side bit and a flag bit in the walk's stacks
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_sse_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_sse_serial<<<blocks, threads, smem, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep, par);
+    k_sse_serial<<<blocks, threads, smem, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep, par, layout);
+    return par && (layout & 1) && (phases & 2u);
 }
 void launch_sse_verify(const SseDev &D, uint32_t r, int *ok_dev, uint32_t *scratch_dev, cudaStream_t st) {
     k_sse_verify<<<1, 32, 0, st>>>(D, r, ok_dev, scratch_dev);
