@@ -236,8 +236,9 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
             for (uint64_t tgt = origin + 1; tgt <= h->target && ok; tgt++) {
                 int nl = launch_sse_fast(h->D, h->tune, tgt, 1u | 16u, freq, origin, nullptr, 0, h->stream);
                 if (nl < 0) { ok = false; break; }
-                h->strict_wl_last = launch_sse_serial(h->D, 0, tgt, 2u | 4u | 8u | 16u, freq, origin, samples_dev, spr, h->strict_layout, h->stream) != 0;
-                h->launches += (uint64_t)nl + 1;
+                const int ns = launch_sse_serial(h->D, 0, tgt, 2u | 4u | 8u | 16u, freq, origin, samples_dev, spr, h->strict_layout, h->stream);
+                h->strict_wl_last = ns != 0;
+                h->launches += (uint64_t)nl + (ns == 2 ? 2 : 1);
             }
             if (ok) {
                 CUDA_TRY(cudaGetLastError());
@@ -663,7 +664,7 @@ extern "C" int qmcb_get_mode(const QmcbHandle *h, int *mode) {
 extern "C" int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value) {
     if (!h || !name) return fail(QMCB_ERR_BAD_ARG, "null argument");
     if (!strcmp(name, "strict_layout")) {
-        if (value < 0 || value > 3 || value == 2) return fail(QMCB_ERR_BAD_ARG, "strict_layout is 0 (one record per slot), 1 (world-line arrays) or 3 (world-line arrays + next-line prefetch)");
+        if (value < 0 || value > 7 || (value && !(value & 1))) return fail(QMCB_ERR_BAD_ARG, "strict_layout is 0 (one record per slot) or 1 (world-line arrays) [| 2 next-line prefetch | 4 links in their own launch]");
         h->strict_layout = (int)value;
         return QMCB_OK;
     }

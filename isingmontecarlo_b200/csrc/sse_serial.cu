@@ -1067,9 +1067,12 @@ __device__ void free_spins(const SseDev &D, uint32_t r, const Rep &V, int lane) 
 // latency-bound kernel needs (at 80 registers it ran in two waves: 467 ms instead of 290 ms per sweep on config #3)
 __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint64_t target, uint32_t phases,
                                                     uint64_t sample_freq, uint64_t sample_origin,
-                                                    uint8_t *samples, uint64_t samples_per_rep, int par_links, int layout) {
-    extern __shared__ uint32_t smem_warp[];  // per warp: [STK_I + STK_F] stack tops of the STRICT walk, then [N] `last` table when par_links
-    uint32_t *const my_smem = smem_warp + (size_t)(threadIdx.x >> 5) * (STK_I + STK_F + (par_links ? D.N : 0u));
+                                                    uint8_t *samples, uint64_t samples_per_rep, int par_links, int layout, int split) {
+    // per warp: [STK_I + STK_F] stack tops of the STRICT walk, then [N] per-variable table of the link pass when par_links.
+    // split = 1: build the links and stop (this launch carries the table); split = 2: the links exist, do the rest with
+    // the stacks only -- 7 blocks x 16 KB of tables would otherwise take the shared memory that the walk wants as L1.
+    extern __shared__ uint32_t smem_warp[];
+    uint32_t *const my_smem = smem_warp + (size_t)(threadIdx.x >> 5) * (STK_I + STK_F + (par_links && split != 2 ? D.N : 0u));
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= D.R) return;
@@ -1092,7 +1095,8 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
         if (phases & 2u) {
             const bool wl = mode == 0 && par_links && (layout & 1);
             long long st_t = clock64();
-            if (wl) {
+            if (split == 2) {
+            } else if (wl) {
                 links_wl(D, r, V, lane, my_smem + STK_I + STK_F);
             } else if (mode == 0 && par_links) {
                 links_parallel(D, r, V, lane, my_smem + STK_I + STK_F);
@@ -1103,6 +1107,7 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
                 __syncwarp();
             }
             ST_MARK(0);
+            if (split == 1) break;
             uint32_t ncl = wl ? cluster_strict_wl(D, r, V, lane, my_smem, st_t, (layout & 2) != 0)
                               : (mode == 0 ? cluster_strict(D, r, V, lane, my_smem, st_t) : cluster_fast_serial(D, r, V, lane, false));
             if (lane == 0) D.ncl[r] = ncl;
@@ -1276,8 +1281,14 @@ int launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phase
     if (!par) smem = stk;
     if (D.cap >= (1ull << 27) || !D.ent) layout = 0;  // entry indices carry a side bit and a flag bit in the walk's stacks
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_sse_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_sse_serial<<<blocks, threads, smem, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep, par, layout);
-    return par && (layout & 1) && (phases & 2u);
+    const bool wl = par && (layout & 1) && (phases & 2u);
+    if (wl && (layout & 4) && (phases & 16u)) {  // one sweep per launch: links in their own launch, the walk with the stacks only
+        k_sse_serial<<<blocks, threads, smem, st>>>(D, mode, target, 2u | 16u, sample_freq, sample_origin, samples, samples_per_rep, par, layout, 1);
+        k_sse_serial<<<blocks, threads, stk, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep, par, layout, 2);
+        return 2;
+    }
+    k_sse_serial<<<blocks, threads, smem, st>>>(D, mode, target, phases, sample_freq, sample_origin, samples, samples_per_rep, par, layout, 0);
+    return wl;
 }
 void launch_sse_verify(const SseDev &D, uint32_t r, int *ok_dev, uint32_t *scratch_dev, cudaStream_t st) {
     k_sse_verify<<<1, 32, 0, st>>>(D, r, ok_dev, scratch_dev);

@@ -20,7 +20,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("layout", [1, 0])
+@pytest.mark.parametrize("layout", [1, 0, 7])  # 7: world lines + next-line prefetch + links in their own launch
 @pytest.mark.parametrize("name,edges,gamma,h,cutoff,beta,sweeps", CASES)
 def test_numbering_matches_reference_order(name, edges, gamma, h, cutoff, beta, sweeps, layout):
     from isingmontecarlo_b200.sse import QmcIsingGraph

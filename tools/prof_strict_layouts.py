@@ -21,7 +21,7 @@ DBG = bool(os.environ.get("PROF_DBG"))
 if DBG:
     g.set_option("debug_counters", 1)
 last = g.debug_counters().astype(np.float64) if DBG else None
-plan = [(1, 0), (3, 0), (0, 0), (1, 128), (3, 128), (0, 128), (1, 32), (1, 64)]
+plan = [(int(x), 0) for x in os.environ.get("PROF_LAYOUTS", "1,5,0,1,5").split(",")]
 for layout, gran in plan:
     g.set_option("strict_layout", layout)
     if gran:
