@@ -86,7 +86,7 @@ template <int G>
 struct SqTables {
     uint32_t rk[20];
     uint32_t tk[G > 0 ? G : 1][32];               // tk[g][k]: bit (31 - k) of the threshold of group g (0/1: a multiplier, FMA pipe)
-    __align__(16) uint32_t cmsk[G + 1][12];       // [set][own * 5 + cnt] class membership as masks; set G = always-flip
+    __align__(16) uint32_t cmsk[G + 1][12];       // [set][own * 5 + cnt] class membership, 0/1 (a multiplier); set G = always-flip
 };
 template <int G>
 __device__ __forceinline__ void sq_load_tables(const ClsDev &D, uint32_t r, SqTables<G> &S) {
@@ -102,21 +102,48 @@ __device__ __forceinline__ void sq_load_tables(const ClsDev &D, uint32_t r, SqTa
     for (uint32_t i = threadIdx.x; i < (uint32_t)(G + 1) * 10; i += blockDim.x) {
         const uint32_t set = i / 10, j = i % 10;  // j = own * 5 + cnt  ->  class bit own * 8 + cnt
         const uint32_t members = set < (uint32_t)G ? D.sq_gmem[(size_t)r * SQ_MAXG + set] : D.sq_always[r];
-        S.cmsk[set][j] = ((members >> ((j / 5) * 8 + (j % 5))) & 1u) ? 0xFFFFFFFFu : 0u;
+        S.cmsk[set][j] = (members >> ((j / 5) * 8 + (j % 5))) & 1u;
     }
 }
-// the update of one word (32 sites of one colour) at sweep `sweep`.  CG: the planes are read through L2 (another SM
-// wrote the neighbouring rows earlier in the same launch).
+// classes of the 32 sites of a word from its four neighbour words: always-flip sites (returned), sites of every
+// probabilistic group sel[g], eq = their union
+template <int G>
+__device__ __forceinline__ uint32_t sq_classes(const SqTables<G> &S, uint32_t own, uint32_t same, uint32_t side, uint32_t up, uint32_t dn,
+                                               uint32_t (&sel)[G > 0 ? G : 1], uint32_t &eq) {
+    // bit-sliced count of anti-aligned neighbours: cnt = lo + 2 mid + 4 hi, then one-hot masks
+    const uint32_t a = own ^ same, b = own ^ side, c = own ^ up, d = own ^ dn;
+    const uint32_t s1 = a ^ b ^ c, c1 = (a & b) | (c & (a ^ b));
+    const uint32_t lo = s1 ^ d, c2 = s1 & d;
+    const uint32_t mid = c1 ^ c2, hi = c1 & c2;
+    uint32_t cm[5];
+    cm[0] = ~(lo | mid | hi), cm[1] = lo & ~mid, cm[2] = mid & ~lo, cm[3] = lo & mid, cm[4] = hi;
+    // sites of a set of classes: the membership of class (own, cnt) is a block-uniform 0/1 in shared memory; the one-hot
+    // masks are disjoint, so "or of the selected masks" is a sum of products (integer multiply-adds: the FMA pipe is idle,
+    // the ALU pipe that runs the logic ops is the binding unit of this kernel)
+    auto class_sites = [&](const uint32_t *mk) -> uint32_t {
+        uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+        for (int cc = 0; cc < 5; cc++) m0 = cm[cc] * mk[cc] + m0, m1 = cm[cc] * mk[5 + cc] + m1;
+        return (~own & m0) | (own & m1);
+    };
+    eq = 0;
+#pragma unroll
+    for (int g = 0; g < G; g++) sel[g] = class_sites(S.cmsk[g]), eq |= sel[g];
+    return class_sites(S.cmsk[G]);  // delta_e <= 0 (threshold 2^32): always
+}
+// the update of one word (32 sites of one colour) at sweep `sweep`, in pieces.  CG: the planes are read through L2
+// (another SM wrote the neighbouring rows earlier in the same launch).
+// sq_front: own word, always-flip sites (returned), sites of every probabilistic group sel[g], eq = their union
 template <int G, bool CG>
-__device__ __forceinline__ void sq_update_word(const ClsDev &D, const SqTables<G> &S, uint32_t *mine, const uint32_t *other, uint32_t t,
-                                               uint32_t colour, uint64_t sweep) {
+__device__ __forceinline__ uint32_t sq_front(const ClsDev &D, const SqTables<G> &S, const uint32_t *mine, const uint32_t *other, uint32_t t,
+                                             uint32_t colour, uint32_t &own, uint32_t (&sel)[G > 0 ? G : 1], uint32_t &eq) {
     auto ld = [](const uint32_t *p) -> uint32_t { return CG ? __ldcg(p) : *p; };
     const uint32_t WPR = D.L >> 6;
     uint32_t y, w;
     if (D.sq_wpr_shift >= 0) y = t >> D.sq_wpr_shift, w = t & (WPR - 1u);
     else y = t / WPR, w = t - y * WPR;
     const uint32_t yu = y == 0 ? D.L - 1 : y - 1, yd = y + 1 == D.L ? 0 : y + 1;
-    const uint32_t own = ld(mine + t);
+    own = ld(mine + t);
     const uint32_t same = ld(other + t);
     const uint32_t up = ld(other + yu * WPR + w), dn = ld(other + yd * WPR + w);
     uint32_t side;
@@ -127,61 +154,146 @@ __device__ __forceinline__ void sq_update_word(const ClsDev &D, const SqTables<G
         const uint32_t prv = ld(other + (w == 0 ? t + WPR - 1 : t - 1));
         side = (same << 1) | (prv >> 31);
     }
-    // bit-sliced count of anti-aligned neighbours: cnt = lo + 2 mid + 4 hi, then one-hot masks
-    const uint32_t a = own ^ same, b = own ^ side, c = own ^ up, d = own ^ dn;
-    const uint32_t s1 = a ^ b ^ c, c1 = (a & b) | (c & (a ^ b));
-    const uint32_t lo = s1 ^ d, c2 = s1 & d;
-    const uint32_t mid = c1 ^ c2, hi = c1 & c2;
-    uint32_t cm[5];
-    cm[0] = ~(lo | mid | hi), cm[1] = lo & ~mid, cm[2] = mid & ~lo, cm[3] = lo & mid, cm[4] = hi;
-    // sites of a set of classes: the membership of class (own, cnt) is a block-uniform mask in shared memory
-    auto class_sites = [&](const uint32_t *mk) -> uint32_t {
-        uint32_t m0 = 0, m1 = 0;
+    return sq_classes<G>(S, own, same, side, up, dn, sel, eq);
+}
+// four planes K0..K0+3 of the bit-serial compare: per plane the threshold bit of every site is muxed from its group
+// (disjoint sel: mux by multiply-add, FMA pipe), then lt |= eq & ~p & t; eq &= ~(p ^ t)
+template <int G, int K0>
+__device__ __forceinline__ void sq_ripple4(const SqTables<G> &S, const uint32_t (&sel)[G > 0 ? G : 1], const uint32_t *pl, uint32_t &lt, uint32_t &eq) {
 #pragma unroll
-        for (int cc = 0; cc < 5; cc++) m0 |= cm[cc] & mk[cc], m1 |= cm[cc] & mk[5 + cc];
-        return (~own & m0) | (own & m1);
-    };
-    uint32_t flip = class_sites(S.cmsk[G]);  // delta_e <= 0 (threshold 2^32): always
-    if (G > 0) {
-        uint32_t sel[G > 0 ? G : 1], eq = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t tk = 0;
 #pragma unroll
-        for (int g = 0; g < G; g++) sel[g] = class_sites(S.cmsk[g]), eq |= sel[g];
-        uint32_t lt = 0;
-        uint32_t pl[4];
-        // planes 0..11 always; 12..15 and 16..31 only while some site still ties with its threshold
-        // (p = 2^-12 resp. 2^-16 per site), so most words need three Philox calls
-#define RIPPLE_PLANE(k)                                              \
-    {                                                                \
-        uint32_t tk = 0;                                             \
-        _Pragma("unroll") for (int g = 0; g < G; g++) tk = sel[g] * S.tk[g][k] + tk; /* disjoint sel: mux by multiply-add */ \
-        const uint32_t p = pl[(k) & 3];                              \
-        lt |= eq & ~p & tk;                                          \
-        eq &= ~(p ^ tk);                                             \
+        for (int g = 0; g < G; g++) tk = sel[g] * S.tk[g][K0 + i] + tk;
+        const uint32_t p = pl[i];
+        lt |= eq & ~p & tk;
+        eq &= ~(p ^ tk);
     }
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            philox_rk(4 * t + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
-#pragma unroll
-            for (int i = 0; i < 4; i++) RIPPLE_PLANE(4 * q + i)
-        }
-        if (eq) {
-            philox_rk(4 * t + 3, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
-#pragma unroll
-            for (int i = 0; i < 4; i++) RIPPLE_PLANE(12 + i)
-            if (eq) {
+}
+// planes 12..15 and 16..31: only while some site still ties with its threshold (p = 2^-12 resp. 2^-16 per site)
+template <int G>
+__device__ __forceinline__ void sq_low_planes(const SqTables<G> &S, const uint32_t (&sel)[G > 0 ? G : 1], uint32_t t, uint32_t colour, uint64_t sweep,
+                                              uint32_t &lt, uint32_t &eq) {
+    uint32_t pl[4];
+    philox_rk(4 * t + 3, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
+    sq_ripple4<G, 12>(S, sel, pl, lt, eq);
+    if (!eq) return;
 #pragma unroll 1
-                for (int q = 0; q < 4; q++) {
-                    philox_rk(4 * t + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB2 | colour, S.rk, pl);
+    for (int q = 0; q < 4; q++) {
+        philox_rk(4 * t + q, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB2 | colour, S.rk, pl);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) RIPPLE_PLANE(16 + 4 * q + i)
-                }
-            }
+        for (int i = 0; i < 4; i++) {
+            const int k = 16 + 4 * q + i;
+            uint32_t tk = 0;
+#pragma unroll
+            for (int g = 0; g < G; g++) tk = sel[g] * S.tk[g][k] + tk;
+            const uint32_t p = pl[i];
+            lt |= eq & ~p & tk;
+            eq &= ~(p ^ tk);
         }
-#undef RIPPLE_PLANE
+    }
+}
+// One thread per 32 sites; planes 0..11 always, so most words need three Philox calls.
+template <int G, bool CG>
+__device__ __forceinline__ void sq_update_word(const ClsDev &D, const SqTables<G> &S, uint32_t *mine, const uint32_t *other, uint32_t t,
+                                               uint32_t colour, uint64_t sweep) {
+    uint32_t own, eq, sel[G > 0 ? G : 1];
+    uint32_t flip = sq_front<G, CG>(D, S, mine, other, t, colour, own, sel, eq);
+    if (G > 0) {
+        uint32_t lt = 0, pl[4];
+        philox_rk(4 * t + 0, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
+        sq_ripple4<G, 0>(S, sel, pl, lt, eq);
+        philox_rk(4 * t + 1, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
+        sq_ripple4<G, 4>(S, sel, pl, lt, eq);
+        philox_rk(4 * t + 2, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
+        sq_ripple4<G, 8>(S, sel, pl, lt, eq);
+        if (eq) sq_low_planes<G>(S, sel, t, colour, sweep, lt, eq);
         flip |= lt;
     }
     if (CG) __stcg(mine + t, own ^ flip);
     else mine[t] = own ^ flip;
+}
+// The same update with the third Philox call DEFERRED: after planes 0..7 a word still has a tie with probability
+// ~ 32 * 2^-8, so almost every warp would execute the third call for a handful of its lanes.  Words with a tie are
+// parked in a per-warp queue in shared memory instead ({t, eq, lt}: everything else is recomputed -- the other colour
+// does not change during the pass and the word itself is only written when it is resolved) and resolved 32 at a time
+// with all lanes busy.  Same planes, same result: only WHEN a plane is generated changes.
+#define SQ_QCAP 64
+struct SqQueue {
+    uint32_t t[SQ_QCAP], eq[SQ_QCAP], lt[SQ_QCAP];
+};
+template <int G, bool CG>
+__device__ __forceinline__ void sq_resolve(const ClsDev &D, const SqTables<G> &S, uint32_t *mine, const uint32_t *other, uint32_t t, uint32_t eq,
+                                           uint32_t lt, uint32_t colour, uint64_t sweep) {
+    uint32_t own, eq0, sel[G > 0 ? G : 1], pl[4];
+    const uint32_t flip = sq_front<G, CG>(D, S, mine, other, t, colour, own, sel, eq0);
+    philox_rk(4 * t + 2, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
+    sq_ripple4<G, 8>(S, sel, pl, lt, eq);
+    if (eq) sq_low_planes<G>(S, sel, t, colour, sweep, lt, eq);
+    if (CG) __stcg(mine + t, own ^ (flip | lt));
+    else mine[t] = own ^ (flip | lt);
+}
+// one colour pass over the words [t0, t1) of a block, a warp taking 32 consecutive words per round
+template <int G, bool CG>
+__device__ __forceinline__ void sq_pass_deferred(const ClsDev &D, const SqTables<G> &S, SqQueue &Q, uint32_t *mine, const uint32_t *other, uint32_t t0,
+                                                 uint32_t t1, uint32_t colour, uint64_t sweep) {
+    auto ld = [](const uint32_t *p) -> uint32_t { return CG ? __ldcg(p) : *p; };
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    const uint32_t WPR = D.L >> 6, nwords = D.L * WPR;
+    // when a round of the block covers an even number of whole rows, a thread stays in its column and on its row parity:
+    // the five loads of a word sit at fixed distances from it (except in the first and the last row of the lattice)
+    const bool fixed = D.sq_wpr_shift >= 0 && (blockDim.x >> D.sq_wpr_shift) >= 2 && ((blockDim.x >> D.sq_wpr_shift) << D.sq_wpr_shift) == blockDim.x &&
+                       ((blockDim.x >> D.sq_wpr_shift) & 1u) == 0;
+    int dside = 0;
+    bool odd = false;  // my x is odd: the second horizontal neighbour has compressed index xc + 1, else xc - 1
+    if (fixed) {
+        const uint32_t tt = t0 + threadIdx.x, y = tt >> D.sq_wpr_shift, w = tt & (WPR - 1u);
+        odd = (y + colour) & 1u;
+        dside = odd ? (w + 1 == WPR ? 1 - (int)WPR : 1) : (w == 0 ? (int)WPR - 1 : -1);
+    }
+    uint32_t qn = 0;
+    for (uint32_t base = t0 + (threadIdx.x & ~31u); base < t1; base += blockDim.x) {
+        const uint32_t t = base + lane;
+        uint32_t eq = 0, lt = 0;
+        if (t < t1) {
+            uint32_t own, flip, sel[G > 0 ? G : 1], pl[8];
+            if (fixed) {
+                const uint32_t *po = other + t;
+                own = ld(mine + t);
+                const uint32_t same = ld(po), sidew = ld(po + dside);
+                const uint32_t up = ld(t < WPR ? po + (nwords - WPR) : po - WPR), dn = ld(t + WPR >= nwords ? po - (nwords - WPR) : po + WPR);
+                const uint32_t side = odd ? (same >> 1) | (sidew << 31) : (same << 1) | (sidew >> 31);
+                flip = sq_classes<G>(S, own, same, side, up, dn, sel, eq);
+            } else {
+                flip = sq_front<G, CG>(D, S, mine, other, t, colour, own, sel, eq);
+            }
+            philox_rk(4 * t + 0, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl);
+            philox_rk(4 * t + 1, (uint32_t)sweep, (uint32_t)(sweep >> 32), QMCB_TAG_CB | colour, S.rk, pl + 4);
+            sq_ripple4<G, 0>(S, sel, pl, lt, eq);
+            sq_ripple4<G, 4>(S, sel, pl + 4, lt, eq);
+            if (!eq) {
+                if (CG) __stcg(mine + t, own ^ (flip | lt));
+                else mine[t] = own ^ (flip | lt);
+            }
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq != 0);
+        if (m) {
+            if (eq) {
+                const uint32_t pos = qn + (uint32_t)__popc(m & lt_mask);
+                Q.t[pos] = t, Q.eq[pos] = eq, Q.lt[pos] = lt;
+            }
+            qn += (uint32_t)__popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                const uint32_t qt = Q.t[qn + lane], qe = Q.eq[qn + lane], ql = Q.lt[qn + lane];
+                __syncwarp();
+                sq_resolve<G, CG>(D, S, mine, other, qt, qe, ql, colour, sweep);
+            }
+        }
+    }
+    if (lane < qn) sq_resolve<G, CG>(D, S, mine, other, Q.t[lane], Q.eq[lane], Q.lt[lane], colour, sweep);
+    __syncwarp();
 }
 
 // one colour pass of one sweep per launch
@@ -207,6 +319,7 @@ template <int G>
 __global__ void __launch_bounds__(128, 8) k_cls_square_sweeps(ClsDev D, uint32_t r0, uint64_t sweep0, uint32_t nsweeps, unsigned int *bar,
                                                                unsigned int bar_base) {
     __shared__ SqTables<G> S;
+    __shared__ SqQueue Q[4];  // one per warp (128 threads)
     const uint32_t r = r0 + blockIdx.y;
     sq_load_tables<G>(D, r, S);
     __syncthreads();
@@ -220,7 +333,9 @@ __global__ void __launch_bounds__(128, 8) k_cls_square_sweeps(ClsDev D, uint32_t
         for (uint32_t colour = 0; colour < 2; colour++) {
             uint32_t *mine = plane0 + colour * words_per_plane;
             const uint32_t *other = plane0 + (colour ^ 1u) * words_per_plane;
-            for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) sq_update_word<G, true>(D, S, mine, other, t, colour, sweep0 + s);
+            if (G > 0) sq_pass_deferred<G, true>(D, S, Q[threadIdx.x >> 5], mine, other, t0, t1, colour, sweep0 + s);
+            else
+                for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) sq_update_word<G, true>(D, S, mine, other, t, colour, sweep0 + s);
             // per-replica barrier: my rows are visible before the neighbours' next pass reads them
             __syncthreads();
             arrivals += SQ_BPR;

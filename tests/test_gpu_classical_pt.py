@@ -282,3 +282,25 @@ def test_square_fused_launches_equal_per_pass_launches():
             ref.checkerboard_sweeps(float(betas[2]), col, 1 + sweeps)
             assert np.array_equal(a.state_ref()[2], ref.state())
         a.close(), b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,R,sweeps", [(128, 3, 6), (192, 2, 5), (320, 2, 3), (1024, 1, 2)])
+def test_square_row_widths_against_oracle(L, R, sweeps):
+    """The fused kernel addresses a word's neighbours at fixed distances when a round of a block covers an even number of
+    whole rows (L/64 a power of two up to 64) and generically otherwise (L = 192, 320): both against the oracle, and the
+    deferred third Philox call (words with a tie after eight bit planes are parked and resolved 32 at a time)."""
+    from isingmontecarlo_b200.classical import GraphState
+
+    edges = lattices.square_periodic(L, -1.0)
+    keys = 0xB2200000 + np.arange(R, dtype=np.uint64)
+    betas = np.linspace(0.35, 0.5, R)
+    g = GraphState(edges, np.full(L * L, 0.1 if L == 192 else 0.0), keys, betas)
+    assert g.is_bitpacked_square()
+    g.sweeps(1), g.sweeps(sweeps - 1)
+    col, _ = g.colours()
+    r = R - 1
+    ref = po.ClassicalOracle(edges, np.full(L * L, 0.1 if L == 192 else 0.0), key=int(keys[r]))
+    ref.checkerboard_sweeps(float(betas[r]), col, sweeps)
+    assert np.array_equal(g.state_ref()[r], ref.state())
+    g.close()
