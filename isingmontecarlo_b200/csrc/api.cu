@@ -96,7 +96,7 @@ struct QmcbHandle {
     Pool pool;
     int mode = QMCB_MODE_STRICT;
     int impl = 0;  // 0 auto (warp-parallel FAST kernels where supported), 1 serial kernels only
-    int strict_layout = 1;  // STRICT cluster step: 1 world-line arrays (default), 0 one record per slot (qmcb_set_option "strict_layout")
+    int strict_layout = 9;  // STRICT cluster step: 1 world-line arrays | 8 other leg of a bond op requested in L1 (default), 0 one record per slot (qmcb_set_option "strict_layout")
     bool strict_wl_last = false;  // which layout the last STRICT cluster step left in the workspace (qmcb_get_boundaries)
     double offset = 0.0;
     uint64_t target = 0;  // sweeps requested so far
@@ -664,7 +664,7 @@ extern "C" int qmcb_get_mode(const QmcbHandle *h, int *mode) {
 extern "C" int qmcb_set_option(QmcbHandle *h, const char *name, int64_t value) {
     if (!h || !name) return fail(QMCB_ERR_BAD_ARG, "null argument");
     if (!strcmp(name, "strict_layout")) {
-        if (value < 0 || value > 7 || (value && !(value & 1))) return fail(QMCB_ERR_BAD_ARG, "strict_layout is 0 (one record per slot) or 1 (world-line arrays) [| 2 next-line prefetch | 4 links in their own launch]");
+        if (value < 0 || value > 15 || (value && !(value & 1))) return fail(QMCB_ERR_BAD_ARG, "strict_layout is 0 (one record per slot) or 1 (world-line arrays) [| 2 next interior entry requested in L1 | 4 links in their own launch | 8 other leg of a bond op requested in L1]");
         h->strict_layout = (int)value;
         return QMCB_OK;
     }

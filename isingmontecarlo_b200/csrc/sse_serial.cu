@@ -393,6 +393,7 @@ __device__ __forceinline__ uint32_t rec_link(const uint4 &lo, const uint4 &hi, u
 // entries); what does not fit spills to the global-memory stacks, which keep the exact LIFO order.
 #define STK_I 192
 #define STK_F 128
+#define STK_WORDS 384  // per warp: max(STK_I, STK_IW) + STK_F
 __device__ uint32_t label_strict(const SseDev &D, const Rep &V, int &err, int lane, uint32_t *stk) {
     const uint32_t last_p = V.ends[1], cp = V.ends[2];
     const uint32_t E = D.E, EN = D.E + D.N;
@@ -719,37 +720,54 @@ __device__ __forceinline__ uint32_t *wl_bnd(const Rep &V, uint32_t idx, uint32_t
     return reinterpret_cast<uint32_t *>(V.wl + idx) + 2 + side;
 }
 
-template <bool PF>
+// Both LIFO stacks keep their TOP in shared memory: a ring of STK_F / STK_IW entries holds the logical positions
+// [base, len); when it is full its lower half is written to the global stack (in order), when it runs empty the half below
+// is read back.  (The first version kept the BOTTOM 192 interior entries in shared memory: clusters of config #3 stack
+// thousands of legs, and 43 % of the pops came from global memory.)
+// OPT bit 0: every interior pop requests (prefetch.global.L1) the entry the leg BELOW the popped one lands on -- the next
+// pop unless this one pushes; bit 1: a bond op requests the line of its other leg in L1 as soon as it is recognised.
+// Tried and dropped: next-line L2 prefetch along the walk, and a prefetch of the frontier entries two or four places below
+// the top at every frontier pop (227.5 against 229 ms per sweep: frontier entries are popped while their line is still in L1).
+#define STK_IW 256
+template <int OPT>
 __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int lane, uint32_t *stk) {
     const uint32_t last_p = V.ends[1], cp = V.ends[2];
-    uint32_t *const ist = stk, *const fst = stk + STK_I;
-    uint64_t flen = 0, ilen = 0, fbase = 0;
+    uint32_t *const ist = stk, *const fst = stk + STK_IW;
+    uint32_t flen = 0, fbase = 0, ilen = 0, ibase = 0;
+    const uint32_t fcap = (uint32_t)V.fcap, icap = (uint32_t)V.icap;
     auto fpush = [&](uint32_t x) {
         if (flen - fbase == STK_F) {
-            for (uint32_t j = 0; j < STK_F / 2; j++) V.frontier[fbase + j] = fst[j];
-            for (uint32_t j = 0; j < STK_F / 2; j++) fst[j] = fst[j + STK_F / 2];
+            for (uint32_t j = 0; j < STK_F / 2; j++) V.frontier[fbase + j] = fst[(fbase + j) & (STK_F - 1)];
             fbase += STK_F / 2;
         }
-        fst[flen - fbase] = x;
+        fst[flen & (STK_F - 1)] = x;
         flen++;
     };
     auto fpop = [&]() -> uint32_t {
         if (flen == fbase) {
-            const uint64_t take = fbase < STK_F / 2 ? fbase : STK_F / 2;
-            for (uint64_t j = 0; j < take; j++) fst[j] = V.frontier[fbase - take + j];
+            const uint32_t take = fbase < STK_F / 2 ? fbase : STK_F / 2;
+            for (uint32_t j = 0; j < take; j++) fst[(fbase - take + j) & (STK_F - 1)] = V.frontier[fbase - take + j];
             fbase -= take;
         }
         flen--;
-        return fst[flen - fbase];
+        return fst[flen & (STK_F - 1)];
     };
     auto ipush = [&](uint32_t x) {
-        if (ilen < STK_I) ist[ilen] = x;
-        else V.interior[ilen] = x;
+        if (ilen - ibase == STK_IW) {
+            for (uint32_t j = 0; j < STK_IW / 2; j++) V.interior[ibase + j] = ist[(ibase + j) & (STK_IW - 1)];
+            ibase += STK_IW / 2;
+        }
+        ist[ilen & (STK_IW - 1)] = x;
         ilen++;
     };
     auto ipop = [&]() -> uint32_t {
+        if (ilen == ibase) {
+            const uint32_t take = ibase < STK_IW / 2 ? ibase : STK_IW / 2;
+            for (uint32_t j = 0; j < take; j++) ist[(ibase - take + j) & (STK_IW - 1)] = V.interior[ibase - take + j];
+            ibase -= take;
+        }
         ilen--;
-        return ilen < STK_I ? ist[ilen] : V.interior[ilen];
+        return ist[ilen & (STK_IW - 1)];
     };
     // an interior entry is where the leg LANDS: (neighbouring entry << 1 | side it arrives at) [| bit 31: leg of the start op]
     auto push_leg = [&](uint32_t idx, uint32_t side, uint32_t flag) { ipush((((side == SIDE_IN ? idx - 1u : idx + 1u) << 1) | (side ^ 1u)) | flag); };
@@ -769,7 +787,7 @@ __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int
                 const uint4 E0 = V.wl[i0];
                 if (E0.z != NONE32 && E0.w != NONE32) continue;
                 const uint32_t kind0 = WL_KIND(E0.x), x0 = E0.y >> 1;
-                ilen = 0;
+                ilen = 0, ibase = 0;
                 if (kind0 != KIND_SITE) {  // :205-211 (i0 is the entry of leg 0: the scan below hands out ent[p])
                     push_leg(i0, SIDE_IN, 0x80000000u);
                     if (kind0 == KIND_BOND) push_leg(x0, SIDE_IN, 0x80000000u);
@@ -783,6 +801,8 @@ __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int
                     ST_COUNT(0);
                     const uint32_t sq = it & 1u;
                     uint32_t q = (it & 0x7FFFFFFFu) >> 1;
+                    if ((OPT & 1) && ilen != ibase)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(V.wl + ((ist[(ilen - 1u) & (STK_IW - 1)] & 0x7FFFFFFFu) >> 1)));
                     if (it & 0x80000000u) {  // set_boundary(p0, side, cnum) :218, :289-306
                         uint32_t *b = wl_bnd(V, i0, sq ^ 1u);
                         const uint32_t curb = *b;
@@ -798,17 +818,14 @@ __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int
                         ST_COUNT(3);
                     }
                     const uint32_t kq = WL_KIND(e.x);
-                    if (PF) {  // the walk marches along the line: request the next 128-byte line (8 entries) in its direction
-                        if (sq == SIDE_IN ? (q & 7u) == 0u : (q & 7u) == 7u)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(V.wl + (sq == SIDE_IN ? q + 8u : q - 8u)));
-                    }
+                    if ((OPT & 2) && kq == KIND_BOND) asm volatile("prefetch.global.L1 [%0];" ::"l"(V.wl + (e.y >> 1)));
                     if (kq == KIND_SITE) {  // cluster edge :245-248
                         ST_COUNT(1);
                         const uint32_t mine = sq ? e.w : e.z, other = sq ? e.z : e.w;
                         if (mine == NONE32) *wl_bnd(V, q, sq) = cnum;
                         else if (mine != cnum) err |= DEV_ERR_INVARIANT;
                         if (other == NONE32) {
-                            if (flen >= V.fcap) err |= DEV_ERR_STACK;
+                            if (flen >= fcap) err |= DEV_ERR_STACK;
                             else fpush((q << 1) | (sq ^ 1u));
                         }
                     } else {  // interior op :249-268
@@ -818,10 +835,9 @@ __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int
                             ST_COUNT(2);
                             const uint32_t xq = e.y >> 1, kme = (e.x >> 2) & 1u;
                             *reinterpret_cast<uint2 *>(wl_bnd(V, q, 0)) = make_uint2(cnum, cnum);
-                            if (ilen + 4 > V.icap) { err |= DEV_ERR_STACK; break; }
+                            if (ilen + 4 > icap) { err |= DEV_ERR_STACK; break; }
                             if (kq == KIND_BOND) {
                                 *reinterpret_cast<uint2 *>(wl_bnd(V, xq, 0)) = make_uint2(cnum, cnum);
-                                if (PF) asm volatile("prefetch.global.L2 [%0];" ::"l"(V.wl + xq + (sq == SIDE_IN ? 4u : 0u) - 2u));
                                 const uint32_t i_k0 = kme ? xq : q, i_k1 = kme ? q : xq;
                                 if (!(kme == 0 && sq == SIDE_IN)) push_leg(i_k0, SIDE_IN, 0u);
                                 if (!(kme == 1 && sq == SIDE_IN)) push_leg(i_k1, SIDE_IN, 0u);
@@ -865,14 +881,19 @@ __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int
 }
 
 // flip_each_cluster_rng (cluster.rs:36-172) on the world-line layout, whole warp; returns n_clusters
-__device__ uint32_t cluster_strict_wl(const SseDev &D, uint32_t r, const Rep &V, int lane, uint32_t *stk, long long &st_t, bool pf) {
+__device__ uint32_t cluster_strict_wl(const SseDev &D, uint32_t r, const Rep &V, int lane, uint32_t *stk, long long &st_t, int pf) {
     const uint32_t n = D.n[r];
     if (n == 0) return 0;
     const uint32_t last_p = V.ends[1], cp = V.ends[2];
     uint32_t ncl = 1;
     int err = 0;
     if (cp != NONE32) {
-        ncl = pf ? label_strict_wl<true>(D, V, err, lane, stk) : label_strict_wl<false>(D, V, err, lane, stk);
+        switch (pf) {  // strict_layout bits 2 and 8
+            case 1: ncl = label_strict_wl<1>(D, V, err, lane, stk); break;
+            case 2: ncl = label_strict_wl<2>(D, V, err, lane, stk); break;
+            case 3: ncl = label_strict_wl<3>(D, V, err, lane, stk); break;
+            default: ncl = label_strict_wl<0>(D, V, err, lane, stk); break;
+        }
     } else {  // :98-107 the whole thing is one cluster
         for (uint32_t p = lane; p <= last_p; p += 32)
             if (V.ops[p] != OP_EMPTY) *reinterpret_cast<uint2 *>(wl_bnd(V, V.ent[p], 0)) = make_uint2(0u, 0u);
@@ -1072,7 +1093,7 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
     // split = 1: build the links and stop (this launch carries the table); split = 2: the links exist, do the rest with
     // the stacks only -- 7 blocks x 16 KB of tables would otherwise take the shared memory that the walk wants as L1.
     extern __shared__ uint32_t smem_warp[];
-    uint32_t *const my_smem = smem_warp + (size_t)(threadIdx.x >> 5) * (STK_I + STK_F + (par_links && split != 2 ? D.N : 0u));
+    uint32_t *const my_smem = smem_warp + (size_t)(threadIdx.x >> 5) * (STK_WORDS + (par_links && split != 2 ? D.N : 0u));
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= D.R) return;
@@ -1097,9 +1118,9 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
             long long st_t = clock64();
             if (split == 2) {
             } else if (wl) {
-                links_wl(D, r, V, lane, my_smem + STK_I + STK_F);
+                links_wl(D, r, V, lane, my_smem + STK_WORDS);
             } else if (mode == 0 && par_links) {
-                links_parallel(D, r, V, lane, my_smem + STK_I + STK_F);
+                links_parallel(D, r, V, lane, my_smem + STK_WORDS);
             } else {
                 for (uint32_t v = lane; v < D.N; v += 32) V.vfirst[v] = NONE32, V.vlast[v] = NONE32;
                 __syncwarp();
@@ -1108,7 +1129,7 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
             }
             ST_MARK(0);
             if (split == 1) break;
-            uint32_t ncl = wl ? cluster_strict_wl(D, r, V, lane, my_smem, st_t, (layout & 2) != 0)
+            uint32_t ncl = wl ? cluster_strict_wl(D, r, V, lane, my_smem, st_t, ((layout >> 1) & 1) | ((layout >> 2) & 2))
                               : (mode == 0 ? cluster_strict(D, r, V, lane, my_smem, st_t) : cluster_fast_serial(D, r, V, lane, false));
             if (lane == 0) D.ncl[r] = ncl;
             free_spins(D, r, V, lane);
@@ -1275,7 +1296,7 @@ int launch_sse_serial(const SseDev &D, int mode, uint64_t target, uint32_t phase
                       uint64_t sample_origin, uint8_t *samples, uint64_t samples_per_rep, int layout, cudaStream_t st) {
     const int threads = 128;
     const uint32_t blocks = (uint32_t)(((uint64_t)D.R * 32 + threads - 1) / threads);
-    const size_t stk = (size_t)(threads / 32) * (STK_I + STK_F) * sizeof(uint32_t);
+    const size_t stk = (size_t)(threads / 32) * STK_WORDS * sizeof(uint32_t);
     size_t smem = stk + (size_t)(threads / 32) * D.N * sizeof(uint32_t);
     const int par = mode == 0 && smem <= 160 * 1024;
     if (!par) smem = stk;

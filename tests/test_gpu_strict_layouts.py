@@ -1,4 +1,4 @@
-"""STRICT cluster step on both workspace layouts (qmcb_set_option "strict_layout": 1 = world-line arrays, the default;
+"""STRICT cluster step on both workspace layouts (qmcb_set_option "strict_layout": bit 0 = world-line arrays, the default (9 = with the bond-partner request);
 0 = one 32-byte record per slot): the cluster NUMBERING (cluster.rs:57-97 discovery order) and everything that follows
 from it must equal the oracle's literal walk on either."""
 import numpy as np
@@ -20,7 +20,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("layout", [1, 0, 7])  # 7: world lines + next-line prefetch + links in their own launch
+@pytest.mark.parametrize("layout", [9, 0, 1, 15])  # 9: the default; 15: world lines + both L1 requests + links in their own launch
 @pytest.mark.parametrize("name,edges,gamma,h,cutoff,beta,sweeps", CASES)
 def test_numbering_matches_reference_order(name, edges, gamma, h, cutoff, beta, sweeps, layout):
     from isingmontecarlo_b200.sse import QmcIsingGraph
