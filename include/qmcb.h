@@ -80,11 +80,16 @@ int qmcb_create(const QmcbLattice *lattice, uint32_t n_replicas, const double *b
  * Interactions as the reference's make_interaction / make_diagonal_interaction take them: matrices in Interaction::at
  * indexing (qmc_runner.rs:560-664: first variable most significant, outputs more significant than inputs), 2^nv entries
  * for a diagonal interaction, 4^nv for a full one.  The weights of the diagonal update come from these tables (a
- * different code path from the (J, Gamma, h) arithmetic of qmcb_create); Qmc::timestep = diagonal update, cluster
- * update with Ising symmetry, free-spin flips (:363-377).  Supported shape (anything else: QMCB_ERR_UNSUPPORTED with the
- * reason): E interactions of two variables, each symmetric under the global flip, followed by exactly one CONSTANT
- * one-variable interaction per variable, in variable order -- what into_qmc builds, with arbitrary two-variable
- * weights and per-variable transverse weights.  Loop updates (directed_loop.rs) are not offered.
+ * different code path from the (J, Gamma, h) arithmetic of qmcb_create); Qmc::timestep = diagonal update, loop update
+ * when do_loop_updates, cluster update with Ising symmetry, free-spin flips (:363-377).  Supported shape (anything else:
+ * QMCB_ERR_UNSUPPORTED with the reason): E interactions of two variables, each symmetric under the global flip, followed
+ * by either exactly one CONSTANT one-variable interaction per variable, in variable order -- what into_qmc builds, with
+ * arbitrary two-variable weights and per-variable transverse weights -- or by no one-variable interaction at all (no
+ * cluster edges: the model moves by loop updates only).
+ * Loop updates (directed_loop.rs:103-301, Qmc::new(.., do_loop_updates) / set_do_loop_updates / loop_update): the
+ * two-variable matrices may then carry off-diagonal elements (exchange terms).  A handle with loop updates on, with
+ * such elements, or without cluster edges runs in QMCB_MODE_STRICT only, one lane per replica on the reference's link
+ * structure (the walk of a directed loop is one chain; replicas are the parallel axis).
  * `offset`: what Qmc::get_offset returns (the *_and_offset constructors accumulate it on the host side). */
 typedef struct {
     uint32_t nvars;
@@ -94,7 +99,7 @@ typedef struct {
     const uint32_t *mat_len; /* [n] 2^nv (diagonal) or 4^nv (full) */
     const double *mats;      /* the matrices, concatenated */
     double offset;
-    int do_loop_updates;     /* must be 0 */
+    int do_loop_updates;     /* Qmc::new's flag (qmc_runner.rs:48) */
 } QmcbInteractions;
 int qmcb_create_qmc(const QmcbInteractions *interactions, uint32_t n_replicas, const double *betas, const uint64_t *rng_keys,
                     uint64_t cutoff0, uint64_t capacity, const uint8_t *init_state, int device, QmcbHandle **out);
@@ -154,6 +159,12 @@ int qmcb_synchronize(QmcbHandle *h);
 /* single_diagonal_step / single_cluster_step (qmc_ising.rs:208-270, :273-320) */
 int qmcb_single_diagonal_step(QmcbHandle *h);
 int qmcb_single_cluster_step(QmcbHandle *h, uint64_t *n_clusters_out /* [R] or NULL */);
+/* Qmc::loop_update (qmc_runner.rs:205-220 -> LoopUpdater::make_loop_update_with_rng, directed_loop.rs:103-171): one
+ * directed-loop update of every replica; Qmc::set_do_loop_updates / should_do_loop_update (:268-275).  Handles made by
+ * qmcb_create_qmc only. */
+int qmcb_loop_update(QmcbHandle *h);
+int qmcb_set_do_loop_updates(QmcbHandle *h, int enable);
+int qmcb_get_do_loop_updates(const QmcbHandle *h, int *enabled);
 /* sum over replicas and sweeps so far of n after each sweep (the metric's "vertex updates") */
 int qmcb_total_vertex_updates(QmcbHandle *h, uint64_t *total);
 /* number of kernels this handle has launched so far */

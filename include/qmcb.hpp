@@ -223,8 +223,109 @@ public:
         return c;
     }
     QmcbHandle *raw() { return h_; }
+    // FastOps::new_from_ops (fast_ops.rs:80-87) for replica r: op words as include/qmcb.h packs them
+    void load_ops(size_t r, const std::vector<uint32_t> &words, const std::vector<bool> *state = nullptr) {
+        std::vector<uint8_t> st;
+        if (state)
+            for (bool b : *state) st.push_back(b ? 1 : 0);
+        check(qmcb_load_ops(h_, (uint32_t)r, words.data(), words.size(), state ? st.data() : nullptr));
+    }
+    std::vector<uint32_t> dump_ops(size_t r) {
+        std::vector<uint64_t> cut(replicas_);
+        check(qmcb_get_cutoffs(h_, cut.data()));
+        std::vector<uint32_t> w(cut[r]);
+        check(qmcb_dump_ops(h_, (uint32_t)r, w.data(), w.size()));
+        return w;
+    }
+
+protected:
+    void adopt(QmcbHandle *h, size_t nvars, size_t replicas) { h_ = h, nvars_ = nvars, replicas_ = replicas; }
+    bool has_handle() const { return h_ != nullptr; }
 };
 using DefaultQmcIsingGraph = QmcIsingGraph;
+
+// qmc::sse::Qmc (qmc_runner.rs:22-403): interactions given as matrices (Interaction::at indexing, :560-664); the batch is
+// built when the first step needs it.  timestep = diagonal update, loop update when do_loop_updates (directed_loop.rs:
+// 103-301), cluster update with Ising symmetry, free bits (:363-377).  Every QmcIsingGraph accessor works on it.
+class Qmc : public QmcIsingGraph {
+    struct Bond {
+        std::vector<double> mat;
+        std::vector<uint32_t> vars;
+    };
+    std::vector<Bond> bonds_;
+    std::vector<uint64_t> keys_;
+    std::vector<uint8_t> init_;
+    size_t nv_ = 0, cutoff_ = 0;
+    double offset_ = 0.0;
+    bool loops_ = false;
+    int mode_ = QMCB_MODE_STRICT, device_ = 0;
+
+    void add(std::vector<double> mat, const std::vector<size_t> &vars, bool diagonal, bool and_offset) {
+        if (has_handle()) throw Error(QMCB_ERR_UNSUPPORTED, "interactions are fixed once the batch has been stepped");
+        const size_t n = vars.size(), tn = (size_t)1 << n;
+        if (mat.size() != (diagonal ? tn : tn * tn)) throw Error(QMCB_ERR_BAD_ARG, "Given vars do not match the matrix size");
+        if (and_offset) {  // new_offset :508-521 / new_diagonal_offset :424-436
+            const size_t stride = diagonal ? 1 : tn + 1;
+            double lo = mat[0];
+            for (size_t k = 0; k < tn; k++) lo = std::min(lo, mat[k * stride]);
+            for (size_t k = 0; k < tn; k++) mat[k * stride] -= lo;
+            offset_ -= lo;
+        }
+        Bond b;
+        b.mat = std::move(mat);
+        for (size_t v : vars) b.vars.push_back((uint32_t)v);
+        bonds_.push_back(std::move(b));
+    }
+
+public:
+    // Qmc::new / new_with_state (qmc_runner.rs:48-87): cutoff = nvars, one Philox key per replica
+    Qmc(size_t nvars, const std::vector<uint64_t> &rng_keys, bool do_loop_updates, const std::vector<bool> *state = nullptr,
+        int mode = QMCB_MODE_STRICT, int device = 0)
+        : keys_(rng_keys), nv_(nvars), cutoff_(nvars), loops_(do_loop_updates), mode_(mode), device_(device) {
+        if (state)
+            for (size_t r = 0; r < rng_keys.size(); r++)
+                for (bool b : *state) init_.push_back(b ? 1 : 0);
+    }
+    void make_interaction(std::vector<double> mat, const std::vector<size_t> &vars) { add(std::move(mat), vars, false, false); }             // :113-122
+    void make_interaction_and_offset(std::vector<double> mat, const std::vector<size_t> &vars) { add(std::move(mat), vars, false, true); }   // :125-135
+    void make_diagonal_interaction(std::vector<double> mat, const std::vector<size_t> &vars) { add(std::move(mat), vars, true, false); }     // :138-146
+    void make_diagonal_interaction_and_offset(std::vector<double> mat, const std::vector<size_t> &vars) { add(std::move(mat), vars, true, true); }  // :149-156
+    void increase_cutoff_to(size_t cutoff) { cutoff_ = std::max(cutoff_, cutoff); }  // :307-309 (before the first step)
+    // builds the batch; called by the first step
+    void build() {
+        if (has_handle()) return;
+        std::vector<uint32_t> nv, vars, len;
+        std::vector<double> mats;
+        for (auto &b : bonds_) {
+            nv.push_back((uint32_t)b.vars.size()), len.push_back((uint32_t)b.mat.size());
+            vars.push_back(b.vars[0]), vars.push_back(b.vars.size() > 1 ? b.vars[1] : 0);
+            mats.insert(mats.end(), b.mat.begin(), b.mat.end());
+        }
+        QmcbInteractions in{(uint32_t)nv_, (uint32_t)bonds_.size(), nv.data(), vars.data(), len.data(), mats.data(), offset_, loops_ ? 1 : 0};
+        std::vector<double> betas(keys_.size(), 1.0);
+        QmcbHandle *h = nullptr;
+        check(qmcb_create_qmc(&in, (uint32_t)keys_.size(), betas.data(), keys_.data(), cutoff_, 0, init_.empty() ? nullptr : init_.data(), device_, &h));
+        adopt(h, nv_, keys_.size());
+        set_mode(mode_);
+    }
+    void loop_update() {  // Qmc::loop_update :205-220
+        build();
+        check(qmcb_loop_update(raw()));
+    }
+    void set_do_loop_updates(bool enable) {  // :268-270
+        loops_ = enable;
+        if (has_handle()) check(qmcb_set_do_loop_updates(raw(), enable ? 1 : 0));
+    }
+    bool should_do_loop_update() const { return loops_; }
+    std::vector<double> timesteps(size_t t, double beta) {
+        build();
+        return QmcIsingGraph::timesteps(t, beta);
+    }
+    std::vector<std::vector<bool>> timestep(double beta) {
+        build();
+        return QmcIsingGraph::timestep(beta);
+    }
+};
 
 // qmc::sse::parallel_tempering::TemperingContainer (tempering_container.rs:19-302) on one GPU: n_chains ladders of
 // betas.size() slots; add_qmc_stepper is replaced by giving the whole ladder at construction.

@@ -63,6 +63,9 @@ SIGNATURES = {
     "qmcb_synchronize": [vp],
     "qmcb_single_diagonal_step": [vp],
     "qmcb_single_cluster_step": [vp, u64p],
+    "qmcb_loop_update": [vp],
+    "qmcb_set_do_loop_updates": [vp, C.c_int],
+    "qmcb_get_do_loop_updates": [vp, C.POINTER(C.c_int)],
     "qmcb_total_vertex_updates": [vp, u64p],
     "qmcb_launch_count": [vp, u64p],
     "qmcb_get_state": [vp, C.c_uint32, u8p],

@@ -131,6 +131,7 @@ struct QmcbHandle {
     uint64_t *pt_rec_all_dev = nullptr;  // [S] gathered records
     double *pt_energy_dev = nullptr;     // [S] per-segment energies of qmcb_pt_timesteps_sample
     bool generic = false;  // created by qmcb_create_qmc: weights from interaction tables
+    bool offdiag2 = false; // ... some two-variable interaction has off-diagonal elements (only loop updates produce such ops)
     std::vector<double> gw2_h, ggam_h;
     // kernel-selection knobs of the warp-parallel sweep (qmcb_set_option), per handle
     SseTuning tune{};
@@ -228,7 +229,7 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
     if (h->mode == QMCB_MODE_STRICT) {
         if ((rc = alloc_strict_ws(h))) return rc;
         const bool full = (phases & 0xFu) == 0xFu;
-        if (full && h->impl != 1 && h->target > origin) {
+        if (full && h->impl != 1 && !h->D.loop_path && h->target > origin) {
             // the diagonal update is order-exact in the warp-parallel kernel, so STRICT sweeps use it too:
             // per sweep one launch for the diagonal update, one for links + reference-order clusters
             if ((rc = alloc_fast_ws(h))) return rc;
@@ -245,7 +246,7 @@ static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t
                 return QMCB_OK;
             }
         }
-        const int wl = launch_sse_serial(h->D, 0, h->target, phases, freq, origin, samples_dev, spr, h->impl == 1 ? 0 : h->strict_layout, h->stream);
+        const int wl = launch_sse_serial(h->D, 0, h->target, phases, freq, origin, samples_dev, spr, h->impl == 1 || h->D.loop_path ? 0 : h->strict_layout, h->stream);
         if (phases & 2u) h->strict_wl_last = wl != 0;
         h->launches += 1;
     } else if (h->mode == QMCB_MODE_COUNTER) {
@@ -428,10 +429,15 @@ extern "C" int qmcb_create(const QmcbLattice *lat, uint32_t R, const double *bet
 extern "C" int qmcb_create_qmc(const QmcbInteractions *I, uint32_t R, const double *betas, const uint64_t *keys, uint64_t cutoff0,
                                uint64_t capacity, const uint8_t *init_state, int device, QmcbHandle **out) {
     if (!I || !out || !I->nv || !I->vars || !I->mat_len || !I->mats || I->nvars == 0) return fail(QMCB_ERR_BAD_ARG, "null argument or no variables");
-    if (I->do_loop_updates) return fail(QMCB_ERR_UNSUPPORTED, "loop updates (directed_loop.rs:103-301) are not offered: do_loop_updates must be false");
     const uint32_t N = I->nvars, n = I->n_interactions;
-    if (n < N) return fail(QMCB_ERR_UNSUPPORTED, "need one constant one-variable interaction per variable (cluster edges) after the two-variable ones");
-    const uint32_t E = n - N;
+    // shape taken: E two-variable interactions, then either one constant one-variable interaction per variable (cluster
+    // edges) or none at all (a model that moves by loop updates only)
+    uint32_t E = 0;
+    while (E < n && I->nv[E] == 2) E++;
+    const bool no_site = E == n;
+    if (!no_site && n - E != N) return fail(QMCB_ERR_UNSUPPORTED, "need one constant one-variable interaction per variable (cluster edges) after the two-variable ones, or none");
+    bool offdiag2 = false;
+    std::vector<double> full(16 * (size_t)E + 4 * (size_t)N, 0.0);
     std::vector<uint32_t> va(E), vb(E);
     std::vector<double> w2(4 * (size_t)E), gam((size_t)n, 0.0), Jz(E, 0.0);
     const double *m = I->mats;
@@ -456,10 +462,17 @@ extern "C" int qmcb_create_qmc(const QmcbInteractions *I, uint32_t R, const doub
             // sym_under_ising :626-648 on the diagonal, and no off-diagonal elements (they only matter for loop updates)
             if (!(std::fabs(d[0] - d[3]) < EPS && std::fabs(d[1] - d[2]) < EPS))
                 return fail(QMCB_ERR_UNSUPPORTED, "a two-variable interaction breaks the Ising symmetry: the reference then runs no cluster update (qmc_runner.rs:278-281); not offered");
-            if (!diagonal)
+            if (!diagonal) {  // off-diagonal elements matter to loop updates only; the cluster update flips all four legs, so
+                              // the whole matrix has to be symmetric under the global flip (sym_under_ising :626-648)
+                for (uint32_t x = 0; x < 16; x++)
+                    if (!(std::fabs(m[x] - m[(~x) & 15u]) < EPS))
+                        return fail(QMCB_ERR_UNSUPPORTED, "a two-variable interaction breaks the Ising symmetry: the reference then runs no cluster update (qmc_runner.rs:278-281); not offered");
                 for (uint32_t o = 0; o < 4; o++)
                     for (uint32_t i = 0; i < 4; i++)
-                        if (o != i && m[(o << 2) + i] != 0.0) return fail(QMCB_ERR_UNSUPPORTED, "off-diagonal two-variable matrix elements need loop updates (not offered)");
+                        if (o != i && m[(o << 2) + i] != 0.0) offdiag2 = true;
+            }
+            for (uint32_t x = 0; x < 16; x++)  // Interaction::at (:560-600): a Diagonal interaction is 0 off the diagonal
+                full[16 * (size_t)b + x] = diagonal ? ((x >> 2) == (x & 3u) ? m[x & 3u] : 0.0) : m[x];
             va[b] = I->vars[2 * b], vb[b] = I->vars[2 * b + 1];
             for (uint32_t s0 = 0; s0 < 2; s0++)
                 for (uint32_t s1 = 0; s1 < 2; s1++) w2[4 * (size_t)b + (s0 | (s1 << 1))] = d[(s0 << 1) | s1];
@@ -471,9 +484,11 @@ extern "C" int qmcb_create_qmc(const QmcbInteractions *I, uint32_t R, const doub
             for (uint32_t k = 1; constant && k < len; k++) constant = std::fabs(m[k - 1] - m[k]) < EPS;
             if (!constant) return fail(QMCB_ERR_UNSUPPORTED, "one-variable interactions must be constant (cluster edges, cluster.rs:284-286)");
             gam[b] = m[0];
+            for (uint32_t x = 0; x < 4; x++) full[16 * (size_t)E + 4 * (size_t)v + x] = m[x];
         }
         m += len;
     }
+    if (no_site) gam.resize((size_t)E + N, 0.0);
     QmcbLattice lat{N, E, va.data(), vb.data(), Jz.data(), gam[E], 0.0};
     QmcbHandle *h = nullptr;
     int rc = qmcb_create(&lat, R, betas, keys, cutoff0, capacity, init_state, device, &h);
@@ -488,7 +503,25 @@ extern "C" int qmcb_create_qmc(const QmcbInteractions *I, uint32_t R, const doub
         qmcb_destroy(h);
         return fail_cuda(e, "interaction tables", __FILE__, __LINE__);
     }
-    D.g_w2 = w2_dev, D.g_gam = gam_dev;
+    double *full_dev = nullptr;
+    e = h->pool.alloc(&full_dev, full.size());
+    if (e == cudaSuccess) e = cudaMemcpy(full_dev, full.data(), sizeof(double) * full.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        qmcb_destroy(h);
+        return fail_cuda(e, "interaction tables", __FILE__, __LINE__);
+    }
+    D.g_w2 = w2_dev, D.g_gam = gam_dev, D.g_full = full_dev;
+    D.loop_updates = I->do_loop_updates ? 1 : 0, D.no_site = no_site ? 1 : 0;
+    h->offdiag2 = offdiag2;
+    D.loop_path = D.loop_updates || D.no_site || offdiag2;
+    if (no_site) {  // bond indices are the two-variable interactions only (qmc_runner.rs:177)
+        D.Nb = E;
+        D.zone = E ? (((uint64_t)E << __builtin_clzll((unsigned long long)E)) - 1ull) : 0;
+        if (E == 0) {
+            qmcb_destroy(h);
+            return fail(QMCB_ERR_BAD_ARG, "no interactions");
+        }
+    }
     D.epk = nullptr;  // the packed (J, Gamma) tables of the Ising path do not describe this handle
     h->generic = true, h->gw2_h = w2, h->ggam_h = gam;
     h->offset = I->offset, h->offset_h = {I->offset};
@@ -516,6 +549,7 @@ extern "C" int qmcb_set_stream(QmcbHandle *h, void *s) {
 extern "C" int qmcb_set_mode(QmcbHandle *h, int mode) {
     CHECK_H(h);
     if (mode != QMCB_MODE_STRICT && mode != QMCB_MODE_FAST && mode != QMCB_MODE_COUNTER) return fail(QMCB_ERR_BAD_ARG, "unknown mode");
+    if (mode != QMCB_MODE_STRICT && h->D.loop_path) return fail(QMCB_ERR_UNSUPPORTED, "models with loop updates, off-diagonal two-variable interactions or no cluster edges run in QMCB_MODE_STRICT only");
     if (mode == QMCB_MODE_COUNTER && h->D.hb_cum) return fail(QMCB_ERR_UNSUPPORTED, "the heat-bath diagonal update has no COUNTER-mode contract (use FAST or STRICT)");
     h->mode = mode;
     return QMCB_OK;
@@ -941,6 +975,29 @@ extern "C" int qmcb_single_cluster_step(QmcbHandle *h, uint64_t *ncl_out) {
         CUDA_TRY(cudaMemcpy(ncl.data(), h->D.ncl, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
         for (uint32_t r = 0; r < h->D.R; r++) ncl_out[r] = ncl[r];
     }
+    return QMCB_OK;
+}
+// Qmc::loop_update (qmc_runner.rs:205-220): one directed-loop update of every replica
+extern "C" int qmcb_loop_update(QmcbHandle *h) {
+    CHECK_H(h);
+    if (!h->generic) return fail(QMCB_ERR_UNSUPPORTED, "loop updates belong to handles made by qmcb_create_qmc (QmcIsingGraph has none, qmc_ising.rs:644-795)");
+    if (h->mode != QMCB_MODE_STRICT) return fail(QMCB_ERR_UNSUPPORTED, "loop updates run in QMCB_MODE_STRICT");
+    int rc = ensure_capacity(h);
+    return rc ? rc : run_to_target(h, 32u, 1, 0, nullptr, 0);
+}
+// Qmc::set_do_loop_updates (qmc_runner.rs:268-270)
+extern "C" int qmcb_set_do_loop_updates(QmcbHandle *h, int enable) {
+    CHECK_H(h);
+    if (!h->generic) return fail(QMCB_ERR_UNSUPPORTED, "loop updates belong to handles made by qmcb_create_qmc");
+    if (enable && h->mode != QMCB_MODE_STRICT) return fail(QMCB_ERR_UNSUPPORTED, "loop updates run in QMCB_MODE_STRICT: set the mode first");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->D.loop_updates = enable ? 1 : 0;
+    h->D.loop_path = h->D.loop_updates || h->D.no_site || h->offdiag2;
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_do_loop_updates(const QmcbHandle *h, int *enabled) {
+    if (!h || !enabled) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *enabled = h->D.loop_updates;
     return QMCB_OK;
 }
 extern "C" int qmcb_total_vertex_updates(QmcbHandle *h, uint64_t *total) {

@@ -53,6 +53,13 @@ struct SseDev {
     // g_w2[4 b + (s0 | s1 << 1)] for the two-variable interaction b, g_gam[v] for the constant one-variable op of
     // variable v, stored at its bond index: g_gam[E + v].  NULL = the transverse-field Ising weights of qmc_ising.rs:863-888.
     const double *g_w2, *g_gam;
+    // loop updates (directed_loop.rs:103-301) need every matrix element: g_full[16 b + (o0 o1 i0 i1)] for the two-variable
+    // interaction b, g_full[16 E + 4 v + (o i)] for the one-variable interaction of variable v (Interaction::at indexing,
+    // qmc_runner.rs:560-600, 650-664).  NULL = no loop updates.  no_site: the model has no one-variable interactions at all
+    // (Nb = E, no cluster edges, hence no cluster step: qmc_runner.rs:278-281).  loop_path: the sweep takes the all-serial
+    // step on the per-slot records (loop updates on, two-variable ops that can be off-diagonal, or no_site).
+    const double *g_full;
+    int loop_updates, no_site, loop_path;
     // heat-bath diagonal update (heatbath.rs:10-61 BondWeights); NULL = Metropolis rule
     const double *hb_cum, *hb_maxw;  // [Nb] cumulative / per-bond maximum diagonal weight
     double hb_total;

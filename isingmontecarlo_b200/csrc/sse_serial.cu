@@ -1086,6 +1086,96 @@ __device__ void free_spins(const SseDev &D, uint32_t r, const Rep &V, int lane) 
 // bit4 run only the single step that takes the replica from target - 1 to target
 // 7 blocks of 4 warps per SM (72 registers): 4096 replicas are resident in one wave, which is what this
 // latency-bound kernel needs (at 80 registers it ran in two waves: 467 ms instead of 290 ms per sweep on config #3)
+// ------------------------------------------------------------------------------------------
+// Directed-loop update (directed_loop.rs:103-171 make_loop_update_with_rng with initial_n = None, as Qmc::loop_update
+// qmc_runner.rs:205-220 calls it; :183-211 apply_loop_update; :214-301 loop_body), lane 0, on the per-slot records
+// (links of links_serial / links_parallel).  A leg is (relative variable, side); the weight of leaving through a leg is
+// the matrix element of the op with the entrance leg and that leg flipped (adjust_states, qmc_types.rs:28-37).
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void loop_update_serial(const SseDev &D, uint32_t r, const Rep &V) {
+    const uint32_t n = D.n[r];
+    if (n == 0) return;  // :139
+    const uint64_t key = D.key[r];
+    uint64_t cur = D.cursor[r];
+    auto gen_range = [&](uint64_t range) -> uint64_t {  // rand 0.8 UniformInt<usize>::sample_single
+        const uint64_t zone = (range << __clzll((long long)range)) - 1ull;
+        uint64_t hi, lo;
+        do {
+            const uint64_t v = stream_word(key, cur++);
+            hi = __umul64hi(v, range), lo = v * range;
+        } while (lo > zone);
+        return hi;
+    };
+    const uint64_t initial_n = gen_range(n);  // :140-142
+    uint32_t p0 = V.ends[0];                  // get_nth_p :76-87
+    for (uint64_t seen = 0;; p0++) {
+        if (V.ops[p0] == OP_EMPTY) continue;
+        if (seen == initial_n) break;
+        seen++;
+    }
+    const uint32_t w0 = REC_OP(V, p0);
+    const uint32_t v0 = (uint32_t)gen_range(bond_kind(D, op_bond(w0)) == KIND_BOND ? 2u : 1u);  // :147
+    const uint32_t s0 = ((int32_t)(uint32_t)(stream_word(key, cur++) >> 32) < 0) ? SIDE_IN : SIDE_OUT;  // rng.gen::<bool>() :148-152
+    uint32_t sel = p0, ev = v0, es = s0;
+    int err = 0;
+    for (;;) {  // :195-210
+        uint32_t w = REC_OP(V, sel);
+        const uint32_t b = op_bond(w);
+        const int kind = bond_kind(D, b);
+        const uint32_t nv = kind == KIND_BOND ? 2u : 1u, nlegs = 2u * nv;
+        const uint32_t in_e = op_in(w) ^ (es == SIDE_IN ? 1u << ev : 0u), out_e = op_out(w) ^ (es == SIDE_OUT ? 1u << ev : 0u);
+        double wt[4], total = 0.0;
+        for (uint32_t k = 0; k < nlegs; k++) {  // inputs legs, then outputs legs :231-240
+            const uint32_t kv = k < nv ? k : k - nv;
+            const uint32_t in = in_e ^ (k < nv ? 1u << kv : 0u), out = out_e ^ (k < nv ? 0u : 1u << kv);
+            // Interaction::at: outputs more significant than inputs, first variable most significant
+            const size_t idx = kind == KIND_BOND
+                                   ? 16 * (size_t)b + ((((out & 1u) << 1) | (out >> 1)) << 2 | ((in & 1u) << 1) | (in >> 1))
+                                   : 16 * (size_t)D.E + 4 * (size_t)(b - D.E) + ((out & 1u) << 1 | (in & 1u));
+            wt[k] = __ldg(D.g_full + idx);
+            total = total + wt[k];  // :242
+        }
+        if (!(0.0 < total) || isinf(total)) {  // gen_range(0. ..total) panics on an empty or unbounded range
+            err = DEV_ERR_PROB;
+            break;
+        }
+        double c;
+        do c = unit_f64(stream_word(key, cur++)) * total + 0.0;  // gen_range(0. ..total) :243
+        while (!(c < total));
+        uint32_t ex = NONE32;
+        for (uint32_t k = 0; k < nlegs; k++) {  // try_fold :244-253
+            if (c < wt[k]) {
+                ex = k;
+                break;
+            }
+            c = c - wt[k];
+        }
+        if (ex == NONE32) {  // unwrap_err() on Ok: rounding left the choice beyond the last leg
+            err = DEV_ERR_PROB;
+            break;
+        }
+        const uint32_t xv = ex < nv ? ex : ex - nv, xs = ex < nv ? SIDE_IN : SIDE_OUT;
+        const uint32_t in_n = in_e ^ (xs == SIDE_IN ? 1u << xv : 0u), out_n = out_e ^ (xs == SIDE_OUT ? 1u << xv : 0u);
+        w = make_op(b, in_n, out_n);  // :256-259
+        REC_OP(V, sel) = w, V.ops[sel] = w;
+        if (sel == p0 && xv == v0 && xs == s0) break;  // :266-267
+        uint32_t vv[2];
+        bond_vars(D, b, kind, vv[0], vv[1]);
+        const uint32_t var = vv[xv];
+        uint32_t leg = REC_LINK(V, sel, (xs == SIDE_OUT ? 2u : 0u) + xv);
+        if (leg == NONE32) {  // the world line closes through p = 0: the state there changes :274-289
+            const uint32_t bit = ((xs == SIDE_OUT ? out_n : in_n) >> xv) & 1u;
+            V.state[var >> 5] = (V.state[var >> 5] & ~(1u << (var & 31))) | (bit << (var & 31));
+            leg = xs == SIDE_OUT ? V.vfirst[var] : V.vlast[var];
+        }
+        const uint32_t q = leg >> 1, rq = leg & 1u, ns = xs ^ 1u;  // :291
+        if (q == p0 && rq == v0 && ns == s0) break;               // :293-294
+        sel = q, ev = rq, es = ns;
+    }
+    D.cursor[r] = cur;
+    if (err) atomicOr(D.status, err);
+}
+
 __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint64_t target, uint32_t phases,
                                                     uint64_t sample_freq, uint64_t sample_origin,
                                                     uint8_t *samples, uint64_t samples_per_rep, int par_links, int layout, int split) {
@@ -1113,7 +1203,29 @@ __global__ void __launch_bounds__(128, 7) k_sse_serial(SseDev D, int mode, uint6
             }
             __syncwarp();
         }
-        if (phases & 2u) {
+        if (phases & 32u) {  // Qmc::loop_update on its own (qmc_runner.rs:205-220): links, one loop update
+            for (uint32_t v = lane; v < D.N; v += 32) V.vfirst[v] = NONE32, V.vlast[v] = NONE32;
+            __syncwarp();
+            if (lane == 0) {
+                links_serial(D, r, V, true);
+                loop_update_serial(D, r, V);
+            }
+            __syncwarp();
+            break;
+        }
+        if ((phases & 2u) && D.loop_path) {  // a model with loop updates: all-serial step on the per-slot records
+            for (uint32_t v = lane; v < D.N; v += 32) V.vfirst[v] = NONE32, V.vlast[v] = NONE32;
+            __syncwarp();
+            if (lane == 0) {
+                links_serial(D, r, V, true);
+                if (D.loop_updates) loop_update_serial(D, r, V);  // qmc_runner.rs:366-368: between the diagonal and the cluster update
+            }
+            __syncwarp();
+            long long st_t = 0;
+            uint32_t ncl = D.no_site ? 0u : cluster_strict(D, r, V, lane, my_smem, st_t);
+            if (lane == 0) D.ncl[r] = ncl;
+            free_spins(D, r, V, lane);
+        } else if (phases & 2u) {
             const bool wl = mode == 0 && par_links && (layout & 1);
             long long st_t = clock64();
             if (split == 2) {
@@ -1180,7 +1292,12 @@ __global__ void k_sse_verify(SseDev D, uint32_t r, int *ok_out, uint32_t *scratc
         uint32_t v0, v1;
         bond_vars(D, b, kind, v0, v1);
         uint32_t in = op_in(w), out = op_out(w);
-        if (kind != KIND_SITE) {
+        if (D.g_full) {  // generic interactions: the matrix element of the op as it stands (Interaction::at) must not vanish
+            const size_t idx = kind == KIND_BOND
+                                   ? 16 * (size_t)b + ((((out & 1u) << 1) | (out >> 1)) << 2 | ((in & 1u) << 1) | (in >> 1))
+                                   : 16 * (size_t)D.E + 4 * (size_t)(b - D.E) + ((out & 1u) << 1 | (in & 1u));
+            if (kind == KIND_LONG || !(fabs(D.g_full[idx]) > 2.220446049250313e-16)) ok = 0;
+        } else if (kind != KIND_SITE) {
             if (in != out) ok = 0;  // off-diagonal two-site / longitudinal ops have zero weight
             else if (!(fabs(bond_weight(Hm, b, kind, in & 1u, (in >> 1) & 1u)) > 2.220446049250313e-16)) ok = 0;
         } else if (!(fabs(Hm.gamma) > 2.220446049250313e-16)) ok = 0;

@@ -394,8 +394,9 @@ class Qmc(QmcIsingGraph):
     its weights from those tables -- `qmcb_create_qmc`, a different code path from the (J, Gamma, h) arithmetic of
     QmcIsingGraph.  `timestep` is Qmc::timestep (:363-377): diagonal update, cluster update with Ising symmetry, free
     bits.  The handle is created when the first step (or accessor) needs it; the shape the engine takes is stated in
-    include/qmcb.h (two-variable interactions first, then one constant one-variable interaction per variable).  Loop
-    updates (directed_loop.rs) are not offered: QMCB_ERR_UNSUPPORTED.  Every QmcIsingGraph accessor works on it."""
+    include/qmcb.h (two-variable interactions first, then one constant one-variable interaction per variable, or none).
+    `do_loop_updates` / `set_do_loop_updates` / `loop_update` are the reference's directed-loop update
+    (directed_loop.rs:103-301; STRICT mode, one lane per replica).  Every QmcIsingGraph accessor works on it."""
 
     def __init__(self, nvars, rng_keys, betas=1.0, state=None, do_loop_updates=False, mode=MODE_STRICT, device=0, capacity=0):
         self._L = _lib.load()
@@ -459,13 +460,21 @@ class Qmc(QmcIsingGraph):
                 if cur[r] < cutoff:
                     self.set_cutoff(int(cutoff), r)
 
-    def set_do_loop_updates(self, flag):
-        if flag:
-            raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "directed-loop updates are not offered on the GPU path")
+    def set_do_loop_updates(self, flag):  # qmc_runner.rs:268-270
+        self.do_loop_updates = bool(flag)
+        if self._h is not None:
+            check(self._L.qmcb_set_do_loop_updates(self._h, int(bool(flag))))
 
-    def should_do_cluster_update(self):
+    def should_do_loop_update(self):  # :273-275
+        return self.do_loop_updates
+
+    def loop_update(self):
+        """Qmc::loop_update (qmc_runner.rs:205-220): one directed-loop update of every replica"""
         self._ensure()
-        return True  # the shapes qmcb_create_qmc accepts have cluster edges and keep the Ising symmetry
+        check(self._L.qmcb_loop_update(self._h))
+
+    def should_do_cluster_update(self):  # :278-281; the shapes qmcb_create_qmc accepts keep the Ising symmetry
+        return any(len(v) == 1 for _, v, _ in self._bonds)
 
     def _ensure(self):
         if self._h is not None:

@@ -287,7 +287,7 @@ struct OrcSse {
     /* generic Qmc (qmc_runner.rs:22-45): a list of interactions instead of (edges, transverse, longitudinal) */
     struct OrcInteraction *inter;
     uint32_t ninter;
-    int is_qmc, has_cluster_edges, breaks_ising_symmetry;
+    int is_qmc, has_cluster_edges, breaks_ising_symmetry, do_loop_updates;
 };
 
 /* Interaction, qmc_runner.rs:406-421: type Full(constant) | Diagonal, mat, n, vars, constant_along_diagonal */
@@ -1019,13 +1019,89 @@ static uint64_t cluster_and_free_spins(OrcSse *g, int mode) {
     return ncl;
 }
 
-/* Qmc::timestep, qmc_runner.rs:363-377: diagonal_update (:158-201, the cutoff grows there), cluster_update with Ising
- * symmetry and no weights when should_do_cluster_update (:223-238, :278-281), flip_free_bits (:241-256).  Loop updates
- * (directed_loop.rs) are not restated. */
+/* ===================================================================================
+ * Directed-loop update: directed_loop.rs:103-171 (make_loop_update_with_rng, initial_n = None as Qmc::loop_update
+ * qmc_runner.rs:205-220 calls it), :183-211 (apply_loop_update), :214-301 (loop_body).  A leg is (relative variable,
+ * side); the weight of leaving through a leg is the matrix element of the op with the entrance leg and that leg
+ * flipped (adjust_states, qmc_types.rs:28-37; entering and leaving through the same leg is the bounce).
+ * =================================================================================== */
+static void flip_leg(uint8_t *in, uint8_t *out, int var, int side) {
+    if (side == SIDE_IN) in[var] ^= 1;
+    else out[var] ^= 1;
+}
+void orc_qmc_loop_update(OrcSse *g) {
+    if (g->n == 0) return; /* :139; post_loop_update_hook (:174) is empty */
+    const uint64_t initial_n = gen_range_usize(&g->rng, g->n); /* :140-142 */
+    int64_t p = g->first_p;                                     /* get_nth_p :76-87 */
+    for (uint64_t i = 0; i < initial_n; i++) p = g->ops[p].next_p;
+    const int64_t p0 = p;
+    const int v0 = (int)gen_range_usize(&g->rng, g->ops[p].nv);      /* :147 */
+    const int s0 = gen_std_bool(&g->rng) ? SIDE_IN : SIDE_OUT;       /* :148-152 */
+    int64_t sel = p0;
+    int ev = v0, es = s0;
+    for (;;) { /* :195-210 */
+        Node *op = &g->ops[sel];
+        const int nv = op->nv, nlegs = 2 * nv;
+        double w[4], total = 0.0;
+        for (int k = 0; k < nlegs; k++) { /* inputs legs, then outputs legs :231-240 */
+            uint8_t in[2] = {op->in[0], op->in[1]}, out[2] = {op->out[0], op->out[1]};
+            flip_leg(in, out, ev, es);
+            flip_leg(in, out, k % nv, k < nv ? SIDE_IN : SIDE_OUT);
+            w[k] = hamiltonian(g, op->bond, in, out);
+            total = total + w[k]; /* :242 */
+        }
+        if (!(0.0 < total) || !isfinite(total)) { /* gen_range(0. ..total) panics on an empty or unbounded range */
+            g->error |= 32;
+            return;
+        }
+        double c = gen_range_f64(&g->rng, 0.0, total); /* :243 */
+        int ex = -1;
+        for (int k = 0; k < nlegs; k++) { /* try_fold :244-253 */
+            if (c < w[k]) {
+                ex = k;
+                break;
+            }
+            c = c - w[k];
+        }
+        if (ex < 0) { /* unwrap_err() on Ok: rounding left the choice beyond the last leg */
+            g->error |= 32;
+            return;
+        }
+        const int xv = ex % nv, xs = ex < nv ? SIDE_IN : SIDE_OUT;
+        flip_leg(op->in, op->out, ev, es); /* :256-259 */
+        flip_leg(op->in, op->out, xv, xs);
+        if (sel == p0 && xv == v0 && xs == s0) return; /* :266-267 */
+        int64_t q;
+        int rq;
+        const uint32_t var = op->vars[xv];
+        if (xs == SIDE_OUT) { /* :274-281 */
+            q = op->next_vp[xv], rq = op->next_vr[xv];
+            if (q == NONE) {
+                g->state[var] = op->out[xv];
+                q = g->vfirst_p[var], rq = g->vfirst_r[var];
+            }
+        } else { /* :282-289 */
+            q = op->prev_vp[xv], rq = op->prev_vr[xv];
+            if (q == NONE) {
+                g->state[var] = op->in[xv];
+                q = g->vlast_p[var], rq = g->vlast_r[var];
+            }
+        }
+        const int ns = xs == SIDE_OUT ? SIDE_IN : SIDE_OUT; /* :291 */
+        if (q == p0 && rq == v0 && ns == s0) return;        /* :293-294 */
+        sel = q, ev = rq, es = ns;
+    }
+}
+void orc_qmc_set_do_loop_updates(OrcSse *g, int enable) { g->do_loop_updates = enable != 0; } /* qmc_runner.rs:268-270 */
+
+/* Qmc::timestep, qmc_runner.rs:363-377: diagonal_update (:158-201, the cutoff grows there), loop_update when
+ * do_loop_updates (:366-368), cluster_update with Ising symmetry and no weights when should_do_cluster_update (:223-238,
+ * :278-281), flip_free_bits (:241-256). */
 void orc_qmc_timestep(OrcSse *g, double beta, int mode) {
     diagonal_step(g, beta, mode);
     uint64_t grown = g->n + g->n / 2; /* :195 */
     if (grown > g->cutoff) g->cutoff = grown;
+    if (g->do_loop_updates) orc_qmc_loop_update(g);
     if (!g->breaks_ising_symmetry && g->has_cluster_edges) {
         if (mode != ORC_MODE_STRICT) cluster_update_fast(g, 0, 0);
         else cluster_update_strict(g, 0);

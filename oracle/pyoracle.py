@@ -64,6 +64,8 @@ def lib():
     sig("orc_qmc_create", vp, C.c_uint32, C.c_uint64, u8p)
     sig("orc_qmc_make_interaction", C.c_int, vp, f64p, C.c_uint32, u32p, C.c_uint32, C.c_int, C.c_int)
     sig("orc_qmc_flags", C.c_int, vp)
+    sig("orc_qmc_loop_update", None, vp)
+    sig("orc_qmc_set_do_loop_updates", None, vp, C.c_int)
     sig("orc_sse_single_diagonal_step", None, vp, C.c_double)
     sig("orc_sse_single_diagonal_step_mode", None, vp, C.c_double, C.c_int)
     sig("orc_sse_single_cluster_step", C.c_uint64, vp, C.c_int)
@@ -389,6 +391,12 @@ class QmcOracle(SseOracle):
 
     def make_diagonal_interaction_and_offset(self, mat, vars_):  # :149-156
         self._make(mat, vars_, True, True)
+
+    def loop_update(self):  # Qmc::loop_update, qmc_runner.rs:205-220
+        lib().orc_qmc_loop_update(self._h)
+
+    def set_do_loop_updates(self, enable):  # qmc_runner.rs:268-270
+        lib().orc_qmc_set_do_loop_updates(self._h, int(bool(enable)))
 
     @property
     def has_cluster_edges(self):

@@ -110,6 +110,42 @@ int main() {
         auto ac = g2.calculate_variable_autocorrelation(64, 1.0, 1);
         ASSERT(ac.size() == 3 && ac[0].size() == 64 && std::abs(ac[0][0] - 1.0) < 1e-12);
     }
+    {  // tests/check_loop_crash.rs:6-74 run_single_bond / run_double_bond: 100 loop updates on a hand-built string, verify
+        std::vector<double> swap(16, 0.0);  // weight 1 when inputs == outputs or inputs == reversed outputs (:19-27)
+        for (int o0 = 0; o0 < 2; o0++)
+            for (int o1 = 0; o1 < 2; o1++)
+                for (int i0 = 0; i0 < 2; i0++)
+                    for (int i1 = 0; i1 < 2; i1++)
+                        if ((i0 == o0 && i1 == o1) || (i0 == o1 && i1 == o0)) swap[(o0 << 3) | (o1 << 2) | (i0 << 1) | i1] = 1.0;
+        for (size_t nbonds : {(size_t)1, (size_t)2}) {
+            std::vector<bool> st(nbonds + 1, false);
+            qmcb::Qmc q(nbonds + 1, seeds, true, &st);
+            for (size_t b = 0; b < nbonds; b++) q.make_interaction(swap, {b, b + 1});
+            q.increase_cutoff_to(nbonds);
+            q.build();
+            std::vector<uint32_t> ops;
+            for (size_t b = 0; b < nbonds; b++) ops.push_back((uint32_t)b);  // FastOp::diagonal([b, b+1], b, [false, false])
+            for (size_t r = 0; r < seeds.size(); r++) q.load_ops(r, ops, &st);
+            for (int i = 0; i < 100; i++) q.loop_update();
+            ASSERT(q.verify());
+            bool moved = false;
+            for (auto &s : q.state_ref())
+                for (bool b : s) moved = moved || b;
+            ASSERT(moved);
+        }
+        // a model that moves by loop updates only (exchange terms, no cluster edges): Qmc::timestep with do_loop_updates
+        auto xxz = [](double d0, double d1, double x) {
+            std::vector<double> m(16, 0.0);
+            m[0] = m[15] = d0, m[5] = m[10] = d1, m[6] = m[9] = x;
+            return m;
+        };
+        qmcb::Qmc q(4, seeds, true);
+        q.make_interaction(xxz(0.4, 1.1, 0.8), {0, 1}), q.make_interaction(xxz(0.9, 0.5, 0.6), {1, 2});
+        q.make_interaction(xxz(0.3, 1.0, 1.0), {2, 3}), q.make_interaction(xxz(0.7, 0.7, 0.5), {3, 0});
+        auto e = q.timesteps(500, 1.2);
+        ASSERT(q.verify() && e.size() == seeds.size());
+        for (double x : e) ASSERT(x < 0.0);
+    }
     {  // error behaviour: status codes become exceptions, never aborts
         bool threw = false;
         try {
