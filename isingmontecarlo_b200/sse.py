@@ -105,6 +105,15 @@ class QmcIsingGraph:
         check(self._L.qmcb_set_mode(self._h, mode))
         self.mode = mode
 
+    def set_run_rvb(self, run_rvb):
+        """QmcIsingGraph::set_run_rvb (qmc_ising.rs:434-441).  The RVB update (rvb.rs) is not built (DESIGN.md section 0):
+        off -- the reference's default (:122) -- is accepted, on is refused."""
+        if run_rvb:
+            raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "the RVB update (rvb.rs:60-291) is not offered")
+
+    def single_rvb_sweep(self, updates_in_sweep=None):  # qmc_ising.rs:322-420
+        raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "the RVB update (rvb.rs:60-291) is not offered")
+
     def set_enable_heatbath(self, enable_heatbath):
         """qmc_ising.rs:444-486: heat-bath diagonal updates (heatbath.rs:149-209) for every replica."""
         check(self._L.qmcb_set_enable_heatbath(self._h, int(bool(enable_heatbath))))

@@ -360,5 +360,6 @@ def test_generic_qmc_interactions_bit_exact(mode):
     asym.make_interaction([0.5] * 4, [0]), asym.make_interaction([0.5] * 4, [1])
     with pytest.raises(QmcbError, match="Ising symmetry"):
         asym.timestep(1.0)
-    with pytest.raises(QmcbError, match="loop"):
-        Qmc(2, [1], 1.0).set_do_loop_updates(True)
+    lp = Qmc(2, [1], 1.0)  # loop updates are offered (tests/test_gpu_loop_update.py): the flag is Qmc::set_do_loop_updates
+    lp.set_do_loop_updates(True)
+    assert lp.should_do_loop_update()
