@@ -4,6 +4,7 @@
 //! spins and the operator string of every STRICT case of tests/golden/sse_golden.json -- the same fixtures
 //! `tests/test_golden.py` checks against the CUDA path.  Green here + green there = the CUDA path is bit-exact with the
 //! reference's own update path, and the "parity unpinned" label in DESIGN.md 6 can be dropped.
+//! A second test does the same for the generic `Qmc` runner with directed-loop updates (tests/golden/qmc_golden.json).
 //! SOURCE ONLY in this repository (no Rust toolchain in the build image); needs no GPU.
 use qmc::sse::*;
 use qmcb::PhiloxStream;
@@ -54,6 +55,42 @@ fn reference_reproduces_the_strict_golden_cases() {
             assert_eq!(format!("{:016x}", hash), rep["ops_fnv1a64"].as_str().unwrap(), "{} operator string", case["name"]);
             assert_eq!(e.to_bits(), python_hex_bits(rep["energy_hex"].as_str().unwrap()), "{} energy", case["name"]);
             assert!(g.verify());
+            checked += 1;
+        }
+    }
+    assert!(checked >= 12);
+}
+
+/// The generic runner with directed-loop updates: the real `qmc::sse::Qmc` (qmc_runner.rs:22-403, loop update
+/// directed_loop.rs:103-301) against tests/golden/qmc_golden.json -- the fixtures `tests/test_golden.py` checks against
+/// `qmcb_create_qmc` / `qmcb_loop_update` on the GPU.
+#[test]
+fn reference_reproduces_the_qmc_golden_cases() {
+    let path = concat!(env!("CARGO_MANIFEST_DIR"), "/../../tests/golden/qmc_golden.json");
+    let doc: Value = serde_json::from_str(&std::fs::read_to_string(path).unwrap()).unwrap();
+    let mut checked = 0;
+    for case in doc["cases"].as_array().unwrap() {
+        let nvars = case["nvars"].as_u64().unwrap() as usize;
+        let (beta, sweeps) = (case["beta"].as_f64().unwrap(), case["sweeps"].as_u64().unwrap() as usize);
+        for rep in case["replicas"].as_array().unwrap() {
+            let rng = PhiloxStream { key: rep["key"].as_u64().unwrap(), cursor: 0 };
+            // Qmc::new draws the state from the stream (qmc_runner.rs:48-51), as qmcb_create_qmc does with init_state = NULL
+            let mut q = DefaultQmc::<PhiloxStream>::new(nvars, rng, case["do_loop_updates"].as_bool().unwrap());
+            for it in case["interactions"].as_array().unwrap() {
+                let mat: Vec<f64> = it["mat"].as_array().unwrap().iter().map(|x| x.as_f64().unwrap()).collect();
+                let vars: Vec<usize> = it["vars"].as_array().unwrap().iter().map(|v| v.as_u64().unwrap() as usize).collect();
+                if it["diagonal"].as_bool().unwrap() { q.make_diagonal_interaction(mat, vars).unwrap(); } else { q.make_interaction(mat, vars).unwrap(); }
+            }
+            let e = q.timesteps(sweeps, beta);
+            assert_eq!(q.get_n() as u64, rep["n"].as_u64().unwrap(), "{} n", case["name"]);
+            assert_eq!(q.get_cutoff() as u64, rep["cutoff"].as_u64().unwrap(), "{} cutoff", case["name"]);
+            let state: String = q.state_ref().iter().map(|b| if *b { '1' } else { '0' }).collect();
+            assert_eq!(state, rep["state"].as_str().unwrap(), "{} state", case["name"]);
+            let m = q.get_manager_ref();
+            let words: Vec<u32> = (0..q.get_cutoff()).map(|p| op_word(m.get_pth(p))).collect();
+            let hash = fnv1a64(words.iter().flat_map(|w| w.to_le_bytes()));
+            assert_eq!(format!("{:016x}", hash), rep["ops_fnv1a64"].as_str().unwrap(), "{} operator string", case["name"]);
+            assert_eq!(e.to_bits(), python_hex_bits(rep["energy_hex"].as_str().unwrap()), "{} energy", case["name"]);
             checked += 1;
         }
     }
