@@ -636,9 +636,13 @@ __device__ void links_wl(const SseDev &D, uint32_t r, const Rep &V, int lane, ui
     for (uint32_t v = lane; v < D.N; v += 32) fill[v] = 0;
     __syncwarp();
     uint32_t first_p = NONE32, last_p = NONE32, first_site = NONE32;
+    // (both passes stream the operator string; the next line is requested before the current one is worked on, otherwise
+    // every step of every warp waits for one DRAM round trip)
+    uint32_t wnext = (uint32_t)lane < M ? V.ops[lane] : OP_EMPTY;
     for (uint32_t base = 0; base < M; base += 32) {  // pass A: legs per variable
         const uint32_t p = base + lane;
-        const uint32_t w = p < M ? V.ops[p] : OP_EMPTY;
+        const uint32_t w = wnext;
+        wnext = p + 32 < M ? V.ops[p + 32] : OP_EMPTY;
         int kind = -1;
         if (w != OP_EMPTY) {
             uint32_t v0, v1;
@@ -675,9 +679,11 @@ __device__ void links_wl(const SseDev &D, uint32_t r, const Rep &V, int lane, ui
         running += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
     __syncwarp();
+    wnext = (uint32_t)lane < M ? V.ops[lane] : OP_EMPTY;
     for (uint32_t base = 0; base < M; base += 32) {  // pass B: entries in p order
         const uint32_t p = base + lane;
-        const uint32_t w = p < M ? V.ops[p] : OP_EMPTY;
+        const uint32_t w = wnext;
+        wnext = p + 32 < M ? V.ops[p + 32] : OP_EMPTY;
         int kind = -1;
         uint32_t v0 = 0, v1 = 0;
         if (w != OP_EMPTY) {
@@ -924,10 +930,14 @@ __device__ uint32_t cluster_strict_wl(const SseDev &D, uint32_t r, const Rep &V,
     }
     __syncwarp();
     ST_MARK(2);
-    for (uint32_t p = lane; p <= last_p; p += 32) {  // apply (:139-167)
-        const uint32_t w = V.ops[p];
+    uint32_t wnext = (uint32_t)lane <= last_p ? V.ops[lane] : OP_EMPTY;
+    uint32_t enext = (uint32_t)lane <= last_p ? V.ent[lane] : 0u;  // (the entry of an empty slot is never looked at)
+    for (uint32_t p = lane; p <= last_p; p += 32) {  // apply (:139-167); the next line of ops and entry indices is requested first
+        const uint32_t w = wnext, ei = enext;
+        wnext = p + 32 <= last_p ? V.ops[p + 32] : OP_EMPTY;
+        enext = p + 32 <= last_p ? V.ent[p + 32] : 0u;
         if (w == OP_EMPTY) continue;
-        const uint4 e = V.wl[V.ent[p]];
+        const uint4 e = V.wl[ei];
         const uint32_t ci = e.z, co = e.w;
         const bool fi = (V.bits[ci >> 5] >> (ci & 31)) & 1u, fo = (V.bits[co >> 5] >> (co & 31)) & 1u;
         if (!(fi || fo)) continue;
