@@ -42,14 +42,20 @@
 #define CLS_SITE 32u
 #define CLS_LONG 33u
 
-__host__ __device__ inline size_t cnt_smem_bytes(uint32_t N, uint32_t Nw) { return (CT_VAR + ((size_t)4 * Nw + N) * 4 + 15) / 16 * 16; }
+// (+ 72 words when two warps share a replica: [2][32] final op words of a step, 8 words exchanged between the roles)
+__host__ __device__ inline size_t cnt_smem_bytes(uint32_t N, uint32_t Nw, bool pipe = false) { return (CT_VAR + ((size_t)4 * Nw + N + (pipe ? 72u : 0u)) * 4 + 15) / 16 * 16; }
 
 #ifndef QMCB_WPB
 #define QMCB_WPB 4
 #endif
 
-template <bool HAS_H, int MINB, bool MH, int PK>
-__global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
+// PIPE: two warps per replica, for batches that leave most of an SM empty (tempering ladders, big lattices: the sweep of
+// a long string is one dependent chain and nothing hides it there).  Role A runs the diagonal update of step k while role B
+// does the segment bookkeeping and the unions of step k - 1; the final op words of a step are handed over through a two-slot
+// ring in shared memory and the two warps meet at one named barrier per step.  B then does the closure and P2; P3 is split:
+// A applies the first half of the string, B the second (it knows how many site ops precede it from its own count).
+template <bool HAS_H, int MINB, bool MH, int PK, bool PIPE>
+__global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2 : 4 * MINB / QMCB_WPB)
     k_sse_counter(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin, uint8_t *samples,
                   uint64_t samples_per_rep, uint32_t smem_stride, uint32_t epk_off) {
     extern __shared__ __align__(16) unsigned char smem_all[];
@@ -59,7 +65,13 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
         __syncthreads();
     }
     const uint32_t *const epk_s = PK == 2 ? D.epk : (const uint32_t *)(smem_all + epk_off);
-    const uint32_t wib = __reduce_max_sync(FULL, threadIdx.x >> 5);  // warp-uniform by construction (uniform registers)
+    const uint32_t wraw = __reduce_max_sync(FULL, threadIdx.x >> 5);  // warp-uniform by construction (uniform registers)
+    const uint32_t wib = PIPE ? wraw >> 1 : wraw;
+    const bool roleA = !PIPE || (wraw & 1u) == 0, roleB = !PIPE || (wraw & 1u) == 1;
+#define PAIR_SYNC()                                                            \
+    do {                                                                       \
+        if (PIPE) asm volatile("bar.sync %0, 64;" ::"r"(wib + 1u) : "memory"); \
+    } while (0)
     unsigned char *const smem_raw = smem_all + wib * smem_stride;
     const int lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * QMCB_WPB + wib;
@@ -69,6 +81,8 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
     uint32_t *const s_fl = (uint32_t *)(smem_raw + CT_FL), *const s_line = (uint32_t *)(smem_raw + CT_LINE);
     uint32_t *const s_st = (uint32_t *)(smem_raw + CT_VAR), *const s_tb = s_st + Nw, *const s_cd = s_st + 2 * Nw, *const s_sb = s_st + 3 * Nw;
     uint32_t *const s_rep = s_st + 4 * Nw;
+    uint32_t *const hand = s_rep + N;                                   // PIPE: [2][32] final op words of a step
+    volatile uint32_t *const xchg = (volatile uint32_t *)(hand + 64);  // PIPE: n, cluster count, site ops before the second half
     uint32_t *ops = D.ops + (size_t)r * D.cap;
     uint32_t *sid = D.sid + (size_t)r * D.cap;
     uint32_t *gstate = D.state + (size_t)r * Nw;
@@ -113,8 +127,11 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
         uint64_t cur = D.cursor[r];
         const double bn = D.beta[r] * (double)Nb;  // diagonal.rs:168, left-to-right product
         const bool do_diag = phases & 1u, do_clus = phases & 2u;
-        for (uint32_t j = lane; j < Nw; j += 32) s_st[j] = gstate[j], s_cd[j] = 0, s_tb[j] = 0, s_sb[j] = 0;
-        if (PK) {
+        if (roleA)
+            for (uint32_t j = lane; j < Nw; j += 32) s_st[j] = gstate[j], s_cd[j] = 0;
+        if (roleB)
+            for (uint32_t j = lane; j < Nw; j += 32) s_tb[j] = 0, s_sb[j] = 0;
+        if (PK && roleA) {
             for (uint32_t c = lane; c < 36; c += 32) {
                 double wgt = 0.0;
                 if (c < 32) {
@@ -126,13 +143,14 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                 numtab[c] = num, rnumtab[c] = 1.0 / num;
             }
         }
-        if (do_clus) {
+        if (do_clus && roleB) {
             for (uint32_t v = lane; v < N; v += 32) s_rep[v] = v, st_cg(P + v, v);
             if (HAS_H)
                 for (uint32_t j = lane; j < (uint32_t)bstride; j += 32) st_cg(frz + j, 0u);
         }
         __syncwarp();
-        uint32_t nsite = 0;
+        PAIR_SYNC();
+        uint32_t nsite = 0, ks_half = 0;
         bool anylong = false, alltb = false;
         const uint64_t cdiag = cur;  // nonce of this diagonal step
         if (do_diag) cur += 1;
@@ -155,7 +173,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
         }
         __syncwarp();
 #else
-        if (M) fetch_line_pol(s_line, ops, lane, pol_stream);
+        if (M && roleA) fetch_line_pol(s_line, ops, lane, pol_stream);
 #endif
         // the slot's words: one Philox block per slot.  Independent of the operator string, so the block of step k + 1 is
         // computed at the end of step k, between issuing the step's union-find CAS and looking at its result.
@@ -166,9 +184,14 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
             wA = ((uint64_t)o.y << 32) | o.x, wB = ((uint64_t)o.w << 32) | o.z;
             pb = (uint32_t)__umul64hi(wA, (uint64_t)Nb);
         };
-        if (do_diag) draw((uint32_t)lane);
-        for (uint32_t it = 0; it < nit; it++) {
+        if (do_diag && roleA) draw((uint32_t)lane);
+        const uint32_t half_it = ((nit / 2 + 3) / 4) * 4;  // PIPE: P3 is split here (a multiple of its four-line iterations)
+        for (uint32_t it = 0; it < nit + (PIPE ? 1u : 0u); it++) {
             const uint32_t base = it * 32, p = base + lane;
+            uint32_t w = OP_EMPTY, neww = OP_EMPTY, v0 = 0, v1 = 0, fmask = 0, flipv = NONE32;  // flipv: the variable my off-diagonal op flips
+            int kind = -1;
+            bool changed = false;
+            if (roleA && it < nit) {
             const bool valid = p < M;
 #if QMCB_BULK_LINES
             const uint32_t tile = it / LPS, tl = it % LPS;
@@ -176,25 +199,23 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                 mbar_wait(bars + (tile & 1u), (phase_bits >> (tile & 1u)) & 1u);
                 phase_bits ^= 1u << (tile & 1u);
             }
-            uint32_t w = ring[((tile & 1u) * LPS + tl) * 32 + lane];
+            w = ring[((tile & 1u) * LPS + tl) * 32 + lane];
             if (!valid) w = OP_EMPTY;
             if (tl == LPS - 1 || it + 1 == nit) {  // the stage is consumed: refill it with the tile after next
                 __syncwarp();
                 if (lane == 0 && tile + 2 < ntile) issue_tile(tile + 2);
             }
 #else
-            uint32_t w = take_line(s_line, lane);
+            w = take_line(s_line, lane);
             if (!valid) w = OP_EMPTY;
             if (base + 32 < M) fetch_line_pol(s_line, ops + base + 32, lane, pol_stream);
 #endif
             const int type = !valid ? T_NONE : (w == OP_EMPTY ? T_EMPTY : (op_is_diag(w) ? T_DIAG : T_OFFD));
             // one decode for every lane: the op in the slot, or the op an empty slot proposes
             const uint32_t beff = w == OP_EMPTY ? pb : op_bond(w);
-            int kind = bkind<HAS_H>(D, beff);
-            uint32_t v0, v1, neww = w;
+            kind = bkind<HAS_H>(D, beff);
+            neww = w;
             const uint32_t ee = evars(beff, kind, v0, v1);
-            uint32_t fmask = 0, flipv = NONE32;  // off-diagonal ops of this step; the variable mine flips
-            bool changed = false;
 #ifdef QMCB_PREFETCH_PARENTS
             if (do_clus && w != OP_EMPTY && kind == KIND_BOND) {  // experiment: the parents the union stage will ask for, into L2
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(P + s_rep[v0]));
@@ -291,6 +312,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                 changed = neww != w;
             }
             if (neww == OP_EMPTY) kind = -1;  // no op in this slot after the diagonal update
+            }  // role A
             // what is left of the diagonal step (store, state flips) and the words of the next step do not depend on the
             // union-find: they run between the CAS and the look at its result
             auto step_tail = [&]() {
@@ -301,7 +323,26 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                 }
                 if (do_diag && it + 1 < nit) draw(base + 32u + (uint32_t)lane);
             };
-            if (do_clus) {
+            uint32_t pc = p, itc = it;  // the step the cluster bookkeeping works on
+            if (PIPE) {
+                if (roleA && it < nit) {
+                    hand[(it & 1u) * 32 + lane] = neww;
+                    step_tail();
+                }
+                pc = p - 32u, itc = it - 1u;
+                if (roleB) {  // role B works on the step role A finished one iteration ago
+                    kind = -1;
+                    if (it >= 1) {
+                        const uint32_t wf = hand[((it - 1u) & 1u) * 32 + lane];
+                        if (wf != OP_EMPTY) {
+                            kind = bkind<HAS_H>(D, op_bond(wf));
+                            evars(op_bond(wf), kind, v0, v1);
+                        }
+                    }
+                }
+            }
+            if (do_clus && roleB && (!PIPE || it >= 1)) {
+                if (PIPE && itc == half_it) ks_half = nsite;
                 // ---- segments and unions on the final ops of this step
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
                 const uint32_t myid = N + nsite + (uint32_t)__popc(smask & lt_mask);
@@ -334,7 +375,7 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                 }
                 __syncwarp();  // new ids are initialised before anyone follows them; bitmap reads are done
                 if (kind == KIND_SITE) atomicAnd(&s_sb[v0 >> 5], ~(1u << (v0 & 31)));
-                if (kind >= 0) st_cg_pol(sid + p, ra, pol_stream);  // P3 looks the input-side flip up through this id
+                if (kind >= 0) st_cg_pol(sid + pc, ra, pol_stream);  // P3 looks the input-side flip up through this id
                 uint32_t ua = 0, ub = 0, uold = 0;
                 bool casd = false;
                 if (kind == KIND_BOND && ra != rb) {
@@ -364,22 +405,33 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                     anylong = true;
                 }
                 if (kind == KIND_SITE) atomicMax(&s_rep[v0], myid);  // the site op with the highest lane owns the variable from here on (roots are minima: a cached root is below every id of this step)
-                step_tail();
+                if (!PIPE) step_tail();
                 if (casd && uold != ub) uf_union_pol(P, ua, ub, pol_keep);  // lost a race against a lane of this step: redo
                 nsite += (uint32_t)__popc(smask);
-                if (!alltb && (it & 31u) == 31u) {  // once every variable has an op the touched bits need no more updates
+                if (!alltb && (itc & 31u) == 31u) {  // once every variable has an op the touched bits need no more updates
                     uint32_t cnt = 0;
                     for (uint32_t j = lane; j < Nw; j += 32) cnt += (uint32_t)__popc(s_tb[j]);
                     alltb = __reduce_add_sync(FULL, cnt) == N;
                 }
                 __syncwarp();
-            } else step_tail();
+            } else if (!PIPE) step_tail();
+            PAIR_SYNC();
         }
-        if (do_diag && lane == 0) D.n[r] = n;
+        if (do_diag && roleA && lane == 0) D.n[r] = n;
+        if (PIPE) {  // role B needs n for the closure, role A the site ops before the second half for its share of P3
+            if (lane == 0) {
+                if (roleA) xchg[0] = n;
+                else xchg[2] = (half_it >= nit) ? nsite : ks_half;
+            }
+            PAIR_SYNC();
+            if (roleB) n = xchg[0];
+            ks_half = xchg[2];
+        }
 
         uint32_t ncl = 0;
         if (do_clus && n > 0) {
             const uint64_t c0 = cur;
+            if (roleB) {
             // periodic closure: the segment open at the end of variable v is the one crossing p = 0
             for (uint32_t v = lane; v < N; v += 32) {
                 const uint32_t rp = s_rep[v];
@@ -470,30 +522,38 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
             }
             untouched = __reduce_add_sync(FULL, untouched);
             ncl = nsite == 0 ? 1u : nroots - untouched;
+            }  // role B
             __threadfence_block();
             __syncwarp();
+            if (PIPE) {  // the flip bits are complete: both roles apply them
+                if (roleB && lane == 0) xchg[1] = ncl;
+                PAIR_SYNC();
+                ncl = xchg[1];
+            }
 
             // =========================== P3: apply the flips (stateless) ===========================
-            uint32_t ks = 0;
+            // PIPE: role A applies the slots before half_it * 32, role B the rest, starting from its own count of the site ops before them
+            const uint32_t p3_lo = (PIPE && !roleA) ? min(M, half_it * 32u) : 0u, p3_hi = (PIPE && roleA) ? min(M, half_it * 32u) : M;
+            uint32_t ks = (PIPE && !roleA) ? ks_half : 0u;
             const uint32_t EN = E + N;
             // software pipeline: the op words and records of the next four lines are requested before the flip bits of the
             // current four are looked up, so one iteration waits for one round trip (the gathers), not three
             uint32_t wN[4], sN[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t p = 32u * j + lane;
-                wN[j] = p < M ? ld_cg_pol(ops + p, pol_stream) : OP_EMPTY;
-                sN[j] = p < M ? ld_cg_pol(sid + p, pol_stream) : 0u;
+                const uint32_t p = p3_lo + 32u * j + lane;
+                wN[j] = p < p3_hi ? ld_cg_pol(ops + p, pol_stream) : OP_EMPTY;
+                sN[j] = p < p3_hi ? ld_cg_pol(sid + p, pol_stream) : 0u;
             }
-            for (uint32_t base = 0; base < M; base += 128) {
+            for (uint32_t base = p3_lo; base < p3_hi; base += 128) {
                 uint32_t w4[4], s4[4], sm4[4], di4[4], do4[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) w4[j] = wN[j], s4[j] = sN[j];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const uint32_t p = base + 128u + 32u * j + lane;
-                    wN[j] = p < M ? ld_cg_pol(ops + p, pol_stream) : OP_EMPTY;
-                    sN[j] = p < M ? ld_cg_pol(sid + p, pol_stream) : 0u;
+                    wN[j] = p < p3_hi ? ld_cg_pol(ops + p, pol_stream) : OP_EMPTY;
+                    sN[j] = p < p3_hi ? ld_cg_pol(sid + p, pol_stream) : 0u;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -526,11 +586,12 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
                 }
             }
             // spins: the segment of variable v crossing p = 0 has id v
-            for (uint32_t j = lane; j < Nw; j += 32) s_st[j] ^= ld_cg(decb + j) & s_tb[j];
+            if (roleA)
+                for (uint32_t j = lane; j < Nw; j += 32) s_st[j] ^= ld_cg(decb + j) & s_tb[j];
             cur = c0 + 1;
             __syncwarp();
         }
-        if (do_clus) {
+        if (do_clus && roleA) {
             // free spins: qmc_ising.rs:780-784
             for (uint32_t base = 0; base < N; base += 32) {
                 const uint32_t v = base + lane;
@@ -545,8 +606,9 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
             __syncwarp();
             if (lane == 0) D.ncl[r] = ncl;
         }
-        for (uint32_t j = lane; j < Nw; j += 32) gstate[j] = s_st[j];
-        if (lane == 0) {
+        if (roleA)
+            for (uint32_t j = lane; j < Nw; j += 32) gstate[j] = s_st[j];
+        if (lane == 0 && roleA) {
             D.cursor[r] = cur;
             if (phases & 4u) {
                 const uint32_t grown = n + n / 2;  // qmc_ising.rs:786
@@ -556,19 +618,21 @@ __global__ void __launch_bounds__(32 * QMCB_WPB, 4 * MINB / QMCB_WPB)
         if (phases & 8u) {
             done++;
             const uint64_t idx = done - sample_origin;
-            if (lane == 0) D.vupd[r] += n;
-            if (idx % sample_freq == 0) {
+            if (lane == 0 && roleA) D.vupd[r] += n;
+            if (idx % sample_freq == 0 && roleA) {
                 if (lane == 0) D.sum_n[r] += n;
                 if (samples) {
                     uint8_t *dst = samples + ((size_t)r * samples_per_rep + (idx / sample_freq - 1)) * N;
                     for (uint32_t v = lane; v < N; v += 32) dst[v] = (uint8_t)state_bit(s_st, v);
                 }
             }
-            if (lane == 0) D.done[r] = done;
+            if (lane == 0 && roleA) D.done[r] = done;
         }
         __syncwarp();
+        PAIR_SYNC();  // role B reads n, the cursor and the cutoff of the next sweep after role A wrote them
     }
     if (err) atomicOr(D.status, err);
+#undef PAIR_SYNC
 }
 
 // returns the number of kernel launches, or -1 if this shape is not supported by the warp kernels
@@ -596,16 +660,20 @@ int launch_sse_counter(const SseDev &D, const SseTuning &T, uint64_t target, uin
         if (with >= 1 && with >= std::min<size_t>(without, 4)) epk_bytes = want;
     }
     const int pk = !have_epk ? 0 : (epk_bytes ? 1 : 2);
+    // two warps per replica (PIPE) when at most two blocks of four replicas per SM are wanted and fit
+    const size_t smem_p = cnt_smem_bytes(D.N, D.Nw, true);
+    const bool pipe = minb == 4 && T.pipe && wanted <= 2 && (size_t)(227 * 1024) / (smem_p * QMCB_WPB + epk_bytes + 1024) >= wanted;
+    const size_t smem_used = pipe ? smem_p : smem;
     Kern kern;
-#define PICKC(MINB_, MH_)                                                                                             \
-    switch (pk) {                                                                                                     \
-        case 1: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 1> : k_sse_counter<false, MINB_, MH_, 1>; break;     \
-        case 2: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 2> : k_sse_counter<false, MINB_, MH_, 2>; break;     \
-        default: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 0> : k_sse_counter<false, MINB_, MH_, 0>; break;    \
+#define PICKC(MINB_, MH_, PIPE_)                                                                                                    \
+    switch (pk) {                                                                                                                   \
+        case 1: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 1, PIPE_> : k_sse_counter<false, MINB_, MH_, 1, PIPE_>; break;     \
+        case 2: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 2, PIPE_> : k_sse_counter<false, MINB_, MH_, 2, PIPE_>; break;     \
+        default: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 0, PIPE_> : k_sse_counter<false, MINB_, MH_, 0, PIPE_>; break;    \
     }
     if (D.ham) {
-        if (minb == 4) { PICKC(4, true) } else { PICKC(7, true) }
-    } else if (minb == 4) { PICKC(4, false) } else { PICKC(7, false) }
+        if (pipe) { PICKC(4, true, true) } else if (minb == 4) { PICKC(4, true, false) } else { PICKC(7, true, false) }
+    } else if (pipe) { PICKC(4, false, true) } else if (minb == 4) { PICKC(4, false, false) } else { PICKC(7, false, false) }
 #undef PICKC
     {
         static std::mutex mu;
@@ -619,9 +687,9 @@ int launch_sse_counter(const SseDev &D, const SseTuning &T, uint64_t target, uin
             cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, T.carveout);
         done[{(const void *)kern, dev}] = T.carveout;
     }
-    size_t dyn = smem * QMCB_WPB + epk_bytes + (size_t)std::max(T.pad, 0);
+    size_t dyn = smem_used * QMCB_WPB + epk_bytes + (size_t)std::max(T.pad, 0);
     if (dyn > 227 * 1024) dyn = 227 * 1024;
-    kern<<<blocks, 32 * QMCB_WPB, dyn, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem,
-                                            epk_bytes ? (uint32_t)(smem * QMCB_WPB) : 0u);
+    kern<<<blocks, (pipe ? 64 : 32) * QMCB_WPB, dyn, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem_used,
+                                                          epk_bytes ? (uint32_t)(smem_used * QMCB_WPB) : 0u);
     return 1;
 }

@@ -89,8 +89,9 @@ def test_small_beta_regime_takes_the_division_path():
             assert same(g, r, ref), (chunk, r)
 
 
-@pytest.mark.parametrize("minblocks,shared_edges", [(7, 1), (7, 0), (4, 0), (4, 1)])
-def test_every_kernel_build_is_bit_exact(minblocks, shared_edges):
+@pytest.mark.parametrize("minblocks,shared_edges,pipeline", [(7, 1, 1), (7, 0, 1), (4, 0, 1), (4, 1, 1), (4, 0, 0), (4, 1, 0)])
+def test_every_kernel_build_is_bit_exact(minblocks, shared_edges, pipeline):
+    # minblocks 4 with the pipeline on is the two-warps-per-replica build (small batches pick it by themselves)
     from isingmontecarlo_b200.sse import QmcIsingGraph
 
     edges = lattices.square_periodic(32, -1.0)
@@ -98,6 +99,7 @@ def test_every_kernel_build_is_bit_exact(minblocks, shared_edges):
     g = QmcIsingGraph(edges, 3.04, 0.0, 1024, 0x0B100000 + np.arange(R, dtype=np.uint64), 8.0, mode=MODE_COUNTER)
     g.set_option("minblocks", minblocks)
     g.set_option("shared_edge_table", shared_edges)
+    g.set_option("pipeline", pipeline)
     g.timesteps(30, 8.0)
     refs = {r: to_oracle(g, r, edges, 3.04, 0.0) for r in (0, 5, R - 1)}
     e = g.timesteps(3, 8.0)
@@ -217,4 +219,36 @@ def test_production_shape_two_warp_build():
         e_ref = ref.timesteps(20, 16.0, MODE_FAST)
         assert ref.error == 0 and same(g, r, ref), r
         assert e[r] == e_ref
+    assert all(g.verify(r) for r in range(0, R, 16))
+
+
+@pytest.mark.parametrize("h,R", [(0.0, 512), (0.3, 300)])
+def test_production_shape_two_warp_counter_build(h, R):
+    """Few replicas (at most two blocks of four per SM): the COUNTER launcher picks the two-warps-per-replica build -- role A
+    the diagonal update of step k, role B segments and unions of step k - 1, P3 split in halves -- with and without a
+    longitudinal field; sweeps in one launch and one by one; against the oracle from the thermalised state, and against
+    the one-warp build of the same kernel."""
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.square_periodic(32, -1.0)
+    keys = 0x55E10000 + np.arange(R, dtype=np.uint64)
+    g = QmcIsingGraph(edges, 3.04, h, 1024, keys, 8.0, mode=MODE_COUNTER)
+    one = QmcIsingGraph(edges, 3.04, h, 1024, keys, 8.0, mode=MODE_COUNTER)
+    one.set_option("pipeline", 0)
+    g.timesteps(30, 8.0), one.timesteps(30, 8.0)
+    picks = sorted(int(x) for x in np.random.default_rng(44).choice(R, size=6, replace=False))
+    refs = {r: to_oracle(g, r, edges, 3.04, h) for r in picks}
+    e = g.timesteps(8, 8.0)
+    for _ in range(3):
+        g.timesteps(1, 8.0)
+    eo = one.timesteps(11, 8.0)
+    for r, ref in refs.items():
+        e_ref = ref.timesteps(8, 8.0, MODE_COUNTER)
+        assert e[r] == e_ref
+        ref.timesteps(3, 8.0, MODE_COUNTER)
+        assert ref.error == 0 and same(g, r, ref), r
+    assert np.array_equal(g.state_ref(), one.state_ref()) and np.array_equal(g.get_n(), one.get_n())
+    assert np.array_equal(g.rng_cursors(), one.rng_cursors()) and np.array_equal(g.get_cutoff(), one.get_cutoff())
+    for r in picks:
+        assert np.array_equal(g.dump_ops(r), one.dump_ops(r))
     assert all(g.verify(r) for r in range(0, R, 16))
