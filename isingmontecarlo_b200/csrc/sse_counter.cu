@@ -43,7 +43,8 @@
 #define CLS_LONG 33u
 
 // (+ 72 words when two warps share a replica: [2][32] final op words of a step, 8 words exchanged between the roles)
-__host__ __device__ inline size_t cnt_smem_bytes(uint32_t N, uint32_t Nw, bool pipe = false) { return (CT_VAR + ((size_t)4 * Nw + N + (pipe ? 72u : 0u)) * 4 + 15) / 16 * 16; }
+// (three roles: + [2][3][32] words of the unions role B hands to role C)
+__host__ __device__ inline size_t cnt_smem_bytes(uint32_t N, uint32_t Nw, int pipe = 0) { return (CT_VAR + ((size_t)4 * Nw + N + (pipe ? 72u : 0u) + (pipe == 3 ? 192u : 0u)) * 4 + 15) / 16 * 16; }
 
 #ifndef QMCB_WPB
 #define QMCB_WPB 4
@@ -54,8 +55,12 @@ __host__ __device__ inline size_t cnt_smem_bytes(uint32_t N, uint32_t Nw, bool p
 // does the segment bookkeeping and the unions of step k - 1; the final op words of a step are handed over through a two-slot
 // ring in shared memory and the two warps meet at one named barrier per step.  B then does the closure and P2; P3 is split:
 // A applies the first half of the string, B the second (it knows how many site ops precede it from its own count).
-template <bool HAS_H, int MINB, bool MH, int PK, bool PIPE>
-__global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2 : 4 * MINB / QMCB_WPB)
+// PIPE = 3: a third warp (role C) takes the union-find of step k - 2 off role B: the climbs and the CAS are dependent L2
+// round trips, and with two roles B was the longer half by a factor of two (role A spent half its time at the barrier).
+// B hands C one (member of set a, member of set b, variables + flags) triple per lane; C hooks the roots and caches them in
+// the per-variable table with the same CAS as before, so a stale entry is never overwritten.  P3 is split in thirds.
+template <bool HAS_H, int MINB, bool MH, int PK, int PIPE>
+__global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2 : 4 * MINB / QMCB_WPB)
     k_sse_counter(SseDev D, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin, uint8_t *samples,
                   uint64_t samples_per_rep, uint32_t smem_stride, uint32_t epk_off) {
     extern __shared__ __align__(16) unsigned char smem_all[];
@@ -66,11 +71,12 @@ __global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2
     }
     const uint32_t *const epk_s = PK == 2 ? D.epk : (const uint32_t *)(smem_all + epk_off);
     const uint32_t wraw = __reduce_max_sync(FULL, threadIdx.x >> 5);  // warp-uniform by construction (uniform registers)
-    const uint32_t wib = PIPE ? wraw >> 1 : wraw;
-    const bool roleA = !PIPE || (wraw & 1u) == 0, roleB = !PIPE || (wraw & 1u) == 1;
+    const uint32_t wib = PIPE ? wraw / (uint32_t)(PIPE ? PIPE : 1) : wraw;
+    const uint32_t role = PIPE ? wraw - wib * (uint32_t)PIPE : 0u;
+    const bool roleA = !PIPE || role == 0, roleB = !PIPE || role == 1, roleC = PIPE == 3 && role == 2;
 #define PAIR_SYNC()                                                            \
     do {                                                                       \
-        if (PIPE) asm volatile("bar.sync %0, 64;" ::"r"(wib + 1u) : "memory"); \
+        if (PIPE) asm volatile("bar.sync %0, %1;" ::"r"(wib + 1u), "n"(PIPE ? 32 * PIPE : 32) : "memory"); \
     } while (0)
     unsigned char *const smem_raw = smem_all + wib * smem_stride;
     const int lane = threadIdx.x & 31;
@@ -82,7 +88,8 @@ __global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2
     uint32_t *const s_st = (uint32_t *)(smem_raw + CT_VAR), *const s_tb = s_st + Nw, *const s_cd = s_st + 2 * Nw, *const s_sb = s_st + 3 * Nw;
     uint32_t *const s_rep = s_st + 4 * Nw;
     uint32_t *const hand = s_rep + N;                                   // PIPE: [2][32] final op words of a step
-    volatile uint32_t *const xchg = (volatile uint32_t *)(hand + 64);  // PIPE: n, cluster count, site ops before the second half
+    volatile uint32_t *const xchg = (volatile uint32_t *)(hand + 64);  // PIPE: n, cluster count, site ops before the later parts of P3
+    uint32_t *const un = hand + 72;                                     // PIPE 3: [2][3][32] unions of a step, role B -> role C
     uint32_t *ops = D.ops + (size_t)r * D.cap;
     uint32_t *sid = D.sid + (size_t)r * D.cap;
     uint32_t *gstate = D.state + (size_t)r * Nw;
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2
         }
         __syncwarp();
         PAIR_SYNC();
-        uint32_t nsite = 0, ks_half = 0;
+        uint32_t nsite = 0, ks_half = 0, ks_third = 0;
         bool anylong = false, alltb = false;
         const uint64_t cdiag = cur;  // nonce of this diagonal step
         if (do_diag) cur += 1;
@@ -185,8 +192,11 @@ __global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2
             pb = (uint32_t)__umul64hi(wA, (uint64_t)Nb);
         };
         if (do_diag && roleA) draw((uint32_t)lane);
-        const uint32_t half_it = ((nit / 2 + 3) / 4) * 4;  // PIPE: P3 is split here (a multiple of its four-line iterations)
-        for (uint32_t it = 0; it < nit + (PIPE ? 1u : 0u); it++) {
+        // PIPE: P3 is split at these steps (multiples of its four-line iterations): two roles [0, half) [half, end), three roles
+        // [0, half) [half, third) [third, end)
+        const uint32_t half_it = PIPE == 3 ? ((nit / 3 + 3) / 4) * 4 : ((nit / 2 + 3) / 4) * 4;
+        const uint32_t third_it = PIPE == 3 ? min(nit, ((2 * nit / 3 + 3) / 4) * 4) : nit;
+        for (uint32_t it = 0; it < nit + (PIPE ? (uint32_t)PIPE - 1u : 0u); it++) {
             const uint32_t base = it * 32, p = base + lane;
             uint32_t w = OP_EMPTY, neww = OP_EMPTY, v0 = 0, v1 = 0, fmask = 0, flipv = NONE32;  // flipv: the variable my off-diagonal op flips
             int kind = -1;
@@ -341,8 +351,34 @@ __global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2
                     }
                 }
             }
-            if (do_clus && roleB && (!PIPE || it >= 1)) {
+            if (PIPE == 3 && roleC && do_clus && it >= 2) {  // role C: the unions of step it - 2
+                const uint32_t *u = un + ((it - 2u) & 1u) * 96;
+                const uint32_t meta = u[64 + lane];
+                if (meta >> 30) {
+                    const uint32_t ra = u[lane], rb = u[32 + lane], cv0 = meta & 0x3FFFu, cv1 = (meta >> 14) & 0x3FFFu;
+                    uint32_t a = ra, b = rb;
+                    uint32_t pa = ld_cg_pol(P + a, pol_keep), pq = ld_cg_pol(P + b, pol_keep);
+                    const uint32_t pa0 = pa, pq0 = pq;
+                    while (pa != a || pq != b) {
+                        a = pa, b = pq;
+                        pa = ld_cg_pol(P + a, pol_keep), pq = ld_cg_pol(P + b, pol_keep);
+                    }
+                    if (pa0 != a) st_cg_pol(P + ra, a, pol_keep);  // a stale value is still an ancestor
+                    if (pq0 != b) st_cg_pol(P + rb, b, pol_keep);
+                    if (a != b) {
+                        if (a > b) {
+                            const uint32_t t = a;
+                            a = b, b = t;
+                        }
+                        if (atomicCAS(P + b, b, a) != b) uf_union_pol(P, a, b, pol_keep);  // lost a race against a lane of this step: redo
+                    }
+                    if ((meta >> 28) & 1u) atomicCAS(&s_rep[cv0], ra, a);  // cache the root (only over the entry the segment stage read)
+                    if ((meta >> 29) & 1u) atomicCAS(&s_rep[cv1], rb, a);
+                }
+            }
+            if (do_clus && roleB && (!PIPE || (it >= 1 && it <= nit))) {
                 if (PIPE && itc == half_it) ks_half = nsite;
+                if (PIPE == 3 && itc == third_it) ks_third = nsite;
                 // ---- segments and unions on the final ops of this step
                 const uint32_t smask = __ballot_sync(FULL, kind == KIND_SITE);
                 const uint32_t myid = N + nsite + (uint32_t)__popc(smask & lt_mask);
@@ -378,7 +414,12 @@ __global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2
                 if (kind >= 0) st_cg_pol(sid + pc, ra, pol_stream);  // P3 looks the input-side flip up through this id
                 uint32_t ua = 0, ub = 0, uold = 0;
                 bool casd = false;
-                if (kind == KIND_BOND && ra != rb) {
+                if (PIPE == 3) {  // the unions of this step go to role C
+                    uint32_t *u = un + (itc & 1u) * 96;
+                    const bool dou = kind == KIND_BOND && ra != rb;
+                    u[lane] = ra, u[32 + lane] = rb;
+                    u[64 + lane] = v0 | (v1 << 14) | (fa ? 1u << 28 : 0u) | (fb ? 1u << 29 : 0u) | (dou ? 1u << 30 : 0u);
+                } else if (kind == KIND_BOND && ra != rb) {
                     // lock-free min-root union (sse_warp.cuh uf_union_pol), split: climb, hook with a CAS -- and look at
                     // the CAS result only after the independent tail of the step (a lost race is redone there)
                     uint32_t a = ra, b = rb;
@@ -418,14 +459,14 @@ __global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2
             PAIR_SYNC();
         }
         if (do_diag && roleA && lane == 0) D.n[r] = n;
-        if (PIPE) {  // role B needs n for the closure, role A the site ops before the second half for its share of P3
+        if (PIPE) {  // role B needs n for the closure, the others the site ops before their share of P3
             if (lane == 0) {
                 if (roleA) xchg[0] = n;
-                else xchg[2] = (half_it >= nit) ? nsite : ks_half;
+                if (roleB) xchg[2] = (half_it >= nit) ? nsite : ks_half, xchg[3] = (third_it >= nit) ? nsite : ks_third;
             }
             PAIR_SYNC();
-            if (roleB) n = xchg[0];
-            ks_half = xchg[2];
+            n = xchg[0];
+            ks_half = xchg[2], ks_third = xchg[3];
         }
 
         uint32_t ncl = 0;
@@ -533,8 +574,9 @@ __global__ void __launch_bounds__(PIPE ? 64 * QMCB_WPB : 32 * QMCB_WPB, PIPE ? 2
 
             // =========================== P3: apply the flips (stateless) ===========================
             // PIPE: role A applies the slots before half_it * 32, role B the rest, starting from its own count of the site ops before them
-            const uint32_t p3_lo = (PIPE && !roleA) ? min(M, half_it * 32u) : 0u, p3_hi = (PIPE && roleA) ? min(M, half_it * 32u) : M;
-            uint32_t ks = (PIPE && !roleA) ? ks_half : 0u;
+            const uint32_t cut1 = min(M, half_it * 32u), cut2 = PIPE == 3 ? max(cut1, min(M, third_it * 32u)) : M;
+            const uint32_t p3_lo = !PIPE || roleA ? 0u : (roleB ? cut1 : cut2), p3_hi = !PIPE ? M : (roleA ? cut1 : (roleB ? cut2 : M));
+            uint32_t ks = !PIPE || roleA ? 0u : (roleB ? ks_half : ks_third);
             const uint32_t EN = E + N;
             // software pipeline: the op words and records of the next four lines are requested before the flip bits of the
             // current four are looked up, so one iteration waits for one round trip (the gathers), not three
@@ -661,9 +703,14 @@ int launch_sse_counter(const SseDev &D, const SseTuning &T, uint64_t target, uin
     }
     const int pk = !have_epk ? 0 : (epk_bytes ? 1 : 2);
     // two warps per replica (PIPE) when at most two blocks of four replicas per SM are wanted and fit
-    const size_t smem_p = cnt_smem_bytes(D.N, D.Nw, true);
-    const bool pipe = minb == 4 && T.pipe && wanted <= 2 && (size_t)(227 * 1024) / (smem_p * QMCB_WPB + epk_bytes + 1024) >= wanted;
-    const size_t smem_used = pipe ? smem_p : smem;
+    // (T.pipe: 0 never, 1 three roles if they fit else two, 2 two roles)
+    const size_t smem_p2 = cnt_smem_bytes(D.N, D.Nw, 2), smem_p3 = cnt_smem_bytes(D.N, D.Nw, 3);
+    int pipe = 0;
+    if (minb == 4 && T.pipe && wanted <= 2) {
+        if (T.pipe != 2 && D.N <= 16384 && (size_t)(227 * 1024) / (smem_p3 * QMCB_WPB + epk_bytes + 1024) >= wanted) pipe = 3;
+        else if ((size_t)(227 * 1024) / (smem_p2 * QMCB_WPB + epk_bytes + 1024) >= wanted) pipe = 2;
+    }
+    const size_t smem_used = pipe == 3 ? smem_p3 : (pipe == 2 ? smem_p2 : smem);
     Kern kern;
 #define PICKC(MINB_, MH_, PIPE_)                                                                                                    \
     switch (pk) {                                                                                                                   \
@@ -672,8 +719,8 @@ int launch_sse_counter(const SseDev &D, const SseTuning &T, uint64_t target, uin
         default: kern = D.has_h ? k_sse_counter<true, MINB_, MH_, 0, PIPE_> : k_sse_counter<false, MINB_, MH_, 0, PIPE_>; break;    \
     }
     if (D.ham) {
-        if (pipe) { PICKC(4, true, true) } else if (minb == 4) { PICKC(4, true, false) } else { PICKC(7, true, false) }
-    } else if (pipe) { PICKC(4, false, true) } else if (minb == 4) { PICKC(4, false, false) } else { PICKC(7, false, false) }
+        if (pipe == 3) { PICKC(4, true, 3) } else if (pipe == 2) { PICKC(4, true, 2) } else if (minb == 4) { PICKC(4, true, 0) } else { PICKC(7, true, 0) }
+    } else if (pipe == 3) { PICKC(4, false, 3) } else if (pipe == 2) { PICKC(4, false, 2) } else if (minb == 4) { PICKC(4, false, 0) } else { PICKC(7, false, 0) }
 #undef PICKC
     {
         static std::mutex mu;
@@ -689,7 +736,7 @@ int launch_sse_counter(const SseDev &D, const SseTuning &T, uint64_t target, uin
     }
     size_t dyn = smem_used * QMCB_WPB + epk_bytes + (size_t)std::max(T.pad, 0);
     if (dyn > 227 * 1024) dyn = 227 * 1024;
-    kern<<<blocks, (pipe ? 64 : 32) * QMCB_WPB, dyn, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem_used,
+    kern<<<blocks, (pipe ? 32 * pipe : 32) * QMCB_WPB, dyn, st>>>(D, target, phases, sample_freq, sample_origin, samples, samples_per_rep, (uint32_t)smem_used,
                                                           epk_bytes ? (uint32_t)(smem_used * QMCB_WPB) : 0u);
     return 1;
 }

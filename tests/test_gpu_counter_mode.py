@@ -89,9 +89,9 @@ def test_small_beta_regime_takes_the_division_path():
             assert same(g, r, ref), (chunk, r)
 
 
-@pytest.mark.parametrize("minblocks,shared_edges,pipeline", [(7, 1, 1), (7, 0, 1), (4, 0, 1), (4, 1, 1), (4, 0, 0), (4, 1, 0)])
+@pytest.mark.parametrize("minblocks,shared_edges,pipeline", [(7, 1, 1), (7, 0, 1), (4, 0, 1), (4, 1, 1), (4, 0, 2), (4, 1, 2), (4, 0, 0), (4, 1, 0)])
 def test_every_kernel_build_is_bit_exact(minblocks, shared_edges, pipeline):
-    # minblocks 4 with the pipeline on is the two-warps-per-replica build (small batches pick it by themselves)
+    # minblocks 4 with the pipeline on: three warps per replica (1) or two (2); small batches pick it by themselves
     from isingmontecarlo_b200.sse import QmcIsingGraph
 
     edges = lattices.square_periodic(32, -1.0)
@@ -222,8 +222,8 @@ def test_production_shape_two_warp_build():
     assert all(g.verify(r) for r in range(0, R, 16))
 
 
-@pytest.mark.parametrize("h,R", [(0.0, 512), (0.3, 300)])
-def test_production_shape_two_warp_counter_build(h, R):
+@pytest.mark.parametrize("h,R,pipeline", [(0.0, 512, 1), (0.3, 300, 1), (0.0, 512, 2), (0.3, 300, 2)])
+def test_production_shape_two_warp_counter_build(h, R, pipeline):
     """Few replicas (at most two blocks of four per SM): the COUNTER launcher picks the two-warps-per-replica build -- role A
     the diagonal update of step k, role B segments and unions of step k - 1, P3 split in halves -- with and without a
     longitudinal field; sweeps in one launch and one by one; against the oracle from the thermalised state, and against
@@ -233,6 +233,7 @@ def test_production_shape_two_warp_counter_build(h, R):
     edges = lattices.square_periodic(32, -1.0)
     keys = 0x55E10000 + np.arange(R, dtype=np.uint64)
     g = QmcIsingGraph(edges, 3.04, h, 1024, keys, 8.0, mode=MODE_COUNTER)
+    g.set_option("pipeline", pipeline)  # 1: role C takes the union-find as well; 2: two roles
     one = QmcIsingGraph(edges, 3.04, h, 1024, keys, 8.0, mode=MODE_COUNTER)
     one.set_option("pipeline", 0)
     g.timesteps(30, 8.0), one.timesteps(30, 8.0)
