@@ -197,6 +197,73 @@ impl BatchedQmcStepper for BatchedQmcIsingGraph {
 }
 impl Drop for BatchedQmcIsingGraph { fn drop(&mut self) { unsafe { sys::qmcb_destroy(self.h); } } }
 
+/// `qmc::sse::Qmc` (qmc_runner.rs:22-403) for a batch of replicas: interactions are collected with the reference's
+/// `make_interaction*` calls (matrices in `Interaction::at` indexing) and the batch is built by `build()`; every
+/// `BatchedQmcStepper` method then works on `graph_mut()`.  `loop_update` / `set_do_loop_updates` are the directed-loop
+/// update of directed_loop.rs:103-301 (STRICT mode).
+pub struct BatchedQmc { nvars: usize, keys: Vec<u64>, state: Option<Vec<bool>>, do_loop_updates: bool, offset: f64, cutoff: usize,
+                        nv: Vec<u32>, vars: Vec<u32>, mat_len: Vec<u32>, mats: Vec<f64>, graph: Option<BatchedQmcIsingGraph> }
+
+impl BatchedQmc {
+    /// Qmc::new / new_with_state (qmc_runner.rs:48-87): cutoff = nvars, one Philox key per replica
+    pub fn new(nvars: usize, rng_keys: &[u64], do_loop_updates: bool, state: Option<Vec<bool>>) -> Self {
+        Self { nvars, keys: rng_keys.to_vec(), state, do_loop_updates, offset: 0.0, cutoff: nvars, nv: vec![], vars: vec![], mat_len: vec![],
+               mats: vec![], graph: None }
+    }
+    fn add(&mut self, mut mat: Vec<f64>, vars: &[usize], diagonal: bool, and_offset: bool) -> Result<(), String> {
+        if self.graph.is_some() { return Err("interactions are fixed once the batch has been built".into()); }
+        let (n, tn) = (vars.len(), 1usize << vars.len());
+        if n == 0 || n > 2 || mat.len() != if diagonal { tn } else { tn * tn } { return Err(format!("Given {} vars, matrix of {} entries", n, mat.len())); }
+        if and_offset {  // Interaction::new_offset :508-521 / new_diagonal_offset :424-436
+            let stride = if diagonal { 1 } else { tn + 1 };
+            let lo = (0..tn).map(|k| mat[k * stride]).fold(f64::MAX, f64::min);
+            (0..tn).for_each(|k| mat[k * stride] -= lo);
+            self.offset -= lo;
+        }
+        if !diagonal && mat.iter().any(|x| *x < 0.0) { return Err("Interaction contains negative weights".into()); }
+        self.nv.push(n as u32);
+        self.vars.push(vars[0] as u32);
+        self.vars.push(if n > 1 { vars[1] as u32 } else { 0 });
+        self.mat_len.push(mat.len() as u32);
+        self.mats.extend(mat);
+        Ok(())
+    }
+    pub fn make_interaction(&mut self, mat: Vec<f64>, vars: Vec<usize>) -> Result<(), String> { self.add(mat, &vars, false, false) }            // :113-122
+    pub fn make_interaction_and_offset(&mut self, mat: Vec<f64>, vars: Vec<usize>) -> Result<(), String> { self.add(mat, &vars, false, true) }   // :125-135
+    pub fn make_diagonal_interaction(&mut self, mat: Vec<f64>, vars: Vec<usize>) -> Result<(), String> { self.add(mat, &vars, true, false) }     // :138-146
+    pub fn make_diagonal_interaction_and_offset(&mut self, mat: Vec<f64>, vars: Vec<usize>) -> Result<(), String> { self.add(mat, &vars, true, true) }  // :149-156
+    pub fn increase_cutoff_to(&mut self, cutoff: usize) { self.cutoff = self.cutoff.max(cutoff); }  // :307-309, before build()
+    pub fn get_offset(&self) -> f64 { self.offset }
+    /// qmcb_create_qmc: from here on the interactions are fixed
+    pub fn build(&mut self, betas: &[f64], mode: Mode, device: i32) -> Result<&mut BatchedQmcIsingGraph, String> {
+        if self.graph.is_none() {
+            let ints = sys::QmcbInteractions { nvars: self.nvars as u32, n_interactions: self.nv.len() as u32, nv: self.nv.as_ptr(), vars: self.vars.as_ptr(),
+                                               mat_len: self.mat_len.as_ptr(), mats: self.mats.as_ptr(), offset: self.offset,
+                                               do_loop_updates: self.do_loop_updates as i32 };
+            let init: Option<Vec<u8>> = self.state.as_ref().map(|s| (0..self.keys.len()).flat_map(|_| s.iter().map(|b| *b as u8)).collect());
+            let mut h = std::ptr::null_mut();
+            check(unsafe { sys::qmcb_create_qmc(&ints, self.keys.len() as u32, betas.as_ptr(), self.keys.as_ptr(), self.cutoff as u64, 0,
+                                                init.as_ref().map_or(std::ptr::null(), |v| v.as_ptr()), device, &mut h) })?;
+            let g = BatchedQmcIsingGraph { h, nvars: self.nvars, replicas: self.keys.len(), offset: self.offset };
+            check(unsafe { sys::qmcb_set_mode(g.h, mode as i32) })?;
+            self.graph = Some(g);
+        }
+        Ok(self.graph.as_mut().unwrap())
+    }
+    pub fn graph_mut(&mut self) -> Option<&mut BatchedQmcIsingGraph> { self.graph.as_mut() }
+    /// Qmc::loop_update (qmc_runner.rs:205-220): one directed-loop update of every replica
+    pub fn loop_update(&mut self) -> Result<(), String> {
+        let g = self.graph.as_ref().ok_or("build() first")?;
+        check(unsafe { sys::qmcb_loop_update(g.h) })
+    }
+    /// Qmc::set_do_loop_updates / should_do_loop_update (qmc_runner.rs:268-275)
+    pub fn set_do_loop_updates(&mut self, do_loop_updates: bool) -> Result<(), String> {
+        self.do_loop_updates = do_loop_updates;
+        match self.graph.as_ref() { Some(g) => check(unsafe { sys::qmcb_set_do_loop_updates(g.h, do_loop_updates as i32) }), None => Ok(()) }
+    }
+    pub fn should_do_loop_update(&self) -> bool { self.do_loop_updates }
+}
+
 /// `TemperingContainer` (tempering_container.rs:19-302; parallel variants :316-478) over one handle per rank:
 /// `n_chains` independent ladders of `betas.len()` slots.  `add_qmc_stepper` is replaced by giving the ladder at
 /// construction (all slots share one lattice, so `can_swap_graphs` holds; unequal Hamiltonians per ladder position
