@@ -253,3 +253,25 @@ def test_production_shape_two_warp_counter_build(h, R, pipeline):
     for r in picks:
         assert np.array_equal(g.dump_ops(r), one.dump_ops(r))
     assert all(g.verify(r) for r in range(0, R, 16))
+
+
+@pytest.mark.parametrize("pipeline", [0, 1, 2])
+def test_capacity_growth_in_every_build(pipeline):
+    """A sweep that finds its cutoff above the capacity stops that replica (every role of the multi-warp builds leaves
+    the sweep at the same place), the host re-lays the strings out and relaunches: results do not depend on where growth
+    happened."""
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.square_periodic(6, -1.0)
+    keys = [0xCA9A0 + r for r in range(5)]
+    g = QmcIsingGraph(edges, 2.5, 0.0, 36, keys, 4.0, mode=MODE_COUNTER, capacity=64)
+    g.set_option("auto_capacity", 1)
+    g.set_option("minblocks", 4)
+    g.set_option("pipeline", pipeline)
+    refs = [po.SseOracle(edges, 2.5, 0.0, 36, key=k) for k in keys]
+    for chunk in (7, 1, 12):
+        e = g.timesteps(chunk, 4.0)
+        for r, ref in enumerate(refs):
+            assert e[r] == ref.timesteps(chunk, 4.0, MODE_COUNTER)
+            assert same(g, r, ref), (pipeline, chunk, r)
+    assert g.get_capacity() > 64 and g.verify()
