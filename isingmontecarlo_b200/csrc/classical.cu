@@ -16,7 +16,9 @@
 //  * generic graph: one byte per spin (the reference's Vec<bool>), CSR neighbours, one thread per
 //    group of 32 ranks of a colour, threshold table per (replica, site class).
 //  * L x L periodic square lattice, uniform J and bias: spins bit-packed in two colour planes,
-//    one thread per 32 sites: neighbour counts by bit-sliced adders, 4 Philox calls, no divergence.
+//    one thread per 32 sites: neighbour counts by bit-sliced adders; two Philox calls (eight bit planes) decide nine
+//    words in ten, the words that still hold a tie are parked in a per-warp queue and get their further planes 32 at a
+//    time (k_cls_square_sweeps: both colours of many sweeps in one cooperative launch).
 #include <algorithm>
 
 #include "classical.cuh"

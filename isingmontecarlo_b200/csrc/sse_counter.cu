@@ -12,6 +12,7 @@
 //  P2  one flip bit per segment id (parent id < child id), four words per round.
 //  P3  stateless apply: op word + sid -> flip bits looked up per slot; no per-variable state, no lattice tables, no
 //      match; four lines in flight per iteration.
+// Batches that leave most of an SM empty run with two or three warps per replica (template parameter PIPE below).
 #include <algorithm>
 #include <map>
 #include <mutex>
