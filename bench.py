@@ -580,6 +580,8 @@ def bench_reference(args):
     cores = po.max_threads()
     edges = lattices.square_periodic(c["L"], c["J"])
     reps = [po.SseOracle(edges, c["gamma"], c["h"], c["cutoff0"], key=c["key0"] + r) for r in range(cores)]
+    for g in reps:
+        g.use_small_rng()  # the generator the reference's own benches use (rand's SmallRng = xoshiro256++, benches/end_to_end.rs:49); measured 2 % faster than Philox here
     betas = [c["beta"]] * cores
     po.sse_batch_timesteps(reps, args.ref_therm, betas, po.MODE_STRICT)  # thermalise on the CPU (untimed)
     for _ in range(args.warmup):
@@ -599,7 +601,8 @@ def bench_reference(args):
                                    f"bounded sample: {cores} replicas, one per host core"},
             "cpu_baseline": {"value": value, "unit": "vertex_updates/s", "cores": cores, "kind": "port",
                              "sample": f"{cores} replicas x {args.steps} sweeps after {args.ref_therm} thermalisation sweeps, "
-                                       "oracle/oracle.c restatement of the Rust reference (no Rust toolchain in this image)"},
+                                       "oracle/oracle.c restatement of the Rust reference (no Rust toolchain in this image), "
+                                       "xoshiro256++ words as in the reference's own benches (SmallRng)"},
             "e2e": {"value": value, "unit": "vertex_updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "classical": {"metric": "classical_spin_flips_per_sec", "value": cb["value"], "unit": cb["unit"], "cpu_baseline": cb}}
     print(json.dumps(line))

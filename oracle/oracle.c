@@ -59,7 +59,25 @@ typedef struct {
     /* last Philox block (two stream words), so that a block is computed once, not twice */
     uint64_t blk_key, blk_idx, blk_w[2];
     int blk_valid;
+    /* TIMING ONLY (bench.py's CPU arm): the reference's own benches seed rand's SmallRng (benches/end_to_end.rs:49),
+     * which is xoshiro256++ on 64-bit targets -- two orders of magnitude cheaper per word than Philox4x32-10.  With
+     * small_rng set the words come from xoshiro256++ (state seeded from the key by SplitMix64, as rand_xoshiro's
+     * seed_from_u64 does); the cursor still counts words, but such a stream has no GPU counterpart and no test uses it. */
+    int small_rng;
+    uint64_t xs[4];
 } Stream;
+
+static uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static void small_rng_seed(Stream *s, uint64_t seed) {
+    for (int i = 0; i < 4; i++) { /* SplitMix64 */
+        seed += 0x9E3779B97F4A7C15ull;
+        uint64_t z = seed;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        s->xs[i] = z ^ (z >> 31);
+    }
+    s->small_rng = 1;
+}
 
 static uint64_t next_u64(Stream *s) {
     if (s->script) {
@@ -69,6 +87,13 @@ static uint64_t next_u64(Stream *s) {
             return 0;
         }
         return s->script[s->cursor++];
+    }
+    if (s->small_rng) { /* xoshiro256++ */
+        uint64_t *x = s->xs;
+        const uint64_t result = rotl64(x[0] + x[3], 23) + x[0], t = x[1] << 17;
+        x[2] ^= x[0], x[3] ^= x[1], x[1] ^= x[2], x[0] ^= x[3], x[2] ^= t, x[3] = rotl64(x[3], 45);
+        s->cursor++;
+        return result;
     }
     {
         const uint64_t c = s->cursor++, blk = c >> 1;
@@ -162,43 +187,43 @@ static double gen_f64(Stream *s) {
 static int gen_std_bool(Stream *s) { return (int32_t)next_u32(s) < 0; }
 
 int orc_gen_bool(uint64_t key, uint64_t *cursor, double p) {
-    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0, 0, {0, 0, 0, 0}};
     int r = gen_bool(&s, p);
     *cursor = s.cursor;
     return r;
 }
 uint64_t orc_gen_range_usize(uint64_t key, uint64_t *cursor, uint64_t n) {
-    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0, 0, {0, 0, 0, 0}};
     uint64_t r = gen_range_usize(&s, n);
     *cursor = s.cursor;
     return r;
 }
 uint32_t orc_gen_range_u8(uint64_t key, uint64_t *cursor, uint32_t n) {
-    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0, 0, {0, 0, 0, 0}};
     uint32_t r = gen_range_u8(&s, n);
     *cursor = s.cursor;
     return r;
 }
 double orc_gen_range_f64_01(uint64_t key, uint64_t *cursor) {
-    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0, 0, {0, 0, 0, 0}};
     double r = gen_range_f64_01(&s);
     *cursor = s.cursor;
     return r;
 }
 double orc_gen_range_f64(uint64_t key, uint64_t *cursor, double low, double high) {
-    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0, 0, {0, 0, 0, 0}};
     double r = gen_range_f64(&s, low, high);
     *cursor = s.cursor;
     return r;
 }
 double orc_gen_f64(uint64_t key, uint64_t *cursor) {
-    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0, 0, {0, 0, 0, 0}};
     double r = gen_f64(&s);
     *cursor = s.cursor;
     return r;
 }
 int orc_gen_std_bool(uint64_t key, uint64_t *cursor) {
-    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
+    Stream s = {key, *cursor, NULL, 0, 0, 0, 0, {0, 0}, 0, 0, {0, 0, 0, 0}};
     int r = gen_std_bool(&s);
     *cursor = s.cursor;
     return r;
@@ -1155,6 +1180,7 @@ void orc_sse_set_cutoff(OrcSse *g, uint64_t cutoff) { /* qmc_ising.rs:537-540 */
     g->cutoff = cutoff;
     ops_resize(g, cutoff);
 }
+void orc_sse_use_small_rng(OrcSse *g) { small_rng_seed(&g->rng, g->rng.key); } /* timing only, see Stream */
 uint64_t orc_sse_get_cursor(const OrcSse *g) { return g->rng.cursor; }
 void orc_sse_set_cursor(OrcSse *g, uint64_t cursor) { g->rng.cursor = cursor; }
 void orc_sse_set_key(OrcSse *g, uint64_t key) { g->rng.key = key; }
@@ -1383,7 +1409,7 @@ uint64_t orc_pt_step(OrcSse **slots, uint32_t nslots, const double *betas, uint6
     for (uint32_t i = 0; i < nslots; i++)
         if (slots[i]->cutoff > max_cutoff) max_cutoff = slots[i]->cutoff;
     for (uint32_t i = 0; i < nslots; i++) orc_sse_set_cutoff(slots[i], max_cutoff);
-    Stream rng = {pt_key, *pt_cursor, NULL, 0, 0, 0, 0, {0, 0}, 0};
+    Stream rng = {pt_key, *pt_cursor, NULL, 0, 0, 0, 0, {0, 0}, 0, 0, {0, 0, 0, 0}};
     /* make_first_subgraphs / make_second_subgraphs :83-99 */
     uint32_t a_len = (nslots % 2 == 0) ? nslots : nslots - 1;
     uint32_t b_len = (nslots % 2 == 1) ? nslots - 1 : nslots - 2;

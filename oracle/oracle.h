@@ -65,6 +65,7 @@ OrcSse *orc_qmc_create(uint32_t nvars, uint64_t rng_key, const uint8_t *state_or
 int orc_qmc_make_interaction(OrcSse *g, const double *mat, uint32_t len, const uint32_t *vars, uint32_t nvars_given, int diagonal, int and_offset);
 int orc_qmc_flags(const OrcSse *g); /* bit 0 has_cluster_edges, bit 1 breaks_ising_symmetry */
 void orc_qmc_timestep(OrcSse *g, double beta, int mode);
+void orc_sse_use_small_rng(OrcSse *g); /* TIMING ONLY: xoshiro256++ words (the generator the reference's benches use) instead of Philox */
 void orc_qmc_loop_update(OrcSse *g);                      /* Qmc::loop_update, qmc_runner.rs:205-220 -> directed_loop.rs:103-301 */
 void orc_qmc_set_do_loop_updates(OrcSse *g, int enable);  /* qmc_runner.rs:268-270 */
 void orc_sse_single_diagonal_step(OrcSse *g, double beta);

@@ -64,6 +64,7 @@ def lib():
     sig("orc_qmc_create", vp, C.c_uint32, C.c_uint64, u8p)
     sig("orc_qmc_make_interaction", C.c_int, vp, f64p, C.c_uint32, u32p, C.c_uint32, C.c_int, C.c_int)
     sig("orc_qmc_flags", C.c_int, vp)
+    sig("orc_sse_use_small_rng", None, vp)
     sig("orc_qmc_loop_update", None, vp)
     sig("orc_qmc_set_do_loop_updates", None, vp, C.c_int)
     sig("orc_sse_single_diagonal_step", None, vp, C.c_double)
@@ -155,6 +156,11 @@ class SseOracle:
         if getattr(self, "_h", None) and _lib is not None:
             _lib.orc_sse_destroy(self._h)
             self._h = None
+
+    def use_small_rng(self):
+        """TIMING ONLY (bench.py's CPU arm): words from xoshiro256++ -- rand's SmallRng, which the reference's benches
+        use (benches/end_to_end.rs:49) -- instead of Philox4x32-10; no GPU counterpart."""
+        lib().orc_sse_use_small_rng(self._h)
 
     def set_script(self, words):
         self._script = np.ascontiguousarray(words, dtype=np.uint64)
