@@ -544,31 +544,38 @@ int orc_sse_error(const OrcSse *g) { return g->error | (g->rng.error << 8); }
 /* Rebuild every link from the op array.  Semantically what the incremental splices in
  * FastOps::mutate_p maintain (fast_ops.rs:337-607; same construction as
  * clear_and_install_ops fast_ops.rs:89-173). */
-static void rebuild_links(OrcSse *g) {
+static void links_begin(OrcSse *g) {
     for (uint32_t v = 0; v < g->nvars; v++) g->vfirst_p[v] = g->vlast_p[v] = NONE;
     g->first_p = g->last_p = NONE;
+}
+/* append the op in slot p (the highest occupied slot so far) to the p list and to the lists of its variables */
+static inline void links_append(OrcSse *g, uint64_t p) {
+    Node *nd = &g->ops[p];
+    nd->prev_p = g->last_p, nd->next_p = NONE;
+    if (g->last_p != NONE) g->ops[g->last_p].next_p = (int64_t)p;
+    else g->first_p = (int64_t)p;
+    g->last_p = (int64_t)p;
+    for (int r = 0; r < nd->nv; r++) {
+        uint32_t v = nd->vars[r];
+        nd->next_vp[r] = NONE, nd->next_vr[r] = 0;
+        if (g->vlast_p[v] != NONE) {
+            Node *pn = &g->ops[g->vlast_p[v]];
+            pn->next_vp[g->vlast_r[v]] = (int64_t)p, pn->next_vr[g->vlast_r[v]] = (int8_t)r;
+            nd->prev_vp[r] = g->vlast_p[v], nd->prev_vr[r] = g->vlast_r[v];
+        } else {
+            nd->prev_vp[r] = NONE, nd->prev_vr[r] = 0;
+            g->vfirst_p[v] = (int64_t)p, g->vfirst_r[v] = (int8_t)r;
+        }
+        g->vlast_p[v] = (int64_t)p, g->vlast_r[v] = (int8_t)r;
+    }
+}
+static void rebuild_links(OrcSse *g) {
+    links_begin(g);
     uint64_t n = 0;
     for (uint64_t p = 0; p < g->ops_len; p++) {
-        Node *nd = &g->ops[p];
-        if (!nd->present) continue;
+        if (!g->ops[p].present) continue;
         n++;
-        nd->prev_p = g->last_p, nd->next_p = NONE;
-        if (g->last_p != NONE) g->ops[g->last_p].next_p = (int64_t)p;
-        else g->first_p = (int64_t)p;
-        g->last_p = (int64_t)p;
-        for (int r = 0; r < nd->nv; r++) {
-            uint32_t v = nd->vars[r];
-            nd->next_vp[r] = NONE, nd->next_vr[r] = 0;
-            if (g->vlast_p[v] != NONE) {
-                Node *pn = &g->ops[g->vlast_p[v]];
-                pn->next_vp[g->vlast_r[v]] = (int64_t)p, pn->next_vr[g->vlast_r[v]] = (int8_t)r;
-                nd->prev_vp[r] = g->vlast_p[v], nd->prev_vr[r] = g->vlast_r[v];
-            } else {
-                nd->prev_vp[r] = NONE, nd->prev_vr[r] = 0;
-                g->vfirst_p[v] = (int64_t)p, g->vfirst_r[v] = (int8_t)r;
-            }
-            g->vlast_p[v] = (int64_t)p, g->vlast_r[v] = (int8_t)r;
-        }
+        links_append(g, p);
     }
     g->n = n;
 }
@@ -582,6 +589,9 @@ static void diagonal_update(OrcSse *g, double beta) {
     ops_resize(g, cutoff); /* fast_ops.rs:622-624 */
     uint8_t *state = g->state;
     uint64_t n = g->n; /* s.get_n(): live */
+    /* the links (what mutate_p's splices maintain, fast_ops.rs:337-607) are rebuilt in the same pass: the op that ends up in
+     * slot p is appended to the lists right away, so the sweep reads the string once, as the reference does */
+    links_begin(g);
     for (uint64_t p = 0; p < cutoff; p++) {
         Node *nd = &g->ops[p];
         uint32_t b;
@@ -591,6 +601,7 @@ static void diagonal_update(OrcSse *g, double beta) {
             b = nd->bond; /* :153 */
         } else {
             for (int r = 0; r < nd->nv; r++) state[nd->vars[r]] = nd->out[r]; /* :154-160 */
+            links_append(g, p);
             continue;
         }
         uint32_t vars[2];
@@ -615,9 +626,11 @@ static void diagonal_update(OrcSse *g, double beta) {
                 n--;
             }
         }
+        if (nd->present) links_append(g, p);
     }
+    for (uint64_t p = cutoff; p < g->ops_len; p++) /* (slots above the cutoff hold no ops: set_cutoff refuses to orphan any) */
+        if (g->ops[p].present) links_append(g, p);
     g->n = n;
-    rebuild_links(g);
 }
 
 /* ===================================================================================
