@@ -542,16 +542,21 @@ __global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, P
                         dec = (pw >> (par & 31)) & 1u;
                         known = true;
                     }
-                    for (;;) {  // parents inside this word: resolve by rounds
+                    // parents inside this word: resolve by rounds.  Consecutive ids are consecutive site ops of the string and
+                    // min-root unions leave chains among them, so a lane whose parent is not decided yet jumps to its parent's
+                    // parent (pointer doubling through a shuffle): log2(depth) rounds instead of depth
+                    uint32_t pl = known ? (uint32_t)lane : par - wd * 32;
+                    for (;;) {
                         const uint32_t kmask = __ballot_sync(FULL, known), dmask = __ballot_sync(FULL, dec);
                         if (kmask == FULL) {
                             out4[j] = dmask;
                             if (lane == 0 && wd < nwords) st_cg(decb + wd, dmask);
                             break;
                         }
+                        const uint32_t ppl = __shfl_sync(FULL, pl, pl);
                         if (!known) {
-                            const uint32_t pl = par - wd * 32;
                             if ((kmask >> pl) & 1u) dec = (dmask >> pl) & 1u, known = true;
+                            else pl = ppl;
                         }
                     }
                 }
