@@ -125,6 +125,21 @@ __global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, P
     const uint64_t nsteps = (phases & 16u) ? (done + 1 == target ? 1 : 0) : ((phases & 8u) ? (target > done ? target - done : 0) : 1);
     int err = 0;
 
+#ifdef QMCB_PHASE_TIMERS
+    // cycles of lane 0 of every role per phase, summed over replicas and sweeps: dbg[32 + 8 * role + k], k = 0 set-up,
+    // 1 P1 loop, 2 closure (+ frozen marks), 3 P2, 4 P3, 5 sweep tail
+    long long ct_ = clock64();
+#define CTICK(k)                                                                                  \
+    do {                                                                                          \
+        if (lane == 0 && D.dbg) {                                                                 \
+            const long long t_ = clock64();                                                       \
+            atomicAdd(&D.dbg[32 + 8 * (PIPE ? role : 0u) + (k)], (unsigned long long)(t_ - ct_)); \
+            ct_ = t_;                                                                             \
+        }                                                                                         \
+    } while (0)
+#else
+#define CTICK(k) ((void)0)
+#endif
     for (uint64_t sw = 0; sw < nsteps; sw++) {
         const uint32_t M = D.M[r];
         if (M > D.cap) {
@@ -163,6 +178,7 @@ __global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, P
         const uint64_t cdiag = cur;  // nonce of this diagonal step
         if (do_diag) cur += 1;
 
+        CTICK(0);
         // =========================== P1: diagonal update + segments + unions ===========================
         const uint32_t nit = (M + 31) / 32;
 #if QMCB_BULK_LINES
@@ -457,7 +473,13 @@ __global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, P
                 }
                 __syncwarp();
             } else if (!PIPE) step_tail();
+#ifdef QMCB_PHASE_TIMERS
+            const long long tb_ = clock64();  // cycles every role waits at the step barrier: dbg[56 + role]
             PAIR_SYNC();
+            if (PIPE && lane == 0 && D.dbg) atomicAdd(&D.dbg[56 + role], (unsigned long long)(clock64() - tb_));
+#else
+            PAIR_SYNC();
+#endif
         }
         if (do_diag && roleA && lane == 0) D.n[r] = n;
         if (PIPE) {  // role B needs n for the closure, the others the site ops before their share of P3
@@ -470,6 +492,7 @@ __global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, P
             ks_half = xchg[2], ks_third = xchg[3];
         }
 
+        CTICK(1);
         uint32_t ncl = 0;
         if (do_clus && n > 0) {
             const uint64_t c0 = cur;
@@ -502,6 +525,7 @@ __global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, P
                     __syncwarp();
                 }
             }
+            CTICK(2);
             // =========================== P2: one flip bit per segment ===========================
             // ascending ids (parent id < child id).  Four words (= one Philox block of flip bits) per round: their parents
             // are loaded together, then the decisions of parents from earlier rounds, and only the parents inside the round
@@ -578,6 +602,7 @@ __global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, P
                 ncl = xchg[1];
             }
 
+            CTICK(3);
             // =========================== P3: apply the flips (stateless) ===========================
             // PIPE: role A applies the slots before half_it * 32, role B the rest, starting from its own count of the site ops before them
             const uint32_t cut1 = min(M, half_it * 32u), cut2 = PIPE == 3 ? max(cut1, min(M, third_it * 32u)) : M;
@@ -633,6 +658,7 @@ __global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, P
                     }
                 }
             }
+            CTICK(4);
             // spins: the segment of variable v crossing p = 0 has id v
             if (roleA)
                 for (uint32_t j = lane; j < Nw; j += 32) s_st[j] ^= ld_cg(decb + j) & s_tb[j];
@@ -678,6 +704,7 @@ __global__ void __launch_bounds__(PIPE ? 32 * PIPE * QMCB_WPB : 32 * QMCB_WPB, P
         }
         __syncwarp();
         PAIR_SYNC();  // role B reads n, the cursor and the cutoff of the next sweep after role A wrote them
+        CTICK(5);
     }
     if (err) atomicOr(D.status, err);
 #undef PAIR_SYNC

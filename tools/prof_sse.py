@@ -51,3 +51,11 @@ if os.environ.get('PROF_DBG'):
     print("phase cycles per replica-sweep (lane 0 clock64, summed over replicas / R / sweeps):")
     for nm, v in zip(names, t):
         print(f"  {nm:22s} {v / R / sweeps / 1e6:8.2f} Mcycles  {100 * v / t.sum():5.1f}%")
+if os.environ.get('PROF_DBG') and mode == MODE_COUNTER:
+    c = g.debug_counters().astype(np.float64)
+    names = ["set-up", "P1 loop", "closure", "P2", "P3", "tail"]
+    for role in range(3):
+        v = c[32 + 8 * role:32 + 8 * role + 6] / R / sweeps
+        if v.sum() > 0:
+            print(f"role {'ABC'[role]} Mcycles per replica-sweep: " + ", ".join(f"{n} {x / 1e6:.2f}" for n, x in zip(names, v))
+                  + f"; waiting at the step barrier {c[56 + role] / R / sweeps / 1e6:.2f}")
