@@ -741,9 +741,12 @@ __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int
     uint32_t *const ist = stk, *const fst = stk + STK_IW;
     uint32_t flen = 0, fbase = 0, ilen = 0, ibase = 0;
     const uint32_t fcap = (uint32_t)V.fcap, icap = (uint32_t)V.icap;
+    // (the capacity checks live in the spill paths: a ring that never spills cannot overflow the global stacks)
     auto fpush = [&](uint32_t x) {
         if (flen - fbase == STK_F) {
-            for (uint32_t j = 0; j < STK_F / 2; j++) V.frontier[fbase + j] = fst[(fbase + j) & (STK_F - 1)];
+            if (fbase + STK_F / 2 > fcap) err |= DEV_ERR_STACK;
+            else
+                for (uint32_t j = 0; j < STK_F / 2; j++) V.frontier[fbase + j] = fst[(fbase + j) & (STK_F - 1)];
             fbase += STK_F / 2;
         }
         fst[flen & (STK_F - 1)] = x;
@@ -760,7 +763,9 @@ __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int
     };
     auto ipush = [&](uint32_t x) {
         if (ilen - ibase == STK_IW) {
-            for (uint32_t j = 0; j < STK_IW / 2; j++) V.interior[ibase + j] = ist[(ibase + j) & (STK_IW - 1)];
+            if (ibase + STK_IW / 2 > icap) err |= DEV_ERR_STACK;
+            else
+                for (uint32_t j = 0; j < STK_IW / 2; j++) V.interior[ibase + j] = ist[(ibase + j) & (STK_IW - 1)];
             ibase += STK_IW / 2;
         }
         ist[ilen & (STK_IW - 1)] = x;
@@ -775,8 +780,8 @@ __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int
         ilen--;
         return ist[ilen & (STK_IW - 1)];
     };
-    // an interior entry is where the leg LANDS: (neighbouring entry << 1 | side it arrives at) [| bit 31: leg of the start op]
-    auto push_leg = [&](uint32_t idx, uint32_t side, uint32_t flag) { ipush((((side == SIDE_IN ? idx - 1u : idx + 1u) << 1) | (side ^ 1u)) | flag); };
+    // an interior entry is where the leg LANDS: neighbouring entry << 1 | side it arrives at
+    auto push_leg = [&](uint32_t idx, uint32_t side) { ipush(((side == SIDE_IN ? idx - 1u : idx + 1u) << 1) | (side ^ 1u)); };
     if (lane == 0) {
         const uint32_t e0 = V.ent[cp];
         fpush((e0 << 1) | SIDE_OUT);  // cluster.rs:57-59
@@ -794,64 +799,66 @@ __device__ uint32_t label_strict_wl(const SseDev &D, const Rep &V, int &err, int
                 if (E0.z != NONE32 && E0.w != NONE32) continue;
                 const uint32_t kind0 = WL_KIND(E0.x), x0 = E0.y >> 1;
                 ilen = 0, ibase = 0;
-                if (kind0 != KIND_SITE) {  // :205-211 (i0 is the entry of leg 0: the scan below hands out ent[p])
-                    push_leg(i0, SIDE_IN, 0x80000000u);
-                    if (kind0 == KIND_BOND) push_leg(x0, SIDE_IN, 0x80000000u);
-                    push_leg(i0, SIDE_OUT, 0x80000000u);
-                    if (kind0 == KIND_BOND) push_leg(x0, SIDE_OUT, 0x80000000u);
-                } else {  // :212-215
-                    push_leg(i0, side0, 0x80000000u);
-                }
-                while (ilen) {
-                    const uint32_t it = ipop();
-                    ST_COUNT(0);
-                    const uint32_t sq = it & 1u;
-                    uint32_t q = (it & 0x7FFFFFFFu) >> 1;
-                    if ((OPT & 1) && ilen != ibase)
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(V.wl + ((ist[(ilen - 1u) & (STK_IW - 1)] & 0x7FFFFFFFu) >> 1)));
-                    if (it & 0x80000000u) {  // set_boundary(p0, side, cnum) :218, :289-306
-                        uint32_t *b = wl_bnd(V, i0, sq ^ 1u);
+                // the legs of the start op (:205-215: in0, in1, out0, out1 of a non-edge op, the one leg of an edge) are popped
+                // last-pushed first and everything a leg reaches is popped before the next one, so they are taken one by one
+                // here instead of travelling through the stack with a flag; set_boundary(p0, side, cnum) (:218, :289-306)
+                // happens when the leg is popped, as in the reference
+                const uint32_t nstart = kind0 == KIND_SITE ? 1u : (kind0 == KIND_BOND ? 4u : 2u);
+#pragma unroll 1
+                for (uint32_t k = nstart; k-- > 0;) {
+                    const uint32_t sside = kind0 == KIND_SITE ? side0 : (kind0 == KIND_BOND ? (k >> 1) : k);
+                    const uint32_t sidx = (kind0 == KIND_BOND && (k & 1u)) ? x0 : i0;
+                    {
+                        uint32_t *b = wl_bnd(V, i0, sside);
                         const uint32_t curb = *b;
                         if (curb == NONE32) {
                             *b = cnum;
-                            if (kind0 == KIND_BOND) *wl_bnd(V, x0, sq ^ 1u) = cnum;
+                            if (kind0 == KIND_BOND) *wl_bnd(V, x0, sside) = cnum;
                         } else if (curb != cnum) err |= DEV_ERR_INVARIANT;
                     }
-                    uint4 e = V.wl[q];
-                    if (WL_KIND(e.x) == WL_SENT) {  // end of the world line: continue at the other end :224-241
-                        q = e.y;
-                        e = V.wl[q];
-                        ST_COUNT(3);
-                    }
-                    const uint32_t kq = WL_KIND(e.x);
-                    if ((OPT & 2) && kq == KIND_BOND) asm volatile("prefetch.global.L1 [%0];" ::"l"(V.wl + (e.y >> 1)));
-                    if (kq == KIND_SITE) {  // cluster edge :245-248
-                        ST_COUNT(1);
-                        const uint32_t mine = sq ? e.w : e.z, other = sq ? e.z : e.w;
-                        if (mine == NONE32) *wl_bnd(V, q, sq) = cnum;
-                        else if (mine != cnum) err |= DEV_ERR_INVARIANT;
-                        if (other == NONE32) {
-                            if (flen >= fcap) err |= DEV_ERR_STACK;
-                            else fpush((q << 1) | (sq ^ 1u));
+                    push_leg(sidx, sside);
+                    while (ilen) {
+                        const uint32_t it = ipop();
+                        ST_COUNT(0);
+                        const uint32_t sq = it & 1u;
+                        uint32_t q = it >> 1;
+                        if ((OPT & 1) && ilen != ibase) asm volatile("prefetch.global.L1 [%0];" ::"l"(V.wl + (ist[(ilen - 1u) & (STK_IW - 1)] >> 1)));
+                        uint4 *pe = V.wl + q;
+                        uint4 e = *pe;
+                        uint32_t kq = WL_KIND(e.x);
+                        if (kq == WL_SENT) {  // end of the world line: continue at the other end :224-241
+                            q = e.y;
+                            pe = V.wl + q;
+                            e = *pe;
+                            kq = WL_KIND(e.x);
+                            ST_COUNT(3);
                         }
-                    } else {  // interior op :249-268
-                        const uint32_t a = e.z, bb = e.w;
-                        const bool ok = (a == NONE32 && bb == NONE32) || (a == cnum && bb == NONE32) || (a == NONE32 && bb == cnum);
-                        if (ok) {
-                            ST_COUNT(2);
-                            const uint32_t xq = e.y >> 1, kme = (e.x >> 2) & 1u;
-                            *reinterpret_cast<uint2 *>(wl_bnd(V, q, 0)) = make_uint2(cnum, cnum);
-                            if (ilen + 4 > icap) { err |= DEV_ERR_STACK; break; }
-                            if (kq == KIND_BOND) {
-                                *reinterpret_cast<uint2 *>(wl_bnd(V, xq, 0)) = make_uint2(cnum, cnum);
-                                const uint32_t i_k0 = kme ? xq : q, i_k1 = kme ? q : xq;
-                                if (!(kme == 0 && sq == SIDE_IN)) push_leg(i_k0, SIDE_IN, 0u);
-                                if (!(kme == 1 && sq == SIDE_IN)) push_leg(i_k1, SIDE_IN, 0u);
-                                if (!(kme == 0 && sq == SIDE_OUT)) push_leg(i_k0, SIDE_OUT, 0u);
-                                if (!(kme == 1 && sq == SIDE_OUT)) push_leg(i_k1, SIDE_OUT, 0u);
-                            } else {
-                                if (sq != SIDE_IN) push_leg(q, SIDE_IN, 0u);
-                                if (sq != SIDE_OUT) push_leg(q, SIDE_OUT, 0u);
+                        if ((OPT & 2) && kq == KIND_BOND) asm volatile("prefetch.global.L1 [%0];" ::"l"(V.wl + (e.y >> 1)));
+                        uint32_t *const bq = reinterpret_cast<uint32_t *>(pe) + 2;
+                        if (kq == KIND_SITE) {  // cluster edge :245-248
+                            ST_COUNT(1);
+                            const uint32_t mine = sq ? e.w : e.z, other = sq ? e.z : e.w;
+                            if (mine == NONE32) bq[sq] = cnum;
+                            else if (mine != cnum) err |= DEV_ERR_INVARIANT;
+                            if (other == NONE32) fpush((q << 1) | (sq ^ 1u));
+                        } else {  // interior op :249-268
+                            const uint32_t a = e.z, bb = e.w;
+                            const bool ok = (a == NONE32 && bb == NONE32) || (a == cnum && bb == NONE32) || (a == NONE32 && bb == cnum);
+                            if (ok) {
+                                ST_COUNT(2);
+                                const uint32_t xq = e.y >> 1, kme = (e.x >> 2) & 1u;
+                                *reinterpret_cast<uint2 *>(bq) = make_uint2(cnum, cnum);
+                                if (kq == KIND_BOND) {
+                                    *reinterpret_cast<uint2 *>(wl_bnd(V, xq, 0)) = make_uint2(cnum, cnum);
+                                    const uint32_t i_k0 = kme ? xq : q, i_k1 = kme ? q : xq;
+                                    if (!(kme == 0 && sq == SIDE_IN)) push_leg(i_k0, SIDE_IN);
+                                    if (!(kme == 1 && sq == SIDE_IN)) push_leg(i_k1, SIDE_IN);
+                                    if (!(kme == 0 && sq == SIDE_OUT)) push_leg(i_k0, SIDE_OUT);
+                                    if (!(kme == 1 && sq == SIDE_OUT)) push_leg(i_k1, SIDE_OUT);
+                                } else {
+                                    if (sq != SIDE_IN) push_leg(q, SIDE_IN);
+                                    if (sq != SIDE_OUT) push_leg(q, SIDE_OUT);
+                                }
                             }
                         }
                     }
