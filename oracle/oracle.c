@@ -313,6 +313,9 @@ struct OrcSse {
     struct OrcInteraction *inter;
     uint32_t ninter;
     int is_qmc, has_cluster_edges, breaks_ising_symmetry, do_loop_updates;
+    /* RVB update (qmc_ising.rs:39-43) */
+    int run_rvb;
+    uint64_t total_rvb_successes, rvb_clusters_counted;
 };
 
 /* Interaction, qmc_runner.rs:406-421: type Full(constant) | Diagonal, mat, n, vars, constant_along_diagonal */
@@ -1148,13 +1151,608 @@ void orc_qmc_timestep(OrcSse *g, double beta, int mode) {
         if (g->vfirst_p[v] == NONE) g->state[v] = (uint8_t)gen_bool(&g->rng, 0.5);
 }
 
-/* QmcIsingGraph::timestep, qmc_ising.rs:644-795 (rvb off: default :122) */
+
+/* ===================================================================================
+ * RVB update: rvb.rs:60-291 (RvbUpdater::rvb_update_with_ising_weight), :294-616 (mutate_graph), :617-646
+ * (set_initial_bonds), :649-946 (calculate_flip_prob), :955-1052 (VarPos, WeightedBoundaryManager), :1054-1122
+ * (build_cluster), :1124-1160 (find_overlapping_starts), :1162-1188 (find_constants), :1190-1192 (contiguous_bits),
+ * :1194-1221 (calculate_mult); util/bondcontainer.rs:10-159 (BondContainer); util/vec_help.rs:2-23 (remove_doubles);
+ * caller qmc_ising.rs:705-752 (timestep), :322-420 (single_rvb_sweep), EdgeNav :610-636, make_classical_bonds :420-432.
+ *
+ * The reference walks the per-variable links with binary heaps and "hints" (fast_ops.rs:639-808, 896-1172); those decide
+ * HOW ops are found, not WHICH: calculate_flip_prob and mutate_subsection_ops visit every op that touches a sub-variable,
+ * in p order, and get_propagated_substate_with_hint returns the state just before p.  This restatement does the same
+ * visits on the flat op array; every draw, every f64 operation and the key order inside the BondContainers (push at the
+ * end, swap-remove) are the reference's.  Links are rebuilt once at the end (the reference splices them per change).
+ * =================================================================================== */
+typedef struct { int64_t v, p; double w; } BcKey; /* (T, f64); T = bond (p = NONE) or VarPos{v, p} (rvb.rs:957-965) */
+typedef struct {
+    int64_t *map; uint64_t map_len; /* Vec<Option<usize>>: index into keys, NONE */
+    BcKey *keys; uint64_t len, cap;
+    double total;
+} BondContainer;
+static uint64_t bc_index(int64_t v, int64_t p) { return (uint64_t)(p != NONE ? p : v); } /* From<VarPos> for usize, :961-965 */
+static void bc_free(BondContainer *c) { free(c->map), free(c->keys); memset(c, 0, sizeof(*c)); }
+static void bc_clear(BondContainer *c) { /* bondcontainer.rs:133-142 */
+    for (uint64_t i = 0; i < c->len; i++) c->map[bc_index(c->keys[i].v, c->keys[i].p)] = NONE;
+    c->len = 0, c->total = 0.0;
+}
+static int bc_contains(const BondContainer *c, int64_t v, int64_t p) { /* :90-97 */
+    uint64_t t = bc_index(v, p);
+    return t < c->map_len && c->map[t] != NONE;
+}
+static int bc_get_weight(const BondContainer *c, int64_t v, int64_t p, double *w) { /* :100-107 */
+    uint64_t t = bc_index(v, p);
+    if (t >= c->map_len || c->map[t] == NONE) return 0;
+    *w = c->keys[c->map[t]].w;
+    return 1;
+}
+static void bc_correct_total(BondContainer *c) { if (c->total < 0.0) c->total = 0.0; } /* :76-87 */
+static void bc_insert(BondContainer *c, int64_t v, int64_t p, double w) { /* :110-130 */
+    uint64_t t = bc_index(v, p);
+    if (t >= c->map_len) {
+        c->map = (int64_t *)realloc(c->map, (t + 1) * sizeof(int64_t));
+        for (uint64_t i = c->map_len; i <= t; i++) c->map[i] = NONE;
+        c->map_len = t + 1;
+    }
+    if (c->map[t] != NONE) {
+        BcKey *k = &c->keys[c->map[t]];
+        double old = k->w;
+        k->w = w;
+        c->total += w - old;
+        bc_correct_total(c);
+    } else {
+        if (c->len == c->cap) c->cap = c->cap ? 2 * c->cap : 64, c->keys = (BcKey *)realloc(c->keys, c->cap * sizeof(BcKey));
+        c->map[t] = (int64_t)c->len;
+        c->keys[c->len].v = v, c->keys[c->len].p = p, c->keys[c->len].w = w;
+        c->len++;
+        c->total += w;
+    }
+}
+static void bc_remove_index(BondContainer *c, uint64_t ki) { /* :58-74: swap with the last key, pop */
+    uint64_t last = c->len - 1;
+    BcKey tmp = c->keys[ki];
+    c->keys[ki] = c->keys[last], c->keys[last] = tmp;
+    c->map[bc_index(c->keys[ki].v, c->keys[ki].p)] = (int64_t)ki;
+    BcKey out = c->keys[last];
+    c->len--;
+    c->map[bc_index(out.v, out.p)] = NONE;
+    c->total -= out.w;
+    bc_correct_total(c);
+}
+static void bc_remove(BondContainer *c, int64_t v, int64_t p) { /* :47-56 */
+    uint64_t t = bc_index(v, p);
+    if (t < c->map_len && c->map[t] != NONE) bc_remove_index(c, (uint64_t)c->map[t]);
+}
+/* get_random, :30-44: index of the chosen key, or NONE where the reference panics */
+static int64_t bc_get_random(const BondContainer *c, OrcSse *g) {
+    if (c->len == 0) { g->error |= 64; return NONE; }                  /* .unwrap() on None */
+    if (!(0.0 < c->total)) { g->error |= 64; return NONE; }            /* gen_range panics on an empty range */
+    double p = gen_range_f64(&g->rng, 0.0, c->total);
+    uint64_t i = 0;
+    while (i < c->len) {
+        p -= c->keys[i].w;
+        if (p <= 0.0) break;
+        i++;
+    }
+    if (i >= c->len) { g->error |= 64; return NONE; }                  /* index out of bounds */
+    return (int64_t)i;
+}
+
+typedef struct {
+    OrcSse *g;
+    /* EdgeNav (qmc_ising.rs:610-636): classical_bonds[v] = bonds of v in bond order (make_classical_bonds :420-432) */
+    uint32_t *vb_start, *vb_list;
+    /* find_constants, rvb.rs:1162-1188 */
+    uint64_t *var_starts, *var_lengths, *constant_ps, ncp;
+    uint32_t *zero_vars, nzero;
+    /* WeightedBoundaryManager, :967-973 */
+    BondContainer b_flips, b_noflips;
+    uint8_t *pos_popped, *nopos_popped;
+    /* per update */
+    int64_t *cl_vars, *cl_flips; uint64_t ncl;
+    uint32_t *subvars, nsub; int64_t *v2s;
+    uint8_t *cstate, *substate;
+    uint64_t *toggles, ntog;
+    BondContainer bonds, bonds_before, bonds_after;
+} Rvb;
+
+static int64_t rvb_other_var(const OrcSse *g, uint32_t v, uint32_t b) { /* EdgeNavigator::other_var_for_bond, rvb.rs:22-31 */
+    if (v == g->ea[b]) return g->eb[b];
+    if (v == g->eb[b]) return g->ea[b];
+    return NONE;
+}
+static double rvb_edge_weight(const OrcSse *g, uint32_t b, int sa, int sb) { /* the closure of qmc_ising.rs:718-721 */
+    return two_site_hamiltonian(sa, sb, sa, sb, g->J[b]);
+}
+/* WeightedBoundaryManager::push_adjacent, rvb.rs:1028-1047 */
+static void cbm_push_adjacent(Rvb *R, uint32_t var, int64_t pos, int has_w, double weight) {
+    double w = has_w ? weight : 1.0;
+    BondContainer *bd = pos != NONE ? &R->b_flips : &R->b_noflips;
+    uint8_t *popped = pos != NONE ? R->pos_popped : R->nopos_popped;
+    uint64_t idx = bc_index(var, pos);
+    if (!popped[idx]) {
+        double cur = 0.0;
+        if (!bc_get_weight(bd, var, pos, &cur)) cur = 0.0;
+        bc_insert(bd, var, pos, cur + w);
+    }
+}
+/* pop_index, :1010-1026 */
+static int cbm_pop_index(Rvb *R, uint32_t *v_out, int64_t *p_out) {
+    OrcSse *g = R->g;
+    double total = R->b_flips.total + R->b_noflips.total;
+    double f_ratio = R->b_flips.total / total;
+    int pick_flips = gen_bool(&g->rng, f_ratio);
+    if (g->rng.error) return 0;
+    BondContainer *bd = pick_flips ? &R->b_flips : &R->b_noflips;
+    uint8_t *popped = pick_flips ? R->pos_popped : R->nopos_popped;
+    int64_t i = bc_get_random(bd, g);
+    if (i == NONE) return 0;
+    BcKey k = bd->keys[i];
+    popped[bc_index(k.v, k.p)] = 1;
+    bc_remove(bd, k.v, k.p);
+    *v_out = (uint32_t)k.v, *p_out = k.p;
+    return 1;
+}
+/* find_overlapping_starts, :1124-1160: calls push_adjacent for every index it yields */
+static void rvb_push_overlapping(Rvb *R, uint32_t ov, uint64_t p_start, uint64_t p_end, uint64_t cutoff, double weight) {
+    const uint64_t *fp = R->constant_ps + R->var_starts[ov];
+    const uint64_t len = R->var_lengths[ov];
+    uint64_t bin_found = 0; /* binary_search(&p_start).unwrap_err(): number of entries below p_start */
+    while (bin_found < len && fp[bin_found] < p_start) bin_found++;
+    if (bin_found < len && fp[bin_found] == p_start) { R->g->error |= 64; return; } /* unwrap_err on Ok */
+    const uint64_t prev = (bin_found + len - 1) % len;
+    const uint64_t lowest = fp[prev];
+    const uint64_t off_start = (p_start + cutoff - lowest) % cutoff, off_end = (p_end + cutoff - lowest) % cutoff;
+    for (uint64_t k = 0; k < len; k++) {
+        const uint64_t ip = (prev + k) % len; /* [prev..] then [..prev] */
+        const uint64_t check_start = (fp[ip] + cutoff - lowest) % cutoff;
+        const uint64_t check_end = (fp[(ip + 1) % len] + cutoff - lowest) % cutoff;
+        const int has_overlap_start = check_start < off_start && off_start < check_end;
+        const int has_start_within = off_start < check_start && check_start < off_end;
+        const int eq = (p_start == p_end) || (check_start == check_end);
+        if (!(eq || has_overlap_start || has_start_within)) break; /* take_while */
+        cbm_push_adjacent(R, ov, (int64_t)(ip + R->var_starts[ov]), 1, weight);
+    }
+}
+/* build_cluster, :1054-1122 */
+static void rvb_build_cluster(Rvb *R, uint64_t cluster_size, uint32_t init_var, int64_t init_flip, uint64_t cutoff) {
+    OrcSse *g = R->g;
+    cbm_push_adjacent(R, init_var, init_flip, 0, 0.0);
+    while (cluster_size > 0 && !(R->b_flips.len == 0 && R->b_noflips.len == 0)) {
+        uint32_t v;
+        int64_t flip;
+        if (!cbm_pop_index(R, &v, &flip)) return;
+        R->cl_vars[R->ncl] = v, R->cl_flips[R->ncl] = flip, R->ncl++;
+        const uint64_t vs = R->var_starts[v], vl = R->var_lengths[v];
+        if (flip != NONE) {
+            uint64_t rel = (uint64_t)flip - vs;
+            cbm_push_adjacent(R, v, (int64_t)((rel + vl - 1) % vl + vs), 0, 0.0);
+            cbm_push_adjacent(R, v, (int64_t)((rel + 1) % vl + vs), 0, 0.0);
+        }
+        for (uint32_t k = R->vb_start[v]; k < R->vb_start[v + 1]; k++) {
+            const uint32_t b = R->vb_list[k];
+            const double weight = fabs(g->J[b]); /* bond_mag */
+            const int64_t ov = rvb_other_var(g, v, b);
+            if (R->var_lengths[ov] == 0) {
+                cbm_push_adjacent(R, (uint32_t)ov, NONE, 1, weight);
+            } else if (flip != NONE) {
+                uint64_t rel = (uint64_t)flip - vs, flip_inc = (rel + 1) % vl + vs;
+                rvb_push_overlapping(R, (uint32_t)ov, R->constant_ps[flip], R->constant_ps[flip_inc], cutoff, weight);
+            } else {
+                for (uint64_t pi = R->var_starts[ov]; pi < R->var_starts[ov] + R->var_lengths[ov]; pi++)
+                    cbm_push_adjacent(R, (uint32_t)ov, (int64_t)pi, 1, weight);
+            }
+        }
+        cluster_size--;
+    }
+}
+static int rvb_near(const Rvb *R, const Node *nd) { /* does the op touch a sub-variable */
+    for (int r = 0; r < nd->nv; r++)
+        if (R->v2s[nd->vars[r]] != NONE) return 1;
+    return 0;
+}
+/* ws_for_flip, :665-683 */
+static void rvb_ws_for_flip(const Rvb *R, uint32_t b, int64_t sub_flip, double *wbef, double *waft) {
+    const OrcSse *g = R->g;
+    const int64_t suba = R->v2s[g->ea[b]], subb = R->v2s[g->eb[b]];
+    int ba = R->substate[suba], bb = R->substate[subb];
+    *wbef = rvb_edge_weight(g, b, ba, bb);
+    if (sub_flip == suba) ba = !ba;
+    else bb = !bb;
+    *waft = rvb_edge_weight(g, b, ba, bb);
+}
+/* calculate_mult, :1194-1221 */
+static double rvb_calculate_mult(const BondContainer *bef, const BondContainer *aft, uint64_t n) {
+    const int close = fabs(bef->total - aft->total) < DBL_EPSILON;
+    if (n == 0 || close) return 1.0;
+    return orc_powi(aft->total / bef->total, (int)n);
+}
+/* calculate_flip_prob, :649-946 */
+static double rvb_calculate_flip_prob(Rvb *R) {
+    OrcSse *g = R->g;
+    uint64_t cluster_size = 0, next_ci = 0, n_bonds = 0;
+    double mult = 1.0;
+    for (uint32_t s = 0; s < R->nsub; s++) cluster_size += R->cstate[s];
+    bc_clear(&R->bonds_before), bc_clear(&R->bonds_after);
+    if (cluster_size != 0) { /* set_initial_bonds, :617-646 */
+        for (uint32_t s = 0; s < R->nsub; s++) {
+            if (!R->cstate[s]) continue;
+            const uint32_t v = R->subvars[s];
+            for (uint32_t k = R->vb_start[v]; k < R->vb_start[v + 1]; k++) {
+                const uint32_t b = R->vb_list[k];
+                const int64_t os = R->v2s[rvb_other_var(g, v, b)];
+                if (os == NONE) { g->error |= 64; return 0.0; } /* .unwrap() */
+                if (!R->cstate[os]) {
+                    double wb, wa;
+                    rvb_ws_for_flip(R, b, s, &wb, &wa);
+                    bc_insert(&R->bonds_before, b, NONE, wb), bc_insert(&R->bonds_after, b, NONE, wa);
+                }
+            }
+        }
+    }
+    uint64_t pos = 0; /* every op below pos has been popped from the heap */
+    for (;;) {
+        uint64_t q = pos; /* heap top: the next op on a sub-variable's world line */
+        while (q < g->ops_len && !(g->ops[q].present && rvb_near(R, &g->ops[q]))) q++;
+        if (q >= g->ops_len) break;
+        uint64_t p = q;
+        if (cluster_size == 0) { /* :722-733: jump to the next cluster flip */
+            if (next_ci < R->ntog) p = R->toggles[next_ci];
+            else break;
+        }
+        for (uint64_t x = q; x < p; x++) { /* popped < p: their outputs propagate the substate, :742-768 */
+            const Node *nd = &g->ops[x];
+            if (!nd->present) continue;
+            for (int r = 0; r < nd->nv; r++)
+                if (R->v2s[nd->vars[r]] != NONE) R->substate[R->v2s[nd->vars[r]]] = nd->out[r];
+        }
+        pos = p + 1;
+        const Node *op = &g->ops[p];
+        if (p >= g->ops_len || !op->present) { g->error |= 64; return 0.0; }
+        const int is_cluster_bound = next_ci < R->ntog && p == R->toggles[next_ci];
+        const int will_flip_spins = !node_is_diagonal(op);
+        const int will_change_bonds = will_flip_spins || is_cluster_bound;
+        int completely_in_cluster = 1;
+        for (int r = 0; r < op->nv; r++) {
+            const int64_t s = R->v2s[op->vars[r]];
+            if (s == NONE || !R->cstate[s]) completely_in_cluster = 0;
+        }
+        if (bc_contains(&R->bonds_before, op->bond, NONE)) {
+            n_bonds++;
+            continue;
+        }
+        if (is_cluster_bound) { /* :852-867 */
+            const int64_t s = R->v2s[op->vars[0]];
+            if (s == NONE) { g->error |= 64; return 0.0; }
+            R->cstate[s] = !R->cstate[s];
+            if (R->cstate[s]) cluster_size++;
+            else cluster_size--;
+            next_ci++;
+        }
+        if (will_flip_spins)
+            for (int r = 0; r < op->nv; r++)
+                if (R->v2s[op->vars[r]] != NONE) R->substate[R->v2s[op->vars[r]]] = op->out[r];
+        if (completely_in_cluster) { /* ising_ratio, qmc_ising.rs:722-735; rvb_update (:60-79) uses 1.0 */
+            const int long_bond = fabs(g->longitudinal) > DBL_EPSILON && op->bond >= g->nedges + g->nvars;
+            mult *= long_bond ? 0.0 : 1.0;
+            if (mult < DBL_EPSILON) break;
+        }
+        if (will_change_bonds) {
+            mult *= rvb_calculate_mult(&R->bonds_before, &R->bonds_after, n_bonds);
+            n_bonds = 0;
+            if (mult < DBL_EPSILON) break;
+            for (int r = 0; r < op->nv; r++) { /* :901-934 */
+                const uint32_t v = op->vars[r];
+                const int64_t s = R->v2s[v];
+                if (s == NONE) continue;
+                for (uint32_t k = R->vb_start[v]; k < R->vb_start[v + 1]; k++) {
+                    const uint32_t b = R->vb_list[k];
+                    const int64_t os = R->v2s[rvb_other_var(g, v, b)];
+                    if (os == NONE) continue;
+                    if (R->cstate[s] == R->cstate[os]) {
+                        if (bc_contains(&R->bonds_before, b, NONE)) bc_remove(&R->bonds_before, b, NONE), bc_remove(&R->bonds_after, b, NONE);
+                    } else {
+                        double wb, wa;
+                        rvb_ws_for_flip(R, b, R->cstate[s] ? s : os, &wb, &wa);
+                        bc_insert(&R->bonds_before, b, NONE, wb), bc_insert(&R->bonds_after, b, NONE, wa);
+                    }
+                }
+            }
+        }
+    }
+    mult *= rvb_calculate_mult(&R->bonds_before, &R->bonds_after, n_bonds);
+    return mult;
+}
+/* the "Now update bonds" block of mutate_graph, :561-593 */
+static void rvb_mutate_update_bonds(Rvb *R, const Node *op) {
+    const OrcSse *g = R->g;
+    for (int r = 0; r < op->nv; r++) {
+        const uint32_t v = op->vars[r];
+        const int64_t s = R->v2s[v];
+        if (s == NONE) continue;
+        for (uint32_t k = R->vb_start[v]; k < R->vb_start[v + 1]; k++) {
+            const uint32_t b = R->vb_list[k];
+            const int64_t os = R->v2s[rvb_other_var(g, v, b)];
+            if (os == NONE) continue;
+            if (R->cstate[s] == R->cstate[os]) {
+                if (bc_contains(&R->bonds, b, NONE)) bc_remove(&R->bonds, b, NONE);
+            } else {
+                bc_insert(&R->bonds, b, NONE, rvb_edge_weight(g, b, R->substate[R->v2s[g->ea[b]]], R->substate[R->v2s[g->eb[b]]]));
+            }
+        }
+    }
+}
+/* mutate_graph, :294-616 */
+static void rvb_mutate_graph(Rvb *R) {
+    OrcSse *g = R->g;
+    uint64_t *jump_to = (uint64_t *)malloc((R->ntog + 2) * sizeof(uint64_t));
+    uint64_t *cont_until = (uint64_t *)malloc((R->ntog + 2) * sizeof(uint64_t));
+    uint64_t nj = 0, nc = 0, count = 0;
+    for (uint32_t s = 0; s < R->nsub; s++) count += R->cstate[s];
+    if (count != 0) {
+        jump_to[nj++] = 0;
+        for (uint32_t s = 0; s < R->nsub; s++) R->substate[s] ^= R->cstate[s];
+    }
+    for (uint64_t t = 0; t < R->ntog; t++) {
+        const uint64_t p = R->toggles[t];
+        if (count == 0) jump_to[nj++] = p;
+        const Node *op = &g->ops[p];
+        for (int r = 0; r < op->nv; r++) {
+            const int64_t s = R->v2s[op->vars[r]];
+            if (s == NONE) continue;
+            R->cstate[s] = !R->cstate[s];
+            if (R->cstate[s]) count++;
+            else count--;
+        }
+        if (count == 0) cont_until[nc++] = p;
+    }
+    if (count != 0) cont_until[nc++] = g->ops_len; /* rvb.get_cutoff() = ops.len(), fast_ops.rs:1255-1257 */
+    if (nj != nc) g->error |= 64;
+    bc_clear(&R->bonds);
+    uint64_t next_ci = 0;
+    for (uint32_t s = 0; s < R->nsub && !(g->error & 64); s++) { /* :366-381 */
+        if (!R->cstate[s]) continue;
+        const uint32_t v = R->subvars[s];
+        for (uint32_t k = R->vb_start[v]; k < R->vb_start[v + 1]; k++) {
+            const uint32_t b = R->vb_list[k];
+            const int64_t os = R->v2s[rvb_other_var(g, v, b)];
+            if (os == NONE) { g->error |= 64; break; }
+            if (!R->cstate[os])
+                bc_insert(&R->bonds, b, NONE, rvb_edge_weight(g, b, R->substate[R->v2s[g->ea[b]]], R->substate[R->v2s[g->eb[b]]]));
+        }
+    }
+    for (uint64_t k = 0; k < nj && k < nc && !(g->error & 64); k++) {
+        const uint64_t from = jump_to[k], until = cont_until[k];
+        /* get_propagated_substate_with_hint (fast_ops.rs:1027-1172): the state just before `from` */
+        for (uint32_t s = 0; s < R->nsub; s++) {
+            const uint32_t v = R->subvars[s];
+            int val = g->state[v];
+            for (uint64_t x = from; x-- > 0;) {
+                const Node *nd = &g->ops[x];
+                if (!nd->present) continue;
+                int hit = 0;
+                for (int r = 0; r < nd->nv; r++)
+                    if (nd->vars[r] == v) val = nd->out[r], hit = 1;
+                if (hit) break;
+            }
+            R->substate[s] = (uint8_t)(val ^ R->cstate[s]); /* :396-399 */
+        }
+        /* mutate_subsection_ops (fast_ops.rs:639-775): ops with p in [from, until] on the sub-variables' world lines */
+        for (uint64_t p = from; p <= until && p < g->ops_len && !(g->error & 64); p++) {
+            Node *op = &g->ops[p];
+            if (!op->present || !rvb_near(R, op)) continue;
+            const int in_bonds = bc_contains(&R->bonds, op->bond, NONE);
+            const int at_next = next_ci < R->ntog && p == R->toggles[next_ci];
+            if (in_bonds) { /* :411-432: rotate the diagonal op onto a bond drawn from the border */
+                const int64_t i = bc_get_random(&R->bonds, g);
+                if (i == NONE) break;
+                const uint32_t nb = (uint32_t)R->bonds.keys[i].v;
+                const int64_t sa = R->v2s[g->ea[nb]], sb = R->v2s[g->eb[nb]];
+                if (sa == NONE || sb == NONE) { g->error |= 64; break; }
+                op->nv = 2, op->vars[0] = g->ea[nb], op->vars[1] = g->eb[nb], op->bond = nb;
+                op->in[0] = op->out[0] = R->substate[sa], op->in[1] = op->out[1] = R->substate[sb];
+                continue; /* constant stays op.is_constant() */
+            }
+            const Node old = *op; /* the bonds are updated with the vars of the op as it was (same vars either way) */
+            if (at_next) { /* :434-469 */
+                for (int r = 0; r < op->nv; r++) {
+                    const int64_t s = R->v2s[op->vars[r]];
+                    if (s == NONE) { g->error |= 64; break; }
+                    op->in[r] = op->in[r] != R->cstate[s];
+                    op->out[r] = op->out[r] != !R->cstate[s];
+                }
+                for (int r = 0; r < op->nv && !(g->error & 64); r++) {
+                    const int64_t s = R->v2s[op->vars[r]];
+                    R->cstate[s] = !R->cstate[s];
+                    R->substate[s] = op->out[r];
+                }
+                next_ci++;
+            } else { /* :470-557 */
+                int any_in_cluster = 0;
+                for (int r = 0; r < op->nv; r++) {
+                    const int64_t s = R->v2s[op->vars[r]];
+                    if (s != NONE && R->cstate[s]) any_in_cluster = 1;
+                }
+                if (!any_in_cluster && node_is_diagonal(op)) {
+                } else if (any_in_cluster) {
+                    for (int r = 0; r < op->nv; r++) {
+                        if (R->v2s[op->vars[r]] == NONE) { g->error |= 64; break; }
+                        op->in[r] = !op->in[r], op->out[r] = !op->out[r];
+                    }
+                    if (!node_is_diagonal(op))
+                        for (int r = 0; r < op->nv && !(g->error & 64); r++) R->substate[R->v2s[op->vars[r]]] = op->out[r];
+                } else {
+                    int k2 = 0; /* filter_map(var_to_subvar).zip(outputs): the k-th sub-variable takes output k */
+                    for (int r = 0; r < op->nv; r++)
+                        if (R->v2s[op->vars[r]] != NONE) R->substate[R->v2s[op->vars[r]]] = op->out[k2++];
+                }
+            }
+            rvb_mutate_update_bonds(R, &old);
+        }
+    }
+    free(jump_to), free(cont_until);
+}
+/* contiguous_bits, rvb.rs:1190-1192: next_u64().trailing_ones() */
+static uint64_t rvb_contiguous_bits(Stream *s) {
+    uint64_t x = next_u64(s);
+    return ~x == 0 ? 64u : (uint64_t)__builtin_ctzll(~x);
+}
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+/* RvbUpdater::rvb_update_with_ising_weight as QmcIsingGraph calls it (qmc_ising.rs:705-752): returns the successes */
+uint64_t orc_sse_rvb_update(OrcSse *g, uint64_t updates) {
+    if (g->is_qmc) { g->error |= 64; return 0; }
+    Rvb R;
+    memset(&R, 0, sizeof(R));
+    R.g = g;
+    const uint32_t N = g->nvars, E = g->nedges;
+    /* make_classical_bonds */
+    R.vb_start = (uint32_t *)calloc(N + 2, sizeof(uint32_t));
+    R.vb_list = (uint32_t *)malloc((2 * (size_t)E + 1) * sizeof(uint32_t));
+    for (uint32_t b = 0; b < E; b++) R.vb_start[g->ea[b] + 1]++, R.vb_start[g->eb[b] + 1]++;
+    for (uint32_t v = 0; v < N; v++) R.vb_start[v + 1] += R.vb_start[v];
+    {
+        uint32_t *fill = (uint32_t *)calloc(N + 1, sizeof(uint32_t));
+        for (uint32_t b = 0; b < E; b++) {
+            R.vb_list[R.vb_start[g->ea[b]] + fill[g->ea[b]]++] = b;
+            R.vb_list[R.vb_start[g->eb[b]] + fill[g->eb[b]]++] = b;
+        }
+        free(fill);
+    }
+    /* find_constants, rvb.rs:1162-1188 (constant_ops_on_var, fast_ops.rs:1466-1480: p order on each variable) */
+    R.var_starts = (uint64_t *)calloc(N + 1, sizeof(uint64_t));
+    R.var_lengths = (uint64_t *)calloc(N + 1, sizeof(uint64_t));
+    R.zero_vars = (uint32_t *)malloc((N + 1) * sizeof(uint32_t));
+    for (uint64_t p = 0; p < g->ops_len; p++) {
+        const Node *nd = &g->ops[p];
+        if (nd->present && nd->constant) {
+            if (nd->nv != 1) g->error |= 64;
+            R.var_lengths[nd->vars[0]]++, R.ncp++;
+        }
+    }
+    R.constant_ps = (uint64_t *)malloc((R.ncp + 1) * sizeof(uint64_t));
+    {
+        uint64_t acc = 0;
+        for (uint32_t v = 0; v < N; v++) {
+            R.var_starts[v] = acc, acc += R.var_lengths[v];
+            if (R.var_lengths[v] == 0) R.zero_vars[R.nzero++] = v;
+        }
+        uint64_t *fill = (uint64_t *)calloc(N + 1, sizeof(uint64_t));
+        for (uint64_t p = 0; p < g->ops_len; p++) {
+            const Node *nd = &g->ops[p];
+            if (nd->present && nd->constant && nd->nv == 1) R.constant_ps[R.var_starts[nd->vars[0]] + fill[nd->vars[0]]++] = p;
+        }
+        free(fill);
+    }
+    R.pos_popped = (uint8_t *)calloc(R.ncp + N + 1, 1);
+    R.nopos_popped = (uint8_t *)calloc(N + 1, 1);
+    R.cl_vars = (int64_t *)malloc(80 * sizeof(int64_t)), R.cl_flips = (int64_t *)malloc(80 * sizeof(int64_t));
+    R.subvars = (uint32_t *)malloc((N + 1) * sizeof(uint32_t));
+    R.v2s = (int64_t *)malloc((N + 1) * sizeof(int64_t));
+    R.cstate = (uint8_t *)malloc(N + 1), R.substate = (uint8_t *)malloc(N + 1);
+    R.toggles = (uint64_t *)malloc(170 * sizeof(uint64_t));
+    uint8_t *mark = (uint8_t *)calloc(N + 1, 1);
+    uint64_t num_succ = 0;
+    for (uint64_t u = 0; u < updates && !g->error && !g->rng.error; u++) {
+        const uint64_t choice = gen_range_usize(&g->rng, R.ncp + R.nzero); /* rvb.rs:125 */
+        uint32_t v;
+        int64_t flip;
+        if (choice < R.ncp) { /* :126-139: the last variable whose start is <= choice */
+            uint32_t lo = 0;
+            for (uint32_t i = 0; i < N; i++)
+                if (R.var_starts[i] <= choice) lo = i;
+            v = lo, flip = (int64_t)choice;
+        } else {
+            v = R.zero_vars[choice - R.ncp], flip = NONE;
+        }
+        const uint64_t cluster_size = rvb_contiguous_bits(&g->rng) + 1;
+        /* fresh boundary manager (:152) */
+        bc_clear(&R.b_flips), bc_clear(&R.b_noflips);
+        memset(R.pos_popped, 0, R.ncp + N + 1), memset(R.nopos_popped, 0, N + 1);
+        R.ncl = 0;
+        rvb_build_cluster(&R, cluster_size, v, flip, g->ops_len);
+        if (g->error || g->rng.error) break;
+        /* dissolve_into (:987-1007) + sub-variables (:168-180) */
+        R.nsub = 0;
+        for (uint64_t i = 0; i < R.ncl; i++) mark[R.cl_vars[i]] = 1;
+        for (uint64_t i = 0; i < R.b_flips.len; i++) mark[R.b_flips.keys[i].v] = 1;
+        for (uint64_t i = 0; i < R.b_noflips.len; i++) mark[R.b_noflips.keys[i].v] = 1;
+        for (uint32_t w = 0; w < N; w++) {
+            R.v2s[w] = NONE;
+            if (mark[w]) R.v2s[w] = R.nsub, R.subvars[R.nsub++] = w, mark[w] = 0;
+        }
+        memset(R.cstate, 0, R.nsub);
+        R.ntog = 0;
+        for (uint64_t i = 0; i < R.ncl; i++) { /* :182-203 */
+            const int64_t s = R.v2s[R.cl_vars[i]], fi = R.cl_flips[i];
+            if (fi != NONE) {
+                const uint64_t vstart = R.var_starts[R.cl_vars[i]], fi_rel = (uint64_t)fi - vstart;
+                if (fi_rel + 1 >= R.var_lengths[R.cl_vars[i]]) {
+                    R.cstate[s] = 1;
+                    R.toggles[R.ntog++] = R.constant_ps[fi], R.toggles[R.ntog++] = R.constant_ps[vstart];
+                } else {
+                    R.toggles[R.ntog++] = R.constant_ps[fi], R.toggles[R.ntog++] = R.constant_ps[fi + 1];
+                }
+            } else {
+                R.cstate[s] = 1;
+            }
+        }
+        for (uint32_t s = 0; s < R.nsub; s++) R.substate[s] = g->state[R.subvars[s]];
+        qsort(R.toggles, R.ntog, sizeof(uint64_t), cmp_u64);
+        { /* remove_doubles, vec_help.rs:2-23 */
+            uint64_t ii = 0, jj = 0;
+            while (jj + 1 < R.ntog) {
+                if (R.toggles[jj] == R.toggles[jj + 1]) jj += 2;
+                else R.toggles[ii++] = R.toggles[jj++];
+            }
+            if (jj < R.ntog) R.toggles[ii++] = R.toggles[jj++];
+            R.ntog = ii;
+        }
+        const double p_to_flip = rvb_calculate_flip_prob(&R);
+        if (g->error) break;
+        const int should_mutate = p_to_flip >= 1.0 ? 1 : gen_bool(&g->rng, p_to_flip);
+        if (should_mutate) {
+            rvb_mutate_graph(&R);
+            int starting = 0;
+            for (uint32_t s = 0; s < R.nsub; s++) starting |= R.cstate[s];
+            if (starting)
+                for (uint32_t s = 0; s < R.nsub; s++) g->state[R.subvars[s]] ^= R.cstate[s];
+            num_succ++;
+        }
+    }
+    rebuild_links(g);
+    free(R.vb_start), free(R.vb_list), free(R.var_starts), free(R.var_lengths), free(R.constant_ps), free(R.zero_vars);
+    free(R.pos_popped), free(R.nopos_popped), free(R.cl_vars), free(R.cl_flips), free(R.subvars), free(R.v2s);
+    free(R.cstate), free(R.substate), free(R.toggles), free(mark);
+    bc_free(&R.b_flips), bc_free(&R.b_noflips), bc_free(&R.bonds), bc_free(&R.bonds_before), bc_free(&R.bonds_after);
+    return num_succ;
+}
+
+/* set_run_rvb (qmc_ising.rs:434-441), rvb_success_rate (:604-607), single_rvb_sweep (:322-420) */
+void orc_sse_set_run_rvb(OrcSse *g, int run_rvb) { g->run_rvb = run_rvb != 0; }
+double orc_sse_rvb_success_rate(const OrcSse *g) { return (double)g->total_rvb_successes / (double)g->rvb_clusters_counted; }
+uint64_t orc_sse_single_rvb_sweep(OrcSse *g, int64_t updates_in_sweep, uint64_t *steps_out) {
+    uint64_t steps = updates_in_sweep >= 0 ? (uint64_t)updates_in_sweep : ((uint64_t)g->nvars + 1) / 2;
+    if (steps_out) *steps_out = steps;
+    return orc_sse_rvb_update(g, steps);
+}
+
+/* QmcIsingGraph::timestep, qmc_ising.rs:644-795 (rvb off by default, :122; when on it runs between the diagonal and the
+ * cluster update, :705-752) */
 void orc_sse_timestep(OrcSse *g, double beta, int mode) {
     if (g->is_qmc) {
         orc_qmc_timestep(g, beta, mode);
         return;
     }
     diagonal_step(g, beta, mode);
+    if (g->run_rvb) {
+        const uint64_t steps = ((uint64_t)g->nvars + 1) / 2; /* :711 */
+        g->total_rvb_successes += orc_sse_rvb_update(g, steps);
+        g->rvb_clusters_counted += steps;
+    }
     cluster_and_free_spins(g, mode);
     uint64_t grown = g->n + g->n / 2; /* :786 */
     if (grown > g->cutoff) g->cutoff = grown;

@@ -66,6 +66,13 @@ int orc_qmc_make_interaction(OrcSse *g, const double *mat, uint32_t len, const u
 int orc_qmc_flags(const OrcSse *g); /* bit 0 has_cluster_edges, bit 1 breaks_ising_symmetry */
 void orc_qmc_timestep(OrcSse *g, double beta, int mode);
 void orc_sse_use_small_rng(OrcSse *g); /* TIMING ONLY: xoshiro256++ words (the generator the reference's benches use) instead of Philox */
+/* RVB update (rvb.rs:60-291 as QmcIsingGraph::timestep calls it, qmc_ising.rs:705-752): `updates` cluster proposals,
+ * returns the number accepted; set_run_rvb (:434-441), single_rvb_sweep (:322-420; updates_in_sweep < 0 = None),
+ * rvb_success_rate (:604-607).  orc_sse_error() bit 64 = the reference would have panicked inside the update. */
+uint64_t orc_sse_rvb_update(OrcSse *g, uint64_t updates);
+void orc_sse_set_run_rvb(OrcSse *g, int run_rvb);
+uint64_t orc_sse_single_rvb_sweep(OrcSse *g, int64_t updates_in_sweep, uint64_t *steps_out);
+double orc_sse_rvb_success_rate(const OrcSse *g);
 void orc_qmc_loop_update(OrcSse *g);                      /* Qmc::loop_update, qmc_runner.rs:205-220 -> directed_loop.rs:103-301 */
 void orc_qmc_set_do_loop_updates(OrcSse *g, int enable);  /* qmc_runner.rs:268-270 */
 void orc_sse_single_diagonal_step(OrcSse *g, double beta);

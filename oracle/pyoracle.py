@@ -66,6 +66,10 @@ def lib():
     sig("orc_qmc_flags", C.c_int, vp)
     sig("orc_sse_use_small_rng", None, vp)
     sig("orc_qmc_loop_update", None, vp)
+    sig("orc_sse_rvb_update", C.c_uint64, vp, C.c_uint64)
+    sig("orc_sse_set_run_rvb", None, vp, C.c_int)
+    sig("orc_sse_single_rvb_sweep", C.c_uint64, vp, C.c_int64, u64p)
+    sig("orc_sse_rvb_success_rate", C.c_double, vp)
     sig("orc_qmc_set_do_loop_updates", None, vp, C.c_int)
     sig("orc_sse_single_diagonal_step", None, vp, C.c_double)
     sig("orc_sse_single_diagonal_step_mode", None, vp, C.c_double, C.c_int)
@@ -173,6 +177,20 @@ class SseOracle:
     def set_enable_heatbath(self, enable):
         """QmcIsingGraph::set_enable_heatbath (qmc_ising.rs:444-486)"""
         lib().orc_sse_set_enable_heatbath(self._h, int(bool(enable)))
+
+    def set_run_rvb(self, run_rvb):  # qmc_ising.rs:434-441
+        lib().orc_sse_set_run_rvb(self._h, int(bool(run_rvb)))
+
+    def rvb_update(self, updates):  # rvb.rs:60-291 as qmc_ising.rs:705-752 calls it; returns the successes
+        return int(lib().orc_sse_rvb_update(self._h, int(updates)))
+
+    def single_rvb_sweep(self, updates_in_sweep=None):  # qmc_ising.rs:322-420 -> (successes, attempts)
+        steps = C.c_uint64(0)
+        succ = lib().orc_sse_single_rvb_sweep(self._h, -1 if updates_in_sweep is None else int(updates_in_sweep), C.byref(steps))
+        return int(succ), int(steps.value)
+
+    def rvb_success_rate(self):  # qmc_ising.rs:604-607
+        return float(lib().orc_sse_rvb_success_rate(self._h))
 
     def timestep(self, beta, mode=MODE_STRICT):
         lib().orc_sse_timestep(self._h, beta, mode)
