@@ -165,6 +165,17 @@ int qmcb_single_cluster_step(QmcbHandle *h, uint64_t *n_clusters_out /* [R] or N
 int qmcb_loop_update(QmcbHandle *h);
 int qmcb_set_do_loop_updates(QmcbHandle *h, int enable);
 int qmcb_get_do_loop_updates(const QmcbHandle *h, int *enabled);
+/* RVB update (RvbUpdater::rvb_update_with_ising_weight, rvb.rs:60-291, with build_cluster :1054-1122, calculate_flip_prob
+ * :649-946, mutate_graph :294-616 and BondContainer util/bondcontainer.rs).  qmcb_set_run_rvb = QmcIsingGraph::set_run_rvb
+ * (qmc_ising.rs:434-441): every sweep then runs (nvars + 1) / 2 RVB updates between the diagonal and the cluster update
+ * (:705-752), in every mode (the update draws from the replica's sequential stream).  qmcb_single_rvb_sweep =
+ * single_rvb_sweep (:322-420; updates_in_sweep < 0 = None); qmcb_rvb_success_rate = rvb_success_rate (:604-607), any
+ * output may be NULL.  Handles made by qmcb_create only (Qmc has no RVB step).  The flag and the two counters are not
+ * part of the checkpoint blob: set the flag again after qmcb_checkpoint_load. */
+int qmcb_set_run_rvb(QmcbHandle *h, int run_rvb);
+int qmcb_get_run_rvb(const QmcbHandle *h, int *run_rvb);
+int qmcb_single_rvb_sweep(QmcbHandle *h, int64_t updates_in_sweep, uint64_t *successes_out /* [R] or NULL */, uint64_t *attempts_out /* or NULL */);
+int qmcb_rvb_success_rate(QmcbHandle *h, double *rate_out /* [R] */, uint64_t *successes_out /* [R] */, uint64_t *counted_out /* [R] */);
 /* sum over replicas and sweeps so far of n after each sweep (the metric's "vertex updates") */
 int qmcb_total_vertex_updates(QmcbHandle *h, uint64_t *total);
 /* number of kernels this handle has launched so far */

@@ -66,6 +66,10 @@ SIGNATURES = {
     "qmcb_loop_update": [vp],
     "qmcb_set_do_loop_updates": [vp, C.c_int],
     "qmcb_get_do_loop_updates": [vp, C.POINTER(C.c_int)],
+    "qmcb_set_run_rvb": [vp, C.c_int],
+    "qmcb_get_run_rvb": [vp, C.POINTER(C.c_int)],
+    "qmcb_single_rvb_sweep": [vp, C.c_int64, u64p, u64p],
+    "qmcb_rvb_success_rate": [vp, f64p, u64p, u64p],
     "qmcb_total_vertex_updates": [vp, u64p],
     "qmcb_launch_count": [vp, u64p],
     "qmcb_get_state": [vp, C.c_uint32, u8p],

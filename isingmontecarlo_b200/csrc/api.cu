@@ -33,6 +33,7 @@ int launch_sse_fast(const SseDev &D, const SseTuning &T, uint64_t target, uint32
                     uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
 int launch_sse_counter(const SseDev &D, const SseTuning &T, uint64_t target, uint32_t phases, uint64_t sample_freq, uint64_t sample_origin,
                        uint8_t *samples, uint64_t samples_per_rep, cudaStream_t st);  // returns #launches, <0 unsupported
+int launch_sse_rvb(const SseDev &D, const RvbDev &W, uint64_t target, long long updates, unsigned long long *succ_out, cudaStream_t st);
 int launch_pt_export(const SseDev &D, const PtDev &P, uint64_t *rec, cudaStream_t st);
 void launch_pt_apply(const SseDev &D, const PtDev &P, const uint64_t *rec, uint32_t S, cudaStream_t st);
 void launch_cls_generic(const ClsDev &D, uint32_t colour, uint32_t cstart, uint32_t ccount, uint64_t sweep, cudaStream_t st);
@@ -135,6 +136,10 @@ struct QmcbHandle {
     std::vector<double> gw2_h, ggam_h;
     // kernel-selection knobs of the warp-parallel sweep (qmcb_set_option), per handle
     SseTuning tune{};
+    // RVB update (qmc_ising.rs:39-43: run_rvb_steps, classical_bonds, the two success counters)
+    bool rvb_on = false, rvb_ws = false;
+    RvbDev W{};
+    unsigned long long *rvb_succ_last = nullptr;  // [R] successes of the last qmcb_single_rvb_sweep
 };
 
 static void pt_comm_release(QmcbHandle *h);
@@ -168,6 +173,54 @@ static int alloc_counter_ws(QmcbHandle *h) {
     CUDA_TRY(h->pool.alloc(&D.sid, (size_t)D.R * D.cap));
     h->counter_ws = true;
     return QMCB_OK;
+}
+
+// RVB workspace: scratch only (every launch starts from an empty workspace), sized by the capacity; the lattice's
+// classical_bonds table and the two counters are made once
+static int alloc_rvb_ws(QmcbHandle *h) {
+    if (h->rvb_ws) return QMCB_OK;
+    SseDev &D = h->D;
+    RvbDev &W = h->W;
+    if (!W.vb_start) {
+        std::vector<uint32_t> start(D.N + 1, 0), list(2 * (size_t)D.E + 1), fill(D.N, 0);
+        for (uint32_t b = 0; b < D.E; b++) start[h->va_h[b] + 1]++, start[h->vb_h[b] + 1]++;
+        for (uint32_t v = 0; v < D.N; v++) start[v + 1] += start[v];
+        for (uint32_t b = 0; b < D.E; b++) {  // bond order: edge_lookup[a].push(bond); edge_lookup[b].push(bond)
+            list[start[h->va_h[b]] + fill[h->va_h[b]]++] = b;
+            list[start[h->vb_h[b]] + fill[h->vb_h[b]]++] = b;
+        }
+        uint32_t *sd, *ld;
+        CUDA_TRY(h->pool.alloc(&sd, start.size()));
+        CUDA_TRY(h->pool.alloc(&ld, list.size()));
+        CUDA_TRY(cudaMemcpy(sd, start.data(), sizeof(uint32_t) * start.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(ld, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice));
+        W.vb_start = sd, W.vb_list = ld;
+        CUDA_TRY(h->pool.alloc(&W.succ, D.R));
+        CUDA_TRY(h->pool.alloc(&W.count, D.R));
+        CUDA_TRY(h->pool.alloc(&h->rvb_succ_last, D.R));
+        CUDA_TRY(cudaMemset(W.succ, 0, sizeof(unsigned long long) * D.R));
+        CUDA_TRY(cudaMemset(W.count, 0, sizeof(unsigned long long) * D.R));
+        CUDA_TRY(cudaMemset(h->rvb_succ_last, 0, sizeof(unsigned long long) * D.R));
+    }
+    W.stride32 = rvb_stride32(D), W.stride64 = rvb_stride64(D), W.stride8 = rvb_stride8(D);
+    cudaError_t e = h->pool.alloc(&W.u32, (size_t)D.R * W.stride32);
+    if (e == cudaSuccess) e = h->pool.alloc(&W.f64, (size_t)D.R * W.stride64);
+    if (e == cudaSuccess) e = h->pool.alloc(&W.u8, (size_t)D.R * W.stride8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        h->pool.release(W.u32), h->pool.release(W.f64), h->pool.release(W.u8);
+        W.u32 = nullptr, W.f64 = nullptr, W.u8 = nullptr;
+        return fail(QMCB_ERR_CAPACITY, "out of device memory for the RVB workspace");
+    }
+    h->rvb_ws = true;
+    return QMCB_OK;
+}
+static void release_rvb_ws(QmcbHandle *h) {  // the capacity changed: the next RVB launch allocates for the new one
+    if (!h->rvb_ws) return;
+    RvbDev &W = h->W;
+    h->pool.release(W.u32), h->pool.release(W.f64), h->pool.release(W.u8);
+    W.u32 = nullptr, W.f64 = nullptr, W.u8 = nullptr;
+    h->rvb_ws = false;
 }
 
 // re-layout every per-slot array for a larger per-replica capacity
@@ -206,6 +259,7 @@ static int grow(QmcbHandle *h, uint64_t newcap) {
     D.ent = nent;
     D.ops = nops, D.bits = nbits, D.frozen = nfrozen, D.rec = nrec, D.frontier = nfrontier, D.interior = ninterior, D.parent = nparent, D.sid = nsid;
     D.cap = newcap;
+    release_rvb_ws(h);
     return QMCB_OK;
 }
 
@@ -226,6 +280,35 @@ static int status_to_error(int st) {
 
 static int launch_sweeps(QmcbHandle *h, uint32_t phases, uint64_t freq, uint64_t origin, uint8_t *samples_dev, uint64_t spr) {
     int rc;
+    if (h->rvb_on && (phases & 0xFu) == 0xFu) {
+        // QmcIsingGraph::timestep with run_rvb_steps (qmc_ising.rs:644-795): diagonal update, RVB update (:705-752), cluster
+        // update, in three launches per sweep; every launch takes only the replicas whose next sweep is `tgt`
+        if ((rc = alloc_rvb_ws(h))) return rc;
+        if (h->mode == QMCB_MODE_STRICT && (rc = alloc_strict_ws(h))) return rc;
+        if ((h->mode != QMCB_MODE_STRICT || h->impl != 1) && (rc = alloc_fast_ws(h))) return rc;
+        if (h->mode == QMCB_MODE_COUNTER && (rc = alloc_counter_ws(h))) return rc;
+        auto part = [&](uint64_t tgt, uint32_t ph, uint8_t *smp, uint64_t sp) {
+            int nl = -1;
+            if (h->impl != 1) {
+                if (h->mode == QMCB_MODE_COUNTER) nl = launch_sse_counter(h->D, h->tune, tgt, ph, freq, origin, smp, sp, h->stream);
+                else if (h->mode == QMCB_MODE_FAST || ph == (1u | 16u)) nl = launch_sse_fast(h->D, h->tune, tgt, ph, freq, origin, smp, sp, h->stream);
+            }
+            if (nl < 0) {
+                const int wl = launch_sse_serial(h->D, h->mode == QMCB_MODE_STRICT ? 0 : (h->mode == QMCB_MODE_FAST ? 1 : 2), tgt, ph, freq, origin, smp, sp,
+                                                 h->mode == QMCB_MODE_STRICT && h->impl != 1 ? h->strict_layout : 0, h->stream);
+                if (ph & 2u) h->strict_wl_last = wl != 0;
+                nl = wl == 2 ? 2 : 1;
+            }
+            h->launches += (uint64_t)nl;
+        };
+        for (uint64_t tgt = origin + 1; tgt <= h->target; tgt++) {
+            part(tgt, 1u | 16u, nullptr, 0);
+            h->launches += (uint64_t)launch_sse_rvb(h->D, h->W, tgt, -1, nullptr, h->stream);
+            part(tgt, 2u | 4u | 8u | 16u, samples_dev, spr);
+        }
+        CUDA_TRY(cudaGetLastError());
+        return QMCB_OK;
+    }
     if (h->mode == QMCB_MODE_STRICT) {
         if ((rc = alloc_strict_ws(h))) return rc;
         const bool full = (phases & 0xFu) == 0xFu;
@@ -974,6 +1057,59 @@ extern "C" int qmcb_single_cluster_step(QmcbHandle *h, uint64_t *ncl_out) {
         std::vector<uint32_t> ncl(h->D.R);
         CUDA_TRY(cudaMemcpy(ncl.data(), h->D.ncl, sizeof(uint32_t) * h->D.R, cudaMemcpyDeviceToHost));
         for (uint32_t r = 0; r < h->D.R; r++) ncl_out[r] = ncl[r];
+    }
+    return QMCB_OK;
+}
+// QmcIsingGraph::set_run_rvb (qmc_ising.rs:434-441)
+extern "C" int qmcb_set_run_rvb(QmcbHandle *h, int run_rvb) {
+    CHECK_H(h);
+    if (run_rvb && h->generic) return fail(QMCB_ERR_UNSUPPORTED, "the RVB update belongs to QmcIsingGraph (qmc_ising.rs:705-752); Qmc has none");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (run_rvb) {
+        int rc = alloc_rvb_ws(h);
+        if (rc) return rc;
+    }
+    h->rvb_on = run_rvb != 0;
+    return QMCB_OK;
+}
+extern "C" int qmcb_get_run_rvb(const QmcbHandle *h, int *run_rvb) {
+    if (!h || !run_rvb) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    *run_rvb = h->rvb_on ? 1 : 0;
+    return QMCB_OK;
+}
+// QmcIsingGraph::single_rvb_sweep (qmc_ising.rs:322-420): updates_in_sweep < 0 = None = (nvars + 1) / 2
+extern "C" int qmcb_single_rvb_sweep(QmcbHandle *h, int64_t updates_in_sweep, uint64_t *successes_out, uint64_t *attempts_out) {
+    CHECK_H(h);
+    if (h->generic) return fail(QMCB_ERR_UNSUPPORTED, "the RVB update belongs to QmcIsingGraph (qmc_ising.rs:322-420); Qmc has none");
+    int rc = ensure_capacity(h);
+    if (rc || (rc = alloc_rvb_ws(h))) return rc;
+    h->launches += (uint64_t)launch_sse_rvb(h->D, h->W, 0, updates_in_sweep < 0 ? -1 : (long long)updates_in_sweep, h->rvb_succ_last, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    int st = 0;
+    if ((rc = check_status(h, &st)) || (rc = status_to_error(st))) return rc;
+    if (successes_out) {
+        static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+        CUDA_TRY(cudaMemcpy(successes_out, h->rvb_succ_last, sizeof(uint64_t) * h->D.R, cudaMemcpyDeviceToHost));
+    }
+    if (attempts_out) *attempts_out = updates_in_sweep < 0 ? ((uint64_t)h->D.N + 1) / 2 : (uint64_t)updates_in_sweep;
+    return QMCB_OK;
+}
+// QmcIsingGraph::rvb_success_rate (qmc_ising.rs:604-607) of every replica: total_rvb_successes / rvb_clusters_counted
+// (NaN before the first sweep with RVB steps, as 0 / 0 is in the reference); the two totals on request
+extern "C" int qmcb_rvb_success_rate(QmcbHandle *h, double *rate_out, uint64_t *successes_out, uint64_t *counted_out) {
+    CHECK_H(h);
+    if (!rate_out && !successes_out && !counted_out) return fail(QMCB_ERR_BAD_ARG, "null argument");
+    const uint32_t R = h->D.R;
+    std::vector<uint64_t> s(R, 0), c(R, 0);
+    if (h->W.succ) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaMemcpy(s.data(), h->W.succ, sizeof(uint64_t) * R, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(c.data(), h->W.count, sizeof(uint64_t) * R, cudaMemcpyDeviceToHost));
+    }
+    for (uint32_t r = 0; r < R; r++) {
+        if (rate_out) rate_out[r] = (double)s[r] / (double)c[r];
+        if (successes_out) successes_out[r] = s[r];
+        if (counted_out) counted_out[r] = c[r];
     }
     return QMCB_OK;
 }

@@ -106,13 +106,23 @@ class QmcIsingGraph:
         self.mode = mode
 
     def set_run_rvb(self, run_rvb):
-        """QmcIsingGraph::set_run_rvb (qmc_ising.rs:434-441).  The RVB update (rvb.rs) is not built (DESIGN.md section 0):
-        off -- the reference's default (:122) -- is accepted, on is refused."""
-        if run_rvb:
-            raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "the RVB update (rvb.rs:60-291) is not offered")
+        """QmcIsingGraph::set_run_rvb (qmc_ising.rs:434-441): (nvars + 1) / 2 RVB updates (rvb.rs:60-291) in every sweep, between
+        the diagonal and the cluster update (:705-752)."""
+        check(self._L.qmcb_set_run_rvb(self._h, int(bool(run_rvb))))
 
-    def single_rvb_sweep(self, updates_in_sweep=None):  # qmc_ising.rs:322-420
-        raise _lib.QmcbError(_lib.ERR_UNSUPPORTED, "the RVB update (rvb.rs:60-291) is not offered")
+    def single_rvb_sweep(self, updates_in_sweep=None):
+        """qmc_ising.rs:322-420 for every replica: (successes per replica, attempts)."""
+        succ = np.zeros(self.R, dtype=np.uint64)
+        att = C.c_uint64(0)
+        check(self._L.qmcb_single_rvb_sweep(self._h, -1 if updates_in_sweep is None else int(updates_in_sweep),
+                                            succ.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(att)))
+        return succ, int(att.value)
+
+    def rvb_success_rate(self):
+        """qmc_ising.rs:604-607 for every replica (NaN before the first sweep with RVB steps)."""
+        rate = np.zeros(self.R, dtype=np.float64)
+        check(self._L.qmcb_rvb_success_rate(self._h, rate.ctypes.data_as(C.POINTER(C.c_double)), None, None))
+        return rate
 
     def set_enable_heatbath(self, enable_heatbath):
         """qmc_ising.rs:444-486: heat-bath diagonal updates (heatbath.rs:149-209) for every replica."""

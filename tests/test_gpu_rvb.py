@@ -1,0 +1,103 @@
+"""RVB update on the device (sse_rvb.cu: qmcb_set_run_rvb, qmcb_single_rvb_sweep, qmcb_rvb_success_rate) against the
+oracle's restatement of rvb.rs, bit-exact: spins, operator words, stream cursors, success counts -- in all three modes,
+with and without a longitudinal field, through capacity growth, and as a stand-alone sweep."""
+import numpy as np
+import pytest
+
+from isingmontecarlo_b200 import MODE_COUNTER, MODE_FAST, MODE_STRICT, QmcbError, lattices
+from oracle import pyoracle as po
+from tests.ed import tfim_thermal
+from tests.test_gpu_sse_parity import assert_same, make_pair
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, edges, gamma, h, cutoff0, beta, sweeps
+    ("mixed3x3", lattices.two_d_periodic_mixed(3), 0.1, 0.0, 9, 1.0, 40),        # check_rvb_crash.rs:296-315
+    ("mixed4x4", lattices.two_d_periodic_mixed(4), 0.1, 0.0, 16, 1.0, 30),       # :318-337
+    ("two_unit_cell", lattices.two_unit_cell(), 1.0, 0.0, 8, 1.0, 40),           # :340-359
+    ("two_unit_cell_h", lattices.two_unit_cell(), 1.0, 1.0, 8, 1.0, 40),         # longitudinal_crash.rs, rvb cases
+    ("mixed4x4_h", lattices.two_d_periodic_mixed(4), 1.0, -0.4, 16, 2.0, 25),
+    ("tri6_frustrated", lattices.triangular_periodic(6, 1.0), 0.6, 0.0, 36, 2.0, 12),
+    ("tri6_frustrated_h", lattices.triangular_periodic(6, 1.0), 1.0, 0.2, 36, 2.0, 12),
+]
+
+
+@pytest.mark.parametrize("mode,impl", [(MODE_STRICT, 0), (MODE_STRICT, 1), (MODE_FAST, 0), (MODE_COUNTER, 0), (MODE_COUNTER, 1)])
+@pytest.mark.parametrize("name,edges,gamma,h,cutoff,beta,sweeps", CASES)
+def test_sweeps_with_rvb_steps_bit_exact(name, edges, gamma, h, cutoff, beta, sweeps, mode, impl):
+    g, refs = make_pair(edges, gamma, h, cutoff, beta, mode, impl=impl)
+    g.set_run_rvb(True)
+    for ref in refs:
+        ref.set_run_rvb(True)
+    for chunk in (1, 1, 3, sweeps - 5):
+        e_gpu = g.timesteps(chunk, beta)
+        e_ref = [ref.timesteps(chunk, beta, mode) for ref in refs]
+        assert_same(g, refs, f"{name} after +{chunk}")
+        assert np.array_equal(e_gpu, np.array(e_ref)), name
+    assert g.verify()
+    rate = g.rvb_success_rate()
+    assert np.array_equal(rate, np.array([ref.rvb_success_rate() for ref in refs]))
+    assert (rate > 0).all() and (rate < 1).all()
+    # off again: the plain sweep (qmc_ising.rs:705)
+    g.set_run_rvb(False)
+    for ref in refs:
+        ref.set_run_rvb(False)
+    g.timesteps(2, beta)
+    for ref in refs:
+        ref.timesteps(2, beta, mode)
+    assert_same(g, refs, f"{name} rvb off")
+
+
+def test_single_rvb_sweep_matches():
+    edges = lattices.triangular_periodic(6, 1.0)
+    g, refs = make_pair(edges, 0.8, 0.0, 36, 2.0, MODE_STRICT, R=6)
+    g.timesteps(15, 2.0)
+    for ref in refs:
+        ref.timesteps(15, 2.0)
+    for updates in (None, 1, 50):
+        succ, att = g.single_rvb_sweep(updates)
+        want = [ref.single_rvb_sweep(updates) for ref in refs]
+        assert att == want[0][1]
+        assert [int(s) for s in succ] == [w[0] for w in want]
+        assert_same(g, refs, f"single_rvb_sweep({updates})")
+    assert g.verify()
+
+
+def test_rvb_through_capacity_growth():
+    # cutoff 8 -> hundreds of slots: the workspace follows the re-layout of the operator strings
+    edges = lattices.two_unit_cell()
+    g, refs = make_pair(edges, 1.0, 0.0, 8, 6.0, MODE_FAST, R=3)
+    g.set_run_rvb(True)
+    for ref in refs:
+        ref.set_run_rvb(True)
+    g.timesteps(40, 6.0)
+    for ref in refs:
+        ref.timesteps(40, 6.0, MODE_FAST)
+    assert_same(g, refs, "growth")
+    assert g.verify()
+
+
+def test_rvb_energy_matches_exact_diagonalisation_on_the_device():
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = [((0, 1), 1.0), ((1, 2), 1.0), ((2, 0), 1.0), ((2, 3), 1.0), ((3, 4), 1.0), ((4, 2), 1.0)]
+    gamma, beta, R = 0.3, 3.0, 256
+    exact = tfim_thermal(edges, 5, gamma, 0.0, beta)
+    g = QmcIsingGraph(edges, gamma, 0.0, 5, 0xEB0000 + np.arange(R, dtype=np.uint64), beta, mode=MODE_COUNTER)
+    g.set_run_rvb(True)
+    g.timesteps(300, beta)
+    e = g.timesteps(3000, beta)
+    assert g.verify()
+    mean, err = e.mean(), e.std(ddof=1) / np.sqrt(R)
+    assert abs(mean - exact["E"]) < 3.0 * err + 1e-9, (mean, err, exact["E"])
+    assert (g.rvb_success_rate() > 0.2).all()
+
+
+def test_generic_qmc_has_no_rvb():
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    g = QmcIsingGraph(lattices.small_qmc_ring(), 1.0, 0.0, 3, [1, 2], 1.0)
+    q = g.into_qmc()
+    with pytest.raises(QmcbError):
+        q.set_run_rvb(True)  # Qmc::timestep has no RVB step (qmc_runner.rs:363-377)
