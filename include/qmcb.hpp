@@ -166,6 +166,20 @@ public:
     }
     void set_mode(int mode) { check(qmcb_set_mode(h_, mode)); }
     void set_enable_heatbath(bool enable) { check(qmcb_set_enable_heatbath(h_, enable ? 1 : 0)); }  // qmc_ising.rs:444-486
+    // RVB update (rvb.rs:60-291): set_run_rvb qmc_ising.rs:434-441, single_rvb_sweep :322-420 (successes per replica,
+    // attempts), rvb_success_rate :604-607
+    void set_run_rvb(bool run_rvb) { check(qmcb_set_run_rvb(h_, run_rvb ? 1 : 0)); }
+    std::pair<std::vector<uint64_t>, uint64_t> single_rvb_sweep(int64_t updates_in_sweep = -1) {
+        std::vector<uint64_t> succ(replicas_);
+        uint64_t attempts = 0;
+        check(qmcb_single_rvb_sweep(h_, updates_in_sweep, succ.data(), &attempts));
+        return {succ, attempts};
+    }
+    std::vector<double> rvb_success_rate() {
+        std::vector<double> rate(replicas_);
+        check(qmcb_rvb_success_rate(h_, rate.data(), nullptr, nullptr));
+        return rate;
+    }
     // graphs with their own couplings in one batch (tempering_traits.rs:122-154): rows of (J[E], transverse, longitudinal)
     void set_hamiltonians(const std::vector<std::vector<double>> &j_rows, const std::vector<double> &transverse,
                           const std::vector<double> &longitudinal, const std::vector<uint32_t> &ham_of_replica) {

@@ -95,6 +95,24 @@ impl BatchedQmcIsingGraph {
     pub fn set_enable_heatbath(&mut self, enable_heatbath: bool) -> Result<(), String> {
         check(unsafe { sys::qmcb_set_enable_heatbath(self.h, enable_heatbath as i32) })
     }
+    /// QmcIsingGraph::set_run_rvb (qmc_ising.rs:434-441): RVB updates (rvb.rs:60-291) in every sweep
+    pub fn set_run_rvb(&mut self, run_rvb: bool) -> Result<(), String> {
+        check(unsafe { sys::qmcb_set_run_rvb(self.h, run_rvb as i32) })
+    }
+    /// QmcIsingGraph::single_rvb_sweep (qmc_ising.rs:322-420) of every replica: (successes, attempts)
+    pub fn single_rvb_sweep(&mut self, updates_in_sweep: Option<usize>) -> Result<(Vec<u64>, usize), String> {
+        let mut succ = vec![0u64; self.replicas];
+        let mut attempts = 0u64;
+        let updates = updates_in_sweep.map(|u| u as i64).unwrap_or(-1);
+        check(unsafe { sys::qmcb_single_rvb_sweep(self.h, updates, succ.as_mut_ptr(), &mut attempts) })?;
+        Ok((succ, attempts as usize))
+    }
+    /// QmcIsingGraph::rvb_success_rate (qmc_ising.rs:604-607) of every replica
+    pub fn rvb_success_rate(&mut self) -> Result<Vec<f64>, String> {
+        let mut rate = vec![0f64; self.replicas];
+        check(unsafe { sys::qmcb_rvb_success_rate(self.h, rate.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) })?;
+        Ok(rate)
+    }
     /// single_diagonal_step / single_cluster_step (qmc_ising.rs:208-320)
     pub fn single_diagonal_step(&mut self) -> Result<(), String> { check(unsafe { sys::qmcb_single_diagonal_step(self.h) }) }
     pub fn single_cluster_step(&mut self) -> Result<Vec<u64>, String> {

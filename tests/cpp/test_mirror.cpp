@@ -72,6 +72,16 @@ int main() {
             ASSERT(mean > -4.6 && mean < -3.6);
             ASSERT(g.verify());
         }
+        {  // tests/check_rvb_crash.rs:340-359 run_two_unit_cell: set_run_rvb(true), timesteps, verify
+            auto ising = qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 1}, -1.0}, {{1, 2}, 1.0}, {{2, 3}, 1.0}, {{3, 0}, 1.0}, {{1, 7}, 1.0}, {{4, 5}, -1.0}, {{5, 6}, 1.0}, {{6, 7}, 1.0}, {{7, 4}, 1.0}},
+                                                                  1.0, 0.0, 8, seeds, nullptr, mode);
+            ising.set_run_rvb(true);
+            ising.timesteps(200, 1.0);
+            ASSERT(ising.verify());
+            for (double rate : ising.rvb_success_rate()) ASSERT(rate > 0.0 && rate < 1.0);
+            auto sw = ising.single_rvb_sweep();
+            ASSERT(sw.second == (8 + 1) / 2 && ising.verify());
+        }
         {  // convert_test.rs lattice: timestep returns the state, sampling shape
             std::vector<bool> st(3, true);
             auto ising = qmcb::DefaultQmcIsingGraph::new_with_rng({{{0, 1}, 1.0}, {{1, 2}, 1.0}, {{2, 0}, 1.0}}, 1.0, 0.0, 3, {1234}, &st, mode);
