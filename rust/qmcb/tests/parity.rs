@@ -41,6 +41,7 @@ fn reference_reproduces_the_strict_golden_cases() {
             // state = None: the spins are drawn from the stream (classical/graph.rs:451-453), as qmcb_create does
             let mut g = DefaultQmcIsingGraph::<PhiloxStream>::new_with_rng(edges.clone(), gamma, h, cutoff, rng, None);
             g.set_enable_heatbath(case["heatbath"].as_bool().unwrap());
+            g.set_run_rvb(case["rvb"].as_bool().unwrap_or(false));  // RVB updates (rvb.rs:60-291) in every sweep, qmc_ising.rs:705-752
             let e = g.timesteps(sweeps, beta);
             assert_eq!(g.get_n() as u64, rep["n"].as_u64().unwrap(), "{} n", case["name"]);
             assert_eq!(g.get_cutoff() as u64, rep["cutoff"].as_u64().unwrap(), "{} cutoff", case["name"]);
@@ -58,7 +59,7 @@ fn reference_reproduces_the_strict_golden_cases() {
             checked += 1;
         }
     }
-    assert!(checked >= 12);
+    assert!(checked >= 18);  // 8 cases x 3 replicas, two of them with RVB steps
 }
 
 /// The generic runner with directed-loop updates: the real `qmc::sse::Qmc` (qmc_runner.rs:22-403, loop update

@@ -18,13 +18,15 @@ from isingmontecarlo_b200 import lattices  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
 
 CASES = [
-    # name, lattice builder (by name, args), gamma, h, cutoff, beta, sweeps, heatbath
+    # name, lattice builder (by name, args), gamma, h, cutoff, beta, sweeps, heatbath[, rvb steps (set_run_rvb, qmc_ising.rs:434-441)]
     ("small_qmc_ring", ("small_qmc_ring", []), 1.0, 0.0, 3, 1.0, 25, False),
     ("mixed4x4_h", ("two_d_periodic_mixed", [4]), 1.0, 1.0, 16, 1.0, 20, False),
     ("square8_crit", ("square_periodic", [8, -1.0]), 3.04, 0.0, 64, 4.0, 12, False),
     ("tri6_frustrated_h", ("triangular_periodic", [6, 1.0]), 1.0, 0.2, 36, 2.0, 10, False),
     ("square8_heatbath", ("square_periodic", [8, -1.0]), 3.04, 0.0, 64, 4.0, 12, True),
     ("two_unit_cell_heatbath_h", ("two_unit_cell", []), 1.0, -0.4, 8, 2.0, 20, True),
+    ("two_unit_cell_rvb", ("two_unit_cell", []), 1.0, 0.0, 8, 1.0, 25, False, True),          # check_rvb_crash.rs:340-359
+    ("tri6_frustrated_rvb_h", ("triangular_periodic", [6, 1.0]), 1.0, 0.2, 36, 2.0, 10, False, True),
 ]
 KEYS = [0x601D0000 + r for r in range(3)]
 
@@ -42,12 +44,13 @@ def fnv1a64(arr):
 
 
 def run_case(case, mode):
-    name, (builder, args), gamma, h, cutoff, beta, sweeps, hb = case
+    name, (builder, args), gamma, h, cutoff, beta, sweeps, hb = case[:8]
     edges = getattr(lattices, builder)(*args)
     out = []
     for k in KEYS:
         g = po.SseOracle(edges, gamma, h, cutoff, key=k)
         g.set_enable_heatbath(hb)
+        g.set_run_rvb(len(case) > 8 and case[8])
         e = g.timesteps(sweeps, beta, mode)
         assert g.error == 0 and g.verify()
         ops = g.dump_ops()
@@ -61,12 +64,12 @@ def main():
     doc = {"_provenance": __doc__.split("Run from")[0].strip(), "cases": []}
     for case in CASES:
         for mode, mname in ((po.MODE_STRICT, "strict"), (po.MODE_FAST, "fast"), (po.MODE_COUNTER, "counter")):
-            name, (builder, args), gamma, h, cutoff, beta, sweeps, hb = case
+            name, (builder, args), gamma, h, cutoff, beta, sweeps, hb = case[:8]
             if hb and mode == po.MODE_COUNTER:
                 continue  # the heat-bath rule has no COUNTER-mode contract
             edges = getattr(lattices, builder)(*args)
             doc["cases"].append({"name": name, "builder": builder, "args": args, "gamma": gamma, "h": h, "cutoff": cutoff, "beta": beta,
-                                 "sweeps": sweeps, "heatbath": hb, "mode": mname, "edges": [[a, b, j] for (a, b), j in edges],
+                                 "sweeps": sweeps, "heatbath": hb, "rvb": bool(len(case) > 8 and case[8]), "mode": mname, "edges": [[a, b, j] for (a, b), j in edges],
                                  "replicas": run_case(case, mode)})
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "sse_golden.json"), "w") as f:
         json.dump(doc, f, indent=1)

@@ -101,3 +101,57 @@ def test_generic_qmc_has_no_rvb():
     q = g.into_qmc()
     with pytest.raises(QmcbError):
         q.set_run_rvb(True)  # Qmc::timestep has no RVB step (qmc_runner.rs:363-377)
+
+
+@pytest.mark.parametrize("mode", [MODE_STRICT, MODE_FAST])
+def test_rvb_with_heatbath_diagonal_update(mode):
+    # longitudinal_crash.rs:39-178 runs its lattices with and without rvb, with and without the heat-bath rule
+    g, refs = make_pair(lattices.two_d_periodic_mixed(4), 1.0, 1.0, 16, 1.0, mode)
+    g.set_run_rvb(True)
+    g.set_enable_heatbath(True)
+    for ref in refs:
+        ref.set_run_rvb(True)
+        ref.set_enable_heatbath(True)
+    g.timesteps(30, 1.0)
+    for ref in refs:
+        ref.timesteps(30, 1.0, mode)
+    assert_same(g, refs, "rvb + heatbath")
+    assert g.verify()
+
+
+def test_tempering_ladder_with_rvb_steps():
+    # tempering_container.rs:121-149 steps graphs that run their own timestep: with set_run_rvb the RVB updates are part of it
+    from isingmontecarlo_b200.tempering import TemperingContainer
+
+    edges = lattices.two_unit_cell()
+    n_chains, n_betas, mode = 2, 4, MODE_COUNTER
+    betas = np.linspace(0.5, 2.0, n_betas)
+    keys = 0x55E00000 + np.arange(n_chains * n_betas, dtype=np.uint64)
+    pt_key = 0xABCDEF
+    tc = TemperingContainer(edges, 1.0, 0.0, 8, betas, n_chains=n_chains, rng_keys=keys, pt_key=pt_key, mode=mode)
+    tc.graph.set_run_rvb(True)
+    slots = [[po.SseOracle(edges, 1.0, 0.0, 8, key=int(keys[c * n_betas + k])) for k in range(n_betas)] for c in range(n_chains)]
+    for ladder in slots:
+        for ref in ladder:
+            ref.set_run_rvb(True)
+    cursors = [0] * n_chains
+    swaps_ref = 0
+    for _ in range(10):
+        tc.timesteps(2)
+        for c in range(n_chains):
+            for k in range(n_betas):
+                slots[c][k].timesteps(2, float(betas[k]), mode)
+        tc.tempering_step()
+        for c in range(n_chains):
+            s, cursors[c] = po.pt_step(slots[c], betas, pt_key + c, cursors[c])
+            swaps_ref += s
+        g = tc.graph
+        n, cut, cur, st = g.get_n(), g.get_cutoff(), g.rng_cursors(), g.state_ref()
+        for s_local, slot in enumerate(tc.slots()):
+            ref = slots[slot // n_betas][slot % n_betas]
+            assert ref.error == 0
+            assert int(n[s_local]) == ref.n and int(cut[s_local]) == ref.cutoff and int(cur[s_local]) == ref.cursor
+            assert np.array_equal(st[s_local], ref.state())
+            assert np.array_equal(g.dump_ops(s_local), ref.dump_ops())
+        assert tc.get_total_swaps() == swaps_ref
+    assert swaps_ref > 0 and tc.verify()
