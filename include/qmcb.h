@@ -170,8 +170,8 @@ int qmcb_get_do_loop_updates(const QmcbHandle *h, int *enabled);
  * (qmc_ising.rs:434-441): every sweep then runs (nvars + 1) / 2 RVB updates between the diagonal and the cluster update
  * (:705-752), in every mode (the update draws from the replica's sequential stream).  qmcb_single_rvb_sweep =
  * single_rvb_sweep (:322-420; updates_in_sweep < 0 = None); qmcb_rvb_success_rate = rvb_success_rate (:604-607), any
- * output may be NULL.  Handles made by qmcb_create only (Qmc has no RVB step).  The flag and the two counters are not
- * part of the checkpoint blob: set the flag again after qmcb_checkpoint_load. */
+ * output may be NULL.  Handles made by qmcb_create only (Qmc has no RVB step).  The flag travels in the checkpoint blob
+ * (the two counters restart at 0); under tempering the counters follow the configuration, not the slot. */
 int qmcb_set_run_rvb(QmcbHandle *h, int run_rvb);
 int qmcb_get_run_rvb(const QmcbHandle *h, int *run_rvb);
 int qmcb_single_rvb_sweep(QmcbHandle *h, int64_t updates_in_sweep, uint64_t *successes_out /* [R] or NULL */, uint64_t *attempts_out /* or NULL */);

@@ -1715,7 +1715,7 @@ extern "C" int qmcb_pt_get_slots(QmcbHandle *h, uint32_t *slots) {
 // tempering container as (graph, beta) pairs + total_swaps (tempering_container.rs:671-793).  Here the
 // injected stream is (key, cursor), 16 bytes, so it is part of the record and a restored batch continues
 // bit-identically.  Layout (little-endian), all arrays replica-major:
-//   "QMCBCKP1" | u32 version, N, E, R, mode, flags(bit0 heat-bath, bit1 tempering, bit2 Hamiltonian table) | u64 target |
+//   "QMCBCKP1" | u32 version, N, E, R, mode, flags(bit0 heat-bath, bit1 tempering, bit2 Hamiltonian table, bit3 run_rvb_steps) | u64 target |
 //   f64 transverse, longitudinal | va[E] u32 | vb[E] u32 | pad to 8 | J[E] f64 |
 //   beta[R] f64 | key[R] u64 | cursor[R] u64 | done[R] u64 | vupd[R] u64 | M[R] u32 | n[R] u32 |
 //   state[R][Nw] u32 | pad to 8 | ops of replica 0 (M[0] words), replica 1, ... | pad to 8 |
@@ -1792,7 +1792,7 @@ static int checkpoint_write(QmcbHandle *h, CkWriter &W) {
     CUDA_TRY(fetch(state, D.state, (size_t)D.R * D.Nw));
     W.put("QMCBCKP1", 8);
     W.val<uint32_t>(1), W.val<uint32_t>(D.N), W.val<uint32_t>(D.E), W.val<uint32_t>(D.R);
-    W.val<uint32_t>((uint32_t)h->mode), W.val<uint32_t>((D.hb_cum ? 1u : 0u) | (h->pt_on ? 2u : 0u) | (D.ham ? 4u : 0u));
+    W.val<uint32_t>((uint32_t)h->mode), W.val<uint32_t>((D.hb_cum ? 1u : 0u) | (h->pt_on ? 2u : 0u) | (D.ham ? 4u : 0u) | (h->rvb_on ? 8u : 0u));
     W.val<uint64_t>(h->target);
     W.val<double>(D.gamma), W.val<double>(D.h);
     W.put(h->va_h.data(), 4ull * D.E), W.put(h->vb_h.data(), 4ull * D.E), W.pad8();
@@ -1954,6 +1954,7 @@ extern "C" int qmcb_checkpoint_load(const void *buf, uint64_t bytes, int device,
     if ((flags & 4u) && (rc = qmcb_set_hamiltonians(h, H, Jtab.data(), gtab.data(), htab.data(), hrep.data()))) return bail(rc);
     if ((rc = qmcb_set_mode(h, (int)mode))) return bail(rc);
     if ((flags & 1u) && (rc = qmcb_set_enable_heatbath(h, 1))) return bail(rc);
+    if ((flags & 8u) && (rc = qmcb_set_run_rvb(h, 1))) return bail(rc);  // run_rvb_steps is part of the reference's serde mirror (qmc_ising.rs:1020)
     if (flags & 2u) {
         // slot labels index the per-slot tables of the swap kernels: every one must be a slot of the ladder, no two alike
         const uint64_t S = (uint64_t)n_chains * n_betas;

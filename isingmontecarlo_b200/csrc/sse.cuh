@@ -74,7 +74,8 @@ struct SseDev {
 
 // workspace of the RVB update (sse_rvb.cu), allocated by qmcb_set_run_rvb / qmcb_single_rvb_sweep.  Per replica:
 // u32: var_starts[N+1] var_lengths[N] zero_vars[N] constant_ps[cap] | boundary_flips map/keys(v)/keys(p) [3][cap] |
-//      boundary_noflips map/keys [2][N] | subvars[N] var_to_subvar[N] | bonds, bonds_before, bonds_after map [3][E], keys [3][E] | fill[N]
+//      boundary_noflips map/keys [2][N] | subvars[N] var_to_subvar[N] | bonds, bonds_before, bonds_after map [3][E], keys [3][E] | fill[N] |
+//      world lines: start[N] len[N] cap[N] cursor index[N] cursor position[N] positions[rvb_lines_total]
 // f64: key weights of boundary_flips [cap], boundary_noflips [N], the three bond sets [3][E]
 // u8 : var_pos_popped[cap] var_nopos_popped[N] cluster_state[N] substate[N] mark[N]
 struct RvbDev {
@@ -85,7 +86,11 @@ struct RvbDev {
     size_t stride32, stride64, stride8;
     unsigned long long *succ, *count;  // [R] total_rvb_successes, rvb_clusters_counted (qmc_ising.rs:42-43)
 };
-__host__ __device__ __forceinline__ size_t rvb_stride32(const SseDev &D) { return 8 * (size_t)D.N + 1 + 4 * (size_t)D.cap + 6 * (size_t)D.E; }
+// world lines (positions of the ops on each variable, with slack for rotations): at most 2 n * 1.25 + 32 N entries
+__host__ __device__ __forceinline__ size_t rvb_lines_total(const SseDev &D) { return (size_t)D.cap * 5 / 2 + 32 * (size_t)D.N + 64; }
+__host__ __device__ __forceinline__ size_t rvb_stride32(const SseDev &D) {
+    return 13 * (size_t)D.N + 1 + 4 * (size_t)D.cap + 6 * (size_t)D.E + rvb_lines_total(D);
+}
 __host__ __device__ __forceinline__ size_t rvb_stride64(const SseDev &D) { return (size_t)D.cap + D.N + 3 * (size_t)D.E; }
 __host__ __device__ __forceinline__ size_t rvb_stride8(const SseDev &D) { return (size_t)D.cap + 4 * (size_t)D.N; }
 

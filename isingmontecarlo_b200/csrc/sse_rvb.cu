@@ -8,9 +8,11 @@
 // help with the workspace set-up.  The reference finds ops through per-variable links, binary heaps and "hints"
 // (fast_ops.rs:639-808, 896-1172); those decide HOW ops are found, not WHICH: calculate_flip_prob (rvb.rs:649-946) and
 // mutate_subsection_ops visit every op that touches a sub-variable, in p order, and get_propagated_substate_with_hint
-// returns the state just before p.  This kernel makes the same visits on the flat operator words (a rotation rewrites
-// one word; there are no links to splice).  What is kept literally because results depend on it: every draw and its
-// order, every f64 operation (the running totals of the weighted sets are accumulated in the reference's order), and
+// returns the state just before p.  This kernel makes the same visits on the flat operator words plus one sorted
+// position list per variable (the ops on its world line, built once per launch with slack, patched when a rotation moves
+// an op to other variables, rebuilt if a list outgrows its slack): "next op on a sub-variable's line at or after p" is a
+// binary search per sub-variable, so a proposal costs what the cluster touches, not the length of the string.  What is
+// kept literally because results depend on it: every draw and its order, every f64 operation (the running totals of the weighted sets are accumulated in the reference's order), and
 // the key order inside BondContainer (util/bondcontainer.rs:10-159: push at the end, swap-remove), which decides what
 // get_random returns.  The move is off by default in the reference (qmc_ising.rs:122) and here; it is not a tuned path.
 #include "sse.cuh"
@@ -102,6 +104,10 @@ struct Ctx {
     uint8_t *cstate, *substate, *mark;
     uint32_t toggles[150], ntog;
     BC bonds, bef, aft;
+    // world lines: the positions of the ops on each variable, ascending, in lines[ln_start[v] .. + ln_len[v]) (room for ln_cap[v])
+    uint32_t *ln_start, *ln_len, *ln_cap, *lines;
+    size_t lines_total;
+    uint32_t *c_idx, *c_pos;  // per sub-variable: cursor into its line and the position there (NONE32 past the end)
 
     __device__ __forceinline__ uint64_t next_u64() { return stream_word(key, cur++); }
     __device__ bool gen_bool(double p) {  // rand 0.8 Bernoulli
@@ -153,10 +159,93 @@ struct Ctx {
         o.constant = kind == KIND_SITE;
         return true;
     }
-    __device__ __forceinline__ bool near(const Op &o) const {
-        for (uint32_t r = 0; r < o.nv; r++)
-            if (v2s[o.v[r]] != NONE32) return true;
-        return false;
+    // (re)build every world line from the operator words; slack so that rotations can move ops between lines
+    __device__ void build_lines() {
+        const uint32_t N = D.N;
+        for (uint32_t v = 0; v < N; v++) ln_len[v] = 0;
+        for (uint32_t p = 0; p < M; p++) {
+            Op o;
+            if (!decode(p, o)) continue;
+            for (uint32_t r = 0; r < o.nv; r++) ln_len[o.v[r]]++;
+        }
+        size_t acc = 0;
+        for (uint32_t v = 0; v < N; v++) {
+            ln_start[v] = (uint32_t)acc, ln_cap[v] = ln_len[v] + ln_len[v] / 4 + 32;
+            acc += ln_cap[v], ln_len[v] = 0;
+        }
+        if (acc > lines_total) {  // cannot happen: lines_total = 2.5 cap + 32 N + 64 and n <= cap
+            err |= DEV_ERR_INVARIANT;
+            return;
+        }
+        for (uint32_t p = 0; p < M; p++) {
+            Op o;
+            if (!decode(p, o)) continue;
+            for (uint32_t r = 0; r < o.nv; r++) lines[ln_start[o.v[r]] + ln_len[o.v[r]]++] = p;
+        }
+    }
+    // index of the first entry >= p on the line of variable v
+    __device__ __forceinline__ uint32_t lower_bound(uint32_t v, uint32_t p) const {
+        const uint32_t *ln = lines + ln_start[v];
+        uint32_t lo = 0, hi = ln_len[v];
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (ln[mid] < p) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    }
+    // point every sub-variable's cursor at its first op at or after pos
+    __device__ void seek(uint32_t pos) {
+        for (uint32_t s = 0; s < nsub; s++) {
+            const uint32_t v = subvars[s], i = lower_bound(v, pos);
+            c_idx[s] = i, c_pos[s] = i < ln_len[v] ? lines[ln_start[v] + i] : NONE32;
+        }
+    }
+    // the first op at or after pos on a sub-variable's world line (what the reference's heaps pop next), or NONE32;
+    // pos never decreases between two seeks, so the cursors only move forward
+    __device__ uint32_t next_near(uint32_t pos) {
+        uint32_t best = NONE32;
+        for (uint32_t s = 0; s < nsub; s++) {
+            uint32_t cp = c_pos[s];
+            if (cp < pos) {
+                const uint32_t v = subvars[s], len = ln_len[v];
+                const uint32_t *ln = lines + ln_start[v];
+                uint32_t i = c_idx[s];
+                do cp = ++i < len ? ln[i] : NONE32;
+                while (cp < pos);
+                c_idx[s] = i, c_pos[s] = cp;
+            }
+            best = min(best, cp);
+        }
+        return best;
+    }
+    // the state of variable v just before p: the output of the last op below p on its line, else `otherwise`
+    __device__ __forceinline__ uint32_t state_before(uint32_t v, uint32_t p, uint32_t otherwise) const {
+        const uint32_t i = lower_bound(v, p);
+        if (i == 0) return otherwise;
+        Op t;
+        decode(lines[ln_start[v] + i - 1], t);
+        return (t.out >> (t.v[0] == v ? 0 : 1)) & 1u;
+    }
+    __device__ void line_remove(uint32_t v, uint32_t p) {
+        uint32_t *ln = lines + ln_start[v];
+        const uint32_t i = lower_bound(v, p), len = ln_len[v];
+        if (i >= len || ln[i] != p) {
+            err |= DEV_ERR_INVARIANT;
+            return;
+        }
+        for (uint32_t k = i; k + 1 < len; k++) ln[k] = ln[k + 1];
+        ln_len[v] = len - 1;
+    }
+    __device__ bool line_insert(uint32_t v, uint32_t p) {  // false: no room left, the caller rebuilds
+        uint32_t *ln = lines + ln_start[v];
+        const uint32_t len = ln_len[v];
+        if (len >= ln_cap[v]) return false;
+        const uint32_t i = lower_bound(v, p);
+        for (uint32_t k = len; k > i; k--) ln[k] = ln[k - 1];
+        ln[i] = p;
+        ln_len[v] = len + 1;
+        return true;
     }
     __device__ __forceinline__ uint32_t other_var(uint32_t v, uint32_t b) const {  // rvb.rs:22-31
         const uint32_t a = __ldg(D.va + b), c = __ldg(D.vb + b);
@@ -288,21 +377,19 @@ struct Ctx {
             }
         }
         uint32_t pos = 0;  // every op below pos has left the heap
+        seek(0);
         for (;;) {
             Op o;
-            uint32_t q = pos;  // heap top: the next op on a sub-variable's world line
-            while (q < M && !(decode(q, o) && near(o))) q++;
-            if (q >= M) break;
+            const uint32_t q = next_near(pos);  // heap top: the next op on a sub-variable's world line
+            if (q == NONE32) break;
             uint32_t p = q;
             if (cluster_size == 0) {  // :722-733: jump to the next cluster flip
                 if (next_ci < ntog) p = toggles[next_ci];
                 else break;
             }
-            for (uint32_t x = q; x < p; x++) {  // popped < p: outputs propagate the substate, :742-768
-                Op t;
-                if (!decode(x, t)) continue;
-                for (uint32_t r = 0; r < t.nv; r++)
-                    if (v2s[t.v[r]] != NONE32) substate[v2s[t.v[r]]] = (uint8_t)((t.out >> r) & 1u);
+            if (p > q) {  // popped < p: their outputs propagate the substate, :742-768
+                for (uint32_t s = 0; s < nsub; s++) substate[s] = (uint8_t)state_before(subvars[s], p, substate[s]);
+                seek(p);
             }
             pos = p + 1;
             if (p >= M || !decode(p, o)) {
@@ -433,21 +520,19 @@ struct Ctx {
             // get_propagated_substate_with_hint (fast_ops.rs:1027-1172): the state just before `from`
             for (uint32_t s = 0; s < nsub; s++) {
                 const uint32_t v = subvars[s];
-                uint32_t val = state_bit(state, v);
-                for (uint32_t x = from; x-- > 0;) {
-                    Op t;
-                    if (!decode(x, t)) continue;
-                    bool hit = false;
-                    for (uint32_t r = 0; r < t.nv; r++)
-                        if (t.v[r] == v) val = (t.out >> r) & 1u, hit = true;
-                    if (hit) break;
-                }
-                substate[s] = (uint8_t)(val ^ cstate[s]);  // :396-399
+                substate[s] = (uint8_t)(state_before(v, from, state_bit(state, v)) ^ cstate[s]);  // :396-399
             }
             // mutate_subsection_ops (fast_ops.rs:639-775): ops with p in [from, until] on the sub-variables' world lines
-            for (uint32_t p = from; p <= until && p < M && !err; p++) {
+            seek(from);
+            for (uint32_t pos = from; !err;) {
+                const uint32_t p = next_near(pos);
+                if (p == NONE32 || p > until || p >= M) break;
+                pos = p + 1;
                 Op o;
-                if (!decode(p, o) || !near(o)) continue;
+                if (!decode(p, o)) {
+                    err |= DEV_ERR_INVARIANT;
+                    break;
+                }
                 const bool in_bonds = bc_contains(bonds, o.b);
                 const bool at_next = next_ci < ntog && p == toggles[next_ci];
                 if (in_bonds) {  // :411-432: rotate the diagonal op onto a bond drawn from the border
@@ -461,6 +546,11 @@ struct Ctx {
                     }
                     const uint32_t st = (uint32_t)substate[sa] | ((uint32_t)substate[sb] << 1);
                     ops[p] = make_op(nb, st, st);
+                    if (nb != o.b) {  // the op moves to the world lines of the new bond's variables
+                        line_remove(o.v[0], p), line_remove(o.v[1], p);
+                        if (!line_insert(__ldg(D.va + nb), p) || !line_insert(__ldg(D.vb + nb), p)) build_lines();
+                        seek(pos);
+                    }
                     continue;
                 }
                 uint32_t in = o.in, out = o.out;
@@ -533,12 +623,70 @@ __global__ void __launch_bounds__(128) k_sse_rvb(SseDev D, RvbDev W, uint64_t ta
     uint32_t *fl_map = constant_ps + cap, *fl_kv = fl_map + cap, *fl_kp = fl_kv + cap;
     uint32_t *nf_map = fl_kp + cap, *nf_kv = nf_map + N, *subvars = nf_kv + N, *v2s = subvars + N;
     uint32_t *bd_map = v2s + N, *bd_kv = bd_map + 3 * (size_t)E, *fill = bd_kv + 3 * (size_t)E;
+    uint32_t *ln_start = fill + N, *ln_len = ln_start + N, *ln_cap = ln_len + N, *c_idx = ln_cap + N, *c_pos = c_idx + N, *lines = c_pos + N;
     double *fl_kw = f64, *nf_kw = fl_kw + cap, *bd_kw = nf_kw + N;
     uint8_t *pos_popped = u8, *nopos_popped = pos_popped + cap, *cstate = nopos_popped + N, *substate = cstate + N, *mark = substate + N;
     // empty containers, nothing popped, no sub-variables (all lanes)
     for (size_t i = lane; i < cap; i += 32) fl_map[i] = NONE32, pos_popped[i] = 0;
-    for (uint32_t i = lane; i < N; i += 32) nf_map[i] = NONE32, v2s[i] = NONE32, nopos_popped[i] = 0, mark[i] = 0, var_lengths[i] = 0, fill[i] = 0;
+    for (uint32_t i = lane; i < N; i += 32) nf_map[i] = NONE32, v2s[i] = NONE32, nopos_popped[i] = 0, mark[i] = 0, var_lengths[i] = 0, ln_len[i] = 0;
     for (uint32_t i = lane; i < 3 * E; i += 32) bd_map[i] = NONE32;
+    __syncwarp();
+    // find_constants (rvb.rs:1162-1188; constant_ops_on_var fast_ops.rs:1466-1480: the p of every constant op of a variable,
+    // ascending) and the world lines, by all lanes: count, lay out, fill (order inside a 32-slot step is whatever the
+    // atomics gave), then one lane per variable puts its line in order and copies out its constant ops
+    const uint32_t *opw = D.ops + (size_t)r * D.cap;
+    for (uint32_t base = 0; base < M; base += 32) {
+        const uint32_t p = base + lane;
+        const uint32_t w = p < M ? opw[p] : OP_EMPTY;
+        if (w != OP_EMPTY) {
+            const uint32_t b = op_bond(w);
+            const int kind = bond_kind(D, b);
+            uint32_t v0, v1;
+            bond_vars(D, b, kind, v0, v1);
+            atomicAdd(ln_len + v0, 1u);
+            if (kind == KIND_BOND) atomicAdd(ln_len + v1, 1u);
+            if (kind == KIND_SITE) atomicAdd(var_lengths + v0, 1u);
+        }
+    }
+    __syncwarp();
+    uint32_t ncp = 0, nzero = 0;
+    if (lane == 0) {
+        size_t acc = 0;
+        for (uint32_t v = 0; v < N; v++) {
+            ln_start[v] = (uint32_t)acc, ln_cap[v] = ln_len[v] + ln_len[v] / 4 + 32;
+            acc += ln_cap[v], ln_len[v] = 0;
+            var_starts[v] = ncp, ncp += var_lengths[v];
+            if (var_lengths[v] == 0) zero_vars[nzero++] = v;
+        }
+        var_starts[N] = ncp;
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < M; base += 32) {
+        const uint32_t p = base + lane;
+        const uint32_t w = p < M ? opw[p] : OP_EMPTY;
+        if (w != OP_EMPTY) {
+            const uint32_t b = op_bond(w);
+            const int kind = bond_kind(D, b);
+            uint32_t v0, v1;
+            bond_vars(D, b, kind, v0, v1);
+            lines[ln_start[v0] + atomicAdd(ln_len + v0, 1u)] = p;
+            if (kind == KIND_BOND) lines[ln_start[v1] + atomicAdd(ln_len + v1, 1u)] = p;
+        }
+        __syncwarp();  // steps do not interleave: a line is out of order only inside one step's entries
+    }
+    for (uint32_t v = lane; v < N; v += 32) {
+        uint32_t *ln = lines + ln_start[v];
+        const uint32_t len = ln_len[v];
+        uint32_t k = var_starts[v];
+        for (uint32_t i = 0; i < len; i++) {
+            const uint32_t x = ln[i];
+            uint32_t j = i;
+            while (j > 0 && ln[j - 1] > x) ln[j] = ln[j - 1], j--;
+            ln[j] = x;
+        }
+        for (uint32_t i = 0; i < len; i++)
+            if (bond_kind(D, op_bond(opw[ln[i]])) == KIND_SITE) constant_ps[k++] = ln[i];
+    }
     __syncwarp();
     if (lane != 0) return;
 
@@ -554,29 +702,9 @@ __global__ void __launch_bounds__(128) k_sse_rvb(SseDev D, RvbDev W, uint64_t ta
     C.bonds = BC{bd_map, bd_kv, nullptr, bd_kw, E, 0, 0.0};
     C.bef = BC{bd_map + E, bd_kv + E, nullptr, bd_kw + E, E, 0, 0.0};
     C.aft = BC{bd_map + 2 * (size_t)E, bd_kv + 2 * (size_t)E, nullptr, bd_kw + 2 * (size_t)E, E, 0, 0.0};
-    // find_constants (constant_ops_on_var, fast_ops.rs:1466-1480): the p of every constant op, per variable, in p order
-    uint32_t ncp = 0, nzero = 0;
-    for (uint32_t p = 0; p < M; p++) {
-        const uint32_t w = C.ops[p];
-        if (w == OP_EMPTY) continue;
-        const uint32_t b = op_bond(w);
-        if (bond_kind(D, b) == KIND_SITE) var_lengths[b - E]++, ncp++;
-    }
-    {
-        uint32_t acc = 0;
-        for (uint32_t v = 0; v < N; v++) {
-            var_starts[v] = acc, acc += var_lengths[v];
-            if (var_lengths[v] == 0) zero_vars[nzero++] = v;
-        }
-        var_starts[N] = acc;
-        for (uint32_t p = 0; p < M; p++) {
-            const uint32_t w = C.ops[p];
-            if (w == OP_EMPTY) continue;
-            const uint32_t b = op_bond(w);
-            if (bond_kind(D, b) == KIND_SITE) constant_ps[var_starts[b - E] + fill[b - E]++] = p;
-        }
-    }
     C.ncp = ncp, C.nzero = nzero;
+    C.ln_start = ln_start, C.ln_len = ln_len, C.ln_cap = ln_cap, C.lines = lines, C.lines_total = rvb_lines_total(D);
+    C.c_idx = c_idx, C.c_pos = c_pos;
     const uint64_t updates = updates_arg >= 0 ? (uint64_t)updates_arg : ((uint64_t)N + 1) / 2;
     unsigned long long num_succ = 0;
     for (uint64_t u = 0; u < updates && !C.err; u++) {
@@ -605,11 +733,19 @@ __global__ void __launch_bounds__(128) k_sse_rvb(SseDev D, RvbDev W, uint64_t ta
         C.build_cluster(cluster_size, v, flip);
         if (C.err) break;
         // dissolve_into (:987-1007) and the sorted, deduplicated sub-variables (:168-180)
-        for (uint32_t i = 0; i < C.ncl; i++) mark[C.cl_vars[i]] = 1;
-        for (uint32_t i = 0; i < C.fl.len; i++) mark[C.fl.kv[i]] = 1;
-        for (uint32_t i = 0; i < C.nf.len; i++) mark[C.nf.kv[i]] = 1;
-        for (uint32_t w = 0; w < N; w++)
-            if (mark[w]) v2s[w] = C.nsub, subvars[C.nsub++] = w, mark[w] = 0;
+        auto add = [&](uint32_t w) {
+            if (!mark[w]) mark[w] = 1, subvars[C.nsub++] = w;
+        };
+        for (uint32_t i = 0; i < C.ncl; i++) add(C.cl_vars[i]);
+        for (uint32_t i = 0; i < C.fl.len; i++) add(C.fl.kv[i]);
+        for (uint32_t i = 0; i < C.nf.len; i++) add(C.nf.kv[i]);
+        for (uint32_t i = 1; i < C.nsub; i++) {  // sort_unstable + dedup (the marks kept duplicates out)
+            const uint32_t x = subvars[i];
+            uint32_t j = i;
+            while (j > 0 && subvars[j - 1] > x) subvars[j] = subvars[j - 1], j--;
+            subvars[j] = x;
+        }
+        for (uint32_t s = 0; s < C.nsub; s++) v2s[subvars[s]] = s, mark[subvars[s]] = 0;
         for (uint32_t s = 0; s < C.nsub; s++) cstate[s] = 0, substate[s] = (uint8_t)state_bit(C.state, subvars[s]);
         C.ntog = 0;
         for (uint32_t i = 0; i < C.ncl; i++) {  // :182-203

@@ -40,6 +40,22 @@ def test_checkpoint_round_trip_continues_bit_identically(mode, heatbath):
     assert g2.save_checkpoint() == g.save_checkpoint()  # same state -> same bytes
 
 
+def test_checkpoint_carries_the_rvb_flag():
+    # run_rvb_steps is part of the reference's serialised graph (qmc_ising.rs:1020, 1044): a restored batch keeps running RVB steps
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.two_unit_cell()
+    g = QmcIsingGraph(edges, 1.0, 0.0, 8, 0xC0FFEE40 + np.arange(4, dtype=np.uint64), 2.0, mode=MODE_FAST)
+    g.set_run_rvb(True)
+    g.timesteps(20)
+    blob = g.save_checkpoint()
+    e_a = g.timesteps(10)
+    g2 = QmcIsingGraph.from_checkpoint(blob)
+    e_b = g2.timesteps(10)
+    assert np.array_equal(e_a, e_b) and same_snapshot(snapshot(g), snapshot(g2)) and g2.verify()
+    assert (g2.rvb_success_rate() > 0).all()  # counted from the restore on
+
+
 def test_checkpoint_rejects_corruption_and_truncation():
     from isingmontecarlo_b200.sse import QmcIsingGraph
 
