@@ -298,16 +298,18 @@ struct Ctx {
     __device__ void push_overlapping(uint32_t ov, uint32_t p_start, uint32_t p_end, double weight) {
         const uint32_t *fp = constant_ps + var_starts[ov];
         const uint32_t len = var_lengths[ov];
-        const uint64_t cutoff = M;
+        const uint32_t cutoff = M;  // every position is below the cutoff (< 2^29), so the sums below fit 32 bits
         uint32_t bin_found = 0;  // binary_search(&p_start).unwrap_err()
         while (bin_found < len && fp[bin_found] < p_start) bin_found++;
-        const uint32_t prev = (bin_found + len - 1) % len;
-        const uint64_t lowest = fp[prev];
-        const uint64_t off_start = (p_start + cutoff - lowest) % cutoff, off_end = (p_end + cutoff - lowest) % cutoff;
-        for (uint32_t k = 0; k < len; k++) {
-            const uint32_t ip = (prev + k) % len;
-            const uint64_t check_start = (fp[ip] + cutoff - lowest) % cutoff;
-            const uint64_t check_end = (fp[(ip + 1) % len] + cutoff - lowest) % cutoff;
+        const uint32_t prev = bin_found == 0 ? len - 1 : bin_found - 1;  // (bin_found + len - 1) % len
+        const uint32_t lowest = fp[prev];
+        // (x + cutoff - lowest) % cutoff for x < cutoff: one conditional subtraction
+        auto rel = [&](uint32_t x) { const uint32_t y = x + cutoff - lowest; return y >= cutoff ? y - cutoff : y; };
+        const uint32_t off_start = rel(p_start), off_end = rel(p_end);
+        uint32_t ip = prev;
+        for (uint32_t k = 0; k < len; k++, ip = ip + 1 == len ? 0 : ip + 1) {  // [prev..] then [..prev]
+            const uint32_t check_start = rel(fp[ip]);
+            const uint32_t check_end = rel(fp[ip + 1 == len ? 0 : ip + 1]);
             const bool has_overlap_start = check_start < off_start && off_start < check_end;
             const bool has_start_within = off_start < check_start && check_start < off_end;
             const bool eq = (p_start == p_end) || (check_start == check_end);
@@ -603,7 +605,10 @@ struct Ctx {
 
 // updates < 0: the (N + 1) / 2 of the timestep (qmc_ising.rs:711).  target != 0: only replicas whose next sweep is `target`
 // (the diagonal update of that sweep has run; the cluster update follows), and the counters of rvb_success_rate advance.
-__global__ void __launch_bounds__(128) k_sse_rvb(SseDev D, RvbDev W, uint64_t target, long long updates_arg, unsigned long long *succ_out) {
+#ifndef QMCB_RVB_MINB
+#define QMCB_RVB_MINB 7  // 72 registers: 4096 replicas are resident in one wave (measured 231 -> 181 ms per sweep of a 4096-replica L = 24 batch)
+#endif
+__global__ void __launch_bounds__(128, QMCB_RVB_MINB) k_sse_rvb(SseDev D, RvbDev W, uint64_t target, long long updates_arg, unsigned long long *succ_out) {
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= D.R) return;

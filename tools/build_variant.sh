@@ -7,7 +7,7 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 out=$root/isingmontecarlo_b200/_variants/$name
 mkdir -p "$out/obj"
 cd "$root/isingmontecarlo_b200/csrc"
-for f in api sse_serial sse_fast sse_counter classical classical_ref pt; do
+for f in api sse_serial sse_fast sse_counter sse_rvb classical classical_ref pt; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ --fmad=false "$@" -c $f.cu -o "$out/obj/$f.o" &
 done
 wait
