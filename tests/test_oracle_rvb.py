@@ -48,6 +48,8 @@ def test_single_rvb_sweep_counts_and_keeps_the_invariant():
     ("two_triangles", TRI2, 0.3, 0.0, 3.0),
     ("diamond_mixed_J", [((0, 1), 1.0), ((1, 2), 0.7), ((2, 0), 1.3), ((2, 3), -1.0), ((3, 0), 1.0)], 0.4, 0.0, 2.5),
     ("diamond_h", DIAMOND, 0.4, 0.25, 2.0),
+    ("triangular_torus_3x4", [((jj * 3 + i, k), 1.0) for i in range(3) for jj in range(4)
+                              for k in (jj * 3 + (i + 1) % 3, ((jj + 1) % 4) * 3 + i, ((jj + 1) % 4) * 3 + (i + 1) % 3)], 0.7, 0.0, 3.0),
 ])
 def test_rvb_energy_matches_exact_diagonalisation(name, edges, gamma, h, beta):
     nvars = lattices.nvars_of(edges)
