@@ -213,6 +213,19 @@ int qmcb_spin_product_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t sampli
                                       double *autocorr_out, uint8_t *samples_out, double *energy_out);
 int qmcb_bond_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t sampling_freq, double *autocorr_out, uint8_t *samples_out,
                               double *energy_out);
+/* ParallelTemperingAutocorrelations::calculate_variable_autocorrelation / calculate_spin_product_autocorrelation and
+ * ParallelTemperingBondAutoCorrelations::calculate_bond_autocorrelation for a TemperingContainer
+ * (tempering_container.rs:484-630): parallel_timesteps_sample (:411-453) with a tempering step every replica_swap_freq
+ * sweeps (0 = None = 1), then one autocorrelation per ladder SLOT over the samples taken at that slot.  autocorr_out
+ * [S][T], samples_out [S][T][nvars] in slot order or NULL, energy_out [S] = the reference's energy_acc or NULL.  The
+ * whole ladder must live in this handle (QMCB_ERR_UNSUPPORTED otherwise). */
+int qmcb_pt_variable_autocorrelation(QmcbHandle *h, uint64_t timesteps, uint64_t replica_swap_freq, uint64_t sampling_freq,
+                                     double *autocorr_out, uint8_t *samples_out, double *energy_out);
+int qmcb_pt_spin_product_autocorrelation(QmcbHandle *h, uint64_t timesteps, uint64_t replica_swap_freq, uint64_t sampling_freq,
+                                         uint32_t n_products, const uint32_t *product_offsets, const uint32_t *product_vars,
+                                         double *autocorr_out, uint8_t *samples_out, double *energy_out);
+int qmcb_pt_bond_autocorrelation(QmcbHandle *h, uint64_t timesteps, uint64_t replica_swap_freq, uint64_t sampling_freq,
+                                 double *autocorr_out, uint8_t *samples_out, double *energy_out);
 int qmcb_get_rng_cursors(QmcbHandle *h, uint64_t *cursors /* [R] */);
 int qmcb_set_rng_cursor(QmcbHandle *h, uint32_t r, uint64_t cursor);
 int qmcb_get_rng_keys(QmcbHandle *h, uint64_t *keys /* [R] */);

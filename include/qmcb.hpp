@@ -381,8 +381,38 @@ public:
         check(qmcb_pt_total_swaps(g_.raw(), &s));
         return s;
     }
+    // ParallelTemperingAutocorrelations / ParallelTemperingBondAutoCorrelations (:484-630): one autocorrelation per slot
+    std::vector<std::vector<double>> calculate_variable_autocorrelation(size_t timesteps, size_t replica_swap_freq = 1, size_t sampling_freq = 1) {
+        const size_t S = n_betas_ * n_chains_, T = timesteps / sampling_freq;
+        std::vector<double> ac(S * T);
+        check(qmcb_pt_variable_autocorrelation(g_.raw(), timesteps, replica_swap_freq, sampling_freq, ac.data(), nullptr, nullptr));
+        return split(ac, S, T);
+    }
+    std::vector<std::vector<double>> calculate_spin_product_autocorrelation(size_t timesteps, size_t replica_swap_freq,
+                                                                            const std::vector<std::vector<uint32_t>> &var_products, size_t sampling_freq = 1) {
+        const size_t S = n_betas_ * n_chains_, T = timesteps / sampling_freq;
+        std::vector<uint32_t> off(1, 0), flat;
+        for (auto &p : var_products) flat.insert(flat.end(), p.begin(), p.end()), off.push_back((uint32_t)flat.size());
+        std::vector<double> ac(S * T);
+        check(qmcb_pt_spin_product_autocorrelation(g_.raw(), timesteps, replica_swap_freq, sampling_freq, (uint32_t)var_products.size(), off.data(),
+                                                   flat.data(), ac.data(), nullptr, nullptr));
+        return split(ac, S, T);
+    }
+    std::vector<std::vector<double>> calculate_bond_autocorrelation(size_t timesteps, size_t replica_swap_freq = 1, size_t sampling_freq = 1) {
+        const size_t S = n_betas_ * n_chains_, T = timesteps / sampling_freq;
+        std::vector<double> ac(S * T);
+        check(qmcb_pt_bond_autocorrelation(g_.raw(), timesteps, replica_swap_freq, sampling_freq, ac.data(), nullptr, nullptr));
+        return split(ac, S, T);
+    }
     bool verify() { return g_.verify(); }
     QmcIsingGraph &graph() { return g_; }
+
+private:
+    static std::vector<std::vector<double>> split(const std::vector<double> &flat, size_t S, size_t T) {
+        std::vector<std::vector<double>> out(S);
+        for (size_t s = 0; s < S; s++) out[s].assign(flat.begin() + s * T, flat.begin() + (s + 1) * T);
+        return out;
+    }
 };
 
 class GraphState {

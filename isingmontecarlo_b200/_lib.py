@@ -66,6 +66,9 @@ SIGNATURES = {
     "qmcb_loop_update": [vp],
     "qmcb_set_do_loop_updates": [vp, C.c_int],
     "qmcb_get_do_loop_updates": [vp, C.POINTER(C.c_int)],
+    "qmcb_pt_variable_autocorrelation": [vp, C.c_uint64, C.c_uint64, C.c_uint64, f64p, u8p, f64p],
+    "qmcb_pt_spin_product_autocorrelation": [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, u32p, u32p, f64p, u8p, f64p],
+    "qmcb_pt_bond_autocorrelation": [vp, C.c_uint64, C.c_uint64, C.c_uint64, f64p, u8p, f64p],
     "qmcb_set_run_rvb": [vp, C.c_int],
     "qmcb_get_run_rvb": [vp, C.POINTER(C.c_int)],
     "qmcb_single_rvb_sweep": [vp, C.c_int64, u64p, u64p],

@@ -938,7 +938,7 @@ extern "C" int qmcb_timesteps(QmcbHandle *h, uint64_t t, uint64_t freq, double *
 // normalisation makes the sign convention irrelevant), of which calculate_bond_autocorrelation (:80-97, value_for_bond
 // qmc_ising.rs:988-997) is the instance "one product per edge".  Work buffers belong to the handle and are reused.
 static int autocorrelation_impl(QmcbHandle *h, uint64_t t, uint64_t freq, uint32_t n_products, const uint32_t *offsets, const uint32_t *vars,
-                                double *autocorr_out, uint8_t *samples_out, double *energy_out) {
+                                double *autocorr_out, uint8_t *samples_out, double *energy_out, uint64_t pt_swap_freq = 0) {
     if (!autocorr_out) return fail(QMCB_ERR_BAD_ARG, "null argument");
     if (freq == 0) freq = 1;
     const SseDev &D = h->D;
@@ -953,8 +953,37 @@ static int autocorrelation_impl(QmcbHandle *h, uint64_t t, uint64_t freq, uint32
         for (uint32_t i = 0; i < nv_total; i++)
             if (vars[i] >= D.N) return fail(QMCB_ERR_BAD_ARG, "product variable out of range");
     }
-    int rc = timesteps_impl(h, t, freq, energy_out, samples_out, true);
-    if (rc) return rc;
+    int rc;
+    if (pt_swap_freq) {
+        // ParallelTemperingAutocorrelations::calculate_autocorrelation (tempering_container.rs:580-606): the series of SLOT s
+        // are the samples parallel_timesteps_sample (:411-453) collected for the graph at ladder position s, whichever
+        // configuration sat there; the series are put in slot order and handed to the same device kernels
+        const uint32_t R = D.R, S = h->pt_S;
+        if (!h->pt_on) return fail(QMCB_ERR_BAD_ARG, "tempering not configured");
+        if (!(h->P.cfg_begin == 0 && R == S))
+            return fail(QMCB_ERR_UNSUPPORTED, "tempering autocorrelations need the whole ladder in one handle (a slot's series would be spread over ranks)");
+        std::vector<uint8_t> smp((size_t)R * T * D.N), by_slot((size_t)R * T * D.N);
+        std::vector<uint32_t> sslots((size_t)R * T);
+        std::vector<double> eacc(S);
+        if ((rc = qmcb_pt_timesteps_sample(h, t, pt_swap_freq, freq, eacc.data(), smp.data(), sslots.data()))) return rc;
+        for (uint32_t r = 0; r < R; r++)
+            for (uint64_t k = 0; k < T; k++)
+                memcpy(&by_slot[((size_t)sslots[(size_t)r * T + k] * T + k) * D.N], &smp[((size_t)r * T + k) * D.N], D.N);
+        if (by_slot.size() > h->samples_cap) {
+            if (h->samples_dev) h->pool.release(h->samples_dev);
+            h->samples_dev = nullptr, h->samples_cap = 0;
+            cudaError_t ea = h->pool.alloc(&h->samples_dev, by_slot.size());
+            if (ea != cudaSuccess) return fail_cuda(ea, "sample buffer", __FILE__, __LINE__);
+            h->samples_cap = by_slot.size();
+        }
+        CUDA_TRY(cudaMemcpyAsync(h->samples_dev, by_slot.data(), by_slot.size(), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));  // by_slot goes out of scope
+        if (samples_out) memcpy(samples_out, by_slot.data(), by_slot.size());
+        if (energy_out)
+            for (uint32_t sl = 0; sl < S; sl++) energy_out[sl] = eacc[sl];  // energy_acc of parallel_timesteps_sample: sum of te * t, as the reference leaves it
+    } else if ((rc = timesteps_impl(h, t, freq, energy_out, samples_out, true))) {
+        return rc;
+    }
     const uint32_t K = n_products ? n_products : D.N;  // number of series per replica
     const uint32_t Tw = (uint32_t)((T + 31) / 32);
     const size_t need_bits = (size_t)D.R * K * (2 * Tw + 1), need_ones = (size_t)D.R * K, need_out = (size_t)D.R * T;
@@ -1009,6 +1038,34 @@ extern "C" int qmcb_bond_autocorrelation(QmcbHandle *h, uint64_t t, uint64_t fre
     for (uint32_t b = 0; b < E; b++) off[b] = 2 * b, vars[2 * b] = h->va_h[b], vars[2 * b + 1] = h->vb_h[b];
     off[E] = 2 * E;
     return autocorrelation_impl(h, t, freq, E, off.data(), vars.data(), autocorr_out, samples_out, energy_out);
+}
+
+// ParallelTemperingAutocorrelations / ParallelTemperingBondAutoCorrelations for TemperingContainer
+// (tempering_container.rs:484-630): one autocorrelation per ladder slot, autocorr_out [S][T]
+extern "C" int qmcb_pt_variable_autocorrelation(QmcbHandle *h, uint64_t timesteps, uint64_t replica_swap_freq, uint64_t sampling_freq,
+                                                double *autocorr_out, uint8_t *samples_out, double *energy_out) {
+    CHECK_H(h);
+    if (replica_swap_freq == 0) replica_swap_freq = 1;  // Option::unwrap_or(1) :590
+    return autocorrelation_impl(h, timesteps, sampling_freq, 0, nullptr, nullptr, autocorr_out, samples_out, energy_out, replica_swap_freq);
+}
+extern "C" int qmcb_pt_spin_product_autocorrelation(QmcbHandle *h, uint64_t timesteps, uint64_t replica_swap_freq, uint64_t sampling_freq,
+                                                    uint32_t n_products, const uint32_t *product_offsets, const uint32_t *product_vars,
+                                                    double *autocorr_out, uint8_t *samples_out, double *energy_out) {
+    CHECK_H(h);
+    if (n_products == 0) return fail(QMCB_ERR_BAD_ARG, "no products given");
+    if (replica_swap_freq == 0) replica_swap_freq = 1;
+    return autocorrelation_impl(h, timesteps, sampling_freq, n_products, product_offsets, product_vars, autocorr_out, samples_out, energy_out, replica_swap_freq);
+}
+extern "C" int qmcb_pt_bond_autocorrelation(QmcbHandle *h, uint64_t timesteps, uint64_t replica_swap_freq, uint64_t sampling_freq,
+                                            double *autocorr_out, uint8_t *samples_out, double *energy_out) {
+    CHECK_H(h);
+    const uint32_t E = h->D.E;
+    if (E == 0) return fail(QMCB_ERR_BAD_ARG, "lattice without edges");
+    if (replica_swap_freq == 0) replica_swap_freq = 1;
+    std::vector<uint32_t> off(E + 1), vars(2 * (size_t)E);
+    for (uint32_t b = 0; b < E; b++) off[b] = 2 * b, vars[2 * b] = h->va_h[b], vars[2 * b + 1] = h->vb_h[b];
+    off[E] = 2 * E;
+    return autocorrelation_impl(h, timesteps, sampling_freq, E, off.data(), vars.data(), autocorr_out, samples_out, energy_out, replica_swap_freq);
 }
 
 extern "C" int qmcb_enqueue_sweeps(QmcbHandle *h, uint64_t t) {

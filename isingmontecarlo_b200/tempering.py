@@ -226,5 +226,30 @@ class TemperingContainer:
             energy_acc = tacc.cpu().numpy()
         return states, energy_acc
 
+    # -- ParallelTemperingAutocorrelations / ParallelTemperingBondAutoCorrelations (tempering_container.rs:484-630) --------
+    def _autocorr(self, fn, timesteps, replica_swap_freq, sampling_freq, extra=(), return_samples=False):
+        T = int(timesteps) // int(sampling_freq or 1)
+        ac = np.zeros((self.S, T), dtype=np.float64)
+        smp = np.zeros((self.S, T, self.graph.nvars), dtype=np.uint8) if return_samples else None
+        check(fn(self.graph._h, int(timesteps), int(replica_swap_freq or 1), int(sampling_freq or 1), *extra, ptr(ac, C.c_double),
+                 ptr(smp, C.c_uint8) if return_samples else None, None))
+        return (ac, smp) if return_samples else ac
+
+    def calculate_variable_autocorrelation(self, timesteps, replica_swap_freq=None, sampling_freq=None, return_samples=False):
+        """:536-554: one autocorrelation per ladder slot, [S][T]"""
+        return self._autocorr(self.graph._L.qmcb_pt_variable_autocorrelation, timesteps, replica_swap_freq, sampling_freq, (), return_samples)
+
+    def calculate_spin_product_autocorrelation(self, timesteps, replica_swap_freq, var_products, sampling_freq=None, return_samples=False):
+        """:556-578: series = products of the spins listed in each entry of var_products"""
+        off = np.zeros(len(var_products) + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(p) for p in var_products])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.uint32) for p in var_products]) if len(var_products) else np.zeros(0, np.uint32))
+        return self._autocorr(self.graph._L.qmcb_pt_spin_product_autocorrelation, timesteps, replica_swap_freq, sampling_freq,
+                              (len(var_products), ptr(off, C.c_uint32), ptr(flat, C.c_uint32)), return_samples)
+
+    def calculate_bond_autocorrelation(self, timesteps, replica_swap_freq=None, sampling_freq=None, return_samples=False):
+        """:608-630: one series per edge (value_for_bond, qmc_ising.rs:988-997)"""
+        return self._autocorr(self.graph._L.qmcb_pt_bond_autocorrelation, timesteps, replica_swap_freq, sampling_freq, (), return_samples)
+
     def verify(self):
         return self.graph.verify()

@@ -341,6 +341,40 @@ impl TemperingContainer {
         }
         Ok(out)
     }
+    /// ParallelTemperingAutocorrelations::calculate_variable_autocorrelation (tempering_container.rs:536-554): one
+    /// autocorrelation per ladder slot
+    pub fn calculate_variable_autocorrelation(&mut self, timesteps: usize, replica_swap_freq: Option<usize>, sampling_freq: Option<usize>)
+                                              -> Result<Vec<Vec<f64>>, String> {
+        let (swap, freq) = (replica_swap_freq.unwrap_or(1), sampling_freq.unwrap_or(1));
+        let t = timesteps / freq;
+        let mut ac = vec![0.0; self.n_slots * t];
+        check(unsafe { sys::qmcb_pt_variable_autocorrelation(self.graph.h, timesteps as u64, swap as u64, freq as u64, ac.as_mut_ptr(),
+                                                             std::ptr::null_mut(), std::ptr::null_mut()) })?;
+        Ok(ac.chunks(t.max(1)).map(|c| c.to_vec()).collect())
+    }
+    /// calculate_spin_product_autocorrelation (:556-578)
+    pub fn calculate_spin_product_autocorrelation(&mut self, timesteps: usize, replica_swap_freq: Option<usize>, var_products: &[&[usize]],
+                                                  sampling_freq: Option<usize>) -> Result<Vec<Vec<f64>>, String> {
+        let (swap, freq) = (replica_swap_freq.unwrap_or(1), sampling_freq.unwrap_or(1));
+        let t = timesteps / freq;
+        let mut off = vec![0u32];
+        let mut flat: Vec<u32> = Vec::new();
+        for p in var_products { flat.extend(p.iter().map(|v| *v as u32)); off.push(flat.len() as u32); }
+        let mut ac = vec![0.0; self.n_slots * t];
+        check(unsafe { sys::qmcb_pt_spin_product_autocorrelation(self.graph.h, timesteps as u64, swap as u64, freq as u64, var_products.len() as u32,
+                                                                 off.as_ptr(), flat.as_ptr(), ac.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) })?;
+        Ok(ac.chunks(t.max(1)).map(|c| c.to_vec()).collect())
+    }
+    /// ParallelTemperingBondAutoCorrelations::calculate_bond_autocorrelation (:608-630)
+    pub fn calculate_bond_autocorrelation(&mut self, timesteps: usize, replica_swap_freq: Option<usize>, sampling_freq: Option<usize>)
+                                          -> Result<Vec<Vec<f64>>, String> {
+        let (swap, freq) = (replica_swap_freq.unwrap_or(1), sampling_freq.unwrap_or(1));
+        let t = timesteps / freq;
+        let mut ac = vec![0.0; self.n_slots * t];
+        check(unsafe { sys::qmcb_pt_bond_autocorrelation(self.graph.h, timesteps as u64, swap as u64, freq as u64, ac.as_mut_ptr(),
+                                                         std::ptr::null_mut(), std::ptr::null_mut()) })?;
+        Ok(ac.chunks(t.max(1)).map(|c| c.to_vec()).collect())
+    }
     /// get_total_swaps (tempering_container.rs:231-233)
     pub fn get_total_swaps(&mut self) -> Result<u64, String> {
         let mut s = 0u64;

@@ -3,6 +3,7 @@
 //   examples/small_qmc.rs               (4-site ring, 1000 steps)
 //   tests/convert_test.rs:5-7 lattice   (3-ring, 10 steps)
 // Batched: the 16 seeds of a reference test are the 16 replicas of one handle.  Both cluster orders run.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -104,6 +105,12 @@ int main() {
         auto se = tc.timesteps_sample(12, 2, 3);  // tempering_container.rs:166-208
         ASSERT(se.size() == 12);
         for (auto &slot : se) ASSERT(slot.first.size() == 4 && slot.first[0].size() == 16 && slot.second == slot.second);
+        // ParallelTemperingAutocorrelations (:484-630): one autocorrelation per slot, lag 0 is 1
+        auto ac = tc.calculate_variable_autocorrelation(64, 2, 2);
+        ASSERT(ac.size() == 12 && ac[0].size() == 32);
+        for (auto &a : ac) ASSERT(std::fabs(a[0] - 1.0) < 1e-12);
+        auto bc = tc.calculate_bond_autocorrelation(64, 2, 2);
+        ASSERT(bc.size() == 12 && bc[0].size() == 32 && tc.verify());
     }
     {  // serde round trip (qmc_ising.rs serialize_test): a restored batch continues identically
         auto g = qmcb::DefaultQmcIsingGraph::new_with_rng(two_d_periodic(3), 1.0, 0.3, 9, {21, 22, 23}, nullptr, QMCB_MODE_FAST);
