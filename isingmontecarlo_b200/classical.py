@@ -19,6 +19,7 @@ class GraphState:
         self.nvars = len(bz)
         keys = np.ascontiguousarray(rng_keys, dtype=np.uint64)
         self.R = len(keys)
+        self._edges, self.biases, self._keys = list(edges), bz.copy(), keys.copy()  # what QmcIsingGraph::new_from_graph takes over
         b = np.ascontiguousarray(np.broadcast_to(np.asarray(betas, dtype=np.float64), (self.R,)))
         lat, self._keep = _lattice(edges, 0.0, 0.0, self.nvars)
         st = None
@@ -36,6 +37,12 @@ class GraphState:
     @classmethod
     def new_with_state_and_rng(cls, state, edges, biases, rng_keys, betas, **kw):
         return cls(edges, biases, rng_keys, betas, state=state, **kw)
+
+    def get_edges(self):  # graph.rs: the edge list the graph was built from
+        return self._edges
+
+    def rng_keys(self):
+        return self._keys
 
     def close(self):
         if getattr(self, "_h", None):

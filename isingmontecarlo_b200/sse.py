@@ -303,7 +303,48 @@ class QmcIsingGraph:
         check(self._L.qmcb_get_states(self._h, ptr(out, C.c_uint8)))
         return out
 
-    clone_state = state_ref
+    clone_state = state_ref  # qmc_ising.rs:502-504
+
+    def into_vec(self):
+        """qmc_ising.rs:507-509 / qmc_runner.rs:284-286: the p = 0 states; the batch is released"""
+        st = self.state_ref().astype(bool)
+        self.close()
+        return st
+
+    def get_transverse_field(self):  # qmc_ising.rs:522-524
+        return self.transverse
+
+    def get_longitudinal_field(self):  # qmc_ising.rs:527-529
+        return self.longitudinal
+
+    @classmethod
+    def new_from_graph(cls, graph, transverse, longitudinal, cutoff, betas=1.0, mode=MODE_STRICT, device=0):
+        """QmcIsingGraph::new_from_graph / new_qmc_from_graph (qmc_ising.rs:68-75, 151-166): the edges, the streams and the
+        current states of a classical `GraphState` batch; its biases must be zero (the reference asserts it)."""
+        if np.any(np.asarray(graph.biases) != 0.0):
+            raise _lib.QmcbError(_lib.ERR_BAD_ARG, "new_from_graph: the classical graph has biases (qmc_ising.rs:157)")
+        return cls(graph.get_edges(), transverse, longitudinal, cutoff, graph.rng_keys(), betas, state=graph.state_ref(), mode=mode, device=device)
+
+    def print_debug(self, r=0, file=None):
+        """qmc_ising.rs:489-494 -> debug_print_diagonal (diagonal.rs:193-234): the world lines of replica r, one row per slot"""
+        import sys
+
+        out = file or sys.stdout
+        n = self.nvars
+        E = len(self._edges)
+        print("=" * n, file=out)
+        print("".join("1" if b else "0" for b in self.state_ref()[r]), file=out)
+        for p, w in enumerate(self.dump_ops(r)):
+            if int(w) == _lib.OP_EMPTY:
+                print("|" * n + f"\tp={p}", file=out)
+                continue
+            b, outs = int(w) & 0xFFFFFF, (int(w) >> 26) & 3
+            vs = list(self._edges[b][0]) if b < E else [b - E if b < E + n else b - E - n]
+            row, last = "", 0
+            for var, bit in sorted((v, (outs >> k) & 1) for k, v in enumerate(vs)):
+                row += "|" * (var - last) + str(bit)
+                last = var + 1
+            print(row + "|" * (n - last) + f"\tp={p}\t{b}: {vs}", file=out)
 
     def set_state(self, r, state):
         st = np.ascontiguousarray(state, dtype=np.uint8)
@@ -483,6 +524,19 @@ class Qmc(QmcIsingGraph):
         self.do_loop_updates = bool(flag)
         if self._h is not None:
             check(self._L.qmcb_set_do_loop_updates(self._h, int(bool(flag))))
+
+    def set_do_heatbath(self, do_heatbath):  # qmc_runner.rs:258-260: heat-bath diagonal updates over the interactions' weights
+        self._ensure()
+        self.set_enable_heatbath(do_heatbath)
+
+    def should_do_heatbath(self):  # :263-265
+        return bool(self._h) and self.get_enable_heatbath()
+
+    def diagonal_update(self, beta):
+        """Qmc::diagonal_update (qmc_runner.rs:159-202): one diagonal update of every replica and the cutoff growth (:195)"""
+        self._ensure()
+        self._set_beta(beta)
+        check(self._L.qmcb_single_diagonal_step(self._h))
 
     def should_do_loop_update(self):  # :273-275
         return self.do_loop_updates

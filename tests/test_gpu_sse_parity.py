@@ -363,3 +363,32 @@ def test_generic_qmc_interactions_bit_exact(mode):
     lp = Qmc(2, [1], 1.0)  # loop updates are offered (tests/test_gpu_loop_update.py): the flag is Qmc::set_do_loop_updates
     lp.set_do_loop_updates(True)
     assert lp.should_do_loop_update()
+
+
+def test_small_accessors_and_new_from_graph(capsys):
+    # get_transverse_field / get_longitudinal_field / clone_state / into_vec (qmc_ising.rs:497-529), print_debug (:489-494,
+    # diagonal.rs:193-234), new_from_graph (:151-166), Qmc::diagonal_update / set_do_heatbath (qmc_runner.rs:159-202, 258-265)
+    from isingmontecarlo_b200.classical import GraphState
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.small_qmc_ring()
+    c = GraphState(edges, np.zeros(4), [11, 12], 0.5)
+    c.sweeps(3)
+    g = QmcIsingGraph.new_from_graph(c, 1.0, 0.25, 4, betas=1.0, mode=MODE_FAST)
+    assert np.array_equal(g.state_ref(), c.state_ref()) and list(g.rng_keys()) == [11, 12]
+    assert g.get_transverse_field() == 1.0 and g.get_longitudinal_field() == 0.25 and g.get_edges() == list(edges)
+    g.timesteps(10, 1.0)
+    g.print_debug(1)
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[0] == "====" and lines[1] == "".join(str(int(b)) for b in g.state_ref()[1])
+    assert len(lines) == 2 + int(g.get_cutoff()[1]) and sum("\t" in ln and ":" in ln for ln in lines) == int(g.get_n()[1])
+    st = g.clone_state()
+    assert np.array_equal(g.into_vec(), st.astype(bool))
+    with pytest.raises(QmcbError):  # biases must vanish (qmc_ising.rs:157)
+        QmcIsingGraph.new_from_graph(GraphState(edges, np.ones(4), [1], 0.5), 1.0, 0.0, 4)
+    q = QmcIsingGraph(edges, 1.0, 0.0, 4, [5, 6], 1.0, mode=MODE_FAST).into_qmc()
+    q.set_do_heatbath(True)
+    assert q.should_do_heatbath()
+    q.diagonal_update(1.0)
+    q.timesteps(5, 1.0)
+    assert q.verify()
