@@ -189,18 +189,30 @@ static int alloc_rvb_ws(QmcbHandle *h) {
             list[start[h->va_h[b]] + fill[h->va_h[b]]++] = b;
             list[start[h->vb_h[b]] + fill[h->vb_h[b]]++] = b;
         }
-        uint32_t *sd, *ld;
-        CUDA_TRY(h->pool.alloc(&sd, start.size()));
-        CUDA_TRY(h->pool.alloc(&ld, list.size()));
-        CUDA_TRY(cudaMemcpy(sd, start.data(), sizeof(uint32_t) * start.size(), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(ld, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice));
+        uint32_t *sd = nullptr, *ld = nullptr;
+        cudaError_t e0 = h->pool.alloc(&sd, start.size());
+        if (e0 == cudaSuccess) e0 = h->pool.alloc(&ld, list.size());
+        if (e0 == cudaSuccess) e0 = cudaMemcpy(sd, start.data(), sizeof(uint32_t) * start.size(), cudaMemcpyHostToDevice);
+        if (e0 == cudaSuccess) e0 = cudaMemcpy(ld, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice);
+        if (e0 != cudaSuccess) {
+            h->pool.release(sd), h->pool.release(ld);
+            return fail_cuda(e0, "RVB bond table", __FILE__, __LINE__);
+        }
         W.vb_start = sd, W.vb_list = ld;
-        CUDA_TRY(h->pool.alloc(&W.succ, D.R));
-        CUDA_TRY(h->pool.alloc(&W.count, D.R));
-        CUDA_TRY(h->pool.alloc(&h->rvb_succ_last, D.R));
-        CUDA_TRY(cudaMemset(W.succ, 0, sizeof(unsigned long long) * D.R));
-        CUDA_TRY(cudaMemset(W.count, 0, sizeof(unsigned long long) * D.R));
-        CUDA_TRY(cudaMemset(h->rvb_succ_last, 0, sizeof(unsigned long long) * D.R));
+    }
+    if (!h->rvb_succ_last) {  // the counters: all three or none
+        unsigned long long *a = nullptr, *b = nullptr, *c = nullptr;
+        cudaError_t e0 = h->pool.alloc(&a, D.R);
+        if (e0 == cudaSuccess) e0 = h->pool.alloc(&b, D.R);
+        if (e0 == cudaSuccess) e0 = h->pool.alloc(&c, D.R);
+        if (e0 == cudaSuccess) e0 = cudaMemset(a, 0, sizeof(unsigned long long) * D.R);
+        if (e0 == cudaSuccess) e0 = cudaMemset(b, 0, sizeof(unsigned long long) * D.R);
+        if (e0 == cudaSuccess) e0 = cudaMemset(c, 0, sizeof(unsigned long long) * D.R);
+        if (e0 != cudaSuccess) {
+            h->pool.release(a), h->pool.release(b), h->pool.release(c);
+            return fail_cuda(e0, "RVB counters", __FILE__, __LINE__);
+        }
+        W.succ = a, W.count = b, h->rvb_succ_last = c;
     }
     W.stride32 = rvb_stride32(D), W.stride64 = rvb_stride64(D), W.stride8 = rvb_stride8(D);
     cudaError_t e = h->pool.alloc(&W.u32, (size_t)D.R * W.stride32);
