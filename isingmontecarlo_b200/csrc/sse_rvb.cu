@@ -17,6 +17,18 @@
 // get_random returns.  The move is off by default in the reference (qmc_ising.rs:122) and here; it is not a tuned path.
 #include "sse.cuh"
 
+// -DQMCB_RVB_CHECK: every write with a computed index is checked against the size of its array (compute-sanitizer is not
+// available on the pool this was developed on); a violation ends up in the handle's status as DEV_ERR_STACK
+#ifdef QMCB_RVB_CHECK
+__device__ int g_rvb_check_fail = 0;
+#define RVB_CHK(cond)                                \
+    do {                                             \
+        if (!(cond)) atomicOr(&g_rvb_check_fail, 1); \
+    } while (0)
+#else
+#define RVB_CHK(cond) ((void)0)
+#endif
+
 namespace {
 
 // BondContainer<T> (util/bondcontainer.rs): T = bond (kp == nullptr) or VarPos{v, p} (rvb.rs:957-965, index p.unwrap_or(v))
@@ -34,6 +46,7 @@ __device__ __forceinline__ void bc_clear(BC &c) {  // :133-142
 }
 __device__ __forceinline__ void bc_insert(BC &c, uint32_t v, uint32_t p, double w) {  // :110-130
     const uint32_t t = bc_idx(v, p);
+    RVB_CHK(t < c.maplen);
     const uint32_t at = c.map[t];
     if (at != NONE32) {
         const double old = c.kw[at];
@@ -41,6 +54,7 @@ __device__ __forceinline__ void bc_insert(BC &c, uint32_t v, uint32_t p, double 
         c.total = c.total + (w - old);
         if (c.total < 0.0) c.total = 0.0;  // correct_total_weight :76-87
     } else {
+        RVB_CHK(c.len < c.maplen);  // the key arrays are as long as the map
         c.map[t] = c.len;
         c.kv[c.len] = v, c.kw[c.len] = w;
         if (c.kp) c.kp[c.len] = p;
@@ -242,6 +256,7 @@ struct Ctx {
         const uint32_t len = ln_len[v];
         if (len >= ln_cap[v]) return false;
         const uint32_t i = lower_bound(v, p);
+        RVB_CHK(ln_start[v] + len < lines_total);
         for (uint32_t k = len; k > i; k--) ln[k] = ln[k - 1];
         ln[i] = p;
         ln_len[v] = len + 1;
@@ -289,6 +304,7 @@ struct Ctx {
         if (i == NONE32) return false;
         v = bd.kv[i], p = bd.kp ? bd.kp[i] : NONE32;
         const uint32_t idx = bc_idx(v, p);
+        RVB_CHK(npopped_pos < 80 && npopped_nopos < 80 && idx < (pick_flips ? fl.maplen : nf.maplen));
         if (pick_flips) pos_popped[idx] = 1, popped_idx[npopped_pos++] = idx;
         else nopos_popped[idx] = 1, popped_idx2[npopped_nopos++] = idx;
         bc_remove(bd, v, p);
@@ -323,6 +339,7 @@ struct Ctx {
         while (cluster_size > 0 && !(fl.len == 0 && nf.len == 0)) {
             uint32_t v, flip;
             if (!pop_index(v, flip)) return;
+            RVB_CHK(ncl < 72);
             cl_vars[ncl] = v, cl_flips[ncl] = flip, ncl++;
             const uint32_t vs = var_starts[v], vl = var_lengths[v];
             if (flip != NONE32) {
@@ -482,6 +499,7 @@ struct Ctx {
         }
         for (uint32_t t = 0; t < ntog; t++) {
             const uint32_t p = toggles[t];
+            RVB_CHK(nj < 151 && nc < 151);
             if (count == 0) jump_to[nj++] = p;
             Op o;
             if (!decode(p, o)) {
@@ -674,8 +692,14 @@ __global__ void __launch_bounds__(128, QMCB_RVB_MINB) k_sse_rvb(SseDev D, RvbDev
             const int kind = bond_kind(D, b);
             uint32_t v0, v1;
             bond_vars(D, b, kind, v0, v1);
-            lines[ln_start[v0] + atomicAdd(ln_len + v0, 1u)] = p;
-            if (kind == KIND_BOND) lines[ln_start[v1] + atomicAdd(ln_len + v1, 1u)] = p;
+            const uint32_t i0 = atomicAdd(ln_len + v0, 1u);
+            RVB_CHK(i0 < ln_cap[v0] && ln_start[v0] + i0 < rvb_lines_total(D));
+            lines[ln_start[v0] + i0] = p;
+            if (kind == KIND_BOND) {
+                const uint32_t i1 = atomicAdd(ln_len + v1, 1u);
+                RVB_CHK(i1 < ln_cap[v1] && ln_start[v1] + i1 < rvb_lines_total(D));
+                lines[ln_start[v1] + i1] = p;
+            }
         }
         __syncwarp();  // steps do not interleave: a line is out of order only inside one step's entries
     }
@@ -690,7 +714,10 @@ __global__ void __launch_bounds__(128, QMCB_RVB_MINB) k_sse_rvb(SseDev D, RvbDev
             ln[j] = x;
         }
         for (uint32_t i = 0; i < len; i++)
-            if (bond_kind(D, op_bond(opw[ln[i]])) == KIND_SITE) constant_ps[k++] = ln[i];
+            if (bond_kind(D, op_bond(opw[ln[i]])) == KIND_SITE) {
+                RVB_CHK(k < var_starts[v + 1] && k < cap);
+                constant_ps[k++] = ln[i];
+            }
     }
     __syncwarp();
     if (lane != 0) return;
@@ -739,6 +766,7 @@ __global__ void __launch_bounds__(128, QMCB_RVB_MINB) k_sse_rvb(SseDev D, RvbDev
         if (C.err) break;
         // dissolve_into (:987-1007) and the sorted, deduplicated sub-variables (:168-180)
         auto add = [&](uint32_t w) {
+            RVB_CHK(w < N && C.nsub < N + (mark[w] ? 1u : 0u));
             if (!mark[w]) mark[w] = 1, subvars[C.nsub++] = w;
         };
         for (uint32_t i = 0; i < C.ncl; i++) add(C.cl_vars[i]);
@@ -757,6 +785,7 @@ __global__ void __launch_bounds__(128, QMCB_RVB_MINB) k_sse_rvb(SseDev D, RvbDev
             const uint32_t cv = C.cl_vars[i], s = v2s[cv], fi = C.cl_flips[i];
             if (fi != NONE32) {
                 const uint32_t vstart = var_starts[cv], fi_rel = fi - vstart;
+                RVB_CHK(C.ntog + 2 <= 150 && s < C.nsub && fi < ncp);
                 if (fi_rel + 1 >= var_lengths[cv]) {
                     cstate[s] = 1;
                     C.toggles[C.ntog++] = constant_ps[fi], C.toggles[C.ntog++] = constant_ps[vstart];
@@ -798,6 +827,9 @@ __global__ void __launch_bounds__(128, QMCB_RVB_MINB) k_sse_rvb(SseDev D, RvbDev
     }
     D.cursor[r] = C.cur;
     if (C.err) atomicOr(D.status, C.err);
+#ifdef QMCB_RVB_CHECK
+    if (g_rvb_check_fail) atomicOr(D.status, DEV_ERR_STACK);
+#endif
     if (succ_out) succ_out[r] = num_succ;
     if (target != 0) W.succ[r] += num_succ, W.count[r] += updates;
 }
