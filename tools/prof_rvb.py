@@ -1,5 +1,6 @@
 """Cost of the RVB update (sse_rvb.cu) next to the plain sweep: triangular lattice L x L, J = 1, Gamma = 1, R replicas.
-usage: python tools/prof_rvb.py [L] [beta] [R] [sweeps]"""
+usage: [PROF_H=h] python tools/prof_rvb.py [L] [beta] [R] [sweeps]"""
+import os
 import sys
 import time
 
@@ -14,7 +15,8 @@ beta = float(sys.argv[2]) if len(sys.argv) > 2 else 4.0
 R = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 sweeps = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 edges = lattices.triangular_periodic(L, 1.0)
-g = QmcIsingGraph(edges, 1.0, 0.0, L * L, 0xB0B0000 + np.arange(R, dtype=np.uint64), beta, mode=MODE_COUNTER)
+h = float(os.environ.get("PROF_H", "0"))
+g = QmcIsingGraph(edges, 1.0, h, L * L, 0xB0B0000 + np.arange(R, dtype=np.uint64), beta, mode=MODE_COUNTER)
 g.timesteps(60, beta)
 for rvb in (False, True):
     g.set_run_rvb(rvb)
