@@ -164,6 +164,18 @@ public:
         }
         return true;
     }
+    // get_transverse_field / get_longitudinal_field / clone_state (qmc_ising.rs:502-529)
+    double get_transverse_field() const {
+        double t = 0, l = 0;
+        check(qmcb_get_fields(h_, &t, &l));
+        return t;
+    }
+    double get_longitudinal_field() const {
+        double t = 0, l = 0;
+        check(qmcb_get_fields(h_, &t, &l));
+        return l;
+    }
+    std::vector<std::vector<bool>> clone_state() { return state_ref(); }
     void set_mode(int mode) { check(qmcb_set_mode(h_, mode)); }
     void set_enable_heatbath(bool enable) { check(qmcb_set_enable_heatbath(h_, enable ? 1 : 0)); }  // qmc_ising.rs:444-486
     // RVB update (rvb.rs:60-291): set_run_rvb qmc_ising.rs:434-441, single_rvb_sweep :322-420 (successes per replica,

@@ -86,6 +86,14 @@ impl BatchedQmcIsingGraph {
     pub fn num_replicas(&self) -> usize { self.replicas }
     pub fn get_nvars(&self) -> usize { self.nvars }
     pub fn get_offset(&self) -> f64 { self.offset }
+    /// get_transverse_field / get_longitudinal_field (qmc_ising.rs:522-529)
+    pub fn get_fields(&self) -> Result<(f64, f64), String> {
+        let (mut t, mut l) = (0f64, 0f64);
+        check(unsafe { sys::qmcb_get_fields(self.h, &mut t, &mut l) })?;
+        Ok((t, l))
+    }
+    pub fn get_transverse_field(&self) -> Result<f64, String> { Ok(self.get_fields()?.0) }
+    pub fn get_longitudinal_field(&self) -> Result<f64, String> { Ok(self.get_fields()?.1) }
     pub fn set_mode(&mut self, mode: Mode) -> Result<(), String> { check(unsafe { sys::qmcb_set_mode(self.h, mode as i32) }) }
     pub fn set_betas(&mut self, betas: &[f64]) -> Result<(), String> {
         assert_eq!(betas.len(), self.replicas);
