@@ -183,3 +183,25 @@ def test_rvb_energy_on_a_frustrated_torus_matches_exact_diagonalisation():
     assert (g.rvb_success_rate() > 0.1).all()
     mean, err = e.mean(), e.std(ddof=1) / np.sqrt(R)
     assert abs(mean - exact["E"]) < 3.0 * err + 1e-9, (mean, err, exact["E"])
+
+
+@pytest.mark.parametrize("mode", [MODE_STRICT, MODE_COUNTER])
+def test_rvb_with_per_replica_hamiltonians(mode):
+    # one batch, three Hamiltonians (couplings of the same signs, different magnitudes, own fields): the RVB weights
+    # (bond_mag, the diagonal edge weights) are those of the replica's own row, as for one reference graph per Hamiltonian
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+
+    edges = lattices.two_unit_cell()
+    scales, gammas, fields = [1.0, 1.5, 0.6], [1.0, 0.8, 1.3], [0.0, 0.0, 0.0]
+    keys = [0x4A770000 + r for r in range(3)]
+    g = QmcIsingGraph(edges, 1.0, 0.0, 8, keys, 1.5, mode=mode)
+    g.set_hamiltonians([[j * s for _, j in edges] for s in scales], gammas, fields, [0, 1, 2])
+    g.set_run_rvb(True)
+    refs = [po.SseOracle([(e, j * s) for e, j in edges], gam, h, 8, key=k) for s, gam, h, k in zip(scales, gammas, fields, keys)]
+    for ref in refs:
+        ref.set_run_rvb(True)
+    g.timesteps(30, 1.5)
+    for ref in refs:
+        ref.timesteps(30, 1.5, mode)
+    assert_same(g, refs, "per-replica Hamiltonians")
+    assert g.verify()
