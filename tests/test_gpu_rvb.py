@@ -205,3 +205,18 @@ def test_rvb_with_per_replica_hamiltonians(mode):
         ref.timesteps(30, 1.5, mode)
     assert_same(g, refs, "per-replica Hamiltonians")
     assert g.verify()
+
+
+def test_rvb_through_enqueue_sweeps():
+    # the asynchronous entry point (qmcb_enqueue_sweeps + qmcb_synchronize) takes the same three launches per sweep
+    g, refs = make_pair(lattices.two_d_periodic_mixed(3), 0.1, 0.0, 9, 1.0, MODE_COUNTER, R=4)
+    g.set_run_rvb(True)
+    for ref in refs:
+        ref.set_run_rvb(True)
+    g.enqueue_sweeps(7)
+    g.enqueue_sweeps(5)
+    g.synchronize()
+    for ref in refs:
+        ref.timesteps(12, 1.0, MODE_COUNTER)
+    assert_same(g, refs, "enqueue_sweeps")
+    assert g.verify()
