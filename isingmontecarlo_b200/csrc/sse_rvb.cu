@@ -29,6 +29,14 @@ __device__ int g_rvb_check_fail = 0;
 #define RVB_CHK(cond) ((void)0)
 #endif
 
+// room a world line gets beyond its length (rotations move ops between lines); -DQMCB_RVB_TIGHT_LINES builds lines with
+// one spare entry so that the rebuild path runs constantly (test builds only)
+#ifdef QMCB_RVB_TIGHT_LINES
+#define RVB_LINE_SLACK(len) 1u
+#else
+#define RVB_LINE_SLACK(len) ((len) / 4 + 32)
+#endif
+
 namespace {
 
 // BondContainer<T> (util/bondcontainer.rs): T = bond (kp == nullptr) or VarPos{v, p} (rvb.rs:957-965, index p.unwrap_or(v))
@@ -184,7 +192,7 @@ struct Ctx {
         }
         size_t acc = 0;
         for (uint32_t v = 0; v < N; v++) {
-            ln_start[v] = (uint32_t)acc, ln_cap[v] = ln_len[v] + ln_len[v] / 4 + 32;
+            ln_start[v] = (uint32_t)acc, ln_cap[v] = ln_len[v] + RVB_LINE_SLACK(ln_len[v]);
             acc += ln_cap[v], ln_len[v] = 0;
         }
         if (acc > lines_total) {  // cannot happen: lines_total = 2.5 cap + 32 N + 64 and n <= cap
@@ -676,7 +684,7 @@ __global__ void __launch_bounds__(128, QMCB_RVB_MINB) k_sse_rvb(SseDev D, RvbDev
     if (lane == 0) {
         size_t acc = 0;
         for (uint32_t v = 0; v < N; v++) {
-            ln_start[v] = (uint32_t)acc, ln_cap[v] = ln_len[v] + ln_len[v] / 4 + 32;
+            ln_start[v] = (uint32_t)acc, ln_cap[v] = ln_len[v] + RVB_LINE_SLACK(ln_len[v]);
             acc += ln_cap[v], ln_len[v] = 0;
             var_starts[v] = ncp, ncp += var_lengths[v];
             if (var_lengths[v] == 0) zero_vars[nzero++] = v;

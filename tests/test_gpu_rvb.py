@@ -220,3 +220,30 @@ def test_rvb_through_enqueue_sweeps():
         ref.timesteps(12, 1.0, MODE_COUNTER)
     assert_same(g, refs, "enqueue_sweeps")
     assert g.verify()
+
+
+@pytest.mark.parametrize("h", [0.0, 0.2])
+def test_rvb_parity_on_long_strings_from_a_thermalised_batch(h):
+    # long world lines (triangular L = 12, beta = 6: ~5000 ops, ~70 per variable), clusters that wrap through p = 0, dozens of
+    # rotations per sweep: four replicas of a thermalised 128-replica batch are copied into oracle graphs and both sides run
+    # sweeps with RVB steps
+    from isingmontecarlo_b200.sse import QmcIsingGraph
+    from tests.test_gpu_full_size import same, to_oracle
+
+    edges = lattices.triangular_periodic(12, 1.0)
+    gamma, beta, R = 1.0, 6.0, 128
+    g = QmcIsingGraph(edges, gamma, h, 144, 0x7B1C0000 + np.arange(R, dtype=np.uint64), beta, mode=MODE_COUNTER)
+    g.timesteps(40, beta)
+    g.set_run_rvb(True)
+    g.timesteps(3, beta)
+    picks = (0, 37, 90, R - 1)
+    refs = {r: to_oracle(g, r, edges, gamma, h) for r in picks}
+    for ref in refs.values():
+        ref.set_run_rvb(True)
+    e = g.timesteps(4, beta)
+    for r, ref in refs.items():
+        e_ref = ref.timesteps(4, beta, MODE_COUNTER)
+        assert ref.error == 0 and same(g, r, ref), r
+        assert e[r] == e_ref
+    assert g.verify()
+    assert (g.rvb_success_rate() > 0.05).all()
