@@ -208,3 +208,28 @@ def test_rand_known_answer_fixture_is_what_the_oracle_computes():
     assert kat["gen_f64"] == [float((w >> 11) * 2.0 ** -53).hex() for w in words]
     unit = [(float.fromhex("0x1." + "%013x" % (w >> 12) + "p+0") - 1.0).hex() for w in words]
     assert [v for v, _ in kat["gen_range_f64_unit"]] == unit
+
+
+def test_host_mirrors_offer_the_reference_method_names():
+    """The drop-in boundary seen from the host side: the Python mirrors carry the public method names of the reference's
+    types (static lists, written down from qmc_ising.rs, qmc_stepper.rs, qmc_runner.rs, autocorrelations.rs,
+    tempering_container.rs and classical/graph.rs; the reference tree is not read at test time)."""
+    from isingmontecarlo_b200.classical import GraphState
+    from isingmontecarlo_b200.sse import Qmc, QmcIsingGraph
+    from isingmontecarlo_b200.tempering import TemperingContainer
+
+    ising = """new_with_rng new_from_graph single_diagonal_step single_cluster_step single_rvb_sweep set_run_rvb set_enable_heatbath
+        print_debug clone_state into_vec get_nvars get_edges get_transverse_field get_longitudinal_field get_cutoff set_cutoff
+        get_offset rvb_success_rate into_qmc verify timestep timesteps timesteps_sample timesteps_measure timesteps_sample_iter
+        timesteps_sample_iter_zip get_n state_ref get_bond_count get_energy_for_average_n imaginary_time_fold
+        calculate_variable_autocorrelation calculate_spin_product_autocorrelation calculate_bond_autocorrelation""".split()
+    qmc = """make_interaction make_interaction_and_offset make_diagonal_interaction make_diagonal_interaction_and_offset
+        diagonal_update loop_update set_do_heatbath should_do_heatbath set_do_loop_updates should_do_loop_update
+        should_do_cluster_update get_bonds get_offset increase_cutoff_to clone_state into_vec timestep timesteps""".split()
+    tempering = """timesteps tempering_step timesteps_sample num_graphs get_total_swaps verify calculate_variable_autocorrelation
+        calculate_spin_product_autocorrelation calculate_bond_autocorrelation""".split()
+    classical = """new new_with_state_and_rng do_time_step enable_edge_importance_sampling get_state clone_state state_ref
+        set_state get_energy""".split()
+    for cls, names in ((QmcIsingGraph, ising), (Qmc, qmc), (TemperingContainer, tempering), (GraphState, classical)):
+        missing = [n for n in names if not hasattr(cls, n)]
+        assert not missing, (cls.__name__, missing)
